@@ -1,0 +1,562 @@
+// bmpc_core.cuh — numerical core of the batched linear-MPC solver (fp64), written once against a
+// "team" abstraction so that the same code runs as
+//   * WarpTeam  : one warp per MPC instance (small problems: pendulum, point mass),
+//   * BlockTeam : one CTA per MPC instance (large problems: MIMO nx=8,nu=4,Np=40),
+//   * SeqTeam   : one host thread (tests/hostemu only — index-logic checks without a GPU; never
+//                 linked into the product library).
+//
+// What is computed (reference: /root/reference/pyMPC/mpc.py; math: doc/latex/main.tex:535-671):
+//   K1  condense   Ad^k, block-Toeplitz prediction matrix, H = B'P_X B + P_U, K = H + sigma I + A'RA,
+//                  their inverses, and the dual operators A H^-1, A H^-1 A' used by the polish
+//                  (replaces _compute_QP_matrices_, mpc.py:456-615, + OSQP setup)
+//   K3  prep       per-step linear term g and affine offset cc from (x0, u_-1, xref)
+//                  (replaces _update_QP_matrices_, mpc.py:386-454)
+//   K4  admm       OSQP-form ADMM iterations on the condensed QP with the slack block eliminated in
+//                  closed form (soft box = prox of a squared distance)      (replaces OSQP.solve, mpc.py:369)
+//   K5  polish     primal-dual active-set refinement with KKT verification -> exact minimiser
+//
+// The condensed problem has the SAME minimiser (u-block) as the QP the reference assembles:
+//   variables U (NU = Nc*nu), rows z = A U + cc,  A = [Bcal ; I ; D]  (mc = NX + NU + (Nc+1)*nu rows)
+//   rows [0,NX)      : predicted states x_k, SOFT box [xmin,xmax] with weight eps_feas  (mpc.py:555-559)
+//   rows [NX,NX+NU)  : inputs, hard box [umin,umax]                                     (mpc.py:561-565)
+//   rows [NX+NU,mc)  : the reference's "delta-u" rows, reproduced with its scalar-shift quirk (mpc.py:569-580)
+#pragma once
+#include <math.h>
+
+#ifdef BMPC_HOSTEMU
+#define BMPC_HD inline
+#else
+#define BMPC_HD __device__ __forceinline__
+#endif
+
+struct BmpcDims {
+    int nx, nu, Np, Nc, NX, NU, ND, mc;
+};
+
+// Offsets (in doubles) of every array inside one system block.
+struct BmpcSysOff {
+    // inputs (copied from the host by bmpc_setup)
+    int Ad, Bd, Qx, QxN, Qu, QDu, xmin, xmax, umin, umax, Dumin, Dumax, uref;
+    // derived by the condense kernel
+    int pw, Acal, Bcal, BcalT, PB, H, Hinv, K, Kinv, AHinv, M, Gx0, Gref, GrefFull, g0, lo0, hi0, rho, scal;
+    int total;
+};
+
+// scal[] slots
+enum { BMPC_S_RHO = 0, BMPC_S_SIGMA, BMPC_S_ALPHA, BMPC_S_RHOE, BMPC_S_ERR, BMPC_S_TRH, BMPC_S_TRA, BMPC_S_COUNT = 8 };
+
+BMPC_HD BmpcDims bmpc_make_dims(int nx, int nu, int Np, int Nc) {
+    BmpcDims d;
+    d.nx = nx; d.nu = nu; d.Np = Np; d.Nc = Nc;
+    d.NX = (Np + 1) * nx; d.NU = Nc * nu; d.ND = (Nc + 1) * nu; d.mc = d.NX + d.NU + d.ND;
+    return d;
+}
+
+BMPC_HD BmpcSysOff bmpc_make_off(const BmpcDims& d) {
+    BmpcSysOff o; int p = 0;
+#define BMPC_TAKE(f, cnt) o.f = p; p += (cnt)
+    BMPC_TAKE(Ad, d.nx * d.nx); BMPC_TAKE(Bd, d.nx * d.nu); BMPC_TAKE(Qx, d.nx * d.nx); BMPC_TAKE(QxN, d.nx * d.nx);
+    BMPC_TAKE(Qu, d.nu * d.nu); BMPC_TAKE(QDu, d.nu * d.nu);
+    BMPC_TAKE(xmin, d.nx); BMPC_TAKE(xmax, d.nx); BMPC_TAKE(umin, d.nu); BMPC_TAKE(umax, d.nu);
+    BMPC_TAKE(Dumin, d.nu); BMPC_TAKE(Dumax, d.nu); BMPC_TAKE(uref, d.nu);
+    BMPC_TAKE(pw, (d.Np + 1) * d.nx * d.nx); BMPC_TAKE(Acal, d.NX * d.nx);
+    BMPC_TAKE(Bcal, d.NX * d.NU); BMPC_TAKE(BcalT, d.NX * d.NU); BMPC_TAKE(PB, d.NX * d.NU);
+    BMPC_TAKE(H, d.NU * d.NU); BMPC_TAKE(Hinv, d.NU * d.NU); BMPC_TAKE(K, d.NU * d.NU); BMPC_TAKE(Kinv, d.NU * d.NU);
+    BMPC_TAKE(AHinv, d.mc * d.NU); BMPC_TAKE(M, d.mc * d.mc);
+    BMPC_TAKE(Gx0, d.NU * d.nx); BMPC_TAKE(Gref, d.NU * d.nx); BMPC_TAKE(GrefFull, d.NU * d.NX); BMPC_TAKE(g0, d.NU);
+    BMPC_TAKE(lo0, d.mc); BMPC_TAKE(hi0, d.mc); BMPC_TAKE(rho, d.mc); BMPC_TAKE(scal, BMPC_S_COUNT);
+#undef BMPC_TAKE
+    o.total = (p + 1) & ~1;
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sequential team (host emulation / one thread).  Warp and block teams live in bmpc_kernels.cu.
+struct SeqTeam {
+    int tid; int n;
+    BMPC_HD SeqTeam() : tid(0), n(1) {}
+    BMPC_HD void sync() {}
+    BMPC_HD bool all(bool p) { return p; }
+    BMPC_HD double max(double v) { return v; }
+    BMPC_HD int excl_scan(int f, int& total) { total = f; return 0; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Row helpers
+BMPC_HD void bmpc_row_bounds(const BmpcDims& d, const double* lo0, const double* hi0, const double* um1, int i,
+                             double& lo, double& hi) {
+    lo = lo0[i]; hi = hi0[i];
+    int r = i - (d.NX + d.NU);
+    if (r >= 0 && r < d.nu) { lo += um1[r]; hi += um1[r]; }
+}
+
+// prox of the row function: hard box -> projection; soft box with weight rho_e -> pulled toward the bound
+BMPC_HD double bmpc_prox(double v, double lo, double hi, bool soft, double rho, double rho_e) {
+    if (v > hi) return soft ? (rho * v + rho_e * hi) / (rho + rho_e) : hi;
+    if (v < lo) return soft ? (rho * v + rho_e * lo) / (rho + rho_e) : lo;
+    return v;
+}
+
+// (A x)_i for the structured A = [Bcal ; I ; D]   (without the affine offset)
+BMPC_HD double bmpc_Arow_dot(const BmpcDims& d, const double* BcalT, const double* x, int i) {
+    if (i < d.NX) {
+        int k = i / d.nx;
+        int jend = (k < d.Nc ? k : d.Nc) * d.nu;          // block-lower-triangular: x_k depends on u_j, j < k
+        double a0 = 0.0, a1 = 0.0;
+        int a = 0;
+        for (; a + 1 < jend; a += 2) { a0 += BcalT[a * d.NX + i] * x[a]; a1 += BcalT[(a + 1) * d.NX + i] * x[a + 1]; }
+        if (a < jend) a0 += BcalT[a * d.NX + i] * x[a];
+        return a0 + a1;
+    }
+    if (i < d.NX + d.NU) return x[i - d.NX];
+    int r = i - d.NX - d.NU;
+    if (r < d.nu) return x[r];
+    int s = r - d.nu;
+    return -x[s] + (s + 1 < d.NU ? x[s + 1] : 0.0);
+}
+
+// (A' w)_a
+BMPC_HD double bmpc_ATcol_dot(const BmpcDims& d, const double* Bcal, const double* w, int a) {
+    int j = a / d.nu;
+    int i0 = (j + 1) * d.nx;                               // first state row that sees u_j
+    double a0 = 0.0, a1 = 0.0;
+    int i = i0;
+    for (; i + 1 < d.NX; i += 2) { a0 += Bcal[i * d.NU + a] * w[i]; a1 += Bcal[(i + 1) * d.NU + a] * w[i + 1]; }
+    if (i < d.NX) a0 += Bcal[i * d.NU + a] * w[i];
+    const double* wd = w + d.NX + d.NU;
+    double acc = a0 + a1 + w[d.NX + a];
+    if (a < d.nu) acc += wd[a];
+    acc -= wd[d.nu + a];
+    if (a >= 1) acc += wd[d.nu + a - 1];
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: condense one system.  `sys` points at the system block (inputs already filled in).
+// In-place Gauss-Jordan inversion of an SPD matrix (no pivoting needed for SPD); returns false if a
+// pivot is not positive.  Row/column k are staged in colbuf/rowbuf so the rank-1 update is race-free.
+template <class Team>
+BMPC_HD bool bmpc_spd_inverse2(Team& t, double* A, int n, double* colbuf, double* rowbuf) {
+    bool ok = true;
+    for (int k = 0; k < n; k++) {
+        double p = A[k * n + k];
+        if (!(p > 0.0)) ok = false;
+        double pinv = 1.0 / p;
+        for (int i = t.tid; i < n; i += t.n) { colbuf[i] = A[i * n + k]; rowbuf[i] = A[k * n + i]; }
+        t.sync();
+        for (int idx = t.tid; idx < n * n; idx += t.n) {
+            int i = idx / n, j = idx % n;
+            double v;
+            if (i == k && j == k) v = pinv;
+            else if (i == k) v = rowbuf[j] * pinv;
+            else if (j == k) v = -colbuf[i] * pinv;
+            else v = A[idx] - colbuf[i] * rowbuf[j] * pinv;
+            A[idx] = v;
+        }
+        t.sync();
+    }
+    return ok;
+}
+
+// rho_in <= 0 -> automatic rho = sqrt(trace(H) / trace(A'A))
+template <class Team>
+BMPC_HD void bmpc_condense(Team& t, const BmpcDims& d, const BmpcSysOff& o, double* sys, double rho_in, double sigma,
+                           double alpha, double eps_feas, int soft_on) {
+    const int nx = d.nx, nu = d.nu, Np = d.Np, Nc = d.Nc, NX = d.NX, NU = d.NU, mc = d.mc;
+    const double *Ad = sys + o.Ad, *Bd = sys + o.Bd, *Qx = sys + o.Qx, *QxN = sys + o.QxN, *Qu = sys + o.Qu, *QDu = sys + o.QDu;
+    double *pw = sys + o.pw, *Acal = sys + o.Acal, *Bcal = sys + o.Bcal, *BcalT = sys + o.BcalT, *PB = sys + o.PB;
+    double *H = sys + o.H, *Hinv = sys + o.Hinv, *K = sys + o.K, *Kinv = sys + o.Kinv, *AHinv = sys + o.AHinv, *M = sys + o.M;
+    double *Gx0 = sys + o.Gx0, *Gref = sys + o.Gref, *GrefFull = sys + o.GrefFull, *g0 = sys + o.g0;
+    double *lo0 = sys + o.lo0, *hi0 = sys + o.hi0, *rhov = sys + o.rho, *scal = sys + o.scal;
+
+    // powers of Ad: pw[k] = Ad^k, k = 0..Np
+    for (int idx = t.tid; idx < nx * nx; idx += t.n) pw[idx] = (idx / nx == idx % nx) ? 1.0 : 0.0;
+    t.sync();
+    for (int k = 1; k <= Np; k++) {
+        for (int idx = t.tid; idx < nx * nx; idx += t.n) {
+            int r = idx / nx, c = idx % nx; double acc = 0.0;
+            for (int q = 0; q < nx; q++) acc += Ad[r * nx + q] * pw[(k - 1) * nx * nx + q * nx + c];
+            pw[k * nx * nx + idx] = acc;
+        }
+        t.sync();
+    }
+    // Acal = [I; Ad; ...; Ad^Np]
+    for (int idx = t.tid; idx < NX * nx; idx += t.n) Acal[idx] = pw[idx];
+    // Bcal[(k,a),(j,b)] = sum_{j' < k, min(j',Nc-1) = j} (Ad^(k-1-j') Bd)[a,b]      (mpc.py:537-544)
+    for (int idx = t.tid; idx < NX * NU; idx += t.n) {
+        int i = idx / NU, c = idx % NU;
+        int k = i / nx, a = i % nx, j = c / nu, b = c % nu;
+        double acc = 0.0;
+        int jlo = j, jhi = (j == Nc - 1) ? (k - 1) : j;   // held input collects j' = Nc-1 .. k-1
+        for (int jp = jlo; jp <= jhi && jp < k; jp++) {
+            const double* P = pw + (k - 1 - jp) * nx * nx;
+            for (int q = 0; q < nx; q++) acc += P[a * nx + q] * Bd[q * nu + b];
+        }
+        Bcal[idx] = acc; BcalT[c * NX + i] = acc;
+    }
+    t.sync();
+    // PB = P_X Bcal  (P_X = blkdiag(Qx x Np, QxN), mpc.py:486-487)
+    for (int idx = t.tid; idx < NX * NU; idx += t.n) {
+        int i = idx / NU, c = idx % NU, k = i / nx, a = i % nx;
+        const double* Q = (k < Np) ? Qx : QxN; double acc = 0.0;
+        for (int q = 0; q < nx; q++) acc += Q[a * nx + q] * Bcal[(k * nx + q) * NU + c];
+        PB[idx] = acc;
+    }
+    t.sync();
+    // H = Bcal' PB + P_U ;  P_U = kron(diag(w), Qu) + kron(T, QDu)   (mpc.py:510-524)
+    for (int idx = t.tid; idx < NU * NU; idx += t.n) {
+        int r = idx / NU, c = idx % NU; double acc = 0.0;
+        for (int i = 0; i < NX; i++) acc += BcalT[r * NX + i] * PB[i * NU + c];
+        int jr = r / nu, br = r % nu, jc = c / nu, bc = c % nu;
+        if (jr == jc) {
+            double wq = (jr == Nc - 1) ? (double)(Np - Nc + 1) : 1.0;
+            double tdiag = (jr == Nc - 1) ? 1.0 : 2.0;
+            acc += wq * Qu[br * nu + bc] + tdiag * QDu[br * nu + bc];
+        } else if (jr == jc + 1 || jc == jr + 1) {
+            acc -= QDu[br * nu + bc];
+        }
+        H[idx] = acc;
+    }
+    t.sync();
+    // symmetrise, copy
+    for (int idx = t.tid; idx < NU * NU; idx += t.n) { int r = idx / NU, c = idx % NU; Hinv[idx] = 0.5 * (H[idx] + H[c * NU + r]); }
+    t.sync();
+    for (int idx = t.tid; idx < NU * NU; idx += t.n) H[idx] = Hinv[idx];
+    t.sync();
+    // traces for the automatic rho
+    if (t.tid == 0) {
+        double trH = 0.0, trA = 0.0;
+        for (int a = 0; a < NU; a++) trH += H[a * NU + a];
+        for (int idx = 0; idx < NX * NU; idx++) trA += Bcal[idx] * Bcal[idx];
+        trA += (double)NU + (double)nu + 2.0 * (double)NU - 1.0;     // ||I||_F^2 + ||D||_F^2
+        scal[BMPC_S_TRH] = trH; scal[BMPC_S_TRA] = trA;
+        double rho = rho_in > 0.0 ? rho_in : sqrt(trH / trA);
+        if (!(rho > 1e-6)) rho = 1e-6;
+        if (rho > 1e6) rho = 1e6;
+        scal[BMPC_S_RHO] = rho; scal[BMPC_S_SIGMA] = sigma; scal[BMPC_S_ALPHA] = alpha;
+        scal[BMPC_S_RHOE] = soft_on ? eps_feas : 0.0; scal[BMPC_S_ERR] = 0.0;
+    }
+    t.sync();
+    const double rho = scal[BMPC_S_RHO];
+    // bounds and per-row rho (rows with both bounds infinite get rho_min like OSQP)
+    for (int i = t.tid; i < mc; i += t.n) {
+        double lo, hi;
+        if (i < NX) { lo = sys[o.xmin + i % nx]; hi = sys[o.xmax + i % nx]; }
+        else if (i < NX + NU) { lo = sys[o.umin + (i - NX) % nu]; hi = sys[o.umax + (i - NX) % nu]; }
+        else { int r = i - NX - NU; lo = sys[o.Dumin + r % nu]; hi = sys[o.Dumax + r % nu]; }
+        lo0[i] = lo; hi0[i] = hi;
+        bool free_row = (lo < -1e29) && (hi > 1e29);
+        rhov[i] = free_row ? 1e-6 : rho;
+    }
+    t.sync();
+    // K = H + sigma I + Bcal' Rx Bcal + Ru + D' Rd D
+    for (int idx = t.tid; idx < NU * NU; idx += t.n) {
+        int r = idx / NU, c = idx % NU;
+        double acc = H[idx];
+        for (int i = 0; i < NX; i++) acc += rhov[i] * BcalT[r * NX + i] * BcalT[c * NX + i];
+        const double* rd = rhov + NX + NU;
+        if (r == c) {
+            acc += sigma + rhov[NX + r];
+            if (r < nu) acc += rd[r];
+            acc += rd[nu + r];                       // row nu+r has -1 at column r
+            if (r >= 1) acc += rd[nu + r - 1];       // row nu+r-1 has +1 at column r
+        } else if (c == r + 1) acc -= rd[nu + r];    // row nu+r: (-1 at r)(+1 at r+1)
+        else if (r == c + 1) acc -= rd[nu + c];
+        K[idx] = acc; Kinv[idx] = acc;
+    }
+    t.sync();
+    // inverses (scratch: g0 / GrefFull are not yet in use)
+    bool okH = bmpc_spd_inverse2(t, Hinv, NU, GrefFull, GrefFull + NU);
+    bool okK = bmpc_spd_inverse2(t, Kinv, NU, GrefFull, GrefFull + NU);
+    if (t.tid == 0 && !(okH && okK)) scal[BMPC_S_ERR] = okH ? 2.0 : 1.0;
+    t.sync();
+    // AHinv = A Hinv  (rows: Bcal Hinv ; Hinv ; D Hinv)
+    for (int idx = t.tid; idx < mc * NU; idx += t.n) {
+        int i = idx / NU, c = idx % NU; double acc = 0.0;
+        if (i < NX) { for (int a = 0; a < NU; a++) acc += Bcal[i * NU + a] * Hinv[a * NU + c]; }
+        else if (i < NX + NU) acc = Hinv[(i - NX) * NU + c];
+        else {
+            int r = i - NX - NU;
+            if (r < nu) acc = Hinv[r * NU + c];
+            else { int s = r - nu; acc = -Hinv[s * NU + c] + (s + 1 < NU ? Hinv[(s + 1) * NU + c] : 0.0); }
+        }
+        AHinv[idx] = acc;
+    }
+    t.sync();
+    // M = AHinv A'
+    for (int idx = t.tid; idx < mc * mc; idx += t.n) {
+        int i = idx / mc, c = idx % mc; const double* row = AHinv + i * NU; double acc = 0.0;
+        if (c < NX) { for (int a = 0; a < NU; a++) acc += row[a] * Bcal[c * NU + a]; }
+        else if (c < NX + NU) acc = row[c - NX];
+        else {
+            int r = c - NX - NU;
+            if (r < nu) acc = row[r];
+            else { int s = r - nu; acc = -row[s] + (s + 1 < NU ? row[s + 1] : 0.0); }
+        }
+        M[idx] = acc;
+    }
+    // linear-term operators:  g = Gx0 x0 + Gref xref (or GrefFull vec(Xref)) + g0 + [-QDu u_-1 ; 0]
+    for (int idx = t.tid; idx < NU * nx; idx += t.n) {
+        int a = idx / nx, c = idx % nx; double acc = 0.0, accr = 0.0;
+        for (int i = 0; i < NX; i++) { acc += PB[i * NU + a] * Acal[i * nx + c]; if (i % nx == c) accr -= PB[i * NU + a]; }
+        Gx0[idx] = acc; Gref[idx] = accr;
+    }
+    for (int idx = t.tid; idx < NU * NX; idx += t.n) { int a = idx / NX, i = idx % NX; GrefFull[idx] = -PB[i * NU + a]; }
+    for (int a = t.tid; a < NU; a += t.n) {
+        int j = a / nu, b = a % nu; double wq = (j == Nc - 1) ? (double)(Np - Nc + 1) : 1.0, acc = 0.0;
+        for (int q = 0; q < nu; q++) acc += Qu[b * nu + q] * sys[o.uref + q];
+        g0[a] = -wq * acc;
+    }
+    t.sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: per-step data.  xref_mode 0: xref is (nx) ; 1: xref is ((Np+1)*nx) time-varying (mpc.py:414-421)
+template <class Team>
+BMPC_HD void bmpc_prep(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, const double* x0,
+                       const double* um1, const double* xref, int xref_mode, double* g, double* cc) {
+    const double *Gx0 = sys + o.Gx0, *Gref = sys + o.Gref, *GrefFull = sys + o.GrefFull, *g0 = sys + o.g0, *QDu = sys + o.QDu;
+    const double* Acal = sys + o.Acal;
+    for (int a = t.tid; a < d.NU; a += t.n) {
+        double acc = g0[a];
+        for (int c = 0; c < d.nx; c++) acc += Gx0[a * d.nx + c] * x0[c];
+        if (xref_mode == 0) { for (int c = 0; c < d.nx; c++) acc += Gref[a * d.nx + c] * xref[c]; }
+        else { for (int i = 0; i < d.NX; i++) acc += GrefFull[a * d.NX + i] * xref[i]; }
+        if (a < d.nu) { for (int q = 0; q < d.nu; q++) acc -= QDu[a * d.nu + q] * um1[q]; }
+        g[a] = acc;
+    }
+    for (int i = t.tid; i < d.NX; i += t.n) {
+        double acc = 0.0;
+        for (int c = 0; c < d.nx; c++) acc += Acal[i * d.nx + c] * x0[c];
+        cc[i] = acc;
+    }
+    t.sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: `niter` ADMM iterations in Douglas-Rachford form.  State: x (NU), v (mc) with z = prox(v),
+// y = rho (v - z).  One iteration (equivalent to OSQP's Algorithm 1 with the KKT system reduced to
+// (H + sigma I + A'RA) xt = sigma x - g + A'(rho z - y)):
+//     z  = prox(v);  w = rho (2 z - v - cc)
+//     xt = Kinv (sigma x - g + A' w);  zt = A xt + cc
+//     x += alpha (xt - x);  v += alpha (zt - z)
+// On return res[0] = ||zt - z||_inf, res[1] = ||sigma (xt-x) + A' rho (zt - z)||_inf of the LAST
+// iteration, res[2], res[3] = the OSQP normalisers max(||zt||,||z||), max(||H xt||,||A'y||,||g||).
+template <class Team>
+BMPC_HD void bmpc_admm(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, const double* um1,
+                       const double* g, const double* cc, double* x, double* v, double* w, double* xt, double* r,
+                       int niter, double* res) {
+    const double *Bcal = sys + o.Bcal, *BcalT = sys + o.BcalT, *Kinv = sys + o.Kinv, *H = sys + o.H;
+    const double *lo0 = sys + o.lo0, *hi0 = sys + o.hi0, *rhov = sys + o.rho, *scal = sys + o.scal;
+    const double sigma = scal[BMPC_S_SIGMA], alpha = scal[BMPC_S_ALPHA], rho_e = scal[BMPC_S_RHOE];
+    const bool soft_on = rho_e > 0.0;
+    const int NX = d.NX, NU = d.NU, mc = d.mc;
+    double rp = 0.0, rd = 0.0, np_ = 0.0, nd_ = 0.0;
+    for (int it = 0; it < niter; it++) {
+        const bool last = (it == niter - 1);
+        // A: rows
+        for (int i = t.tid; i < mc; i += t.n) {
+            double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
+            double vi = v[i], rho = rhov[i];
+            double z = bmpc_prox(vi, lo, hi, soft_on && i < NX, rho, rho_e);
+            double ci = i < NX ? cc[i] : 0.0;
+            w[i] = rho * (2.0 * z - vi - ci);
+        }
+        t.sync();
+        // B: columns  r = sigma x - g + A' w
+        for (int a = t.tid; a < NU; a += t.n) r[a] = sigma * x[a] - g[a] + bmpc_ATcol_dot(d, Bcal, w, a);
+        t.sync();
+        // C: columns  xt = Kinv r
+        for (int a = t.tid; a < NU; a += t.n) {
+            const double* row = Kinv + a * NU; double a0 = 0.0, a1 = 0.0; int b = 0;
+            for (; b + 1 < NU; b += 2) { a0 += row[b] * r[b]; a1 += row[b + 1] * r[b + 1]; }
+            if (b < NU) a0 += row[b] * r[b];
+            xt[a] = a0 + a1;
+        }
+        t.sync();
+        // D: rows  v += alpha (zt - z)   (w is reused for rho*(zt - z) on the last iteration)
+        double lrp = 0.0, lnp = 0.0;
+        for (int i = t.tid; i < mc; i += t.n) {
+            double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
+            double vi = v[i], rho = rhov[i];
+            double z = bmpc_prox(vi, lo, hi, soft_on && i < NX, rho, rho_e);
+            double zt = bmpc_Arow_dot(d, BcalT, xt, i) + (i < NX ? cc[i] : 0.0);
+            double dz = zt - z;
+            v[i] = vi + alpha * dz;
+            if (last) {
+                w[i] = rho * dz;
+                lrp = fmax(lrp, fabs(dz)); lnp = fmax(lnp, fmax(fabs(zt), fabs(z)));
+            }
+        }
+        if (last) {
+            t.sync();
+            // dual residual sigma dx + A' rho dz ; normaliser pieces ||H xt||, ||g||
+            double lrd = 0.0, lnd = 0.0;
+            for (int a = t.tid; a < NU; a += t.n) {
+                double dx = xt[a] - x[a];
+                lrd = fmax(lrd, fabs(sigma * dx + bmpc_ATcol_dot(d, Bcal, w, a)));
+                const double* row = H + a * NU; double hx = 0.0;
+                for (int b = 0; b < NU; b++) hx += row[b] * xt[b];
+                lnd = fmax(lnd, fmax(fabs(hx), fabs(g[a])));
+            }
+            t.sync();
+            // ||A'y|| with y = rho (v_new - prox(v_new))
+            for (int i = t.tid; i < mc; i += t.n) {
+                double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
+                double vi = v[i], rho = rhov[i];
+                w[i] = rho * (vi - bmpc_prox(vi, lo, hi, soft_on && i < NX, rho, rho_e));
+            }
+            t.sync();
+            for (int a = t.tid; a < NU; a += t.n) lnd = fmax(lnd, fabs(bmpc_ATcol_dot(d, Bcal, w, a)));
+            rp = t.max(lrp); np_ = t.max(lnp); rd = t.max(lrd); nd_ = t.max(lnd);
+        }
+        for (int a = t.tid; a < NU; a += t.n) x[a] += alpha * (xt[a] - x[a]);
+        t.sync();
+    }
+    if (res && t.tid == 0) { res[0] = rp; res[1] = rd; res[2] = np_; res[3] = nd_; }
+    t.sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: polish.  Primal-dual active-set refinement on the condensed QP, in dual (Schur) form:
+// with R the current set of "working" rows (violated soft rows + active hard rows, bound b_R),
+//     S mu = A_R U0 + cc_R - b_R,   S = (A H^-1 A')[R,R] + diag(1/rho_e on soft rows, delta on hard rows)
+//     U = U0 - H^-1 A_R' mu,        zz = A U + cc = W0 - (A H^-1 A')[:,R] mu
+// where U0 = -H^-1 g and W0 = A U0 + cc.  A candidate is accepted only if it satisfies the KKT
+// conditions of the condensed QP (primal feasibility of hard rows, multiplier signs, soft rows on the
+// side their set says) — then it is THE minimiser.  Otherwise the sets are updated from the candidate
+// (primal-dual active-set step) and the solve repeated, up to max_steps times.
+// Returns the number of steps used (>0) on success, 0 if not verified, -1 if the working set outgrew rmax.
+template <class Team>
+BMPC_HD int bmpc_polish(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, const double* um1,
+                        const double* g, const double* cc, const double* v, double* W0, double* zz, double* murow,
+                        int* st, double* S, double* tt, int* R, double* U0, double* U, int rmax, int max_steps) {
+    const double *Hinv = sys + o.Hinv, *AHinv = sys + o.AHinv, *M = sys + o.M;
+    const double *lo0 = sys + o.lo0, *hi0 = sys + o.hi0, *scal = sys + o.scal;
+    const double rho_e = scal[BMPC_S_RHOE];
+    const bool soft_on = rho_e > 0.0;
+    const double inv_rho_e = soft_on ? 1.0 / rho_e : 0.0;
+    const int NX = d.NX, NU = d.NU, mc = d.mc, LD = rmax;
+    const double delta = 1e-13;
+
+    for (int a = t.tid; a < NU; a += t.n) {
+        const double* row = Hinv + a * NU; double acc = 0.0;
+        for (int b = 0; b < NU; b++) acc += row[b] * g[b];
+        U0[a] = -acc;
+    }
+    for (int i = t.tid; i < mc; i += t.n) {
+        const double* row = AHinv + i * NU; double acc = (i < NX) ? cc[i] : 0.0;
+        for (int b = 0; b < NU; b++) acc -= row[b] * g[b];
+        W0[i] = acc;
+        double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
+        st[i] = v[i] > hi ? 1 : (v[i] < lo ? 2 : 0);
+    }
+    t.sync();
+
+    for (int step = 0; step < max_steps; step++) {
+        // working set R (ordered compaction)
+        int cnt = 0;
+        for (int base = 0; base < mc; base += t.n) {
+            int i = base + t.tid;
+            int f = (i < mc && st[i] != 0) ? 1 : 0;
+            int total; int pos = t.excl_scan(f, total);
+            if (f && cnt + pos < rmax) R[cnt + pos] = i;
+            cnt += total;
+        }
+        if (cnt > rmax) return -1;
+        t.sync();
+        const int r = cnt;
+        double mumax = 0.0;
+        if (r > 0) {
+            for (int k = t.tid; k < r; k += t.n) {
+                int i = R[k]; double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
+                tt[k] = W0[i] - (st[i] == 1 ? hi : lo);
+            }
+            for (int idx = t.tid; idx < r * r; idx += t.n) {
+                int k = idx / r, l = idx % r;
+                double val = M[R[k] * mc + R[l]];
+                if (k == l) val += (soft_on && R[k] < NX) ? inv_rho_e : delta * (1.0 + fabs(val));
+                S[k * LD + l] = val;
+            }
+            t.sync();
+            // Cholesky S = L L' (lower, in place)
+            for (int j = 0; j < r; j++) {
+                double djj = S[j * LD + j];
+                if (!(djj > 1e-300)) djj = 1e-300;           // dependent working rows: candidate will fail verification
+                double dj = sqrt(djj), dinv = 1.0 / dj;
+                t.sync();
+                for (int i = j + 1 + t.tid; i < r; i += t.n) S[i * LD + j] *= dinv;
+                if (t.tid == 0) S[j * LD + j] = dj;
+                t.sync();
+                for (int i = j + 1 + t.tid; i < r; i += t.n) {
+                    double lij = S[i * LD + j];
+                    for (int k = j + 1; k <= i; k++) S[i * LD + k] -= lij * S[k * LD + j];
+                }
+                t.sync();
+            }
+            // forward  L y = t
+            for (int j = 0; j < r; j++) {
+                double yj = tt[j] / S[j * LD + j];
+                t.sync();
+                for (int i = j + 1 + t.tid; i < r; i += t.n) tt[i] -= S[i * LD + j] * yj;
+                if (t.tid == 0) tt[j] = yj;
+                t.sync();
+            }
+            // backward L' mu = y
+            for (int j = r - 1; j >= 0; j--) {
+                double mj = tt[j] / S[j * LD + j];
+                t.sync();
+                for (int i = t.tid; i < j; i += t.n) tt[i] -= S[j * LD + i] * mj;
+                if (t.tid == 0) tt[j] = mj;
+                t.sync();
+            }
+        }
+        for (int i = t.tid; i < mc; i += t.n) murow[i] = 0.0;
+        t.sync();
+        double lm = 0.0;
+        for (int k = t.tid; k < r; k += t.n) { murow[R[k]] = tt[k]; lm = fmax(lm, fabs(tt[k])); }
+        mumax = t.max(lm);
+        t.sync();
+        // candidate
+        for (int i = t.tid; i < mc; i += t.n) {
+            const double* row = M + i * mc; double acc = W0[i];
+            for (int k = 0; k < r; k++) acc -= row[R[k]] * tt[k];
+            zz[i] = acc;
+        }
+        for (int a = t.tid; a < NU; a += t.n) {
+            double acc = U0[a];
+            for (int k = 0; k < r; k++) acc -= AHinv[R[k] * NU + a] * tt[k];
+            U[a] = acc;
+        }
+        // verification + next sets
+        bool ok = true;
+        const double mutol = 1e-9 * (1.0 + mumax);
+        for (int i = t.tid; i < mc; i += t.n) {
+            double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
+            int s = st[i], ns; double zi = zz[i];
+            if (soft_on && i < NX) {
+                ns = zi > hi ? 1 : (zi < lo ? 2 : 0);
+                if (ns != s) {
+                    // tolerated only if the row sits on the boundary the two labels disagree about
+                    bool same_hi = (s == 1 || ns == 1) && !(s == 2 || ns == 2);
+                    bool same_lo = (s == 2 || ns == 2) && !(s == 1 || ns == 1);
+                    double gap = same_hi ? fabs(zi - hi) : (same_lo ? fabs(zi - lo) : 1e300);
+                    double bnd = same_hi ? hi : lo;
+                    if (!(gap <= 1e-11 * (1.0 + fabs(bnd)))) ok = false;
+                }
+            } else {
+                double mu = murow[i];
+                bool vu = zi > hi + 1e-9 * (1.0 + fabs(hi));
+                bool vd = zi < lo - 1e-9 * (1.0 + fabs(lo));
+                bool bad = vu || vd || (s == 1 && mu < -mutol) || (s == 2 && mu > mutol);
+                if (bad) ok = false;
+                ns = vu ? 1 : (vd ? 2 : ((s == 1 && mu > 0.0) ? 1 : ((s == 2 && mu < 0.0) ? 2 : 0)));
+            }
+            st[i] = ns;
+        }
+        ok = t.all(ok);
+        t.sync();
+        if (ok) return step + 1;
+    }
+    return 0;
+}

@@ -1,0 +1,70 @@
+"""ctypes front-end of the host emulation of the device core (tests only)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libhostemu.so")
+_NAMES = ["Ad", "Bd", "Qx", "QxN", "Qu", "QDu", "xmin", "xmax", "umin", "umax", "Dumin", "Dumax", "uref",
+          "pw", "Acal", "Bcal", "BcalT", "PB", "H", "Hinv", "K", "Kinv", "AHinv", "M", "Gx0", "Gref", "GrefFull",
+          "g0", "lo0", "hi0", "rho", "scal"]
+
+
+def build():
+    src = os.path.join(_HERE, "hostemu.cpp")
+    core = os.path.join(_HERE, "..", "..", "pympc_b200", "csrc", "bmpc_core.cuh")
+    os.makedirs(os.path.dirname(_SO), exist_ok=True)
+    if (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(core)):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", src, "-o", _SO])
+    return ctypes.CDLL(_SO)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class EmuSystem:
+    def __init__(self, cfg, rho=0.0, sigma=1e-6, alpha=1.6):
+        self.L = build()
+        Ad = np.asarray(cfg["Ad"], float); Bd = np.asarray(cfg["Bd"], float)
+        self.nx, self.nu = Bd.shape
+        self.Np = cfg.get("Np", 20); self.Nc = cfg.get("Nc") or self.Np
+        nx, nu, Np, Nc = self.nx, self.nu, self.Np, self.Nc
+        self.NX, self.NU = (Np + 1) * nx, Nc * nu
+        self.mc = self.NX + self.NU + (Nc + 1) * nu
+        self.off = {n: self.L.emu_offset(nx, nu, Np, Nc, i) for i, n in enumerate(_NAMES)}
+        self.sys = np.zeros(self.L.emu_sys_total(nx, nu, Np, Nc))
+        inf = np.inf
+
+        def put(name, val):
+            val = np.asarray(val.toarray() if hasattr(val, "toarray") else val, float).ravel()
+            self.sys[self.off[name]:self.off[name] + val.size] = val
+        put("Ad", Ad); put("Bd", Bd)
+        Qx = cfg.get("Qx", np.zeros((nx, nx))); put("Qx", Qx); put("QxN", cfg.get("QxN", Qx))
+        put("Qu", cfg.get("Qu", np.zeros((nu, nu)))); put("QDu", cfg.get("QDu", np.zeros((nu, nu))))
+        put("xmin", cfg.get("xmin", -inf * np.ones(nx))); put("xmax", cfg.get("xmax", inf * np.ones(nx)))
+        put("umin", cfg.get("umin", -inf * np.ones(nu))); put("umax", cfg.get("umax", inf * np.ones(nu)))
+        put("Dumin", cfg.get("Dumin", -inf * np.ones(nu))); put("Dumax", cfg.get("Dumax", inf * np.ones(nu)))
+        put("uref", cfg.get("uref", np.zeros(nu)))
+        self.L.emu_condense.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] + [ctypes.c_double] * 4 + [ctypes.c_int]
+        self.L.emu_condense(nx, nu, Np, Nc, _p(self.sys), rho, sigma, alpha, float(cfg.get("eps_feas", 1e6)), 1)
+        self.x = np.zeros(self.NU); self.v = np.zeros(self.mc); self.cold = 1
+
+    def get(self, name, shape):
+        n = int(np.prod(shape))
+        return self.sys[self.off[name]:self.off[name] + n].reshape(shape).copy()
+
+    def solve(self, x0, um1, xref, first_iters=10, max_iter=4000, pdas_steps=10, rmax=64, eps_abs=1e-3, eps_rel=1e-3):
+        x0 = np.ascontiguousarray(x0, float); um1 = np.ascontiguousarray(um1, float); xref = np.ascontiguousarray(xref, float)
+        mode = 0 if xref.ndim == 1 else 1
+        U = np.zeros(self.NU); it = ctypes.c_int(); ps = ctypes.c_int(); res = np.zeros(4)
+        f = self.L.emu_solve
+        f.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 4 + [ctypes.c_int] * 2 + [ctypes.c_void_p] * 3 + \
+                     [ctypes.c_int] * 4 + [ctypes.c_double] * 2 + [ctypes.c_void_p] * 3
+        st = f(self.nx, self.nu, self.Np, self.Nc, _p(self.sys), _p(x0), _p(um1), _p(xref), mode, self.cold,
+               _p(self.x), _p(self.v), _p(U), first_iters, max_iter, pdas_steps, rmax, eps_abs, eps_rel,
+               ctypes.byref(it), ctypes.byref(ps), _p(res))
+        self.cold = 0
+        return U, st, it.value, ps.value, res

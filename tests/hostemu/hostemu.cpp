@@ -1,0 +1,68 @@
+// Host emulation of the device numerical core (TEST INFRASTRUCTURE ONLY).
+// Compiles pympc_b200/csrc/bmpc_core.cuh for the CPU with a one-thread "team" so that index
+// arithmetic and algorithm logic can be checked against numpy without a GPU.  This is NOT a CPU
+// fallback: pympc_b200 never loads this library; it lives under tests/ and is built by the tests.
+#define BMPC_HOSTEMU 1
+#include "../../pympc_b200/csrc/bmpc_core.cuh"
+#include <stdlib.h>
+#include <string.h>
+
+extern "C" {
+
+int emu_sys_total(int nx, int nu, int Np, int Nc) { BmpcDims d = bmpc_make_dims(nx, nu, Np, Nc); return bmpc_make_off(d).total; }
+
+// offsets of a few arrays for inspection: returns offset by name index
+int emu_offset(int nx, int nu, int Np, int Nc, int which) {
+    BmpcDims d = bmpc_make_dims(nx, nu, Np, Nc); BmpcSysOff o = bmpc_make_off(d);
+    int tab[] = {o.Ad, o.Bd, o.Qx, o.QxN, o.Qu, o.QDu, o.xmin, o.xmax, o.umin, o.umax, o.Dumin, o.Dumax, o.uref,
+                 o.pw, o.Acal, o.Bcal, o.BcalT, o.PB, o.H, o.Hinv, o.K, o.Kinv, o.AHinv, o.M, o.Gx0, o.Gref, o.GrefFull,
+                 o.g0, o.lo0, o.hi0, o.rho, o.scal};
+    return tab[which];
+}
+
+void emu_condense(int nx, int nu, int Np, int Nc, double* sys, double rho, double sigma, double alpha, double eps_feas, int soft_on) {
+    BmpcDims d = bmpc_make_dims(nx, nu, Np, Nc); BmpcSysOff o = bmpc_make_off(d);
+    SeqTeam t;
+    bmpc_condense(t, d, o, sys, rho, sigma, alpha, eps_feas, soft_on);
+}
+
+// one full solve of one instance: rounds of ADMM + polish, like the host loop of the library.
+// x,v: warm start in/out (cold != 0 -> initialise).  Returns status (1 solved+polished, 2 solved by eps only, -2 max iter).
+int emu_solve(int nx, int nu, int Np, int Nc, const double* sys, const double* x0, const double* um1, const double* xref,
+              int xref_mode, int cold, double* x, double* v, double* Uout, int first_iters, int max_iter, int pdas_steps,
+              int rmax, double eps_abs, double eps_rel, int* iters_out, int* polish_steps_out, double* res_out) {
+    BmpcDims d = bmpc_make_dims(nx, nu, Np, Nc); BmpcSysOff o = bmpc_make_off(d);
+    SeqTeam t;
+    double* buf = (double*)calloc(8 * d.mc + 8 * d.NU + d.NX + rmax * rmax + rmax + 16, sizeof(double));
+    double *g = buf, *cc = g + d.NU, *w = cc + d.NX, *xt = w + d.mc, *r = xt + d.NU, *W0 = r + d.NU, *zz = W0 + d.mc,
+           *murow = zz + d.mc, *S = murow + d.mc, *tt = S + rmax * rmax, *U0 = tt + rmax, *U = U0 + d.NU, *res = U + d.NU;
+    int* st = (int*)calloc(d.mc + rmax, sizeof(int)); int* R = st + d.mc;
+    bmpc_prep(t, d, o, sys, x0, um1, xref, xref_mode, g, cc);
+    if (cold) { for (int a = 0; a < d.NU; a++) x[a] = 0.0; for (int i = 0; i < d.mc; i++) v[i] = i < d.NX ? cc[i] : 0.0; }
+    int total = 0, chunk = first_iters, status = -2, psteps = 0;
+    const double* rhov = sys + o.rho;
+    while (total < max_iter) {
+        if (chunk > max_iter - total) chunk = max_iter - total;
+        bmpc_admm(t, d, o, sys, um1, g, cc, x, v, w, xt, r, chunk, res);
+        total += chunk;
+        int ps = bmpc_polish(t, d, o, sys, um1, g, cc, v, W0, zz, murow, st, S, tt, R, U0, U, rmax, pdas_steps);
+        if (ps > 0) {
+            psteps += ps; status = 1;
+            for (int a = 0; a < d.NU; a++) { Uout[a] = U[a]; x[a] = U[a]; }
+            for (int i = 0; i < d.mc; i++) v[i] = zz[i] + murow[i] / rhov[i];
+            break;
+        }
+        psteps += pdas_steps;
+        chunk = total < 25 ? 25 - total : total;   // 10, 15, 25, 50, 100, ...
+    }
+    if (status != 1) {
+        bool conv = res[0] <= eps_abs + eps_rel * res[2] && res[1] <= eps_abs + eps_rel * res[3];
+        status = conv ? 2 : -2;
+        for (int a = 0; a < d.NU; a++) Uout[a] = xt[a];
+    }
+    *iters_out = total; *polish_steps_out = psteps;
+    for (int k = 0; k < 4; k++) res_out[k] = res[k];
+    free(buf); free(st);
+    return status;
+}
+}
