@@ -1,0 +1,123 @@
+/*
+ * bmpc.h — C ABI of the B200-native batched linear-MPC solver (libbmpc.so).
+ *
+ * The reference (forgi86/pyMPC) has no FFI of its own: its hot path is the Python class
+ * MPCController (/root/reference/pyMPC/mpc.py:27-615) driving the third-party OSQP object through
+ * three calls (mpc.py:266 setup, :454 update, :369 solve) and slicing the result (mpc.py:301-304).
+ * Each entry point below replaces one of those steps for a BATCH of B independent MPC instances
+ * that live on one CUDA device; pympc_b200/mpc.py binds them with ctypes.
+ *
+ * Conventions: plain pointers and sizes, row-major fp64, batch-major [B, ...]; every call returns 0
+ * on success or a negative bmpc_error; the message is available from bmpc_last_error().  The
+ * library owns all device state; callers own every buffer they pass (copied at call time).
+ * One handle <-> one device + one stream; a handle is not thread-safe.
+ */
+#ifndef BMPC_H
+#define BMPC_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bmpc_handle bmpc_handle;
+
+typedef enum {
+    BMPC_OK = 0,
+    BMPC_ERR_ARG = -1,        /* bad argument (reference: ValueError in MPCController.__init__, mpc.py:82-223) */
+    BMPC_ERR_CUDA = -2,       /* CUDA runtime failure */
+    BMPC_ERR_STATE = -3,      /* call order violated (e.g. solve before setup) */
+    BMPC_ERR_NOT_PD = -4,     /* condensed Hessian not positive definite (QP not strictly convex in U) */
+    BMPC_ERR_NO_DEVICE = -5   /* no usable CUDA device: there is NO CPU fallback */
+} bmpc_error;
+
+/* per-instance solver status written by bmpc_output (mirrors OSQP's status_val where it exists) */
+enum {
+    BMPC_SOLVED = 1,            /* KKT-verified minimiser (polished)            -> reference 'solved' */
+    BMPC_SOLVED_UNPOLISHED = 2, /* ADMM met eps_abs/eps_rel (OSQP's criterion), polish not verified -> 'solved' */
+    BMPC_MAX_ITER = -2,         /* OSQP 'maximum iterations reached'            -> reference falls back to u_failure */
+    BMPC_UNSOLVED = -10
+};
+
+typedef struct {
+    int32_t nx, nu, Np, Nc;     /* Nc <= 0 means Nc = Np            (mpc.py:76-108) */
+    int32_t batch;              /* instances on this device */
+    int32_t device;             /* CUDA ordinal */
+    int32_t soft_on;            /* SOFT_ON flag (mpc.py:237); 0 = hard state bounds */
+    int32_t max_iter;           /* ADMM iteration cap per solve (OSQP default 4000) */
+    int32_t first_iters;        /* ADMM iterations before the first polish attempt */
+    int32_t pdas_steps;         /* active-set refinements per polish attempt */
+    int32_t rmax;               /* working-set capacity of the polish (0 = auto) */
+    int32_t polish;             /* 1 = ADMM + polish (exact), 0 = pure ADMM to eps (OSQP-like) */
+    int32_t team_threads;       /* 0 = auto; 32 = one warp per instance; >32 = one CTA of that size per instance */
+    int32_t warps_per_block;    /* 0 = auto (warp team only) */
+    double eps_feas;            /* slack weight (mpc.py:226) */
+    double rho;                 /* <= 0: automatic sqrt(trace H / trace A'A) */
+    double sigma, alpha;        /* OSQP defaults 1e-6, 1.6 */
+    double eps_abs, eps_rel;    /* OSQP termination tolerances (mpc.py:266) */
+} bmpc_config;
+
+typedef struct {
+    int64_t admm_iters;         /* sum over instances of ADMM iterations in the last solve */
+    int32_t rounds;             /* ADMM/polish rounds of the last solve */
+    int32_t unsolved;           /* instances the polish never verified (status 2 or -2); -1 in pure-ADMM mode */
+    int64_t polish_steps;       /* sum of active-set refinements */
+    float ms_admm;              /* device time of the ADMM kernels in the last solve (CUDA events) */
+    float ms_polish;            /* device time of the polish kernels */
+    int32_t launches;           /* kernels launched by the last solve */
+    int32_t reserved;
+} bmpc_stats;
+
+void bmpc_default_config(bmpc_config* cfg);
+
+/* replaces MPCController.__init__'s solver object creation (mpc.py:241) */
+int bmpc_create(const bmpc_config* cfg, bmpc_handle** out);
+void bmpc_destroy(bmpc_handle* h);
+const char* bmpc_last_error(const bmpc_handle* h);   /* h may be NULL: error of the last failed bmpc_create */
+
+/* replaces _compute_QP_matrices_ + OSQP.setup (mpc.py:254-269, 456-615): condense + factor on device (K1).
+ * All pointers are HOST pointers to one shared system (every instance uses the same matrices). */
+int bmpc_setup(bmpc_handle* h, const double* Ad, const double* Bd, const double* Qx, const double* QxN,
+               const double* Qu, const double* QDu, const double* xmin, const double* xmax, const double* umin,
+               const double* umax, const double* Dumin, const double* Dumax, const double* uref);
+
+/* replaces update()/_update_QP_matrices_/OSQP.update (mpc.py:338-364, 386-454).
+ * x0 [B,nx]; uminus1 [B,nu] or NULL (keep: the previously committed output, quirk Q9);
+ * xref [B,nx] (xref_rows = 1) or [B,Np+1,nx] (xref_rows = Np+1) or NULL (keep).
+ * on_device != 0: the pointers are device pointers on this handle's device. */
+int bmpc_update(bmpc_handle* h, const double* x0, const double* uminus1, const double* xref, int xref_rows, int on_device);
+
+/* replaces OSQP.solve (mpc.py:366-375): K3 + K4 + K5 */
+int bmpc_solve(bmpc_handle* h);
+
+/* replaces output() (mpc.py:271-336): u0 [B,nu] (u_failure = uref where status < 0), status [B] (nullable);
+ * commit_uminus1 != 0 stores u0 as the next uminus1 (mpc.py:330). */
+int bmpc_output(bmpc_handle* h, double* u0, int32_t* status, int commit_uminus1, int on_device);
+
+/* optional info of output(): u_seq [B,Nc*nu], x_seq [B,(Np+1)*nx], eps_seq [B,(Np+1)*nx], obj_val [B]
+ * (QP objective WITHOUT the reference's J_CNST), iters [B]; any pointer may be NULL.  Host pointers. */
+int bmpc_get_sequences(bmpc_handle* h, double* u_seq, double* x_seq, double* eps_seq, double* obj_val, int32_t* iters);
+
+/* let the polish epilogue write u0 straight into a caller-owned DEVICE buffer [B,nu]
+ * (e.g. this rank's slice of an all-gather buffer); NULL restores the internal buffer. */
+int bmpc_bind_output(bmpc_handle* h, double* dev_u0);
+int bmpc_set_stream(bmpc_handle* h, void* cuda_stream);   /* NULL = handle-owned stream */
+int bmpc_synchronize(bmpc_handle* h);
+
+int bmpc_get_stats(bmpc_handle* h, bmpc_stats* out);
+/* export one array of the condensed system for parity tests: name in {"Bcal","H","Hinv","K","Kinv","M","AHinv",
+ * "Gx0","Gref","g0","lo0","hi0","rho","scal"}; out must hold `capacity` doubles; returns the element count. */
+int bmpc_get_sys(bmpc_handle* h, const char* name, double* out, int capacity);
+/* problem sizes: dims[0..7] = nx, nu, Np, Nc, NX, NU, mc, team_threads */
+int bmpc_get_dims(const bmpc_handle* h, int32_t* dims);
+
+/* pinned host memory for the end-to-end path (cudaHostAlloc / cudaFreeHost) */
+void* bmpc_host_alloc(uint64_t bytes);
+void bmpc_host_free(void* p);
+/* number of visible CUDA devices (0 if none / driver missing) */
+int bmpc_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

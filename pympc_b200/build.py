@@ -1,0 +1,29 @@
+"""In-tree build of libbmpc.so for sm_100a (nvcc cross-compiles without a GPU)."""
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(_HERE, "csrc", "bmpc.cu")
+DEPS = [SRC, os.path.join(_HERE, "csrc", "bmpc_core.cuh"), os.path.join(_HERE, "..", "include", "bmpc.h")]
+LIB = os.path.join(_HERE, "libbmpc.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def nvcc_path():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def build(force=False, verbose=False):
+    stale = force or not os.path.exists(LIB) or any(os.path.getmtime(LIB) < os.path.getmtime(p) for p in DEPS)
+    if stale:
+        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [SRC, "-o", LIB]
+        subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

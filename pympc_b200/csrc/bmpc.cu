@@ -1,0 +1,652 @@
+// bmpc.cu — CUDA kernels (sm_100a) and the C ABI of libbmpc.so (see include/bmpc.h).
+//
+// Kernel map:
+//   k_condense   K1/K2  one CTA per system: prediction matrices, H, K, inverses, dual operators
+//   k_admm       K3+K4  one team (warp or CTA) per instance: per-step prep + ADMM iterations, state in smem
+//   k_polish     K5+K6  one team per instance: active-set polish, KKT verification, output epilogue
+//   k_finalize          status / fallback output for instances the polish never verified
+//   k_sequences         optional x/u/eps sequences and objective value (output() info, mpc.py:307-328)
+// Host side: handle management and the round loop  ADMM(first_iters) -> polish -> [ADMM(chunk) -> polish]*.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/bmpc.h"
+#include "bmpc_core.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// teams
+struct WarpTeam {
+    int tid;
+    static constexpr int n = 32;
+    __device__ __forceinline__ WarpTeam() : tid(threadIdx.x & 31) {}
+    __device__ __forceinline__ void sync() { __syncwarp(); }
+    __device__ __forceinline__ bool all(bool p) { return __all_sync(0xffffffffu, p); }
+    __device__ __forceinline__ double max(double v) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, s));
+        return v;
+    }
+    __device__ __forceinline__ double sum(double v) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        return v;
+    }
+    __device__ __forceinline__ int excl_scan(int f, int& total) {
+        unsigned b = __ballot_sync(0xffffffffu, f);
+        total = __popc(b);
+        return __popc(b & ((1u << tid) - 1u));
+    }
+};
+
+struct BlockTeam {
+    int tid, n;
+    double* sd;   // 32 doubles of scratch
+    int* si;      // 32 ints of scratch
+    __device__ __forceinline__ BlockTeam(double* sd_, int* si_) : tid(threadIdx.x), n(blockDim.x), sd(sd_), si(si_) {}
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ bool all(bool p) { return __syncthreads_and(p) != 0; }
+    __device__ __forceinline__ double max(double v) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, s));
+        if ((tid & 31) == 0) sd[tid >> 5] = v;
+        __syncthreads();
+        double r = sd[0];
+        for (int w = 1; w < (n + 31) / 32; w++) r = fmax(r, sd[w]);
+        __syncthreads();
+        return r;
+    }
+    __device__ __forceinline__ double sum(double v) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        if ((tid & 31) == 0) sd[tid >> 5] = v;
+        __syncthreads();
+        double r = 0.0;
+        for (int w = 0; w < (n + 31) / 32; w++) r += sd[w];
+        __syncthreads();
+        return r;
+    }
+    __device__ __forceinline__ int excl_scan(int f, int& total) {
+        unsigned b = __ballot_sync(0xffffffffu, f);
+        if ((tid & 31) == 0) si[tid >> 5] = __popc(b);
+        __syncthreads();
+        int off = 0, tot = 0;
+        for (int w = 0; w < (n + 31) / 32; w++) { int c = si[w]; if (w < (tid >> 5)) off += c; tot += c; }
+        __syncthreads();
+        total = tot;
+        return off + __popc(b & ((1u << (tid & 31)) - 1u));
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// per-instance device arrays
+struct BmpcInst {
+    const double* x0;     // [B,nx]
+    const double* um1;    // [B,nu]
+    const double* xref;   // [B,nx] or [B,NX]
+    double* g;            // [B,NU]   scratch (per-step linear term)
+    double* cc;           // [B,NX]   scratch (free response Acal x0)
+    double* xw;           // [B,NU]   ADMM x (warm start)
+    double* vw;           // [B,mc]   ADMM v (warm start)
+    double* Ua;           // [B,NU]   last ADMM xt (fallback solution)
+    double* Us;           // [B,NU]   solution
+    double* res;          // [B,4]    residuals of the last ADMM iteration
+    double* u0;           // [B,nu]   output
+    int32_t* status;      // [B]
+    int32_t* iters;       // [B]
+    int32_t* psteps;      // [B]
+};
+
+// smem (doubles) per instance for the two kernels — keep in sync with the carve-up below
+__host__ __device__ static inline size_t admm_smem_doubles(const BmpcDims& d) { return 4 * (size_t)d.NU + d.NX + 2 * (size_t)d.mc + d.nu + 4 + 4; }
+__host__ __device__ static inline size_t polish_smem_doubles(const BmpcDims& d, int rmax) {
+    return 3 * (size_t)d.NU + d.NX + 4 * (size_t)d.mc + (size_t)rmax * rmax + rmax + d.nu + 2 + (d.mc + rmax + 3) / 2;
+}
+
+__global__ void k_condense(BmpcDims d, BmpcSysOff o, double* sys, double rho, double sigma, double alpha, double eps_feas,
+                           int soft_on) {
+    __shared__ double sd[32];
+    __shared__ int si[32];
+    BlockTeam t(sd, si);
+    bmpc_condense(t, d, o, sys + (size_t)blockIdx.x * o.total, rho, sigma, alpha, eps_feas, soft_on);
+}
+
+template <bool WARP>
+__global__ void k_admm(BmpcDims d, BmpcSysOff o, const double* __restrict__ sys, BmpcInst I, const int32_t* __restrict__ list,
+                       int count, int niter, int do_prep, int cold, int xref_mode) {
+    extern __shared__ double smem[];
+    __shared__ double sd[32];
+    __shared__ int si[32];
+    int slot, idx;
+    if (WARP) { slot = threadIdx.x >> 5; idx = blockIdx.x * (blockDim.x >> 5) + slot; }
+    else { slot = 0; idx = blockIdx.x; }
+    if (idx >= count) return;
+    const int inst = list ? list[idx] : idx;
+    double* base = smem + (size_t)slot * admm_smem_doubles(d);
+    double *g = base, *cc = g + d.NU, *x = cc + d.NX, *v = x + d.NU, *w = v + d.mc, *xt = w + d.mc, *r = xt + d.NU,
+           *um1 = r + d.NU, *res = um1 + d.nu + (d.nu & 1);
+    auto run = [&](auto& t) {
+        for (int q = t.tid; q < d.nu; q += t.n) um1[q] = I.um1[(size_t)inst * d.nu + q];
+        t.sync();
+        if (do_prep) {
+            const int xl = xref_mode ? d.NX : d.nx;
+            bmpc_prep(t, d, o, sys, I.x0 + (size_t)inst * d.nx, um1, I.xref + (size_t)inst * xl, xref_mode, g, cc);
+            for (int a = t.tid; a < d.NU; a += t.n) I.g[(size_t)inst * d.NU + a] = g[a];
+            for (int i = t.tid; i < d.NX; i += t.n) I.cc[(size_t)inst * d.NX + i] = cc[i];
+        } else {
+            for (int a = t.tid; a < d.NU; a += t.n) g[a] = I.g[(size_t)inst * d.NU + a];
+            for (int i = t.tid; i < d.NX; i += t.n) cc[i] = I.cc[(size_t)inst * d.NX + i];
+        }
+        if (cold) {
+            for (int a = t.tid; a < d.NU; a += t.n) x[a] = 0.0;
+            t.sync();
+            for (int i = t.tid; i < d.mc; i += t.n) v[i] = (i < d.NX) ? cc[i] : 0.0;
+        } else {
+            for (int a = t.tid; a < d.NU; a += t.n) x[a] = I.xw[(size_t)inst * d.NU + a];
+            for (int i = t.tid; i < d.mc; i += t.n) v[i] = I.vw[(size_t)inst * d.mc + i];
+        }
+        t.sync();
+        bmpc_admm(t, d, o, sys, um1, g, cc, x, v, w, xt, r, niter, res);
+        for (int a = t.tid; a < d.NU; a += t.n) { I.xw[(size_t)inst * d.NU + a] = x[a]; I.Ua[(size_t)inst * d.NU + a] = xt[a]; }
+        for (int i = t.tid; i < d.mc; i += t.n) I.vw[(size_t)inst * d.mc + i] = v[i];
+        if (t.tid < 4) I.res[(size_t)inst * 4 + t.tid] = res[t.tid];
+        if (t.tid == 0) I.iters[inst] += niter;
+    };
+    if (WARP) { WarpTeam t; run(t); }
+    else { BlockTeam t(sd, si); run(t); }
+}
+
+template <bool WARP>
+__global__ void k_polish(BmpcDims d, BmpcSysOff o, const double* __restrict__ sys, BmpcInst I, const int32_t* __restrict__ list,
+                         int count, int rmax, int max_steps, int32_t* next_list, int32_t* next_count, double* u0_out) {
+    extern __shared__ double smem[];
+    __shared__ double sd[32];
+    __shared__ int si[32];
+    int slot, idx;
+    if (WARP) { slot = threadIdx.x >> 5; idx = blockIdx.x * (blockDim.x >> 5) + slot; }
+    else { slot = 0; idx = blockIdx.x; }
+    if (idx >= count) return;
+    const int inst = list ? list[idx] : idx;
+    double* base = smem + (size_t)slot * polish_smem_doubles(d, rmax);
+    double *g = base, *cc = g + d.NU, *v = cc + d.NX, *W0 = v + d.mc, *zz = W0 + d.mc, *murow = zz + d.mc,
+           *S = murow + d.mc, *tt = S + (size_t)rmax * rmax, *U0 = tt + rmax, *U = U0 + d.NU, *um1 = U + d.NU;
+    int* st = (int*)(um1 + d.nu + (d.nu & 1));
+    int* R = st + d.mc;
+    auto run = [&](auto& t) {
+        for (int q = t.tid; q < d.nu; q += t.n) um1[q] = I.um1[(size_t)inst * d.nu + q];
+        for (int a = t.tid; a < d.NU; a += t.n) g[a] = I.g[(size_t)inst * d.NU + a];
+        for (int i = t.tid; i < d.NX; i += t.n) cc[i] = I.cc[(size_t)inst * d.NX + i];
+        for (int i = t.tid; i < d.mc; i += t.n) v[i] = I.vw[(size_t)inst * d.mc + i];
+        t.sync();
+        int ps = bmpc_polish(t, d, o, sys, um1, g, cc, v, W0, zz, murow, st, S, tt, R, U0, U, rmax, max_steps);
+        if (ps > 0) {
+            const double* rhov = sys + o.rho;
+            for (int a = t.tid; a < d.NU; a += t.n) {
+                double ua = U[a];
+                I.Us[(size_t)inst * d.NU + a] = ua; I.xw[(size_t)inst * d.NU + a] = ua;
+                if (a < d.nu) u0_out[(size_t)inst * d.nu + a] = ua;
+            }
+            // exact ADMM fixed point of this problem = warm start of the next one: v* = z* + y*/rho
+            for (int i = t.tid; i < d.mc; i += t.n) I.vw[(size_t)inst * d.mc + i] = zz[i] + murow[i] / rhov[i];
+            if (t.tid == 0) { I.status[inst] = BMPC_SOLVED; I.psteps[inst] += ps; atomicAdd(next_count + 1, ps); }
+        } else {
+            if (t.tid == 0) {
+                int used = (ps < 0 ? 1 : max_steps);
+                I.psteps[inst] += used; atomicAdd(next_count + 1, used);
+                int pos = atomicAdd(next_count, 1);
+                next_list[pos] = inst;
+            }
+        }
+    };
+    if (WARP) { WarpTeam t; run(t); }
+    else { BlockTeam t(sd, si); run(t); }
+}
+
+// instances still unverified after the last round: OSQP's criterion decides between "solved" and "max iter";
+// the output falls back to u_failure = uref when not solved (mpc.py:230,303-304).  pure_admm: no polish was run.
+__global__ void k_finalize(BmpcDims d, BmpcSysOff o, const double* __restrict__ sys, BmpcInst I, const int32_t* __restrict__ list,
+                           int count, double eps_abs, double eps_rel, double* u0_out) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    const int inst = list ? list[idx] : idx;
+    const double* res = I.res + (size_t)inst * 4;
+    bool conv = res[0] <= eps_abs + eps_rel * res[2] && res[1] <= eps_abs + eps_rel * res[3];
+    I.status[inst] = conv ? BMPC_SOLVED_UNPOLISHED : BMPC_MAX_ITER;
+    for (int a = 0; a < d.NU; a++) I.Us[(size_t)inst * d.NU + a] = I.Ua[(size_t)inst * d.NU + a];
+    for (int q = 0; q < d.nu; q++) u0_out[(size_t)inst * d.nu + q] = conv ? I.Ua[(size_t)inst * d.NU + q] : sys[o.uref + q];
+}
+
+// pure-ADMM mode: list of instances not yet converged by OSQP's criterion
+__global__ void k_check_converged(BmpcInst I, const int32_t* __restrict__ list, int count, double eps_abs, double eps_rel,
+                                  int32_t* next_list, int32_t* next_count) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    const int inst = list ? list[idx] : idx;
+    const double* res = I.res + (size_t)inst * 4;
+    bool conv = res[0] <= eps_abs + eps_rel * res[2] && res[1] <= eps_abs + eps_rel * res[3];
+    if (!conv) { int pos = atomicAdd(next_count, 1); next_list[pos] = inst; }
+}
+
+__global__ void k_reset(BmpcInst I, int B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) { I.status[i] = BMPC_UNSOLVED; I.iters[i] = 0; I.psteps[i] = 0; }
+}
+
+// x_seq = Acal x0 + Bcal U, eps_seq = distance back to the box, objective of the reference QP (without J_CNST)
+__global__ void k_sequences(BmpcDims d, BmpcSysOff o, const double* __restrict__ sys, BmpcInst I, int B, int xref_mode,
+                            double* xseq, double* epsseq, double* obj) {
+    WarpTeam t;
+    int inst = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (inst >= B) return;
+    const double *BcalT = sys + o.BcalT, *H = sys + o.H, *lo0 = sys + o.lo0, *hi0 = sys + o.hi0;
+    const double *Qx = sys + o.Qx, *QxN = sys + o.QxN;
+    const double rho_e = sys[o.scal + BMPC_S_RHOE];
+    const double* U = I.Us + (size_t)inst * d.NU;
+    const double* cc = I.cc + (size_t)inst * d.NX;
+    const double* g = I.g + (size_t)inst * d.NU;
+    const double* xr = I.xref + (size_t)inst * (xref_mode ? d.NX : d.nx);
+    double part = 0.0;
+    for (int i = t.tid; i < d.NX; i += 32) {
+        double xi = bmpc_Arow_dot(d, BcalT, U, i) + cc[i];
+        double e = xi > hi0[i] ? hi0[i] - xi : (xi < lo0[i] ? lo0[i] - xi : 0.0);
+        if (!(rho_e > 0.0)) e = 0.0;
+        xseq[(size_t)inst * d.NX + i] = xi; epsseq[(size_t)inst * d.NX + i] = e;
+        part += 0.5 * rho_e * e * e;
+        // 0.5 cc' P_X cc + q_X' cc  with q_X = -P_X xref
+        int k = i / d.nx, a = i % d.nx; const double* Q = k < d.Np ? Qx : QxN; double pc = 0.0, pr = 0.0;
+        for (int q = 0; q < d.nx; q++) {
+            pc += Q[a * d.nx + q] * cc[k * d.nx + q];
+            pr += Q[a * d.nx + q] * (xref_mode ? xr[k * d.nx + q] : xr[q]);
+        }
+        part += cc[i] * (0.5 * pc - pr);
+    }
+    for (int a = t.tid; a < d.NU; a += 32) {
+        double hu = 0.0;
+        for (int b = 0; b < d.NU; b++) hu += H[a * d.NU + b] * U[b];
+        part += U[a] * (0.5 * hu + g[a]);
+    }
+    part = t.sum(part);
+    if (t.tid == 0) obj[inst] = part;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+struct bmpc_handle {
+    bmpc_config cfg;
+    BmpcDims d;
+    BmpcSysOff o;
+    int team;        // 32 or CTA size
+    int wpb;         // warps per block (warp team)
+    int rmax;
+    cudaStream_t stream, own_stream;
+    double* sys = nullptr;
+    BmpcInst I;
+    double *x0 = nullptr, *um1 = nullptr, *xref = nullptr, *u0_own = nullptr, *u0_bound = nullptr;
+    double *seq_x = nullptr, *seq_e = nullptr, *seq_obj = nullptr;
+    int32_t *listA = nullptr, *listB = nullptr, *counts = nullptr;  // counts[2]
+    int32_t* h_count = nullptr;                                      // pinned
+    cudaEvent_t ev[4];
+    int xref_mode = 0;
+    bool is_setup = false, cold = true, solved = false;
+    bmpc_stats stats;
+    std::string err;
+    size_t smem_admm = 0, smem_polish = 0;
+};
+
+static std::string g_create_err;
+
+#define BMPC_CUDA(call)                                                                            \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return BMPC_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+extern "C" {
+
+void bmpc_default_config(bmpc_config* c) {
+    memset(c, 0, sizeof(*c));
+    c->Np = 20; c->Nc = 0; c->batch = 1; c->device = 0; c->soft_on = 1;
+    c->max_iter = 4000; c->first_iters = 10; c->pdas_steps = 10; c->rmax = 0; c->polish = 1;
+    c->team_threads = 0; c->warps_per_block = 0;
+    c->eps_feas = 1e6; c->rho = 0.0; c->sigma = 1e-6; c->alpha = 1.6; c->eps_abs = 1e-3; c->eps_rel = 1e-3;
+}
+
+int bmpc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* bmpc_last_error(const bmpc_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+void* bmpc_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void bmpc_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+static int configure_launch(bmpc_handle* h) {
+    const BmpcDims& d = h->d;
+    int dev = h->cfg.device, max_optin = 0;
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    size_t budget = (size_t)max_optin - 1024;
+    int team = h->cfg.team_threads;
+    if (team <= 0) team = (d.mc <= 192 && d.NU <= 64) ? 32 : 256;
+    if (team != 32) { team = ((team + 31) / 32) * 32; if (team > 1024) team = 1024; }
+    h->team = team;
+    int rmax = h->cfg.rmax > 0 ? h->cfg.rmax : (team == 32 ? 48 : 128);
+    if (rmax > d.mc) rmax = d.mc;
+    // shrink rmax until one instance fits
+    while (rmax > 8 && polish_smem_doubles(d, rmax) * 8 > budget) rmax -= 8;
+    if (polish_smem_doubles(d, rmax) * 8 > budget || admm_smem_doubles(d) * 8 > budget) {
+        h->err = "problem too large for the shared-memory resident kernels"; return BMPC_ERR_ARG;
+    }
+    h->rmax = rmax;
+    if (team == 32) {
+        int wpb = h->cfg.warps_per_block > 0 ? h->cfg.warps_per_block : 8;
+        while (wpb > 1 && (size_t)wpb * polish_smem_doubles(d, rmax) * 8 > budget) wpb--;
+        h->wpb = wpb;
+        h->smem_admm = (size_t)wpb * admm_smem_doubles(d) * 8;
+        h->smem_polish = (size_t)wpb * polish_smem_doubles(d, rmax) * 8;
+        BMPC_CUDA(cudaFuncSetAttribute(k_admm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_admm));
+        BMPC_CUDA(cudaFuncSetAttribute(k_polish<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_polish));
+    } else {
+        h->wpb = team / 32;
+        h->smem_admm = admm_smem_doubles(d) * 8;
+        h->smem_polish = polish_smem_doubles(d, rmax) * 8;
+        BMPC_CUDA(cudaFuncSetAttribute(k_admm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_admm));
+        BMPC_CUDA(cudaFuncSetAttribute(k_polish<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_polish));
+    }
+    return BMPC_OK;
+}
+
+int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
+    if (!cfg || !out) { g_create_err = "null argument"; return BMPC_ERR_ARG; }
+    *out = nullptr;
+    if (cfg->nx < 1 || cfg->nu < 1 || cfg->Np < 2 || cfg->batch < 1 || (cfg->Nc > cfg->Np)) {
+        g_create_err = "invalid dimensions (need nx,nu >= 1, Np > 1, Nc <= Np, batch >= 1)"; return BMPC_ERR_ARG;
+    }
+    int ndev = bmpc_device_count();
+    if (ndev <= 0) { g_create_err = "no CUDA device visible: libbmpc has no CPU fallback"; return BMPC_ERR_NO_DEVICE; }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "device ordinal out of range"; return BMPC_ERR_ARG; }
+    bmpc_handle* h = new bmpc_handle();
+    h->cfg = *cfg;
+    if (h->cfg.Nc <= 0) h->cfg.Nc = h->cfg.Np;
+    if (h->cfg.max_iter <= 0) h->cfg.max_iter = 4000;
+    if (h->cfg.first_iters <= 0) h->cfg.first_iters = 10;
+    if (h->cfg.pdas_steps <= 0) h->cfg.pdas_steps = 10;
+    h->d = bmpc_make_dims(cfg->nx, cfg->nu, h->cfg.Np, h->cfg.Nc);
+    h->o = bmpc_make_off(h->d);
+    memset(&h->I, 0, sizeof(h->I)); memset(&h->stats, 0, sizeof(h->stats));
+    auto fail = [&](int code) { g_create_err = h->err; bmpc_destroy(h); return code; };
+    cudaError_t e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return fail(BMPC_ERR_CUDA); }
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "stream create failed"; return fail(BMPC_ERR_CUDA); }
+    h->stream = h->own_stream;
+    for (int i = 0; i < 4; i++) cudaEventCreate(&h->ev[i]);
+    int rc = configure_launch(h);
+    if (rc) return fail(rc);
+    const BmpcDims& d = h->d; size_t B = cfg->batch;
+    auto dalloc = [&](void** p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 8) == cudaSuccess; };
+    bool ok = true;
+    ok &= dalloc((void**)&h->sys, sizeof(double) * h->o.total);
+    ok &= dalloc((void**)&h->x0, sizeof(double) * B * d.nx);
+    ok &= dalloc((void**)&h->um1, sizeof(double) * B * d.nu);
+    ok &= dalloc((void**)&h->xref, sizeof(double) * B * d.NX);
+    ok &= dalloc((void**)&h->u0_own, sizeof(double) * B * d.nu);
+    ok &= dalloc((void**)&h->I.g, sizeof(double) * B * d.NU);
+    ok &= dalloc((void**)&h->I.cc, sizeof(double) * B * d.NX);
+    ok &= dalloc((void**)&h->I.xw, sizeof(double) * B * d.NU);
+    ok &= dalloc((void**)&h->I.vw, sizeof(double) * B * d.mc);
+    ok &= dalloc((void**)&h->I.Ua, sizeof(double) * B * d.NU);
+    ok &= dalloc((void**)&h->I.Us, sizeof(double) * B * d.NU);
+    ok &= dalloc((void**)&h->I.res, sizeof(double) * B * 4);
+    ok &= dalloc((void**)&h->I.status, sizeof(int32_t) * B);
+    ok &= dalloc((void**)&h->I.iters, sizeof(int32_t) * B);
+    ok &= dalloc((void**)&h->I.psteps, sizeof(int32_t) * B);
+    ok &= dalloc((void**)&h->listA, sizeof(int32_t) * B);
+    ok &= dalloc((void**)&h->listB, sizeof(int32_t) * B);
+    ok &= dalloc((void**)&h->counts, sizeof(int32_t) * 2);
+    if (!ok) { h->err = "cudaMalloc failed"; cudaGetLastError(); return fail(BMPC_ERR_CUDA); }
+    if (cudaHostAlloc((void**)&h->h_count, sizeof(int32_t) * 4, cudaHostAllocDefault) != cudaSuccess) { h->err = "cudaHostAlloc failed"; return fail(BMPC_ERR_CUDA); }
+    cudaMemset(h->sys, 0, sizeof(double) * h->o.total);
+    cudaMemset(h->x0, 0, sizeof(double) * B * d.nx);
+    cudaMemset(h->um1, 0, sizeof(double) * B * d.nu);
+    cudaMemset(h->xref, 0, sizeof(double) * B * d.NX);
+    cudaMemset(h->u0_own, 0, sizeof(double) * B * d.nu);
+    cudaMemset(h->I.Us, 0, sizeof(double) * B * d.NU);
+    cudaMemset(h->I.Ua, 0, sizeof(double) * B * d.NU);
+    h->I.x0 = h->x0; h->I.um1 = h->um1; h->I.xref = h->xref; h->I.u0 = h->u0_own;
+    k_reset<<<(int)((B + 255) / 256), 256, 0, h->stream>>>(h->I, (int)B);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "device initialisation failed"; return fail(BMPC_ERR_CUDA); }
+    *out = h;
+    return BMPC_OK;
+}
+
+void bmpc_destroy(bmpc_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    void* ptrs[] = {h->sys, h->x0, h->um1, h->xref, h->u0_own, h->I.g, h->I.cc, h->I.xw, h->I.vw, h->I.Ua, h->I.Us, h->I.res,
+                    h->I.status, h->I.iters, h->I.psteps, h->listA, h->listB, h->counts, h->seq_x, h->seq_e, h->seq_obj};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (h->h_count) cudaFreeHost(h->h_count);
+    for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int bmpc_set_stream(bmpc_handle* h, void* s) {
+    if (!h) return BMPC_ERR_ARG;
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return BMPC_OK;
+}
+
+int bmpc_synchronize(bmpc_handle* h) {
+    if (!h) return BMPC_ERR_ARG;
+    BMPC_CUDA(cudaSetDevice(h->cfg.device));
+    BMPC_CUDA(cudaStreamSynchronize(h->stream));
+    return BMPC_OK;
+}
+
+int bmpc_bind_output(bmpc_handle* h, double* dev_u0) {
+    if (!h) return BMPC_ERR_ARG;
+    h->u0_bound = dev_u0;
+    h->I.u0 = dev_u0 ? dev_u0 : h->u0_own;
+    return BMPC_OK;
+}
+
+int bmpc_get_dims(const bmpc_handle* h, int32_t* dims) {
+    if (!h || !dims) return BMPC_ERR_ARG;
+    dims[0] = h->d.nx; dims[1] = h->d.nu; dims[2] = h->d.Np; dims[3] = h->d.Nc; dims[4] = h->d.NX; dims[5] = h->d.NU;
+    dims[6] = h->d.mc; dims[7] = h->team;
+    return BMPC_OK;
+}
+
+int bmpc_setup(bmpc_handle* h, const double* Ad, const double* Bd, const double* Qx, const double* QxN, const double* Qu,
+               const double* QDu, const double* xmin, const double* xmax, const double* umin, const double* umax,
+               const double* Dumin, const double* Dumax, const double* uref) {
+    if (!h) return BMPC_ERR_ARG;
+    if (!Ad || !Bd || !Qx || !QxN || !Qu || !QDu || !xmin || !xmax || !umin || !umax || !Dumin || !Dumax || !uref) {
+        h->err = "bmpc_setup: null pointer"; return BMPC_ERR_ARG;
+    }
+    BMPC_CUDA(cudaSetDevice(h->cfg.device));
+    const BmpcDims& d = h->d; const BmpcSysOff& o = h->o;
+    std::vector<double> in(o.pw, 0.0);
+    auto put = [&](int off, const double* src, int cnt) { memcpy(in.data() + off, src, sizeof(double) * cnt); };
+    put(o.Ad, Ad, d.nx * d.nx); put(o.Bd, Bd, d.nx * d.nu); put(o.Qx, Qx, d.nx * d.nx); put(o.QxN, QxN, d.nx * d.nx);
+    put(o.Qu, Qu, d.nu * d.nu); put(o.QDu, QDu, d.nu * d.nu); put(o.xmin, xmin, d.nx); put(o.xmax, xmax, d.nx);
+    put(o.umin, umin, d.nu); put(o.umax, umax, d.nu); put(o.Dumin, Dumin, d.nu); put(o.Dumax, Dumax, d.nu); put(o.uref, uref, d.nu);
+    BMPC_CUDA(cudaMemcpyAsync(h->sys, in.data(), sizeof(double) * o.pw, cudaMemcpyHostToDevice, h->stream));
+    k_condense<<<1, 256, 0, h->stream>>>(d, o, h->sys, h->cfg.rho, h->cfg.sigma, h->cfg.alpha, h->cfg.eps_feas, h->cfg.soft_on);
+    BMPC_CUDA(cudaGetLastError());
+    double scal[BMPC_S_COUNT];
+    BMPC_CUDA(cudaMemcpyAsync(scal, h->sys + o.scal, sizeof(scal), cudaMemcpyDeviceToHost, h->stream));
+    BMPC_CUDA(cudaStreamSynchronize(h->stream));
+    if (scal[BMPC_S_ERR] != 0.0) {
+        h->err = "condensed Hessian is not positive definite (Qu/QDu/Qx make the QP non-strictly convex in U)";
+        return BMPC_ERR_NOT_PD;
+    }
+    // uminus1 default = uref for every instance (mpc.py:141); caller overrides through bmpc_update
+    h->is_setup = true; h->cold = true; h->solved = false;
+    return BMPC_OK;
+}
+
+int bmpc_update(bmpc_handle* h, const double* x0, const double* uminus1, const double* xref, int xref_rows, int on_device) {
+    if (!h) return BMPC_ERR_ARG;
+    if (!h->is_setup) { h->err = "bmpc_update before bmpc_setup"; return BMPC_ERR_STATE; }
+    BMPC_CUDA(cudaSetDevice(h->cfg.device));
+    const BmpcDims& d = h->d; size_t B = h->cfg.batch;
+    cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (x0) BMPC_CUDA(cudaMemcpyAsync(h->x0, x0, sizeof(double) * B * d.nx, kind, h->stream));
+    if (uminus1) BMPC_CUDA(cudaMemcpyAsync(h->um1, uminus1, sizeof(double) * B * d.nu, kind, h->stream));
+    if (xref) {
+        if (xref_rows != 1 && xref_rows != d.Np + 1) { h->err = "xref_rows must be 1 or Np+1"; return BMPC_ERR_ARG; }
+        h->xref_mode = xref_rows == 1 ? 0 : 1;
+        BMPC_CUDA(cudaMemcpyAsync(h->xref, xref, sizeof(double) * B * (h->xref_mode ? d.NX : d.nx), kind, h->stream));
+    }
+    return BMPC_OK;
+}
+
+static void launch_admm(bmpc_handle* h, const int32_t* list, int count, int niter, int do_prep) {
+    const int cold = h->cold ? 1 : 0;
+    if (h->team == 32) {
+        int grid = (count + h->wpb - 1) / h->wpb;
+        k_admm<true><<<grid, h->wpb * 32, h->smem_admm, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode);
+    } else {
+        k_admm<false><<<count, h->team, h->smem_admm, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode);
+    }
+    h->stats.launches++;
+}
+
+static void launch_polish(bmpc_handle* h, const int32_t* list, int count, int32_t* next_list, int32_t* next_count) {
+    if (h->team == 32) {
+        int grid = (count + h->wpb - 1) / h->wpb;
+        k_polish<true><<<grid, h->wpb * 32, h->smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0);
+    } else {
+        k_polish<false><<<count, h->team, h->smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0);
+    }
+    h->stats.launches++;
+}
+
+int bmpc_solve(bmpc_handle* h) {
+    if (!h) return BMPC_ERR_ARG;
+    if (!h->is_setup) { h->err = "bmpc_solve before bmpc_setup"; return BMPC_ERR_STATE; }
+    BMPC_CUDA(cudaSetDevice(h->cfg.device));
+    const int B = h->cfg.batch;
+    memset(&h->stats, 0, sizeof(h->stats));
+    k_reset<<<(B + 255) / 256, 256, 0, h->stream>>>(h->I, B);
+    h->stats.launches++;
+    const int32_t* list = nullptr; int count = B;
+    int32_t *cur = h->listA, *nxt = h->listB;
+    int total = 0, chunk = h->cfg.polish ? h->cfg.first_iters : 25, round = 0;
+    float ms_a = 0.f, ms_p = 0.f;
+    if (chunk > h->cfg.max_iter) chunk = h->cfg.max_iter;
+    while (count > 0 && total < h->cfg.max_iter) {
+        if (chunk > h->cfg.max_iter - total) chunk = h->cfg.max_iter - total;
+        BMPC_CUDA(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 2, h->stream));
+        BMPC_CUDA(cudaEventRecord(h->ev[0], h->stream));
+        launch_admm(h, list, count, chunk, round == 0 ? 1 : 0);
+        BMPC_CUDA(cudaEventRecord(h->ev[1], h->stream));
+        if (h->cfg.polish) launch_polish(h, list, count, nxt, h->counts);
+        else { k_check_converged<<<(count + 255) / 256, 256, 0, h->stream>>>(h->I, list, count, h->cfg.eps_abs, h->cfg.eps_rel, nxt, h->counts); h->stats.launches++; }
+        BMPC_CUDA(cudaEventRecord(h->ev[2], h->stream));
+        BMPC_CUDA(cudaMemcpyAsync(h->h_count, h->counts, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, h->stream));
+        BMPC_CUDA(cudaStreamSynchronize(h->stream));
+        BMPC_CUDA(cudaGetLastError());
+        float a = 0.f, p = 0.f;
+        cudaEventElapsedTime(&a, h->ev[0], h->ev[1]); cudaEventElapsedTime(&p, h->ev[1], h->ev[2]);
+        ms_a += a; ms_p += p;
+        h->stats.admm_iters += (int64_t)count * chunk;
+        total += chunk; round++;
+        h->cold = false;
+        count = h->h_count[0];
+        h->stats.polish_steps += h->h_count[1];
+        list = nxt; int32_t* tmp = cur; cur = nxt; nxt = tmp;
+        // polish mode: cumulative 10, 25, 50, 100, 200, ...; pure ADMM: OSQP's check_termination = 25
+        chunk = h->cfg.polish ? (total < 25 ? 25 - total : total) : 25;
+    }
+    if (!h->cfg.polish) {
+        // pure-ADMM mode: every instance gets its status from OSQP's criterion on its last residuals
+        k_finalize<<<(B + 127) / 128, 128, 0, h->stream>>>(h->d, h->o, h->sys, h->I, nullptr, B, h->cfg.eps_abs, h->cfg.eps_rel, h->I.u0);
+        h->stats.launches++;
+    } else if (count > 0) {
+        k_finalize<<<(count + 127) / 128, 128, 0, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->cfg.eps_abs, h->cfg.eps_rel, h->I.u0);
+        h->stats.launches++;
+    }
+    BMPC_CUDA(cudaGetLastError());
+    h->stats.rounds = round; h->stats.unsolved = h->cfg.polish ? count : -1; h->stats.ms_admm = ms_a; h->stats.ms_polish = ms_p;
+    h->solved = true;
+    return BMPC_OK;
+}
+
+int bmpc_output(bmpc_handle* h, double* u0, int32_t* status, int commit_uminus1, int on_device) {
+    if (!h) return BMPC_ERR_ARG;
+    if (!h->solved) { h->err = "bmpc_output before bmpc_solve"; return BMPC_ERR_STATE; }
+    BMPC_CUDA(cudaSetDevice(h->cfg.device));
+    const BmpcDims& d = h->d; size_t B = h->cfg.batch;
+    cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (commit_uminus1) BMPC_CUDA(cudaMemcpyAsync(h->um1, h->I.u0, sizeof(double) * B * d.nu, cudaMemcpyDeviceToDevice, h->stream));
+    if (u0 && u0 != h->I.u0) BMPC_CUDA(cudaMemcpyAsync(u0, h->I.u0, sizeof(double) * B * d.nu, kind, h->stream));
+    if (status) BMPC_CUDA(cudaMemcpyAsync(status, h->I.status, sizeof(int32_t) * B, kind, h->stream));
+    if (!on_device) BMPC_CUDA(cudaStreamSynchronize(h->stream));
+    return BMPC_OK;
+}
+
+int bmpc_get_sequences(bmpc_handle* h, double* u_seq, double* x_seq, double* eps_seq, double* obj_val, int32_t* iters) {
+    if (!h) return BMPC_ERR_ARG;
+    if (!h->solved) { h->err = "bmpc_get_sequences before bmpc_solve"; return BMPC_ERR_STATE; }
+    BMPC_CUDA(cudaSetDevice(h->cfg.device));
+    const BmpcDims& d = h->d; size_t B = h->cfg.batch;
+    if (x_seq || eps_seq || obj_val) {
+        if (!h->seq_x) {
+            BMPC_CUDA(cudaMalloc((void**)&h->seq_x, sizeof(double) * B * d.NX));
+            BMPC_CUDA(cudaMalloc((void**)&h->seq_e, sizeof(double) * B * d.NX));
+            BMPC_CUDA(cudaMalloc((void**)&h->seq_obj, sizeof(double) * B));
+        }
+        int wpb = 4;
+        k_sequences<<<(int)((B + wpb - 1) / wpb), wpb * 32, 0, h->stream>>>(d, h->o, h->sys, h->I, (int)B, h->xref_mode, h->seq_x, h->seq_e, h->seq_obj);
+        BMPC_CUDA(cudaGetLastError());
+        if (x_seq) BMPC_CUDA(cudaMemcpyAsync(x_seq, h->seq_x, sizeof(double) * B * d.NX, cudaMemcpyDeviceToHost, h->stream));
+        if (eps_seq) BMPC_CUDA(cudaMemcpyAsync(eps_seq, h->seq_e, sizeof(double) * B * d.NX, cudaMemcpyDeviceToHost, h->stream));
+        if (obj_val) BMPC_CUDA(cudaMemcpyAsync(obj_val, h->seq_obj, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (u_seq) BMPC_CUDA(cudaMemcpyAsync(u_seq, h->I.Us, sizeof(double) * B * d.NU, cudaMemcpyDeviceToHost, h->stream));
+    if (iters) BMPC_CUDA(cudaMemcpyAsync(iters, h->I.iters, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, h->stream));
+    BMPC_CUDA(cudaStreamSynchronize(h->stream));
+    return BMPC_OK;
+}
+
+int bmpc_get_stats(bmpc_handle* h, bmpc_stats* out) {
+    if (!h || !out) return BMPC_ERR_ARG;
+    *out = h->stats;    // host-side counters only: no device traffic, safe inside a timed region
+    return BMPC_OK;
+}
+
+int bmpc_get_sys(bmpc_handle* h, const char* name, double* out, int capacity) {
+    if (!h || !name || !out) return BMPC_ERR_ARG;
+    if (!h->is_setup) { h->err = "bmpc_get_sys before bmpc_setup"; return BMPC_ERR_STATE; }
+    BMPC_CUDA(cudaSetDevice(h->cfg.device));
+    const BmpcDims& d = h->d; const BmpcSysOff& o = h->o;
+    struct { const char* n; int off; int cnt; } tab[] = {
+        {"Bcal", o.Bcal, d.NX * d.NU}, {"Acal", o.Acal, d.NX * d.nx}, {"H", o.H, d.NU * d.NU}, {"Hinv", o.Hinv, d.NU * d.NU},
+        {"K", o.K, d.NU * d.NU}, {"Kinv", o.Kinv, d.NU * d.NU}, {"M", o.M, d.mc * d.mc}, {"AHinv", o.AHinv, d.mc * d.NU},
+        {"Gx0", o.Gx0, d.NU * d.nx}, {"Gref", o.Gref, d.NU * d.nx}, {"g0", o.g0, d.NU}, {"lo0", o.lo0, d.mc},
+        {"hi0", o.hi0, d.mc}, {"rho", o.rho, d.mc}, {"scal", o.scal, BMPC_S_COUNT}};
+    for (auto& e : tab) if (strcmp(e.n, name) == 0) {
+        if (capacity < e.cnt) { h->err = "bmpc_get_sys: buffer too small"; return BMPC_ERR_ARG; }
+        BMPC_CUDA(cudaMemcpyAsync(out, h->sys + e.off, sizeof(double) * e.cnt, cudaMemcpyDeviceToHost, h->stream));
+        BMPC_CUDA(cudaStreamSynchronize(h->stream));
+        return e.cnt;
+    }
+    h->err = std::string("bmpc_get_sys: unknown array ") + name;
+    return BMPC_ERR_ARG;
+}
+
+}  // extern "C"

@@ -25,8 +25,10 @@
 
 #ifdef BMPC_HOSTEMU
 #define BMPC_HD inline
+#define BMPC_HOSTDEV inline
 #else
 #define BMPC_HD __device__ __forceinline__
+#define BMPC_HOSTDEV __host__ __device__ __forceinline__
 #endif
 
 struct BmpcDims {
@@ -45,14 +47,14 @@ struct BmpcSysOff {
 // scal[] slots
 enum { BMPC_S_RHO = 0, BMPC_S_SIGMA, BMPC_S_ALPHA, BMPC_S_RHOE, BMPC_S_ERR, BMPC_S_TRH, BMPC_S_TRA, BMPC_S_COUNT = 8 };
 
-BMPC_HD BmpcDims bmpc_make_dims(int nx, int nu, int Np, int Nc) {
+BMPC_HOSTDEV BmpcDims bmpc_make_dims(int nx, int nu, int Np, int Nc) {
     BmpcDims d;
     d.nx = nx; d.nu = nu; d.Np = Np; d.Nc = Nc;
     d.NX = (Np + 1) * nx; d.NU = Nc * nu; d.ND = (Nc + 1) * nu; d.mc = d.NX + d.NU + d.ND;
     return d;
 }
 
-BMPC_HD BmpcSysOff bmpc_make_off(const BmpcDims& d) {
+BMPC_HOSTDEV BmpcSysOff bmpc_make_off(const BmpcDims& d) {
     BmpcSysOff o; int p = 0;
 #define BMPC_TAKE(f, cnt) o.f = p; p += (cnt)
     BMPC_TAKE(Ad, d.nx * d.nx); BMPC_TAKE(Bd, d.nx * d.nu); BMPC_TAKE(Qx, d.nx * d.nx); BMPC_TAKE(QxN, d.nx * d.nx);

@@ -1,0 +1,421 @@
+"""Batched drop-in for ``pyMPC.mpc.MPCController`` on B200 (host side, Python over ctypes).
+
+Mirrors the reference class (/root/reference/pyMPC/mpc.py:27-615): same constructor arguments,
+defaults, validation messages and method surface — ``setup()`` (mpc.py:254), ``output()`` (:271),
+``update()`` (:338), ``solve()`` (:366), ``__controller_function__`` (:377) — but every numerical
+step runs in hand-written CUDA kernels behind the C ABI of ``include/bmpc.h``:
+``_compute_QP_matrices_`` + ``OSQP.setup`` -> ``bmpc_setup`` (condense on device),
+``_update_QP_matrices_`` + ``OSQP.update`` -> ``bmpc_update``, ``OSQP.solve`` -> ``bmpc_solve``
+(ADMM + verified active-set polish), result slicing -> ``bmpc_output``.
+
+Batching (extension): ``batch=B`` runs B independent instances that share (Ad, Bd, weights,
+bounds) and differ in (x0, uminus1, xref).  With ``batch=None`` (default) the class behaves like
+the reference: 1-D inputs, 1-D ``output()``.
+
+There is no CPU fallback: constructing a controller without the CUDA library or without a GPU
+raises.  Unlike OSQP at its default tolerance the solver returns the exact QP minimiser (KKT
+verified), which is what parity at 1e-6 needs; ``eps_abs``/``eps_rel`` keep
+OSQP's meaning for instances the polish cannot verify, and in ``polish=False`` mode.
+"""
+import ctypes
+import types
+import warnings
+
+import numpy as np
+
+from . import _lib
+from ._lib import BmpcConfig, BmpcError, BmpcStats, PinnedArray, ptr
+
+_STATUS_STR = {1: "solved", 2: "solved", -2: "maximum iterations reached", -10: "unsolved"}
+
+
+def __is_vector__(vec):
+    # same acceptance rule as the reference helper (mpc.py:8-17)
+    if vec.ndim == 1:
+        return True
+    if vec.ndim == 2:
+        if vec.shape[0] == 1 or vec.shape[1] == 0:
+            return True
+    return False
+
+
+def __is_matrix__(mat):
+    return mat.ndim == 2
+
+
+def _dense(M):
+    return np.ascontiguousarray(M.toarray() if hasattr(M, "toarray") else M, dtype=float)
+
+
+class MPCController:
+    """Linear constrained MPC controller, batched on one B200.  Arguments as in the reference
+    (mpc.py:30-74), plus:
+
+    batch : int or None
+        Number of independent instances.  ``None``: reference behaviour (one instance, 1-D I/O).
+    device : int
+        CUDA device ordinal.
+    solver options (keyword only): ``rho`` (<=0: automatic), ``sigma``, ``alpha``, ``max_iter``,
+        ``first_iters``, ``pdas_steps``, ``polish``, ``team_threads``, ``warps_per_block``, ``rmax``.
+    """
+
+    def __init__(self, Ad, Bd, Np=20, Nc=None,
+                 x0=None, xref=None, uref=None, uminus1=None,
+                 Qx=None, QxN=None, Qu=None, QDu=None,
+                 xmin=None, xmax=None, umin=None, umax=None, Dumin=None, Dumax=None,
+                 eps_feas=1e6, eps_rel=1e-3, eps_abs=1e-3, batch=None, device=0, **solver_options):
+        Ad = np.asarray(Ad.toarray() if hasattr(Ad, "toarray") else Ad)
+        Bd = np.asarray(Bd.toarray() if hasattr(Bd, "toarray") else Bd)
+        if __is_matrix__(Ad) and (Ad.shape[0] == Ad.shape[1]):
+            self.Ad = Ad
+            self.nx = Ad.shape[0]
+        else:
+            raise ValueError("Ad should be a square matrix of dimension (nx,nx)!")
+        if __is_matrix__(Bd) and Bd.shape[0] == self.nx:
+            self.Bd = Bd
+            self.nu = Bd.shape[1]
+        else:
+            raise ValueError("Bd should be a matrix of dimension (nx, nu)!")
+        if Np > 1:
+            self.Np = Np
+        else:
+            raise ValueError("Np should be > 1!")
+        if Nc is not None:
+            if Nc <= Np:
+                self.Nc = Nc
+            else:
+                raise ValueError("Nc should be <= Np!")
+        else:
+            self.Nc = self.Np
+        self.batch = batch
+        self._B = 1 if batch is None else int(batch)
+        if self._B < 1:
+            raise ValueError("batch should be >= 1!")
+        nx, nu, B = self.nx, self.nu, self._B
+
+        # per-instance quantities: accepted exactly like the reference when unbatched (mpc.py:108-142),
+        # or with a leading batch dimension
+        self.x0 = self._vec_or_batch(x0, nx, "x0 should be an array of dimension (nx,)!", np.zeros(nx))
+        self.xref = self._xref_arg(xref)
+        if uref is not None:
+            uref = np.asarray(uref, dtype=float)
+            if __is_vector__(uref) and uref.size == nu:
+                self.uref = uref.ravel()
+            else:
+                raise ValueError("uref should be a vector of shape (nu,)!")
+        else:
+            self.uref = np.zeros(nu)
+        self.uminus1 = self._vec_or_batch(uminus1, nu, "uminus1 should be a vector of shape (nu,)!", self.uref)
+
+        def weight(Q, n, msg, default):
+            if Q is None:
+                return default
+            Qd = Q if hasattr(Q, "toarray") else np.asarray(Q)
+            if Qd.ndim == 2 and Qd.shape[0] == n and Qd.shape[1] == n:
+                return Q
+            raise ValueError(msg)
+        self.Qx = weight(Qx, nx, "Qx should be a matrix of shape (nx, nx)!", np.zeros((nx, nx)))   # zeros, not eye (mpc.py:150)
+        self.QxN = weight(QxN, nx, "QxN should be a square matrix of shape (nx, nx)!", self.Qx)
+        self.Qu = weight(Qu, nu, "Qu should be a square matrix of shape (nu, nu)!", np.zeros((nu, nu)))
+        self.QDu = weight(QDu, nu, "QDu should be a square matrix of shape (nu, nu)!", np.zeros((nu, nu)))
+
+        def bound(v, n, msg, default):
+            if v is None:
+                return default
+            v = np.asarray(v, dtype=float)
+            if __is_vector__(v) and v.size == n:
+                return v.ravel()
+            raise ValueError(msg)
+        inf = np.inf
+        self.xmin = bound(xmin, nx, "xmin should be a vector of shape (nx,)!", -np.ones(nx) * inf)
+        self.xmax = bound(xmax, nx, "xmax should be a vector of shape (nx,)!", np.ones(nx) * inf)
+        self.umin = bound(umin, nu, "umin should be a vector of shape (nu,)!", -np.ones(nu) * inf)
+        self.umax = bound(umax, nu, "umax should be a vector of shape (nu,)!", np.ones(nu) * inf)
+        self.Dumin = bound(Dumin, nu, "Dumin should be a vector of shape (nu,)!", -np.ones(nu) * inf)
+        self.Dumax = bound(Dumax, nu, "Dumax should be a vector of shape (nu,)!", np.ones(nu) * inf)
+
+        self.eps_feas = eps_feas
+        self.Qeps = eps_feas * np.eye(nx)
+        self.eps_rel = eps_rel
+        self.eps_abs = eps_abs
+        self.u_failure = self.uref
+
+        # hidden settings of the reference (mpc.py:233-238)
+        self.raise_error = False
+        self.JX_ON = True
+        self.JU_ON = True
+        self.JDU_ON = True
+        self.SOFT_ON = True
+        self.COMPUTE_J_CNST = False
+
+        self.device = int(device)
+        self.solver_options = dict(solver_options)
+        self._L = _lib.load()                      # raises if the CUDA extension is missing
+        self._h = None
+        self.res = None
+        self.x0_rh = None
+        self.uminus1_rh = None
+        self.J_CNST = None
+        self._pin = {}
+        self._status = None
+        self._u0 = None
+
+    # ------------------------------------------------------------------ argument helpers
+    def _vec_or_batch(self, v, n, msg, default):
+        if v is None:
+            return np.array(default, dtype=float, copy=True)
+        v = np.asarray(v, dtype=float)
+        if self.batch is not None and v.ndim == 2 and v.shape == (self._B, n):
+            return v
+        if __is_vector__(v) and v.size == n:
+            return v.ravel()
+        raise ValueError(msg)
+
+    def _xref_arg(self, xref):
+        nx, Np, B = self.nx, self.Np, self._B
+        if xref is None:
+            return np.zeros(nx)
+        xref = np.asarray(xref, dtype=float)
+        if self.batch is not None:
+            if xref.ndim == 3 and xref.shape[0] == B and xref.shape[2] == nx and xref.shape[1] >= Np:
+                return xref
+            if xref.ndim == 2 and xref.shape == (B, nx) and not (B >= Np and B == Np + 1):
+                return xref
+        if __is_vector__(xref) and xref.size == nx:
+            return xref.ravel()
+        if __is_matrix__(xref) and xref.shape[1] == nx and xref.shape[0] >= Np:
+            return xref                                         # same acceptance as mpc.py:120 (quirk Q6)
+        raise ValueError("xref should be either a vector of shape (nx,) or a matrix of shape (Np+1, nx)!")
+
+    def _xref_device_layout(self, xref):
+        """-> (array [B,nx] or [B,(Np+1)*nx], rows)"""
+        nx, Np, B = self.nx, self.Np, self._B
+        xref = np.asarray(xref, dtype=float)
+        if xref.ndim == 1:
+            return np.broadcast_to(xref, (B, nx)), 1
+        if xref.ndim == 3:
+            if xref.shape[1] != Np + 1:
+                raise ValueError("time-varying xref needs exactly Np+1 rows")   # the reference crashes here too (Q6)
+            return xref.reshape(B, (Np + 1) * nx), Np + 1
+        if self.batch is not None and xref.shape == (B, nx) and not xref.shape[0] == Np + 1:
+            return xref, 1
+        if xref.shape[0] >= Np + 1:
+            if xref.shape[0] != Np + 1:
+                raise ValueError("time-varying xref needs exactly Np+1 rows")
+            return np.broadcast_to(xref.reshape(1, -1), (B, (Np + 1) * nx)), Np + 1
+        raise ValueError("time-varying xref needs exactly Np+1 rows")
+
+    def _stage(self, name, arr, shape):
+        """copy into a pinned staging buffer (allocated once) and return it"""
+        pin = self._pin.get(name)
+        if pin is None or pin.array.shape != tuple(shape):
+            pin = PinnedArray(shape); self._pin[name] = pin
+        arr = np.asarray(arr)
+        if not (arr.shape == pin.array.shape and arr.ctypes.data == pin.array.ctypes.data):
+            np.copyto(pin.array, np.broadcast_to(arr, shape))
+        return pin.array
+
+    def pinned_buffer(self, name):
+        """Pinned host arrays the caller may fill in place and pass to update()/output() to avoid a staging
+        copy: 'x0' [B,nx], 'uminus1' [B,nu], 'xref' [B,nx], 'u' [B,nu] (output)."""
+        shapes = {"x0": (self._B, self.nx), "uminus1": (self._B, self.nu), "xref": (self._B, self.nx), "u": (self._B, self.nu)}
+        if name not in self._pin:
+            self._pin[name] = PinnedArray(shapes[name])
+        return self._pin[name].array
+
+    def _check(self, rc):
+        if rc < 0:
+            msg = self._L.bmpc_last_error(self._h)
+            raise BmpcError(f"libbmpc error {rc}: {msg.decode() if msg else ''}")
+        return rc
+
+    # ------------------------------------------------------------------ reference API
+    def setup(self, solve=True):
+        """Set up the QP (condense + factor on the GPU).  mpc.py:254-269."""
+        L = self._L
+        B, nx, nu = self._B, self.nx, self.nu
+        self.x0_rh = np.copy(self.x0)
+        self.uminus1_rh = np.copy(self.uminus1)
+        if self._h is not None:
+            L.bmpc_destroy(self._h); self._h = None
+        cfg = BmpcConfig(); L.bmpc_default_config(cfg)
+        cfg.nx, cfg.nu, cfg.Np, cfg.Nc, cfg.batch, cfg.device = nx, nu, self.Np, self.Nc, B, self.device
+        cfg.soft_on = 1 if self.SOFT_ON else 0
+        cfg.eps_feas = float(self.eps_feas)
+        # quirk Q1: the reference hands eps_rel to OSQP as eps_abs and vice versa (mpc.py:266)
+        cfg.eps_abs, cfg.eps_rel = float(self.eps_rel), float(self.eps_abs)
+        for k, v in self.solver_options.items():
+            if not hasattr(cfg, k):
+                raise TypeError(f"unknown solver option {k!r}")
+            setattr(cfg, k, v)
+        h = ctypes.c_void_p()
+        rc = L.bmpc_create(cfg, ctypes.byref(h))
+        if rc < 0:
+            msg = L.bmpc_last_error(None)
+            raise BmpcError(f"bmpc_create failed ({rc}): {msg.decode() if msg else ''}")
+        self._h = h
+        z = np.zeros
+        Qx = _dense(self.Qx) if self.JX_ON else z((nx, nx))
+        QxN = _dense(self.QxN) if self.JX_ON else z((nx, nx))
+        Qu = _dense(self.Qu) if self.JU_ON else z((nu, nu))
+        QDu = _dense(self.QDu) if self.JDU_ON else z((nu, nu))
+        args = [np.ascontiguousarray(a, dtype=float) for a in
+                (self.Ad, self.Bd, Qx, QxN, Qu, QDu, self.xmin, self.xmax, self.umin, self.umax, self.Dumin, self.Dumax, self.uref)]
+        self._check(L.bmpc_setup(self._h, *[ptr(a) for a in args]))
+        self._Qx_d, self._QxN_d, self._Qu_d, self._QDu_d = Qx, QxN, Qu, QDu
+        self._push(self.x0_rh, self.uminus1_rh, self.xref)
+        self._compute_J_CNST()
+        if solve:
+            self.solve()
+
+    def _push(self, x0, um1, xref):
+        B, nx, nu = self._B, self.nx, self.nu
+        px = pu = pr = None; rows = 1
+        if x0 is not None:
+            px = ptr(self._stage("x0", np.asarray(x0, dtype=float).reshape(-1, nx) if np.ndim(x0) > 1 else np.asarray(x0, dtype=float), (B, nx)))
+        if um1 is not None:
+            pu = ptr(self._stage("uminus1", np.asarray(um1, dtype=float).reshape(-1, nu) if np.ndim(um1) > 1 else np.asarray(um1, dtype=float), (B, nu)))
+        if xref is not None:
+            arr, rows = self._xref_device_layout(xref)
+            pr = ptr(self._stage("xref" if rows == 1 else "xref_tv", arr, arr.shape))
+        self._check(self._L.bmpc_update(self._h, px, pu, pr, rows, 0))
+
+    def update(self, x, u=None, xref=None, solve=True):
+        """New measurement (and optionally u_{-1}, xref); re-solve warm-started.  mpc.py:338-364."""
+        if self._h is None:
+            raise BmpcError("update() before setup()")
+        self.x0_rh = x
+        if u is not None:
+            self.uminus1_rh = u
+        if xref is not None:
+            self.xref = xref
+        # u=None: the device already holds the previously output control as uminus1 (committed by output(), Q9)
+        self._push(x, u, xref)
+        self._compute_J_CNST()
+        if solve:
+            self.solve()
+
+    def solve(self):
+        """Solve the QP batch.  mpc.py:366-375."""
+        self._check(self._L.bmpc_solve(self._h))
+        B, nu = self._B, self.nu
+        u = self._pin.get("u") or self._pin.setdefault("u", PinnedArray((B, nu)))
+        st = self._pin.get("status") or self._pin.setdefault("status", PinnedArray((B,), np.int32))
+        self._check(self._L.bmpc_output(self._h, ptr(u.array), ptr(st.array), 0, 0))
+        self._u0, self._status = u.array, st.array
+        self._make_res()
+        if np.any(self._status < 0):
+            warnings.warn('OSQP did not solve the problem!')
+            if self.raise_error:
+                raise ValueError('OSQP did not solve the problem!')
+
+    def _make_res(self):
+        info = types.SimpleNamespace()
+        if self.batch is None:
+            info.status_val = int(self._status[0]); info.status = _STATUS_STR.get(info.status_val, "unsolved")
+            info.polished = info.status_val == 1
+        else:
+            info.status_val = self._status
+            info.status = np.array([_STATUS_STR.get(int(s), "unsolved") for s in self._status]) if self._B <= 4096 else None
+            info.polished = self._status == 1
+        self.res = types.SimpleNamespace(info=info)
+
+    def output(self, return_x_seq=False, return_u_seq=False, return_eps_seq=False, return_status=False, return_obj_val=False):
+        """First optimal input (and optional info); commits it as the next u_{-1}.  mpc.py:271-336."""
+        if self._u0 is None:
+            raise BmpcError("output() before a solve")
+        B, nx, nu, Np, Nc = self._B, self.nx, self.nu, self.Np, self.Nc
+        # failed instances already carry u_failure = uref (written by the device epilogue, mpc.py:303-304)
+        uMPC = self._u0.copy()
+        info = {}
+        if return_x_seq or return_u_seq or return_eps_seq or return_obj_val:
+            useq = np.empty((B, Nc * nu)) if return_u_seq else None
+            xseq = np.empty((B, (Np + 1) * nx)) if return_x_seq else None
+            eseq = np.empty((B, (Np + 1) * nx)) if return_eps_seq else None
+            obj = np.empty(B) if return_obj_val else None
+            self._check(self._L.bmpc_get_sequences(self._h, ptr(useq), ptr(xseq), ptr(eseq), ptr(obj), None))
+            if return_x_seq:
+                info['x_seq'] = xseq.reshape(B, -1, nx) if self.batch is not None else xseq.reshape(-1, nx)
+            if return_u_seq:
+                info['u_seq'] = useq.reshape(B, -1, nu) if self.batch is not None else useq.reshape(-1, nu)
+            if return_eps_seq:
+                info['eps_seq'] = eseq.reshape(B, -1, nx) if self.batch is not None else eseq.reshape(-1, nx)
+            if return_obj_val:
+                val = obj + self.J_CNST
+                info['obj_val'] = val if self.batch is not None else float(val[0])
+        if return_status:
+            if self.batch is None:
+                info['status'] = self.res.info.status
+            else:
+                info['status'] = np.array([_STATUS_STR.get(int(s), "unsolved") for s in self._status])
+        # side effect of the reference: uminus1_rh = uMPC (mpc.py:330) — committed on the device as well
+        self._check(self._L.bmpc_output(self._h, None, None, 1, 0))
+        if self.batch is None:
+            uMPC = uMPC[0]
+        self.uminus1_rh = uMPC
+        if len(info) == 0:
+            return uMPC
+        return uMPC, info
+
+    def __controller_function__(self, x, u, xref=None):
+        """Debug helper of the reference (mpc.py:377-384)."""
+        self.update(x, u, xref=xref, solve=True)
+        return self.output()
+
+    # ------------------------------------------------------------------ extras
+    def _compute_J_CNST(self):
+        """Constant of the cost exactly as the reference accumulates it (mpc.py:412-442; quirk Q7)."""
+        B, Np = self._B, self.Np
+        J = np.zeros(B)
+        uref = self.uref
+        um1 = np.broadcast_to(np.asarray(self.uminus1_rh, dtype=float).reshape(-1, self.nu), (B, self.nu))
+        if self.JX_ON and self.COMPUTE_J_CNST:
+            arr, rows = self._xref_device_layout(self.xref)
+            if rows == 1:
+                xr = np.asarray(arr)
+                J += 0.5 * Np * np.einsum('bi,ij,bj->b', xr, self._QxN_d, xr) + 0.5 * np.einsum('bi,ij,bj->b', xr, self._QxN_d, xr)
+            else:
+                xr = np.asarray(arr).reshape(B, Np + 1, self.nx)
+                J += 0.5 * np.einsum('bki,ij,bkj->b', xr[:, :Np], self._Qx_d, xr[:, :Np]) + \
+                    0.5 * np.einsum('bi,ij,bj->b', xr[:, Np], self._QxN_d, xr[:, Np])
+        if self.JU_ON:
+            J += 0.5 * Np * (uref @ (self._Qu_d @ uref))
+        if self.JDU_ON:
+            J += 0.5 * np.einsum('bi,ij,bj->b', um1, self._QDu_d, um1)
+        self.J_CNST = J if self.batch is not None else float(J[0])
+
+    def stats(self):
+        """Counters of the last solve (ADMM iterations, rounds, device time of the kernels)."""
+        s = BmpcStats()
+        self._check(self._L.bmpc_get_stats(self._h, ctypes.byref(s)))
+        return {f: getattr(s, f) for f, _ in BmpcStats._fields_ if f != "reserved"}
+
+    def iterations(self):
+        it = np.empty(self._B, np.int32)
+        self._check(self._L.bmpc_get_sequences(self._h, None, None, None, None, ptr(it)))
+        return it
+
+    def condensed(self, name):
+        """Export one array of the condensed system computed on the device (parity tests)."""
+        dims = np.zeros(8, np.int32); self._L.bmpc_get_dims(self._h, ptr(dims))
+        nx, nu, Np, Nc, NX, NU, mc, _ = [int(v) for v in dims]
+        shapes = {"Bcal": (NX, NU), "Acal": (NX, nx), "H": (NU, NU), "Hinv": (NU, NU), "K": (NU, NU), "Kinv": (NU, NU),
+                  "M": (mc, mc), "AHinv": (mc, NU), "Gx0": (NU, nx), "Gref": (NU, nx), "g0": (NU,), "lo0": (mc,),
+                  "hi0": (mc,), "rho": (mc,), "scal": (8,)}
+        out = np.empty(shapes[name])
+        self._check(self._L.bmpc_get_sys(self._h, name.encode(), ptr(out), out.size))
+        return out
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self._L.bmpc_destroy(self._h); self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

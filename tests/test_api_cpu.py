@@ -1,0 +1,83 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol of include/bmpc.h, fails loudly
+without a device, and the Python mirror validates its arguments like the reference."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from pympc_b200 import _lib
+from pympc_b200.workloads import point_mass, pendulum
+
+
+def test_library_exports_every_declared_symbol(bmpc_lib):
+    header = open(os.path.join(ROOT, "include", "bmpc.h")).read()
+    declared = set(re.findall(r"\b(bmpc_[a-z_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(bmpc_lib, name)
+
+
+def test_config_struct_layout_matches_defaults(bmpc_lib):
+    c = _lib.BmpcConfig(); bmpc_lib.bmpc_default_config(c)
+    assert (c.Np, c.max_iter, c.first_iters, c.pdas_steps, c.polish, c.soft_on) == (20, 4000, 10, 10, 1, 1)
+    assert (c.eps_feas, c.sigma, c.alpha, c.eps_abs, c.eps_rel) == (1e6, 1e-6, 1.6, 1e-3, 1e-3)
+
+
+def test_create_argument_errors(bmpc_lib):
+    c = _lib.BmpcConfig(); bmpc_lib.bmpc_default_config(c)
+    h = ctypes.c_void_p()
+    c.nx, c.nu, c.Np = 0, 1, 20
+    assert bmpc_lib.bmpc_create(c, ctypes.byref(h)) == -1
+    c.nx, c.Np, c.Nc = 2, 5, 9
+    assert bmpc_lib.bmpc_create(c, ctypes.byref(h)) == -1
+    assert b"invalid dimensions" in bmpc_lib.bmpc_last_error(None)
+
+
+def test_no_cpu_fallback_without_device(bmpc_lib):
+    if bmpc_lib.bmpc_device_count() > 0:
+        pytest.skip("a GPU is visible here")
+    from pympc_b200 import MPCController, BmpcError
+    K = MPCController(**point_mass())
+    with pytest.raises(BmpcError, match="no CUDA device"):
+        K.setup()
+
+
+@pytest.mark.parametrize("kw,msg", [
+    (dict(Ad=np.zeros((2, 3))), "Ad should be a square matrix"),
+    (dict(Bd=np.zeros((3, 1))), "Bd should be a matrix of dimension"),
+    (dict(Np=1), "Np should be > 1"),
+    (dict(Nc=21), "Nc should be <= Np"),
+    (dict(x0=np.zeros(3)), "x0 should be an array of dimension"),
+    (dict(xref=np.zeros((3, 2))), "xref should be either a vector"),
+    (dict(uref=np.zeros(2)), "uref should be a vector"),
+    (dict(uminus1=np.zeros(2)), "uminus1 should be a vector"),
+    (dict(Qx=np.zeros((3, 3))), "Qx should be a matrix"),
+    (dict(QxN=np.zeros((3, 3))), "QxN should be a square matrix"),
+    (dict(Qu=np.zeros((2, 2))), "Qu should be a square matrix"),
+    (dict(QDu=np.zeros((2, 2))), "QDu should be a square matrix"),
+    (dict(xmin=np.zeros(3)), "xmin should be a vector"),
+    (dict(xmax=np.zeros(3)), "xmax should be a vector"),
+    (dict(umin=np.zeros(2)), "umin should be a vector"),
+    (dict(umax=np.zeros(2)), "umax should be a vector"),
+    (dict(Dumin=np.zeros(2)), "Dumin should be a vector"),
+    (dict(Dumax=np.zeros(2)), "Dumax should be a vector"),
+])
+def test_constructor_validation_like_reference(kw, msg, bmpc_lib):
+    from pympc_b200 import MPCController
+    cfg = point_mass(); cfg.update(kw)
+    with pytest.raises(ValueError, match=msg):
+        MPCController(**cfg)
+
+
+def test_defaults_like_reference(bmpc_lib):
+    from pympc_b200 import MPCController
+    cfg = pendulum()
+    K = MPCController(cfg["Ad"], cfg["Bd"])
+    assert K.Np == 20 and K.Nc == 20 and np.all(K.Qx == 0) and K.QxN is K.Qx          # quirk Q3: zeros, not eye
+    assert np.all(np.isinf(K.xmin)) and np.all(K.uminus1 == K.uref) and K.eps_feas == 1e6
+    assert (K.raise_error, K.JX_ON, K.JU_ON, K.JDU_ON, K.SOFT_ON, K.COMPUTE_J_CNST) == (False, True, True, True, True, False)
+    Kb = MPCController(cfg["Ad"], cfg["Bd"], batch=5, x0=np.zeros((5, 4)), xref=np.ones((5, 4)))
+    assert Kb.x0.shape == (5, 4) and Kb._xref_device_layout(Kb.xref)[1] == 1

@@ -1,0 +1,83 @@
+"""CPU checks of the DEVICE numerical core compiled for the host with a one-thread team
+(tests/hostemu).  Catches index/algorithm errors without a GPU; parallel hazards are covered by the
+-m gpu parity tests.  The emulation library is test infrastructure and is never loaded by pympc_b200."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from emu import EmuSystem
+from oracle.qp_assembly import QPData
+from pympc_b200.workloads import point_mass, pendulum, mimo
+
+CASES = {"pm": point_mass, "pend": pendulum, "mimo": mimo}
+
+
+def condensed_numpy(Q):
+    """dense condensed operators from the oracle QP (eliminating X through the dynamics rows)"""
+    NX, NU = Q.NX, Q.NU
+    Ax = Q.A[:NX, :NX]; Bu = Q.A[:NX, NX:NX + NU]
+    Bcal = -np.linalg.solve(Ax, Bu)
+    H = Bcal.T @ Q.P[:NX, :NX] @ Bcal + Q.P[NX:NX + NU, NX:NX + NU]
+    D = Q.A[2 * NX + NU:, NX:NX + NU]
+    A = np.vstack([Bcal, np.eye(NU), D])
+    return Bcal, H, A
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_condense_matches_numpy(name):
+    cfg = CASES[name](); Q = QPData(**cfg); E = EmuSystem(cfg)
+    Bcal, H, A = condensed_numpy(Q)
+    rel = lambda a, b: np.max(np.abs(a - b)) / max(1.0, np.max(np.abs(b)))
+    assert rel(E.get("Bcal", Bcal.shape), Bcal) < 1e-12
+    assert rel(E.get("H", H.shape), H) < 1e-12
+    assert rel(E.get("Hinv", H.shape), np.linalg.inv(H)) < 1e-9
+    rho = E.get("rho", (E.mc,))
+    K = H + 1e-6 * np.eye(Q.NU) + A.T @ (rho[:, None] * A)
+    assert rel(E.get("Kinv", H.shape), np.linalg.inv(K)) < 1e-9
+    assert rel(E.get("M", (E.mc, E.mc)), A @ np.linalg.inv(H) @ A.T) < 1e-9
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_first_solve_matches_golden(name):
+    cfg = CASES[name](); g = golden(f"{name}_first.npz"); E = EmuSystem(cfg)
+    U, st, it, ps, res = E.solve(cfg["x0"], cfg["uminus1"], cfg["xref"])
+    assert st == 1
+    assert np.max(np.abs(U - g["u_seq"])) < 1e-7
+
+
+@pytest.mark.parametrize("name,steps", [("pm", 30), ("pend", 40), ("mimo", 6)])
+def test_closed_loop_matches_golden(name, steps):
+    cfg = CASES[name](); g = golden(f"{name}_loop.npz"); E = EmuSystem(cfg)
+    x = np.array(cfg["x0"], float); um1 = np.array(cfg["uminus1"], float)
+    for t in range(steps):
+        U, st, it, ps, res = E.solve(x, um1, cfg["xref"])
+        assert st == 1
+        u0 = U[:E.nu]
+        assert np.max(np.abs(u0 - g["u"][t])) < 1e-6, (t, u0, g["u"][t])
+        x = cfg["Ad"] @ x + cfg["Bd"] @ u0; um1 = u0
+
+
+def test_variants_match_golden():
+    g = golden("variants.npz")
+    c = point_mass(); c["Np"] = 25; c["Nc"] = 10; c["uref"] = np.array([0.1])
+    c["xmin"] = np.array([-10.0, -10.0]); c["xmax"] = np.array([7.0, 10.0])
+    E = EmuSystem(c); U, st, *_ = E.solve(c["x0"], c["uminus1"], g["a_xref"])
+    assert st == 1 and np.max(np.abs(U - g["a_z"][26 * 2:26 * 2 + 10])) < 1e-7
+    c = mimo(); c["Np"] = 12; c["Nc"] = 5; c["x0"] = np.array([0.3, -0.2, 0.1, 0.0, -0.4, 0.2, 0.0, 0.1])
+    c["umin"] = -0.5 * np.ones(4); c["umax"] = 0.5 * np.ones(4); c["Qu"] = 0.1 * np.eye(4)
+    E = EmuSystem(c); U, st, *_ = E.solve(c["x0"], c["uminus1"], c["xref"])
+    assert st == 1 and np.max(np.abs(U - g["b_z"][13 * 8:13 * 8 + 20])) < 1e-7
+    c = pendulum(); c["x0"] = np.array([0.45, 0.3, -0.05, 0.1])
+    E = EmuSystem(c); U, st, *_ = E.solve(c["x0"], c["uminus1"], c["xref"])
+    assert st == 1 and np.max(np.abs(U - g["c_z"][84:104])) < 1e-7
+
+
+def test_random_batch_matches_golden():
+    g = golden("pend_rand.npz"); cfg = pendulum()
+    for b in range(g["X0"].shape[0]):
+        E = EmuSystem(cfg)
+        x = g["X0"][b].copy(); um1 = np.zeros(1)
+        for t in range(g["U"].shape[0]):
+            U, st, *_ = E.solve(x, um1, g["Xref"][b])
+            assert st == 1 and abs(U[0] - g["U"][t, b, 0]) < 1e-6
+            x = cfg["Ad"] @ x + cfg["Bd"] @ U[:1]; um1 = U[:1]
