@@ -51,6 +51,7 @@ typedef struct {
     int32_t polish;             /* 1 = ADMM + polish (exact), 0 = pure ADMM to eps (OSQP-like) */
     int32_t team_threads;       /* 0 = auto; 32 = one warp per instance; >32 = one CTA of that size per instance */
     int32_t warps_per_block;    /* 0 = auto (warp team only) */
+    int32_t fast_path;          /* 1 = use the thread-per-instance kernels when the shape has one (default), 0 = team kernels only */
     double eps_feas;            /* slack weight (mpc.py:226) */
     double rho;                 /* <= 0: automatic sqrt(trace H / trace A'A) */
     double sigma, alpha;        /* OSQP defaults 1e-6, 1.6 */

@@ -16,6 +16,7 @@
 
 #include "../../include/bmpc.h"
 #include "bmpc_core.cuh"
+#include "bmpc_tpi.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // teams
@@ -273,6 +274,108 @@ __global__ void k_sequences(BmpcDims d, BmpcSysOff o, const double* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// TPI fast path (bmpc_tpi.cuh): one thread per instance, one warp (32 instances) per CTA.
+// The iterate travels between global [inst][mc] and shared [row][lane] through a coalesced transpose.
+constexpr int TPI_STR = 33;   // padded lane stride of the shared-memory columns
+
+template <class S>
+__device__ __forceinline__ void tpi_load_v(const BmpcInst& I, int inst0, int nvalid, double* smem, int row_off) {
+    const double* src = I.vw + (size_t)inst0 * S::mc;
+    for (int idx = threadIdx.x; idx < nvalid * S::mc; idx += 32) {
+        int t = idx / S::mc, i = idx - t * S::mc;
+        if (i >= S::nx) smem[(row_off + i - S::nx) * TPI_STR + t] = src[idx];
+    }
+}
+
+template <class S>
+__global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmmParams<S> P, BmpcInst I, int B, int niter, int cold) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x, inst0 = blockIdx.x * 32, inst = inst0 + lane;
+    const int nvalid = (B - inst0) < 32 ? (B - inst0) : 32;
+    const bool valid = lane < nvalid;
+    if (!cold) { tpi_load_v<S>(I, inst0, nvalid, smem, 0); __syncwarp(); }
+    double x0[S::nx], um1[S::nu], xref[S::nx], x[S::NU];
+#pragma unroll
+    for (int q = 0; q < S::nx; q++) { x0[q] = valid ? I.x0[(size_t)inst * S::nx + q] : 0.0; xref[q] = valid ? I.xref[(size_t)inst * S::nx + q] : 0.0; }
+#pragma unroll
+    for (int q = 0; q < S::nu; q++) um1[q] = valid ? I.um1[(size_t)inst * S::nu + q] : 0.0;
+#pragma unroll
+    for (int a = 0; a < S::NU; a++) x[a] = (valid && !cold) ? I.xw[(size_t)inst * S::NU + a] : 0.0;
+    TpiAcc V{smem + lane, TPI_STR};
+    if (valid) tpi_admm<S>(P, V, x0, um1, xref, x, niter, cold != 0);
+    __syncwarp();
+    double* dst = I.vw + (size_t)inst0 * S::mc;
+    for (int idx = lane; idx < nvalid * S::mc; idx += 32) {
+        int t = idx / S::mc, i = idx - t * S::mc;
+        dst[idx] = (i >= S::nx) ? smem[(i - S::nx) * TPI_STR + t] : I.x0[(size_t)(inst0 + t) * S::nx + i];
+    }
+    if (valid) {
+#pragma unroll
+        for (int a = 0; a < S::NU; a++) { I.xw[(size_t)inst * S::NU + a] = x[a]; I.Ua[(size_t)inst * S::NU + a] = x[a]; }
+        I.iters[inst] += niter;
+    }
+}
+
+template <class S>
+__global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiPolishParams<S> P, BmpcInst I, int B, int max_steps,
+                                                   int32_t* next_list, int32_t* next_count, double* u0_out) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x, inst0 = blockIdx.x * 32, inst = inst0 + lane;
+    const int nvalid = (B - inst0) < 32 ? (B - inst0) : 32;
+    const bool valid = lane < nvalid;
+    tpi_load_v<S>(I, inst0, nvalid, smem, 0);
+    __syncwarp();
+    double x0[S::nx], um1[S::nu], xref[S::nx], g[S::NU], U[S::NU];
+#pragma unroll
+    for (int q = 0; q < S::nx; q++) { x0[q] = valid ? I.x0[(size_t)inst * S::nx + q] : 0.0; xref[q] = valid ? I.xref[(size_t)inst * S::nx + q] : 0.0; }
+#pragma unroll
+    for (int q = 0; q < S::nu; q++) um1[q] = valid ? I.um1[(size_t)inst * S::nu + q] : 0.0;
+    TpiAcc W{smem + lane, TPI_STR};
+    const TpiCommon<S>& c = P.c;
+    int ps = 0;
+    if (valid) {
+        tpi_linear_term<S>(c, x0, um1, xref, g);
+        TpiMask up, dn;
+#pragma unroll
+        for (int i = 0; i < S::MT; i++) {
+            double lo, hi; tpi_row_bounds<S>(c, um1, i, lo, hi);
+            const double vi = W(i);
+            up.set(i, vi > hi + 1e-9 * (1.0 + fabs(hi))); dn.set(i, vi < lo - 1e-9 * (1.0 + fabs(lo)));
+        }
+        ps = tpi_polish<S>(P, W, x0, um1, g, up, dn, U, max_steps);
+        if (ps > 0) {
+            TpiMask act; act.w[0] = up.w[0] | dn.w[0]; act.w[1] = up.w[1] | dn.w[1];
+            // exact ADMM fixed point v* = z* + y*/rho staged at rows [S0, S0+MT) (the S block is dead, mu is not)
+            tpi_rows_of<S>(c, x0, U, [&](int i, double zi) {
+                const double mu = act.get(i) ? W(tpi_rank(act, i)) : 0.0;
+                const double rho = i < S::NS ? c.rhox[i % S::nx] : (i < S::NS + S::NU ? c.rhou[(i - S::NS) % S::nu] : c.rhod[(i - S::NS - S::NU) % S::nu]);
+                W(S::S0 + i) = zi + mu / rho;
+            });
+#pragma unroll
+            for (int a = 0; a < S::NU; a++) { I.Us[(size_t)inst * S::NU + a] = U[a]; I.xw[(size_t)inst * S::NU + a] = U[a]; }
+#pragma unroll
+            for (int q = 0; q < S::nu; q++) u0_out[(size_t)inst * S::nu + q] = U[q];
+            I.status[inst] = BMPC_SOLVED; I.psteps[inst] += ps;
+            atomicAdd(next_count + 1, ps);
+        } else {
+            const int used = ps < 0 ? 1 : max_steps;
+            I.psteps[inst] += used; atomicAdd(next_count + 1, used);
+            next_list[atomicAdd(next_count, 1)] = inst;
+        }
+    }
+    const unsigned okmask = __ballot_sync(0xffffffffu, ps > 0);
+    __syncwarp();
+    double* dst = I.vw + (size_t)inst0 * S::mc;
+    for (int idx = lane; idx < nvalid * S::mc; idx += 32) {
+        int t = idx / S::mc, i = idx - t * S::mc;
+        if ((okmask >> t) & 1u) dst[idx] = (i >= S::nx) ? smem[(S::S0 + i - S::nx) * TPI_STR + t] : I.x0[(size_t)(inst0 + t) * S::nx + i];
+    }
+}
+
+using TpiPend = TpiShape<4, 1, 20, 20>;
+using TpiPm = TpiShape<2, 1, 20, 20>;
+
+// ------------------------------------------------------------------------------------------------
 // host side
 struct bmpc_handle {
     bmpc_config cfg;
@@ -294,6 +397,9 @@ struct bmpc_handle {
     bmpc_stats stats;
     std::string err;
     size_t smem_admm = 0, smem_polish = 0;
+    int tpi_kind = 0;                  // 0 none, 1 pendulum shape (4,1,20,20), 2 point-mass shape (2,1,20,20)
+    void *tpi_admm_params = nullptr, *tpi_polish_params = nullptr;   // host copies of the parameter blocks
+    int tpi_pdas_steps = 6;
 };
 
 static std::string g_create_err;
@@ -307,13 +413,23 @@ static std::string g_create_err;
         }                                                                                          \
     } while (0)
 
+template <class S>
+static void launch_tpi_round(bmpc_handle* h, int B, int niter, cudaEvent_t mid) {
+    const int grid = (B + 31) / 32;
+    k_tpi_admm<S><<<grid, 32, S::MT * TPI_STR * 8, h->stream>>>(*(const TpiAdmmParams<S>*)h->tpi_admm_params, h->I, B, niter, h->cold ? 1 : 0);
+    cudaEventRecord(mid, h->stream);
+    k_tpi_polish<S><<<grid, 32, S::PROWS * TPI_STR * 8, h->stream>>>(*(const TpiPolishParams<S>*)h->tpi_polish_params, h->I, B,
+                                                                     h->tpi_pdas_steps, h->listB, h->counts, h->I.u0);
+    h->stats.launches += 2;
+}
+
 extern "C" {
 
 void bmpc_default_config(bmpc_config* c) {
     memset(c, 0, sizeof(*c));
     c->Np = 20; c->Nc = 0; c->batch = 1; c->device = 0; c->soft_on = 1;
     c->max_iter = 4000; c->first_iters = 10; c->pdas_steps = 10; c->rmax = 0; c->polish = 1;
-    c->team_threads = 0; c->warps_per_block = 0;
+    c->team_threads = 0; c->warps_per_block = 0; c->fast_path = 1;
     c->eps_feas = 1e6; c->rho = 0.0; c->sigma = 1e-6; c->alpha = 1.6; c->eps_abs = 1e-3; c->eps_rel = 1e-3;
 }
 
@@ -437,6 +553,7 @@ void bmpc_destroy(bmpc_handle* h) {
                     h->I.status, h->I.iters, h->I.psteps, h->listA, h->listB, h->counts, h->seq_x, h->seq_e, h->seq_obj};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_count) cudaFreeHost(h->h_count);
+    free(h->tpi_admm_params); free(h->tpi_polish_params);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -493,10 +610,37 @@ int bmpc_setup(bmpc_handle* h, const double* Ad, const double* Bd, const double*
         h->err = "condensed Hessian is not positive definite (Qu/QDu/Qx make the QP non-strictly convex in U)";
         return BMPC_ERR_NOT_PD;
     }
+    // thread-per-instance fast path for the compiled small shapes (pendulum, point mass)
+    h->tpi_kind = 0;
+    if (h->cfg.fast_path && h->team == 32) {
+        if (d.nx == 4 && d.nu == 1 && d.Np == 20 && d.Nc == 20) h->tpi_kind = 1;
+        else if (d.nx == 2 && d.nu == 1 && d.Np == 20 && d.Nc == 20) h->tpi_kind = 2;
+    }
+    if (h->tpi_kind) {
+        std::vector<double> hs(o.total);
+        BMPC_CUDA(cudaMemcpyAsync(hs.data(), h->sys, sizeof(double) * o.total, cudaMemcpyDeviceToHost, h->stream));
+        BMPC_CUDA(cudaStreamSynchronize(h->stream));
+        free(h->tpi_admm_params); free(h->tpi_polish_params);
+        if (h->tpi_kind == 1) {
+            auto* pa = (TpiAdmmParams<TpiPend>*)malloc(sizeof(TpiAdmmParams<TpiPend>)); tpi_fill_admm<TpiPend>(hs.data(), o, *pa);
+            auto* pp = (TpiPolishParams<TpiPend>*)malloc(sizeof(TpiPolishParams<TpiPend>)); tpi_fill_polish<TpiPend>(hs.data(), o, h->sys, *pp);
+            h->tpi_admm_params = pa; h->tpi_polish_params = pp;
+            BMPC_CUDA(cudaFuncSetAttribute(k_tpi_admm<TpiPend>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TpiPend::MT * TPI_STR * 8)));
+            BMPC_CUDA(cudaFuncSetAttribute(k_tpi_polish<TpiPend>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TpiPend::PROWS * TPI_STR * 8)));
+        } else {
+            auto* pa = (TpiAdmmParams<TpiPm>*)malloc(sizeof(TpiAdmmParams<TpiPm>)); tpi_fill_admm<TpiPm>(hs.data(), o, *pa);
+            auto* pp = (TpiPolishParams<TpiPm>*)malloc(sizeof(TpiPolishParams<TpiPm>)); tpi_fill_polish<TpiPm>(hs.data(), o, h->sys, *pp);
+            h->tpi_admm_params = pa; h->tpi_polish_params = pp;
+            BMPC_CUDA(cudaFuncSetAttribute(k_tpi_admm<TpiPm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TpiPm::MT * TPI_STR * 8)));
+            BMPC_CUDA(cudaFuncSetAttribute(k_tpi_polish<TpiPm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TpiPm::PROWS * TPI_STR * 8)));
+        }
+    }
     // uminus1 default = uref for every instance (mpc.py:141); caller overrides through bmpc_update
     h->is_setup = true; h->cold = true; h->solved = false;
     return BMPC_OK;
 }
+
+
 
 int bmpc_update(bmpc_handle* h, const double* x0, const double* uminus1, const double* xref, int xref_rows, int on_device) {
     if (!h) return BMPC_ERR_ARG;
@@ -547,14 +691,24 @@ int bmpc_solve(bmpc_handle* h) {
     int32_t *cur = h->listA, *nxt = h->listB;
     int total = 0, chunk = h->cfg.polish ? h->cfg.first_iters : 25, round = 0;
     float ms_a = 0.f, ms_p = 0.f;
+    bool need_prep = true;
     if (chunk > h->cfg.max_iter) chunk = h->cfg.max_iter;
     while (count > 0 && total < h->cfg.max_iter) {
         if (chunk > h->cfg.max_iter - total) chunk = h->cfg.max_iter - total;
         BMPC_CUDA(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 2, h->stream));
         BMPC_CUDA(cudaEventRecord(h->ev[0], h->stream));
-        launch_admm(h, list, count, chunk, round == 0 ? 1 : 0);
-        BMPC_CUDA(cudaEventRecord(h->ev[1], h->stream));
-        if (h->cfg.polish) launch_polish(h, list, count, nxt, h->counts);
+        const bool tpi = round == 0 && h->tpi_kind && h->cfg.polish && h->xref_mode == 0;
+        if (tpi) {
+            // fast path: every instance, first_iters ADMM iterations + polish; unfinished ones go to listB (= nxt)
+            if (h->tpi_kind == 1) launch_tpi_round<TpiPend>(h, B, chunk, h->ev[1]);
+            else launch_tpi_round<TpiPm>(h, B, chunk, h->ev[1]);
+        } else {
+            launch_admm(h, list, count, chunk, need_prep ? 1 : 0);
+            need_prep = false;
+            BMPC_CUDA(cudaEventRecord(h->ev[1], h->stream));
+        }
+        if (tpi) {}
+        else if (h->cfg.polish) launch_polish(h, list, count, nxt, h->counts);
         else { k_check_converged<<<(count + 255) / 256, 256, 0, h->stream>>>(h->I, list, count, h->cfg.eps_abs, h->cfg.eps_rel, nxt, h->counts); h->stats.launches++; }
         BMPC_CUDA(cudaEventRecord(h->ev[2], h->stream));
         BMPC_CUDA(cudaMemcpyAsync(h->h_count, h->counts, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, h->stream));

@@ -451,7 +451,8 @@ BMPC_HD int bmpc_polish(Team& t, const BmpcDims& d, const BmpcSysOff& o, const d
         for (int b = 0; b < NU; b++) acc -= row[b] * g[b];
         W0[i] = acc;
         double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
-        st[i] = v[i] > hi ? 1 : (v[i] < lo ? 2 : 0);
+        // rows sitting on a bound to rounding level (steady state at xref = xmax, say) stay out of the first guess
+        st[i] = v[i] > hi + 1e-9 * (1.0 + fabs(hi)) ? 1 : (v[i] < lo - 1e-9 * (1.0 + fabs(lo)) ? 2 : 0);
     }
     t.sync();
 
@@ -537,7 +538,7 @@ BMPC_HD int bmpc_polish(Team& t, const BmpcDims& d, const BmpcSysOff& o, const d
             double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
             int s = st[i], ns; double zi = zz[i];
             if (soft_on && i < NX) {
-                ns = zi > hi ? 1 : (zi < lo ? 2 : 0);
+                ns = zi > hi + 1e-11 * (1.0 + fabs(hi)) ? 1 : (zi < lo - 1e-11 * (1.0 + fabs(lo)) ? 2 : 0);
                 if (ns != s) {
                     // tolerated only if the row sits on the boundary the two labels disagree about
                     bool same_hi = (s == 1 || ns == 1) && !(s == 2 || ns == 2);

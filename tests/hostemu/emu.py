@@ -15,9 +15,10 @@ _NAMES = ["Ad", "Bd", "Qx", "QxN", "Qu", "QDu", "xmin", "xmax", "umin", "umax", 
 def build():
     src = os.path.join(_HERE, "hostemu.cpp")
     core = os.path.join(_HERE, "..", "..", "pympc_b200", "csrc", "bmpc_core.cuh")
+    tpi = os.path.join(_HERE, "..", "..", "pympc_b200", "csrc", "bmpc_tpi.cuh")
     os.makedirs(os.path.dirname(_SO), exist_ok=True)
-    if (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(core)):
-        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", src, "-o", _SO])
+    if (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(core), os.path.getmtime(tpi)):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-x", "c++", src, "-o", _SO])
     return ctypes.CDLL(_SO)
 
 
@@ -68,3 +69,14 @@ class EmuSystem:
                ctypes.byref(it), ctypes.byref(ps), _p(res))
         self.cold = 0
         return U, st, it.value, ps.value, res
+
+    def tpi_step(self, x0, um1, xref, first_iters=10, pdas_steps=4):
+        """TPI fast path (ADMM + TPI polish) on the same generic-layout state; returns (U, polish_steps)."""
+        x0 = np.ascontiguousarray(x0, float); um1 = np.ascontiguousarray(um1, float); xref = np.ascontiguousarray(xref, float)
+        U = np.zeros(self.NU)
+        f = self.L.emu_tpi_step
+        f.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 4 + [ctypes.c_int] + [ctypes.c_void_p] * 3 + [ctypes.c_int] * 2
+        ps = f(self.nx, self.nu, self.Np, self.Nc, _p(self.sys), _p(x0), _p(um1), _p(xref), self.cold, _p(self.x), _p(self.v), _p(U),
+               first_iters, pdas_steps)
+        self.cold = 0
+        return U, ps

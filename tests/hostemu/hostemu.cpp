@@ -4,6 +4,7 @@
 // fallback: pympc_b200 never loads this library; it lives under tests/ and is built by the tests.
 #define BMPC_HOSTEMU 1
 #include "../../pympc_b200/csrc/bmpc_core.cuh"
+#include "../../pympc_b200/csrc/bmpc_tpi.cuh"
 #include <stdlib.h>
 #include <string.h>
 
@@ -65,4 +66,48 @@ int emu_solve(int nx, int nu, int Np, int Nc, const double* sys, const double* x
     free(buf); free(st);
     return status;
 }
+
+}  // extern "C"
+
+// TPI fast path for one instance (shape must be one of the compiled ones): first_iters ADMM iterations + TPI polish.
+// x [NU], v [mc] use the GENERIC layout (in/out) exactly like the device kernels.  Returns polish steps (>0 verified,
+// 0 not verified, -1 working set too large, -100 shape not compiled).
+template <class S>
+static int emu_tpi_run(const double* sys, const double* x0, const double* um1, const double* xref, int cold, double* x,
+                       double* v, double* Uout, int first_iters, int pdas_steps) {
+    BmpcDims d = bmpc_make_dims(S::nx, S::nu, S::Np, S::Nc); BmpcSysOff o = bmpc_make_off(d);
+    TpiAdmmParams<S>* PA = new TpiAdmmParams<S>(); TpiPolishParams<S>* PP = new TpiPolishParams<S>();
+    tpi_fill_admm<S>(sys, o, *PA); tpi_fill_polish<S>(sys, o, sys, *PP);
+    double* col = (double*)calloc(S::PROWS + S::MT, sizeof(double));
+    for (int i = 0; i < S::MT; i++) col[i] = v[i + S::nx];
+    TpiAcc V{col, 1};
+    tpi_admm<S>(*PA, V, x0, um1, xref, x, first_iters, cold != 0);
+    for (int i = 0; i < S::MT; i++) v[i + S::nx] = col[i];
+    for (int i = 0; i < S::nx; i++) v[i] = x0[i];
+    double g[S::NU];
+    tpi_linear_term<S>(PP->c, x0, um1, xref, g);
+    TpiMask up, dn;
+    for (int i = 0; i < S::MT; i++) { double lo, hi; tpi_row_bounds<S>(PP->c, um1, i, lo, hi); up.set(i, col[i] > hi + 1e-9 * (1.0 + fabs(hi))); dn.set(i, col[i] < lo - 1e-9 * (1.0 + fabs(lo))); }
+    double U[S::NU];
+    int ps = tpi_polish<S>(*PP, V, x0, um1, g, up, dn, U, pdas_steps);
+    if (ps > 0) {
+        TpiMask act; act.w[0] = up.w[0] | dn.w[0]; act.w[1] = up.w[1] | dn.w[1];
+        const TpiCommon<S>& c = PP->c;
+        tpi_rows_of<S>(c, x0, U, [&](int i, double zi) {
+            double mu = act.get(i) ? V(tpi_rank(act, i)) : 0.0;
+            double rho = i < S::NS ? c.rhox[i % S::nx] : (i < S::NS + S::NU ? c.rhou[(i - S::NS) % S::nu] : c.rhod[(i - S::NS - S::NU) % S::nu]);
+            V(S::S0 + i) = zi + mu / rho;
+        });
+        for (int i = 0; i < S::MT; i++) v[i + S::nx] = col[S::S0 + i];
+        for (int a = 0; a < S::NU; a++) { Uout[a] = U[a]; x[a] = U[a]; }
+    }
+    free(col); delete PA; delete PP;
+    return ps;
+}
+
+extern "C" int emu_tpi_step(int nx, int nu, int Np, int Nc, const double* sys, const double* x0, const double* um1, const double* xref,
+                 int cold, double* x, double* v, double* Uout, int first_iters, int pdas_steps) {
+    if (nx == 4 && nu == 1 && Np == 20 && Nc == 20) return emu_tpi_run<TpiShape<4, 1, 20, 20>>(sys, x0, um1, xref, cold, x, v, Uout, first_iters, pdas_steps);
+    if (nx == 2 && nu == 1 && Np == 20 && Nc == 20) return emu_tpi_run<TpiShape<2, 1, 20, 20>>(sys, x0, um1, xref, cold, x, v, Uout, first_iters, pdas_steps);
+    return -100;
 }

@@ -43,10 +43,12 @@ def test_condense_kernel_vs_oracle_algebra(MPC, name):
     K.close()
 
 
+@pytest.mark.parametrize("fast", [1, 0])
 @pytest.mark.parametrize("name", list(CASES))
-def test_first_solve_vs_golden(MPC, name):
+def test_first_solve_vs_golden(MPC, name, fast):
+    """fast=1: thread-per-instance kernels where the shape has them (pm, pend); fast=0: team kernels only"""
     cfg = CASES[name](); g = golden(f"{name}_first.npz")
-    K = MPC(**cfg); K.setup()
+    K = MPC(**cfg, fast_path=fast); K.setup()
     u, info = K.output(return_u_seq=True, return_x_seq=True, return_eps_seq=True, return_status=True, return_obj_val=True)
     assert info["status"] == "solved"
     assert np.max(np.abs(u - g["u_seq"][:K.nu])) < TOL
@@ -57,12 +59,15 @@ def test_first_solve_vs_golden(MPC, name):
     K.close()
 
 
+@pytest.mark.parametrize("fast", [1, 0])
 @pytest.mark.parametrize("name,steps", [("pm", 30), ("pend", 40), ("mimo", 12)])
-def test_closed_loop_vs_golden(MPC, name, steps):
+def test_closed_loop_vs_golden(MPC, name, steps, fast):
     """update(x, u) -> output() loop of the reference examples (examples/example_inverted_pendulum.py:65-88),
     linear plant, warm start; includes the analytic point-mass ramp 0.2, 0.4, ..., 1.2."""
+    if name == "mimo" and fast == 0:
+        pytest.skip("mimo has no fast path: covered by fast=1")
     cfg = CASES[name](); g = golden(f"{name}_loop.npz")
-    K = MPC(**cfg); K.setup()
+    K = MPC(**cfg, fast_path=fast); K.setup()
     x = np.array(cfg["x0"], float); u = np.array(cfg["uminus1"], float)
     for t in range(steps):
         K.update(x, u)
@@ -89,15 +94,16 @@ def test_random_batch_closed_loop_vs_golden(MPC):
     """config 3 sampling (rng seed 0): per-instance x0 / xref, 4 warm-started steps."""
     g = golden("pend_rand.npz"); cfg = pendulum()
     B = g["X0"].shape[0]
-    K = MPC(cfg["Ad"], cfg["Bd"], Np=20, x0=g["X0"], xref=g["Xref"], uminus1=np.zeros(1), batch=B,
-            **{k: cfg[k] for k in ("Qx", "QxN", "Qu", "QDu", "xmin", "xmax", "umin", "umax", "Dumin", "Dumax", "eps_feas")})
-    K.setup()
-    X = g["X0"].copy(); U = np.zeros((B, 1))
-    for t in range(g["U"].shape[0]):
-        K.update(X, U); U = K.output()
-        assert np.max(np.abs(U - g["U"][t])) < TOL, t
-        X = X @ cfg["Ad"].T + U @ cfg["Bd"].T
-    K.close()
+    for fast in (1, 0):
+        K = MPC(cfg["Ad"], cfg["Bd"], Np=20, x0=g["X0"], xref=g["Xref"], uminus1=np.zeros(1), batch=B, fast_path=fast,
+                **{k: cfg[k] for k in ("Qx", "QxN", "Qu", "QDu", "xmin", "xmax", "umin", "umax", "Dumin", "Dumax", "eps_feas")})
+        K.setup()
+        X = g["X0"].copy(); U = np.zeros((B, 1))
+        for t in range(g["U"].shape[0]):
+            K.update(X, U); U = K.output()
+            assert np.max(np.abs(U - g["U"][t])) < TOL, (fast, t)
+            X = X @ cfg["Ad"].T + U @ cfg["Bd"].T
+        K.close()
 
 
 def test_variants_vs_golden(MPC):
@@ -125,7 +131,7 @@ def test_mimo_cta_team_matches_warp_team_on_small_problem(MPC):
     """the same numerical core runs as one warp or one CTA per instance: both must give the golden answer"""
     cfg = pendulum(); g = golden("pend_first.npz")
     for team in (32, 128):
-        K = MPC(**cfg, team_threads=team); K.setup(); u = K.output()
+        K = MPC(**cfg, team_threads=team, fast_path=0); K.setup(); u = K.output()
         assert np.max(np.abs(u - g["u_seq"][:1])) < TOL
         K.close()
 
