@@ -88,6 +88,7 @@ struct BmpcInst {
     const double* x0;     // [B,nx]
     const double* um1;    // [B,nu]
     const double* xref;   // [B,nx] or [B,NX]
+    const double* um1_solved;  // [B,nu] copy of um1 as seen by the last solve (output() may overwrite um1)
     double* g;            // [B,NU]   scratch (per-step linear term)
     double* cc;           // [B,NX]   scratch (free response Acal x0)
     double* xw;           // [B,NU]   ADMM x (warm start)
@@ -236,19 +237,26 @@ __global__ void k_reset(BmpcInst I, int B) {
     if (i < B) { I.status[i] = BMPC_UNSOLVED; I.iters[i] = 0; I.psteps[i] = 0; }
 }
 
-// x_seq = Acal x0 + Bcal U, eps_seq = distance back to the box, objective of the reference QP (without J_CNST)
+// x_seq = Acal x0 + Bcal U, eps_seq = distance back to the box, objective of the reference QP (without J_CNST).
+// Recomputes g and cc from (x0, u_-1, xref) so it does not depend on which solve path ran.
 __global__ void k_sequences(BmpcDims d, BmpcSysOff o, const double* __restrict__ sys, BmpcInst I, int B, int xref_mode,
                             double* xseq, double* epsseq, double* obj) {
+    extern __shared__ double smem[];
     WarpTeam t;
-    int inst = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int slot = threadIdx.x >> 5;
+    int inst = blockIdx.x * (blockDim.x >> 5) + slot;
     if (inst >= B) return;
+    double* g = smem + (size_t)slot * (d.NU + d.NX + d.nu + 1);
+    double* cc = g + d.NU;
+    double* um1 = cc + d.NX;
     const double *BcalT = sys + o.BcalT, *H = sys + o.H, *lo0 = sys + o.lo0, *hi0 = sys + o.hi0;
     const double *Qx = sys + o.Qx, *QxN = sys + o.QxN;
     const double rho_e = sys[o.scal + BMPC_S_RHOE];
     const double* U = I.Us + (size_t)inst * d.NU;
-    const double* cc = I.cc + (size_t)inst * d.NX;
-    const double* g = I.g + (size_t)inst * d.NU;
     const double* xr = I.xref + (size_t)inst * (xref_mode ? d.NX : d.nx);
+    for (int q = t.tid; q < d.nu; q += 32) um1[q] = I.um1_solved[(size_t)inst * d.nu + q];
+    t.sync();
+    bmpc_prep(t, d, o, sys, I.x0 + (size_t)inst * d.nx, um1, xr, xref_mode, g, cc);
     double part = 0.0;
     for (int i = t.tid; i < d.NX; i += 32) {
         double xi = bmpc_Arow_dot(d, BcalT, U, i) + cc[i];
@@ -325,7 +333,7 @@ __global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiPo
     const bool valid = lane < nvalid;
     tpi_load_v<S>(I, inst0, nvalid, smem, 0);
     __syncwarp();
-    double x0[S::nx], um1[S::nu], xref[S::nx], g[S::NU], U[S::NU];
+    double x0[S::nx], um1[S::nu], xref[S::nx], g[S::NU];
 #pragma unroll
     for (int q = 0; q < S::nx; q++) { x0[q] = valid ? I.x0[(size_t)inst * S::nx + q] : 0.0; xref[q] = valid ? I.xref[(size_t)inst * S::nx + q] : 0.0; }
 #pragma unroll
@@ -336,25 +344,22 @@ __global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiPo
     if (valid) {
         tpi_linear_term<S>(c, x0, um1, xref, g);
         TpiMask up, dn;
-#pragma unroll
-        for (int i = 0; i < S::MT; i++) {
-            double lo, hi; tpi_row_bounds<S>(c, um1, i, lo, hi);
+        tpi_for_rows<S>(c, um1, [&](int i, double lo, double hi, double) {
             const double vi = W(i);
             up.set(i, vi > hi + 1e-9 * (1.0 + fabs(hi))); dn.set(i, vi < lo - 1e-9 * (1.0 + fabs(lo)));
-        }
-        ps = tpi_polish<S>(P, W, x0, um1, g, up, dn, U, max_steps);
+        });
+        ps = tpi_polish<S>(P, W, x0, um1, g, up, dn, max_steps);
         if (ps > 0) {
             TpiMask act; act.w[0] = up.w[0] | dn.w[0]; act.w[1] = up.w[1] | dn.w[1];
-            // exact ADMM fixed point v* = z* + y*/rho staged at rows [S0, S0+MT) (the S block is dead, mu is not)
-            tpi_rows_of<S>(c, x0, U, [&](int i, double zi) {
+            // exact ADMM fixed point v* = z* + y*/rho staged at rows [S0, S0+MT) (the S block is dead, mu and U are not)
+            tpi_rows_of<S>(c, x0, um1, W, S::UB, [&](int i, double, double, double rho, double zi) {
                 const double mu = act.get(i) ? W(tpi_rank(act, i)) : 0.0;
-                const double rho = i < S::NS ? c.rhox[i % S::nx] : (i < S::NS + S::NU ? c.rhou[(i - S::NS) % S::nu] : c.rhod[(i - S::NS - S::NU) % S::nu]);
                 W(S::S0 + i) = zi + mu / rho;
             });
 #pragma unroll
-            for (int a = 0; a < S::NU; a++) { I.Us[(size_t)inst * S::NU + a] = U[a]; I.xw[(size_t)inst * S::NU + a] = U[a]; }
+            for (int a = 0; a < S::NU; a++) { const double ua = W(S::UB + a); I.Us[(size_t)inst * S::NU + a] = ua; I.xw[(size_t)inst * S::NU + a] = ua; }
 #pragma unroll
-            for (int q = 0; q < S::nu; q++) u0_out[(size_t)inst * S::nu + q] = U[q];
+            for (int q = 0; q < S::nu; q++) u0_out[(size_t)inst * S::nu + q] = W(S::UB + q);
             I.status[inst] = BMPC_SOLVED; I.psteps[inst] += ps;
             atomicAdd(next_count + 1, ps);
         } else {
@@ -387,7 +392,7 @@ struct bmpc_handle {
     cudaStream_t stream, own_stream;
     double* sys = nullptr;
     BmpcInst I;
-    double *x0 = nullptr, *um1 = nullptr, *xref = nullptr, *u0_own = nullptr, *u0_bound = nullptr;
+    double *x0 = nullptr, *um1 = nullptr, *um1_solved = nullptr, *xref = nullptr, *u0_own = nullptr, *u0_bound = nullptr;
     double *seq_x = nullptr, *seq_e = nullptr, *seq_obj = nullptr;
     int32_t *listA = nullptr, *listB = nullptr, *counts = nullptr;  // counts[2]
     int32_t* h_count = nullptr;                                      // pinned
@@ -515,6 +520,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     ok &= dalloc((void**)&h->sys, sizeof(double) * h->o.total);
     ok &= dalloc((void**)&h->x0, sizeof(double) * B * d.nx);
     ok &= dalloc((void**)&h->um1, sizeof(double) * B * d.nu);
+    ok &= dalloc((void**)&h->um1_solved, sizeof(double) * B * d.nu);
     ok &= dalloc((void**)&h->xref, sizeof(double) * B * d.NX);
     ok &= dalloc((void**)&h->u0_own, sizeof(double) * B * d.nu);
     ok &= dalloc((void**)&h->I.g, sizeof(double) * B * d.NU);
@@ -539,7 +545,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     cudaMemset(h->u0_own, 0, sizeof(double) * B * d.nu);
     cudaMemset(h->I.Us, 0, sizeof(double) * B * d.NU);
     cudaMemset(h->I.Ua, 0, sizeof(double) * B * d.NU);
-    h->I.x0 = h->x0; h->I.um1 = h->um1; h->I.xref = h->xref; h->I.u0 = h->u0_own;
+    h->I.x0 = h->x0; h->I.um1 = h->um1; h->I.um1_solved = h->um1_solved; h->I.xref = h->xref; h->I.u0 = h->u0_own;
     k_reset<<<(int)((B + 255) / 256), 256, 0, h->stream>>>(h->I, (int)B);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "device initialisation failed"; return fail(BMPC_ERR_CUDA); }
     *out = h;
@@ -549,7 +555,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
 void bmpc_destroy(bmpc_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->sys, h->x0, h->um1, h->xref, h->u0_own, h->I.g, h->I.cc, h->I.xw, h->I.vw, h->I.Ua, h->I.Us, h->I.res,
+    void* ptrs[] = {h->sys, h->x0, h->um1, h->um1_solved, h->xref, h->u0_own, h->I.g, h->I.cc, h->I.xw, h->I.vw, h->I.Ua, h->I.Us, h->I.res,
                     h->I.status, h->I.iters, h->I.psteps, h->listA, h->listB, h->counts, h->seq_x, h->seq_e, h->seq_obj};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_count) cudaFreeHost(h->h_count);
@@ -687,6 +693,7 @@ int bmpc_solve(bmpc_handle* h) {
     memset(&h->stats, 0, sizeof(h->stats));
     k_reset<<<(B + 255) / 256, 256, 0, h->stream>>>(h->I, B);
     h->stats.launches++;
+    BMPC_CUDA(cudaMemcpyAsync(h->um1_solved, h->um1, sizeof(double) * (size_t)B * h->d.nu, cudaMemcpyDeviceToDevice, h->stream));
     const int32_t* list = nullptr; int count = B;
     int32_t *cur = h->listA, *nxt = h->listB;
     int total = 0, chunk = h->cfg.polish ? h->cfg.first_iters : 25, round = 0;
@@ -765,7 +772,9 @@ int bmpc_get_sequences(bmpc_handle* h, double* u_seq, double* x_seq, double* eps
             BMPC_CUDA(cudaMalloc((void**)&h->seq_obj, sizeof(double) * B));
         }
         int wpb = 4;
-        k_sequences<<<(int)((B + wpb - 1) / wpb), wpb * 32, 0, h->stream>>>(d, h->o, h->sys, h->I, (int)B, h->xref_mode, h->seq_x, h->seq_e, h->seq_obj);
+        size_t sm = (size_t)wpb * (d.NU + d.NX + d.nu + 1) * sizeof(double);
+        BMPC_CUDA(cudaFuncSetAttribute(k_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_sequences<<<(int)((B + wpb - 1) / wpb), wpb * 32, sm, h->stream>>>(d, h->o, h->sys, h->I, (int)B, h->xref_mode, h->seq_x, h->seq_e, h->seq_obj);
         BMPC_CUDA(cudaGetLastError());
         if (x_seq) BMPC_CUDA(cudaMemcpyAsync(x_seq, h->seq_x, sizeof(double) * B * d.NX, cudaMemcpyDeviceToHost, h->stream));
         if (eps_seq) BMPC_CUDA(cudaMemcpyAsync(eps_seq, h->seq_e, sizeof(double) * B * d.NX, cudaMemcpyDeviceToHost, h->stream));

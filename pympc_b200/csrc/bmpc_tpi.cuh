@@ -28,8 +28,10 @@ struct TpiShape {
     static constexpr int mc = NX + NU + ND;
     static constexpr int RMAX = 24;                         // working-set capacity of the TPI polish
     static constexpr int T0 = 0, R0 = RMAX, S0 = 2 * RMAX;  // polish workspace rows: t/mu | R | S packed lower
-    static constexpr int WS = S0 + RMAX * (RMAX + 1) / 2;
-    static constexpr int PROWS = (WS > MT + S0 ? WS : MT + S0);   // v* is staged at rows [S0, S0 + MT)
+    static constexpr int U0B = S0 + RMAX * (RMAX + 1) / 2;   // U0 = -H^-1 g
+    static constexpr int UB = U0B + NCc * NUc;               // candidate U
+    static constexpr int WS = UB + NCc * NUc;
+    static constexpr int PROWS = (WS > MT + S0 ? WS : MT + S0);   // v* is staged at rows [S0, S0 + MT) (S is dead by then)
 };
 
 template <class S>
@@ -233,8 +235,12 @@ BMPC_HD void tpi_admm(const TpiAdmmParams<S>& P, TpiAcc V, const double* x0, con
 struct TpiMask {
     unsigned long long w[2];
     BMPC_HD TpiMask() { w[0] = 0ull; w[1] = 0ull; }
-    BMPC_HD bool get(int i) const { return (w[i >> 6] >> (i & 63)) & 1ull; }
-    BMPC_HD void set(int i, bool b) { if (b) w[i >> 6] |= (1ull << (i & 63)); }
+    // explicit selects (no dynamic indexing of w[]) so the masks stay in registers
+    BMPC_HD bool get(int i) const { return (((i < 64) ? w[0] : w[1]) >> (i & 63)) & 1ull; }
+    BMPC_HD void set(int i, bool b) {
+        const unsigned long long bit = (b ? 1ull : 0ull) << (i & 63);
+        if (i < 64) w[0] |= bit; else w[1] |= bit;
+    }
 };
 BMPC_HD int tpi_popc(unsigned long long v) {
 #ifdef BMPC_HOSTEMU
@@ -249,80 +255,116 @@ BMPC_HD int tpi_rank(const TpiMask& a, int i) {
     return tpi_popc(a.w[0]) + tpi_popc(a.w[1] & ((1ull << (i - 64)) - 1ull));
 }
 
-// bound of TPI row i selected by `up`; state rows use xmin/xmax, etc.
-template <class S>
-BMPC_HD void tpi_row_bounds(const TpiCommon<S>& c, const double* um1, int i, double& lo, double& hi) {
-    if (i < S::NS) { lo = c.xmin[i % S::nx]; hi = c.xmax[i % S::nx]; }
-    else if (i < S::NS + S::NU) { lo = c.umin[(i - S::NS) % S::nu]; hi = c.umax[(i - S::NS) % S::nu]; }
-    else tpi_dbounds<S>(c, um1, i - S::NS - S::NU, lo, hi);
+// ---- row iterators (rolled over the horizon so the code stays small; inner nx / nu loops are unrolled) ----
+// f(i, lo, hi, rho) for every TPI row i
+template <class S, class F>
+BMPC_HD void tpi_for_rows(const TpiCommon<S>& c, const double* um1, F f) {
+    constexpr int nx = S::nx, nu = S::nu, Np = S::Np, NS = S::NS, NU = S::NU, ND = S::ND;
+#pragma unroll 1
+    for (int k = 0; k < Np; k++) {
+#pragma unroll
+        for (int a = 0; a < nx; a++) f(k * nx + a, c.xmin[a], c.xmax[a], c.rhox[a]);
+    }
+#pragma unroll 1
+    for (int j = 0; j < NU / nu; j++) {
+#pragma unroll
+        for (int b = 0; b < nu; b++) f(NS + j * nu + b, c.umin[b], c.umax[b], c.rhou[b]);
+    }
+#pragma unroll
+    for (int b = 0; b < nu; b++) f(NS + NU + b, c.dmin[b] + um1[b], c.dmax[b] + um1[b], c.rhod[b]);
+#pragma unroll 1
+    for (int j = 1; j < ND / nu; j++) {
+#pragma unroll
+        for (int b = 0; b < nu; b++) f(NS + NU + j * nu + b, c.dmin[b], c.dmax[b], c.rhod[b]);
+    }
 }
 
-// visit every TPI row of z = A U + cc in order (state rows by simulation), calling f(i, value)
+// f(i, lo, hi, rho, value) with value = (A U + cc)_i, U read from the workspace rows [ub, ub+NU)
 template <class S, class F>
-BMPC_HD void tpi_rows_of(const TpiCommon<S>& c, const double* x0, const double* U, F f) {
+BMPC_HD void tpi_rows_of(const TpiCommon<S>& c, const double* x0, const double* um1, TpiAcc W, int ub, F f) {
     constexpr int nx = S::nx, nu = S::nu, Np = S::Np, Nc = S::Nc, NS = S::NS, NU = S::NU, ND = S::ND;
     double xk[nx];
 #pragma unroll
     for (int q = 0; q < nx; q++) xk[q] = x0[q];
-#pragma unroll
+#pragma unroll 1
     for (int k = 1; k <= Np; k++) {
         const int j = (k - 1 < Nc - 1) ? (k - 1) : (Nc - 1);
+        double uj[nu];
+#pragma unroll
+        for (int b = 0; b < nu; b++) uj[b] = W(ub + j * nu + b);
         double xn[nx];
 #pragma unroll
         for (int a = 0; a < nx; a++) {
-            double acc = 0.0;
+            double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-            for (int q = 0; q < nx; q++) acc += c.Ad[a * nx + q] * xk[q];
+            for (int q = 0; q < nx; q += 2) { a0 += c.Ad[a * nx + q] * xk[q]; if (q + 1 < nx) a1 += c.Ad[a * nx + q + 1] * xk[q + 1]; }
 #pragma unroll
-            for (int b = 0; b < nu; b++) acc += c.Bd[a * nu + b] * U[j * nu + b];
-            xn[a] = acc;
+            for (int b = 0; b < nu; b++) a1 += c.Bd[a * nu + b] * uj[b];
+            xn[a] = a0 + a1;
         }
 #pragma unroll
-        for (int a = 0; a < nx; a++) { xk[a] = xn[a]; f((k - 1) * nx + a, xn[a]); }
+        for (int a = 0; a < nx; a++) { xk[a] = xn[a]; f((k - 1) * nx + a, c.xmin[a], c.xmax[a], c.rhox[a], xn[a]); }
     }
+#pragma unroll 1
+    for (int j = 0; j < NU / nu; j++) {
 #pragma unroll
-    for (int a = 0; a < NU; a++) f(NS + a, U[a]);
+        for (int b = 0; b < nu; b++) f(NS + j * nu + b, c.umin[b], c.umax[b], c.rhou[b], W(ub + j * nu + b));
+    }
+    // delta-u rows: first nu rows = u_0 (bounds shifted by u_-1), then -U[s] + U[s+1] on the scalar stacking
 #pragma unroll
-    for (int rr = 0; rr < ND; rr++)
-        f(NS + NU + rr, rr < nu ? U[rr] : (-U[rr - nu] + (rr - nu + 1 < NU ? U[rr - nu + 1] : 0.0)));
+    for (int b = 0; b < nu; b++) f(NS + NU + b, c.dmin[b] + um1[b], c.dmax[b] + um1[b], c.rhod[b], W(ub + b));
+#pragma unroll 1
+    for (int j = 1; j < ND / nu; j++) {
+#pragma unroll
+        for (int b = 0; b < nu; b++) {
+            const int s2 = (j - 1) * nu + b;
+            const double val = -W(ub + s2) + (s2 + 1 < NU ? W(ub + s2 + 1) : 0.0);
+            f(NS + NU + j * nu + b, c.dmin[b], c.dmax[b], c.rhod[b], val);
+        }
+    }
 }
 
-// W: workspace accessor (rows: [T0,..) t/mu, [R0,..) R, [S0,..) S packed lower, diagonal holds 1/L_jj).
-// up/dn: in = initial sets (from v), out = final sets.  mu_out: multipliers by rank are left in W(0..r).
-// Returns steps used (>0) when KKT-verified, 0 if not verified within max_steps, -1 if the set outgrew RMAX.
+// W: workspace accessor (rows: [T0,..) t/mu, [R0,..) R, [S0,..) S packed lower with 1/L_jj on the diagonal,
+// [U0B,..) U0, [UB,..) candidate U).  up/dn: in = initial sets (from v), out = verified working set.
+// Returns steps used (>0) when KKT-verified (U in rows UB.., multipliers by rank in rows T0..),
+// 0 if not verified within max_steps, -1 if the working set outgrew RMAX.
 template <class S>
 BMPC_HD int tpi_polish(const TpiPolishParams<S>& P, TpiAcc W, const double* x0, const double* um1, const double* g,
-                       TpiMask& up, TpiMask& dn, double* U, int max_steps) {
-    constexpr int NS = S::NS, NU = S::NU, RMAX = S::RMAX, nx = S::nx, R0 = S::R0, S0 = S::S0;
+                       TpiMask& up, TpiMask& dn, int max_steps) {
+    constexpr int NS = S::NS, NU = S::NU, RMAX = S::RMAX, nx = S::nx, R0 = S::R0, S0 = S::S0, U0B = S::U0B, UB = S::UB;
     const TpiCommon<S>& c = P.c;
     const bool soft_on = c.inv_rho_e > 0.0;
-    double U0[NU];
-#pragma unroll
+#pragma unroll 1
     for (int a = 0; a < NU; a++) {
-        double acc = 0.0;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-        for (int b = 0; b < NU; b++) acc += P.Hinv[a * NU + b] * g[b];
-        U0[a] = -acc;
+        for (int b = 0; b < NU; b += 4) {
+            a0 += P.Hinv[a * NU + b] * g[b];
+            if (b + 1 < NU) a1 += P.Hinv[a * NU + b + 1] * g[b + 1];
+            if (b + 2 < NU) a2 += P.Hinv[a * NU + b + 2] * g[b + 2];
+            if (b + 3 < NU) a3 += P.Hinv[a * NU + b + 3] * g[b + 3];
+        }
+        W(U0B + a) = -((a0 + a1) + (a2 + a3));
     }
+#pragma unroll 1
     for (int step = 0; step < max_steps; step++) {
         TpiMask act; act.w[0] = up.w[0] | dn.w[0]; act.w[1] = up.w[1] | dn.w[1];
         const int r = tpi_popc(act.w[0]) + tpi_popc(act.w[1]);
         if (r > RMAX) return -1;
         // residual of the working rows at U0, and their generic row indices
-        tpi_rows_of<S>(c, x0, U0, [&](int i, double val) {
+        tpi_rows_of<S>(c, x0, um1, W, U0B, [&](int i, double lo, double hi, double, double val) {
             if (act.get(i)) {
-                double lo, hi; tpi_row_bounds<S>(c, um1, i, lo, hi);
-                int k = tpi_rank(act, i);
+                const int k = tpi_rank(act, i);
                 W(k) = val - (up.get(i) ? hi : lo);
                 W(R0 + k) = (double)(i + nx);
             }
         });
-        // S = M[R,R] + diag  (packed lower), then Cholesky in place with 1/L_jj on the diagonal
+        // S = M[R,R] + diag (packed lower), then Cholesky in place with 1/L_jj on the diagonal
         for (int p = 0; p < r; p++) {
             const int Rp = (int)W(R0 + p);
+            const double* Mrow = P.M + (size_t)Rp * S::mc;
             for (int q = 0; q <= p; q++) {
-                const int Rq = (int)W(R0 + q);
-                double val = P.M[Rp * S::mc + Rq];
+                double val = Mrow[(int)W(R0 + q)];
                 if (p == q) val += (soft_on && Rp < S::NX) ? c.inv_rho_e : 1e-13 * (1.0 + fabs(val));
                 W(S0 + p * (p + 1) / 2 + q) = val;
             }
@@ -331,17 +373,22 @@ BMPC_HD int tpi_polish(const TpiPolishParams<S>& P, TpiAcc W, const double* x0, 
             const int bi = S0 + i * (i + 1) / 2;
             for (int j = 0; j <= i; j++) {
                 const int bj = S0 + j * (j + 1) / 2;
-                double s = W(bi + j);
-                for (int k = 0; k < j; k++) s -= W(bi + k) * W(bj + k);
+                double s0 = W(bi + j), s1 = 0.0;
+                int k = 0;
+                for (; k + 1 < j; k += 2) { s0 -= W(bi + k) * W(bj + k); s1 -= W(bi + k + 1) * W(bj + k + 1); }
+                if (k < j) s0 -= W(bi + k) * W(bj + k);
+                double s = s0 + s1;
                 if (j < i) W(bi + j) = s * W(bj + j);
                 else { if (!(s > 1e-300)) s = 1e-300; W(bi + i) = 1.0 / sqrt(s); }
             }
         }
         for (int i = 0; i < r; i++) {                         // L y = t
             const int bi = S0 + i * (i + 1) / 2;
-            double s = W(i);
-            for (int k = 0; k < i; k++) s -= W(bi + k) * W(k);
-            W(i) = s * W(bi + i);
+            double s0 = W(i), s1 = 0.0;
+            int k = 0;
+            for (; k + 1 < i; k += 2) { s0 -= W(bi + k) * W(k); s1 -= W(bi + k + 1) * W(k + 1); }
+            if (k < i) s0 -= W(bi + k) * W(k);
+            W(i) = (s0 + s1) * W(bi + i);
         }
         double mumax = 0.0;
         for (int i = r - 1; i >= 0; i--) {                    // L' mu = y
@@ -351,19 +398,23 @@ BMPC_HD int tpi_polish(const TpiPolishParams<S>& P, TpiAcc W, const double* x0, 
             W(i) = s; mumax = fmax(mumax, fabs(s));
         }
         // candidate U = U0 - (A Hinv)[R,:]' mu
+        {
+            double Ur[NU];
 #pragma unroll
-        for (int a = 0; a < NU; a++) U[a] = U0[a];
-        for (int p = 0; p < r; p++) {
-            const double* row = P.AHinv + (int)W(R0 + p) * NU; const double mu = W(p);
+            for (int a = 0; a < NU; a++) Ur[a] = W(U0B + a);
+            for (int p = 0; p < r; p++) {
+                const double* row = P.AHinv + (size_t)((int)W(R0 + p)) * NU; const double mu = W(p);
 #pragma unroll
-            for (int a = 0; a < NU; a++) U[a] -= row[a] * mu;
+                for (int a = 0; a < NU; a++) Ur[a] -= row[a] * mu;
+            }
+#pragma unroll
+            for (int a = 0; a < NU; a++) W(UB + a) = Ur[a];
         }
         // KKT verification + next sets
         bool ok = true;
         const double mutol = 1e-9 * (1.0 + mumax);
         TpiMask nup, ndn;
-        tpi_rows_of<S>(c, x0, U, [&](int i, double zi) {
-            double lo, hi; tpi_row_bounds<S>(c, um1, i, lo, hi);
+        tpi_rows_of<S>(c, x0, um1, W, UB, [&](int i, double lo, double hi, double, double zi) {
             const bool su = up.get(i), sd = dn.get(i);
             bool nu_, nd_;
             if (soft_on && i < NS) {
@@ -375,7 +426,7 @@ BMPC_HD int tpi_polish(const TpiPolishParams<S>& P, TpiAcc W, const double* x0, 
                     if (!(gap <= 1e-11 * (1.0 + fabs(bnd)))) ok = false;
                 }
             } else {
-                const double mu = act.get(i) ? W(tpi_rank(act, i)) : 0.0;
+                const double mu = (su || sd) ? W(tpi_rank(act, i)) : 0.0;
                 const bool vu = zi > hi + 1e-9 * (1.0 + fabs(hi)), vd = zi < lo - 1e-9 * (1.0 + fabs(lo));
                 if (vu || vd || (su && mu < -mutol) || (sd && mu > mutol)) ok = false;
                 nu_ = vu || (!vd && su && mu > 0.0);

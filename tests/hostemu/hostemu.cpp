@@ -78,7 +78,7 @@ static int emu_tpi_run(const double* sys, const double* x0, const double* um1, c
     BmpcDims d = bmpc_make_dims(S::nx, S::nu, S::Np, S::Nc); BmpcSysOff o = bmpc_make_off(d);
     TpiAdmmParams<S>* PA = new TpiAdmmParams<S>(); TpiPolishParams<S>* PP = new TpiPolishParams<S>();
     tpi_fill_admm<S>(sys, o, *PA); tpi_fill_polish<S>(sys, o, sys, *PP);
-    double* col = (double*)calloc(S::PROWS + S::MT, sizeof(double));
+    double* col = (double*)calloc(S::PROWS + S::MT + 8, sizeof(double));
     for (int i = 0; i < S::MT; i++) col[i] = v[i + S::nx];
     TpiAcc V{col, 1};
     tpi_admm<S>(*PA, V, x0, um1, xref, x, first_iters, cold != 0);
@@ -87,19 +87,18 @@ static int emu_tpi_run(const double* sys, const double* x0, const double* um1, c
     double g[S::NU];
     tpi_linear_term<S>(PP->c, x0, um1, xref, g);
     TpiMask up, dn;
-    for (int i = 0; i < S::MT; i++) { double lo, hi; tpi_row_bounds<S>(PP->c, um1, i, lo, hi); up.set(i, col[i] > hi + 1e-9 * (1.0 + fabs(hi))); dn.set(i, col[i] < lo - 1e-9 * (1.0 + fabs(lo))); }
-    double U[S::NU];
-    int ps = tpi_polish<S>(*PP, V, x0, um1, g, up, dn, U, pdas_steps);
+    tpi_for_rows<S>(PP->c, um1, [&](int i, double lo, double hi, double) {
+        up.set(i, col[i] > hi + 1e-9 * (1.0 + fabs(hi))); dn.set(i, col[i] < lo - 1e-9 * (1.0 + fabs(lo))); });
+    int ps = tpi_polish<S>(*PP, V, x0, um1, g, up, dn, pdas_steps);
     if (ps > 0) {
         TpiMask act; act.w[0] = up.w[0] | dn.w[0]; act.w[1] = up.w[1] | dn.w[1];
         const TpiCommon<S>& c = PP->c;
-        tpi_rows_of<S>(c, x0, U, [&](int i, double zi) {
+        tpi_rows_of<S>(c, x0, um1, V, S::UB, [&](int i, double, double, double rho, double zi) {
             double mu = act.get(i) ? V(tpi_rank(act, i)) : 0.0;
-            double rho = i < S::NS ? c.rhox[i % S::nx] : (i < S::NS + S::NU ? c.rhou[(i - S::NS) % S::nu] : c.rhod[(i - S::NS - S::NU) % S::nu]);
             V(S::S0 + i) = zi + mu / rho;
         });
         for (int i = 0; i < S::MT; i++) v[i + S::nx] = col[S::S0 + i];
-        for (int a = 0; a < S::NU; a++) { Uout[a] = U[a]; x[a] = U[a]; }
+        for (int a = 0; a < S::NU; a++) { Uout[a] = col[S::UB + a]; x[a] = col[S::UB + a]; }
     }
     free(col); delete PA; delete PP;
     return ps;
