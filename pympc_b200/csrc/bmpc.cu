@@ -325,55 +325,44 @@ __global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmm
 }
 
 template <class S>
-__global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiPolishParams<S> P, BmpcInst I, int B, int max_steps,
+__global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiRicParams<S> P, BmpcInst I, int B, int max_steps,
                                                    int32_t* next_list, int32_t* next_count, double* u0_out) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x, inst0 = blockIdx.x * 32, inst = inst0 + lane;
     const int nvalid = (B - inst0) < 32 ? (B - inst0) : 32;
-    const bool valid = lane < nvalid;
     tpi_load_v<S>(I, inst0, nvalid, smem, 0);
     __syncwarp();
-    double x0[S::nx], um1[S::nu], xref[S::nx], g[S::NU];
+    if (lane >= nvalid) return;
+    double x0[S::nx], um1[S::nu], xref[S::nx];
 #pragma unroll
-    for (int q = 0; q < S::nx; q++) { x0[q] = valid ? I.x0[(size_t)inst * S::nx + q] : 0.0; xref[q] = valid ? I.xref[(size_t)inst * S::nx + q] : 0.0; }
+    for (int q = 0; q < S::nx; q++) { x0[q] = I.x0[(size_t)inst * S::nx + q]; xref[q] = I.xref[(size_t)inst * S::nx + q]; }
 #pragma unroll
-    for (int q = 0; q < S::nu; q++) um1[q] = valid ? I.um1[(size_t)inst * S::nu + q] : 0.0;
+    for (int q = 0; q < S::nu; q++) um1[q] = I.um1[(size_t)inst * S::nu + q];
     TpiAcc W{smem + lane, TPI_STR};
     const TpiCommon<S>& c = P.c;
-    int ps = 0;
-    if (valid) {
-        tpi_linear_term<S>(c, x0, um1, xref, g);
-        TpiMask up, dn;
-        tpi_for_rows<S>(c, um1, [&](int i, double lo, double hi, double) {
-            const double vi = W(i);
-            up.set(i, vi > hi + 1e-9 * (1.0 + fabs(hi))); dn.set(i, vi < lo - 1e-9 * (1.0 + fabs(lo)));
-        });
-        ps = tpi_polish<S>(P, W, x0, um1, g, up, dn, max_steps);
-        if (ps > 0) {
-            TpiMask act; act.w[0] = up.w[0] | dn.w[0]; act.w[1] = up.w[1] | dn.w[1];
-            // exact ADMM fixed point v* = z* + y*/rho staged at rows [S0, S0+MT) (the S block is dead, mu and U are not)
-            tpi_rows_of<S>(c, x0, um1, W, S::UB, [&](int i, double, double, double rho, double zi) {
-                const double mu = act.get(i) ? W(tpi_rank(act, i)) : 0.0;
-                W(S::S0 + i) = zi + mu / rho;
-            });
+    TpiMask up, dn;
+    tpi_for_rows<S>(c, um1, [&](int i, double lo, double hi, double) {
+        const double vi = W(i);
+        up.set(i, vi > hi + 1e-9 * (1.0 + fabs(hi))); dn.set(i, vi < lo - 1e-9 * (1.0 + fabs(lo)));
+    });
+    // from here on the column is this thread's private workspace (Riccati gains): no cross-lane traffic
+    const int ps = tpi_polish_riccati<S>(P, W, x0, um1, xref, up, dn, max_steps);
+    if (ps > 0) {
+        // emit pass: solution and the exact ADMM fixed point v* = z* + y*/rho (warm start of the next step)
+        double* vdst = I.vw + (size_t)inst * S::mc;
+        double* udst = I.Us + (size_t)inst * S::NU;
+        double* xdst = I.xw + (size_t)inst * S::NU;
+        TpiMask t1, t2; double mm = 0.0;
+        tpi_ric_forward<S, true>(P, W, x0, um1, up, dn, t1, t2, mm,
+            [&](int i, double zi, double mu, double irho) { vdst[S::nx + i] = zi + mu * irho; },
+            [&](int j, double u) { udst[j] = u; xdst[j] = u; if (j == 0) u0_out[inst] = u; });
 #pragma unroll
-            for (int a = 0; a < S::NU; a++) { const double ua = W(S::UB + a); I.Us[(size_t)inst * S::NU + a] = ua; I.xw[(size_t)inst * S::NU + a] = ua; }
-#pragma unroll
-            for (int q = 0; q < S::nu; q++) u0_out[(size_t)inst * S::nu + q] = W(S::UB + q);
-            I.status[inst] = BMPC_SOLVED; I.psteps[inst] += ps;
-            atomicAdd(next_count + 1, ps);
-        } else {
-            const int used = ps < 0 ? 1 : max_steps;
-            I.psteps[inst] += used; atomicAdd(next_count + 1, used);
-            next_list[atomicAdd(next_count, 1)] = inst;
-        }
-    }
-    const unsigned okmask = __ballot_sync(0xffffffffu, ps > 0);
-    __syncwarp();
-    double* dst = I.vw + (size_t)inst0 * S::mc;
-    for (int idx = lane; idx < nvalid * S::mc; idx += 32) {
-        int t = idx / S::mc, i = idx - t * S::mc;
-        if ((okmask >> t) & 1u) dst[idx] = (i >= S::nx) ? smem[(S::S0 + i - S::nx) * TPI_STR + t] : I.x0[(size_t)(inst0 + t) * S::nx + i];
+        for (int q = 0; q < S::nx; q++) vdst[q] = x0[q];
+        I.status[inst] = BMPC_SOLVED; I.psteps[inst] += ps;
+        atomicAdd(next_count + 1, ps);
+    } else {
+        I.psteps[inst] += max_steps; atomicAdd(next_count + 1, max_steps);
+        next_list[atomicAdd(next_count, 1)] = inst;
     }
 }
 
@@ -404,7 +393,7 @@ struct bmpc_handle {
     size_t smem_admm = 0, smem_polish = 0;
     int tpi_kind = 0;                  // 0 none, 1 pendulum shape (4,1,20,20), 2 point-mass shape (2,1,20,20)
     void *tpi_admm_params = nullptr, *tpi_polish_params = nullptr;   // host copies of the parameter blocks
-    int tpi_pdas_steps = 6;
+    int tpi_pdas_steps = 8;
 };
 
 static std::string g_create_err;
@@ -423,7 +412,7 @@ static void launch_tpi_round(bmpc_handle* h, int B, int niter, cudaEvent_t mid) 
     const int grid = (B + 31) / 32;
     k_tpi_admm<S><<<grid, 32, S::MT * TPI_STR * 8, h->stream>>>(*(const TpiAdmmParams<S>*)h->tpi_admm_params, h->I, B, niter, h->cold ? 1 : 0);
     cudaEventRecord(mid, h->stream);
-    k_tpi_polish<S><<<grid, 32, S::PROWS * TPI_STR * 8, h->stream>>>(*(const TpiPolishParams<S>*)h->tpi_polish_params, h->I, B,
+    k_tpi_polish<S><<<grid, 32, S::PROWS * TPI_STR * 8, h->stream>>>(*(const TpiRicParams<S>*)h->tpi_polish_params, h->I, B,
                                                                      h->tpi_pdas_steps, h->listB, h->counts, h->I.u0);
     h->stats.launches += 2;
 }
@@ -629,13 +618,13 @@ int bmpc_setup(bmpc_handle* h, const double* Ad, const double* Bd, const double*
         free(h->tpi_admm_params); free(h->tpi_polish_params);
         if (h->tpi_kind == 1) {
             auto* pa = (TpiAdmmParams<TpiPend>*)malloc(sizeof(TpiAdmmParams<TpiPend>)); tpi_fill_admm<TpiPend>(hs.data(), o, *pa);
-            auto* pp = (TpiPolishParams<TpiPend>*)malloc(sizeof(TpiPolishParams<TpiPend>)); tpi_fill_polish<TpiPend>(hs.data(), o, h->sys, *pp);
+            auto* pp = (TpiRicParams<TpiPend>*)malloc(sizeof(TpiRicParams<TpiPend>)); tpi_fill_riccati<TpiPend>(hs.data(), o, *pp);
             h->tpi_admm_params = pa; h->tpi_polish_params = pp;
             BMPC_CUDA(cudaFuncSetAttribute(k_tpi_admm<TpiPend>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TpiPend::MT * TPI_STR * 8)));
             BMPC_CUDA(cudaFuncSetAttribute(k_tpi_polish<TpiPend>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TpiPend::PROWS * TPI_STR * 8)));
         } else {
             auto* pa = (TpiAdmmParams<TpiPm>*)malloc(sizeof(TpiAdmmParams<TpiPm>)); tpi_fill_admm<TpiPm>(hs.data(), o, *pa);
-            auto* pp = (TpiPolishParams<TpiPm>*)malloc(sizeof(TpiPolishParams<TpiPm>)); tpi_fill_polish<TpiPm>(hs.data(), o, h->sys, *pp);
+            auto* pp = (TpiRicParams<TpiPm>*)malloc(sizeof(TpiRicParams<TpiPm>)); tpi_fill_riccati<TpiPm>(hs.data(), o, *pp);
             h->tpi_admm_params = pa; h->tpi_polish_params = pp;
             BMPC_CUDA(cudaFuncSetAttribute(k_tpi_admm<TpiPm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TpiPm::MT * TPI_STR * 8)));
             BMPC_CUDA(cudaFuncSetAttribute(k_tpi_polish<TpiPm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TpiPm::PROWS * TPI_STR * 8)));

@@ -26,12 +26,7 @@ struct TpiShape {
     static constexpr int MT = NS + NU + ND;
     static constexpr int NX = (NPc + 1) * NXc;
     static constexpr int mc = NX + NU + ND;
-    static constexpr int RMAX = 24;                         // working-set capacity of the TPI polish
-    static constexpr int T0 = 0, R0 = RMAX, S0 = 2 * RMAX;  // polish workspace rows: t/mu | R | S packed lower
-    static constexpr int U0B = S0 + RMAX * (RMAX + 1) / 2;   // U0 = -H^-1 g
-    static constexpr int UB = U0B + NCc * NUc;               // candidate U
-    static constexpr int WS = UB + NCc * NUc;
-    static constexpr int PROWS = (WS > MT + S0 ? WS : MT + S0);   // v* is staged at rows [S0, S0 + MT) (S is dead by then)
+    static constexpr int PROWS = (MT > 6 * NPc ? MT : 6 * NPc) + 1;   // polish workspace rows: v (load) / Riccati gains
 };
 
 template <class S>
@@ -41,6 +36,7 @@ struct TpiCommon {
     double xmin[S::nx], xmax[S::nx], c1x[S::nx], c2x[S::nx], rhox[S::nx];
     double umin[S::nu], umax[S::nu], rhou[S::nu];
     double dmin[S::nu], dmax[S::nu], rhod[S::nu];
+    double irhox[S::nx], irhou[S::nu], irhod[S::nu];   // 1 / rho per row class
     double sigma, alpha, inv_rho_e;      // inv_rho_e = 0 -> hard state rows
 };
 
@@ -49,14 +45,6 @@ struct TpiAdmmParams {
     TpiCommon<S> c;
     double Kinv[S::NU * S::NU];
     double Gcc[S::NU * S::nx];           // B' R_x Acal : folds the affine offset of the state rows into g
-};
-
-template <class S>
-struct TpiPolishParams {
-    TpiCommon<S> c;
-    double Hinv[S::NU * S::NU];
-    const double* M;                      // [mc, mc]  A H^-1 A'   (generic row indexing)
-    const double* AHinv;                  // [mc, NU]
 };
 
 // per-thread strided accessor: element i of this thread's private column
@@ -279,162 +267,236 @@ BMPC_HD void tpi_for_rows(const TpiCommon<S>& c, const double* um1, F f) {
     }
 }
 
-// f(i, lo, hi, rho, value) with value = (A U + cc)_i, U read from the workspace rows [ub, ub+NU)
-template <class S, class F>
-BMPC_HD void tpi_rows_of(const TpiCommon<S>& c, const double* x0, const double* um1, TpiAcc W, int ub, F f) {
-    constexpr int nx = S::nx, nu = S::nu, Np = S::Np, Nc = S::Nc, NS = S::NS, NU = S::NU, ND = S::ND;
-    double xk[nx];
-#pragma unroll
-    for (int q = 0; q < nx; q++) xk[q] = x0[q];
-#pragma unroll 1
-    for (int k = 1; k <= Np; k++) {
-        const int j = (k - 1 < Nc - 1) ? (k - 1) : (Nc - 1);
-        double uj[nu];
-#pragma unroll
-        for (int b = 0; b < nu; b++) uj[b] = W(ub + j * nu + b);
-        double xn[nx];
+// ------------------------------------------------------------------------------------------------
+// Riccati polish (nu == 1, Nc == Np): the equality-constrained QP of one active-set step is an LQ problem
+//   min sum_k [ 1/2 x_k' Qt_k x_k - qt_k' x_k ] + sum_j [ 1/2 Qu u_j^2 - Qu uref u_j + 1/2 QDu (u_j - u_{j-1})^2 ]
+//   s.t. x_{k+1} = Ad x_k + Bd u_k,  some inputs pinned (u_j = bound, or u_j = u_{j-1} + delta)
+// where violated soft rows enter through Qt_k = Q_k + eps_feas diag(mask_k), qt_k = Q_k xref + eps_feas mask_k.*bound.
+// It is solved exactly by one backward sweep on the augmented state xi = [x ; u_prev] (cost-to-go 1/2 xi'P xi + p'xi)
+// and one forward sweep; multipliers of pinned inputs are -dQ/du of the stage Q-function.  Work and storage are
+// O(Np) and independent of the size of the working set (the Schur form needs an r x r factor per instance).
+// Workspace: 6 rows per stage: free stage -> feedback (k[nx+1], kappa); pinned stage -> (m[nx+1], m0) with dQ/du = m'xi + m0.
+template <class S>
+struct TpiRicParams {
+    TpiCommon<S> c;
+    double Qx[S::nx * S::nx], QxN[S::nx * S::nx];
+    double Qu, QDu, uref, rho_e;
+};
+
+enum { TPI_FREE = 0, TPI_UPIN = 1, TPI_DPIN = 2, TPI_QPIN = 3 };
+
+// pin of stage j implied by the working set (priority: input bound, then delta-u row, then the reference's
+// spurious last row  Dumin <= -u_{N-1} <= Dumax)
+template <class S>
+BMPC_HD int tpi_pin_of(const TpiCommon<S>& c, const TpiMask& up, const TpiMask& dn, int j, double& val) {
+    constexpr int NS = S::NS, NU = S::NU, N = S::Np;
+    const int iu = NS + j, id = NS + NU + j, iq = NS + NU + N;
+    if (up.get(iu)) { val = c.umax[0]; return TPI_UPIN; }
+    if (dn.get(iu)) { val = c.umin[0]; return TPI_UPIN; }
+    if (up.get(id)) { val = c.dmax[0]; return TPI_DPIN; }
+    if (dn.get(id)) { val = c.dmin[0]; return TPI_DPIN; }
+    if (j == N - 1) {
+        if (up.get(iq)) { val = -c.dmax[0]; return TPI_QPIN; }     // -u = Dumax
+        if (dn.get(iq)) { val = -c.dmin[0]; return TPI_QPIN; }
+    }
+    val = 0.0; return TPI_FREE;
+}
+
+template <class S>
+BMPC_HD void tpi_ric_backward(const TpiRicParams<S>& P, TpiAcc W, const double* xref, const TpiMask& up, const TpiMask& dn) {
+    static_assert(S::nu == 1 && S::Nc == S::Np, "Riccati polish is specialised to nu == 1, Nc == Np");
+    constexpr int nx = S::nx, N = S::Np, nz = nx + 1;
+    const TpiCommon<S>& c = P.c;
+    // cost-to-go of stage k+1:  Pxx (sym, full storage), pxw, pww, px, pw
+    double Pxx[nx * nx], pxw[nx], px[nx], pww = 0.0, pw = 0.0;
+    // terminal: state cost of x_N
+    {
 #pragma unroll
         for (int a = 0; a < nx; a++) {
-            double a0 = 0.0, a1 = 0.0;
+            const int i = (N - 1) * nx + a;
+            const bool vu = up.get(i), vd = dn.get(i);
+            double q = 0.0;
 #pragma unroll
-            for (int q = 0; q < nx; q += 2) { a0 += c.Ad[a * nx + q] * xk[q]; if (q + 1 < nx) a1 += c.Ad[a * nx + q + 1] * xk[q + 1]; }
-#pragma unroll
-            for (int b = 0; b < nu; b++) a1 += c.Bd[a * nu + b] * uj[b];
-            xn[a] = a0 + a1;
+            for (int b = 0; b < nx; b++) { Pxx[a * nx + b] = P.QxN[a * nx + b]; q += P.QxN[a * nx + b] * xref[b]; }
+            if (vu || vd) { Pxx[a * nx + a] += P.rho_e; q += P.rho_e * (vu ? c.xmax[a] : c.xmin[a]); }
+            px[a] = -q; pxw[a] = 0.0;
         }
-#pragma unroll
-        for (int a = 0; a < nx; a++) { xk[a] = xn[a]; f((k - 1) * nx + a, c.xmin[a], c.xmax[a], c.rhox[a], xn[a]); }
     }
 #pragma unroll 1
-    for (int j = 0; j < NU / nu; j++) {
+    for (int k = N - 1; k >= 0; k--) {
+        // T = Pxx A ; AtPA = A' T ; PB = Pxx B
+        double T[nx * nx], PB[nx];
 #pragma unroll
-        for (int b = 0; b < nu; b++) f(NS + j * nu + b, c.umin[b], c.umax[b], c.rhou[b], W(ub + j * nu + b));
-    }
-    // delta-u rows: first nu rows = u_0 (bounds shifted by u_-1), then -U[s] + U[s+1] on the scalar stacking
+        for (int a = 0; a < nx; a++) {
 #pragma unroll
-    for (int b = 0; b < nu; b++) f(NS + NU + b, c.dmin[b] + um1[b], c.dmax[b] + um1[b], c.rhod[b], W(ub + b));
-#pragma unroll 1
-    for (int j = 1; j < ND / nu; j++) {
+            for (int b = 0; b < nx; b++) {
+                double acc = 0.0;
 #pragma unroll
-        for (int b = 0; b < nu; b++) {
-            const int s2 = (j - 1) * nu + b;
-            const double val = -W(ub + s2) + (s2 + 1 < NU ? W(ub + s2 + 1) : 0.0);
-            f(NS + NU + j * nu + b, c.dmin[b], c.dmax[b], c.rhod[b], val);
+                for (int q = 0; q < nx; q++) acc += Pxx[a * nx + q] * c.Ad[q * nx + b];
+                T[a * nx + b] = acc;
+            }
+            double accb = 0.0;
+#pragma unroll
+            for (int q = 0; q < nx; q++) accb += Pxx[a * nx + q] * c.Bd[q];
+            PB[a] = accb;
+        }
+        double Hxx[nx * nx], hx[nx], gx[nx];       // x-part of Hxx / hxu / gx ; the w-part is (QDu, -QDu, 0)
+        double huu = pww + P.Qu + P.QDu, gu = pw - P.Qu * P.uref;
+#pragma unroll
+        for (int a = 0; a < nx; a++) { huu += c.Bd[a] * (PB[a] + 2.0 * pxw[a]); gu += c.Bd[a] * px[a]; }
+#pragma unroll
+        for (int a = 0; a < nx; a++) {
+#pragma unroll
+            for (int b = 0; b < nx; b++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < nx; q++) acc += c.Ad[q * nx + a] * T[q * nx + b];
+                Hxx[a * nx + b] = acc;
+            }
+            double h = 0.0, g = 0.0;
+#pragma unroll
+            for (int q = 0; q < nx; q++) { h += c.Ad[q * nx + a] * (PB[q] + pxw[q]); g += c.Ad[q * nx + a] * px[q]; }
+            hx[a] = h; gx[a] = g;
+        }
+        if (k >= 1) {                              // stage cost of x_k (x_0 is data)
+#pragma unroll
+            for (int a = 0; a < nx; a++) {
+                const int i = (k - 1) * nx + a;
+                const bool vu = up.get(i), vd = dn.get(i);
+                double q = 0.0;
+#pragma unroll
+                for (int b = 0; b < nx; b++) { Hxx[a * nx + b] += P.Qx[a * nx + b]; q += P.Qx[a * nx + b] * xref[b]; }
+                if (vu || vd) { Hxx[a * nx + a] += P.rho_e; q += P.rho_e * (vu ? c.xmax[a] : c.xmin[a]); }
+                gx[a] -= q;
+            }
+        }
+        double hw = -P.QDu, Hww = P.QDu, gw = 0.0;   // w-parts:  hxu = [hx ; hw], Hxx_full = blkdiag(Hxx, Hww), gx_full = [gx ; gw]
+        double pin; const int type = tpi_pin_of<S>(c, up, dn, k, pin);
+        const int base = k * (nz + 1);
+        if (type == TPI_FREE) {
+            const double inv = 1.0 / huu;
+#pragma unroll
+            for (int a = 0; a < nx; a++) W(base + a) = hx[a] * inv;
+            W(base + nx) = hw * inv; W(base + nz) = gu * inv;
+            // P = Hxx - hxu hxu'/huu ; p = gx - hxu gu/huu
+#pragma unroll
+            for (int a = 0; a < nx; a++) {
+#pragma unroll
+                for (int b = 0; b < nx; b++) Pxx[a * nx + b] = Hxx[a * nx + b] - hx[a] * hx[b] * inv;
+                pxw[a] = -hx[a] * hw * inv; px[a] = gx[a] - hx[a] * gu * inv;
+            }
+            pww = Hww - hw * hw * inv; pw = gw - hw * gu * inv;
+        } else if (type == TPI_DPIN) {
+            // u = w + pin :  dQ/du = hx'x + (hw + huu) w + huu pin + gu
+#pragma unroll
+            for (int a = 0; a < nx; a++) W(base + a) = hx[a];
+            W(base + nx) = hw + huu; W(base + nz) = huu * pin + gu;
+#pragma unroll
+            for (int a = 0; a < nx; a++) {
+#pragma unroll
+                for (int b = 0; b < nx; b++) Pxx[a * nx + b] = Hxx[a * nx + b];
+                pxw[a] = hx[a]; px[a] = gx[a] + hx[a] * pin;
+            }
+            pww = Hww + 2.0 * hw + huu; pw = gw + hw * pin + huu * pin + gu;
+        } else {
+            // u = pin :  dQ/du = hx'x + hw w + huu pin + gu
+#pragma unroll
+            for (int a = 0; a < nx; a++) W(base + a) = hx[a];
+            W(base + nx) = hw; W(base + nz) = huu * pin + gu;
+#pragma unroll
+            for (int a = 0; a < nx; a++) {
+#pragma unroll
+                for (int b = 0; b < nx; b++) Pxx[a * nx + b] = Hxx[a * nx + b];
+                pxw[a] = 0.0; px[a] = gx[a] + hx[a] * pin;
+            }
+            pww = Hww; pw = gw + hw * pin;
         }
     }
 }
 
-// W: workspace accessor (rows: [T0,..) t/mu, [R0,..) R, [S0,..) S packed lower with 1/L_jj on the diagonal,
-// [U0B,..) U0, [UB,..) candidate U).  up/dn: in = initial sets (from v), out = verified working set.
-// Returns steps used (>0) when KKT-verified (U in rows UB.., multipliers by rank in rows T0..),
-// 0 if not verified within max_steps, -1 if the working set outgrew RMAX.
-template <class S>
-BMPC_HD int tpi_polish(const TpiPolishParams<S>& P, TpiAcc W, const double* x0, const double* um1, const double* g,
-                       TpiMask& up, TpiMask& dn, int max_steps) {
-    constexpr int NS = S::NS, NU = S::NU, RMAX = S::RMAX, nx = S::nx, R0 = S::R0, S0 = S::S0, U0B = S::U0B, UB = S::UB;
+// Forward sweep.  EMIT == false: KKT verification, returns ok and the next working set (nup, ndn), updates mumax.
+// EMIT == true : calls out(i, zi, mu_i, 1/rho_i) for every TPI row and outu(j, u_j) for every input.
+template <class S, bool EMIT, class FR, class FU>
+BMPC_HD bool tpi_ric_forward(const TpiRicParams<S>& P, TpiAcc W, const double* x0, const double* um1, const TpiMask& up,
+                             const TpiMask& dn, TpiMask& nup, TpiMask& ndn, double& mumax, FR out, FU outu) {
+    constexpr int nx = S::nx, N = S::Np, nz = nx + 1, NS = S::NS, NU = S::NU;
     const TpiCommon<S>& c = P.c;
-    const bool soft_on = c.inv_rho_e > 0.0;
+    const double mutol = 1e-9 * (1.0 + mumax);
+    double mnew = 0.0;
+    bool ok = true;
+    double x[nx], w = um1[0];
+#pragma unroll
+    for (int a = 0; a < nx; a++) x[a] = x0[a];
+    auto hard_row = [&](int i, double zi, double lo, double hi, double mu, double irho) {
+        if (EMIT) { out(i, zi, mu, irho); return; }
+        const bool su = up.get(i), sd = dn.get(i);
+        const bool vu = zi > hi + 1e-9 * (1.0 + fabs(hi)), vd = zi < lo - 1e-9 * (1.0 + fabs(lo));
+        if (vu || vd || (su && mu < -mutol) || (sd && mu > mutol)) ok = false;
+        const bool nu_ = vu || (!vd && su && mu > 0.0);
+        nup.set(i, nu_); ndn.set(i, (!nu_) && (vd || (sd && mu < 0.0)));
+    };
 #pragma unroll 1
-    for (int a = 0; a < NU; a++) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int k = 0; k < N; k++) {
+        double pin; const int type = tpi_pin_of<S>(c, up, dn, k, pin);
+        const int base = k * (nz + 1);
+        double lin = W(base + nz);
 #pragma unroll
-        for (int b = 0; b < NU; b += 4) {
-            a0 += P.Hinv[a * NU + b] * g[b];
-            if (b + 1 < NU) a1 += P.Hinv[a * NU + b + 1] * g[b + 1];
-            if (b + 2 < NU) a2 += P.Hinv[a * NU + b + 2] * g[b + 2];
-            if (b + 3 < NU) a3 += P.Hinv[a * NU + b + 3] * g[b + 3];
-        }
-        W(U0B + a) = -((a0 + a1) + (a2 + a3));
-    }
-#pragma unroll 1
-    for (int step = 0; step < max_steps; step++) {
-        TpiMask act; act.w[0] = up.w[0] | dn.w[0]; act.w[1] = up.w[1] | dn.w[1];
-        const int r = tpi_popc(act.w[0]) + tpi_popc(act.w[1]);
-        if (r > RMAX) return -1;
-        // residual of the working rows at U0, and their generic row indices
-        tpi_rows_of<S>(c, x0, um1, W, U0B, [&](int i, double lo, double hi, double, double val) {
-            if (act.get(i)) {
-                const int k = tpi_rank(act, i);
-                W(k) = val - (up.get(i) ? hi : lo);
-                W(R0 + k) = (double)(i + nx);
-            }
-        });
-        // S = M[R,R] + diag (packed lower), then Cholesky in place with 1/L_jj on the diagonal
-        for (int p = 0; p < r; p++) {
-            const int Rp = (int)W(R0 + p);
-            const double* Mrow = P.M + (size_t)Rp * S::mc;
-            for (int q = 0; q <= p; q++) {
-                double val = Mrow[(int)W(R0 + q)];
-                if (p == q) val += (soft_on && Rp < S::NX) ? c.inv_rho_e : 1e-13 * (1.0 + fabs(val));
-                W(S0 + p * (p + 1) / 2 + q) = val;
-            }
-        }
-        for (int i = 0; i < r; i++) {
-            const int bi = S0 + i * (i + 1) / 2;
-            for (int j = 0; j <= i; j++) {
-                const int bj = S0 + j * (j + 1) / 2;
-                double s0 = W(bi + j), s1 = 0.0;
-                int k = 0;
-                for (; k + 1 < j; k += 2) { s0 -= W(bi + k) * W(bj + k); s1 -= W(bi + k + 1) * W(bj + k + 1); }
-                if (k < j) s0 -= W(bi + k) * W(bj + k);
-                double s = s0 + s1;
-                if (j < i) W(bi + j) = s * W(bj + j);
-                else { if (!(s > 1e-300)) s = 1e-300; W(bi + i) = 1.0 / sqrt(s); }
-            }
-        }
-        for (int i = 0; i < r; i++) {                         // L y = t
-            const int bi = S0 + i * (i + 1) / 2;
-            double s0 = W(i), s1 = 0.0;
-            int k = 0;
-            for (; k + 1 < i; k += 2) { s0 -= W(bi + k) * W(k); s1 -= W(bi + k + 1) * W(k + 1); }
-            if (k < i) s0 -= W(bi + k) * W(k);
-            W(i) = (s0 + s1) * W(bi + i);
-        }
-        double mumax = 0.0;
-        for (int i = r - 1; i >= 0; i--) {                    // L' mu = y
-            double s = W(i);
-            for (int k = i + 1; k < r; k++) s -= W(S0 + k * (k + 1) / 2 + i) * W(k);
-            s *= W(S0 + i * (i + 1) / 2 + i);
-            W(i) = s; mumax = fmax(mumax, fabs(s));
-        }
-        // candidate U = U0 - (A Hinv)[R,:]' mu
-        {
-            double Ur[NU];
+        for (int a = 0; a < nx; a++) lin += W(base + a) * x[a];
+        lin += W(base + nx) * w;
+        double u, mu_u = 0.0, mu_d = 0.0, mu_q = 0.0;
+        if (type == TPI_FREE) u = -lin;
+        else if (type == TPI_UPIN) { u = pin; mu_u = -lin; }
+        else if (type == TPI_DPIN) { u = w + pin; mu_d = -lin; }
+        else { u = pin; mu_q = lin; }
+        mnew = fmax(mnew, fmax(fabs(mu_u), fmax(fabs(mu_d), fabs(mu_q))));
+        if (EMIT) outu(k, u);
+        hard_row(NS + k, u, c.umin[0], c.umax[0], mu_u, c.irhou[0]);
+        if (k == 0) hard_row(NS + NU, u, c.dmin[0] + w, c.dmax[0] + w, mu_d, c.irhod[0]);     // row value u_0, bounds shifted by u_-1
+        else hard_row(NS + NU + k, u - w, c.dmin[0], c.dmax[0], mu_d, c.irhod[0]);
+        if (k == N - 1) hard_row(NS + NU + N, -u, c.dmin[0], c.dmax[0], mu_q, c.irhod[0]);
+        double xn[nx];
 #pragma unroll
-            for (int a = 0; a < NU; a++) Ur[a] = W(U0B + a);
-            for (int p = 0; p < r; p++) {
-                const double* row = P.AHinv + (size_t)((int)W(R0 + p)) * NU; const double mu = W(p);
+        for (int a = 0; a < nx; a++) {
+            double a0 = c.Bd[a] * u, a1 = 0.0;
 #pragma unroll
-                for (int a = 0; a < NU; a++) Ur[a] -= row[a] * mu;
-            }
-#pragma unroll
-            for (int a = 0; a < NU; a++) W(UB + a) = Ur[a];
+            for (int q = 0; q < nx; q += 2) { a0 += c.Ad[a * nx + q] * x[q]; if (q + 1 < nx) a1 += c.Ad[a * nx + q + 1] * x[q + 1]; }
+            xn[a] = a0 + a1;
         }
-        // KKT verification + next sets
-        bool ok = true;
-        const double mutol = 1e-9 * (1.0 + mumax);
-        TpiMask nup, ndn;
-        tpi_rows_of<S>(c, x0, um1, W, UB, [&](int i, double lo, double hi, double, double zi) {
+        w = u;
+#pragma unroll
+        for (int a = 0; a < nx; a++) {
+            x[a] = xn[a];
+            const int i = k * nx + a;
+            const double zi = xn[a], lo = c.xmin[a], hi = c.xmax[a];
             const bool su = up.get(i), sd = dn.get(i);
-            bool nu_, nd_;
-            if (soft_on && i < NS) {
-                nu_ = zi > hi + 1e-11 * (1.0 + fabs(hi)); nd_ = (!nu_) && zi < lo - 1e-11 * (1.0 + fabs(lo));
-                if (nu_ != su || nd_ != sd) {
-                    const bool hi_side = (su || nu_) && !(sd || nd_), lo_side = (sd || nd_) && !(su || nu_);
-                    const double gap = hi_side ? fabs(zi - hi) : (lo_side ? fabs(zi - lo) : 1e300);
-                    const double bnd = hi_side ? hi : lo;
-                    if (!(gap <= 1e-11 * (1.0 + fabs(bnd)))) ok = false;
-                }
-            } else {
-                const double mu = (su || sd) ? W(tpi_rank(act, i)) : 0.0;
-                const bool vu = zi > hi + 1e-9 * (1.0 + fabs(hi)), vd = zi < lo - 1e-9 * (1.0 + fabs(lo));
-                if (vu || vd || (su && mu < -mutol) || (sd && mu > mutol)) ok = false;
-                nu_ = vu || (!vd && su && mu > 0.0);
-                nd_ = (!nu_) && (vd || (sd && mu < 0.0));
+            if (EMIT) { out(i, zi, su ? P.rho_e * (zi - hi) : (sd ? P.rho_e * (zi - lo) : 0.0), c.irhox[a]); continue; }
+            const bool nu_ = zi > hi + 1e-11 * (1.0 + fabs(hi)), nd_ = (!nu_) && zi < lo - 1e-11 * (1.0 + fabs(lo));
+            if (nu_ != su || nd_ != sd) {
+                const bool hi_side = (su || nu_) && !(sd || nd_), lo_side = (sd || nd_) && !(su || nu_);
+                const double gap = hi_side ? fabs(zi - hi) : (lo_side ? fabs(zi - lo) : 1e300);
+                const double bnd = hi_side ? hi : lo;
+                if (!(gap <= 1e-11 * (1.0 + fabs(bnd)))) ok = false;
             }
             nup.set(i, nu_); ndn.set(i, nd_);
-        });
-        if (ok) return step + 1;      // `up`/`dn` still describe the verified working set; W(0..r) = mu by rank
+        }
+    }
+    mumax = mnew;
+    return ok;
+}
+
+// returns steps used (>0) when KKT-verified (then `up`/`dn` hold the verified set and the gains in W are those of
+// the accepted solve, ready for the emit pass), 0 otherwise
+template <class S>
+BMPC_HD int tpi_polish_riccati(const TpiRicParams<S>& P, TpiAcc W, const double* x0, const double* um1, const double* xref,
+                               TpiMask& up, TpiMask& dn, int max_steps) {
+    double mumax = 0.0;
+#pragma unroll 1
+    for (int step = 0; step < max_steps; step++) {
+        tpi_ric_backward<S>(P, W, xref, up, dn);
+        TpiMask nup, ndn;
+        const bool ok = tpi_ric_forward<S, false>(P, W, x0, um1, up, dn, nup, ndn, mumax,
+                                                  [](int, double, double, double) {}, [](int, double) {});
+        if (ok) return step + 1;
         up = nup; dn = ndn;
     }
     return 0;
@@ -455,13 +517,13 @@ inline void tpi_fill_common(const double* sys, const BmpcSysOff& o, TpiCommon<S>
     c.sigma = sys[o.scal + BMPC_S_SIGMA]; c.alpha = sys[o.scal + BMPC_S_ALPHA];
     for (int a = 0; a < nx; a++) {
         c.xmin[a] = sys[o.lo0 + nx + a]; c.xmax[a] = sys[o.hi0 + nx + a];
-        const double rho = sys[o.rho + nx + a]; c.rhox[a] = rho;
+        const double rho = sys[o.rho + nx + a]; c.rhox[a] = rho; c.irhox[a] = 1.0 / rho;
         if (rho_e > 0.0) { c.c1x[a] = rho / (rho + rho_e); c.c2x[a] = rho_e / (rho + rho_e); }
         else { c.c1x[a] = 0.0; c.c2x[a] = 1.0; }
     }
     for (int b = 0; b < nu; b++) {
-        c.umin[b] = sys[o.lo0 + NX + b]; c.umax[b] = sys[o.hi0 + NX + b]; c.rhou[b] = sys[o.rho + NX + b];
-        c.dmin[b] = sys[o.lo0 + NX + NU + b]; c.dmax[b] = sys[o.hi0 + NX + NU + b]; c.rhod[b] = sys[o.rho + NX + NU + b];
+        c.umin[b] = sys[o.lo0 + NX + b]; c.umax[b] = sys[o.hi0 + NX + b]; c.rhou[b] = sys[o.rho + NX + b]; c.irhou[b] = 1.0 / c.rhou[b];
+        c.dmin[b] = sys[o.lo0 + NX + NU + b]; c.dmax[b] = sys[o.hi0 + NX + NU + b]; c.rhod[b] = sys[o.rho + NX + NU + b]; c.irhod[b] = 1.0 / c.rhod[b];
     }
 }
 template <class S>
@@ -477,8 +539,8 @@ inline void tpi_fill_admm(const double* sys, const BmpcSysOff& o, TpiAdmmParams<
         }
 }
 template <class S>
-inline void tpi_fill_polish(const double* sys, const BmpcSysOff& o, const double* dev_sys, TpiPolishParams<S>& P) {
+inline void tpi_fill_riccati(const double* sys, const BmpcSysOff& o, TpiRicParams<S>& P) {
     tpi_fill_common<S>(sys, o, P.c);
-    for (int i = 0; i < S::NU * S::NU; i++) P.Hinv[i] = sys[o.Hinv + i];
-    P.M = dev_sys + o.M; P.AHinv = dev_sys + o.AHinv;
+    for (int i = 0; i < S::nx * S::nx; i++) { P.Qx[i] = sys[o.Qx + i]; P.QxN[i] = sys[o.QxN + i]; }
+    P.Qu = sys[o.Qu]; P.QDu = sys[o.QDu]; P.uref = sys[o.uref]; P.rho_e = sys[o.scal + BMPC_S_RHOE];
 }

@@ -70,8 +70,8 @@ class EmuSystem:
         self.cold = 0
         return U, st, it.value, ps.value, res
 
-    def tpi_step(self, x0, um1, xref, first_iters=10, pdas_steps=4):
-        """TPI fast path (ADMM + TPI polish) on the same generic-layout state; returns (U, polish_steps)."""
+    def tpi_step(self, x0, um1, xref, first_iters=10, pdas_steps=8):
+        """TPI fast path (ADMM + Riccati polish) on the same generic-layout state; returns (U, polish_steps)."""
         x0 = np.ascontiguousarray(x0, float); um1 = np.ascontiguousarray(um1, float); xref = np.ascontiguousarray(xref, float)
         U = np.zeros(self.NU)
         f = self.L.emu_tpi_step

@@ -69,38 +69,32 @@ int emu_solve(int nx, int nu, int Np, int Nc, const double* sys, const double* x
 
 }  // extern "C"
 
-// TPI fast path for one instance (shape must be one of the compiled ones): first_iters ADMM iterations + TPI polish.
-// x [NU], v [mc] use the GENERIC layout (in/out) exactly like the device kernels.  Returns polish steps (>0 verified,
-// 0 not verified, -1 working set too large, -100 shape not compiled).
+// TPI fast path for one instance (nu == 1, Nc == Np shapes): first_iters ADMM iterations + Riccati polish on the
+// generic-layout state (x [NU], v [mc], in/out) exactly like the device kernels.  Returns polish steps (>0 verified,
+// 0 not verified, -100 shape not compiled).
 template <class S>
 static int emu_tpi_run(const double* sys, const double* x0, const double* um1, const double* xref, int cold, double* x,
-                       double* v, double* Uout, int first_iters, int pdas_steps) {
+                           double* v, double* Uout, int first_iters, int pdas_steps) {
     BmpcDims d = bmpc_make_dims(S::nx, S::nu, S::Np, S::Nc); BmpcSysOff o = bmpc_make_off(d);
-    TpiAdmmParams<S>* PA = new TpiAdmmParams<S>(); TpiPolishParams<S>* PP = new TpiPolishParams<S>();
-    tpi_fill_admm<S>(sys, o, *PA); tpi_fill_polish<S>(sys, o, sys, *PP);
+    TpiAdmmParams<S>* PA = new TpiAdmmParams<S>(); TpiRicParams<S>* PR = new TpiRicParams<S>();
+    tpi_fill_admm<S>(sys, o, *PA); tpi_fill_riccati<S>(sys, o, *PR);
     double* col = (double*)calloc(S::PROWS + S::MT + 8, sizeof(double));
     for (int i = 0; i < S::MT; i++) col[i] = v[i + S::nx];
     TpiAcc V{col, 1};
     tpi_admm<S>(*PA, V, x0, um1, xref, x, first_iters, cold != 0);
     for (int i = 0; i < S::MT; i++) v[i + S::nx] = col[i];
     for (int i = 0; i < S::nx; i++) v[i] = x0[i];
-    double g[S::NU];
-    tpi_linear_term<S>(PP->c, x0, um1, xref, g);
     TpiMask up, dn;
-    tpi_for_rows<S>(PP->c, um1, [&](int i, double lo, double hi, double) {
+    tpi_for_rows<S>(PR->c, um1, [&](int i, double lo, double hi, double) {
         up.set(i, col[i] > hi + 1e-9 * (1.0 + fabs(hi))); dn.set(i, col[i] < lo - 1e-9 * (1.0 + fabs(lo))); });
-    int ps = tpi_polish<S>(*PP, V, x0, um1, g, up, dn, pdas_steps);
+    int ps = tpi_polish_riccati<S>(*PR, V, x0, um1, xref, up, dn, pdas_steps);
     if (ps > 0) {
-        TpiMask act; act.w[0] = up.w[0] | dn.w[0]; act.w[1] = up.w[1] | dn.w[1];
-        const TpiCommon<S>& c = PP->c;
-        tpi_rows_of<S>(c, x0, um1, V, S::UB, [&](int i, double, double, double rho, double zi) {
-            double mu = act.get(i) ? V(tpi_rank(act, i)) : 0.0;
-            V(S::S0 + i) = zi + mu / rho;
-        });
-        for (int i = 0; i < S::MT; i++) v[i + S::nx] = col[S::S0 + i];
-        for (int a = 0; a < S::NU; a++) { Uout[a] = col[S::UB + a]; x[a] = col[S::UB + a]; }
+        TpiMask t1, t2; double mm = 0.0;
+        tpi_ric_forward<S, true>(*PR, V, x0, um1, up, dn, t1, t2, mm,
+            [&](int i, double zi, double mu, double irho) { v[i + S::nx] = zi + mu * irho; },
+            [&](int j, double u) { Uout[j] = u; x[j] = u; });
     }
-    free(col); delete PA; delete PP;
+    free(col); delete PA; delete PR;
     return ps;
 }
 

@@ -90,7 +90,7 @@ def test_tpi_fast_path_closed_loop(name, steps):
     x = np.array(cfg["x0"], float); um1 = np.array(cfg["uminus1"], float)
     used = 0
     for t in range(steps):
-        U, ps = E.tpi_step(x, um1, cfg["xref"], pdas_steps=6)
+        U, ps = E.tpi_step(x, um1, cfg["xref"], pdas_steps=8)
         if ps <= 0:
             U, st, *_ = E.solve(x, um1, cfg["xref"]); assert st == 1
         else:
@@ -106,7 +106,7 @@ def test_tpi_fast_path_random_batch():
         E = EmuSystem(cfg)
         x = g["X0"][b].copy(); um1 = np.zeros(1)
         for t in range(g["U"].shape[0]):
-            U, ps = E.tpi_step(x, um1, g["Xref"][b], pdas_steps=6)
+            U, ps = E.tpi_step(x, um1, g["Xref"][b], pdas_steps=8)
             if ps <= 0:
                 U, st, *_ = E.solve(x, um1, g["Xref"][b]); assert st == 1
             assert abs(U[0] - g["U"][t, b, 0]) < 1e-6
