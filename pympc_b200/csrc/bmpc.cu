@@ -410,7 +410,7 @@ static std::string g_create_err;
 template <class S>
 static void launch_tpi_round(bmpc_handle* h, int B, int niter, cudaEvent_t mid) {
     const int grid = (B + 31) / 32;
-    k_tpi_admm<S><<<grid, 32, S::MT * TPI_STR * 8, h->stream>>>(*(const TpiAdmmParams<S>*)h->tpi_admm_params, h->I, B, niter, h->cold ? 1 : 0);
+    k_tpi_admm<S><<<grid, 32, S::AROWS * TPI_STR * 8, h->stream>>>(*(const TpiAdmmParams<S>*)h->tpi_admm_params, h->I, B, niter, h->cold ? 1 : 0);
     cudaEventRecord(mid, h->stream);
     k_tpi_polish<S><<<grid, 32, S::PROWS * TPI_STR * 8, h->stream>>>(*(const TpiRicParams<S>*)h->tpi_polish_params, h->I, B,
                                                                      h->tpi_pdas_steps, h->listB, h->counts, h->I.u0);
@@ -620,13 +620,13 @@ int bmpc_setup(bmpc_handle* h, const double* Ad, const double* Bd, const double*
             auto* pa = (TpiAdmmParams<TpiPend>*)malloc(sizeof(TpiAdmmParams<TpiPend>)); tpi_fill_admm<TpiPend>(hs.data(), o, *pa);
             auto* pp = (TpiRicParams<TpiPend>*)malloc(sizeof(TpiRicParams<TpiPend>)); tpi_fill_riccati<TpiPend>(hs.data(), o, *pp);
             h->tpi_admm_params = pa; h->tpi_polish_params = pp;
-            BMPC_CUDA(cudaFuncSetAttribute(k_tpi_admm<TpiPend>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TpiPend::MT * TPI_STR * 8)));
+            BMPC_CUDA(cudaFuncSetAttribute(k_tpi_admm<TpiPend>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TpiPend::AROWS * TPI_STR * 8)));
             BMPC_CUDA(cudaFuncSetAttribute(k_tpi_polish<TpiPend>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TpiPend::PROWS * TPI_STR * 8)));
         } else {
             auto* pa = (TpiAdmmParams<TpiPm>*)malloc(sizeof(TpiAdmmParams<TpiPm>)); tpi_fill_admm<TpiPm>(hs.data(), o, *pa);
             auto* pp = (TpiRicParams<TpiPm>*)malloc(sizeof(TpiRicParams<TpiPm>)); tpi_fill_riccati<TpiPm>(hs.data(), o, *pp);
             h->tpi_admm_params = pa; h->tpi_polish_params = pp;
-            BMPC_CUDA(cudaFuncSetAttribute(k_tpi_admm<TpiPm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TpiPm::MT * TPI_STR * 8)));
+            BMPC_CUDA(cudaFuncSetAttribute(k_tpi_admm<TpiPm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TpiPm::AROWS * TPI_STR * 8)));
             BMPC_CUDA(cudaFuncSetAttribute(k_tpi_polish<TpiPm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TpiPm::PROWS * TPI_STR * 8)));
         }
     }

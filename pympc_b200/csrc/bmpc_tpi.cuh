@@ -26,6 +26,7 @@ struct TpiShape {
     static constexpr int MT = NS + NU + ND;
     static constexpr int NX = (NPc + 1) * NXc;
     static constexpr int mc = NX + NU + ND;
+    static constexpr int AROWS = MT + NCc * NUc;             // ADMM column: v rows + g'
     static constexpr int PROWS = (MT > 6 * NPc ? MT : 6 * NPc) + 1;   // polish workspace rows: v (load) / Riccati gains
 };
 
@@ -55,10 +56,11 @@ struct TpiAcc {
 
 template <class S>
 BMPC_HD double tpi_prox_x(const TpiCommon<S>& c, int a, double v) {
-    const double lo = c.xmin[a], hi = c.xmax[a];
-    return v > hi ? c.c1x[a] * v + c.c2x[a] * hi : (v < lo ? c.c1x[a] * v + c.c2x[a] * lo : v);
+    // soft box: z = v + c2 (clamp(v) - v), c2 = eps_feas / (rho + eps_feas); hard box: c2 = 1.  Branch-free.
+    const double t = fmin(fmax(v, c.xmin[a]), c.xmax[a]);
+    return fma(c.c2x[a], t - v, v);
 }
-BMPC_HD double tpi_clamp(double v, double lo, double hi) { return v > hi ? hi : (v < lo ? lo : v); }
+BMPC_HD double tpi_clamp(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
 
 template <class S>
 BMPC_HD void tpi_dbounds(const TpiCommon<S>& c, const double* um1, int rr, double& lo, double& hi) {
@@ -89,12 +91,16 @@ BMPC_HD void tpi_admm(const TpiAdmmParams<S>& P, TpiAcc V, const double* x0, con
                       double* x, int niter, bool cold) {
     constexpr int nx = S::nx, nu = S::nu, Np = S::Np, Nc = S::Nc, NS = S::NS, NU = S::NU, ND = S::ND;
     const TpiCommon<S>& c = P.c;
-    double gp[NU];
-    tpi_linear_term<S>(c, x0, um1, xref, gp);
+    // g' = g + B' R_x Acal x0 is parked in rows [MT, MT+NU) of this thread's column (read once per iteration)
+    {
+        double gp[NU];
+        tpi_linear_term<S>(c, x0, um1, xref, gp);
 #pragma unroll
-    for (int a = 0; a < NU; a++) {
+        for (int a = 0; a < NU; a++) {
 #pragma unroll
-        for (int q = 0; q < nx; q++) gp[a] += P.Gcc[a * nx + q] * x0[q];
+            for (int q = 0; q < nx; q++) gp[a] += P.Gcc[a * nx + q] * x0[q];
+            V(S::MT + a) = gp[a];
+        }
     }
     if (cold) {
         // x = 0, v = A x + cc : free response on the state rows, zeros elsewhere
@@ -119,37 +125,31 @@ BMPC_HD void tpi_admm(const TpiAdmmParams<S>& P, TpiAcc V, const double* x0, con
 #pragma unroll
         for (int a = 0; a < NU; a++) x[a] = 0.0;
     }
+    // One ADMM iteration = two fused sweeps over the horizon (everything unrolled, all register indices static):
+    //  backward: lam_k = w_k + Ad' lam_{k+1}; as soon as stage j = k-1 knows lam_{j+1} its r_s is final and is scattered
+    //            at once into the NU independent accumulators xt += Kinv[:, s] r_s  (ILP beside the serial lam chain)
+    //  forward : x_{k+1} = Ad x_k + Bd xt_k with the row updates v += alpha (zt - prox(v)) riding along
+    auto wrow_d = [&](int rr) {                       // w = rho (2 clamp(v) - v) of delta-u row rr
+        double lo, hi; tpi_dbounds<S>(c, um1, rr, lo, hi);
+        const double v = V(NS + NU + rr);
+        return c.rhod[rr % nu] * (2.0 * tpi_clamp(v, lo, hi) - v);
+    };
 #pragma unroll 1
     for (int it = 0; it < niter; it++) {
-        double r[NU];
+        double xt[NU], lam[nx], hold[nu];
 #pragma unroll
-        for (int a = 0; a < NU; a++) r[a] = c.sigma * x[a] - gp[a];
-        // input rows
-#pragma unroll
-        for (int a = 0; a < NU; a++) {
-            double v = V(NS + a);
-            double z = tpi_clamp(v, c.umin[a % nu], c.umax[a % nu]);
-            r[a] += c.rhou[a % nu] * (2.0 * z - v);
-        }
-        // delta-u rows (reference quirk: scalar shift)
-#pragma unroll
-        for (int rr = 0; rr < ND; rr++) {
-            double lo, hi; tpi_dbounds<S>(c, um1, rr, lo, hi);
-            double v = V(NS + NU + rr);
-            double w = c.rhod[rr % nu] * (2.0 * tpi_clamp(v, lo, hi) - v);
-            if (rr < nu) r[rr] += w;
-            else { r[rr - nu] -= w; if (rr - nu + 1 < NU) r[rr - nu + 1] += w; }
-        }
-        // state rows: adjoint sweep  lam_k = w_k + Ad' lam_{k+1} ; r_j += Bd' lam_{j+1}
-        double lam[nx];
+        for (int a = 0; a < NU; a++) xt[a] = 0.0;
 #pragma unroll
         for (int q = 0; q < nx; q++) lam[q] = 0.0;
+#pragma unroll
+        for (int b = 0; b < nu; b++) hold[b] = 0.0;
+        double e_cur = wrow_d(nu + NU - 1);           // row nu+s holds -U[s] + U[s+1]; visited by descending s
 #pragma unroll
         for (int k = Np; k >= 1; k--) {
             double ln[nx];
 #pragma unroll
             for (int a = 0; a < nx; a++) {
-                double v = V((k - 1) * nx + a);
+                const double v = V((k - 1) * nx + a);
                 double acc = c.rhox[a] * (2.0 * tpi_prox_x<S>(c, a, v) - v);
 #pragma unroll
                 for (int q = 0; q < nx; q++) acc += c.Ad[q * nx + a] * lam[q];
@@ -157,25 +157,31 @@ BMPC_HD void tpi_admm(const TpiAdmmParams<S>& P, TpiAcc V, const double* x0, con
             }
 #pragma unroll
             for (int a = 0; a < nx; a++) lam[a] = ln[a];
-            const int j = (k - 1 < Nc - 1) ? (k - 1) : (Nc - 1);
+            if (k - 1 > Nc - 1) {                     // held input (Nc < Np): collect Bd' lam_k
 #pragma unroll
-            for (int b = 0; b < nu; b++) {
-                double acc = 0.0;
+                for (int b = 0; b < nu; b++) {
 #pragma unroll
-                for (int q = 0; q < nx; q++) acc += c.Bd[q * nu + b] * lam[q];
-                r[j * nu + b] += acc;
+                    for (int q = 0; q < nx; q++) hold[b] += c.Bd[q * nu + b] * lam[q];
+                }
+            } else {
+                const int j = k - 1;
+#pragma unroll
+                for (int b = nu - 1; b >= 0; b--) {
+                    const int s2 = j * nu + b;
+                    double r = c.sigma * x[s2] - V(S::MT + s2) + ((j == Nc - 1) ? hold[b] : 0.0);
+#pragma unroll
+                    for (int q = 0; q < nx; q++) r += c.Bd[q * nu + b] * lam[q];
+                    const double vu = V(NS + s2);
+                    r += c.rhou[b] * (2.0 * tpi_clamp(vu, c.umin[b], c.umax[b]) - vu);
+                    const double e_prev = (s2 >= 1) ? wrow_d(nu + s2 - 1) : 0.0;
+                    r += e_prev - e_cur;
+                    if (s2 < nu) r += wrow_d(s2);
+                    e_cur = e_prev;
+#pragma unroll
+                    for (int a = 0; a < NU; a++) xt[a] += P.Kinv[a * NU + s2] * r;
+                }
             }
         }
-        // xt = Kinv r
-        double xt[NU];
-#pragma unroll
-        for (int a = 0; a < NU; a++) {
-            double acc = 0.0;
-#pragma unroll
-            for (int b = 0; b < NU; b++) acc += P.Kinv[a * NU + b] * r[b];
-            xt[a] = acc;
-        }
-        // forward simulation: zt on the state rows, v += alpha (zt - z)
         double xk[nx];
 #pragma unroll
         for (int q = 0; q < nx; q++) xk[q] = x0[q];
@@ -185,34 +191,40 @@ BMPC_HD void tpi_admm(const TpiAdmmParams<S>& P, TpiAcc V, const double* x0, con
             double xn[nx];
 #pragma unroll
             for (int a = 0; a < nx; a++) {
-                double acc = 0.0;
+                double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-                for (int q = 0; q < nx; q++) acc += c.Ad[a * nx + q] * xk[q];
+                for (int b = 0; b < nu; b++) a0 += c.Bd[a * nu + b] * xt[j * nu + b];
 #pragma unroll
-                for (int b = 0; b < nu; b++) acc += c.Bd[a * nu + b] * xt[j * nu + b];
-                xn[a] = acc;
+                for (int q = 0; q < nx; q += 2) { a0 += c.Ad[a * nx + q] * xk[q]; if (q + 1 < nx) a1 += c.Ad[a * nx + q + 1] * xk[q + 1]; }
+                xn[a] = a0 + a1;
             }
 #pragma unroll
             for (int a = 0; a < nx; a++) {
                 xk[a] = xn[a];
-                double v = V((k - 1) * nx + a);
+                const double v = V((k - 1) * nx + a);
                 V((k - 1) * nx + a) = v + c.alpha * (xn[a] - tpi_prox_x<S>(c, a, v));
             }
-        }
+            if (k - 1 <= Nc - 1) {
 #pragma unroll
-        for (int a = 0; a < NU; a++) {
-            double v = V(NS + a);
-            V(NS + a) = v + c.alpha * (xt[a] - tpi_clamp(v, c.umin[a % nu], c.umax[a % nu]));
+                for (int b = 0; b < nu; b++) {
+                    const int s2 = (k - 1) * nu + b;
+                    const double vu = V(NS + s2);
+                    V(NS + s2) = vu + c.alpha * (xt[s2] - tpi_clamp(vu, c.umin[b], c.umax[b]));
+                    {
+                        double lo, hi; tpi_dbounds<S>(c, um1, nu + s2, lo, hi);
+                        const double v = V(NS + NU + nu + s2);
+                        const double zt = -xt[s2] + (s2 + 1 < NU ? xt[s2 + 1] : 0.0);
+                        V(NS + NU + nu + s2) = v + c.alpha * (zt - tpi_clamp(v, lo, hi));
+                    }
+                    if (s2 < nu) {
+                        double lo, hi; tpi_dbounds<S>(c, um1, s2, lo, hi);
+                        const double v = V(NS + NU + s2);
+                        V(NS + NU + s2) = v + c.alpha * (xt[s2] - tpi_clamp(v, lo, hi));
+                    }
+                    x[s2] += c.alpha * (xt[s2] - x[s2]);
+                }
+            }
         }
-#pragma unroll
-        for (int rr = 0; rr < ND; rr++) {
-            double lo, hi; tpi_dbounds<S>(c, um1, rr, lo, hi);
-            double v = V(NS + NU + rr);
-            double zt = rr < nu ? xt[rr] : (-xt[rr - nu] + (rr - nu + 1 < NU ? xt[rr - nu + 1] : 0.0));
-            V(NS + NU + rr) = v + c.alpha * (zt - tpi_clamp(v, lo, hi));
-        }
-#pragma unroll
-        for (int a = 0; a < NU; a++) x[a] += c.alpha * (xt[a] - x[a]);
     }
 }
 
