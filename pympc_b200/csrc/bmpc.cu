@@ -391,6 +391,8 @@ struct bmpc_handle {
     bmpc_stats stats;
     std::string err;
     size_t smem_admm = 0, smem_polish = 0;
+    // low-latency CTA-per-instance variant for the few stragglers of a warp-team / TPI handle
+    int fb_team = 0, fb_rmax = 0; size_t fb_smem_admm = 0, fb_smem_polish = 0;
     int tpi_kind = 0;                  // 0 none, 1 pendulum shape (4,1,20,20), 2 point-mass shape (2,1,20,20)
     void *tpi_admm_params = nullptr, *tpi_polish_params = nullptr;   // host copies of the parameter blocks
     int tpi_pdas_steps = 8;
@@ -422,7 +424,7 @@ extern "C" {
 void bmpc_default_config(bmpc_config* c) {
     memset(c, 0, sizeof(*c));
     c->Np = 20; c->Nc = 0; c->batch = 1; c->device = 0; c->soft_on = 1;
-    c->max_iter = 4000; c->first_iters = 10; c->pdas_steps = 10; c->rmax = 0; c->polish = 1;
+    c->max_iter = 4000; c->first_iters = 3; c->pdas_steps = 10; c->rmax = 0; c->polish = 1;
     c->team_threads = 0; c->warps_per_block = 0; c->fast_path = 1;
     c->eps_feas = 1e6; c->rho = 0.0; c->sigma = 1e-6; c->alpha = 1.6; c->eps_abs = 1e-3; c->eps_rel = 1e-3;
 }
@@ -467,6 +469,15 @@ static int configure_launch(bmpc_handle* h) {
         h->smem_polish = (size_t)wpb * polish_smem_doubles(d, rmax) * 8;
         BMPC_CUDA(cudaFuncSetAttribute(k_admm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_admm));
         BMPC_CUDA(cudaFuncSetAttribute(k_polish<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_polish));
+        // stragglers (instances the first round did not verify) are few and latency-bound: give each a whole CTA
+        int frmax = d.mc < 96 ? d.mc : 96;
+        while (frmax > 8 && polish_smem_doubles(d, frmax) * 8 > budget) frmax -= 8;
+        if (polish_smem_doubles(d, frmax) * 8 <= budget) {
+            h->fb_team = 128; h->fb_rmax = frmax;
+            h->fb_smem_admm = admm_smem_doubles(d) * 8; h->fb_smem_polish = polish_smem_doubles(d, frmax) * 8;
+            BMPC_CUDA(cudaFuncSetAttribute(k_admm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fb_smem_admm));
+            BMPC_CUDA(cudaFuncSetAttribute(k_polish<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fb_smem_polish));
+        }
     } else {
         h->wpb = team / 32;
         h->smem_admm = admm_smem_doubles(d) * 8;
@@ -490,7 +501,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     h->cfg = *cfg;
     if (h->cfg.Nc <= 0) h->cfg.Nc = h->cfg.Np;
     if (h->cfg.max_iter <= 0) h->cfg.max_iter = 4000;
-    if (h->cfg.first_iters <= 0) h->cfg.first_iters = 10;
+    if (h->cfg.first_iters <= 0) h->cfg.first_iters = 3;
     if (h->cfg.pdas_steps <= 0) h->cfg.pdas_steps = 10;
     h->d = bmpc_make_dims(cfg->nx, cfg->nu, h->cfg.Np, h->cfg.Nc);
     h->o = bmpc_make_off(h->d);
@@ -653,9 +664,15 @@ int bmpc_update(bmpc_handle* h, const double* x0, const double* uminus1, const d
     return BMPC_OK;
 }
 
+static bool use_fallback_team(const bmpc_handle* h, const int32_t* list, int count) {
+    return h->team == 32 && h->fb_team && list != nullptr && count <= 4096;
+}
+
 static void launch_admm(bmpc_handle* h, const int32_t* list, int count, int niter, int do_prep) {
     const int cold = h->cold ? 1 : 0;
-    if (h->team == 32) {
+    if (use_fallback_team(h, list, count)) {
+        k_admm<false><<<count, h->fb_team, h->fb_smem_admm, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode);
+    } else if (h->team == 32) {
         int grid = (count + h->wpb - 1) / h->wpb;
         k_admm<true><<<grid, h->wpb * 32, h->smem_admm, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode);
     } else {
@@ -665,7 +682,9 @@ static void launch_admm(bmpc_handle* h, const int32_t* list, int count, int nite
 }
 
 static void launch_polish(bmpc_handle* h, const int32_t* list, int count, int32_t* next_list, int32_t* next_count) {
-    if (h->team == 32) {
+    if (use_fallback_team(h, list, count)) {
+        k_polish<false><<<count, h->fb_team, h->fb_smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->fb_rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0);
+    } else if (h->team == 32) {
         int grid = (count + h->wpb - 1) / h->wpb;
         k_polish<true><<<grid, h->wpb * 32, h->smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0);
     } else {
@@ -720,7 +739,7 @@ int bmpc_solve(bmpc_handle* h) {
         h->stats.polish_steps += h->h_count[1];
         list = nxt; int32_t* tmp = cur; cur = nxt; nxt = tmp;
         // polish mode: cumulative 10, 25, 50, 100, 200, ...; pure ADMM: OSQP's check_termination = 25
-        chunk = h->cfg.polish ? (total < 25 ? 25 - total : total) : 25;
+        chunk = h->cfg.polish ? (total < 25 ? 25 - total : total) : 25;   // cumulative first_iters, 25, 50, 100, ...
     }
     if (!h->cfg.polish) {
         // pure-ADMM mode: every instance gets its status from OSQP's criterion on its last residuals

@@ -155,7 +155,8 @@ class MPCController:
         self.res = None
         self.x0_rh = None
         self.uminus1_rh = None
-        self.J_CNST = None
+        self._J_CNST = None
+        self._J_dirty = True
         self._pin = {}
         self._status = None
         self._u0 = None
@@ -263,8 +264,9 @@ class MPCController:
                 (self.Ad, self.Bd, Qx, QxN, Qu, QDu, self.xmin, self.xmax, self.umin, self.umax, self.Dumin, self.Dumax, self.uref)]
         self._check(L.bmpc_setup(self._h, *[ptr(a) for a in args]))
         self._Qx_d, self._QxN_d, self._Qu_d, self._QDu_d = Qx, QxN, Qu, QDu
+        self._um1_for_J = self.uminus1_rh
         self._push(self.x0_rh, self.uminus1_rh, self.xref)
-        self._compute_J_CNST()
+        self._J_dirty = True
         if solve:
             self.solve()
 
@@ -290,8 +292,9 @@ class MPCController:
         if xref is not None:
             self.xref = xref
         # u=None: the device already holds the previously output control as uminus1 (committed by output(), Q9)
+        self._um1_for_J = self.uminus1_rh
         self._push(x, u, xref)
-        self._compute_J_CNST()
+        self._J_dirty = True           # J_CNST is recomputed lazily (it is O(B) host work and rarely read)
         if solve:
             self.solve()
 
@@ -363,12 +366,25 @@ class MPCController:
         return self.output()
 
     # ------------------------------------------------------------------ extras
+    @property
+    def J_CNST(self):
+        """Constant term of the cost (mpc.py:412-442), evaluated on demand."""
+        if self._J_dirty and self.uminus1_rh is not None:
+            self._compute_J_CNST()
+            self._J_dirty = False
+        return self._J_CNST
+
+    @J_CNST.setter
+    def J_CNST(self, value):
+        self._J_CNST = value
+        self._J_dirty = False
+
     def _compute_J_CNST(self):
         """Constant of the cost exactly as the reference accumulates it (mpc.py:412-442; quirk Q7)."""
         B, Np = self._B, self.Np
         J = np.zeros(B)
         uref = self.uref
-        um1 = np.broadcast_to(np.asarray(self.uminus1_rh, dtype=float).reshape(-1, self.nu), (B, self.nu))
+        um1 = np.broadcast_to(np.asarray(self._um1_for_J, dtype=float).reshape(-1, self.nu), (B, self.nu))
         if self.JX_ON and self.COMPUTE_J_CNST:
             arr, rows = self._xref_device_layout(self.xref)
             if rows == 1:
@@ -382,7 +398,7 @@ class MPCController:
             J += 0.5 * Np * (uref @ (self._Qu_d @ uref))
         if self.JDU_ON:
             J += 0.5 * np.einsum('bi,ij,bj->b', um1, self._QDu_d, um1)
-        self.J_CNST = J if self.batch is not None else float(J[0])
+        self._J_CNST = J if self.batch is not None else float(J[0])
 
     def stats(self):
         """Counters of the last solve (ADMM iterations, rounds, device time of the kernels)."""
