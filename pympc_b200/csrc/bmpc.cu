@@ -296,12 +296,21 @@ __device__ __forceinline__ void tpi_load_v(const BmpcInst& I, int inst0, int nva
 }
 
 template <class S>
-__global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmmParams<S> P, BmpcInst I, int B, int niter, int cold) {
+__global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmmParams<S> P, BmpcInst I, const int32_t* __restrict__ list, int B, int niter, int cold) {
+    // list == nullptr: instances blockIdx*32 .. +31 (coalesced transpose of the iterate through shared memory);
+    // list != nullptr: B arbitrary instances (straggler rounds): each thread moves its own rows directly.
     extern __shared__ double smem[];
-    const int lane = threadIdx.x, inst0 = blockIdx.x * 32, inst = inst0 + lane;
-    const int nvalid = (B - inst0) < 32 ? (B - inst0) : 32;
+    const int lane = threadIdx.x, idx0 = blockIdx.x * 32;
+    const int nvalid = (B - idx0) < 32 ? (B - idx0) : 32;
     const bool valid = lane < nvalid;
-    if (!cold) { tpi_load_v<S>(I, inst0, nvalid, smem, 0); __syncwarp(); }
+    const int inst = list ? (valid ? list[idx0 + lane] : 0) : idx0 + lane;
+    TpiAcc V{smem + lane, TPI_STR};
+    if (!cold) {
+        if (list) {
+            if (valid) { const double* src = I.vw + (size_t)inst * S::mc + S::nx; for (int i = 0; i < S::MT; i++) V(i) = src[i]; }
+        } else { tpi_load_v<S>(I, idx0, nvalid, smem, 0); }
+        __syncwarp();
+    }
     double x0[S::nx], um1[S::nu], xref[S::nx], x[S::NU];
 #pragma unroll
     for (int q = 0; q < S::nx; q++) { x0[q] = valid ? I.x0[(size_t)inst * S::nx + q] : 0.0; xref[q] = valid ? I.xref[(size_t)inst * S::nx + q] : 0.0; }
@@ -309,13 +318,21 @@ __global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmm
     for (int q = 0; q < S::nu; q++) um1[q] = valid ? I.um1[(size_t)inst * S::nu + q] : 0.0;
 #pragma unroll
     for (int a = 0; a < S::NU; a++) x[a] = (valid && !cold) ? I.xw[(size_t)inst * S::NU + a] : 0.0;
-    TpiAcc V{smem + lane, TPI_STR};
     if (valid) tpi_admm<S>(P, V, x0, um1, xref, x, niter, cold != 0);
     __syncwarp();
-    double* dst = I.vw + (size_t)inst0 * S::mc;
-    for (int idx = lane; idx < nvalid * S::mc; idx += 32) {
-        int t = idx / S::mc, i = idx - t * S::mc;
-        dst[idx] = (i >= S::nx) ? smem[(i - S::nx) * TPI_STR + t] : I.x0[(size_t)(inst0 + t) * S::nx + i];
+    if (list) {
+        if (valid) {
+            double* dst = I.vw + (size_t)inst * S::mc;
+            for (int i = 0; i < S::MT; i++) dst[S::nx + i] = V(i);
+#pragma unroll
+            for (int q = 0; q < S::nx; q++) dst[q] = x0[q];
+        }
+    } else {
+        double* dst = I.vw + (size_t)idx0 * S::mc;
+        for (int idx = lane; idx < nvalid * S::mc; idx += 32) {
+            int t = idx / S::mc, i = idx - t * S::mc;
+            dst[idx] = (i >= S::nx) ? smem[(i - S::nx) * TPI_STR + t] : I.x0[(size_t)(idx0 + t) * S::nx + i];
+        }
     }
     if (valid) {
 #pragma unroll
@@ -325,12 +342,16 @@ __global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmm
 }
 
 template <class S>
-__global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiRicParams<S> P, BmpcInst I, int B, int max_steps,
+__global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiRicParams<S> P, BmpcInst I, const int32_t* __restrict__ list, int B, int max_steps,
                                                    int32_t* next_list, int32_t* next_count, double* u0_out) {
     extern __shared__ double smem[];
-    const int lane = threadIdx.x, inst0 = blockIdx.x * 32, inst = inst0 + lane;
-    const int nvalid = (B - inst0) < 32 ? (B - inst0) : 32;
-    tpi_load_v<S>(I, inst0, nvalid, smem, 0);
+    const int lane = threadIdx.x, idx0 = blockIdx.x * 32;
+    const int nvalid = (B - idx0) < 32 ? (B - idx0) : 32;
+    const int inst = list ? (lane < nvalid ? list[idx0 + lane] : 0) : idx0 + lane;
+    TpiAcc W{smem + lane, TPI_STR};
+    if (list) {
+        if (lane < nvalid) { const double* src = I.vw + (size_t)inst * S::mc + S::nx; for (int i = 0; i < S::MT; i++) W(i) = src[i]; }
+    } else { tpi_load_v<S>(I, idx0, nvalid, smem, 0); }
     __syncwarp();
     if (lane >= nvalid) return;
     double x0[S::nx], um1[S::nu], xref[S::nx];
@@ -338,7 +359,6 @@ __global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiRi
     for (int q = 0; q < S::nx; q++) { x0[q] = I.x0[(size_t)inst * S::nx + q]; xref[q] = I.xref[(size_t)inst * S::nx + q]; }
 #pragma unroll
     for (int q = 0; q < S::nu; q++) um1[q] = I.um1[(size_t)inst * S::nu + q];
-    TpiAcc W{smem + lane, TPI_STR};
     const TpiCommon<S>& c = P.c;
     TpiMask up, dn;
     tpi_for_rows<S>(c, um1, [&](int i, double lo, double hi, double) {
@@ -410,12 +430,12 @@ static std::string g_create_err;
     } while (0)
 
 template <class S>
-static void launch_tpi_round(bmpc_handle* h, int B, int niter, cudaEvent_t mid) {
-    const int grid = (B + 31) / 32;
-    k_tpi_admm<S><<<grid, 32, S::AROWS * TPI_STR * 8, h->stream>>>(*(const TpiAdmmParams<S>*)h->tpi_admm_params, h->I, B, niter, h->cold ? 1 : 0);
+static void launch_tpi_round(bmpc_handle* h, const int32_t* list, int count, int niter, int32_t* next_list, cudaEvent_t mid) {
+    const int grid = (count + 31) / 32;
+    k_tpi_admm<S><<<grid, 32, S::AROWS * TPI_STR * 8, h->stream>>>(*(const TpiAdmmParams<S>*)h->tpi_admm_params, h->I, list, count, niter, h->cold ? 1 : 0);
     cudaEventRecord(mid, h->stream);
-    k_tpi_polish<S><<<grid, 32, S::PROWS * TPI_STR * 8, h->stream>>>(*(const TpiRicParams<S>*)h->tpi_polish_params, h->I, B,
-                                                                     h->tpi_pdas_steps, h->listB, h->counts, h->I.u0);
+    k_tpi_polish<S><<<grid, 32, S::PROWS * TPI_STR * 8, h->stream>>>(*(const TpiRicParams<S>*)h->tpi_polish_params, h->I, list, count,
+                                                                     h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
     h->stats.launches += 2;
 }
 
@@ -712,11 +732,11 @@ int bmpc_solve(bmpc_handle* h) {
         if (chunk > h->cfg.max_iter - total) chunk = h->cfg.max_iter - total;
         BMPC_CUDA(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 2, h->stream));
         BMPC_CUDA(cudaEventRecord(h->ev[0], h->stream));
-        const bool tpi = round == 0 && h->tpi_kind && h->cfg.polish && h->xref_mode == 0;
+        // fast path (thread-per-instance kernels) for the first rounds; the team kernels take the long tail
+        const bool tpi = h->tpi_kind && h->cfg.polish && h->xref_mode == 0 && total < 200;
         if (tpi) {
-            // fast path: every instance, first_iters ADMM iterations + polish; unfinished ones go to listB (= nxt)
-            if (h->tpi_kind == 1) launch_tpi_round<TpiPend>(h, B, chunk, h->ev[1]);
-            else launch_tpi_round<TpiPm>(h, B, chunk, h->ev[1]);
+            if (h->tpi_kind == 1) launch_tpi_round<TpiPend>(h, list, count, chunk, nxt, h->ev[1]);
+            else launch_tpi_round<TpiPm>(h, list, count, chunk, nxt, h->ev[1]);
         } else {
             launch_admm(h, list, count, chunk, need_prep ? 1 : 0);
             need_prep = false;
