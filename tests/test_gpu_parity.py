@@ -190,3 +190,71 @@ def test_pure_admm_mode_behaves_like_osqp(MPC, osqp_port_lib):
     assert info["status"] == "solved"
     assert abs(u[0] - g["u_seq"][0]) < 5e-2
     K.close()
+
+
+def _oracle_u(cfg, **qp_kw):
+    from oracle.qp_assembly import QPData
+    from oracle.kkt import solve_exact
+    Q = QPData(**cfg, **qp_kw)
+    z, y, r = solve_exact(Q.P, Q.q, Q.A, Q.l, Q.u)
+    return z[Q.NX:Q.NX + Q.NU], Q
+
+
+def test_hidden_flags_like_reference(MPC):
+    """SOFT_ON / JX_ON / JU_ON / JDU_ON (mpc.py:233-238) toggled before setup(): compare with the oracle QP
+    assembled with the same switches."""
+    cfg = point_mass(); cfg["xmax"] = np.array([3.0, 100.0]); cfg["x0"] = np.array([0.1, 0.2])
+    # hard state bounds (SOFT_ON = False): the mpc_no_slack formulation
+    K = MPC(**cfg); K.SOFT_ON = False; K.setup(); u, info = K.output(return_u_seq=True)
+    ref, Q = _oracle_u(cfg, soft=False)
+    assert np.max(np.abs(info["u_seq"].ravel() - ref)) < TOL
+    K.close()
+    # cost switches
+    for flag, zero in (("JU_ON", "Qu"), ("JX_ON", "Qx")):
+        c2 = dict(cfg); c2[zero] = 0 * np.asarray(c2[zero]); 
+        if zero == "Qx":
+            c2["QxN"] = 0 * np.asarray(c2["QxN"])
+        K = MPC(**cfg); setattr(K, flag, False); K.setup(); u, info = K.output(return_u_seq=True)
+        ref, Q = _oracle_u(c2)
+        assert np.max(np.abs(info["u_seq"].ravel() - ref)) < TOL, flag
+        K.close()
+
+
+def test_full_size_mimo_batch(MPC):
+    """BASELINE config 4: MIMO reference-governor shape nx=8, nu=4, Np=40, batch 16 384 (CTA-per-instance team),
+    per-instance random x0; all solved, sampled instances agree with the oracle, hard rows feasible."""
+    cfg = mimo(); B = 16384
+    rng = np.random.default_rng(4)
+    X0 = 0.3 * rng.standard_normal((B, 8))
+    K = MPC(cfg["Ad"], cfg["Bd"], Np=40, x0=X0, xref=cfg["xref"], uminus1=np.zeros(4), batch=B,
+            **{k: cfg[k] for k in ("Qx", "QxN", "Qu", "QDu", "xmin", "xmax", "umin", "umax", "Dumin", "Dumax")})
+    K.setup()
+    X = X0.copy(); U = np.zeros((B, 4))
+    for t in range(2):
+        K.update(X, U); Un, info = K.output(return_u_seq=True)
+        assert K.stats()["unsolved"] == 0
+        for b in rng.integers(0, B, 3):
+            c = dict(cfg); c["x0"] = X[b]; c["uminus1"] = U[b]
+            ref, Q = _oracle_u(c)
+            assert np.max(np.abs(info["u_seq"][b].ravel() - ref)) < TOL, (t, b)
+        assert np.max(np.abs(Un - U)) <= 0.2 + 1e-8          # first delta-u rows
+        U = Un; X = X @ cfg["Ad"].T + U @ cfg["Bd"].T
+    K.close()
+
+
+def test_long_closed_loop_random_batch_stays_solved(MPC):
+    """BASELINE config 3 flavour: per-instance random x0/xref, 150 warm-started closed-loop steps at B = 8192;
+    every step fully solved and the loop converges to the references (soft bound respected up to the slack)."""
+    cfg = pendulum(); B = 8192
+    X0, Xref = pendulum_random(B, seed=0)
+    K = MPC(cfg["Ad"], cfg["Bd"], Np=20, x0=X0, xref=Xref, uminus1=np.zeros(1), batch=B,
+            **{k: cfg[k] for k in ("Qx", "QxN", "Qu", "QDu", "xmin", "xmax", "umin", "umax", "Dumin", "Dumax", "eps_feas")})
+    K.setup()
+    X = X0.copy(); U = np.zeros((B, 1)); worst = 0
+    for t in range(150):
+        K.update(X, U); U = K.output()
+        worst = max(worst, K.stats()["unsolved"])
+        X = X @ cfg["Ad"].T + U @ cfg["Bd"].T
+    assert worst == 0
+    assert np.max(np.abs(X[:, 0] - Xref[:, 0])) < 5e-3 and np.max(np.abs(X[:, 2])) < 1e-3
+    K.close()
