@@ -41,6 +41,11 @@ struct WarpTeam {
         total = __popc(b);
         return __popc(b & ((1u << tid) - 1u));
     }
+    __device__ __forceinline__ int warp() const { return 0; }
+    __device__ __forceinline__ int nwarps() const { return 1; }
+    __device__ __forceinline__ int lane() const { return tid; }
+    __device__ __forceinline__ int lanes() const { return 32; }
+    __device__ __forceinline__ double wsum(double v) { return sum(v); }
 };
 
 struct BlockTeam {
@@ -79,6 +84,15 @@ struct BlockTeam {
         __syncthreads();
         total = tot;
         return off + __popc(b & ((1u << (tid & 31)) - 1u));
+    }
+    __device__ __forceinline__ int warp() const { return tid >> 5; }
+    __device__ __forceinline__ int nwarps() const { return n >> 5; }
+    __device__ __forceinline__ int lane() const { return tid & 31; }
+    __device__ __forceinline__ int lanes() const { return 32; }
+    __device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        return v;
     }
 };
 
@@ -638,7 +652,8 @@ int bmpc_setup(bmpc_handle* h, const double* Ad, const double* Bd, const double*
     }
     // thread-per-instance fast path for the compiled small shapes (pendulum, point mass)
     h->tpi_kind = 0;
-    if (h->cfg.fast_path && h->team == 32) {
+    // (the Riccati polish treats state rows as the soft penalty they are by default; hard state rows -> team kernels)
+    if (h->cfg.fast_path && h->team == 32 && h->cfg.soft_on) {
         if (d.nx == 4 && d.nu == 1 && d.Np == 20 && d.Nc == 20) h->tpi_kind = 1;
         else if (d.nx == 2 && d.nu == 1 && d.Np == 20 && d.Nc == 20) h->tpi_kind = 2;
     }

@@ -81,7 +81,29 @@ struct SeqTeam {
     BMPC_HD bool all(bool p) { return p; }
     BMPC_HD double max(double v) { return v; }
     BMPC_HD int excl_scan(int f, int& total) { total = f; return 0; }
+    // sub-team topology used by the row-parallel mat-vecs: rows go to warps, columns to lanes
+    BMPC_HD int warp() const { return 0; }
+    BMPC_HD int nwarps() const { return 1; }
+    BMPC_HD int lane() const { return 0; }
+    BMPC_HD int lanes() const { return 1; }
+    BMPC_HD double wsum(double v) { return v; }
 };
+
+// y_r = sum_{c in [c0(r), c1(r))} M[r*ld + c] x[c]; rows striped over the team's warps, columns over the lanes of a
+// warp (coalesced row reads, shuffle reduction); out(r, y_r) is called by lane 0 of the owning warp.
+template <class Team, class C0, class C1, class Out>
+BMPC_HD void bmpc_gemv(Team& t, const double* M, int ld, int nrows, const double* x, C0 c0, C1 c1, Out out) {
+    for (int r = t.warp(); r < nrows; r += t.nwarps()) {
+        const double* row = M + (size_t)r * ld;
+        double a0 = 0.0, a1 = 0.0;
+        int c = c0(r) + t.lane();
+        const int ce = c1(r), st = t.lanes();
+        for (; c + st < ce; c += 2 * st) { a0 += row[c] * x[c]; a1 += row[c + st] * x[c + st]; }
+        if (c < ce) a0 += row[c] * x[c];
+        const double acc = t.wsum(a0 + a1);
+        if (t.lane() == 0) out(r, acc);
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // Row helpers
@@ -352,64 +374,80 @@ BMPC_HD void bmpc_admm(Team& t, const BmpcDims& d, const BmpcSysOff& o, const do
     const double *lo0 = sys + o.lo0, *hi0 = sys + o.hi0, *rhov = sys + o.rho, *scal = sys + o.scal;
     const double sigma = scal[BMPC_S_SIGMA], alpha = scal[BMPC_S_ALPHA], rho_e = scal[BMPC_S_RHOE];
     const bool soft_on = rho_e > 0.0;
-    const int NX = d.NX, NU = d.NU, mc = d.mc;
+    const int nx = d.nx, nu = d.nu, Nc = d.Nc, NX = d.NX, NU = d.NU, mc = d.mc;
+    // (A' w)_a beyond the dense state block: input row + the reference's delta-u rows
+    auto at_tail = [&](const double* ww, int a) {
+        const double* wd = ww + NX + NU;
+        double acc = ww[NX + a] - wd[nu + a];
+        if (a < nu) acc += wd[a];
+        if (a >= 1) acc += wd[nu + a - 1];
+        return acc;
+    };
+    auto col0 = [&](int a) { return (a / nu + 1) * nx; };          // first state row that sees input a
+    auto colN = [&](int) { return NX; };
+    auto zero = [&](int) { return 0; };
+    auto allU = [&](int) { return NU; };
+    auto rowend = [&](int i) { int k = i / nx; return (k < Nc ? k : Nc) * nu; };   // x_k depends on u_j, j < k
     double rp = 0.0, rd = 0.0, np_ = 0.0, nd_ = 0.0;
     for (int it = 0; it < niter; it++) {
         const bool last = (it == niter - 1);
-        // A: rows
+        // A: rows  w = rho (2 prox(v) - v - cc)
         for (int i = t.tid; i < mc; i += t.n) {
             double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
-            double vi = v[i], rho = rhov[i];
-            double z = bmpc_prox(vi, lo, hi, soft_on && i < NX, rho, rho_e);
-            double ci = i < NX ? cc[i] : 0.0;
-            w[i] = rho * (2.0 * z - vi - ci);
+            const double vi = v[i], rho = rhov[i];
+            const double z = bmpc_prox(vi, lo, hi, soft_on && i < NX, rho, rho_e);
+            w[i] = rho * (2.0 * z - vi - (i < NX ? cc[i] : 0.0));
         }
         t.sync();
-        // B: columns  r = sigma x - g + A' w
-        for (int a = t.tid; a < NU; a += t.n) r[a] = sigma * x[a] - g[a] + bmpc_ATcol_dot(d, Bcal, w, a);
+        // B: r = sigma x - g + A' w      (rows of B' striped over warps, lanes over the horizon)
+        bmpc_gemv(t, BcalT, NX, NU, w, col0, colN, [&](int a, double acc) { r[a] = sigma * x[a] - g[a] + acc + at_tail(w, a); });
         t.sync();
-        // C: columns  xt = Kinv r
-        for (int a = t.tid; a < NU; a += t.n) {
-            const double* row = Kinv + a * NU; double a0 = 0.0, a1 = 0.0; int b = 0;
-            for (; b + 1 < NU; b += 2) { a0 += row[b] * r[b]; a1 += row[b + 1] * r[b + 1]; }
-            if (b < NU) a0 += row[b] * r[b];
-            xt[a] = a0 + a1;
-        }
+        // C: xt = Kinv r
+        bmpc_gemv(t, Kinv, NU, NU, r, zero, allU, [&](int a, double acc) { xt[a] = acc; });
         t.sync();
-        // D: rows  v += alpha (zt - z)   (w is reused for rho*(zt - z) on the last iteration)
+        // D1: zt on the state rows (kept in w, which is dead now)
+        bmpc_gemv(t, Bcal, NU, NX, xt, zero, rowend, [&](int i, double acc) { w[i] = acc + cc[i]; });
+        t.sync();
+        // D2: rows  v += alpha (zt - prox(v))
         double lrp = 0.0, lnp = 0.0;
         for (int i = t.tid; i < mc; i += t.n) {
             double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
-            double vi = v[i], rho = rhov[i];
-            double z = bmpc_prox(vi, lo, hi, soft_on && i < NX, rho, rho_e);
-            double zt = bmpc_Arow_dot(d, BcalT, xt, i) + (i < NX ? cc[i] : 0.0);
-            double dz = zt - z;
-            v[i] = vi + alpha * dz;
-            if (last) {
-                w[i] = rho * dz;
-                lrp = fmax(lrp, fabs(dz)); lnp = fmax(lnp, fmax(fabs(zt), fabs(z)));
+            const double vi = v[i], rho = rhov[i];
+            const double z = bmpc_prox(vi, lo, hi, soft_on && i < NX, rho, rho_e);
+            double zt;
+            if (i < NX) zt = w[i];
+            else if (i < NX + NU) zt = xt[i - NX];
+            else {
+                const int rr = i - NX - NU;
+                if (rr < nu) zt = xt[rr];
+                else { const int s2 = rr - nu; zt = -xt[s2] + (s2 + 1 < NU ? xt[s2 + 1] : 0.0); }
             }
+            const double dz = zt - z;
+            v[i] = vi + alpha * dz;
+            if (last) { lrp = fmax(lrp, fabs(dz)); lnp = fmax(lnp, fmax(fabs(zt), fabs(z))); }
+            if (last) w[i] = rho * dz;            // safe: every state row's zt was consumed by this same thread above
         }
         if (last) {
             t.sync();
-            // dual residual sigma dx + A' rho dz ; normaliser pieces ||H xt||, ||g||
+            // OSQP residuals of the last iteration: r_prim = ||zt - z||, r_dual = ||sigma (xt - x) + A' rho (zt - z)||
             double lrd = 0.0, lnd = 0.0;
-            for (int a = t.tid; a < NU; a += t.n) {
-                double dx = xt[a] - x[a];
-                lrd = fmax(lrd, fabs(sigma * dx + bmpc_ATcol_dot(d, Bcal, w, a)));
-                const double* row = H + a * NU; double hx = 0.0;
-                for (int b = 0; b < NU; b++) hx += row[b] * xt[b];
-                lnd = fmax(lnd, fmax(fabs(hx), fabs(g[a])));
-            }
+            bmpc_gemv(t, BcalT, NX, NU, w, col0, colN, [&](int a, double acc) { r[a] = sigma * (xt[a] - x[a]) + acc + at_tail(w, a); });
             t.sync();
-            // ||A'y|| with y = rho (v_new - prox(v_new))
+            for (int a = t.tid; a < NU; a += t.n) { lrd = fmax(lrd, fabs(r[a])); lnd = fmax(lnd, fabs(g[a])); }
+            t.sync();
+            bmpc_gemv(t, H, NU, NU, xt, zero, allU, [&](int a, double acc) { r[a] = acc; });
+            // y = rho (v_new - prox(v_new)) for ||A'y||
             for (int i = t.tid; i < mc; i += t.n) {
                 double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
-                double vi = v[i], rho = rhov[i];
+                const double vi = v[i], rho = rhov[i];
                 w[i] = rho * (vi - bmpc_prox(vi, lo, hi, soft_on && i < NX, rho, rho_e));
             }
             t.sync();
-            for (int a = t.tid; a < NU; a += t.n) lnd = fmax(lnd, fabs(bmpc_ATcol_dot(d, Bcal, w, a)));
+            for (int a = t.tid; a < NU; a += t.n) lnd = fmax(lnd, fabs(r[a]));
+            t.sync();
+            bmpc_gemv(t, BcalT, NX, NU, w, col0, colN, [&](int a, double acc) { r[a] = acc + at_tail(w, a); });
+            t.sync();
+            for (int a = t.tid; a < NU; a += t.n) lnd = fmax(lnd, fabs(r[a]));
             rp = t.max(lrp); np_ = t.max(lnp); rd = t.max(lrd); nd_ = t.max(lnd);
         }
         for (int a = t.tid; a < NU; a += t.n) x[a] += alpha * (xt[a] - x[a]);
