@@ -747,8 +747,9 @@ int bmpc_solve(bmpc_handle* h) {
         if (chunk > h->cfg.max_iter - total) chunk = h->cfg.max_iter - total;
         BMPC_CUDA(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 2, h->stream));
         BMPC_CUDA(cudaEventRecord(h->ev[0], h->stream));
-        // fast path (thread-per-instance kernels) for the first rounds; the team kernels take the long tail
-        const bool tpi = h->tpi_kind && h->cfg.polish && h->xref_mode == 0 && total < 200;
+        // fast path (thread-per-instance kernels, throughput-optimised) for the first round; the few stragglers are
+        // latency-bound and go to the CTA-per-instance team kernels
+        const bool tpi = round == 0 && h->tpi_kind && h->cfg.polish && h->xref_mode == 0;
         if (tpi) {
             if (h->tpi_kind == 1) launch_tpi_round<TpiPend>(h, list, count, chunk, nxt, h->ev[1]);
             else launch_tpi_round<TpiPm>(h, list, count, chunk, nxt, h->ev[1]);

@@ -366,8 +366,85 @@ BMPC_HD void bmpc_prep(Team& t, const BmpcDims& d, const BmpcSysOff& o, const do
 //     x += alpha (xt - x);  v += alpha (zt - z)
 // On return res[0] = ||zt - z||_inf, res[1] = ||sigma (xt-x) + A' rho (zt - z)||_inf of the LAST
 // iteration, res[2], res[3] = the OSQP normalisers max(||zt||,||z||), max(||H xt||,||A'y||,||g||).
+// ---- variant 1 (one warp per instance): lanes own rows / columns, mat-vec loops run along the other dimension ----
 template <class Team>
-BMPC_HD void bmpc_admm(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, const double* um1,
+BMPC_HD void bmpc_admm_lanes(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, const double* um1,
+                       const double* g, const double* cc, double* x, double* v, double* w, double* xt, double* r,
+                       int niter, double* res) {
+    const double *Bcal = sys + o.Bcal, *BcalT = sys + o.BcalT, *Kinv = sys + o.Kinv, *H = sys + o.H;
+    const double *lo0 = sys + o.lo0, *hi0 = sys + o.hi0, *rhov = sys + o.rho, *scal = sys + o.scal;
+    const double sigma = scal[BMPC_S_SIGMA], alpha = scal[BMPC_S_ALPHA], rho_e = scal[BMPC_S_RHOE];
+    const bool soft_on = rho_e > 0.0;
+    const int NX = d.NX, NU = d.NU, mc = d.mc;
+    double rp = 0.0, rd = 0.0, np_ = 0.0, nd_ = 0.0;
+    for (int it = 0; it < niter; it++) {
+        const bool last = (it == niter - 1);
+        // A: rows
+        for (int i = t.tid; i < mc; i += t.n) {
+            double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
+            double vi = v[i], rho = rhov[i];
+            double z = bmpc_prox(vi, lo, hi, soft_on && i < NX, rho, rho_e);
+            double ci = i < NX ? cc[i] : 0.0;
+            w[i] = rho * (2.0 * z - vi - ci);
+        }
+        t.sync();
+        // B: columns  r = sigma x - g + A' w
+        for (int a = t.tid; a < NU; a += t.n) r[a] = sigma * x[a] - g[a] + bmpc_ATcol_dot(d, Bcal, w, a);
+        t.sync();
+        // C: columns  xt = Kinv r
+        for (int a = t.tid; a < NU; a += t.n) {
+            const double* row = Kinv + a * NU; double a0 = 0.0, a1 = 0.0; int b = 0;
+            for (; b + 1 < NU; b += 2) { a0 += row[b] * r[b]; a1 += row[b + 1] * r[b + 1]; }
+            if (b < NU) a0 += row[b] * r[b];
+            xt[a] = a0 + a1;
+        }
+        t.sync();
+        // D: rows  v += alpha (zt - z)   (w is reused for rho*(zt - z) on the last iteration)
+        double lrp = 0.0, lnp = 0.0;
+        for (int i = t.tid; i < mc; i += t.n) {
+            double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
+            double vi = v[i], rho = rhov[i];
+            double z = bmpc_prox(vi, lo, hi, soft_on && i < NX, rho, rho_e);
+            double zt = bmpc_Arow_dot(d, BcalT, xt, i) + (i < NX ? cc[i] : 0.0);
+            double dz = zt - z;
+            v[i] = vi + alpha * dz;
+            if (last) {
+                w[i] = rho * dz;
+                lrp = fmax(lrp, fabs(dz)); lnp = fmax(lnp, fmax(fabs(zt), fabs(z)));
+            }
+        }
+        if (last) {
+            t.sync();
+            // dual residual sigma dx + A' rho dz ; normaliser pieces ||H xt||, ||g||
+            double lrd = 0.0, lnd = 0.0;
+            for (int a = t.tid; a < NU; a += t.n) {
+                double dx = xt[a] - x[a];
+                lrd = fmax(lrd, fabs(sigma * dx + bmpc_ATcol_dot(d, Bcal, w, a)));
+                const double* row = H + a * NU; double hx = 0.0;
+                for (int b = 0; b < NU; b++) hx += row[b] * xt[b];
+                lnd = fmax(lnd, fmax(fabs(hx), fabs(g[a])));
+            }
+            t.sync();
+            // ||A'y|| with y = rho (v_new - prox(v_new))
+            for (int i = t.tid; i < mc; i += t.n) {
+                double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
+                double vi = v[i], rho = rhov[i];
+                w[i] = rho * (vi - bmpc_prox(vi, lo, hi, soft_on && i < NX, rho, rho_e));
+            }
+            t.sync();
+            for (int a = t.tid; a < NU; a += t.n) lnd = fmax(lnd, fabs(bmpc_ATcol_dot(d, Bcal, w, a)));
+            rp = t.max(lrp); np_ = t.max(lnp); rd = t.max(lrd); nd_ = t.max(lnd);
+        }
+        for (int a = t.tid; a < NU; a += t.n) x[a] += alpha * (xt[a] - x[a]);
+        t.sync();
+    }
+    if (res && t.tid == 0) { res[0] = rp; res[1] = rd; res[2] = np_; res[3] = nd_; }
+    t.sync();
+}
+
+// ---- variant 2 (one CTA per instance): rows striped over warps, columns over lanes, shuffle reductions ----
+template <class Team>
+BMPC_HD void bmpc_admm_rows(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, const double* um1,
                        const double* g, const double* cc, double* x, double* v, double* w, double* xt, double* r,
                        int niter, double* res) {
     const double *Bcal = sys + o.Bcal, *BcalT = sys + o.BcalT, *Kinv = sys + o.Kinv, *H = sys + o.H;
@@ -455,6 +532,15 @@ BMPC_HD void bmpc_admm(Team& t, const BmpcDims& d, const BmpcSysOff& o, const do
     }
     if (res && t.tid == 0) { res[0] = rp; res[1] = rd; res[2] = np_; res[3] = nd_; }
     t.sync();
+}
+
+// dispatcher: a lone warp is better off with variant 1 (measured 5x), a CTA with variant 2
+template <class Team>
+BMPC_HD void bmpc_admm(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, const double* um1,
+                       const double* g, const double* cc, double* x, double* v, double* w, double* xt, double* r,
+                       int niter, double* res) {
+    if (t.nwarps() > 1) bmpc_admm_rows(t, d, o, sys, um1, g, cc, x, v, w, xt, r, niter, res);
+    else bmpc_admm_lanes(t, d, o, sys, um1, g, cc, x, v, w, xt, r, niter, res);
 }
 
 // ------------------------------------------------------------------------------------------------
