@@ -114,6 +114,7 @@ struct BmpcInst {
     int32_t* status;      // [B]
     int32_t* iters;       // [B]
     int32_t* psteps;      // [B]
+    int32_t* lvl;         // [B] adaptive-rho ladder level (reset to the base level at every solve)
 };
 
 // smem (doubles) per instance for the two kernels — keep in sync with the carve-up below
@@ -132,7 +133,7 @@ __global__ void k_condense(BmpcDims d, BmpcSysOff o, double* sys, double rho, do
 
 template <bool WARP>
 __global__ void k_admm(BmpcDims d, BmpcSysOff o, const double* __restrict__ sys, BmpcInst I, const int32_t* __restrict__ list,
-                       int count, int niter, int do_prep, int cold, int xref_mode) {
+                       int count, int niter, int do_prep, int cold, int xref_mode, int adapt) {
     extern __shared__ double smem[];
     __shared__ double sd[32];
     __shared__ int si[32];
@@ -165,7 +166,12 @@ __global__ void k_admm(BmpcDims d, BmpcSysOff o, const double* __restrict__ sys,
             for (int i = t.tid; i < d.mc; i += t.n) v[i] = I.vw[(size_t)inst * d.mc + i];
         }
         t.sync();
-        bmpc_admm(t, d, o, sys, um1, g, cc, x, v, w, xt, r, niter, res);
+        int lvl = I.lvl[inst];
+        bmpc_admm(t, d, o, sys, um1, g, cc, x, v, w, xt, r, niter, res, lvl);
+        if (adapt) {
+            const int nl = bmpc_adapt_level(t, d, o, sys, um1, v, res, lvl);
+            if (t.tid == 0 && nl != lvl) I.lvl[inst] = nl;
+        }
         for (int a = t.tid; a < d.NU; a += t.n) { I.xw[(size_t)inst * d.NU + a] = x[a]; I.Ua[(size_t)inst * d.NU + a] = xt[a]; }
         for (int i = t.tid; i < d.mc; i += t.n) I.vw[(size_t)inst * d.mc + i] = v[i];
         if (t.tid < 4) I.res[(size_t)inst * 4 + t.tid] = res[t.tid];
@@ -248,7 +254,7 @@ __global__ void k_check_converged(BmpcInst I, const int32_t* __restrict__ list, 
 
 __global__ void k_reset(BmpcInst I, int B) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B) { I.status[i] = BMPC_UNSOLVED; I.iters[i] = 0; I.psteps[i] = 0; }
+    if (i < B) { I.status[i] = BMPC_UNSOLVED; I.iters[i] = 0; I.psteps[i] = 0; I.lvl[i] = BMPC_LEV0; }
 }
 
 // x_seq = Acal x0 + Bcal U, eps_seq = distance back to the box, objective of the reference QP (without J_CNST).
@@ -567,6 +573,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     ok &= dalloc((void**)&h->I.status, sizeof(int32_t) * B);
     ok &= dalloc((void**)&h->I.iters, sizeof(int32_t) * B);
     ok &= dalloc((void**)&h->I.psteps, sizeof(int32_t) * B);
+    ok &= dalloc((void**)&h->I.lvl, sizeof(int32_t) * B);
     ok &= dalloc((void**)&h->listA, sizeof(int32_t) * B);
     ok &= dalloc((void**)&h->listB, sizeof(int32_t) * B);
     ok &= dalloc((void**)&h->counts, sizeof(int32_t) * 2);
@@ -590,7 +597,7 @@ void bmpc_destroy(bmpc_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     void* ptrs[] = {h->sys, h->x0, h->um1, h->um1_solved, h->xref, h->u0_own, h->I.g, h->I.cc, h->I.xw, h->I.vw, h->I.Ua, h->I.Us, h->I.res,
-                    h->I.status, h->I.iters, h->I.psteps, h->listA, h->listB, h->counts, h->seq_x, h->seq_e, h->seq_obj};
+                    h->I.status, h->I.iters, h->I.psteps, h->I.lvl, h->listA, h->listB, h->counts, h->seq_x, h->seq_e, h->seq_obj};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_count) cudaFreeHost(h->h_count);
     free(h->tpi_admm_params); free(h->tpi_polish_params);
@@ -706,12 +713,12 @@ static bool use_fallback_team(const bmpc_handle* h, const int32_t* list, int cou
 static void launch_admm(bmpc_handle* h, const int32_t* list, int count, int niter, int do_prep) {
     const int cold = h->cold ? 1 : 0;
     if (use_fallback_team(h, list, count)) {
-        k_admm<false><<<count, h->fb_team, h->fb_smem_admm, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode);
+        k_admm<false><<<count, h->fb_team, h->fb_smem_admm, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
     } else if (h->team == 32) {
         int grid = (count + h->wpb - 1) / h->wpb;
-        k_admm<true><<<grid, h->wpb * 32, h->smem_admm, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode);
+        k_admm<true><<<grid, h->wpb * 32, h->smem_admm, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
     } else {
-        k_admm<false><<<count, h->team, h->smem_admm, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode);
+        k_admm<false><<<count, h->team, h->smem_admm, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
     }
     h->stats.launches++;
 }

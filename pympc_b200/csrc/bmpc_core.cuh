@@ -40,11 +40,19 @@ struct BmpcSysOff {
     // inputs (copied from the host by bmpc_setup)
     int Ad, Bd, Qx, QxN, Qu, QDu, xmin, xmax, umin, umax, Dumin, Dumax, uref;
     // derived by the condense kernel
-    int pw, Acal, Bcal, BcalT, PB, H, Hinv, K, Kinv, AHinv, M, Gx0, Gref, GrefFull, g0, lo0, hi0, rho, scal;
+    int pw, Acal, Bcal, BcalT, PB, H, Hinv, K, Kinv, AHinv, M, Gx0, Gref, GrefFull, g0, lo0, hi0, rho, scal, KinvL;
     int total;
 };
 
 // scal[] slots
+// adaptive-rho table: level l uses rho * 10^((l - BMPC_LEV0)/2) and its own K^-1 (OSQP refactors on a rho change; with shared
+// matrices the factors for a fixed ladder are precomputed once instead)
+enum { BMPC_NLEV = 7, BMPC_LEV0 = 2 };
+BMPC_HOSTDEV double bmpc_level_factor(int l) {
+    const double f[BMPC_NLEV] = {0.1, 0.31622776601683794, 1.0, 3.1622776601683795, 10.0, 31.622776601683793, 100.0};
+    return f[l];
+}
+
 enum { BMPC_S_RHO = 0, BMPC_S_SIGMA, BMPC_S_ALPHA, BMPC_S_RHOE, BMPC_S_ERR, BMPC_S_TRH, BMPC_S_TRA, BMPC_S_COUNT = 8 };
 
 BMPC_HOSTDEV BmpcDims bmpc_make_dims(int nx, int nu, int Np, int Nc) {
@@ -67,6 +75,7 @@ BMPC_HOSTDEV BmpcSysOff bmpc_make_off(const BmpcDims& d) {
     BMPC_TAKE(AHinv, d.mc * d.NU); BMPC_TAKE(M, d.mc * d.mc);
     BMPC_TAKE(Gx0, d.NU * d.nx); BMPC_TAKE(Gref, d.NU * d.nx); BMPC_TAKE(GrefFull, d.NU * d.NX); BMPC_TAKE(g0, d.NU);
     BMPC_TAKE(lo0, d.mc); BMPC_TAKE(hi0, d.mc); BMPC_TAKE(rho, d.mc); BMPC_TAKE(scal, BMPC_S_COUNT);
+    BMPC_TAKE(KinvL, BMPC_NLEV * d.NU * d.NU);
 #undef BMPC_TAKE
     o.total = (p + 1) & ~1;
     return o;
@@ -294,6 +303,20 @@ BMPC_HD void bmpc_condense(Team& t, const BmpcDims& d, const BmpcSysOff& o, doub
     bool okK = bmpc_spd_inverse2(t, Kinv, NU, GrefFull, GrefFull + NU);
     if (t.tid == 0 && !(okH && okK)) scal[BMPC_S_ERR] = okH ? 2.0 : 1.0;
     t.sync();
+    // ladder of K^-1 for the adaptive rho: K_l = H + sigma I + f_l (K - H - sigma I)
+    {
+        double* KinvL = sys + o.KinvL;
+        for (int l = 0; l < BMPC_NLEV; l++) {
+            double* Kl = KinvL + (size_t)l * NU * NU;
+            const double f = bmpc_level_factor(l);
+            for (int idx = t.tid; idx < NU * NU; idx += t.n) {
+                const double hs = H[idx] + ((idx / NU == idx % NU) ? sigma : 0.0);
+                Kl[idx] = hs + f * (K[idx] - hs);
+            }
+            t.sync();
+            bmpc_spd_inverse2(t, Kl, NU, GrefFull, GrefFull + NU);
+        }
+    }
     // AHinv = A Hinv  (rows: Bcal Hinv ; Hinv ; D Hinv)
     for (int idx = t.tid; idx < mc * NU; idx += t.n) {
         int i = idx / NU, c = idx % NU; double acc = 0.0;
@@ -370,10 +393,11 @@ BMPC_HD void bmpc_prep(Team& t, const BmpcDims& d, const BmpcSysOff& o, const do
 template <class Team>
 BMPC_HD void bmpc_admm_lanes(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, const double* um1,
                        const double* g, const double* cc, double* x, double* v, double* w, double* xt, double* r,
-                       int niter, double* res) {
-    const double *Bcal = sys + o.Bcal, *BcalT = sys + o.BcalT, *Kinv = sys + o.Kinv, *H = sys + o.H;
+                       int niter, double* res, int lvl) {
+    const double *Bcal = sys + o.Bcal, *BcalT = sys + o.BcalT, *Kinv = sys + o.KinvL + (size_t)lvl * d.NU * d.NU, *H = sys + o.H;
     const double *lo0 = sys + o.lo0, *hi0 = sys + o.hi0, *rhov = sys + o.rho, *scal = sys + o.scal;
     const double sigma = scal[BMPC_S_SIGMA], alpha = scal[BMPC_S_ALPHA], rho_e = scal[BMPC_S_RHOE];
+    const double fac = bmpc_level_factor(lvl);
     const bool soft_on = rho_e > 0.0;
     const int NX = d.NX, NU = d.NU, mc = d.mc;
     double rp = 0.0, rd = 0.0, np_ = 0.0, nd_ = 0.0;
@@ -382,7 +406,7 @@ BMPC_HD void bmpc_admm_lanes(Team& t, const BmpcDims& d, const BmpcSysOff& o, co
         // A: rows
         for (int i = t.tid; i < mc; i += t.n) {
             double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
-            double vi = v[i], rho = rhov[i];
+            double vi = v[i], rho = fac * rhov[i];
             double z = bmpc_prox(vi, lo, hi, soft_on && i < NX, rho, rho_e);
             double ci = i < NX ? cc[i] : 0.0;
             w[i] = rho * (2.0 * z - vi - ci);
@@ -403,7 +427,7 @@ BMPC_HD void bmpc_admm_lanes(Team& t, const BmpcDims& d, const BmpcSysOff& o, co
         double lrp = 0.0, lnp = 0.0;
         for (int i = t.tid; i < mc; i += t.n) {
             double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
-            double vi = v[i], rho = rhov[i];
+            double vi = v[i], rho = fac * rhov[i];
             double z = bmpc_prox(vi, lo, hi, soft_on && i < NX, rho, rho_e);
             double zt = bmpc_Arow_dot(d, BcalT, xt, i) + (i < NX ? cc[i] : 0.0);
             double dz = zt - z;
@@ -428,7 +452,7 @@ BMPC_HD void bmpc_admm_lanes(Team& t, const BmpcDims& d, const BmpcSysOff& o, co
             // ||A'y|| with y = rho (v_new - prox(v_new))
             for (int i = t.tid; i < mc; i += t.n) {
                 double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
-                double vi = v[i], rho = rhov[i];
+                double vi = v[i], rho = fac * rhov[i];
                 w[i] = rho * (vi - bmpc_prox(vi, lo, hi, soft_on && i < NX, rho, rho_e));
             }
             t.sync();
@@ -446,10 +470,11 @@ BMPC_HD void bmpc_admm_lanes(Team& t, const BmpcDims& d, const BmpcSysOff& o, co
 template <class Team>
 BMPC_HD void bmpc_admm_rows(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, const double* um1,
                        const double* g, const double* cc, double* x, double* v, double* w, double* xt, double* r,
-                       int niter, double* res) {
-    const double *Bcal = sys + o.Bcal, *BcalT = sys + o.BcalT, *Kinv = sys + o.Kinv, *H = sys + o.H;
+                       int niter, double* res, int lvl) {
+    const double *Bcal = sys + o.Bcal, *BcalT = sys + o.BcalT, *Kinv = sys + o.KinvL + (size_t)lvl * d.NU * d.NU, *H = sys + o.H;
     const double *lo0 = sys + o.lo0, *hi0 = sys + o.hi0, *rhov = sys + o.rho, *scal = sys + o.scal;
     const double sigma = scal[BMPC_S_SIGMA], alpha = scal[BMPC_S_ALPHA], rho_e = scal[BMPC_S_RHOE];
+    const double fac = bmpc_level_factor(lvl);
     const bool soft_on = rho_e > 0.0;
     const int nx = d.nx, nu = d.nu, Nc = d.Nc, NX = d.NX, NU = d.NU, mc = d.mc;
     // (A' w)_a beyond the dense state block: input row + the reference's delta-u rows
@@ -471,7 +496,7 @@ BMPC_HD void bmpc_admm_rows(Team& t, const BmpcDims& d, const BmpcSysOff& o, con
         // A: rows  w = rho (2 prox(v) - v - cc)
         for (int i = t.tid; i < mc; i += t.n) {
             double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
-            const double vi = v[i], rho = rhov[i];
+            const double vi = v[i], rho = fac * rhov[i];
             const double z = bmpc_prox(vi, lo, hi, soft_on && i < NX, rho, rho_e);
             w[i] = rho * (2.0 * z - vi - (i < NX ? cc[i] : 0.0));
         }
@@ -489,7 +514,7 @@ BMPC_HD void bmpc_admm_rows(Team& t, const BmpcDims& d, const BmpcSysOff& o, con
         double lrp = 0.0, lnp = 0.0;
         for (int i = t.tid; i < mc; i += t.n) {
             double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
-            const double vi = v[i], rho = rhov[i];
+            const double vi = v[i], rho = fac * rhov[i];
             const double z = bmpc_prox(vi, lo, hi, soft_on && i < NX, rho, rho_e);
             double zt;
             if (i < NX) zt = w[i];
@@ -516,7 +541,7 @@ BMPC_HD void bmpc_admm_rows(Team& t, const BmpcDims& d, const BmpcSysOff& o, con
             // y = rho (v_new - prox(v_new)) for ||A'y||
             for (int i = t.tid; i < mc; i += t.n) {
                 double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
-                const double vi = v[i], rho = rhov[i];
+                const double vi = v[i], rho = fac * rhov[i];
                 w[i] = rho * (vi - bmpc_prox(vi, lo, hi, soft_on && i < NX, rho, rho_e));
             }
             t.sync();
@@ -538,9 +563,40 @@ BMPC_HD void bmpc_admm_rows(Team& t, const BmpcDims& d, const BmpcSysOff& o, con
 template <class Team>
 BMPC_HD void bmpc_admm(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, const double* um1,
                        const double* g, const double* cc, double* x, double* v, double* w, double* xt, double* r,
-                       int niter, double* res) {
-    if (t.nwarps() > 1) bmpc_admm_rows(t, d, o, sys, um1, g, cc, x, v, w, xt, r, niter, res);
-    else bmpc_admm_lanes(t, d, o, sys, um1, g, cc, x, v, w, xt, r, niter, res);
+                       int niter, double* res, int lvl) {
+    if (t.nwarps() > 1) bmpc_admm_rows(t, d, o, sys, um1, g, cc, x, v, w, xt, r, niter, res, lvl);
+    else bmpc_admm_lanes(t, d, o, sys, um1, g, cc, x, v, w, xt, r, niter, res, lvl);
+}
+
+// OSQP's adaptive-rho rule (OSQP paper 5.2) on a fixed ladder: estimate rho sqrt((r_prim/n_prim)/(r_dual/n_dual)),
+// move to the nearest ladder level if that is at least one decade away (OSQP's 5x test, coarsened), and rescale
+// v = z + y/rho so that (z, y) are unchanged.  Returns the new level.
+template <class Team>
+BMPC_HD int bmpc_adapt_level(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, const double* um1,
+                             double* v, const double* res, int lvl) {
+    const double rp = res[0] / fmax(res[2], 1e-12), rd = res[1] / fmax(res[3], 1e-12);
+    int nl = lvl;
+    if (rp > 0.0 && rd > 0.0) {
+        const double steps = log10(rp / rd);               // sqrt(ratio) in half-decade steps = log10(ratio)
+        int mv = (int)(steps >= 0.0 ? steps + 0.5 : steps - 0.5);
+        if (mv >= 1 || mv <= -1) nl = lvl + mv;
+        if (nl < 0) nl = 0;
+        if (nl > BMPC_NLEV - 1) nl = BMPC_NLEV - 1;
+    }
+    if (nl != lvl) {
+        const double *lo0 = sys + o.lo0, *hi0 = sys + o.hi0, *rhov = sys + o.rho;
+        const double rho_e = sys[o.scal + BMPC_S_RHOE];
+        const bool soft_on = rho_e > 0.0;
+        const double fo = bmpc_level_factor(lvl), ratio = fo / bmpc_level_factor(nl);
+        for (int i = t.tid; i < d.mc; i += t.n) {
+            double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
+            const double vi = v[i];
+            const double z = bmpc_prox(vi, lo, hi, soft_on && i < d.NX, fo * rhov[i], rho_e);
+            v[i] = z + (vi - z) * ratio;
+        }
+        t.sync();
+    }
+    return nl;
 }
 
 // ------------------------------------------------------------------------------------------------

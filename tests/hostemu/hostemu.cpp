@@ -6,6 +6,7 @@
 #include "../../pympc_b200/csrc/bmpc_core.cuh"
 #include "../../pympc_b200/csrc/bmpc_tpi.cuh"
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 
 extern "C" {
@@ -40,13 +41,15 @@ int emu_solve(int nx, int nu, int Np, int Nc, const double* sys, const double* x
     int* st = (int*)calloc(d.mc + rmax, sizeof(int)); int* R = st + d.mc;
     bmpc_prep(t, d, o, sys, x0, um1, xref, xref_mode, g, cc);
     if (cold) { for (int a = 0; a < d.NU; a++) x[a] = 0.0; for (int i = 0; i < d.mc; i++) v[i] = i < d.NX ? cc[i] : 0.0; }
-    int total = 0, chunk = first_iters, status = -2, psteps = 0;
+    int total = 0, chunk = first_iters, status = -2, psteps = 0, lvl = BMPC_LEV0;
     const double* rhov = sys + o.rho;
     while (total < max_iter) {
         if (chunk > max_iter - total) chunk = max_iter - total;
-        bmpc_admm(t, d, o, sys, um1, g, cc, x, v, w, xt, r, chunk, res);
+        bmpc_admm(t, d, o, sys, um1, g, cc, x, v, w, xt, r, chunk, res, lvl);
+        lvl = bmpc_adapt_level(t, d, o, sys, um1, v, res, lvl);
         total += chunk;
         int ps = bmpc_polish(t, d, o, sys, um1, g, cc, v, W0, zz, murow, st, S, tt, R, U0, U, rmax, pdas_steps);
+        if (getenv("EMU_TRACE")) printf("TRACE %d %.3e %.3e %d\n", total, res[0] / fmax(res[2], 1e-12), res[1] / fmax(res[3], 1e-12), ps);
         if (ps > 0) {
             psteps += ps; status = 1;
             for (int a = 0; a < d.NU; a++) { Uout[a] = U[a]; x[a] = U[a]; }
