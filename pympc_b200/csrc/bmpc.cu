@@ -433,6 +433,8 @@ struct bmpc_handle {
     size_t smem_admm = 0, smem_polish = 0;
     // low-latency CTA-per-instance variant for the few stragglers of a warp-team / TPI handle
     int fb_team = 0, fb_rmax = 0; size_t fb_smem_admm = 0, fb_smem_polish = 0;
+    struct { const int32_t* list; int count; int32_t *cur, *nxt; int total, chunk, round; bool need_prep; } st = {};
+    bool pending = false;              // a round is in flight and has not been retired by the host yet
     int tpi_kind = 0;                  // 0 none, 1 pendulum shape (4,1,20,20), 2 point-mass shape (2,1,20,20)
     void *tpi_admm_params = nullptr, *tpi_polish_params = nullptr;   // host copies of the parameter blocks
     int tpi_pdas_steps = 8;
@@ -460,6 +462,8 @@ static void launch_tpi_round(bmpc_handle* h, const int32_t* list, int count, int
 }
 
 extern "C" {
+
+static int finish_solve(bmpc_handle* h);
 
 void bmpc_default_config(bmpc_config* c) {
     memset(c, 0, sizeof(*c));
@@ -596,6 +600,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
 void bmpc_destroy(bmpc_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
+    if (h->pending) cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->sys, h->x0, h->um1, h->um1_solved, h->xref, h->u0_own, h->I.g, h->I.cc, h->I.xw, h->I.vw, h->I.Ua, h->I.Us, h->I.res,
                     h->I.status, h->I.iters, h->I.psteps, h->I.lvl, h->listA, h->listB, h->counts, h->seq_x, h->seq_e, h->seq_obj};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -608,6 +613,7 @@ void bmpc_destroy(bmpc_handle* h) {
 
 int bmpc_set_stream(bmpc_handle* h, void* s) {
     if (!h) return BMPC_ERR_ARG;
+    if (h->pending) { cudaSetDevice(h->cfg.device); int rc = finish_solve(h); if (rc) return rc; }
     h->stream = s ? (cudaStream_t)s : h->own_stream;
     return BMPC_OK;
 }
@@ -615,6 +621,7 @@ int bmpc_set_stream(bmpc_handle* h, void* s) {
 int bmpc_synchronize(bmpc_handle* h) {
     if (!h) return BMPC_ERR_ARG;
     BMPC_CUDA(cudaSetDevice(h->cfg.device));
+    if (h->pending) { int rc = finish_solve(h); if (rc) return rc; }
     BMPC_CUDA(cudaStreamSynchronize(h->stream));
     return BMPC_OK;
 }
@@ -684,7 +691,7 @@ int bmpc_setup(bmpc_handle* h, const double* Ad, const double* Bd, const double*
         }
     }
     // uminus1 default = uref for every instance (mpc.py:141); caller overrides through bmpc_update
-    h->is_setup = true; h->cold = true; h->solved = false;
+    h->is_setup = true; h->cold = true; h->solved = false; h->pending = false;
     return BMPC_OK;
 }
 
@@ -694,6 +701,7 @@ int bmpc_update(bmpc_handle* h, const double* x0, const double* uminus1, const d
     if (!h) return BMPC_ERR_ARG;
     if (!h->is_setup) { h->err = "bmpc_update before bmpc_setup"; return BMPC_ERR_STATE; }
     BMPC_CUDA(cudaSetDevice(h->cfg.device));
+    if (h->pending) { int rc = finish_solve(h); if (rc) return rc; }
     const BmpcDims& d = h->d; size_t B = h->cfg.batch;
     cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (x0) BMPC_CUDA(cudaMemcpyAsync(h->x0, x0, sizeof(double) * B * d.nx, kind, h->stream));
@@ -735,66 +743,88 @@ static void launch_polish(bmpc_handle* h, const int32_t* list, int count, int32_
     h->stats.launches++;
 }
 
+// ---- solve = rounds of [ADMM chunk -> polish]; the host only needs the count of unfinished instances after each
+// round.  bmpc_solve enqueues the first round and returns; whoever needs results next (bmpc_output, ...) waits once,
+// and only if stragglers remain runs further rounds.  In the warm closed loop this is ONE host sync per step.
+static int enqueue_round(bmpc_handle* h) {
+    auto& st = h->st;
+    if (st.chunk > h->cfg.max_iter - st.total) st.chunk = h->cfg.max_iter - st.total;
+    BMPC_CUDA(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 2, h->stream));
+    BMPC_CUDA(cudaEventRecord(h->ev[0], h->stream));
+    // fast path (thread-per-instance kernels, throughput-optimised) for the first round; the few stragglers are
+    // latency-bound and go to the CTA-per-instance team kernels
+    const bool tpi = st.round == 0 && h->tpi_kind && h->cfg.polish && h->xref_mode == 0;
+    if (tpi) {
+        if (h->tpi_kind == 1) launch_tpi_round<TpiPend>(h, st.list, st.count, st.chunk, st.nxt, h->ev[1]);
+        else launch_tpi_round<TpiPm>(h, st.list, st.count, st.chunk, st.nxt, h->ev[1]);
+    } else {
+        launch_admm(h, st.list, st.count, st.chunk, st.need_prep ? 1 : 0);
+        st.need_prep = false;
+        BMPC_CUDA(cudaEventRecord(h->ev[1], h->stream));
+        if (h->cfg.polish) launch_polish(h, st.list, st.count, st.nxt, h->counts);
+        else { k_check_converged<<<(st.count + 255) / 256, 256, 0, h->stream>>>(h->I, st.list, st.count, h->cfg.eps_abs, h->cfg.eps_rel, st.nxt, h->counts); h->stats.launches++; }
+    }
+    BMPC_CUDA(cudaEventRecord(h->ev[2], h->stream));
+    BMPC_CUDA(cudaMemcpyAsync(h->h_count, h->counts, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, h->stream));
+    BMPC_CUDA(cudaGetLastError());
+    return BMPC_OK;
+}
+
+// waits for the round in flight; returns 1 in *more if another round was enqueued (stragglers), 0 if the solve is complete
+static int retire_round(bmpc_handle* h, int* more) {
+    auto& st = h->st;
+    BMPC_CUDA(cudaStreamSynchronize(h->stream));
+    float a = 0.f, p = 0.f;
+    cudaEventElapsedTime(&a, h->ev[0], h->ev[1]); cudaEventElapsedTime(&p, h->ev[1], h->ev[2]);
+    h->stats.ms_admm += a; h->stats.ms_polish += p;
+    h->stats.admm_iters += (int64_t)st.count * st.chunk;
+    st.total += st.chunk; st.round++;
+    h->cold = false;
+    st.count = h->h_count[0];
+    h->stats.polish_steps += h->h_count[1];
+    st.list = st.nxt; int32_t* tmp = st.cur; st.cur = st.nxt; st.nxt = tmp;
+    // polish mode: cumulative first_iters, 25, 50, 100, ...; pure ADMM: OSQP's check_termination = 25
+    st.chunk = h->cfg.polish ? (st.total < 25 ? 25 - st.total : st.total) : 25;
+    if (st.count > 0 && st.total < h->cfg.max_iter) { *more = 1; return enqueue_round(h); }
+    *more = 0;
+    const int B = h->cfg.batch;
+    if (!h->cfg.polish) {
+        // pure-ADMM mode: every instance gets its status from OSQP's criterion on its last residuals
+        k_finalize<<<(B + 127) / 128, 128, 0, h->stream>>>(h->d, h->o, h->sys, h->I, nullptr, B, h->cfg.eps_abs, h->cfg.eps_rel, h->I.u0);
+        h->stats.launches++;
+    } else if (st.count > 0) {
+        k_finalize<<<(st.count + 127) / 128, 128, 0, h->stream>>>(h->d, h->o, h->sys, h->I, st.list, st.count, h->cfg.eps_abs, h->cfg.eps_rel, h->I.u0);
+        h->stats.launches++;
+    }
+    BMPC_CUDA(cudaGetLastError());
+    h->stats.rounds = st.round; h->stats.unsolved = h->cfg.polish ? st.count : -1;
+    h->pending = false;
+    return BMPC_OK;
+}
+
+static int finish_solve(bmpc_handle* h) {
+    while (h->pending) { int more = 0; int rc = retire_round(h, &more); if (rc) return rc; }
+    return BMPC_OK;
+}
+
 int bmpc_solve(bmpc_handle* h) {
     if (!h) return BMPC_ERR_ARG;
     if (!h->is_setup) { h->err = "bmpc_solve before bmpc_setup"; return BMPC_ERR_STATE; }
     BMPC_CUDA(cudaSetDevice(h->cfg.device));
+    if (h->pending) { int rc = finish_solve(h); if (rc) return rc; }
     const int B = h->cfg.batch;
     memset(&h->stats, 0, sizeof(h->stats));
     k_reset<<<(B + 255) / 256, 256, 0, h->stream>>>(h->I, B);
     h->stats.launches++;
     BMPC_CUDA(cudaMemcpyAsync(h->um1_solved, h->um1, sizeof(double) * (size_t)B * h->d.nu, cudaMemcpyDeviceToDevice, h->stream));
-    const int32_t* list = nullptr; int count = B;
-    int32_t *cur = h->listA, *nxt = h->listB;
-    int total = 0, chunk = h->cfg.polish ? h->cfg.first_iters : 25, round = 0;
-    float ms_a = 0.f, ms_p = 0.f;
-    bool need_prep = true;
-    if (chunk > h->cfg.max_iter) chunk = h->cfg.max_iter;
-    while (count > 0 && total < h->cfg.max_iter) {
-        if (chunk > h->cfg.max_iter - total) chunk = h->cfg.max_iter - total;
-        BMPC_CUDA(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 2, h->stream));
-        BMPC_CUDA(cudaEventRecord(h->ev[0], h->stream));
-        // fast path (thread-per-instance kernels, throughput-optimised) for the first round; the few stragglers are
-        // latency-bound and go to the CTA-per-instance team kernels
-        const bool tpi = round == 0 && h->tpi_kind && h->cfg.polish && h->xref_mode == 0;
-        if (tpi) {
-            if (h->tpi_kind == 1) launch_tpi_round<TpiPend>(h, list, count, chunk, nxt, h->ev[1]);
-            else launch_tpi_round<TpiPm>(h, list, count, chunk, nxt, h->ev[1]);
-        } else {
-            launch_admm(h, list, count, chunk, need_prep ? 1 : 0);
-            need_prep = false;
-            BMPC_CUDA(cudaEventRecord(h->ev[1], h->stream));
-        }
-        if (tpi) {}
-        else if (h->cfg.polish) launch_polish(h, list, count, nxt, h->counts);
-        else { k_check_converged<<<(count + 255) / 256, 256, 0, h->stream>>>(h->I, list, count, h->cfg.eps_abs, h->cfg.eps_rel, nxt, h->counts); h->stats.launches++; }
-        BMPC_CUDA(cudaEventRecord(h->ev[2], h->stream));
-        BMPC_CUDA(cudaMemcpyAsync(h->h_count, h->counts, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, h->stream));
-        BMPC_CUDA(cudaStreamSynchronize(h->stream));
-        BMPC_CUDA(cudaGetLastError());
-        float a = 0.f, p = 0.f;
-        cudaEventElapsedTime(&a, h->ev[0], h->ev[1]); cudaEventElapsedTime(&p, h->ev[1], h->ev[2]);
-        ms_a += a; ms_p += p;
-        h->stats.admm_iters += (int64_t)count * chunk;
-        total += chunk; round++;
-        h->cold = false;
-        count = h->h_count[0];
-        h->stats.polish_steps += h->h_count[1];
-        list = nxt; int32_t* tmp = cur; cur = nxt; nxt = tmp;
-        // polish mode: cumulative 10, 25, 50, 100, 200, ...; pure ADMM: OSQP's check_termination = 25
-        chunk = h->cfg.polish ? (total < 25 ? 25 - total : total) : 25;   // cumulative first_iters, 25, 50, 100, ...
-    }
-    if (!h->cfg.polish) {
-        // pure-ADMM mode: every instance gets its status from OSQP's criterion on its last residuals
-        k_finalize<<<(B + 127) / 128, 128, 0, h->stream>>>(h->d, h->o, h->sys, h->I, nullptr, B, h->cfg.eps_abs, h->cfg.eps_rel, h->I.u0);
-        h->stats.launches++;
-    } else if (count > 0) {
-        k_finalize<<<(count + 127) / 128, 128, 0, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->cfg.eps_abs, h->cfg.eps_rel, h->I.u0);
-        h->stats.launches++;
-    }
-    BMPC_CUDA(cudaGetLastError());
-    h->stats.rounds = round; h->stats.unsolved = h->cfg.polish ? count : -1; h->stats.ms_admm = ms_a; h->stats.ms_polish = ms_p;
-    h->solved = true;
+    auto& st = h->st;
+    st.list = nullptr; st.count = B; st.cur = h->listA; st.nxt = h->listB;
+    st.total = 0; st.round = 0; st.need_prep = true;
+    st.chunk = h->cfg.polish ? h->cfg.first_iters : 25;
+    if (st.chunk > h->cfg.max_iter) st.chunk = h->cfg.max_iter;
+    int rc = enqueue_round(h);
+    if (rc) return rc;
+    h->pending = true; h->solved = true;
     return BMPC_OK;
 }
 
@@ -804,10 +834,25 @@ int bmpc_output(bmpc_handle* h, double* u0, int32_t* status, int commit_uminus1,
     BMPC_CUDA(cudaSetDevice(h->cfg.device));
     const BmpcDims& d = h->d; size_t B = h->cfg.batch;
     cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    auto copies = [&]() -> int {
+        if (u0 && u0 != h->I.u0) BMPC_CUDA(cudaMemcpyAsync(u0, h->I.u0, sizeof(double) * B * d.nu, kind, h->stream));
+        if (status) BMPC_CUDA(cudaMemcpyAsync(status, h->I.status, sizeof(int32_t) * B, kind, h->stream));
+        return BMPC_OK;
+    };
+    bool copied = false;
+    if (h->pending) {
+        // speculate that the round in flight finishes everything (the common case): queue the result copies behind it
+        // so that a single wait covers the solve and the read-back; redo them if stragglers needed more rounds
+        if (!on_device && !commit_uminus1) { int rc = copies(); if (rc) return rc; copied = true; }
+        int more = 0; int rc = retire_round(h, &more); if (rc) return rc;
+        if (more) { copied = false; rc = finish_solve(h); if (rc) return rc; }
+        else if (h->stats.launches && (h->st.count > 0 || !h->cfg.polish)) copied = false;   // k_finalize rewrote u0/status
+    }
     if (commit_uminus1) BMPC_CUDA(cudaMemcpyAsync(h->um1, h->I.u0, sizeof(double) * B * d.nu, cudaMemcpyDeviceToDevice, h->stream));
-    if (u0 && u0 != h->I.u0) BMPC_CUDA(cudaMemcpyAsync(u0, h->I.u0, sizeof(double) * B * d.nu, kind, h->stream));
-    if (status) BMPC_CUDA(cudaMemcpyAsync(status, h->I.status, sizeof(int32_t) * B, kind, h->stream));
-    if (!on_device) BMPC_CUDA(cudaStreamSynchronize(h->stream));
+    if (!copied && (u0 || status)) {
+        int rc = copies(); if (rc) return rc;
+        if (!on_device) BMPC_CUDA(cudaStreamSynchronize(h->stream));
+    }
     return BMPC_OK;
 }
 
@@ -815,6 +860,7 @@ int bmpc_get_sequences(bmpc_handle* h, double* u_seq, double* x_seq, double* eps
     if (!h) return BMPC_ERR_ARG;
     if (!h->solved) { h->err = "bmpc_get_sequences before bmpc_solve"; return BMPC_ERR_STATE; }
     BMPC_CUDA(cudaSetDevice(h->cfg.device));
+    if (h->pending) { int rc = finish_solve(h); if (rc) return rc; }
     const BmpcDims& d = h->d; size_t B = h->cfg.batch;
     if (x_seq || eps_seq || obj_val) {
         if (!h->seq_x) {
@@ -839,7 +885,8 @@ int bmpc_get_sequences(bmpc_handle* h, double* u_seq, double* x_seq, double* eps
 
 int bmpc_get_stats(bmpc_handle* h, bmpc_stats* out) {
     if (!h || !out) return BMPC_ERR_ARG;
-    *out = h->stats;    // host-side counters only: no device traffic, safe inside a timed region
+    if (h->pending) { cudaSetDevice(h->cfg.device); int rc = finish_solve(h); if (rc) return rc; }
+    *out = h->stats;    // host-side counters only
     return BMPC_OK;
 }
 

@@ -100,7 +100,7 @@ BMPC_HD void tpi_linear_term(const TpiCommon<S>& c, const double* x0, const doub
 template <class S>
 BMPC_HD void tpi_admm(const TpiAdmmParams<S>& P, TpiAcc V, const double* x0, const double* um1, const double* xref,
                       double* x, int niter, bool cold) {
-    constexpr int nx = S::nx, nu = S::nu, Np = S::Np, Nc = S::Nc, NS = S::NS, NU = S::NU, ND = S::ND;
+    constexpr int nx = S::nx, nu = S::nu, Np = S::Np, Nc = S::Nc, NS = S::NS, NU = S::NU;
     const TpiCommon<S>& c = P.c;
     // g' = g + B' R_x Acal x0 is parked in rows [MT, MT+NU) of this thread's column (read once per iteration)
     {
