@@ -468,7 +468,7 @@ static int finish_solve(bmpc_handle* h);
 void bmpc_default_config(bmpc_config* c) {
     memset(c, 0, sizeof(*c));
     c->Np = 20; c->Nc = 0; c->batch = 1; c->device = 0; c->soft_on = 1;
-    c->max_iter = 4000; c->first_iters = 3; c->pdas_steps = 10; c->rmax = 0; c->polish = 1;
+    c->max_iter = 4000; c->first_iters = 0; c->pdas_steps = 10; c->rmax = 0; c->polish = 1;
     c->team_threads = 0; c->warps_per_block = 0; c->fast_path = 1;
     c->eps_feas = 1e6; c->rho = 0.0; c->sigma = 1e-6; c->alpha = 1.6; c->eps_abs = 1e-3; c->eps_rel = 1e-3;
 }
@@ -545,7 +545,6 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     h->cfg = *cfg;
     if (h->cfg.Nc <= 0) h->cfg.Nc = h->cfg.Np;
     if (h->cfg.max_iter <= 0) h->cfg.max_iter = 4000;
-    if (h->cfg.first_iters <= 0) h->cfg.first_iters = 3;
     if (h->cfg.pdas_steps <= 0) h->cfg.pdas_steps = 10;
     h->d = bmpc_make_dims(cfg->nx, cfg->nu, h->cfg.Np, h->cfg.Nc);
     h->o = bmpc_make_off(h->d);
@@ -820,7 +819,9 @@ int bmpc_solve(bmpc_handle* h) {
     auto& st = h->st;
     st.list = nullptr; st.count = B; st.cur = h->listA; st.nxt = h->listB;
     st.total = 0; st.round = 0; st.need_prep = true;
-    st.chunk = h->cfg.polish ? h->cfg.first_iters : 25;
+    // first round: 3 iterations on the fast path (measured: as good as 10 for the warm active-set guess), 10 on the team kernels
+    const bool fast = h->tpi_kind && h->xref_mode == 0;
+    st.chunk = h->cfg.polish ? (h->cfg.first_iters > 0 ? h->cfg.first_iters : (fast ? 3 : 10)) : 25;
     if (st.chunk > h->cfg.max_iter) st.chunk = h->cfg.max_iter;
     int rc = enqueue_round(h);
     if (rc) return rc;

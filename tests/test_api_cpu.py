@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(bmpc_lib):
 
 def test_config_struct_layout_matches_defaults(bmpc_lib):
     c = _lib.BmpcConfig(); bmpc_lib.bmpc_default_config(c)
-    assert (c.Np, c.max_iter, c.first_iters, c.pdas_steps, c.polish, c.soft_on) == (20, 4000, 3, 10, 1, 1)
+    assert (c.Np, c.max_iter, c.first_iters, c.pdas_steps, c.polish, c.soft_on) == (20, 4000, 0, 10, 1, 1)
     assert (c.eps_feas, c.sigma, c.alpha, c.eps_abs, c.eps_rel) == (1e6, 1e-6, 1.6, 1e-3, 1e-3)
 
 
