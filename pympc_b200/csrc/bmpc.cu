@@ -120,7 +120,7 @@ struct BmpcInst {
 // smem (doubles) per instance for the two kernels — keep in sync with the carve-up below
 __host__ __device__ static inline size_t admm_smem_doubles(const BmpcDims& d) { return 4 * (size_t)d.NU + d.NX + 2 * (size_t)d.mc + d.nu + 4 + 4; }
 __host__ __device__ static inline size_t polish_smem_doubles(const BmpcDims& d, int rmax) {
-    return 3 * (size_t)d.NU + d.NX + 4 * (size_t)d.mc + (size_t)rmax * rmax + rmax + d.nu + 2 + (d.mc + rmax + 3) / 2;
+    return 3 * (size_t)d.NU + d.NX + 4 * (size_t)d.mc + (size_t)rmax * (rmax + 1) / 2 + rmax + d.nu + 2 + (d.mc + rmax + 3) / 2;
 }
 
 __global__ void k_condense(BmpcDims d, BmpcSysOff o, double* sys, double rho, double sigma, double alpha, double eps_feas,
@@ -194,7 +194,7 @@ __global__ void k_polish(BmpcDims d, BmpcSysOff o, const double* __restrict__ sy
     const int inst = list ? list[idx] : idx;
     double* base = smem + (size_t)slot * polish_smem_doubles(d, rmax);
     double *g = base, *cc = g + d.NU, *v = cc + d.NX, *W0 = v + d.mc, *zz = W0 + d.mc, *murow = zz + d.mc,
-           *S = murow + d.mc, *tt = S + (size_t)rmax * rmax, *U0 = tt + rmax, *U = U0 + d.NU, *um1 = U + d.NU;
+           *S = murow + d.mc, *tt = S + (size_t)rmax * (rmax + 1) / 2, *U0 = tt + rmax, *U = U0 + d.NU, *um1 = U + d.NU;
     int* st = (int*)(um1 + d.nu + (d.nu & 1));
     int* R = st + d.mc;
     auto run = [&](auto& t) {
@@ -497,7 +497,7 @@ static int configure_launch(bmpc_handle* h) {
     if (team <= 0) team = (d.mc <= 192 && d.NU <= 64) ? 32 : 256;
     if (team != 32) { team = ((team + 31) / 32) * 32; if (team > 1024) team = 1024; }
     h->team = team;
-    int rmax = h->cfg.rmax > 0 ? h->cfg.rmax : (team == 32 ? 48 : 128);
+    int rmax = h->cfg.rmax > 0 ? h->cfg.rmax : (team == 32 ? 64 : 224);     // S is packed: r(r+1)/2 doubles
     if (rmax > d.mc) rmax = d.mc;
     // shrink rmax until one instance fits
     while (rmax > 8 && polish_smem_doubles(d, rmax) * 8 > budget) rmax -= 8;
@@ -514,7 +514,7 @@ static int configure_launch(bmpc_handle* h) {
         BMPC_CUDA(cudaFuncSetAttribute(k_admm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_admm));
         BMPC_CUDA(cudaFuncSetAttribute(k_polish<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_polish));
         // stragglers (instances the first round did not verify) are few and latency-bound: give each a whole CTA
-        int frmax = d.mc < 96 ? d.mc : 96;
+        int frmax = d.mc < 128 ? d.mc : 128;
         while (frmax > 8 && polish_smem_doubles(d, frmax) * 8 > budget) frmax -= 8;
         if (polish_smem_doubles(d, frmax) * 8 <= budget) {
             h->fb_team = 128; h->fb_rmax = frmax;

@@ -618,7 +618,9 @@ BMPC_HD int bmpc_polish(Team& t, const BmpcDims& d, const BmpcSysOff& o, const d
     const double rho_e = scal[BMPC_S_RHOE];
     const bool soft_on = rho_e > 0.0;
     const double inv_rho_e = soft_on ? 1.0 / rho_e : 0.0;
-    const int NX = d.NX, NU = d.NU, mc = d.mc, LD = rmax;
+    const int NX = d.NX, NU = d.NU, mc = d.mc;
+    // S is stored packed (lower triangle by rows): element (k,l), l <= k, at k(k+1)/2 + l
+    #define BMPC_TRI(k, l) ((size_t)(k) * ((k) + 1) / 2 + (l))
     const double delta = 1e-13;
 
     for (int a = t.tid; a < NU; a += t.n) {
@@ -655,41 +657,43 @@ BMPC_HD int bmpc_polish(Team& t, const BmpcDims& d, const BmpcSysOff& o, const d
                 int i = R[k]; double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
                 tt[k] = W0[i] - (st[i] == 1 ? hi : lo);
             }
-            for (int idx = t.tid; idx < r * r; idx += t.n) {
-                int k = idx / r, l = idx % r;
-                double val = M[R[k] * mc + R[l]];
-                if (k == l) val += (soft_on && R[k] < NX) ? inv_rho_e : delta * (1.0 + fabs(val));
-                S[k * LD + l] = val;
+            for (int k = t.tid; k < r; k += t.n) {
+                const double* Mrow = M + (size_t)R[k] * mc;
+                for (int l = 0; l <= k; l++) {
+                    double val = Mrow[R[l]];
+                    if (k == l) val += (soft_on && R[k] < NX) ? inv_rho_e : delta * (1.0 + fabs(val));
+                    S[BMPC_TRI(k, l)] = val;
+                }
             }
             t.sync();
             // Cholesky S = L L' (lower, in place)
             for (int j = 0; j < r; j++) {
-                double djj = S[j * LD + j];
+                double djj = S[BMPC_TRI(j, j)];
                 if (!(djj > 1e-300)) djj = 1e-300;           // dependent working rows: candidate will fail verification
                 double dj = sqrt(djj), dinv = 1.0 / dj;
                 t.sync();
-                for (int i = j + 1 + t.tid; i < r; i += t.n) S[i * LD + j] *= dinv;
-                if (t.tid == 0) S[j * LD + j] = dj;
+                for (int i = j + 1 + t.tid; i < r; i += t.n) S[BMPC_TRI(i, j)] *= dinv;
+                if (t.tid == 0) S[BMPC_TRI(j, j)] = dj;
                 t.sync();
                 for (int i = j + 1 + t.tid; i < r; i += t.n) {
-                    double lij = S[i * LD + j];
-                    for (int k = j + 1; k <= i; k++) S[i * LD + k] -= lij * S[k * LD + j];
+                    double lij = S[BMPC_TRI(i, j)];
+                    for (int k = j + 1; k <= i; k++) S[BMPC_TRI(i, k)] -= lij * S[BMPC_TRI(k, j)];
                 }
                 t.sync();
             }
             // forward  L y = t
             for (int j = 0; j < r; j++) {
-                double yj = tt[j] / S[j * LD + j];
+                double yj = tt[j] / S[BMPC_TRI(j, j)];
                 t.sync();
-                for (int i = j + 1 + t.tid; i < r; i += t.n) tt[i] -= S[i * LD + j] * yj;
+                for (int i = j + 1 + t.tid; i < r; i += t.n) tt[i] -= S[BMPC_TRI(i, j)] * yj;
                 if (t.tid == 0) tt[j] = yj;
                 t.sync();
             }
             // backward L' mu = y
             for (int j = r - 1; j >= 0; j--) {
-                double mj = tt[j] / S[j * LD + j];
+                double mj = tt[j] / S[BMPC_TRI(j, j)];
                 t.sync();
-                for (int i = t.tid; i < j; i += t.n) tt[i] -= S[j * LD + i] * mj;
+                for (int i = t.tid; i < j; i += t.n) tt[i] -= S[BMPC_TRI(j, i)] * mj;
                 if (t.tid == 0) tt[j] = mj;
                 t.sync();
             }

@@ -35,9 +35,9 @@ int emu_solve(int nx, int nu, int Np, int Nc, const double* sys, const double* x
               int rmax, double eps_abs, double eps_rel, int* iters_out, int* polish_steps_out, double* res_out) {
     BmpcDims d = bmpc_make_dims(nx, nu, Np, Nc); BmpcSysOff o = bmpc_make_off(d);
     SeqTeam t;
-    double* buf = (double*)calloc(8 * d.mc + 8 * d.NU + d.NX + rmax * rmax + rmax + 16, sizeof(double));
+    double* buf = (double*)calloc(8 * d.mc + 8 * d.NU + d.NX + rmax * (rmax + 1) / 2 + rmax + 16, sizeof(double));
     double *g = buf, *cc = g + d.NU, *w = cc + d.NX, *xt = w + d.mc, *r = xt + d.NU, *W0 = r + d.NU, *zz = W0 + d.mc,
-           *murow = zz + d.mc, *S = murow + d.mc, *tt = S + rmax * rmax, *U0 = tt + rmax, *U = U0 + d.NU, *res = U + d.NU;
+           *murow = zz + d.mc, *S = murow + d.mc, *tt = S + rmax * (rmax + 1) / 2, *U0 = tt + rmax, *U = U0 + d.NU, *res = U + d.NU;
     int* st = (int*)calloc(d.mc + rmax, sizeof(int)); int* R = st + d.mc;
     bmpc_prep(t, d, o, sys, x0, um1, xref, xref_mode, g, cc);
     if (cold) { for (int a = 0; a < d.NU; a++) x[a] = 0.0; for (int i = 0; i < d.mc; i++) v[i] = i < d.NX ? cc[i] : 0.0; }
