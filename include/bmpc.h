@@ -52,6 +52,7 @@ typedef struct {
     int32_t team_threads;       /* 0 = auto; 32 = one warp per instance; >32 = one CTA of that size per instance */
     int32_t warps_per_block;    /* 0 = auto (warp team only) */
     int32_t fast_path;          /* 1 = use the thread-per-instance kernels when the shape has one (default), 0 = team kernels only */
+    int32_t n_sys;              /* 1 = every instance shares (Ad,Bd,weights,bounds); batch = one system per instance */
     double eps_feas;            /* slack weight (mpc.py:226) */
     double rho;                 /* <= 0: automatic sqrt(trace H / trace A'A) */
     double sigma, alpha;        /* OSQP defaults 1e-6, 1.6 */
@@ -77,7 +78,7 @@ void bmpc_destroy(bmpc_handle* h);
 const char* bmpc_last_error(const bmpc_handle* h);   /* h may be NULL: error of the last failed bmpc_create */
 
 /* replaces _compute_QP_matrices_ + OSQP.setup (mpc.py:254-269, 456-615): condense + factor on device (K1).
- * All pointers are HOST pointers to one shared system (every instance uses the same matrices). */
+ * All pointers are HOST pointers; each array carries a leading n_sys dimension (n_sys = 1: one shared system). */
 int bmpc_setup(bmpc_handle* h, const double* Ad, const double* Bd, const double* Qx, const double* QxN,
                const double* Qu, const double* QDu, const double* xmin, const double* xmax, const double* umin,
                const double* umax, const double* Dumin, const double* Dumax, const double* uref);
@@ -111,6 +112,21 @@ int bmpc_get_stats(bmpc_handle* h, bmpc_stats* out);
 int bmpc_get_sys(bmpc_handle* h, const char* name, double* out, int capacity);
 /* problem sizes: dims[0..7] = nx, nu, Np, Nc, NX, NU, mc, team_threads */
 int bmpc_get_dims(const bmpc_handle* h, int32_t* dims);
+
+/* ---- batched linear state estimator: the step on the INPUT side of the path.
+ * Replaces LinearStateEstimator.predict/update (/root/reference/pyMPC/kalman.py:109-134) for B instances sharing
+ * (A,B,C,L):  predict  x <- A x + B u, y <- C x   (kalman.py:126-129);   update  x <- x + L (y_meas - y)  (:131-133).
+ * The state lives on the device; bmpc_est_state_ptr() can be handed to bmpc_update(..., on_device=1) so the whole
+ * control loop (estimate -> MPC -> plant input) stays on the GPU. */
+typedef struct bmpc_estimator bmpc_estimator;
+int bmpc_est_create(int32_t nx, int32_t nu, int32_t ny, int32_t batch, int32_t device, const double* A, const double* B,
+                    const double* C, const double* L, const double* x0 /* [batch,nx] host */, bmpc_estimator** out);
+void bmpc_est_destroy(bmpc_estimator* e);
+int bmpc_est_predict(bmpc_estimator* e, const double* u /* [batch,nu] */, int on_device);
+int bmpc_est_update(bmpc_estimator* e, const double* y_meas /* [batch,ny] */, int on_device);
+int bmpc_est_get(bmpc_estimator* e, double* x /* [batch,nx] or NULL */, double* y /* [batch,ny] or NULL */);
+double* bmpc_est_state_ptr(bmpc_estimator* e);           /* device pointer to x [batch,nx] */
+int bmpc_est_set_stream(bmpc_estimator* e, void* cuda_stream);
 
 /* pinned host memory for the end-to-end path (cudaHostAlloc / cudaFreeHost) */
 void* bmpc_host_alloc(uint64_t bytes);

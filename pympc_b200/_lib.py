@@ -16,7 +16,7 @@ DP = ctypes.c_void_p
 class BmpcConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
                 ("nx", "nu", "Np", "Nc", "batch", "device", "soft_on", "max_iter", "first_iters", "pdas_steps",
-                 "rmax", "polish", "team_threads", "warps_per_block", "fast_path")] + \
+                 "rmax", "polish", "team_threads", "warps_per_block", "fast_path", "n_sys")] + \
                [(n, ctypes.c_double) for n in ("eps_feas", "rho", "sigma", "alpha", "eps_abs", "eps_rel")]
 
 
@@ -29,7 +29,8 @@ class BmpcStats(ctypes.Structure):
 EXPORTS = ["bmpc_default_config", "bmpc_create", "bmpc_destroy", "bmpc_last_error", "bmpc_setup", "bmpc_update",
            "bmpc_solve", "bmpc_output", "bmpc_get_sequences", "bmpc_bind_output", "bmpc_set_stream",
            "bmpc_synchronize", "bmpc_get_stats", "bmpc_get_sys", "bmpc_get_dims", "bmpc_host_alloc",
-           "bmpc_host_free", "bmpc_device_count"]
+           "bmpc_host_free", "bmpc_device_count", "bmpc_est_create", "bmpc_est_destroy", "bmpc_est_predict",
+           "bmpc_est_update", "bmpc_est_get", "bmpc_est_state_ptr", "bmpc_est_set_stream"]
 
 
 class BmpcError(RuntimeError):
@@ -63,6 +64,13 @@ def load():
     L.bmpc_host_alloc.argtypes = [ctypes.c_uint64]; L.bmpc_host_alloc.restype = P
     L.bmpc_host_free.argtypes = [P]; L.bmpc_host_free.restype = None
     L.bmpc_device_count.argtypes = []; L.bmpc_device_count.restype = ctypes.c_int
+    L.bmpc_est_create.argtypes = [ctypes.c_int32] * 5 + [DP] * 5 + [ctypes.POINTER(P)]; L.bmpc_est_create.restype = ctypes.c_int
+    L.bmpc_est_destroy.argtypes = [P]; L.bmpc_est_destroy.restype = None
+    L.bmpc_est_predict.argtypes = [P, DP, ctypes.c_int]; L.bmpc_est_predict.restype = ctypes.c_int
+    L.bmpc_est_update.argtypes = [P, DP, ctypes.c_int]; L.bmpc_est_update.restype = ctypes.c_int
+    L.bmpc_est_get.argtypes = [P, DP, DP]; L.bmpc_est_get.restype = ctypes.c_int
+    L.bmpc_est_state_ptr.argtypes = [P]; L.bmpc_est_state_ptr.restype = P
+    L.bmpc_est_set_stream.argtypes = [P, P]; L.bmpc_est_set_stream.restype = ctypes.c_int
     _lib = L
     return L
 

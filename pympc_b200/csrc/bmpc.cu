@@ -115,6 +115,7 @@ struct BmpcInst {
     int32_t* iters;       // [B]
     int32_t* psteps;      // [B]
     int32_t* lvl;         // [B] adaptive-rho ladder level (reset to the base level at every solve)
+    size_t sys_stride;    // 0: all instances share one system block; o.total: instance i uses block i (per-instance Ad, Bd, ...)
 };
 
 // smem (doubles) per instance for the two kernels — keep in sync with the carve-up below
@@ -142,6 +143,7 @@ __global__ void k_admm(BmpcDims d, BmpcSysOff o, const double* __restrict__ sys,
     else { slot = 0; idx = blockIdx.x; }
     if (idx >= count) return;
     const int inst = list ? list[idx] : idx;
+    sys += (size_t)inst * I.sys_stride;
     double* base = smem + (size_t)slot * admm_smem_doubles(d);
     double *g = base, *cc = g + d.NU, *x = cc + d.NX, *v = x + d.NU, *w = v + d.mc, *xt = w + d.mc, *r = xt + d.NU,
            *um1 = r + d.NU, *res = um1 + d.nu + (d.nu & 1);
@@ -192,6 +194,7 @@ __global__ void k_polish(BmpcDims d, BmpcSysOff o, const double* __restrict__ sy
     else { slot = 0; idx = blockIdx.x; }
     if (idx >= count) return;
     const int inst = list ? list[idx] : idx;
+    sys += (size_t)inst * I.sys_stride;
     double* base = smem + (size_t)slot * polish_smem_doubles(d, rmax);
     double *g = base, *cc = g + d.NU, *v = cc + d.NX, *W0 = v + d.mc, *zz = W0 + d.mc, *murow = zz + d.mc,
            *S = murow + d.mc, *tt = S + (size_t)rmax * (rmax + 1) / 2, *U0 = tt + rmax, *U = U0 + d.NU, *um1 = U + d.NU;
@@ -234,6 +237,7 @@ __global__ void k_finalize(BmpcDims d, BmpcSysOff o, const double* __restrict__ 
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= count) return;
     const int inst = list ? list[idx] : idx;
+    sys += (size_t)inst * I.sys_stride;
     const double* res = I.res + (size_t)inst * 4;
     bool conv = res[0] <= eps_abs + eps_rel * res[2] && res[1] <= eps_abs + eps_rel * res[3];
     I.status[inst] = conv ? BMPC_SOLVED_UNPOLISHED : BMPC_MAX_ITER;
@@ -266,6 +270,7 @@ __global__ void k_sequences(BmpcDims d, BmpcSysOff o, const double* __restrict__
     const int slot = threadIdx.x >> 5;
     int inst = blockIdx.x * (blockDim.x >> 5) + slot;
     if (inst >= B) return;
+    sys += (size_t)inst * I.sys_stride;
     double* g = smem + (size_t)slot * (d.NU + d.NX + d.nu + 1);
     double* cc = g + d.NU;
     double* um1 = cc + d.NX;
@@ -469,7 +474,7 @@ void bmpc_default_config(bmpc_config* c) {
     memset(c, 0, sizeof(*c));
     c->Np = 20; c->Nc = 0; c->batch = 1; c->device = 0; c->soft_on = 1;
     c->max_iter = 4000; c->first_iters = 0; c->pdas_steps = 10; c->rmax = 0; c->polish = 1;
-    c->team_threads = 0; c->warps_per_block = 0; c->fast_path = 1;
+    c->team_threads = 0; c->warps_per_block = 0; c->fast_path = 1; c->n_sys = 1;
     c->eps_feas = 1e6; c->rho = 0.0; c->sigma = 1e-6; c->alpha = 1.6; c->eps_abs = 1e-3; c->eps_rel = 1e-3;
 }
 
@@ -541,8 +546,10 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     int ndev = bmpc_device_count();
     if (ndev <= 0) { g_create_err = "no CUDA device visible: libbmpc has no CPU fallback"; return BMPC_ERR_NO_DEVICE; }
     if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "device ordinal out of range"; return BMPC_ERR_ARG; }
+    if (cfg->n_sys != 0 && cfg->n_sys != 1 && cfg->n_sys != cfg->batch) { g_create_err = "n_sys must be 1 (shared system) or batch (one system per instance)"; return BMPC_ERR_ARG; }
     bmpc_handle* h = new bmpc_handle();
     h->cfg = *cfg;
+    if (h->cfg.n_sys <= 0) h->cfg.n_sys = 1;
     if (h->cfg.Nc <= 0) h->cfg.Nc = h->cfg.Np;
     if (h->cfg.max_iter <= 0) h->cfg.max_iter = 4000;
     if (h->cfg.pdas_steps <= 0) h->cfg.pdas_steps = 10;
@@ -560,7 +567,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     const BmpcDims& d = h->d; size_t B = cfg->batch;
     auto dalloc = [&](void** p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 8) == cudaSuccess; };
     bool ok = true;
-    ok &= dalloc((void**)&h->sys, sizeof(double) * h->o.total);
+    ok &= dalloc((void**)&h->sys, sizeof(double) * (size_t)h->o.total * h->cfg.n_sys);
     ok &= dalloc((void**)&h->x0, sizeof(double) * B * d.nx);
     ok &= dalloc((void**)&h->um1, sizeof(double) * B * d.nu);
     ok &= dalloc((void**)&h->um1_solved, sizeof(double) * B * d.nu);
@@ -582,13 +589,14 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     ok &= dalloc((void**)&h->counts, sizeof(int32_t) * 2);
     if (!ok) { h->err = "cudaMalloc failed"; cudaGetLastError(); return fail(BMPC_ERR_CUDA); }
     if (cudaHostAlloc((void**)&h->h_count, sizeof(int32_t) * 4, cudaHostAllocDefault) != cudaSuccess) { h->err = "cudaHostAlloc failed"; return fail(BMPC_ERR_CUDA); }
-    cudaMemset(h->sys, 0, sizeof(double) * h->o.total);
+    cudaMemset(h->sys, 0, sizeof(double) * (size_t)h->o.total * h->cfg.n_sys);
     cudaMemset(h->x0, 0, sizeof(double) * B * d.nx);
     cudaMemset(h->um1, 0, sizeof(double) * B * d.nu);
     cudaMemset(h->xref, 0, sizeof(double) * B * d.NX);
     cudaMemset(h->u0_own, 0, sizeof(double) * B * d.nu);
     cudaMemset(h->I.Us, 0, sizeof(double) * B * d.NU);
     cudaMemset(h->I.Ua, 0, sizeof(double) * B * d.NU);
+    h->I.sys_stride = h->cfg.n_sys > 1 ? (size_t)h->o.total : 0;
     h->I.x0 = h->x0; h->I.um1 = h->um1; h->I.um1_solved = h->um1_solved; h->I.xref = h->xref; h->I.u0 = h->u0_own;
     k_reset<<<(int)((B + 255) / 256), 256, 0, h->stream>>>(h->I, (int)B);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "device initialisation failed"; return fail(BMPC_ERR_CUDA); }
@@ -648,25 +656,31 @@ int bmpc_setup(bmpc_handle* h, const double* Ad, const double* Bd, const double*
     }
     BMPC_CUDA(cudaSetDevice(h->cfg.device));
     const BmpcDims& d = h->d; const BmpcSysOff& o = h->o;
-    std::vector<double> in(o.pw, 0.0);
-    auto put = [&](int off, const double* src, int cnt) { memcpy(in.data() + off, src, sizeof(double) * cnt); };
-    put(o.Ad, Ad, d.nx * d.nx); put(o.Bd, Bd, d.nx * d.nu); put(o.Qx, Qx, d.nx * d.nx); put(o.QxN, QxN, d.nx * d.nx);
-    put(o.Qu, Qu, d.nu * d.nu); put(o.QDu, QDu, d.nu * d.nu); put(o.xmin, xmin, d.nx); put(o.xmax, xmax, d.nx);
-    put(o.umin, umin, d.nu); put(o.umax, umax, d.nu); put(o.Dumin, Dumin, d.nu); put(o.Dumax, Dumax, d.nu); put(o.uref, uref, d.nu);
-    BMPC_CUDA(cudaMemcpyAsync(h->sys, in.data(), sizeof(double) * o.pw, cudaMemcpyHostToDevice, h->stream));
-    k_condense<<<1, 256, 0, h->stream>>>(d, o, h->sys, h->cfg.rho, h->cfg.sigma, h->cfg.alpha, h->cfg.eps_feas, h->cfg.soft_on);
+    const int ns = h->cfg.n_sys;
+    std::vector<double> in((size_t)o.pw * ns, 0.0);
+    for (int si = 0; si < ns; si++) {
+        double* blk = in.data() + (size_t)si * o.pw;
+        auto put = [&](int off, const double* src, int cnt) { memcpy(blk + off, src + (size_t)si * cnt, sizeof(double) * cnt); };
+        put(o.Ad, Ad, d.nx * d.nx); put(o.Bd, Bd, d.nx * d.nu); put(o.Qx, Qx, d.nx * d.nx); put(o.QxN, QxN, d.nx * d.nx);
+        put(o.Qu, Qu, d.nu * d.nu); put(o.QDu, QDu, d.nu * d.nu); put(o.xmin, xmin, d.nx); put(o.xmax, xmax, d.nx);
+        put(o.umin, umin, d.nu); put(o.umax, umax, d.nu); put(o.Dumin, Dumin, d.nu); put(o.Dumax, Dumax, d.nu); put(o.uref, uref, d.nu);
+    }
+    BMPC_CUDA(cudaMemcpy2DAsync(h->sys, sizeof(double) * o.total, in.data(), sizeof(double) * o.pw, sizeof(double) * o.pw, ns,
+                                cudaMemcpyHostToDevice, h->stream));
+    k_condense<<<ns, 256, 0, h->stream>>>(d, o, h->sys, h->cfg.rho, h->cfg.sigma, h->cfg.alpha, h->cfg.eps_feas, h->cfg.soft_on);
     BMPC_CUDA(cudaGetLastError());
-    double scal[BMPC_S_COUNT];
-    BMPC_CUDA(cudaMemcpyAsync(scal, h->sys + o.scal, sizeof(scal), cudaMemcpyDeviceToHost, h->stream));
+    std::vector<double> errs(ns);
+    BMPC_CUDA(cudaMemcpy2DAsync(errs.data(), sizeof(double), h->sys + o.scal + BMPC_S_ERR, sizeof(double) * o.total, sizeof(double), ns,
+                                cudaMemcpyDeviceToHost, h->stream));
     BMPC_CUDA(cudaStreamSynchronize(h->stream));
-    if (scal[BMPC_S_ERR] != 0.0) {
+    for (int si = 0; si < ns; si++) if (errs[si] != 0.0) {
         h->err = "condensed Hessian is not positive definite (Qu/QDu/Qx make the QP non-strictly convex in U)";
         return BMPC_ERR_NOT_PD;
     }
     // thread-per-instance fast path for the compiled small shapes (pendulum, point mass)
     h->tpi_kind = 0;
     // (the Riccati polish treats state rows as the soft penalty they are by default; hard state rows -> team kernels)
-    if (h->cfg.fast_path && h->team == 32 && h->cfg.soft_on) {
+    if (h->cfg.fast_path && h->team == 32 && h->cfg.soft_on && ns == 1) {
         if (d.nx == 4 && d.nu == 1 && d.Np == 20 && d.Nc == 20) h->tpi_kind = 1;
         else if (d.nx == 2 && d.nu == 1 && d.Np == 20 && d.Nc == 20) h->tpi_kind = 2;
     }
@@ -910,5 +924,110 @@ int bmpc_get_sys(bmpc_handle* h, const char* name, double* out, int capacity) {
     h->err = std::string("bmpc_get_sys: unknown array ") + name;
     return BMPC_ERR_ARG;
 }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// batched linear state estimator (kalman.py:109-134): one thread per instance, shared matrices in shared memory
+__global__ void k_est(int nx, int nu, int ny, int B, const double* __restrict__ mats, double* __restrict__ x, double* __restrict__ y,
+                      const double* __restrict__ in, int mode) {
+    extern __shared__ double sm[];
+    const int nm = nx * nx + nx * nu + ny * nx + nx * ny;
+    for (int i = threadIdx.x; i < nm; i += blockDim.x) sm[i] = mats[i];
+    __syncthreads();
+    const double *A = sm, *Bm = A + nx * nx, *C = Bm + nx * nu, *L = C + ny * nx;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double* xb = x + (size_t)b * nx; double* yb = y + (size_t)b * ny;
+    double xn[32];
+    if (mode == 0) {            // predict: x <- A x + B u ; y <- C x
+        const double* u = in + (size_t)b * nu;
+        for (int i = 0; i < nx; i++) {
+            double acc = 0.0;
+            for (int j = 0; j < nx; j++) acc += A[i * nx + j] * xb[j];
+            for (int j = 0; j < nu; j++) acc += Bm[i * nu + j] * u[j];
+            xn[i] = acc;
+        }
+        for (int i = 0; i < nx; i++) xb[i] = xn[i];
+        for (int i = 0; i < ny; i++) { double acc = 0.0; for (int j = 0; j < nx; j++) acc += C[i * nx + j] * xn[j]; yb[i] = acc; }
+    } else {                    // update: x <- x + L (y_meas - y)      (y is NOT refreshed, as in the reference)
+        const double* ym = in + (size_t)b * ny;
+        for (int i = 0; i < nx; i++) {
+            double acc = xb[i];
+            for (int j = 0; j < ny; j++) acc += L[i * ny + j] * (ym[j] - yb[j]);
+            xn[i] = acc;
+        }
+        for (int i = 0; i < nx; i++) xb[i] = xn[i];
+    }
+}
+
+struct bmpc_estimator {
+    int nx, nu, ny, B, device;
+    double *mats = nullptr, *x = nullptr, *y = nullptr, *in = nullptr;
+    cudaStream_t stream = nullptr, own = nullptr;
+};
+
+extern "C" {
+
+int bmpc_est_create(int32_t nx, int32_t nu, int32_t ny, int32_t batch, int32_t device, const double* A, const double* B,
+                    const double* C, const double* L, const double* x0, bmpc_estimator** out) {
+    if (!out || !A || !B || !C || !L || !x0 || nx < 1 || nx > 32 || nu < 1 || ny < 1 || batch < 1) { g_create_err = "bmpc_est_create: bad argument (1 <= nx <= 32)"; return BMPC_ERR_ARG; }
+    *out = nullptr;
+    if (bmpc_device_count() <= device) { g_create_err = "no CUDA device visible: libbmpc has no CPU fallback"; return BMPC_ERR_NO_DEVICE; }
+    cudaSetDevice(device);
+    bmpc_estimator* e = new bmpc_estimator();
+    e->nx = nx; e->nu = nu; e->ny = ny; e->B = batch; e->device = device;
+    const size_t nm = (size_t)nx * nx + (size_t)nx * nu + (size_t)ny * nx + (size_t)nx * ny;
+    const int mx = nu > ny ? nu : ny;
+    bool ok = cudaMalloc((void**)&e->mats, nm * 8) == cudaSuccess && cudaMalloc((void**)&e->x, (size_t)batch * nx * 8) == cudaSuccess &&
+              cudaMalloc((void**)&e->y, (size_t)batch * ny * 8) == cudaSuccess && cudaMalloc((void**)&e->in, (size_t)batch * mx * 8) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&e->own, cudaStreamNonBlocking) == cudaSuccess;
+    if (!ok) { g_create_err = "bmpc_est_create: allocation failed"; bmpc_est_destroy(e); return BMPC_ERR_CUDA; }
+    e->stream = e->own;
+    std::vector<double> m(nm);
+    memcpy(m.data(), A, sizeof(double) * nx * nx); memcpy(m.data() + nx * nx, B, sizeof(double) * nx * nu);
+    memcpy(m.data() + nx * nx + nx * nu, C, sizeof(double) * ny * nx); memcpy(m.data() + nx * nx + nx * nu + ny * nx, L, sizeof(double) * nx * ny);
+    cudaMemcpyAsync(e->mats, m.data(), nm * 8, cudaMemcpyHostToDevice, e->stream);
+    cudaMemcpyAsync(e->x, x0, (size_t)batch * nx * 8, cudaMemcpyHostToDevice, e->stream);
+    // y = C x0 (kalman.py:113): a predict with A = I, B = 0 would do; compute on the host instead (setup only)
+    std::vector<double> y0((size_t)batch * ny);
+    for (int b = 0; b < batch; b++) for (int i = 0; i < ny; i++) { double acc = 0; for (int j = 0; j < nx; j++) acc += C[i * nx + j] * x0[(size_t)b * nx + j]; y0[(size_t)b * ny + i] = acc; }
+    cudaMemcpyAsync(e->y, y0.data(), y0.size() * 8, cudaMemcpyHostToDevice, e->stream);
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) { g_create_err = "bmpc_est_create: upload failed"; bmpc_est_destroy(e); return BMPC_ERR_CUDA; }
+    *out = e;
+    return BMPC_OK;
+}
+
+void bmpc_est_destroy(bmpc_estimator* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaFree(e->mats); cudaFree(e->x); cudaFree(e->y); cudaFree(e->in);
+    if (e->own) cudaStreamDestroy(e->own);
+    delete e;
+}
+
+static int est_run(bmpc_estimator* e, const double* in, int n, int on_device, int mode) {
+    if (!e || !in) return BMPC_ERR_ARG;
+    if (cudaSetDevice(e->device) != cudaSuccess) return BMPC_ERR_CUDA;
+    const double* src = in;
+    if (!on_device) {
+        if (cudaMemcpyAsync(e->in, in, (size_t)e->B * n * 8, cudaMemcpyHostToDevice, e->stream) != cudaSuccess) return BMPC_ERR_CUDA;
+        src = e->in;
+    }
+    const size_t nm = (size_t)e->nx * e->nx + (size_t)e->nx * e->nu + (size_t)e->ny * e->nx + (size_t)e->nx * e->ny;
+    k_est<<<(e->B + 127) / 128, 128, nm * 8, e->stream>>>(e->nx, e->nu, e->ny, e->B, e->mats, e->x, e->y, src, mode);
+    return cudaGetLastError() == cudaSuccess ? BMPC_OK : BMPC_ERR_CUDA;
+}
+int bmpc_est_predict(bmpc_estimator* e, const double* u, int on_device) { return est_run(e, u, e ? e->nu : 0, on_device, 0); }
+int bmpc_est_update(bmpc_estimator* e, const double* y_meas, int on_device) { return est_run(e, y_meas, e ? e->ny : 0, on_device, 1); }
+int bmpc_est_get(bmpc_estimator* e, double* x, double* y) {
+    if (!e) return BMPC_ERR_ARG;
+    cudaSetDevice(e->device);
+    if (x) cudaMemcpyAsync(x, e->x, (size_t)e->B * e->nx * 8, cudaMemcpyDeviceToHost, e->stream);
+    if (y) cudaMemcpyAsync(y, e->y, (size_t)e->B * e->ny * 8, cudaMemcpyDeviceToHost, e->stream);
+    return cudaStreamSynchronize(e->stream) == cudaSuccess ? BMPC_OK : BMPC_ERR_CUDA;
+}
+double* bmpc_est_state_ptr(bmpc_estimator* e) { return e ? e->x : nullptr; }
+int bmpc_est_set_stream(bmpc_estimator* e, void* s) { if (!e) return BMPC_ERR_ARG; e->stream = s ? (cudaStream_t)s : e->own; return BMPC_OK; }
 
 }  // extern "C"

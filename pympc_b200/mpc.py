@@ -66,6 +66,18 @@ class MPCController:
                  eps_feas=1e6, eps_rel=1e-3, eps_abs=1e-3, batch=None, device=0, **solver_options):
         Ad = np.asarray(Ad.toarray() if hasattr(Ad, "toarray") else Ad)
         Bd = np.asarray(Bd.toarray() if hasattr(Bd, "toarray") else Bd)
+        # extension: Ad of shape (B, nx, nx) selects one system per instance; Bd, the weights and the
+        # bounds may then carry a leading batch dimension too (otherwise they are shared)
+        self._per_instance = batch is not None and Ad.ndim == 3
+        if self._per_instance:
+            if Ad.shape[0] != int(batch) or Ad.shape[1] != Ad.shape[2]:
+                raise ValueError("Ad should be a square matrix of dimension (nx,nx)!")
+            self._sys_full = dict(Ad=Ad, Bd=Bd, Qx=Qx, QxN=QxN, Qu=Qu, QDu=QDu, xmin=xmin, xmax=xmax, umin=umin, umax=umax,
+                                  Dumin=Dumin, Dumax=Dumax)
+            pick = lambda a, nd: None if a is None else (np.asarray(a)[0] if np.ndim(a) == nd + 1 else a)
+            Ad = Ad[0]; Bd = pick(Bd, 2)
+            Qx, QxN, Qu, QDu = pick(Qx, 2), pick(QxN, 2), pick(Qu, 2), pick(QDu, 2)
+            xmin, xmax, umin, umax, Dumin, Dumax = (pick(a, 1) for a in (xmin, xmax, umin, umax, Dumin, Dumax))
         if __is_matrix__(Ad) and (Ad.shape[0] == Ad.shape[1]):
             self.Ad = Ad
             self.nx = Ad.shape[0]
@@ -245,6 +257,8 @@ class MPCController:
         cfg.eps_feas = float(self.eps_feas)
         # quirk Q1: the reference hands eps_rel to OSQP as eps_abs and vice versa (mpc.py:266)
         cfg.eps_abs, cfg.eps_rel = float(self.eps_rel), float(self.eps_abs)
+        if self._per_instance:
+            cfg.n_sys = B
         for k, v in self.solver_options.items():
             if not hasattr(cfg, k):
                 raise TypeError(f"unknown solver option {k!r}")
@@ -262,6 +276,19 @@ class MPCController:
         QDu = _dense(self.QDu) if self.JDU_ON else z((nu, nu))
         args = [np.ascontiguousarray(a, dtype=float) for a in
                 (self.Ad, self.Bd, Qx, QxN, Qu, QDu, self.xmin, self.xmax, self.umin, self.umax, self.Dumin, self.Dumax, self.uref)]
+        if self._per_instance:
+            # every system array gets a leading batch dimension (shared ones are broadcast)
+            full = self._sys_full
+            def per(name, shared, nd, on=True):
+                a = full.get(name)
+                a = shared if (a is None or np.ndim(a) != nd + 1) else np.asarray(a, dtype=float)
+                a = np.broadcast_to(np.asarray(a, dtype=float), (B,) + np.shape(shared))
+                return np.ascontiguousarray(a if on else 0 * a)
+            args = [per("Ad", args[0], 2), per("Bd", args[1], 2), per("Qx", _dense(self.Qx), 2, self.JX_ON),
+                    per("QxN", _dense(self.QxN), 2, self.JX_ON), per("Qu", _dense(self.Qu), 2, self.JU_ON),
+                    per("QDu", _dense(self.QDu), 2, self.JDU_ON), per("xmin", args[6], 1), per("xmax", args[7], 1),
+                    per("umin", args[8], 1), per("umax", args[9], 1), per("Dumin", args[10], 1), per("Dumax", args[11], 1),
+                    np.ascontiguousarray(np.broadcast_to(self.uref, (B, nu)))]
         self._check(L.bmpc_setup(self._h, *[ptr(a) for a in args]))
         self._Qx_d, self._QxN_d, self._Qu_d, self._QDu_d = Qx, QxN, Qu, QDu
         self._um1_for_J = self.uminus1_rh
@@ -295,6 +322,16 @@ class MPCController:
         self._um1_for_J = self.uminus1_rh
         self._push(x, u, xref)
         self._J_dirty = True           # J_CNST is recomputed lazily (it is O(B) host work and rarely read)
+        if solve:
+            self.solve()
+
+    def update_from_device(self, x_ptr, u_ptr=None, solve=True):
+        """update() with x (and optionally u_-1) already resident on this device, e.g. the state of a
+        ``pympc_b200.kalman.LinearStateEstimator`` — no host round trip between estimator and K3."""
+        if self._h is None:
+            raise BmpcError("update_from_device() before setup()")
+        self._check(self._L.bmpc_update(self._h, x_ptr, u_ptr, None, 1, 1))
+        self._J_dirty = True
         if solve:
             self.solve()
 

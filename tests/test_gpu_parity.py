@@ -258,3 +258,55 @@ def test_long_closed_loop_random_batch_stays_solved(MPC):
     assert worst == 0
     assert np.max(np.abs(X[:, 0] - Xref[:, 0])) < 1e-2 and np.max(np.abs(X[:, 2])) < 1e-2
     K.close()
+
+
+def test_batched_state_estimator_vs_oracle(MPC):
+    """LinearStateEstimator.predict/update (kalman.py:126-133) batched on the GPU vs the numpy restatement; then the
+    estimate feeds the MPC update straight from device memory (estimator -> K3 without a host round trip)."""
+    from pympc_b200.kalman import LinearStateEstimator
+    from oracle.estimator import LinearStateEstimator as Ref
+    cfg = pendulum(); rng = np.random.default_rng(7); B = 257
+    A, Bm = cfg["Ad"], cfg["Bd"]; C = np.array([[1.0, 0, 0, 0], [0, 0, 1.0, 0]]); D = np.zeros((2, 1))
+    L = 0.1 * rng.standard_normal((4, 2))
+    X0 = 0.1 * rng.standard_normal((B, 4))
+    E = LinearStateEstimator(X0, A, Bm, C, D, L, batch=B)
+    refs = [Ref(X0[b], A, Bm, C, D, L) for b in range(B)]
+    for t in range(5):
+        U = rng.standard_normal((B, 1)); Y = rng.standard_normal((B, 2))
+        xp = E.predict(U); xu = E.update(Y)
+        for b in (0, 100, 256):
+            assert np.max(np.abs(refs[b].predict(U[b]) - xp[b])) < 1e-12
+            assert np.max(np.abs(refs[b].update(Y[b]) - xu[b])) < 1e-12
+        for b in range(B):
+            if b not in (0, 100, 256):
+                refs[b].predict(U[b]); refs[b].update(Y[b])
+    # chain: estimator state (device) -> MPC update (device pointer) -> same u as with the host copy of the state
+    K = MPC(cfg["Ad"], cfg["Bd"], Np=20, x0=E.x, xref=cfg["xref"], uminus1=np.zeros(1), batch=B,
+            **{k: cfg[k] for k in ("Qx", "QxN", "Qu", "QDu", "xmin", "xmax", "umin", "umax", "Dumin", "Dumax", "eps_feas")})
+    K.setup(); u_host = K.output()
+    K.update_from_device(E.device_state()); u_dev = K.output()
+    assert np.max(np.abs(u_dev - u_host)) < 1e-9
+    K.close(); E.close()
+
+
+def test_per_instance_systems_vs_oracle(MPC):
+    """heterogeneous (Ad, Bd, weights, bounds) — one system per instance, condensed per instance on the
+    device (k_condense grid = batch), solved by the team kernels; every instance vs the oracle on ITS OWN QP."""
+    cfg = pendulum(); rng = np.random.default_rng(11); B = 12
+    Ad = np.stack([cfg["Ad"] + 0.01 * rng.standard_normal((4, 4)) * (cfg["Ad"] != 0) for _ in range(B)])
+    Bd = np.stack([cfg["Bd"] * (1 + 0.1 * rng.standard_normal()) for _ in range(B)])
+    Qx = np.stack([np.diag([0.3, 0, 1.0, 0]) * (1 + 0.3 * rng.random()) for _ in range(B)])
+    umax = np.stack([np.array([15.0 + 10 * rng.random()]) for _ in range(B)])
+    X0, Xref = pendulum_random(B, seed=3)
+    K = MPC(Ad, Bd, Np=20, x0=X0, xref=Xref, uminus1=np.zeros(1), batch=B, Qx=Qx, QxN=Qx, Qu=cfg["Qu"], QDu=cfg["QDu"],
+            xmin=cfg["xmin"], xmax=cfg["xmax"], umin=-umax, umax=umax, Dumin=cfg["Dumin"], Dumax=cfg["Dumax"], eps_feas=1e3)
+    K.setup()
+    X = X0.copy(); U = np.zeros((B, 1))
+    for t in range(3):
+        K.update(X, U); Un, info = K.output(return_u_seq=True)
+        for b in range(B):
+            c = dict(cfg); c.update(Ad=Ad[b], Bd=Bd[b], Qx=Qx[b], QxN=Qx[b], umin=-umax[b], umax=umax[b], x0=X[b], xref=Xref[b], uminus1=U[b])
+            ref, Q = _oracle_u(c)
+            assert np.max(np.abs(info["u_seq"][b].ravel() - ref)) < TOL, (t, b)
+        U = Un; X = np.einsum("bij,bj->bi", Ad, X) + np.einsum("bij,bj->bi", Bd, U)
+    K.close()
