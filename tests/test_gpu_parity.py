@@ -280,12 +280,15 @@ def test_batched_state_estimator_vs_oracle(MPC):
         for b in range(B):
             if b not in (0, 100, 256):
                 refs[b].predict(U[b]); refs[b].update(Y[b])
-    # chain: estimator state (device) -> MPC update (device pointer) -> same u as with the host copy of the state
-    K = MPC(cfg["Ad"], cfg["Bd"], Np=20, x0=E.x, xref=cfg["xref"], uminus1=np.zeros(1), batch=B,
-            **{k: cfg[k] for k in ("Qx", "QxN", "Qu", "QDu", "xmin", "xmax", "umin", "umax", "Dumin", "Dumax", "eps_feas")})
-    K.setup(); u_host = K.output()
+    # chain: estimator state (device) -> MPC update (device pointer) gives the same u as the host copy of the state
+    kw = {k: cfg[k] for k in ("Qx", "QxN", "Qu", "QDu", "xmin", "xmax", "umin", "umax", "Dumin", "Dumax", "eps_feas")}
+    Ka = MPC(cfg["Ad"], cfg["Bd"], Np=20, x0=np.zeros(4), xref=cfg["xref"], uminus1=np.zeros(1), batch=B, **kw)
+    K = MPC(cfg["Ad"], cfg["Bd"], Np=20, x0=np.zeros(4), xref=cfg["xref"], uminus1=np.zeros(1), batch=B, **kw)
+    Ka.setup(); Ka.output(); K.setup(); K.output()
+    Ka.update(E.x); u_host = Ka.output()
     K.update_from_device(E.device_state()); u_dev = K.output()
     assert np.max(np.abs(u_dev - u_host)) < 1e-9
+    Ka.close()
     K.close(); E.close()
 
 
