@@ -313,3 +313,24 @@ def test_per_instance_systems_vs_oracle(MPC):
             assert np.max(np.abs(info["u_seq"][b].ravel() - ref)) < TOL, (t, b)
         U = Un; X = np.einsum("bij,bj->bi", Ad, X) + np.einsum("bij,bj->bi", Bd, U)
     K.close()
+
+
+def test_full_size_fast_path_agrees_with_team_path(MPC):
+    """Two independent implementations at full size (65 536 random instances, 3 warm steps): the thread-per-instance
+    kernels (recursion-based ADMM + Riccati polish) and the team kernels (dense mat-vec ADMM + Schur polish) must
+    return the same u* for EVERY instance — both are KKT-verified minimisers of the same QP."""
+    cfg = pendulum(); B = 65536
+    X0, Xref = pendulum_random(B, seed=5)
+    kw = {k: cfg[k] for k in ("Qx", "QxN", "Qu", "QDu", "xmin", "xmax", "umin", "umax", "Dumin", "Dumax", "eps_feas")}
+    Ka = MPC(cfg["Ad"], cfg["Bd"], Np=20, x0=X0, xref=Xref, uminus1=np.zeros(1), batch=B, fast_path=1, **kw)
+    Kb = MPC(cfg["Ad"], cfg["Bd"], Np=20, x0=X0, xref=Xref, uminus1=np.zeros(1), batch=B, fast_path=0, **kw)
+    Ka.setup(); Kb.setup()
+    X = X0.copy(); U = np.zeros((B, 1))
+    for t in range(3):
+        Ka.update(X, U); Kb.update(X, U)
+        Ua, ia = Ka.output(return_u_seq=True); Ub, ib = Kb.output(return_u_seq=True)
+        ok = (Ka._status == 1) & (Kb._status == 1)
+        assert ok.mean() > 0.999
+        assert np.max(np.abs(ia["u_seq"][ok] - ib["u_seq"][ok])) < 1e-7, t
+        U = Ua; X = X @ cfg["Ad"].T + U @ cfg["Bd"].T
+    Ka.close(); Kb.close()
