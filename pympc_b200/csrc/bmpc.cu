@@ -313,11 +313,18 @@ constexpr int TPI_STR = 33;   // padded lane stride of the shared-memory columns
 
 template <class S>
 __device__ __forceinline__ void tpi_load_v(const BmpcInst& I, int inst0, int nvalid, double* smem, int row_off) {
+    // coalesced global read -> transposed shared write, issued as asynchronous 8-byte copies (LDGSTS) so that the 125
+    // copies of a lane are all in flight at once instead of one load->store round trip per element
     const double* src = I.vw + (size_t)inst0 * S::mc;
     for (int idx = threadIdx.x; idx < nvalid * S::mc; idx += 32) {
         int t = idx / S::mc, i = idx - t * S::mc;
-        if (i >= S::nx) smem[(row_off + i - S::nx) * TPI_STR + t] = src[idx];
+        if (i >= S::nx) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(smem + (row_off + i - S::nx) * TPI_STR + t);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + idx) : "memory");
+        }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 template <class S>
@@ -354,6 +361,7 @@ __global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmm
         }
     } else {
         double* dst = I.vw + (size_t)idx0 * S::mc;
+#pragma unroll 5
         for (int idx = lane; idx < nvalid * S::mc; idx += 32) {
             int t = idx / S::mc, i = idx - t * S::mc;
             dst[idx] = (i >= S::nx) ? smem[(i - S::nx) * TPI_STR + t] : I.x0[(size_t)(idx0 + t) * S::nx + i];
@@ -385,11 +393,8 @@ __global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiRi
 #pragma unroll
     for (int q = 0; q < S::nu; q++) um1[q] = I.um1[(size_t)inst * S::nu + q];
     const TpiCommon<S>& c = P.c;
-    TpiMask up, dn;
-    tpi_for_rows<S>(c, um1, [&](int i, double lo, double hi, double) {
-        const double vi = W(i);
-        up.set(i, vi > hi + 1e-9 * (1.0 + fabs(hi))); dn.set(i, vi < lo - 1e-9 * (1.0 + fabs(lo)));
-    });
+    TpiSets up, dn;
+    tpi_sets_from_v<S>(c, um1, W, up, dn);
     // from here on the column is this thread's private workspace (Riccati gains): no cross-lane traffic
     const int ps = tpi_polish_riccati<S>(P, W, x0, um1, xref, up, dn, max_steps);
     if (ps > 0) {
@@ -397,7 +402,7 @@ __global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiRi
         double* vdst = I.vw + (size_t)inst * S::mc;
         double* udst = I.Us + (size_t)inst * S::NU;
         double* xdst = I.xw + (size_t)inst * S::NU;
-        TpiMask t1, t2; double mm = 0.0;
+        TpiSets t1, t2; double mm = 0.0;
         tpi_ric_forward<S, true>(P, W, x0, um1, up, dn, t1, t2, mm,
             [&](int i, double zi, double mu, double irho) { vdst[S::nx + i] = zi + mu * irho; },
             [&](int j, double u) { udst[j] = u; xdst[j] = u; if (j == 0) u0_out[inst] = u; });

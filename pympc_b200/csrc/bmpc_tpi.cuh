@@ -242,54 +242,51 @@ BMPC_HD void tpi_admm(const TpiAdmmParams<S>& P, TpiAcc V, const double* x0, con
 }
 
 // ------------------------------------------------------------------------------------------------
-// TPI polish: same primal-dual active-set / KKT-verified scheme as bmpc_polish (bmpc_core.cuh), one thread
-// per instance.  Sets are two 128-bit masks; the candidate's rows come from a forward simulation; the
-// Schur matrix S (<= RMAX x RMAX, packed lower) lives in this thread's shared-memory column.
-struct TpiMask {
-    unsigned long long w[2];
-    BMPC_HD TpiMask() { w[0] = 0ull; w[1] = 0ull; }
-    // explicit selects (no dynamic indexing of w[]) so the masks stay in registers
-    BMPC_HD bool get(int i) const { return (((i < 64) ? w[0] : w[1]) >> (i & 63)) & 1ull; }
-    BMPC_HD void set(int i, bool b) {
-        const unsigned long long bit = (b ? 1ull : 0ull) << (i & 63);
-        if (i < 64) w[0] |= bit; else w[1] |= bit;
-    }
+// Working sets of one instance, split by row class so that the horizon loops read / write a whole stage with one
+// shift (profiles/: per-row 64-bit variable shifts were 28 % of the polish instructions):
+//   x : state rows, bit (k*nx + a) <-> row of x_{k+1}[a]   (Np*nx <= 128 bits)
+//   u : input rows, bit j;   d : delta-u rows, bit rr (rr = 0..Np; rr = Np is the reference's spurious last row)
+struct TpiSets {
+    unsigned long long xl, xh;
+    unsigned u, d;
+    BMPC_HD TpiSets() : xl(0ull), xh(0ull), u(0u), d(0u) {}
 };
-BMPC_HD int tpi_popc(unsigned long long v) {
-#ifdef BMPC_HOSTEMU
-    return __builtin_popcountll(v);
-#else
-    return __popcll(v);
-#endif
+// n (<= 8) state-row bits starting at bit position pos
+BMPC_HD unsigned tpi_xget(const TpiSets& s, int pos, int n) {
+    unsigned long long v;
+    if (pos >= 64) v = s.xh >> (pos - 64);
+    else { v = s.xl >> pos; if (pos + n > 64) v |= s.xh << (64 - pos); }
+    return (unsigned)v & ((1u << n) - 1u);
 }
-// number of set bits strictly below position i
-BMPC_HD int tpi_rank(const TpiMask& a, int i) {
-    if (i < 64) return tpi_popc(a.w[0] & ((1ull << i) - 1ull));
-    return tpi_popc(a.w[0]) + tpi_popc(a.w[1] & ((1ull << (i - 64)) - 1ull));
+BMPC_HD void tpi_xput(TpiSets& s, int pos, int n, unsigned bits) {
+    const unsigned long long b = bits;
+    if (pos >= 64) s.xh |= b << (pos - 64);
+    else { s.xl |= b << pos; if (pos + n > 64) s.xh |= b >> (64 - pos); }
 }
 
-// ---- row iterators (rolled over the horizon so the code stays small; inner nx / nu loops are unrolled) ----
-// f(i, lo, hi, rho) for every TPI row i
-template <class S, class F>
-BMPC_HD void tpi_for_rows(const TpiCommon<S>& c, const double* um1, F f) {
-    constexpr int nx = S::nx, nu = S::nu, Np = S::Np, NS = S::NS, NU = S::NU, ND = S::ND;
+// initial working sets from the ADMM iterate v (rows sitting on a bound to rounding level stay out of the first guess)
+template <class S, class Acc>
+BMPC_HD void tpi_sets_from_v(const TpiCommon<S>& c, const double* um1, Acc V, TpiSets& up, TpiSets& dn) {
+    constexpr int nx = S::nx, Np = S::Np, NS = S::NS, NU = S::NU;
+    static_assert(S::nu == 1 && S::Nc == S::Np && S::NS <= 128 && S::Np < 32, "TPI sets: nu == 1, Nc == Np, Np*nx <= 128");
+    auto over = [](double v, double hi) { return v > hi + 1e-9 * (1.0 + fabs(hi)); };
+    auto under = [](double v, double lo) { return v < lo - 1e-9 * (1.0 + fabs(lo)); };
 #pragma unroll 1
     for (int k = 0; k < Np; k++) {
+        unsigned bu = 0u, bd = 0u;
 #pragma unroll
-        for (int a = 0; a < nx; a++) f(k * nx + a, c.xmin[a], c.xmax[a], c.rhox[a]);
+        for (int a = 0; a < nx; a++) {
+            const double v = V(k * nx + a);
+            bu |= (over(v, c.xmax[a]) ? 1u : 0u) << a; bd |= (under(v, c.xmin[a]) ? 1u : 0u) << a;
+        }
+        tpi_xput(up, k * nx, nx, bu); tpi_xput(dn, k * nx, nx, bd);
+        const double vu = V(NS + k);
+        up.u |= (over(vu, c.umax[0]) ? 1u : 0u) << k; dn.u |= (under(vu, c.umin[0]) ? 1u : 0u) << k;
+        const double vd = V(NS + NU + k), sh = (k == 0) ? um1[0] : 0.0;
+        up.d |= (over(vd, c.dmax[0] + sh) ? 1u : 0u) << k; dn.d |= (under(vd, c.dmin[0] + sh) ? 1u : 0u) << k;
     }
-#pragma unroll 1
-    for (int j = 0; j < NU / nu; j++) {
-#pragma unroll
-        for (int b = 0; b < nu; b++) f(NS + j * nu + b, c.umin[b], c.umax[b], c.rhou[b]);
-    }
-#pragma unroll
-    for (int b = 0; b < nu; b++) f(NS + NU + b, c.dmin[b] + um1[b], c.dmax[b] + um1[b], c.rhod[b]);
-#pragma unroll 1
-    for (int j = 1; j < ND / nu; j++) {
-#pragma unroll
-        for (int b = 0; b < nu; b++) f(NS + NU + j * nu + b, c.dmin[b], c.dmax[b], c.rhod[b]);
-    }
+    const double vq = V(NS + NU + Np);
+    up.d |= (over(vq, c.dmax[0]) ? 1u : 0u) << Np; dn.d |= (under(vq, c.dmin[0]) ? 1u : 0u) << Np;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -313,22 +310,21 @@ enum { TPI_FREE = 0, TPI_UPIN = 1, TPI_DPIN = 2, TPI_QPIN = 3 };
 // pin of stage j implied by the working set (priority: input bound, then delta-u row, then the reference's
 // spurious last row  Dumin <= -u_{N-1} <= Dumax)
 template <class S>
-BMPC_HD int tpi_pin_of(const TpiCommon<S>& c, const TpiMask& up, const TpiMask& dn, int j, double& val) {
-    constexpr int NS = S::NS, NU = S::NU, N = S::Np;
-    const int iu = NS + j, id = NS + NU + j, iq = NS + NU + N;
-    if (up.get(iu)) { val = c.umax[0]; return TPI_UPIN; }
-    if (dn.get(iu)) { val = c.umin[0]; return TPI_UPIN; }
-    if (up.get(id)) { val = c.dmax[0]; return TPI_DPIN; }
-    if (dn.get(id)) { val = c.dmin[0]; return TPI_DPIN; }
+BMPC_HD int tpi_pin_of(const TpiCommon<S>& c, const TpiSets& up, const TpiSets& dn, int j, double& val) {
+    constexpr int N = S::Np;
+    if ((up.u >> j) & 1u) { val = c.umax[0]; return TPI_UPIN; }
+    if ((dn.u >> j) & 1u) { val = c.umin[0]; return TPI_UPIN; }
+    if ((up.d >> j) & 1u) { val = c.dmax[0]; return TPI_DPIN; }
+    if ((dn.d >> j) & 1u) { val = c.dmin[0]; return TPI_DPIN; }
     if (j == N - 1) {
-        if (up.get(iq)) { val = -c.dmax[0]; return TPI_QPIN; }     // -u = Dumax
-        if (dn.get(iq)) { val = -c.dmin[0]; return TPI_QPIN; }
+        if ((up.d >> N) & 1u) { val = -c.dmax[0]; return TPI_QPIN; }     // -u = Dumax
+        if ((dn.d >> N) & 1u) { val = -c.dmin[0]; return TPI_QPIN; }
     }
     val = 0.0; return TPI_FREE;
 }
 
 template <class S>
-BMPC_HD void tpi_ric_backward(const TpiRicParams<S>& P, TpiAcc W, const double* xref, const TpiMask& up, const TpiMask& dn) {
+BMPC_HD void tpi_ric_backward(const TpiRicParams<S>& P, TpiAcc W, const double* xref, const TpiSets& up, const TpiSets& dn) {
     static_assert(S::nu == 1 && S::Nc == S::Np, "Riccati polish is specialised to nu == 1, Nc == Np");
     constexpr int nx = S::nx, N = S::Np, nz = nx + 1;
     const TpiCommon<S>& c = P.c;
@@ -336,10 +332,10 @@ BMPC_HD void tpi_ric_backward(const TpiRicParams<S>& P, TpiAcc W, const double* 
     double Pxx[nx * nx], pxw[nx], px[nx], pww = 0.0, pw = 0.0;
     // terminal: state cost of x_N
     {
+        const unsigned bu = tpi_xget(up, (N - 1) * nx, nx), bd = tpi_xget(dn, (N - 1) * nx, nx);
 #pragma unroll
         for (int a = 0; a < nx; a++) {
-            const int i = (N - 1) * nx + a;
-            const bool vu = up.get(i), vd = dn.get(i);
+            const bool vu = (bu >> a) & 1u, vd = (bd >> a) & 1u;
             double q = 0.0;
 #pragma unroll
             for (int b = 0; b < nx; b++) { Pxx[a * nx + b] = P.QxN[a * nx + b]; q += P.QxN[a * nx + b] * xref[b]; }
@@ -384,10 +380,10 @@ BMPC_HD void tpi_ric_backward(const TpiRicParams<S>& P, TpiAcc W, const double* 
             hx[a] = h; gx[a] = g;
         }
         if (k >= 1) {                              // stage cost of x_k (x_0 is data)
+            const unsigned bu = tpi_xget(up, (k - 1) * nx, nx), bd = tpi_xget(dn, (k - 1) * nx, nx);
 #pragma unroll
             for (int a = 0; a < nx; a++) {
-                const int i = (k - 1) * nx + a;
-                const bool vu = up.get(i), vd = dn.get(i);
+                const bool vu = (bu >> a) & 1u, vd = (bd >> a) & 1u;
                 double q = 0.0;
 #pragma unroll
                 for (int b = 0; b < nx; b++) { Hxx[a * nx + b] += P.Qx[a * nx + b]; q += P.Qx[a * nx + b] * xref[b]; }
@@ -442,8 +438,8 @@ BMPC_HD void tpi_ric_backward(const TpiRicParams<S>& P, TpiAcc W, const double* 
 // Forward sweep.  EMIT == false: KKT verification, returns ok and the next working set (nup, ndn), updates mumax.
 // EMIT == true : calls out(i, zi, mu_i, 1/rho_i) for every TPI row and outu(j, u_j) for every input.
 template <class S, bool EMIT, class FR, class FU>
-BMPC_HD bool tpi_ric_forward(const TpiRicParams<S>& P, TpiAcc W, const double* x0, const double* um1, const TpiMask& up,
-                             const TpiMask& dn, TpiMask& nup, TpiMask& ndn, double& mumax, FR out, FU outu) {
+BMPC_HD bool tpi_ric_forward(const TpiRicParams<S>& P, TpiAcc W, const double* x0, const double* um1, const TpiSets& up,
+                             const TpiSets& dn, TpiSets& nup, TpiSets& ndn, double& mumax, FR out, FU outu) {
     constexpr int nx = S::nx, N = S::Np, nz = nx + 1, NS = S::NS, NU = S::NU;
     const TpiCommon<S>& c = P.c;
     const double mutol = 1e-9 * (1.0 + mumax);
@@ -452,13 +448,14 @@ BMPC_HD bool tpi_ric_forward(const TpiRicParams<S>& P, TpiAcc W, const double* x
     double x[nx], w = um1[0];
 #pragma unroll
     for (int a = 0; a < nx; a++) x[a] = x0[a];
-    auto hard_row = [&](int i, double zi, double lo, double hi, double mu, double irho) {
-        if (EMIT) { out(i, zi, mu, irho); return; }
-        const bool su = up.get(i), sd = dn.get(i);
+    // hard row: KKT check of one row, returns its bits of the next working set (bit0 = up, bit1 = dn)
+    auto hard_row = [&](int i, bool su, bool sd, double zi, double lo, double hi, double mu, double irho) -> unsigned {
+        if (EMIT) { out(i, zi, mu, irho); return 0u; }
         const bool vu = zi > hi + 1e-9 * (1.0 + fabs(hi)), vd = zi < lo - 1e-9 * (1.0 + fabs(lo));
         if (vu || vd || (su && mu < -mutol) || (sd && mu > mutol)) ok = false;
         const bool nu_ = vu || (!vd && su && mu > 0.0);
-        nup.set(i, nu_); ndn.set(i, (!nu_) && (vd || (sd && mu < 0.0)));
+        const bool nd_ = (!nu_) && (vd || (sd && mu < 0.0));
+        return (nu_ ? 1u : 0u) | (nd_ ? 2u : 0u);
     };
 #pragma unroll 1
     for (int k = 0; k < N; k++) {
@@ -475,10 +472,15 @@ BMPC_HD bool tpi_ric_forward(const TpiRicParams<S>& P, TpiAcc W, const double* x
         else { u = pin; mu_q = lin; }
         mnew = fmax(mnew, fmax(fabs(mu_u), fmax(fabs(mu_d), fabs(mu_q))));
         if (EMIT) outu(k, u);
-        hard_row(NS + k, u, c.umin[0], c.umax[0], mu_u, c.irhou[0]);
-        if (k == 0) hard_row(NS + NU, u, c.dmin[0] + w, c.dmax[0] + w, mu_d, c.irhod[0]);     // row value u_0, bounds shifted by u_-1
-        else hard_row(NS + NU + k, u - w, c.dmin[0], c.dmax[0], mu_d, c.irhod[0]);
-        if (k == N - 1) hard_row(NS + NU + N, -u, c.dmin[0], c.dmax[0], mu_q, c.irhod[0]);
+        unsigned hb = hard_row(NS + k, (up.u >> k) & 1u, (dn.u >> k) & 1u, u, c.umin[0], c.umax[0], mu_u, c.irhou[0]);
+        nup.u |= (hb & 1u) << k; ndn.u |= (hb >> 1) << k;
+        const double sh = (k == 0) ? w : 0.0;               // row 0: value u_0, bounds shifted by u_-1; else u_k - u_{k-1}
+        hb = hard_row(NS + NU + k, (up.d >> k) & 1u, (dn.d >> k) & 1u, (k == 0) ? u : u - w, c.dmin[0] + sh, c.dmax[0] + sh, mu_d, c.irhod[0]);
+        nup.d |= (hb & 1u) << k; ndn.d |= (hb >> 1) << k;
+        if (k == N - 1) {
+            hb = hard_row(NS + NU + N, (up.d >> N) & 1u, (dn.d >> N) & 1u, -u, c.dmin[0], c.dmax[0], mu_q, c.irhod[0]);
+            nup.d |= (hb & 1u) << N; ndn.d |= (hb >> 1) << N;
+        }
         double xn[nx];
 #pragma unroll
         for (int a = 0; a < nx; a++) {
@@ -488,13 +490,14 @@ BMPC_HD bool tpi_ric_forward(const TpiRicParams<S>& P, TpiAcc W, const double* x
             xn[a] = a0 + a1;
         }
         w = u;
+        const unsigned bu = tpi_xget(up, k * nx, nx), bd = tpi_xget(dn, k * nx, nx);
+        unsigned nbu = 0u, nbd = 0u;
 #pragma unroll
         for (int a = 0; a < nx; a++) {
             x[a] = xn[a];
-            const int i = k * nx + a;
             const double zi = xn[a], lo = c.xmin[a], hi = c.xmax[a];
-            const bool su = up.get(i), sd = dn.get(i);
-            if (EMIT) { out(i, zi, su ? P.rho_e * (zi - hi) : (sd ? P.rho_e * (zi - lo) : 0.0), c.irhox[a]); continue; }
+            const bool su = (bu >> a) & 1u, sd = (bd >> a) & 1u;
+            if (EMIT) { out(k * nx + a, zi, su ? P.rho_e * (zi - hi) : (sd ? P.rho_e * (zi - lo) : 0.0), c.irhox[a]); continue; }
             const bool nu_ = zi > hi + 1e-11 * (1.0 + fabs(hi)), nd_ = (!nu_) && zi < lo - 1e-11 * (1.0 + fabs(lo));
             if (nu_ != su || nd_ != sd) {
                 const bool hi_side = (su || nu_) && !(sd || nd_), lo_side = (sd || nd_) && !(su || nu_);
@@ -502,8 +505,9 @@ BMPC_HD bool tpi_ric_forward(const TpiRicParams<S>& P, TpiAcc W, const double* x
                 const double bnd = hi_side ? hi : lo;
                 if (!(gap <= 1e-11 * (1.0 + fabs(bnd)))) ok = false;
             }
-            nup.set(i, nu_); ndn.set(i, nd_);
+            nbu |= (nu_ ? 1u : 0u) << a; nbd |= (nd_ ? 1u : 0u) << a;
         }
+        if (!EMIT) { tpi_xput(nup, k * nx, nx, nbu); tpi_xput(ndn, k * nx, nx, nbd); }
     }
     mumax = mnew;
     return ok;
@@ -513,12 +517,12 @@ BMPC_HD bool tpi_ric_forward(const TpiRicParams<S>& P, TpiAcc W, const double* x
 // the accepted solve, ready for the emit pass), 0 otherwise
 template <class S>
 BMPC_HD int tpi_polish_riccati(const TpiRicParams<S>& P, TpiAcc W, const double* x0, const double* um1, const double* xref,
-                               TpiMask& up, TpiMask& dn, int max_steps) {
+                               TpiSets& up, TpiSets& dn, int max_steps) {
     double mumax = 0.0;
 #pragma unroll 1
     for (int step = 0; step < max_steps; step++) {
         tpi_ric_backward<S>(P, W, xref, up, dn);
-        TpiMask nup, ndn;
+        TpiSets nup, ndn;
         const bool ok = tpi_ric_forward<S, false>(P, W, x0, um1, up, dn, nup, ndn, mumax,
                                                   [](int, double, double, double) {}, [](int, double) {});
         if (ok) return step + 1;

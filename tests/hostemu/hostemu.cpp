@@ -87,12 +87,11 @@ static int emu_tpi_run(const double* sys, const double* x0, const double* um1, c
     tpi_admm<S>(*PA, V, x0, um1, xref, x, first_iters, cold != 0);
     for (int i = 0; i < S::MT; i++) v[i + S::nx] = col[i];
     for (int i = 0; i < S::nx; i++) v[i] = x0[i];
-    TpiMask up, dn;
-    tpi_for_rows<S>(PR->c, um1, [&](int i, double lo, double hi, double) {
-        up.set(i, col[i] > hi + 1e-9 * (1.0 + fabs(hi))); dn.set(i, col[i] < lo - 1e-9 * (1.0 + fabs(lo))); });
+    TpiSets up, dn;
+    tpi_sets_from_v<S>(PR->c, um1, V, up, dn);
     int ps = tpi_polish_riccati<S>(*PR, V, x0, um1, xref, up, dn, pdas_steps);
     if (ps > 0) {
-        TpiMask t1, t2; double mm = 0.0;
+        TpiSets t1, t2; double mm = 0.0;
         tpi_ric_forward<S, true>(*PR, V, x0, um1, up, dn, t1, t2, mm,
             [&](int i, double zi, double mu, double irho) { v[i + S::nx] = zi + mu * irho; },
             [&](int j, double u) { Uout[j] = u; x[j] = u; });
