@@ -374,6 +374,47 @@ __global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmm
     }
 }
 
+// one instance of the TPI polish (the column W holds v on entry); returns true when KKT-verified, in which case
+// v* is staged in the column (slots, see below) and U / u0 / status are written
+template <class S>
+__device__ __forceinline__ bool tpi_polish_thread(const TpiRicParams<S>& P, BmpcInst& I, int inst, TpiAcc W, int max_steps,
+                                                  int32_t* next_list, int32_t* next_count, double* u0_out) {
+    double x0[S::nx], um1[S::nu], xref[S::nx];
+#pragma unroll
+    for (int q = 0; q < S::nx; q++) { x0[q] = I.x0[(size_t)inst * S::nx + q]; xref[q] = I.xref[(size_t)inst * S::nx + q]; }
+#pragma unroll
+    for (int q = 0; q < S::nu; q++) um1[q] = I.um1[(size_t)inst * S::nu + q];
+    const TpiCommon<S>& c = P.c;
+    TpiSets up, dn;
+    tpi_sets_from_v<S>(c, um1, W, up, dn);
+    // from here on the column is this thread's private workspace (Riccati gains): no cross-lane traffic
+    const int ps = tpi_polish_riccati<S>(P, W, x0, um1, xref, up, dn, max_steps);
+    if (ps > 0) {
+        // emit pass: solution + the exact ADMM fixed point v* = z* + y*/rho (warm start of the next step).  Stage k
+        // produces exactly nx + 2 rows (x_{k+1}, u_k, delta-u row k) = the nx + 2 gain slots it has just consumed, so v*
+        // is staged IN PLACE and leaves through the coalesced transpose below.
+        constexpr int nz1 = S::nx + 2;
+        double* udst = I.Us + (size_t)inst * S::NU;
+        double* xdst = I.xw + (size_t)inst * S::NU;
+        TpiSets t1, t2; double mm = 0.0;
+        tpi_ric_forward<S, true>(P, W, x0, um1, up, dn, t1, t2, mm,
+            [&](int i, double zi, double mu, double irho) {
+                int slot;
+                if (i < S::NS) slot = (i / S::nx) * nz1 + (i % S::nx);
+                else if (i < S::NS + S::NU) slot = (i - S::NS) * nz1 + S::nx;
+                else { const int rr = i - S::NS - S::NU; slot = rr < S::Np ? rr * nz1 + S::nx + 1 : S::Np * nz1; }
+                W(slot) = zi + mu * irho;
+            },
+            [&](int j, double u) { udst[j] = u; xdst[j] = u; if (j == 0) u0_out[inst] = u; });
+        I.status[inst] = BMPC_SOLVED; I.psteps[inst] += ps;
+        atomicAdd(next_count + 1, ps);
+    } else {
+        I.psteps[inst] += max_steps; atomicAdd(next_count + 1, max_steps);
+        next_list[atomicAdd(next_count, 1)] = inst;
+    }
+    return ps > 0;
+}
+
 template <class S>
 __global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiRicParams<S> P, BmpcInst I, const int32_t* __restrict__ list, int B, int max_steps,
                                                    int32_t* next_list, int32_t* next_count, double* u0_out) {
@@ -386,33 +427,39 @@ __global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiRi
         if (lane < nvalid) { const double* src = I.vw + (size_t)inst * S::mc + S::nx; for (int i = 0; i < S::MT; i++) W(i) = src[i]; }
     } else { tpi_load_v<S>(I, idx0, nvalid, smem, 0); }
     __syncwarp();
-    if (lane >= nvalid) return;
-    double x0[S::nx], um1[S::nu], xref[S::nx];
-#pragma unroll
-    for (int q = 0; q < S::nx; q++) { x0[q] = I.x0[(size_t)inst * S::nx + q]; xref[q] = I.xref[(size_t)inst * S::nx + q]; }
-#pragma unroll
-    for (int q = 0; q < S::nu; q++) um1[q] = I.um1[(size_t)inst * S::nu + q];
-    const TpiCommon<S>& c = P.c;
-    TpiSets up, dn;
-    tpi_sets_from_v<S>(c, um1, W, up, dn);
-    // from here on the column is this thread's private workspace (Riccati gains): no cross-lane traffic
-    const int ps = tpi_polish_riccati<S>(P, W, x0, um1, xref, up, dn, max_steps);
-    if (ps > 0) {
-        // emit pass: solution and the exact ADMM fixed point v* = z* + y*/rho (warm start of the next step)
-        double* vdst = I.vw + (size_t)inst * S::mc;
-        double* udst = I.Us + (size_t)inst * S::NU;
-        double* xdst = I.xw + (size_t)inst * S::NU;
-        TpiSets t1, t2; double mm = 0.0;
-        tpi_ric_forward<S, true>(P, W, x0, um1, up, dn, t1, t2, mm,
-            [&](int i, double zi, double mu, double irho) { vdst[S::nx + i] = zi + mu * irho; },
-            [&](int j, double u) { udst[j] = u; xdst[j] = u; if (j == 0) u0_out[inst] = u; });
-#pragma unroll
-        for (int q = 0; q < S::nx; q++) vdst[q] = x0[q];
-        I.status[inst] = BMPC_SOLVED; I.psteps[inst] += ps;
-        atomicAdd(next_count + 1, ps);
+    const bool ok = (lane < nvalid) && tpi_polish_thread<S>(P, I, inst, W, max_steps, next_list, next_count, u0_out);
+    const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+    __syncwarp();
+    constexpr int nz1 = S::nx + 2;
+    if (list) {
+        if (ok) {
+            double* dst = I.vw + (size_t)inst * S::mc;
+            for (int i = 0; i < S::MT; i++) {
+                int slot;
+                if (i < S::NS) slot = (i / S::nx) * nz1 + (i % S::nx);
+                else if (i < S::NS + S::NU) slot = (i - S::NS) * nz1 + S::nx;
+                else { const int rr = i - S::NS - S::NU; slot = rr < S::Np ? rr * nz1 + S::nx + 1 : S::Np * nz1; }
+                dst[S::nx + i] = W(slot);
+            }
+            for (int q = 0; q < S::nx; q++) dst[q] = I.x0[(size_t)inst * S::nx + q];
+        }
     } else {
-        I.psteps[inst] += max_steps; atomicAdd(next_count + 1, max_steps);
-        next_list[atomicAdd(next_count, 1)] = inst;
+        double* dst = I.vw + (size_t)idx0 * S::mc;
+#pragma unroll 5
+        for (int idx = lane; idx < nvalid * S::mc; idx += 32) {
+            const int t = idx / S::mc, g = idx - t * S::mc;
+            if (!((okmask >> t) & 1u)) continue;
+            double val;
+            if (g < S::nx) val = I.x0[(size_t)(idx0 + t) * S::nx + g];
+            else {
+                const int i = g - S::nx; int slot;
+                if (i < S::NS) slot = (i / S::nx) * nz1 + (i % S::nx);
+                else if (i < S::NS + S::NU) slot = (i - S::NS) * nz1 + S::nx;
+                else { const int rr = i - S::NS - S::NU; slot = rr < S::Np ? rr * nz1 + S::nx + 1 : S::Np * nz1; }
+                val = smem[slot * TPI_STR + t];
+            }
+            dst[idx] = val;
+        }
     }
 }
 
