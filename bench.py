@@ -149,9 +149,28 @@ def gpu_arm(args, rank, world, local_rank):
     stream = torch.cuda.current_stream(dev)
     L.bmpc_set_stream(h, stream.cuda_stream)
     Ad = torch.tensor(cfgp["Ad"], device=dev); Bd = torch.tensor(cfgp["Bd"], device=dev)
-    Xd = torch.tensor(X0, device=dev); Ufull = torch.zeros(Btot, 1, dtype=torch.float64, device=dev)
+    Xd = torch.tensor(X0, device=dev)
+    # K6: the gathered u* buffer.  With torch symmetric memory every rank maps every peer's buffer, and the solver
+    # epilogue stores its slice into all of them over NVLink (bmpc_bind_output_peers): no collective launch, only a
+    # cross-rank barrier.  Fallback: one in-place NCCL all-gather.
+    symm = None
+    if world > 1 and not args.nccl_gather:
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            Ufull = symm_mem.empty((Btot, 1), dtype=torch.float64, device=dev); Ufull.zero_()
+            symm = symm_mem.rendezvous(Ufull, dist.group.WORLD)
+            import ctypes as _ct
+            peers = [int(p) + s * 8 for r, p in enumerate(symm.buffer_ptrs) if r != rank]
+            arr = (_ct.c_void_p * len(peers))(*peers)
+            assert L.bmpc_bind_output_peers(h, arr, len(peers)) == 0
+        except Exception as exc:                               # pragma: no cover
+            if rank == 0:
+                print("symmetric memory unavailable, using NCCL all-gather:", exc, file=sys.stderr)
+            symm = None
+    if symm is None:
+        Ufull = torch.zeros(Btot, 1, dtype=torch.float64, device=dev)
     Uloc = Ufull[s:e]
-    L.bmpc_bind_output(h, Uloc.data_ptr())                     # solver epilogue writes u* into the all-gather slice
+    L.bmpc_bind_output(h, Uloc.data_ptr())                     # solver epilogue writes u* into this rank's slice
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step_device():
@@ -160,7 +179,10 @@ def gpu_arm(args, rank, world, local_rank):
         assert rc == 0, L.bmpc_last_error(h)
         L.bmpc_output(h, None, None, 1, 1)
         if world > 1:
-            allgather_outputs(Ufull, s, e)
+            if symm is not None:
+                symm.barrier()                                 # peers' slices have landed (stores precede the barrier in stream order)
+            else:
+                allgather_outputs(Ufull, s, e)
         st = K.stats()
         torch.matmul(Xd, Ad.T, out=Xd_next); Xd_next.addmm_(Uloc, Bd.T)
         return st
@@ -198,6 +220,7 @@ def gpu_arm(args, rank, world, local_rank):
 
     # ---- end-to-end through the public API with pinned host buffers (H2D and D2H inside the timed region)
     L.bmpc_bind_output(h, None)
+    L.bmpc_bind_output_peers(h, None, 0)
     L.bmpc_set_stream(h, None)
     Xh = K.pinned_buffer("x0"); Uh = K.pinned_buffer("uminus1")
     Xh[...] = X0; Uh[...] = 0.0
@@ -242,7 +265,7 @@ def gpu_arm(args, rank, world, local_rank):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"inverted_pendulum nx=4 nu=1 Np=20, batch={B} per GPU ({args.workload} instances), "
                                "closed loop with the linear plant, warm start (BASELINE configs[1])",
-                   "global_batch": Btot, "parallelism": f"batch-shard x{world}" + (", 1 NCCL all-gather of u*/step" if world > 1 else ""),
+                   "global_batch": Btot, "parallelism": f"batch-shard x{world}" + ((", u* gathered by peer stores fused into the solver epilogue (NVLink symmetric memory) + 1 barrier/step" if symm is not None else ", 1 NCCL all-gather of u*/step") if world > 1 else ""),
                    "l2": "flushed between timed steps (256 MiB write)", "parity": "u* within 1e-6 of the KKT-certified optimum (polish on)"},
         "e2e": {"value": Btot * args.steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": int(B * (4 + 1) * 8 * world),
                 "d2h_bytes_per_step": int(B * (8 + 4) * world), "ms_per_step": 1e3 * e2e_t / args.steps},
@@ -269,6 +292,7 @@ def main():
     ap.add_argument("--workload", default="identical", choices=["identical", "random"])
     ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-gather", action="store_true", help="use the NCCL all-gather instead of fused peer stores")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -103,6 +103,10 @@ int bmpc_get_sequences(bmpc_handle* h, double* u_seq, double* x_seq, double* eps
 /* let the polish epilogue write u0 straight into a caller-owned DEVICE buffer [B,nu]
  * (e.g. this rank's slice of an all-gather buffer); NULL restores the internal buffer. */
 int bmpc_bind_output(bmpc_handle* h, double* dev_u0);
+/* K6 fused: additionally store u0 into up to 8 PEER device buffers (each already offset to this rank's slice of the
+ * peer's gathered [B_total, nu] buffer, e.g. torch symmetric-memory pointers): the epilogue's NVLink peer stores replace
+ * the all-gather collective; the caller only needs a cross-rank barrier before reading.  n = 0 unbinds. */
+int bmpc_bind_output_peers(bmpc_handle* h, double* const* peer_u0, int n);
 int bmpc_set_stream(bmpc_handle* h, void* cuda_stream);   /* NULL = handle-owned stream */
 int bmpc_synchronize(bmpc_handle* h);
 

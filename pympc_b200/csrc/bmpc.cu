@@ -115,8 +115,17 @@ struct BmpcInst {
     int32_t* iters;       // [B]
     int32_t* psteps;      // [B]
     int32_t* lvl;         // [B] adaptive-rho ladder level (reset to the base level at every solve)
+    double* u0_peer[8];   // extra copies of the output slice in peer GPUs' buffers (NVLink peer stores), see bmpc_bind_output_peers
+    int n_peer;
     size_t sys_stride;    // 0: all instances share one system block; o.total: instance i uses block i (per-instance Ad, Bd, ...)
 };
+
+// K6: the solver epilogue stores u* into this rank's output slice and, when peers are bound, straight into every peer
+// GPU's copy of the gathered buffer over NVLink (the all-gather is fused into the kernel: no collective launch)
+__device__ __forceinline__ void bmpc_publish_u0(const BmpcInst& I, double* u0_out, size_t idx, double val) {
+    u0_out[idx] = val;
+    for (int p = 0; p < I.n_peer; p++) I.u0_peer[p][idx] = val;
+}
 
 // smem (doubles) per instance for the two kernels — keep in sync with the carve-up below
 __host__ __device__ static inline size_t admm_smem_doubles(const BmpcDims& d) { return 4 * (size_t)d.NU + d.NX + 2 * (size_t)d.mc + d.nu + 4 + 4; }
@@ -212,7 +221,7 @@ __global__ void k_polish(BmpcDims d, BmpcSysOff o, const double* __restrict__ sy
             for (int a = t.tid; a < d.NU; a += t.n) {
                 double ua = U[a];
                 I.Us[(size_t)inst * d.NU + a] = ua; I.xw[(size_t)inst * d.NU + a] = ua;
-                if (a < d.nu) u0_out[(size_t)inst * d.nu + a] = ua;
+                if (a < d.nu) bmpc_publish_u0(I, u0_out, (size_t)inst * d.nu + a, ua);
             }
             // exact ADMM fixed point of this problem = warm start of the next one: v* = z* + y*/rho
             for (int i = t.tid; i < d.mc; i += t.n) I.vw[(size_t)inst * d.mc + i] = zz[i] + murow[i] / rhov[i];
@@ -242,7 +251,7 @@ __global__ void k_finalize(BmpcDims d, BmpcSysOff o, const double* __restrict__ 
     bool conv = res[0] <= eps_abs + eps_rel * res[2] && res[1] <= eps_abs + eps_rel * res[3];
     I.status[inst] = conv ? BMPC_SOLVED_UNPOLISHED : BMPC_MAX_ITER;
     for (int a = 0; a < d.NU; a++) I.Us[(size_t)inst * d.NU + a] = I.Ua[(size_t)inst * d.NU + a];
-    for (int q = 0; q < d.nu; q++) u0_out[(size_t)inst * d.nu + q] = conv ? I.Ua[(size_t)inst * d.NU + q] : sys[o.uref + q];
+    for (int q = 0; q < d.nu; q++) bmpc_publish_u0(I, u0_out, (size_t)inst * d.nu + q, conv ? I.Ua[(size_t)inst * d.NU + q] : sys[o.uref + q]);
 }
 
 // pure-ADMM mode: list of instances not yet converged by OSQP's criterion
@@ -328,7 +337,8 @@ __device__ __forceinline__ void tpi_load_v(const BmpcInst& I, int inst0, int nva
 }
 
 template <class S>
-__global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmmParams<S> P, BmpcInst I, const int32_t* __restrict__ list, int B, int niter, int cold) {
+__global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmmParams<S> P, BmpcInst I, const int32_t* __restrict__ list, int B, int niter, int cold,
+                                                 int reset, int32_t* counts, double* um1_solved) {
     // list == nullptr: instances blockIdx*32 .. +31 (coalesced transpose of the iterate through shared memory);
     // list != nullptr: B arbitrary instances (straggler rounds): each thread moves its own rows directly.
     extern __shared__ double smem[];
@@ -350,6 +360,15 @@ __global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmm
     for (int q = 0; q < S::nu; q++) um1[q] = valid ? I.um1[(size_t)inst * S::nu + q] : 0.0;
 #pragma unroll
     for (int a = 0; a < S::NU; a++) x[a] = (valid && !cold) ? I.xw[(size_t)inst * S::NU + a] : 0.0;
+    if (reset) {
+        // first round of a solve: the per-solve bookkeeping that k_reset / two memsets would do rides here (3 launches saved)
+        if (valid) {
+            I.status[inst] = BMPC_UNSOLVED; I.iters[inst] = 0; I.psteps[inst] = 0; I.lvl[inst] = BMPC_LEV0;
+#pragma unroll
+            for (int q = 0; q < S::nu; q++) um1_solved[(size_t)inst * S::nu + q] = um1[q];
+        }
+        if (blockIdx.x == 0 && lane == 0) { counts[0] = 0; counts[1] = 0; }
+    }
     if (valid) tpi_admm<S>(P, V, x0, um1, xref, x, niter, cold != 0);
     __syncwarp();
     if (list) {
@@ -405,7 +424,7 @@ __device__ __forceinline__ bool tpi_polish_thread(const TpiRicParams<S>& P, Bmpc
                 else { const int rr = i - S::NS - S::NU; slot = rr < S::Np ? rr * nz1 + S::nx + 1 : S::Np * nz1; }
                 W(slot) = zi + mu * irho;
             },
-            [&](int j, double u) { udst[j] = u; xdst[j] = u; if (j == 0) u0_out[inst] = u; });
+            [&](int j, double u) { udst[j] = u; xdst[j] = u; if (j == 0) bmpc_publish_u0(I, u0_out, (size_t)inst, u); });
         I.status[inst] = BMPC_SOLVED; I.psteps[inst] += ps;
         atomicAdd(next_count + 1, ps);
     } else {
@@ -511,7 +530,8 @@ static std::string g_create_err;
 template <class S>
 static void launch_tpi_round(bmpc_handle* h, const int32_t* list, int count, int niter, int32_t* next_list, cudaEvent_t mid) {
     const int grid = (count + 31) / 32;
-    k_tpi_admm<S><<<grid, 32, S::AROWS * TPI_STR * 8, h->stream>>>(*(const TpiAdmmParams<S>*)h->tpi_admm_params, h->I, list, count, niter, h->cold ? 1 : 0);
+    k_tpi_admm<S><<<grid, 32, S::AROWS * TPI_STR * 8, h->stream>>>(*(const TpiAdmmParams<S>*)h->tpi_admm_params, h->I, list, count, niter, h->cold ? 1 : 0,
+                                                                   h->st.round == 0 ? 1 : 0, h->counts, h->um1_solved);
     cudaEventRecord(mid, h->stream);
     k_tpi_polish<S><<<grid, 32, S::PROWS * TPI_STR * 8, h->stream>>>(*(const TpiRicParams<S>*)h->tpi_polish_params, h->I, list, count,
                                                                      h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
@@ -692,6 +712,14 @@ int bmpc_bind_output(bmpc_handle* h, double* dev_u0) {
     return BMPC_OK;
 }
 
+int bmpc_bind_output_peers(bmpc_handle* h, double* const* peer_u0, int n) {
+    if (!h || n < 0 || n > 8 || (n > 0 && !peer_u0)) return BMPC_ERR_ARG;
+    if (h->pending) { cudaSetDevice(h->cfg.device); int rc = finish_solve(h); if (rc) return rc; }
+    h->I.n_peer = n;
+    for (int p = 0; p < n; p++) h->I.u0_peer[p] = peer_u0[p];
+    return BMPC_OK;
+}
+
 int bmpc_get_dims(const bmpc_handle* h, int32_t* dims) {
     if (!h || !dims) return BMPC_ERR_ARG;
     dims[0] = h->d.nx; dims[1] = h->d.nu; dims[2] = h->d.Np; dims[3] = h->d.Nc; dims[4] = h->d.NX; dims[5] = h->d.NU;
@@ -814,11 +842,19 @@ static void launch_polish(bmpc_handle* h, const int32_t* list, int count, int32_
 static int enqueue_round(bmpc_handle* h) {
     auto& st = h->st;
     if (st.chunk > h->cfg.max_iter - st.total) st.chunk = h->cfg.max_iter - st.total;
-    BMPC_CUDA(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 2, h->stream));
-    BMPC_CUDA(cudaEventRecord(h->ev[0], h->stream));
     // fast path (thread-per-instance kernels, throughput-optimised) for the first round; the few stragglers are
     // latency-bound and go to the CTA-per-instance team kernels
     const bool tpi = st.round == 0 && h->tpi_kind && h->cfg.polish && h->xref_mode == 0;
+    if (!tpi) {
+        if (st.round == 0) {
+            const int B = h->cfg.batch;
+            k_reset<<<(B + 255) / 256, 256, 0, h->stream>>>(h->I, B);
+            h->stats.launches++;
+            BMPC_CUDA(cudaMemcpyAsync(h->um1_solved, h->um1, sizeof(double) * (size_t)B * h->d.nu, cudaMemcpyDeviceToDevice, h->stream));
+        }
+        BMPC_CUDA(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 2, h->stream));
+    }
+    BMPC_CUDA(cudaEventRecord(h->ev[0], h->stream));
     if (tpi) {
         if (h->tpi_kind == 1) launch_tpi_round<TpiPend>(h, st.list, st.count, st.chunk, st.nxt, h->ev[1]);
         else launch_tpi_round<TpiPm>(h, st.list, st.count, st.chunk, st.nxt, h->ev[1]);
@@ -879,9 +915,6 @@ int bmpc_solve(bmpc_handle* h) {
     if (h->pending) { int rc = finish_solve(h); if (rc) return rc; }
     const int B = h->cfg.batch;
     memset(&h->stats, 0, sizeof(h->stats));
-    k_reset<<<(B + 255) / 256, 256, 0, h->stream>>>(h->I, B);
-    h->stats.launches++;
-    BMPC_CUDA(cudaMemcpyAsync(h->um1_solved, h->um1, sizeof(double) * (size_t)B * h->d.nu, cudaMemcpyDeviceToDevice, h->stream));
     auto& st = h->st;
     st.list = nullptr; st.count = B; st.cur = h->listA; st.nxt = h->listB;
     st.total = 0; st.round = 0; st.need_prep = true;
