@@ -291,6 +291,7 @@ class MPCController:
                     np.ascontiguousarray(np.broadcast_to(self.uref, (B, nu)))]
         self._check(L.bmpc_setup(self._h, *[ptr(a) for a in args]))
         self._Qx_d, self._QxN_d, self._Qu_d, self._QDu_d = Qx, QxN, Qu, QDu
+        self._qp_static = None
         self._um1_for_J = self.uminus1_rh
         self._push(self.x0_rh, self.uminus1_rh, self.xref)
         self._J_dirty = True
@@ -436,6 +437,31 @@ class MPCController:
         if self.JDU_ON:
             J += 0.5 * np.einsum('bi,ij,bj->b', um1, self._QDu_d, um1)
         self._J_CNST = J if self.batch is not None else float(J[0])
+
+    # ---- reference-form QP attributes (mpc.py:597-606), built lazily on the host for instance 0 ----
+    def _qp_view(self):
+        from . import qp_view
+        first = lambda a, nd: np.asarray(a, dtype=float)[0] if np.ndim(a) == nd + 1 else np.asarray(a, dtype=float)
+        if getattr(self, "_qp_static", None) is None:
+            z = np.zeros
+            Qx = self._Qx_d; QxN = self._QxN_d; Qu = self._Qu_d; QDu = self._QDu_d
+            self._qp_static = qp_view.assemble(np.asarray(self.Ad, float), np.asarray(self.Bd, float), self.Np, self.Nc, Qx, QxN, Qu, QDu,
+                                               self.xmin, self.xmax, self.umin, self.umax, self.Dumin, self.Dumax,
+                                               float(self.eps_feas), self.uref, bool(self.SOFT_ON))
+        P, A, n, w = self._qp_static
+        x0 = first(self.x0_rh, 1); um1 = first(self.uminus1_rh, 1)
+        xr = np.asarray(self.xref, dtype=float)
+        if self.batch is not None and (xr.ndim == 3 or (xr.ndim == 2 and xr.shape == (self._B, self.nx) and xr.shape[0] != self.Np + 1)):
+            xr = xr[0]
+        q, l, u = qp_view.vectors(self.Np, self.Nc, self.nx, self.nu, self._Qx_d, self._QxN_d, self._Qu_d, self._QDu_d, w, self.xmin,
+                                  self.xmax, self.umin, self.umax, self.Dumin, self.Dumax, self.uref, x0, um1, xr, bool(self.SOFT_ON))
+        return P, q, A, l, u
+
+    P = property(lambda self: self._qp_view()[0])
+    q = property(lambda self: self._qp_view()[1])
+    A = property(lambda self: self._qp_view()[2])
+    l = property(lambda self: self._qp_view()[3])
+    u = property(lambda self: self._qp_view()[4])
 
     def stats(self):
         """Counters of the last solve (ADMM iterations, rounds, device time of the kernels)."""

@@ -334,3 +334,18 @@ def test_full_size_fast_path_agrees_with_team_path(MPC):
         assert np.max(np.abs(ia["u_seq"][ok] - ib["u_seq"][ok])) < 1e-7, t
         U = Ua; X = X @ cfg["Ad"].T + U @ cfg["Bd"].T
     Ka.close(); Kb.close()
+
+
+def test_reference_form_qp_attributes(MPC):
+    """K.P, K.q, K.A, K.l, K.u (mpc.py:597-606) are available after setup()/update() like on the reference object
+    (host-side view, instance 0) and equal the oracle / reference assembly."""
+    from oracle.qp_assembly import QPData
+    cfg = pendulum(); K = MPC(**cfg); K.setup()
+    Q = QPData(**cfg)
+    fin = lambda v: np.where(np.isinf(v), 0, v)
+    assert np.array_equal(K.P.toarray(), Q.P) and np.array_equal(K.A.toarray(), Q.A)
+    assert np.allclose(K.q, Q.q, atol=0, rtol=0) and np.array_equal(fin(K.l), fin(Q.l)) and np.array_equal(fin(K.u), fin(Q.u))
+    x = np.array([0.1, -0.2, 0.05, 0.3]); um1 = np.array([1.5])
+    K.update(x, um1); Q.update(x, um1)
+    assert np.allclose(K.q, Q.q, atol=1e-15) and np.array_equal(fin(K.l), fin(Q.l)) and np.array_equal(fin(K.u), fin(Q.u))
+    K.close()
