@@ -4,7 +4,9 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "bmpc.cu")
-DEPS = [SRC, os.path.join(_HERE, "csrc", "bmpc_core.cuh"), os.path.join(_HERE, "..", "include", "bmpc.h")]
+SHAPES = os.path.join(_HERE, "csrc", "tpi_shapes.inc")
+DEPS = [SRC, os.path.join(_HERE, "csrc", "bmpc_core.cuh"), os.path.join(_HERE, "csrc", "bmpc_tpi.cuh"), SHAPES,
+        os.path.join(_HERE, "..", "include", "bmpc.h")]
 LIB = os.path.join(_HERE, "libbmpc.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -25,5 +27,20 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def add_shape(nx, nu, Np):
+    """Register one more compile-time fast-path shape (nu must be 1, Nc = Np) and rebuild."""
+    if nu != 1 or Np * nx > 128 or Np >= 32:
+        raise ValueError("fast-path shapes need nu == 1, Np*nx <= 128, Np < 32")
+    line = f"BMPC_TPI_SHAPE({nx}, {nu}, {Np}, {Np})"
+    txt = open(SHAPES).read()
+    if line not in txt:
+        open(SHAPES, "a").write(line + "\n")
+    return build(force=True)
+
+
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+    if len(sys.argv) == 3 and sys.argv[1] == "--add-shape":
+        print(add_shape(*[int(v) for v in sys.argv[2].split(",")]))
+    else:
+        print(build(force=True, verbose=True))

@@ -482,8 +482,15 @@ __global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiRi
     }
 }
 
-using TpiPend = TpiShape<4, 1, 20, 20>;
-using TpiPm = TpiShape<2, 1, 20, 20>;
+// Compiled fast-path shapes (nx, nu, Np, Nc) with nu == 1 and Nc == Np: one line per shape in csrc/tpi_shapes.inc
+// (`python -m pympc_b200.build --add-shape nx,1,Np` appends one and rebuilds).
+struct TpiEntry {
+    int nx, nu, Np, Nc;
+    size_t admm_bytes, ric_bytes;
+    void (*fill)(const double* hs, const BmpcSysOff& o, void* pa, void* pp);
+    int (*configure)();
+    void (*launch)(struct bmpc_handle* h, const int32_t* list, int count, int niter, int32_t* next_list, cudaEvent_t mid);
+};
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -511,7 +518,7 @@ struct bmpc_handle {
     int fb_team = 0, fb_rmax = 0; size_t fb_smem_admm = 0, fb_smem_polish = 0;
     struct { const int32_t* list; int count; int32_t *cur, *nxt; int total, chunk, round; bool need_prep; } st = {};
     bool pending = false;              // a round is in flight and has not been retired by the host yet
-    int tpi_kind = 0;                  // 0 none, 1 pendulum shape (4,1,20,20), 2 point-mass shape (2,1,20,20)
+    int tpi_kind = 0;                  // 0 none, else 1 + index into g_tpi_table (compiled fast-path shapes)
     void *tpi_admm_params = nullptr, *tpi_polish_params = nullptr;   // host copies of the parameter blocks
     int tpi_pdas_steps = 8;
 };
@@ -537,6 +544,27 @@ static void launch_tpi_round(bmpc_handle* h, const int32_t* list, int count, int
                                                                      h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
     h->stats.launches += 2;
 }
+
+template <class S>
+static void tpi_fill_entry(const double* hs, const BmpcSysOff& o, void* pa, void* pp) {
+    tpi_fill_admm<S>(hs, o, *(TpiAdmmParams<S>*)pa); tpi_fill_riccati<S>(hs, o, *(TpiRicParams<S>*)pp);
+}
+template <class S>
+static int tpi_configure_entry() {
+    if (cudaFuncSetAttribute(k_tpi_admm<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::AROWS * TPI_STR * 8)) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(k_tpi_polish<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::PROWS * TPI_STR * 8)) != cudaSuccess) return 1;
+    return 0;
+}
+#define BMPC_TPI_SHAPE(NX_, NU_, NP_, NC_)                                                                                   \
+    {NX_, NU_, NP_, NC_, sizeof(TpiAdmmParams<TpiShape<NX_, NU_, NP_, NC_>>), sizeof(TpiRicParams<TpiShape<NX_, NU_, NP_, NC_>>), \
+     tpi_fill_entry<TpiShape<NX_, NU_, NP_, NC_>>, tpi_configure_entry<TpiShape<NX_, NU_, NP_, NC_>>,                         \
+     launch_tpi_round<TpiShape<NX_, NU_, NP_, NC_>>},
+static const TpiEntry g_tpi_table[] = {
+#include "tpi_shapes.inc"
+};
+#undef BMPC_TPI_SHAPE
+static const int g_tpi_count = (int)(sizeof(g_tpi_table) / sizeof(g_tpi_table[0]));
+
 
 extern "C" {
 
@@ -761,27 +789,18 @@ int bmpc_setup(bmpc_handle* h, const double* Ad, const double* Bd, const double*
     h->tpi_kind = 0;
     // (the Riccati polish treats state rows as the soft penalty they are by default; hard state rows -> team kernels)
     if (h->cfg.fast_path && h->team == 32 && h->cfg.soft_on && ns == 1) {
-        if (d.nx == 4 && d.nu == 1 && d.Np == 20 && d.Nc == 20) h->tpi_kind = 1;
-        else if (d.nx == 2 && d.nu == 1 && d.Np == 20 && d.Nc == 20) h->tpi_kind = 2;
+        for (int k = 0; k < g_tpi_count; k++)
+            if (g_tpi_table[k].nx == d.nx && g_tpi_table[k].nu == d.nu && g_tpi_table[k].Np == d.Np && g_tpi_table[k].Nc == d.Nc) { h->tpi_kind = k + 1; break; }
     }
     if (h->tpi_kind) {
+        const TpiEntry& te = g_tpi_table[h->tpi_kind - 1];
         std::vector<double> hs(o.total);
         BMPC_CUDA(cudaMemcpyAsync(hs.data(), h->sys, sizeof(double) * o.total, cudaMemcpyDeviceToHost, h->stream));
         BMPC_CUDA(cudaStreamSynchronize(h->stream));
         free(h->tpi_admm_params); free(h->tpi_polish_params);
-        if (h->tpi_kind == 1) {
-            auto* pa = (TpiAdmmParams<TpiPend>*)malloc(sizeof(TpiAdmmParams<TpiPend>)); tpi_fill_admm<TpiPend>(hs.data(), o, *pa);
-            auto* pp = (TpiRicParams<TpiPend>*)malloc(sizeof(TpiRicParams<TpiPend>)); tpi_fill_riccati<TpiPend>(hs.data(), o, *pp);
-            h->tpi_admm_params = pa; h->tpi_polish_params = pp;
-            BMPC_CUDA(cudaFuncSetAttribute(k_tpi_admm<TpiPend>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TpiPend::AROWS * TPI_STR * 8)));
-            BMPC_CUDA(cudaFuncSetAttribute(k_tpi_polish<TpiPend>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TpiPend::PROWS * TPI_STR * 8)));
-        } else {
-            auto* pa = (TpiAdmmParams<TpiPm>*)malloc(sizeof(TpiAdmmParams<TpiPm>)); tpi_fill_admm<TpiPm>(hs.data(), o, *pa);
-            auto* pp = (TpiRicParams<TpiPm>*)malloc(sizeof(TpiRicParams<TpiPm>)); tpi_fill_riccati<TpiPm>(hs.data(), o, *pp);
-            h->tpi_admm_params = pa; h->tpi_polish_params = pp;
-            BMPC_CUDA(cudaFuncSetAttribute(k_tpi_admm<TpiPm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TpiPm::AROWS * TPI_STR * 8)));
-            BMPC_CUDA(cudaFuncSetAttribute(k_tpi_polish<TpiPm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TpiPm::PROWS * TPI_STR * 8)));
-        }
+        h->tpi_admm_params = malloc(te.admm_bytes); h->tpi_polish_params = malloc(te.ric_bytes);
+        te.fill(hs.data(), o, h->tpi_admm_params, h->tpi_polish_params);
+        if (te.configure()) { h->err = "fast path: shared-memory configuration failed"; return BMPC_ERR_CUDA; }
     }
     // uminus1 default = uref for every instance (mpc.py:141); caller overrides through bmpc_update
     h->is_setup = true; h->cold = true; h->solved = false; h->pending = false;
@@ -856,8 +875,7 @@ static int enqueue_round(bmpc_handle* h) {
     }
     BMPC_CUDA(cudaEventRecord(h->ev[0], h->stream));
     if (tpi) {
-        if (h->tpi_kind == 1) launch_tpi_round<TpiPend>(h, st.list, st.count, st.chunk, st.nxt, h->ev[1]);
-        else launch_tpi_round<TpiPm>(h, st.list, st.count, st.chunk, st.nxt, h->ev[1]);
+        g_tpi_table[h->tpi_kind - 1].launch(h, st.list, st.count, st.chunk, st.nxt, h->ev[1]);
     } else {
         launch_admm(h, st.list, st.count, st.chunk, st.need_prep ? 1 : 0);
         st.need_prep = false;

@@ -349,3 +349,20 @@ def test_reference_form_qp_attributes(MPC):
     K.update(x, um1); Q.update(x, um1)
     assert np.allclose(K.q, Q.q, atol=1e-15) and np.array_equal(fin(K.l), fin(Q.l)) and np.array_equal(fin(K.u), fin(Q.u))
     K.close()
+
+
+def test_other_compiled_fast_path_shape(MPC):
+    """a non-default compile-time fast-path shape (4,1,10,10) from csrc/tpi_shapes.inc: fast path == team path == oracle"""
+    cfg = pendulum(); cfg["Np"] = 10
+    ref, Q = _oracle_u(cfg)
+    traj = {}
+    for fast in (1, 0):
+        K = MPC(**cfg, fast_path=fast); K.setup(); u, info = K.output(return_u_seq=True)
+        assert np.max(np.abs(info["u_seq"].ravel() - ref)) < TOL, fast
+        x = np.array(cfg["x0"], float); us = []
+        for t in range(8):
+            x = cfg["Ad"] @ x + cfg["Bd"] @ u
+            K.update(x, u); u = K.output(); us.append(u.copy())
+        traj[fast] = np.array(us)
+        K.close()
+    assert np.max(np.abs(traj[1] - traj[0])) < TOL
