@@ -406,25 +406,27 @@ __device__ __forceinline__ bool tpi_polish_thread(const TpiRicParams<S>& P, Bmpc
     const TpiCommon<S>& c = P.c;
     TpiSets up, dn;
     tpi_sets_from_v<S>(c, um1, W, up, dn);
-    // from here on the column is this thread's private workspace (Riccati gains): no cross-lane traffic
-    const int ps = tpi_polish_riccati<S>(P, W, x0, um1, xref, up, dn, max_steps);
+    // from here on the column is this thread's private workspace (Riccati gains): no cross-lane traffic.
+    // Every forward sweep of the polish both verifies and emits: stage k produces exactly nx + 2 rows of the exact ADMM
+    // fixed point v* = z* + y*/rho (x_{k+1}, u_k, delta-u row k) = the nx + 2 gain slots it has just consumed, so v* is
+    // staged IN PLACE and leaves through the coalesced transpose of the caller; U goes to I.Us (an output-only array).
+    constexpr int nz1 = S::nx + 2;
+    double* udst = I.Us + (size_t)inst * S::NU;
+    double u_first = 0.0;
+    const int ps = tpi_polish_riccati<S>(P, W, x0, um1, xref, up, dn, max_steps,
+        [&](int i, double zi, double mu, double irho) {
+            int slot;
+            if (i < S::NS) slot = (i / S::nx) * nz1 + (i % S::nx);
+            else if (i < S::NS + S::NU) slot = (i - S::NS) * nz1 + S::nx;
+            else { const int rr = i - S::NS - S::NU; slot = rr < S::Np ? rr * nz1 + S::nx + 1 : S::Np * nz1; }
+            W(slot) = zi + mu * irho;
+        },
+        [&](int j, double u) { udst[j] = u; if (j == 0) u_first = u; });
     if (ps > 0) {
-        // emit pass: solution + the exact ADMM fixed point v* = z* + y*/rho (warm start of the next step).  Stage k
-        // produces exactly nx + 2 rows (x_{k+1}, u_k, delta-u row k) = the nx + 2 gain slots it has just consumed, so v*
-        // is staged IN PLACE and leaves through the coalesced transpose below.
-        constexpr int nz1 = S::nx + 2;
-        double* udst = I.Us + (size_t)inst * S::NU;
         double* xdst = I.xw + (size_t)inst * S::NU;
-        TpiSets t1, t2; double mm = 0.0;
-        tpi_ric_forward<S, true>(P, W, x0, um1, up, dn, t1, t2, mm,
-            [&](int i, double zi, double mu, double irho) {
-                int slot;
-                if (i < S::NS) slot = (i / S::nx) * nz1 + (i % S::nx);
-                else if (i < S::NS + S::NU) slot = (i - S::NS) * nz1 + S::nx;
-                else { const int rr = i - S::NS - S::NU; slot = rr < S::Np ? rr * nz1 + S::nx + 1 : S::Np * nz1; }
-                W(slot) = zi + mu * irho;
-            },
-            [&](int j, double u) { udst[j] = u; xdst[j] = u; if (j == 0) bmpc_publish_u0(I, u0_out, (size_t)inst, u); });
+#pragma unroll 4
+        for (int j = 0; j < S::NU; j++) xdst[j] = udst[j];      // warm start x = U* (xw must stay the ADMM x on failure)
+        bmpc_publish_u0(I, u0_out, (size_t)inst, u_first);
         I.status[inst] = BMPC_SOLVED; I.psteps[inst] += ps;
         atomicAdd(next_count + 1, ps);
     } else {

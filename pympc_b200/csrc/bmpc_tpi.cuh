@@ -435,13 +435,15 @@ BMPC_HD void tpi_ric_backward(const TpiRicParams<S>& P, TpiAcc W, const double* 
     }
 }
 
-// Forward sweep.  EMIT == false: KKT verification, returns ok and the next working set (nup, ndn), updates mumax.
-// EMIT == true : calls out(i, zi, mu_i, 1/rho_i) for every TPI row and outu(j, u_j) for every input.
-template <class S, bool EMIT, class FR, class FU>
+// Forward sweep.  MODE 0: KKT verification only: returns ok and the next working set (nup, ndn), updates mumax.
+// MODE 1: emit only: out(i, zi, mu_i, 1/rho_i) for every TPI row and outu(j, u_j) for every input.
+// MODE 2: both in one pass (the emitted values are meaningful only if the pass returns ok).
+template <class S, int MODE, class FR, class FU>
 BMPC_HD bool tpi_ric_forward(const TpiRicParams<S>& P, TpiAcc W, const double* x0, const double* um1, const TpiSets& up,
                              const TpiSets& dn, TpiSets& nup, TpiSets& ndn, double& mumax, FR out, FU outu) {
     constexpr int nx = S::nx, N = S::Np, nz = nx + 1, NS = S::NS, NU = S::NU;
     const TpiCommon<S>& c = P.c;
+    constexpr bool EMIT = (MODE >= 1), VERIFY = (MODE != 1);
     const double mutol = 1e-9 * (1.0 + mumax);
     double mnew = 0.0;
     bool ok = true;
@@ -450,7 +452,8 @@ BMPC_HD bool tpi_ric_forward(const TpiRicParams<S>& P, TpiAcc W, const double* x
     for (int a = 0; a < nx; a++) x[a] = x0[a];
     // hard row: KKT check of one row, returns its bits of the next working set (bit0 = up, bit1 = dn)
     auto hard_row = [&](int i, bool su, bool sd, double zi, double lo, double hi, double mu, double irho) -> unsigned {
-        if (EMIT) { out(i, zi, mu, irho); return 0u; }
+        if (EMIT) out(i, zi, mu, irho);
+        if (!VERIFY) return 0u;
         const bool vu = zi > hi + 1e-9 * (1.0 + fabs(hi)), vd = zi < lo - 1e-9 * (1.0 + fabs(lo));
         if (vu || vd || (su && mu < -mutol) || (sd && mu > mutol)) ok = false;
         const bool nu_ = vu || (!vd && su && mu > 0.0);
@@ -497,7 +500,8 @@ BMPC_HD bool tpi_ric_forward(const TpiRicParams<S>& P, TpiAcc W, const double* x
             x[a] = xn[a];
             const double zi = xn[a], lo = c.xmin[a], hi = c.xmax[a];
             const bool su = (bu >> a) & 1u, sd = (bd >> a) & 1u;
-            if (EMIT) { out(k * nx + a, zi, su ? P.rho_e * (zi - hi) : (sd ? P.rho_e * (zi - lo) : 0.0), c.irhox[a]); continue; }
+            if (EMIT) out(k * nx + a, zi, su ? P.rho_e * (zi - hi) : (sd ? P.rho_e * (zi - lo) : 0.0), c.irhox[a]);
+            if (!VERIFY) continue;
             const bool nu_ = zi > hi + 1e-11 * (1.0 + fabs(hi)), nd_ = (!nu_) && zi < lo - 1e-11 * (1.0 + fabs(lo));
             if (nu_ != su || nd_ != sd) {
                 const bool hi_side = (su || nu_) && !(sd || nd_), lo_side = (sd || nd_) && !(su || nu_);
@@ -507,24 +511,24 @@ BMPC_HD bool tpi_ric_forward(const TpiRicParams<S>& P, TpiAcc W, const double* x
             }
             nbu |= (nu_ ? 1u : 0u) << a; nbd |= (nd_ ? 1u : 0u) << a;
         }
-        if (!EMIT) { tpi_xput(nup, k * nx, nx, nbu); tpi_xput(ndn, k * nx, nx, nbd); }
+        if (VERIFY) { tpi_xput(nup, k * nx, nx, nbu); tpi_xput(ndn, k * nx, nx, nbd); }
     }
     mumax = mnew;
     return ok;
 }
 
-// returns steps used (>0) when KKT-verified (then `up`/`dn` hold the verified set and the gains in W are those of
-// the accepted solve, ready for the emit pass), 0 otherwise
-template <class S>
+// returns steps used (>0) when KKT-verified, 0 otherwise.  Every forward sweep verifies AND emits through out / outu (row
+// values v* = z* + y*/rho, inputs u_j): the values of the accepted (last) sweep are the solution, earlier ones are
+// overwritten, so no separate emit pass is needed.
+template <class S, class FR, class FU>
 BMPC_HD int tpi_polish_riccati(const TpiRicParams<S>& P, TpiAcc W, const double* x0, const double* um1, const double* xref,
-                               TpiSets& up, TpiSets& dn, int max_steps) {
+                               TpiSets& up, TpiSets& dn, int max_steps, FR out, FU outu) {
     double mumax = 0.0;
 #pragma unroll 1
     for (int step = 0; step < max_steps; step++) {
         tpi_ric_backward<S>(P, W, xref, up, dn);
         TpiSets nup, ndn;
-        const bool ok = tpi_ric_forward<S, false>(P, W, x0, um1, up, dn, nup, ndn, mumax,
-                                                  [](int, double, double, double) {}, [](int, double) {});
+        const bool ok = tpi_ric_forward<S, 2>(P, W, x0, um1, up, dn, nup, ndn, mumax, out, outu);
         if (ok) return step + 1;
         up = nup; dn = ndn;
     }

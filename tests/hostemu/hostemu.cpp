@@ -89,12 +89,14 @@ static int emu_tpi_run(const double* sys, const double* x0, const double* um1, c
     for (int i = 0; i < S::nx; i++) v[i] = x0[i];
     TpiSets up, dn;
     tpi_sets_from_v<S>(PR->c, um1, V, up, dn);
-    int ps = tpi_polish_riccati<S>(*PR, V, x0, um1, xref, up, dn, pdas_steps);
+    // the polish emits on every forward sweep; keep the values of the accepted one
+    double vstar[S::MT], Ustar[S::NU];
+    int ps = tpi_polish_riccati<S>(*PR, V, x0, um1, xref, up, dn, pdas_steps,
+        [&](int i, double zi, double mu, double irho) { vstar[i] = zi + mu * irho; },
+        [&](int j, double u) { Ustar[j] = u; });
     if (ps > 0) {
-        TpiSets t1, t2; double mm = 0.0;
-        tpi_ric_forward<S, true>(*PR, V, x0, um1, up, dn, t1, t2, mm,
-            [&](int i, double zi, double mu, double irho) { v[i + S::nx] = zi + mu * irho; },
-            [&](int j, double u) { Uout[j] = u; x[j] = u; });
+        for (int i = 0; i < S::MT; i++) v[i + S::nx] = vstar[i];
+        for (int j = 0; j < S::NU; j++) { Uout[j] = Ustar[j]; x[j] = Ustar[j]; }
     }
     free(col); delete PA; delete PR;
     return ps;
