@@ -143,7 +143,6 @@ def gpu_arm(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from pympc_b200 import MPCController, build
-    from pympc_b200._lib import ptr
     from pympc_b200.dist import shard_range, allgather_outputs
     if rank == 0:
         build.build()

@@ -169,7 +169,7 @@ BMPC_HD double bmpc_ATcol_dot(const BmpcDims& d, const double* Bcal, const doubl
 // In-place Gauss-Jordan inversion of an SPD matrix (no pivoting needed for SPD); returns false if a
 // pivot is not positive.  Row/column k are staged in colbuf/rowbuf so the rank-1 update is race-free.
 template <class Team>
-BMPC_HD bool bmpc_spd_inverse2(Team& t, double* A, int n, double* colbuf, double* rowbuf) {
+BMPC_HD bool bmpc_spd_inverse(Team& t, double* A, int n, double* colbuf, double* rowbuf) {
     bool ok = true;
     for (int k = 0; k < n; k++) {
         double p = A[k * n + k];
@@ -299,8 +299,8 @@ BMPC_HD void bmpc_condense(Team& t, const BmpcDims& d, const BmpcSysOff& o, doub
     }
     t.sync();
     // inverses (scratch: g0 / GrefFull are not yet in use)
-    bool okH = bmpc_spd_inverse2(t, Hinv, NU, GrefFull, GrefFull + NU);
-    bool okK = bmpc_spd_inverse2(t, Kinv, NU, GrefFull, GrefFull + NU);
+    bool okH = bmpc_spd_inverse(t, Hinv, NU, GrefFull, GrefFull + NU);
+    bool okK = bmpc_spd_inverse(t, Kinv, NU, GrefFull, GrefFull + NU);
     if (t.tid == 0 && !(okH && okK)) scal[BMPC_S_ERR] = okH ? 2.0 : 1.0;
     t.sync();
     // ladder of K^-1 for the adaptive rho: K_l = H + sigma I + f_l (K - H - sigma I)
@@ -314,7 +314,7 @@ BMPC_HD void bmpc_condense(Team& t, const BmpcDims& d, const BmpcSysOff& o, doub
                 Kl[idx] = hs + f * (K[idx] - hs);
             }
             t.sync();
-            bmpc_spd_inverse2(t, Kl, NU, GrefFull, GrefFull + NU);
+            bmpc_spd_inverse(t, Kl, NU, GrefFull, GrefFull + NU);
         }
     }
     // AHinv = A Hinv  (rows: Bcal Hinv ; Hinv ; D Hinv)
