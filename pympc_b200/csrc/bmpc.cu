@@ -17,6 +17,7 @@
 #include "../../include/bmpc.h"
 #include "bmpc_core.cuh"
 #include "bmpc_tpi.cuh"
+#include "bmpc_tile.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // teams
@@ -190,6 +191,60 @@ __global__ void k_admm(BmpcDims d, BmpcSysOff o, const double* __restrict__ sys,
     };
     if (WARP) { WarpTeam t; run(t); }
     else { BlockTeam t(sd, si); run(t); }
+}
+
+
+// K3+K4 for large shapes: one CTA per TILE of T instances (bmpc_tile.cuh).  Same contract as k_admm.
+template <int T, int NS>
+__global__ void k_admm_tile(BmpcDims d, BmpcSysOff o, const double* __restrict__ sys, BmpcInst I, const int32_t* __restrict__ list,
+                            int count, int niter, int do_prep, int cold, int xref_mode, int adapt) {
+    extern __shared__ double smem[];
+    __shared__ double sd[32];
+    __shared__ int si[32];
+    BlockTeam t(sd, si);
+    BmpcTile<T> S; S.carve(smem, d);
+    const int first = blockIdx.x * T;
+    const int nact = (count - first) < T ? (count - first) : T;       // a partial tile repeats its last instance (no write-back)
+    if (t.tid < T) {
+        const int e = t.tid < nact ? t.tid : nact - 1;
+        const int inst = list ? list[first + e] : first + e;
+        S.inst[t.tid] = inst; S.lvl[t.tid] = I.lvl[inst];
+    }
+    t.sync();
+    bmpc_tile_load_phi(t, d, sys + o.Bcal, S.phi1, S.phi2);
+    for (int idx = t.tid; idx < d.nu * T; idx += t.n) { const int e = idx / d.nu, q = idx % d.nu; S.um1[idx] = I.um1[(size_t)S.inst[e] * d.nu + q]; }
+    if (do_prep) {
+        double* x0 = S.r;                                              // staging: r is free until the first iteration
+        for (int idx = t.tid; idx < d.nx * T; idx += t.n) { const int e = idx / d.nx, c = idx % d.nx; x0[idx] = I.x0[(size_t)S.inst[e] * d.nx + c]; }
+        t.sync();
+        bmpc_tile_prep(t, d, o, sys, S, x0, I.xref, xref_mode);
+        for (int idx = t.tid; idx < d.NU * nact; idx += t.n) { const int e = idx / d.NU, a = idx % d.NU; I.g[(size_t)S.inst[e] * d.NU + a] = S.g[(size_t)a * T + e]; }
+        for (int idx = t.tid; idx < d.NX * nact; idx += t.n) { const int e = idx / d.NX, i = idx % d.NX; I.cc[(size_t)S.inst[e] * d.NX + i] = S.cc[(size_t)i * T + e]; }
+    } else {
+        for (int idx = t.tid; idx < d.NU * T; idx += t.n) { const int e = idx / d.NU, a = idx % d.NU; S.g[(size_t)a * T + e] = I.g[(size_t)S.inst[e] * d.NU + a]; }
+        for (int idx = t.tid; idx < d.NX * T; idx += t.n) { const int e = idx / d.NX, i = idx % d.NX; S.cc[(size_t)i * T + e] = I.cc[(size_t)S.inst[e] * d.NX + i]; }
+    }
+    t.sync();
+    if (cold) {
+        for (int idx = t.tid; idx < d.NU * T; idx += t.n) S.x[idx] = 0.0;
+        for (int idx = t.tid; idx < d.mc * T; idx += t.n) S.v[idx] = (idx / T < d.NX) ? S.cc[idx] : 0.0;
+    } else {
+        for (int idx = t.tid; idx < d.NU * T; idx += t.n) { const int e = idx / d.NU, a = idx % d.NU; S.x[(size_t)a * T + e] = I.xw[(size_t)S.inst[e] * d.NU + a]; }
+        for (int idx = t.tid; idx < d.mc * T; idx += t.n) { const int e = idx / d.mc, i = idx % d.mc; S.v[(size_t)i * T + e] = I.vw[(size_t)S.inst[e] * d.mc + i]; }
+    }
+    t.sync();
+    bmpc_admm_tile<T, NS>(t, d, o, sys, S, niter);
+    if (adapt) {
+        bmpc_tile_adapt(t, d, o, sys, S);
+        if (t.tid < nact && S.nlvl[t.tid] != S.lvl[t.tid]) I.lvl[S.inst[t.tid]] = S.nlvl[t.tid];
+    }
+    for (int idx = t.tid; idx < d.NU * nact; idx += t.n) {
+        const int e = idx / d.NU, a = idx % d.NU; const size_t gidx = (size_t)S.inst[e] * d.NU + a;
+        I.xw[gidx] = S.x[(size_t)a * T + e]; I.Ua[gidx] = S.xt[(size_t)a * T + e];
+    }
+    for (int idx = t.tid; idx < d.mc * nact; idx += t.n) { const int e = idx / d.mc, i = idx % d.mc; I.vw[(size_t)S.inst[e] * d.mc + i] = S.v[(size_t)i * T + e]; }
+    for (int idx = t.tid; idx < 4 * nact; idx += t.n) I.res[(size_t)S.inst[idx / 4] * 4 + idx % 4] = S.res[idx];
+    if (t.tid < nact) I.iters[S.inst[t.tid]] += niter;
 }
 
 template <bool WARP>
@@ -519,6 +574,7 @@ struct bmpc_handle {
     size_t smem_admm = 0, smem_polish = 0;
     // low-latency CTA-per-instance variant for the few stragglers of a warp-team / TPI handle
     int fb_team = 0, fb_rmax = 0; size_t fb_smem_admm = 0, fb_smem_polish = 0;
+    int tile_T = 0, tile_threads = 0;                  // > 0: the ADMM of this shape runs on tiles of T instances per CTA
     struct { const int32_t* list; int count; int32_t *cur, *nxt; int total, chunk, round; bool need_prep; } st = {};
     bool pending = false;              // a round is in flight and has not been retired by the host yet
     int tpi_kind = 0;                  // 0 none, else 1 + index into g_tpi_table (compiled fast-path shapes)
@@ -638,6 +694,20 @@ static int configure_launch(bmpc_handle* h) {
             BMPC_CUDA(cudaFuncSetAttribute(k_polish<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fb_smem_polish));
         }
     } else {
+        // large shapes with one shared system: the ADMM runs on tiles of T instances per CTA (bmpc_tile.cuh)
+        h->tile_T = 0;
+        if (h->cfg.team_threads == 0 && h->cfg.n_sys <= 1) {
+            if (bmpc_tile_smem_doubles(d, 8) * 8 <= budget) {
+                h->tile_T = 8;
+                BMPC_CUDA(cudaFuncSetAttribute(k_admm_tile<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bmpc_tile_smem_doubles(d, 8) * 8)));
+            } else if (bmpc_tile_smem_doubles(d, 4) * 8 <= budget) {
+                h->tile_T = 4;
+                BMPC_CUDA(cudaFuncSetAttribute(k_admm_tile<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bmpc_tile_smem_doubles(d, 4) * 8)));
+            }
+            int th = d.NX > 2 * d.NU ? d.NX : 2 * d.NU;
+            th = ((th + 31) / 32) * 32; if (th < 128) th = 128; if (th > 512) th = 512;
+            h->tile_threads = th;
+        }
         h->wpb = team / 32;
         h->smem_admm = admm_smem_doubles(d) * 8;
         h->smem_polish = polish_smem_doubles(d, rmax) * 8;
@@ -847,6 +917,10 @@ static void launch_admm(bmpc_handle* h, const int32_t* list, int count, int nite
     } else if (h->team == 32) {
         int grid = (count + h->wpb - 1) / h->wpb;
         k_admm<true><<<grid, h->wpb * 32, h->smem_admm, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
+    } else if (h->tile_T == 8) {
+        k_admm_tile<8, 2><<<(count + 7) / 8, h->tile_threads, bmpc_tile_smem_doubles(h->d, 8) * 8, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
+    } else if (h->tile_T == 4) {
+        k_admm_tile<4, 2><<<(count + 3) / 4, h->tile_threads, bmpc_tile_smem_doubles(h->d, 4) * 8, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
     } else {
         k_admm<false><<<count, h->team, h->smem_admm, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
     }

@@ -613,7 +613,7 @@ template <class Team>
 BMPC_HD int bmpc_polish(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, const double* um1,
                         const double* g, const double* cc, const double* v, double* W0, double* zz, double* murow,
                         int* st, double* S, double* tt, int* R, double* U0, double* U, int rmax, int max_steps) {
-    const double *Hinv = sys + o.Hinv, *AHinv = sys + o.AHinv, *M = sys + o.M;
+    const double *Hinv = sys + o.Hinv, *AHinv = sys + o.AHinv, *M = sys + o.M, *BcalT = sys + o.BcalT;
     const double *lo0 = sys + o.lo0, *hi0 = sys + o.hi0, *scal = sys + o.scal;
     const double rho_e = scal[BMPC_S_RHOE];
     const bool soft_on = rho_e > 0.0;
@@ -704,17 +704,15 @@ BMPC_HD int bmpc_polish(Team& t, const BmpcDims& d, const BmpcSysOff& o, const d
         for (int k = t.tid; k < r; k += t.n) { murow[R[k]] = tt[k]; lm = fmax(lm, fabs(tt[k])); }
         mumax = t.max(lm);
         t.sync();
-        // candidate
-        for (int i = t.tid; i < mc; i += t.n) {
-            const double* row = M + i * mc; double acc = W0[i];
-            for (int k = 0; k < r; k++) acc -= row[R[k]] * tt[k];
-            zz[i] = acc;
-        }
+        // candidate: U = U0 - (A H^-1)[R,:]' mu (rows of A H^-1: coalesced), rows zz = A U + cc through the structured A
+        // (BcalT read coalesced over the rows; an M[:,R] gather would touch one 32-byte sector per 8-byte entry)
         for (int a = t.tid; a < NU; a += t.n) {
             double acc = U0[a];
             for (int k = 0; k < r; k++) acc -= AHinv[R[k] * NU + a] * tt[k];
             U[a] = acc;
         }
+        t.sync();
+        for (int i = t.tid; i < mc; i += t.n) zz[i] = bmpc_Arow_dot(d, BcalT, U, i) + (i < NX ? cc[i] : 0.0);
         // verification + next sets
         bool ok = true;
         const double mutol = 1e-9 * (1.0 + mumax);

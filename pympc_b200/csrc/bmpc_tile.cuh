@@ -1,0 +1,299 @@
+// bmpc_tile.cuh — K4 for large shapes (MIMO nx=8, nu=4, Np=40: NU=160, mc=652): one CTA iterates a TILE of T instances
+// together.  Same iteration and same residual bookkeeping as bmpc_admm_rows (bmpc_core.cuh), reorganised so that the
+// shared matrices are read once per tile instead of once per instance:
+//   * vectors of the T instances are interleaved in shared memory, element-major: vec[e*T + t]; a thread that owns one
+//     output row reads its matrix entry once and the T right-hand-side values as one broadcast, T FMAs per entry;
+//   * the prediction matrix Bcal is block-Toeplitz (block (k,j) = Ad^(k-1-j) Bd, plus the "held input" block column
+//     when Nc < Np, mpc.py:537-544): its Np (+ Np-Nc+1) distinct nx*nu blocks live in shared memory (10 KB for MIMO
+//     instead of 2 x 420 KB streamed from L2 per instance-iteration);
+//   * K^-1 (symmetric, NU x NU, one copy per adaptive-rho level) is the only matrix streamed from L2: NU^2*8 bytes per
+//     TILE-iteration; instances of a tile that sit on different levels are served level by level.
+// Written against the team abstraction (tid, n, sync) so that tests/hostemu runs the same code on the host.
+#pragma once
+#include "bmpc_core.cuh"
+
+// strides of one nx*nu block in the two shared-memory copies of the Toeplitz generator:
+//   copy 1 [q][c] (rows of Bcal: consecutive threads = consecutive state rows c), copy 2 [c][q] (columns: consecutive inputs q)
+BMPC_HOSTDEV int bmpc_tile_stride1(const BmpcDims& d) { int s = d.nx * d.nu; return s + ((8 - s % 16) + 16) % 16; }
+BMPC_HOSTDEV int bmpc_tile_stride2(const BmpcDims& d) { int s = d.nx * d.nu; return s + ((d.nu % 16 - s % 16) + 16) % 16; }
+BMPC_HOSTDEV int bmpc_tile_nblocks(const BmpcDims& d) { return d.Np + (d.Np - d.Nc + 1); }
+BMPC_HOSTDEV size_t bmpc_tile_phi_doubles(const BmpcDims& d) {
+    return (size_t)bmpc_tile_nblocks(d) * (bmpc_tile_stride1(d) + bmpc_tile_stride2(d));
+}
+// per-instance doubles: g, x, xt, r (NU each), cc (NX), v, w (mc each), um1 (nu), res (4)
+BMPC_HOSTDEV size_t bmpc_tile_inst_doubles(const BmpcDims& d) { return 4 * (size_t)d.NU + d.NX + 2 * (size_t)d.mc + d.nu + 4; }
+BMPC_HOSTDEV size_t bmpc_tile_smem_doubles(const BmpcDims& d, int T) {
+    return bmpc_tile_phi_doubles(d) + (size_t)T * bmpc_tile_inst_doubles(d) + 2 * (size_t)T /* lvl, new lvl, instance ids as ints */ + 2;
+}
+
+// index of block (k, j) of Bcal (state stage k in 1..Np, input block j < min(k, Nc)) in the generator tables
+BMPC_HD int bmpc_tile_block(const BmpcDims& d, int k, int j) { return (j < d.Nc - 1) ? (k - 1 - j) : (d.Np + k - d.Nc); }
+
+template <class Team>
+BMPC_HD void bmpc_tile_load_phi(Team& t, const BmpcDims& d, const double* Bcal, double* phi1, double* phi2) {
+    const int nb = bmpc_tile_nblocks(d), s1 = bmpc_tile_stride1(d), s2 = bmpc_tile_stride2(d), bs = d.nx * d.nu;
+    for (int idx = t.tid; idx < nb * bs; idx += t.n) {
+        const int b = idx / bs, e = idx % bs, c = e / d.nu, q = e % d.nu;
+        int k, j;
+        if (b < d.Np) { k = b + 1; j = 0; } else { k = d.Nc + (b - d.Np); j = d.Nc - 1; }
+        const double val = Bcal[(size_t)(k * d.nx + c) * d.NU + j * d.nu + q];
+        phi1[b * s1 + q * d.nx + c] = val;
+        phi2[b * s2 + c * d.nu + q] = val;
+    }
+}
+
+#ifdef BMPC_HOSTEMU
+#define BMPC_TILE_MAX(slot, val) do { if ((val) > *(slot)) *(slot) = (val); } while (0)
+#else
+// non-negative doubles order like their bit patterns
+#define BMPC_TILE_MAX(slot, val) atomicMax((unsigned long long*)(slot), (unsigned long long)__double_as_longlong(val))
+#endif
+
+// nearest ladder level suggested by OSQP's rule (see bmpc_adapt_level)
+BMPC_HD int bmpc_next_level(const double* res, int lvl) {
+    const double rp = res[0] / fmax(res[2], 1e-12), rd = res[1] / fmax(res[3], 1e-12);
+    int nl = lvl;
+    if (rp > 0.0 && rd > 0.0) {
+        const double steps = log10(rp / rd);
+        int mv = (int)(steps >= 0.0 ? steps + 0.5 : steps - 0.5);
+        if (mv >= 1 || mv <= -1) nl = lvl + mv;
+        if (nl < 0) nl = 0;
+        if (nl > BMPC_NLEV - 1) nl = BMPC_NLEV - 1;
+    }
+    return nl;
+}
+
+// Shared-memory view of one tile
+template <int T>
+struct BmpcTile {
+    double *phi1, *phi2;                       // Toeplitz generator, two layouts
+    double *g, *cc, *x, *v, *w, *xt, *r;       // [elem][T]
+    double *um1;                               // [T][nu]
+    double *res;                               // [T][4]   rp, rd, np, nd of the last iteration
+    double *fac;                               // [T]      rho factor of each instance's ladder level
+    int *lvl, *nlvl, *inst;                    // [T]
+    BMPC_HD void carve(double* base, const BmpcDims& d) {
+        const int nb = bmpc_tile_nblocks(d);
+        phi1 = base; phi2 = phi1 + (size_t)nb * bmpc_tile_stride1(d);
+        g = phi2 + (size_t)nb * bmpc_tile_stride2(d); cc = g + (size_t)d.NU * T; x = cc + (size_t)d.NX * T;
+        v = x + (size_t)d.NU * T; w = v + (size_t)d.mc * T; xt = w + (size_t)d.mc * T; r = xt + (size_t)d.NU * T;
+        um1 = r + (size_t)d.NU * T; res = um1 + (size_t)d.nu * T;
+        fac = res + 4 * T;
+        lvl = (int*)(fac + T); nlvl = lvl + T; inst = nlvl + T;
+    }
+};
+
+// `niter` ADMM iterations for the T instances of a tile.  NS = how many threads share one output row (each takes
+// T/NS instances).  On return S.res holds the residuals of the last iteration (as bmpc_admm_rows reports them).
+template <int T, int NS, class Team>
+BMPC_HD void bmpc_admm_tile(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, BmpcTile<T>& S, int niter) {
+    constexpr int TG = T / NS;
+    const double *H = sys + o.H, *lo0 = sys + o.lo0, *hi0 = sys + o.hi0, *rhov = sys + o.rho, *scal = sys + o.scal;
+    const double sigma = scal[BMPC_S_SIGMA], alpha = scal[BMPC_S_ALPHA], rho_e = scal[BMPC_S_RHOE];
+    const bool soft_on = rho_e > 0.0;
+    const int nx = d.nx, nu = d.nu, Np = d.Np, Nc = d.Nc, NX = d.NX, NU = d.NU, mc = d.mc;
+    const int s1 = bmpc_tile_stride1(d), s2 = bmpc_tile_stride2(d);
+    double *g = S.g, *cc = S.cc, *x = S.x, *v = S.v, *w = S.w, *xt = S.xt, *r = S.r;
+
+    // (A' w)_a for TG instances: Toeplitz part over the state rows + input row + the reference's delta-u rows
+    auto ATw = [&](const double* ww, int a, int sg, double* acc) {
+        const int j = a / nu, q = a % nu;
+        for (int e = 0; e < TG; e++) acc[e] = 0.0;
+        for (int k = Np; k > j; k--) {                     // descending: every lane of a warp reads the same w rows (broadcast)
+            const double* blk = S.phi2 + bmpc_tile_block(d, k, j) * s2 + q;
+            const double* wk = ww + (size_t)(k * nx) * T + sg * TG;
+            for (int c = 0; c < nx; c++) {
+                const double m = blk[c * nu];
+#pragma unroll
+                for (int e = 0; e < TG; e++) acc[e] += m * wk[c * T + e];
+            }
+        }
+        const double* wu = ww + (size_t)(NX + a) * T + sg * TG;
+        const double* wd = ww + (size_t)(NX + NU) * T + sg * TG;
+#pragma unroll
+        for (int e = 0; e < TG; e++) {
+            double s = wu[e] - wd[(size_t)(nu + a) * T + e];
+            if (a < nu) s += wd[(size_t)a * T + e];
+            if (a >= 1) s += wd[(size_t)(nu + a - 1) * T + e];
+            acc[e] += s;
+        }
+    };
+    // out_a = sum_b Msym[b*NU + a] in[b]   (symmetric matrix streamed from global memory, coalesced over a)
+    auto symv = [&](const double* Msym, const double* in, int a, int sg, double* acc) {
+        for (int e = 0; e < TG; e++) acc[e] = 0.0;
+        const double* col = Msym + a;
+        const double* iv = in + sg * TG;
+        int b = 0;
+        for (; b + 4 <= NU; b += 4) {
+            const double m0 = col[(size_t)b * NU], m1 = col[(size_t)(b + 1) * NU], m2 = col[(size_t)(b + 2) * NU], m3 = col[(size_t)(b + 3) * NU];
+#pragma unroll
+            for (int e = 0; e < TG; e++)
+                acc[e] += m0 * iv[(size_t)b * T + e] + m1 * iv[(size_t)(b + 1) * T + e] + m2 * iv[(size_t)(b + 2) * T + e] + m3 * iv[(size_t)(b + 3) * T + e];
+        }
+        for (; b < NU; b++) {
+            const double m0 = col[(size_t)b * NU];
+#pragma unroll
+            for (int e = 0; e < TG; e++) acc[e] += m0 * iv[(size_t)b * T + e];
+        }
+    };
+    auto row_prox = [&](int i, int e, double vi, double& rho) {
+        double lo, hi; bmpc_row_bounds(d, lo0, hi0, S.um1 + e * nu, i, lo, hi);
+        rho = S.fac[e] * rhov[i];
+        return bmpc_prox(vi, lo, hi, soft_on && i < NX, rho, rho_e);
+    };
+    for (int e = t.tid; e < 4 * T; e += t.n) S.res[e] = 0.0;
+    for (int e = t.tid; e < T; e += t.n) S.fac[e] = bmpc_level_factor(S.lvl[e]);
+    t.sync();
+    // levels present in this tile
+    unsigned lmask = 0;
+    for (int e = 0; e < T; e++) lmask |= 1u << S.lvl[e];
+
+    for (int it = 0; it < niter; it++) {
+        const bool last = (it == niter - 1);
+        // A: rows  w = rho (2 prox(v) - v - cc)
+        for (int idx = t.tid; idx < mc * T; idx += t.n) {
+            const int i = idx / T, e = idx % T;
+            const double vi = v[idx]; double rho;
+            const double z = row_prox(i, e, vi, rho);
+            w[idx] = rho * (2.0 * z - vi - (i < NX ? cc[idx] : 0.0));
+        }
+        t.sync();
+        // B: r = sigma x - g + A' w
+        for (int wk = t.tid; wk < NU * NS; wk += t.n) {
+            const int a = wk / NS, sg = wk % NS; double acc[TG];
+            ATw(w, a, sg, acc);
+#pragma unroll
+            for (int e = 0; e < TG; e++) { const size_t p = (size_t)a * T + sg * TG + e; r[p] = sigma * x[p] - g[p] + acc[e]; }
+        }
+        t.sync();
+        // C: xt = Kinv[level] r, level by level
+        for (int L = 0; L < BMPC_NLEV; L++) {
+            if (!((lmask >> L) & 1u)) continue;
+            const double* Kinv = sys + o.KinvL + (size_t)L * NU * NU;
+            for (int wk = t.tid; wk < NU * NS; wk += t.n) {
+                const int a = wk / NS, sg = wk % NS; double acc[TG];
+                symv(Kinv, r, a, sg, acc);
+#pragma unroll
+                for (int e = 0; e < TG; e++) if (S.lvl[sg * TG + e] == L) xt[(size_t)a * T + sg * TG + e] = acc[e];
+            }
+        }
+        t.sync();
+        // D1: zt on the state rows (kept in w, which is dead now): row (k,c) = cc + sum_{j<min(k,Nc)} block(k,j)[c,:] xt_j
+        for (int i = t.tid; i < NX; i += t.n) {
+            const int k = i / nx, c = i % nx;
+            double acc[T];
+#pragma unroll
+            for (int e = 0; e < T; e++) acc[e] = cc[(size_t)i * T + e];
+            const int jend = k < Nc ? k : Nc;
+            for (int j = 0; j < jend; j++) {
+                const double* blk = S.phi1 + bmpc_tile_block(d, k, j) * s1 + c;
+                const double* xj = xt + (size_t)(j * nu) * T;
+                for (int q = 0; q < nu; q++) {
+                    const double m = blk[q * nx];
+#pragma unroll
+                    for (int e = 0; e < T; e++) acc[e] += m * xj[q * T + e];
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < T; e++) w[(size_t)i * T + e] = acc[e];
+        }
+        t.sync();
+        // D2: rows  v += alpha (zt - prox(v))
+        for (int idx = t.tid; idx < mc * T; idx += t.n) {
+            const int i = idx / T, e = idx % T;
+            const double vi = v[idx]; double rho;
+            const double z = row_prox(i, e, vi, rho);
+            double zt;
+            if (i < NX) zt = w[idx];
+            else if (i < NX + NU) zt = xt[(size_t)(i - NX) * T + e];
+            else {
+                const int rr = i - NX - NU;
+                if (rr < nu) zt = xt[(size_t)rr * T + e];
+                else { const int q2 = rr - nu; zt = -xt[(size_t)q2 * T + e] + (q2 + 1 < NU ? xt[(size_t)(q2 + 1) * T + e] : 0.0); }
+            }
+            const double dz = zt - z;
+            v[idx] = vi + alpha * dz;
+            if (last) {
+                BMPC_TILE_MAX(S.res + e * 4 + 0, fabs(dz));
+                BMPC_TILE_MAX(S.res + e * 4 + 2, fmax(fabs(zt), fabs(z)));
+                w[idx] = rho * dz;
+            }
+        }
+        if (last) {
+            t.sync();
+            // r_dual = ||sigma (xt - x) + A' rho (zt - z)||, normalisers ||g||, ||H xt||, ||A' y||
+            for (int wk = t.tid; wk < NU * NS; wk += t.n) {
+                const int a = wk / NS, sg = wk % NS; double acc[TG], hx[TG];
+                ATw(w, a, sg, acc);
+                symv(H, xt, a, sg, hx);
+#pragma unroll
+                for (int e = 0; e < TG; e++) {
+                    const size_t p = (size_t)a * T + sg * TG + e;
+                    BMPC_TILE_MAX(S.res + (sg * TG + e) * 4 + 1, fabs(sigma * (xt[p] - x[p]) + acc[e]));
+                    BMPC_TILE_MAX(S.res + (sg * TG + e) * 4 + 3, fmax(fabs(hx[e]), fabs(g[p])));
+                }
+            }
+            t.sync();
+            for (int idx = t.tid; idx < mc * T; idx += t.n) {
+                const int i = idx / T, e = idx % T;
+                const double vi = v[idx]; double rho;
+                const double z = row_prox(i, e, vi, rho);
+                w[idx] = rho * (vi - z);
+            }
+            t.sync();
+            for (int wk = t.tid; wk < NU * NS; wk += t.n) {
+                const int a = wk / NS, sg = wk % NS; double acc[TG];
+                ATw(w, a, sg, acc);
+#pragma unroll
+                for (int e = 0; e < TG; e++) BMPC_TILE_MAX(S.res + (sg * TG + e) * 4 + 3, fabs(acc[e]));
+            }
+        }
+        for (int idx = t.tid; idx < NU * T; idx += t.n) x[idx] += alpha * (xt[idx] - x[idx]);
+        t.sync();
+    }
+}
+
+// adaptive-rho move for every instance of the tile (v rescaled so that (z, y) are unchanged); S.nlvl = new levels
+template <int T, class Team>
+BMPC_HD void bmpc_tile_adapt(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, BmpcTile<T>& S) {
+    const double *lo0 = sys + o.lo0, *hi0 = sys + o.hi0, *rhov = sys + o.rho;
+    const double rho_e = sys[o.scal + BMPC_S_RHOE];
+    const bool soft_on = rho_e > 0.0;
+    for (int e = t.tid; e < T; e += t.n) S.nlvl[e] = bmpc_next_level(S.res + e * 4, S.lvl[e]);
+    t.sync();
+    for (int idx = t.tid; idx < d.mc * T; idx += t.n) {
+        const int i = idx / T, e = idx % T;
+        if (S.nlvl[e] == S.lvl[e]) continue;
+        const double fo = bmpc_level_factor(S.lvl[e]), ratio = fo / bmpc_level_factor(S.nlvl[e]);
+        double lo, hi; bmpc_row_bounds(d, lo0, hi0, S.um1 + e * d.nu, i, lo, hi);
+        const double vi = S.v[idx];
+        const double z = bmpc_prox(vi, lo, hi, soft_on && i < d.NX, fo * rhov[i], rho_e);
+        S.v[idx] = z + (vi - z) * ratio;
+    }
+    t.sync();
+}
+
+// K3 for a tile: g and cc of every instance (same formulas as bmpc_prep)
+template <int T, class Team>
+BMPC_HD void bmpc_tile_prep(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, BmpcTile<T>& S,
+                            const double* x0 /*[T][nx]*/, const double* xref_all /*[B][xl]*/, int xref_mode) {
+    const double *Gx0 = sys + o.Gx0, *Gref = sys + o.Gref, *GrefFull = sys + o.GrefFull, *g0 = sys + o.g0, *QDu = sys + o.QDu;
+    const double* Acal = sys + o.Acal;
+    for (int idx = t.tid; idx < d.NU * T; idx += t.n) {
+        const int a = idx / T, e = idx % T;
+        const double* xe = x0 + e * d.nx; const double* xr = xref_all + (size_t)S.inst[e] * (xref_mode ? d.NX : d.nx);
+        double acc = g0[a];
+        for (int c = 0; c < d.nx; c++) acc += Gx0[a * d.nx + c] * xe[c];
+        if (xref_mode == 0) { for (int c = 0; c < d.nx; c++) acc += Gref[a * d.nx + c] * xr[c]; }
+        else { for (int i = 0; i < d.NX; i++) acc += GrefFull[(size_t)a * d.NX + i] * xr[i]; }
+        if (a < d.nu) { for (int q = 0; q < d.nu; q++) acc -= QDu[a * d.nu + q] * S.um1[e * d.nu + q]; }
+        S.g[idx] = acc;
+    }
+    for (int idx = t.tid; idx < d.NX * T; idx += t.n) {
+        const int i = idx / T, e = idx % T;
+        const double* xe = x0 + e * d.nx; double acc = 0.0;
+        for (int c = 0; c < d.nx; c++) acc += Acal[i * d.nx + c] * xe[c];
+        S.cc[idx] = acc;
+    }
+    t.sync();
+}

@@ -16,8 +16,9 @@ def build():
     src = os.path.join(_HERE, "hostemu.cpp")
     core = os.path.join(_HERE, "..", "..", "pympc_b200", "csrc", "bmpc_core.cuh")
     tpi = os.path.join(_HERE, "..", "..", "pympc_b200", "csrc", "bmpc_tpi.cuh")
+    tile = os.path.join(_HERE, "..", "..", "pympc_b200", "csrc", "bmpc_tile.cuh")
     os.makedirs(os.path.dirname(_SO), exist_ok=True)
-    if (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(core), os.path.getmtime(tpi)):
+    if (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(core), os.path.getmtime(tpi), os.path.getmtime(tile)):
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-x", "c++", src, "-o", _SO])
     return ctypes.CDLL(_SO)
 
@@ -80,3 +81,25 @@ class EmuSystem:
                first_iters, pdas_steps)
         self.cold = 0
         return U, ps
+
+
+    def tile_compare(self, X0, Um1, Xref, niter, lvl=None, x_in=None, v_in=None):
+        """Run the tile ADMM and the per-instance team ADMM on the same 4 instances; returns (ref, tile) dicts."""
+        T = 4
+        X0 = np.ascontiguousarray(X0, float); Um1 = np.ascontiguousarray(Um1, float); Xref = np.ascontiguousarray(Xref, float)
+        mode = 0 if Xref.ndim == 2 else 1
+        Xref = Xref.reshape(T, -1)
+        lvl = np.ascontiguousarray(lvl if lvl is not None else [2] * T, np.int32)
+        cold = 1 if x_in is None else 0
+        xin = np.ascontiguousarray(x_in if x_in is not None else np.zeros((T, self.NU)), float)
+        vin = np.ascontiguousarray(v_in if v_in is not None else np.zeros((T, self.mc)), float)
+        out = {}
+        for tag in ("ref", "tile"):
+            out[tag] = {"x": np.zeros((T, self.NU)), "v": np.zeros((T, self.mc)), "xt": np.zeros((T, self.NU)),
+                        "res": np.zeros((T, 4)), "lvl": np.zeros(T, np.int32)}
+        f = self.L.emu_tile_compare
+        f.restype = None
+        f.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 4 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 13
+        f(self.nx, self.nu, self.Np, self.Nc, _p(self.sys), _p(X0), _p(Um1), _p(Xref), mode, cold, niter, _p(lvl), _p(xin), _p(vin),
+          *[_p(out[tag][k]) for tag in ("ref", "tile") for k in ("x", "v", "xt", "res", "lvl")])
+        return out["ref"], out["tile"]

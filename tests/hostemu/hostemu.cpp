@@ -5,6 +5,7 @@
 #define BMPC_HOSTEMU 1
 #include "../../pympc_b200/csrc/bmpc_core.cuh"
 #include "../../pympc_b200/csrc/bmpc_tpi.cuh"
+#include "../../pympc_b200/csrc/bmpc_tile.cuh"
 #include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
@@ -107,4 +108,50 @@ extern "C" int emu_tpi_step(int nx, int nu, int Np, int Nc, const double* sys, c
     if (nx == 4 && nu == 1 && Np == 20 && Nc == 20) return emu_tpi_run<TpiShape<4, 1, 20, 20>>(sys, x0, um1, xref, cold, x, v, Uout, first_iters, pdas_steps);
     if (nx == 2 && nu == 1 && Np == 20 && Nc == 20) return emu_tpi_run<TpiShape<2, 1, 20, 20>>(sys, x0, um1, xref, cold, x, v, Uout, first_iters, pdas_steps);
     return -100;
+}
+
+
+// Tile ADMM (bmpc_tile.cuh) against the per-instance team ADMM on the same T = 4 instances: prep + niter iterations +
+// adaptive-rho move.  x, v: [T][NU], [T][mc] warm start in (ignored when cold), results out (ref_* per-instance code,
+// tile_* tile code); res [T][4]; lvl [T] in/out.
+extern "C" void emu_tile_compare(int nx, int nu, int Np, int Nc, const double* sys, const double* x0, const double* um1, const double* xref,
+                                 int xref_mode, int cold, int niter, const int* lvl_in, const double* x_in, const double* v_in,
+                                 double* ref_x, double* ref_v, double* ref_xt, double* ref_res, int* ref_lvl,
+                                 double* tile_x, double* tile_v, double* tile_xt, double* tile_res, int* tile_lvl) {
+    constexpr int T = 4;
+    BmpcDims d = bmpc_make_dims(nx, nu, Np, Nc); BmpcSysOff o = bmpc_make_off(d);
+    SeqTeam t;
+    const int xl = xref_mode ? d.NX : d.nx;
+    // reference: one instance at a time
+    double* buf = (double*)calloc(4 * d.NU + d.NX + 2 * d.mc + 8, sizeof(double));
+    double *g = buf, *cc = g + d.NU, *w = cc + d.NX, *xt = w + d.mc, *r = xt + d.NU, *res = r + d.NU;
+    for (int e = 0; e < T; e++) {
+        double* x = ref_x + e * d.NU; double* v = ref_v + e * d.mc;
+        bmpc_prep(t, d, o, sys, x0 + e * nx, um1 + e * nu, xref + e * xl, xref_mode, g, cc);
+        if (cold) { for (int a = 0; a < d.NU; a++) x[a] = 0.0; for (int i = 0; i < d.mc; i++) v[i] = i < d.NX ? cc[i] : 0.0; }
+        else { memcpy(x, x_in + e * d.NU, sizeof(double) * d.NU); memcpy(v, v_in + e * d.mc, sizeof(double) * d.mc); }
+        bmpc_admm(t, d, o, sys, um1 + e * nu, g, cc, x, v, w, xt, r, niter, res, lvl_in[e]);
+        ref_lvl[e] = bmpc_adapt_level(t, d, o, sys, um1 + e * nu, v, res, lvl_in[e]);
+        memcpy(ref_xt + e * d.NU, xt, sizeof(double) * d.NU); memcpy(ref_res + e * 4, res, sizeof(double) * 4);
+    }
+    free(buf);
+    // tile
+    double* sm = (double*)calloc(bmpc_tile_smem_doubles(d, T) + 8, sizeof(double));
+    BmpcTile<T> S; S.carve(sm, d);
+    for (int e = 0; e < T; e++) { S.inst[e] = e; S.lvl[e] = lvl_in[e]; for (int q = 0; q < nu; q++) S.um1[e * nu + q] = um1[e * nu + q]; }
+    bmpc_tile_load_phi(t, d, sys + o.Bcal, S.phi1, S.phi2);
+    bmpc_tile_prep(t, d, o, sys, S, x0, xref, xref_mode);
+    for (int e = 0; e < T; e++) {
+        for (int a = 0; a < d.NU; a++) S.x[a * T + e] = cold ? 0.0 : x_in[e * d.NU + a];
+        for (int i = 0; i < d.mc; i++) S.v[i * T + e] = cold ? (i < d.NX ? S.cc[i * T + e] : 0.0) : v_in[e * d.mc + i];
+    }
+    bmpc_admm_tile<T, 2>(t, d, o, sys, S, niter);
+    bmpc_tile_adapt(t, d, o, sys, S);
+    for (int e = 0; e < T; e++) {
+        for (int a = 0; a < d.NU; a++) { tile_x[e * d.NU + a] = S.x[a * T + e]; tile_xt[e * d.NU + a] = S.xt[a * T + e]; }
+        for (int i = 0; i < d.mc; i++) tile_v[e * d.mc + i] = S.v[i * T + e];
+        for (int k = 0; k < 4; k++) tile_res[e * 4 + k] = S.res[e * 4 + k];
+        tile_lvl[e] = S.nlvl[e];
+    }
+    free(sm);
 }
