@@ -212,6 +212,7 @@ __global__ void k_admm_tile(BmpcDims d, BmpcSysOff o, const double* __restrict__
     }
     t.sync();
     bmpc_tile_load_phi(t, d, sys + o.Bcal, S.phi1, S.phi2);
+    bmpc_tile_load_rows(t, d, o, sys, S.lo, S.hi, S.rho);
     for (int idx = t.tid; idx < d.nu * T; idx += t.n) { const int e = idx / d.nu, q = idx % d.nu; S.um1[idx] = I.um1[(size_t)S.inst[e] * d.nu + q]; }
     if (do_prep) {
         double* x0 = S.r;                                              // staging: r is free until the first iteration
@@ -249,13 +250,15 @@ __global__ void k_admm_tile(BmpcDims d, BmpcSysOff o, const double* __restrict__
 
 template <bool WARP>
 __global__ void k_polish(BmpcDims d, BmpcSysOff o, const double* __restrict__ sys, BmpcInst I, const int32_t* __restrict__ list,
-                         int count, int rmax, int max_steps, int32_t* next_list, int32_t* next_count, double* u0_out) {
+                         int count, int rmax, int max_steps, int32_t* next_list, int32_t* next_count, double* u0_out,
+                         const int32_t* dev_count, int32_t* ovf_list) {
     extern __shared__ double smem[];
     __shared__ double sd[32];
     __shared__ int si[32];
     int slot, idx;
     if (WARP) { slot = threadIdx.x >> 5; idx = blockIdx.x * (blockDim.x >> 5) + slot; }
     else { slot = 0; idx = blockIdx.x; }
+    if (dev_count) count = *dev_count;                 // second tier: the list was filled by the launch before this one
     if (idx >= count) return;
     const int inst = list ? list[idx] : idx;
     sys += (size_t)inst * I.sys_stride;
@@ -281,6 +284,9 @@ __global__ void k_polish(BmpcDims d, BmpcSysOff o, const double* __restrict__ sy
             // exact ADMM fixed point of this problem = warm start of the next one: v* = z* + y*/rho
             for (int i = t.tid; i < d.mc; i += t.n) I.vw[(size_t)inst * d.mc + i] = zz[i] + murow[i] / rhov[i];
             if (t.tid == 0) { I.status[inst] = BMPC_SOLVED; I.psteps[inst] += ps; atomicAdd(next_count + 1, ps); }
+        } else if (ps < 0 && ovf_list) {
+            // working set larger than this tier's capacity: hand the instance to the large-capacity launch that follows
+            if (t.tid == 0) { int pos = atomicAdd(next_count + 2, 1); ovf_list[pos] = inst; }
         } else {
             if (t.tid == 0) {
                 int used = (ps < 0 ? 1 : max_steps);
@@ -574,6 +580,7 @@ struct bmpc_handle {
     size_t smem_admm = 0, smem_polish = 0;
     // low-latency CTA-per-instance variant for the few stragglers of a warp-team / TPI handle
     int fb_team = 0, fb_rmax = 0; size_t fb_smem_admm = 0, fb_smem_polish = 0;
+    int rmax_small = 0; size_t smem_polish_small = 0; int32_t* ovf = nullptr;   // small-capacity polish tier (CTA teams) + its overflow list
     int tile_T = 0, tile_threads = 0;                  // > 0: the ADMM of this shape runs on tiles of T instances per CTA
     struct { const int32_t* list; int count; int32_t *cur, *nxt; int total, chunk, round; bool need_prep; } st = {};
     bool pending = false;              // a round is in flight and has not been retired by the host yet
@@ -708,6 +715,7 @@ static int configure_launch(bmpc_handle* h) {
             th = ((th + 31) / 32) * 32; if (th < 128) th = 128; if (th > 512) th = 512;
             h->tile_threads = th;
         }
+        if (h->cfg.rmax == 0 && rmax > 96) { h->rmax_small = 80; h->smem_polish_small = polish_smem_doubles(d, 80) * 8; }
         h->wpb = team / 32;
         h->smem_admm = admm_smem_doubles(d) * 8;
         h->smem_polish = polish_smem_doubles(d, rmax) * 8;
@@ -766,7 +774,8 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     ok &= dalloc((void**)&h->I.lvl, sizeof(int32_t) * B);
     ok &= dalloc((void**)&h->listA, sizeof(int32_t) * B);
     ok &= dalloc((void**)&h->listB, sizeof(int32_t) * B);
-    ok &= dalloc((void**)&h->counts, sizeof(int32_t) * 2);
+    ok &= dalloc((void**)&h->counts, sizeof(int32_t) * 4);
+    ok &= dalloc((void**)&h->ovf, sizeof(int32_t) * (size_t)B);
     if (!ok) { h->err = "cudaMalloc failed"; cudaGetLastError(); return fail(BMPC_ERR_CUDA); }
     if (cudaHostAlloc((void**)&h->h_count, sizeof(int32_t) * 4, cudaHostAllocDefault) != cudaSuccess) { h->err = "cudaHostAlloc failed"; return fail(BMPC_ERR_CUDA); }
     cudaMemset(h->sys, 0, sizeof(double) * (size_t)h->o.total * h->cfg.n_sys);
@@ -789,7 +798,7 @@ void bmpc_destroy(bmpc_handle* h) {
     cudaSetDevice(h->cfg.device);
     if (h->pending) cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->sys, h->x0, h->um1, h->um1_solved, h->xref, h->u0_own, h->I.g, h->I.cc, h->I.xw, h->I.vw, h->I.Ua, h->I.Us, h->I.res,
-                    h->I.status, h->I.iters, h->I.psteps, h->I.lvl, h->listA, h->listB, h->counts, h->seq_x, h->seq_e, h->seq_obj};
+                    h->I.status, h->I.iters, h->I.psteps, h->I.lvl, h->listA, h->listB, h->counts, h->ovf, h->seq_x, h->seq_e, h->seq_obj};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_count) cudaFreeHost(h->h_count);
     free(h->tpi_admm_params); free(h->tpi_polish_params);
@@ -929,12 +938,18 @@ static void launch_admm(bmpc_handle* h, const int32_t* list, int count, int nite
 
 static void launch_polish(bmpc_handle* h, const int32_t* list, int count, int32_t* next_list, int32_t* next_count) {
     if (use_fallback_team(h, list, count)) {
-        k_polish<false><<<count, h->fb_team, h->fb_smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->fb_rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0);
+        k_polish<false><<<count, h->fb_team, h->fb_smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->fb_rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0, nullptr, nullptr);
     } else if (h->team == 32) {
         int grid = (count + h->wpb - 1) / h->wpb;
-        k_polish<true><<<grid, h->wpb * 32, h->smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0);
+        k_polish<true><<<grid, h->wpb * 32, h->smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0, nullptr, nullptr);
+    } else if (h->rmax_small > 0) {
+        // two capacity tiers: the small one keeps several CTAs resident per SM (the polish is latency-bound); working
+        // sets that outgrow it are listed and redone by the full-capacity launch right after (count read on the device)
+        k_polish<false><<<count, h->team, h->smem_polish_small, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->rmax_small, h->cfg.pdas_steps, next_list, next_count, h->I.u0, nullptr, h->ovf);
+        k_polish<false><<<count, h->team, h->smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, h->ovf, count, h->rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0, next_count + 2, nullptr);
+        h->stats.launches++;
     } else {
-        k_polish<false><<<count, h->team, h->smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0);
+        k_polish<false><<<count, h->team, h->smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0, nullptr, nullptr);
     }
     h->stats.launches++;
 }
@@ -955,7 +970,7 @@ static int enqueue_round(bmpc_handle* h) {
             h->stats.launches++;
             BMPC_CUDA(cudaMemcpyAsync(h->um1_solved, h->um1, sizeof(double) * (size_t)B * h->d.nu, cudaMemcpyDeviceToDevice, h->stream));
         }
-        BMPC_CUDA(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 2, h->stream));
+        BMPC_CUDA(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 4, h->stream));
     }
     BMPC_CUDA(cudaEventRecord(h->ev[0], h->stream));
     if (tpi) {

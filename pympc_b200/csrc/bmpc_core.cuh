@@ -623,15 +623,16 @@ BMPC_HD int bmpc_polish(Team& t, const BmpcDims& d, const BmpcSysOff& o, const d
     #define BMPC_TRI(k, l) ((size_t)(k) * ((k) + 1) / 2 + (l))
     const double delta = 1e-13;
 
+    // U0 = -H^-1 g (H^-1 symmetric: column reads are coalesced over a), W0 = A U0 + cc through the structured A
     for (int a = t.tid; a < NU; a += t.n) {
-        const double* row = Hinv + a * NU; double acc = 0.0;
-        for (int b = 0; b < NU; b++) acc += row[b] * g[b];
-        U0[a] = -acc;
+        const double* col = Hinv + a; double a0 = 0.0, a1 = 0.0; int b = 0;
+        for (; b + 1 < NU; b += 2) { a0 += col[(size_t)b * NU] * g[b]; a1 += col[(size_t)(b + 1) * NU] * g[b + 1]; }
+        if (b < NU) a0 += col[(size_t)b * NU] * g[b];
+        U0[a] = -(a0 + a1);
     }
+    t.sync();
     for (int i = t.tid; i < mc; i += t.n) {
-        const double* row = AHinv + i * NU; double acc = (i < NX) ? cc[i] : 0.0;
-        for (int b = 0; b < NU; b++) acc -= row[b] * g[b];
-        W0[i] = acc;
+        W0[i] = bmpc_Arow_dot(d, BcalT, U0, i) + ((i < NX) ? cc[i] : 0.0);
         double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
         // rows sitting on a bound to rounding level (steady state at xref = xmax, say) stay out of the first guess
         st[i] = v[i] > hi + 1e-9 * (1.0 + fabs(hi)) ? 1 : (v[i] < lo - 1e-9 * (1.0 + fabs(lo)) ? 2 : 0);
@@ -657,13 +658,14 @@ BMPC_HD int bmpc_polish(Team& t, const BmpcDims& d, const BmpcSysOff& o, const d
                 int i = R[k]; double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
                 tt[k] = W0[i] - (st[i] == 1 ? hi : lo);
             }
-            for (int k = t.tid; k < r; k += t.n) {
-                const double* Mrow = M + (size_t)R[k] * mc;
-                for (int l = 0; l <= k; l++) {
-                    double val = Mrow[R[l]];
-                    if (k == l) val += (soft_on && R[k] < NX) ? inv_rho_e : delta * (1.0 + fabs(val));
-                    S[BMPC_TRI(k, l)] = val;
-                }
+            for (int e = t.tid; e < r * (r + 1) / 2; e += t.n) {       // all threads share the r(r+1)/2 gathers
+                int k = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+                while ((k + 1) * (k + 2) / 2 <= e) k++;
+                while (k * (k + 1) / 2 > e) k--;
+                const int l = e - k * (k + 1) / 2;
+                double val = M[(size_t)R[k] * mc + R[l]];
+                if (k == l) val += (soft_on && R[k] < NX) ? inv_rho_e : delta * (1.0 + fabs(val));
+                S[e] = val;
             }
             t.sync();
             // Cholesky S = L L' (lower, in place)

@@ -18,7 +18,8 @@ BMPC_HOSTDEV int bmpc_tile_stride1(const BmpcDims& d) { int s = d.nx * d.nu; ret
 BMPC_HOSTDEV int bmpc_tile_stride2(const BmpcDims& d) { int s = d.nx * d.nu; return s + ((d.nu % 16 - s % 16) + 16) % 16; }
 BMPC_HOSTDEV int bmpc_tile_nblocks(const BmpcDims& d) { return d.Np + (d.Np - d.Nc + 1); }
 BMPC_HOSTDEV size_t bmpc_tile_phi_doubles(const BmpcDims& d) {
-    return (size_t)bmpc_tile_nblocks(d) * (bmpc_tile_stride1(d) + bmpc_tile_stride2(d));
+    size_t n = (size_t)bmpc_tile_nblocks(d) * (bmpc_tile_stride1(d) + bmpc_tile_stride2(d)) + 3 * (size_t)d.mc;   // + row bounds and rho
+    return (n + 1) & ~(size_t)1;                       // even: the tile vectors behind it stay 16-byte aligned
 }
 // per-instance doubles: g, x, xt, r (NU each), cc (NX), v, w (mc each), um1 (nu), res (4)
 BMPC_HOSTDEV size_t bmpc_tile_inst_doubles(const BmpcDims& d) { return 4 * (size_t)d.NU + d.NX + 2 * (size_t)d.mc + d.nu + 4; }
@@ -28,6 +29,11 @@ BMPC_HOSTDEV size_t bmpc_tile_smem_doubles(const BmpcDims& d, int T) {
 
 // index of block (k, j) of Bcal (state stage k in 1..Np, input block j < min(k, Nc)) in the generator tables
 BMPC_HD int bmpc_tile_block(const BmpcDims& d, int k, int j) { return (j < d.Nc - 1) ? (k - 1 - j) : (d.Np + k - d.Nc); }
+
+template <class Team>
+BMPC_HD void bmpc_tile_load_rows(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, double* lo, double* hi, double* rho) {
+    for (int i = t.tid; i < d.mc; i += t.n) { lo[i] = sys[o.lo0 + i]; hi[i] = sys[o.hi0 + i]; rho[i] = sys[o.rho + i]; }
+}
 
 template <class Team>
 BMPC_HD void bmpc_tile_load_phi(Team& t, const BmpcDims& d, const double* Bcal, double* phi1, double* phi2) {
@@ -41,6 +47,17 @@ BMPC_HD void bmpc_tile_load_phi(Team& t, const BmpcDims& d, const double* Bcal, 
         phi2[b * s2 + c * d.nu + q] = val;
     }
 }
+
+// N consecutive doubles of a tile vector (16-byte aligned by construction) -> registers, as 128-bit shared-memory loads
+#ifdef BMPC_HOSTEMU
+template <int N> BMPC_HD void bmpc_ldv(const double* p, double* o) { for (int i = 0; i < N; i++) o[i] = p[i]; }
+#else
+template <int N> BMPC_HD void bmpc_ldv(const double* p, double* o) {
+    static_assert(N % 2 == 0, "tile vectors are read in pairs");
+#pragma unroll
+    for (int i = 0; i < N; i += 2) { const double2 t2 = *reinterpret_cast<const double2*>(p + i); o[i] = t2.x; o[i + 1] = t2.y; }
+}
+#endif
 
 #ifdef BMPC_HOSTEMU
 #define BMPC_TILE_MAX(slot, val) do { if ((val) > *(slot)) *(slot) = (val); } while (0)
@@ -67,6 +84,7 @@ BMPC_HD int bmpc_next_level(const double* res, int lvl) {
 template <int T>
 struct BmpcTile {
     double *phi1, *phi2;                       // Toeplitz generator, two layouts
+    double *lo, *hi, *rho;                     // [mc] row bounds (without the u_-1 shift) and base rho of every row
     double *g, *cc, *x, *v, *w, *xt, *r;       // [elem][T]
     double *um1;                               // [T][nu]
     double *res;                               // [T][4]   rp, rd, np, nd of the last iteration
@@ -75,7 +93,8 @@ struct BmpcTile {
     BMPC_HD void carve(double* base, const BmpcDims& d) {
         const int nb = bmpc_tile_nblocks(d);
         phi1 = base; phi2 = phi1 + (size_t)nb * bmpc_tile_stride1(d);
-        g = phi2 + (size_t)nb * bmpc_tile_stride2(d); cc = g + (size_t)d.NU * T; x = cc + (size_t)d.NX * T;
+        lo = phi2 + (size_t)nb * bmpc_tile_stride2(d); hi = lo + d.mc; rho = hi + d.mc;
+        g = base + bmpc_tile_phi_doubles(d); cc = g + (size_t)d.NU * T; x = cc + (size_t)d.NX * T;
         v = x + (size_t)d.NU * T; w = v + (size_t)d.mc * T; xt = w + (size_t)d.mc * T; r = xt + (size_t)d.NU * T;
         um1 = r + (size_t)d.NU * T; res = um1 + (size_t)d.nu * T;
         fac = res + 4 * T;
@@ -88,7 +107,7 @@ struct BmpcTile {
 template <int T, int NS, class Team>
 BMPC_HD void bmpc_admm_tile(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, BmpcTile<T>& S, int niter) {
     constexpr int TG = T / NS;
-    const double *H = sys + o.H, *lo0 = sys + o.lo0, *hi0 = sys + o.hi0, *rhov = sys + o.rho, *scal = sys + o.scal;
+    const double *H = sys + o.H, *lo0 = S.lo, *hi0 = S.hi, *rhov = S.rho, *scal = sys + o.scal;
     const double sigma = scal[BMPC_S_SIGMA], alpha = scal[BMPC_S_ALPHA], rho_e = scal[BMPC_S_RHOE];
     const bool soft_on = rho_e > 0.0;
     const int nx = d.nx, nu = d.nu, Np = d.Np, Nc = d.Nc, NX = d.NX, NU = d.NU, mc = d.mc;
@@ -103,9 +122,10 @@ BMPC_HD void bmpc_admm_tile(Team& t, const BmpcDims& d, const BmpcSysOff& o, con
             const double* blk = S.phi2 + bmpc_tile_block(d, k, j) * s2 + q;
             const double* wk = ww + (size_t)(k * nx) * T + sg * TG;
             for (int c = 0; c < nx; c++) {
-                const double m = blk[c * nu];
+                const double m = blk[c * nu]; double wv[TG];
+                bmpc_ldv<TG>(wk + c * T, wv);
 #pragma unroll
-                for (int e = 0; e < TG; e++) acc[e] += m * wk[c * T + e];
+                for (int e = 0; e < TG; e++) acc[e] = fma(m, wv[e], acc[e]);
             }
         }
         const double* wu = ww + (size_t)(NX + a) * T + sg * TG;
@@ -124,16 +144,23 @@ BMPC_HD void bmpc_admm_tile(Team& t, const BmpcDims& d, const BmpcSysOff& o, con
         const double* col = Msym + a;
         const double* iv = in + sg * TG;
         int b = 0;
-        for (; b + 4 <= NU; b += 4) {
-            const double m0 = col[(size_t)b * NU], m1 = col[(size_t)(b + 1) * NU], m2 = col[(size_t)(b + 2) * NU], m3 = col[(size_t)(b + 3) * NU];
+        for (; b + 8 <= NU; b += 8) {                      // 8 matrix loads in flight per thread
+            double m[8];
 #pragma unroll
-            for (int e = 0; e < TG; e++)
-                acc[e] += m0 * iv[(size_t)b * T + e] + m1 * iv[(size_t)(b + 1) * T + e] + m2 * iv[(size_t)(b + 2) * T + e] + m3 * iv[(size_t)(b + 3) * T + e];
+            for (int u = 0; u < 8; u++) m[u] = col[(size_t)(b + u) * NU];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                double rv[TG];
+                bmpc_ldv<TG>(iv + (size_t)(b + u) * T, rv);
+#pragma unroll
+                for (int e = 0; e < TG; e++) acc[e] = fma(m[u], rv[e], acc[e]);
+            }
         }
         for (; b < NU; b++) {
-            const double m0 = col[(size_t)b * NU];
+            const double m0 = col[(size_t)b * NU]; double rv[TG];
+            bmpc_ldv<TG>(iv + (size_t)b * T, rv);
 #pragma unroll
-            for (int e = 0; e < TG; e++) acc[e] += m0 * iv[(size_t)b * T + e];
+            for (int e = 0; e < TG; e++) acc[e] = fma(m0, rv[e], acc[e]);
         }
     };
     auto row_prox = [&](int i, int e, double vi, double& rho) {
@@ -182,16 +209,16 @@ BMPC_HD void bmpc_admm_tile(Team& t, const BmpcDims& d, const BmpcSysOff& o, con
         for (int i = t.tid; i < NX; i += t.n) {
             const int k = i / nx, c = i % nx;
             double acc[T];
-#pragma unroll
-            for (int e = 0; e < T; e++) acc[e] = cc[(size_t)i * T + e];
+            bmpc_ldv<T>(cc + (size_t)i * T, acc);
             const int jend = k < Nc ? k : Nc;
             for (int j = 0; j < jend; j++) {
                 const double* blk = S.phi1 + bmpc_tile_block(d, k, j) * s1 + c;
                 const double* xj = xt + (size_t)(j * nu) * T;
                 for (int q = 0; q < nu; q++) {
-                    const double m = blk[q * nx];
+                    const double m = blk[q * nx]; double xv[T];
+                    bmpc_ldv<T>(xj + q * T, xv);
 #pragma unroll
-                    for (int e = 0; e < T; e++) acc[e] += m * xj[q * T + e];
+                    for (int e = 0; e < T; e++) acc[e] = fma(m, xv[e], acc[e]);
                 }
             }
 #pragma unroll
@@ -256,7 +283,7 @@ BMPC_HD void bmpc_admm_tile(Team& t, const BmpcDims& d, const BmpcSysOff& o, con
 // adaptive-rho move for every instance of the tile (v rescaled so that (z, y) are unchanged); S.nlvl = new levels
 template <int T, class Team>
 BMPC_HD void bmpc_tile_adapt(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, BmpcTile<T>& S) {
-    const double *lo0 = sys + o.lo0, *hi0 = sys + o.hi0, *rhov = sys + o.rho;
+    const double *lo0 = S.lo, *hi0 = S.hi, *rhov = S.rho;
     const double rho_e = sys[o.scal + BMPC_S_RHOE];
     const bool soft_on = rho_e > 0.0;
     for (int e = t.tid; e < T; e += t.n) S.nlvl[e] = bmpc_next_level(S.res + e * 4, S.lvl[e]);

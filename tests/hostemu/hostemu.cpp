@@ -140,6 +140,7 @@ extern "C" void emu_tile_compare(int nx, int nu, int Np, int Nc, const double* s
     BmpcTile<T> S; S.carve(sm, d);
     for (int e = 0; e < T; e++) { S.inst[e] = e; S.lvl[e] = lvl_in[e]; for (int q = 0; q < nu; q++) S.um1[e * nu + q] = um1[e * nu + q]; }
     bmpc_tile_load_phi(t, d, sys + o.Bcal, S.phi1, S.phi2);
+    bmpc_tile_load_rows(t, d, o, sys, S.lo, S.hi, S.rho);
     bmpc_tile_prep(t, d, o, sys, S, x0, xref, xref_mode);
     for (int e = 0; e < T; e++) {
         for (int a = 0; a < d.NU; a++) S.x[a * T + e] = cold ? 0.0 : x_in[e * d.NU + a];
