@@ -196,7 +196,7 @@ __global__ void k_admm(BmpcDims d, BmpcSysOff o, const double* __restrict__ sys,
 
 // K3+K4 for large shapes: one CTA per TILE of T instances (bmpc_tile.cuh).  Same contract as k_admm.
 template <int T, int NS>
-__global__ void k_admm_tile(BmpcDims d, BmpcSysOff o, const double* __restrict__ sys, BmpcInst I, const int32_t* __restrict__ list,
+__global__ void __launch_bounds__(NS >= 4 ? 768 : 512) k_admm_tile(BmpcDims d, BmpcSysOff o, const double* __restrict__ sys, BmpcInst I, const int32_t* __restrict__ list,
                             int count, int niter, int do_prep, int cold, int xref_mode, int adapt) {
     extern __shared__ double smem[];
     __shared__ double sd[32];
@@ -581,6 +581,7 @@ struct bmpc_handle {
     // low-latency CTA-per-instance variant for the few stragglers of a warp-team / TPI handle
     int fb_team = 0, fb_rmax = 0; size_t fb_smem_admm = 0, fb_smem_polish = 0;
     int rmax_small = 0; size_t smem_polish_small = 0; int32_t* ovf = nullptr;   // small-capacity polish tier (CTA teams) + its overflow list
+    int sm_count = 148;
     int tile_T = 0, tile_threads = 0;                  // > 0: the ADMM of this shape runs on tiles of T instances per CTA
     struct { const int32_t* list; int count; int32_t *cur, *nxt; int total, chunk, round; bool need_prep; } st = {};
     bool pending = false;              // a round is in flight and has not been retired by the host yet
@@ -670,6 +671,7 @@ static int configure_launch(bmpc_handle* h) {
     const BmpcDims& d = h->d;
     int dev = h->cfg.device, max_optin = 0;
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
     size_t budget = (size_t)max_optin - 1024;
     int team = h->cfg.team_threads;
     if (team <= 0) team = (d.mc <= 192 && d.NU <= 64) ? 32 : 256;
@@ -704,15 +706,15 @@ static int configure_launch(bmpc_handle* h) {
         // large shapes with one shared system: the ADMM runs on tiles of T instances per CTA (bmpc_tile.cuh)
         h->tile_T = 0;
         if (h->cfg.team_threads == 0 && h->cfg.n_sys <= 1) {
-            if (bmpc_tile_smem_doubles(d, 8) * 8 <= budget) {
-                h->tile_T = 8;
-                BMPC_CUDA(cudaFuncSetAttribute(k_admm_tile<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bmpc_tile_smem_doubles(d, 8) * 8)));
-            } else if (bmpc_tile_smem_doubles(d, 4) * 8 <= budget) {
-                h->tile_T = 4;
-                BMPC_CUDA(cudaFuncSetAttribute(k_admm_tile<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bmpc_tile_smem_doubles(d, 4) * 8)));
-            }
+            for (int T : {8, 4, 2}) if (!h->tile_T && bmpc_tile_smem_doubles(d, T) * 8 <= budget) h->tile_T = T;
+            if (h->tile_T >= 8) BMPC_CUDA(cudaFuncSetAttribute(k_admm_tile<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bmpc_tile_smem_doubles(d, 8) * 8)));
+            if (h->tile_T >= 8) BMPC_CUDA(cudaFuncSetAttribute(k_admm_tile<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bmpc_tile_smem_doubles(d, 8) * 8)));
+            if (h->tile_T >= 4) BMPC_CUDA(cudaFuncSetAttribute(k_admm_tile<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bmpc_tile_smem_doubles(d, 4) * 8)));
+            if (h->tile_T >= 2) BMPC_CUDA(cudaFuncSetAttribute(k_admm_tile<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bmpc_tile_smem_doubles(d, 2) * 8)));
             int th = d.NX > 2 * d.NU ? d.NX : 2 * d.NU;
             th = ((th + 31) / 32) * 32; if (th < 128) th = 128; if (th > 512) th = 512;
+            if (h->cfg.warps_per_block > 0) th = h->cfg.warps_per_block * 32;      // tuning override
+            if (th > 768) th = 768;
             h->tile_threads = th;
         }
         if (h->cfg.rmax == 0 && rmax > 96) { h->rmax_small = 80; h->smem_polish_small = polish_smem_doubles(d, 80) * 8; }
@@ -926,10 +928,17 @@ static void launch_admm(bmpc_handle* h, const int32_t* list, int count, int nite
     } else if (h->team == 32) {
         int grid = (count + h->wpb - 1) / h->wpb;
         k_admm<true><<<grid, h->wpb * 32, h->smem_admm, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
-    } else if (h->tile_T == 8) {
+    } else if (h->tile_T == 8 && count > 2 * h->sm_count * 8) {
+        // throughput tiles: 8 instances share every K^-1 entry
+        if (h->tile_threads >= 4 * h->d.NU)
+            k_admm_tile<8, 4><<<(count + 7) / 8, h->tile_threads, bmpc_tile_smem_doubles(h->d, 8) * 8, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
+        else
         k_admm_tile<8, 2><<<(count + 7) / 8, h->tile_threads, bmpc_tile_smem_doubles(h->d, 8) * 8, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
-    } else if (h->tile_T == 4) {
+    } else if (h->tile_T >= 4 && count > 2 * h->sm_count * 2) {
         k_admm_tile<4, 2><<<(count + 3) / 4, h->tile_threads, bmpc_tile_smem_doubles(h->d, 4) * 8, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
+    } else if (h->tile_T > 0) {
+        // few instances left (straggler rounds): small tiles, more CTAs, a shorter dependent chain per iteration
+        k_admm_tile<2, 1><<<(count + 1) / 2, h->tile_threads, bmpc_tile_smem_doubles(h->d, 2) * 8, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
     } else {
         k_admm<false><<<count, h->team, h->smem_admm, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
     }

@@ -103,7 +103,12 @@ struct BmpcTile {
 };
 
 // `niter` ADMM iterations for the T instances of a tile.  NS = how many threads share one output row (each takes
-// T/NS instances).  On return S.res holds the residuals of the last iteration (as bmpc_admm_rows reports them).
+// TG = T/NS instances).  On return S.res holds the residuals of the last iteration (as bmpc_admm_rows reports them).
+// Three barriers per iteration:
+//   B   r  = sigma x - g + A' w                (x first takes the relaxation step of the previous iteration)
+//   C   xt = Kinv[level] r
+//   D   zt = A xt + cc row by row, in registers; v += alpha (zt - prox(v)); then straight away the next iteration's
+//       w = rho (2 prox(v) - v - cc) for the same element (no separate pass, no extra barrier)
 template <int T, int NS, class Team>
 BMPC_HD void bmpc_admm_tile(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, BmpcTile<T>& S, int niter) {
     constexpr int TG = T / NS;
@@ -120,7 +125,7 @@ BMPC_HD void bmpc_admm_tile(Team& t, const BmpcDims& d, const BmpcSysOff& o, con
         for (int e = 0; e < TG; e++) acc[e] = 0.0;
         for (int k = Np; k > j; k--) {                     // descending: every lane of a warp reads the same w rows (broadcast)
             const double* blk = S.phi2 + bmpc_tile_block(d, k, j) * s2 + q;
-            const double* wk = ww + (size_t)(k * nx) * T + sg * TG;
+            const double* wk = ww + (k * nx) * T + sg * TG;
             for (int c = 0; c < nx; c++) {
                 const double m = blk[c * nu]; double wv[TG];
                 bmpc_ldv<TG>(wk + c * T, wv);
@@ -128,69 +133,93 @@ BMPC_HD void bmpc_admm_tile(Team& t, const BmpcDims& d, const BmpcSysOff& o, con
                 for (int e = 0; e < TG; e++) acc[e] = fma(m, wv[e], acc[e]);
             }
         }
-        const double* wu = ww + (size_t)(NX + a) * T + sg * TG;
-        const double* wd = ww + (size_t)(NX + NU) * T + sg * TG;
+        const double* wu = ww + (NX + a) * T + sg * TG;
+        const double* wd = ww + (NX + NU) * T + sg * TG;
 #pragma unroll
         for (int e = 0; e < TG; e++) {
-            double s = wu[e] - wd[(size_t)(nu + a) * T + e];
-            if (a < nu) s += wd[(size_t)a * T + e];
-            if (a >= 1) s += wd[(size_t)(nu + a - 1) * T + e];
-            acc[e] += s;
+            double sm = wu[e] - wd[(nu + a) * T + e];
+            if (a < nu) sm += wd[a * T + e];
+            if (a >= 1) sm += wd[(nu + a - 1) * T + e];
+            acc[e] += sm;
         }
     };
     // out_a = sum_b Msym[b*NU + a] in[b]   (symmetric matrix streamed from global memory, coalesced over a)
     auto symv = [&](const double* Msym, const double* in, int a, int sg, double* acc) {
         for (int e = 0; e < TG; e++) acc[e] = 0.0;
-        const double* col = Msym + a;
+        const double* pm = Msym + a;
         const double* iv = in + sg * TG;
         int b = 0;
-        for (; b + 8 <= NU; b += 8) {                      // 8 matrix loads in flight per thread
+        for (; b + 8 <= NU; b += 8, pm += 8 * NU, iv += 8 * T) {    // 8 matrix loads in flight per thread
             double m[8];
 #pragma unroll
-            for (int u = 0; u < 8; u++) m[u] = col[(size_t)(b + u) * NU];
+            for (int u = 0; u < 8; u++) m[u] = pm[u * NU];
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 double rv[TG];
-                bmpc_ldv<TG>(iv + (size_t)(b + u) * T, rv);
+                bmpc_ldv<TG>(iv + u * T, rv);
 #pragma unroll
                 for (int e = 0; e < TG; e++) acc[e] = fma(m[u], rv[e], acc[e]);
             }
         }
-        for (; b < NU; b++) {
-            const double m0 = col[(size_t)b * NU]; double rv[TG];
-            bmpc_ldv<TG>(iv + (size_t)b * T, rv);
+        for (; b < NU; b++, pm += NU, iv += T) {
+            const double m0 = pm[0]; double rv[TG];
+            bmpc_ldv<TG>(iv, rv);
 #pragma unroll
             for (int e = 0; e < TG; e++) acc[e] = fma(m0, rv[e], acc[e]);
         }
     };
     auto row_prox = [&](int i, int e, double vi, double& rho) {
-        double lo, hi; bmpc_row_bounds(d, lo0, hi0, S.um1 + e * nu, i, lo, hi);
+        double lo = lo0[i], hi = hi0[i];
+        const int rr = i - (NX + NU);
+        if (rr >= 0 && rr < nu) { const double um = S.um1[e * nu + rr]; lo += um; hi += um; }
         rho = S.fac[e] * rhov[i];
         return bmpc_prox(vi, lo, hi, soft_on && i < NX, rho, rho_e);
     };
+    // one row element: relaxation step of v with this iteration's zt, then either the next iteration's w or (last
+    // iteration) the residual bookkeeping
+    auto row_step = [&](int i, int e, int p, double zt, bool last) {
+        const double vi = v[p]; double rho;
+        const double z = row_prox(i, e, vi, rho);
+        const double dz = zt - z, vn = vi + alpha * dz;
+        v[p] = vn;
+        if (last) {
+            BMPC_TILE_MAX(S.res + e * 4 + 0, fabs(dz));
+            BMPC_TILE_MAX(S.res + e * 4 + 2, fmax(fabs(zt), fabs(z)));
+            w[p] = rho * dz;
+        } else {
+            const double zn = row_prox(i, e, vn, rho);
+            w[p] = rho * (2.0 * zn - vn - (i < NX ? cc[p] : 0.0));
+        }
+    };
+
     for (int e = t.tid; e < 4 * T; e += t.n) S.res[e] = 0.0;
     for (int e = t.tid; e < T; e += t.n) S.fac[e] = bmpc_level_factor(S.lvl[e]);
     t.sync();
     // levels present in this tile
     unsigned lmask = 0;
     for (int e = 0; e < T; e++) lmask |= 1u << S.lvl[e];
+    // w of the first iteration
+    for (int idx = t.tid; idx < mc * T; idx += t.n) {
+        const int i = idx / T, e = idx % T;
+        const double vi = v[idx]; double rho;
+        const double z = row_prox(i, e, vi, rho);
+        w[idx] = rho * (2.0 * z - vi - (i < NX ? cc[idx] : 0.0));
+    }
+    t.sync();
 
     for (int it = 0; it < niter; it++) {
         const bool last = (it == niter - 1);
-        // A: rows  w = rho (2 prox(v) - v - cc)
-        for (int idx = t.tid; idx < mc * T; idx += t.n) {
-            const int i = idx / T, e = idx % T;
-            const double vi = v[idx]; double rho;
-            const double z = row_prox(i, e, vi, rho);
-            w[idx] = rho * (2.0 * z - vi - (i < NX ? cc[idx] : 0.0));
-        }
-        t.sync();
         // B: r = sigma x - g + A' w
         for (int wk = t.tid; wk < NU * NS; wk += t.n) {
             const int a = wk / NS, sg = wk % NS; double acc[TG];
             ATw(w, a, sg, acc);
 #pragma unroll
-            for (int e = 0; e < TG; e++) { const size_t p = (size_t)a * T + sg * TG + e; r[p] = sigma * x[p] - g[p] + acc[e]; }
+            for (int e = 0; e < TG; e++) {
+                const int p = a * T + sg * TG + e;
+                double xa = x[p];
+                if (it > 0) { xa += alpha * (xt[p] - xa); x[p] = xa; }
+                r[p] = sigma * xa - g[p] + acc[e];
+            }
         }
         t.sync();
         // C: xt = Kinv[level] r, level by level
@@ -201,83 +230,71 @@ BMPC_HD void bmpc_admm_tile(Team& t, const BmpcDims& d, const BmpcSysOff& o, con
                 const int a = wk / NS, sg = wk % NS; double acc[TG];
                 symv(Kinv, r, a, sg, acc);
 #pragma unroll
-                for (int e = 0; e < TG; e++) if (S.lvl[sg * TG + e] == L) xt[(size_t)a * T + sg * TG + e] = acc[e];
+                for (int e = 0; e < TG; e++) if (S.lvl[sg * TG + e] == L) xt[a * T + sg * TG + e] = acc[e];
             }
         }
         t.sync();
-        // D1: zt on the state rows (kept in w, which is dead now): row (k,c) = cc + sum_{j<min(k,Nc)} block(k,j)[c,:] xt_j
-        for (int i = t.tid; i < NX; i += t.n) {
-            const int k = i / nx, c = i % nx;
-            double acc[T];
-            bmpc_ldv<T>(cc + (size_t)i * T, acc);
+        // D: state rows: zt = cc + sum_{j<min(k,Nc)} block(k,j)[c,:] xt_j in registers, then the row step
+        for (int wk = t.tid; wk < NX * NS; wk += t.n) {
+            const int i = wk / NS, sg = wk % NS, k = i / nx, c = i % nx;
+            double acc[TG];
+            bmpc_ldv<TG>(cc + i * T + sg * TG, acc);
             const int jend = k < Nc ? k : Nc;
             for (int j = 0; j < jend; j++) {
                 const double* blk = S.phi1 + bmpc_tile_block(d, k, j) * s1 + c;
-                const double* xj = xt + (size_t)(j * nu) * T;
+                const double* xj = xt + (j * nu) * T + sg * TG;
                 for (int q = 0; q < nu; q++) {
-                    const double m = blk[q * nx]; double xv[T];
-                    bmpc_ldv<T>(xj + q * T, xv);
+                    const double m = blk[q * nx]; double xv[TG];
+                    bmpc_ldv<TG>(xj + q * T, xv);
 #pragma unroll
-                    for (int e = 0; e < T; e++) acc[e] = fma(m, xv[e], acc[e]);
+                    for (int e = 0; e < TG; e++) acc[e] = fma(m, xv[e], acc[e]);
                 }
             }
 #pragma unroll
-            for (int e = 0; e < T; e++) w[(size_t)i * T + e] = acc[e];
+            for (int e = 0; e < TG; e++) row_step(i, sg * TG + e, i * T + sg * TG + e, acc[e], last);
         }
-        t.sync();
-        // D2: rows  v += alpha (zt - prox(v))
-        for (int idx = t.tid; idx < mc * T; idx += t.n) {
+        //    input rows and the reference's delta-u rows
+        for (int idx = NX * T + t.tid; idx < mc * T; idx += t.n) {
             const int i = idx / T, e = idx % T;
-            const double vi = v[idx]; double rho;
-            const double z = row_prox(i, e, vi, rho);
             double zt;
-            if (i < NX) zt = w[idx];
-            else if (i < NX + NU) zt = xt[(size_t)(i - NX) * T + e];
+            if (i < NX + NU) zt = xt[(i - NX) * T + e];
             else {
                 const int rr = i - NX - NU;
-                if (rr < nu) zt = xt[(size_t)rr * T + e];
-                else { const int q2 = rr - nu; zt = -xt[(size_t)q2 * T + e] + (q2 + 1 < NU ? xt[(size_t)(q2 + 1) * T + e] : 0.0); }
+                if (rr < nu) zt = xt[rr * T + e];
+                else { const int q2 = rr - nu; zt = -xt[q2 * T + e] + (q2 + 1 < NU ? xt[(q2 + 1) * T + e] : 0.0); }
             }
-            const double dz = zt - z;
-            v[idx] = vi + alpha * dz;
-            if (last) {
-                BMPC_TILE_MAX(S.res + e * 4 + 0, fabs(dz));
-                BMPC_TILE_MAX(S.res + e * 4 + 2, fmax(fabs(zt), fabs(z)));
-                w[idx] = rho * dz;
-            }
+            row_step(i, e, idx, zt, last);
         }
-        if (last) {
-            t.sync();
-            // r_dual = ||sigma (xt - x) + A' rho (zt - z)||, normalisers ||g||, ||H xt||, ||A' y||
-            for (int wk = t.tid; wk < NU * NS; wk += t.n) {
-                const int a = wk / NS, sg = wk % NS; double acc[TG], hx[TG];
-                ATw(w, a, sg, acc);
-                symv(H, xt, a, sg, hx);
-#pragma unroll
-                for (int e = 0; e < TG; e++) {
-                    const size_t p = (size_t)a * T + sg * TG + e;
-                    BMPC_TILE_MAX(S.res + (sg * TG + e) * 4 + 1, fabs(sigma * (xt[p] - x[p]) + acc[e]));
-                    BMPC_TILE_MAX(S.res + (sg * TG + e) * 4 + 3, fmax(fabs(hx[e]), fabs(g[p])));
-                }
-            }
-            t.sync();
-            for (int idx = t.tid; idx < mc * T; idx += t.n) {
-                const int i = idx / T, e = idx % T;
-                const double vi = v[idx]; double rho;
-                const double z = row_prox(i, e, vi, rho);
-                w[idx] = rho * (vi - z);
-            }
-            t.sync();
-            for (int wk = t.tid; wk < NU * NS; wk += t.n) {
-                const int a = wk / NS, sg = wk % NS; double acc[TG];
-                ATw(w, a, sg, acc);
-#pragma unroll
-                for (int e = 0; e < TG; e++) BMPC_TILE_MAX(S.res + (sg * TG + e) * 4 + 3, fabs(acc[e]));
-            }
-        }
-        for (int idx = t.tid; idx < NU * T; idx += t.n) x[idx] += alpha * (xt[idx] - x[idx]);
         t.sync();
     }
+    // residuals of the last iteration: r_dual = ||sigma (xt - x) + A' rho (zt - z)||, normalisers ||g||, ||H xt||, ||A' y||
+    for (int wk = t.tid; wk < NU * NS; wk += t.n) {
+        const int a = wk / NS, sg = wk % NS; double acc[TG], hx[TG];
+        ATw(w, a, sg, acc);
+        symv(H, xt, a, sg, hx);
+#pragma unroll
+        for (int e = 0; e < TG; e++) {
+            const int p = a * T + sg * TG + e;
+            BMPC_TILE_MAX(S.res + (sg * TG + e) * 4 + 1, fabs(sigma * (xt[p] - x[p]) + acc[e]));
+            BMPC_TILE_MAX(S.res + (sg * TG + e) * 4 + 3, fmax(fabs(hx[e]), fabs(g[p])));
+        }
+    }
+    t.sync();
+    for (int idx = t.tid; idx < mc * T; idx += t.n) {
+        const int i = idx / T, e = idx % T;
+        const double vi = v[idx]; double rho;
+        const double z = row_prox(i, e, vi, rho);
+        w[idx] = rho * (vi - z);
+    }
+    t.sync();
+    for (int wk = t.tid; wk < NU * NS; wk += t.n) {
+        const int a = wk / NS, sg = wk % NS; double acc[TG];
+        ATw(w, a, sg, acc);
+#pragma unroll
+        for (int e = 0; e < TG; e++) BMPC_TILE_MAX(S.res + (sg * TG + e) * 4 + 3, fabs(acc[e]));
+    }
+    for (int idx = t.tid; idx < NU * T; idx += t.n) x[idx] += alpha * (xt[idx] - x[idx]);
+    t.sync();
 }
 
 // adaptive-rho move for every instance of the tile (v rescaled so that (z, y) are unchanged); S.nlvl = new levels
