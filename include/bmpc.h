@@ -35,6 +35,7 @@ typedef enum {
 enum {
     BMPC_SOLVED = 1,            /* KKT-verified minimiser (polished)            -> reference 'solved' */
     BMPC_SOLVED_UNPOLISHED = 2, /* ADMM met eps_abs/eps_rel (OSQP's criterion), polish not verified -> 'solved' */
+    BMPC_PRIMAL_INFEASIBLE = -3, /* OSQP 'primal infeasible' (certificate found on the hard rows) -> reference falls back to u_failure */
     BMPC_MAX_ITER = -2,         /* OSQP 'maximum iterations reached'            -> reference falls back to u_failure */
     BMPC_UNSOLVED = -10
 };

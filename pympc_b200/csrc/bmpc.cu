@@ -291,8 +291,7 @@ __global__ void k_polish(BmpcDims d, BmpcSysOff o, const double* __restrict__ sy
             if (t.tid == 0) {
                 int used = (ps < 0 ? 1 : max_steps);
                 I.psteps[inst] += used; atomicAdd(next_count + 1, used);
-                int pos = atomicAdd(next_count, 1);
-                next_list[pos] = inst;
+                if (I.status[inst] != BMPC_PRIMAL_INFEASIBLE) { int pos = atomicAdd(next_count, 1); next_list[pos] = inst; }   // a certified instance is finished
             }
         }
     };
@@ -310,9 +309,67 @@ __global__ void k_finalize(BmpcDims d, BmpcSysOff o, const double* __restrict__ 
     sys += (size_t)inst * I.sys_stride;
     const double* res = I.res + (size_t)inst * 4;
     bool conv = res[0] <= eps_abs + eps_rel * res[2] && res[1] <= eps_abs + eps_rel * res[3];
+    if (I.status[inst] == BMPC_PRIMAL_INFEASIBLE) return;               // certified: status and u_failure already written
     I.status[inst] = conv ? BMPC_SOLVED_UNPOLISHED : BMPC_MAX_ITER;
     for (int a = 0; a < d.NU; a++) I.Us[(size_t)inst * d.NU + a] = I.Ua[(size_t)inst * d.NU + a];
     for (int q = 0; q < d.nu; q++) bmpc_publish_u0(I, u0_out, (size_t)inst * d.nu + q, conv ? I.Ua[(size_t)inst * d.NU + q] : sys[o.uref + q]);
+}
+
+
+// ---- primal infeasibility (OSQP paper 3.4), checked on straggler rounds only: the change of the multipliers y over one
+// ADMM round, projected like OSQP does, is a certificate when A' dy ~ 0 and the support function of the row box is negative.
+// Soft rows are penalties, not constraints: they stay out.  k_snapshot keeps (v, level) of the listed instances before the
+// round; k_infeas compares with the state after it.
+__global__ void k_snapshot(BmpcDims d, BmpcInst I, const int32_t* __restrict__ list, int count, double* vprev, int32_t* lprev) {
+    const int idx = blockIdx.x;
+    if (idx >= count) return;
+    const int inst = list ? list[idx] : idx;
+    for (int i = threadIdx.x; i < d.mc; i += blockDim.x) vprev[(size_t)inst * d.mc + i] = I.vw[(size_t)inst * d.mc + i];
+    if (threadIdx.x == 0) lprev[inst] = I.lvl[inst];
+}
+
+__global__ void k_infeas(BmpcDims d, BmpcSysOff o, const double* __restrict__ sys, BmpcInst I, const int32_t* __restrict__ list, int count,
+                         const double* __restrict__ vprev, const int32_t* __restrict__ lprev, double eps_pinf, double* u0_out) {
+    extern __shared__ double smem[];
+    __shared__ double sd[32];
+    __shared__ int si[32];
+    const int idx = blockIdx.x;
+    if (idx >= count) return;
+    const int inst = list ? list[idx] : idx;
+    sys += (size_t)inst * I.sys_stride;
+    BlockTeam t(sd, si);
+    double* dy = smem; double* um1 = dy + d.mc;
+    const double *lo0 = sys + o.lo0, *hi0 = sys + o.hi0, *rhov = sys + o.rho, *Bcal = sys + o.Bcal;
+    const double rho_e = sys[o.scal + BMPC_S_RHOE];
+    const bool soft_on = rho_e > 0.0;
+    for (int q = t.tid; q < d.nu; q += t.n) um1[q] = I.um1[(size_t)inst * d.nu + q];
+    t.sync();
+    const double f0 = bmpc_level_factor(lprev[inst]), f1 = bmpc_level_factor(I.lvl[inst]);
+    double ln = 0.0, ls = 0.0;
+    for (int i = t.tid; i < d.mc; i += t.n) {
+        double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
+        const bool soft = soft_on && i < d.NX;
+        const double v0 = vprev[(size_t)inst * d.mc + i], v1 = I.vw[(size_t)inst * d.mc + i];
+        const double r0 = f0 * rhov[i], r1 = f1 * rhov[i];
+        double dyi = soft ? 0.0 : r1 * (v1 - bmpc_prox(v1, lo, hi, false, r1, rho_e)) - r0 * (v0 - bmpc_prox(v0, lo, hi, false, r0, rho_e));
+        if (hi > 1e29 && dyi > 0.0) dyi = 0.0;           // projection on the polar of the recession cone of [lo, hi]
+        if (lo < -1e29 && dyi < 0.0) dyi = 0.0;
+        dy[i] = dyi;
+        ln = fmax(ln, fabs(dyi));
+        // rows are z = A U + cc: the box of A U alone is [lo - cc, hi - cc]
+        const double ci = i < d.NX ? I.cc[(size_t)inst * d.NX + i] : 0.0;
+        ls += dyi > 0.0 ? (hi - ci) * dyi : (dyi < 0.0 ? (lo - ci) * dyi : 0.0);
+    }
+    const double ndy = t.max(ln);
+    const double supp = t.sum(ls);
+    if (!(ndy > 1e-30) || !(supp < -eps_pinf * ndy)) return;
+    double la = 0.0;
+    for (int a = t.tid; a < d.NU; a += t.n) la = fmax(la, fabs(bmpc_ATcol_dot(d, Bcal, dy, a)));
+    const double nat = t.max(la);
+    if (nat < eps_pinf * ndy) {
+        if (t.tid == 0) I.status[inst] = BMPC_PRIMAL_INFEASIBLE;
+        for (int q = t.tid; q < d.nu; q += t.n) bmpc_publish_u0(I, u0_out, (size_t)inst * d.nu + q, sys[o.uref + q]);
+    }
 }
 
 // pure-ADMM mode: list of instances not yet converged by OSQP's criterion
@@ -323,7 +380,7 @@ __global__ void k_check_converged(BmpcInst I, const int32_t* __restrict__ list, 
     const int inst = list ? list[idx] : idx;
     const double* res = I.res + (size_t)inst * 4;
     bool conv = res[0] <= eps_abs + eps_rel * res[2] && res[1] <= eps_abs + eps_rel * res[3];
-    if (!conv) { int pos = atomicAdd(next_count, 1); next_list[pos] = inst; }
+    if (!conv && I.status[inst] != BMPC_PRIMAL_INFEASIBLE) { int pos = atomicAdd(next_count, 1); next_list[pos] = inst; }
 }
 
 __global__ void k_reset(BmpcInst I, int B) {
@@ -492,7 +549,7 @@ __device__ __forceinline__ bool tpi_polish_thread(const TpiRicParams<S>& P, Bmpc
         atomicAdd(next_count + 1, ps);
     } else {
         I.psteps[inst] += max_steps; atomicAdd(next_count + 1, max_steps);
-        next_list[atomicAdd(next_count, 1)] = inst;
+        if (I.status[inst] != BMPC_PRIMAL_INFEASIBLE) next_list[atomicAdd(next_count, 1)] = inst;
     }
     return ps > 0;
 }
@@ -582,6 +639,7 @@ struct bmpc_handle {
     int fb_team = 0, fb_rmax = 0; size_t fb_smem_admm = 0, fb_smem_polish = 0;
     int rmax_small = 0; size_t smem_polish_small = 0; int32_t* ovf = nullptr;   // small-capacity polish tier (CTA teams) + its overflow list
     int sm_count = 148;
+    double* vprev = nullptr; int32_t* lprev = nullptr;   // snapshot of (v, level) for the infeasibility check of straggler rounds
     int tile_T = 0, tile_threads = 0;                  // > 0: the ADMM of this shape runs on tiles of T instances per CTA
     struct { const int32_t* list; int count; int32_t *cur, *nxt; int total, chunk, round; bool need_prep; } st = {};
     bool pending = false;              // a round is in flight and has not been retired by the host yet
@@ -778,6 +836,8 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     ok &= dalloc((void**)&h->listB, sizeof(int32_t) * B);
     ok &= dalloc((void**)&h->counts, sizeof(int32_t) * 4);
     ok &= dalloc((void**)&h->ovf, sizeof(int32_t) * (size_t)B);
+    ok &= dalloc((void**)&h->vprev, sizeof(double) * (size_t)B * d.mc);
+    ok &= dalloc((void**)&h->lprev, sizeof(int32_t) * (size_t)B);
     if (!ok) { h->err = "cudaMalloc failed"; cudaGetLastError(); return fail(BMPC_ERR_CUDA); }
     if (cudaHostAlloc((void**)&h->h_count, sizeof(int32_t) * 4, cudaHostAllocDefault) != cudaSuccess) { h->err = "cudaHostAlloc failed"; return fail(BMPC_ERR_CUDA); }
     cudaMemset(h->sys, 0, sizeof(double) * (size_t)h->o.total * h->cfg.n_sys);
@@ -800,7 +860,7 @@ void bmpc_destroy(bmpc_handle* h) {
     cudaSetDevice(h->cfg.device);
     if (h->pending) cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->sys, h->x0, h->um1, h->um1_solved, h->xref, h->u0_own, h->I.g, h->I.cc, h->I.xw, h->I.vw, h->I.Ua, h->I.Us, h->I.res,
-                    h->I.status, h->I.iters, h->I.psteps, h->I.lvl, h->listA, h->listB, h->counts, h->ovf, h->seq_x, h->seq_e, h->seq_obj};
+                    h->I.status, h->I.iters, h->I.psteps, h->I.lvl, h->listA, h->listB, h->counts, h->ovf, h->vprev, h->lprev, h->seq_x, h->seq_e, h->seq_obj};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_count) cudaFreeHost(h->h_count);
     free(h->tpi_admm_params); free(h->tpi_polish_params);
@@ -985,8 +1045,15 @@ static int enqueue_round(bmpc_handle* h) {
     if (tpi) {
         g_tpi_table[h->tpi_kind - 1].launch(h, st.list, st.count, st.chunk, st.nxt, h->ev[1]);
     } else {
+        // infeasible instances never pass the polish: from the third round on, look for OSQP's certificate
+        const bool chk = st.total >= 25 && st.list != nullptr;
+        if (chk) { k_snapshot<<<st.count, 128, 0, h->stream>>>(h->d, h->I, st.list, st.count, h->vprev, h->lprev); h->stats.launches++; }
         launch_admm(h, st.list, st.count, st.chunk, st.need_prep ? 1 : 0);
         st.need_prep = false;
+        if (chk) {
+            k_infeas<<<st.count, 128, sizeof(double) * (h->d.mc + h->d.nu + 2), h->stream>>>(h->d, h->o, h->sys, h->I, st.list, st.count, h->vprev, h->lprev, 1e-4, h->I.u0);
+            h->stats.launches++;
+        }
         BMPC_CUDA(cudaEventRecord(h->ev[1], h->stream));
         // stragglers of a fast-path shape: the Riccati polish (list mode) has ~3x lower latency than the team Schur polish
         if (h->cfg.polish && h->tpi_kind && h->xref_mode == 0 && st.total + st.chunk <= 200)

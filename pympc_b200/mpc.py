@@ -26,7 +26,7 @@ import numpy as np
 from . import _lib
 from ._lib import BmpcConfig, BmpcError, BmpcStats, PinnedArray, ptr
 
-_STATUS_STR = {1: "solved", 2: "solved", -2: "maximum iterations reached", -10: "unsolved"}
+_STATUS_STR = {1: "solved", 2: "solved", -2: "maximum iterations reached", -3: "primal infeasible", -10: "unsolved"}
 
 
 def __is_vector__(vec):

@@ -366,3 +366,44 @@ def test_other_compiled_fast_path_shape(MPC):
         traj[fast] = np.array(us)
         K.close()
     assert np.max(np.abs(traj[1] - traj[0])) < TOL
+
+
+def test_infeasible_instances_fall_back_to_u_failure(MPC, osqp_port_lib):
+    """u_-1 outside what the input box and the delta-u box allow together makes the QP infeasible (the state rows are
+    soft, the input rows are not).  OSQP ends such a problem as 'primal infeasible' or, when the certificate is slow to
+    emerge (this one: the restatement of OSQP runs into max_iter), 'maximum iterations reached'; either way the reference
+    falls back to u_failure (mpc.py:301-304).  Same here for exactly the infeasible instances of a mixed batch, the
+    feasible ones are solved as usual.  Both kernel families (fast path / team kernels)."""
+    import warnings
+    from oracle.qp_assembly import QPData
+    from oracle.osqp_port import OSQP
+    cfg = pendulum(); g = golden("pend_first.npz")
+    B = 64; bad = np.arange(B) % 7 == 3
+    Um1 = np.zeros((B, 1)); Um1[bad] = 30.0                       # umax = 20, Dumin = -5  ->  u0 >= 25 > 20
+    Q = QPData(**dict(cfg, uminus1=np.array([30.0])))
+    m = OSQP(); m.setup(P=Q.to_csc()[0], q=Q.q, A=Q.to_csc()[1], l=Q.l, u=Q.u, verbose=False)
+    assert m.solve().info.status in ("primal infeasible", "maximum iterations reached")
+    for fast in (1, 0):
+        K = MPC(**dict(cfg, x0=np.tile(cfg["x0"], (B, 1)), xref=np.tile(cfg["xref"], (B, 1)), uminus1=Um1), batch=B, fast_path=fast)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            K.setup(); U = K.output()
+        st = K.res.info.status_val
+        assert np.isin(st[bad], (-3, -2)).all() and (st[~bad] == 1).all(), (fast, st)
+        assert np.all(U[bad] == 0.0)                               # u_failure = uref = 0
+        assert np.max(np.abs(U[~bad, 0] - g["u_seq"][0])) < TOL
+        K.close()
+
+
+def test_primal_infeasible_hard_state_rows(MPC):
+    """SOFT_ON = False (the mpc_no_slack QP): an initial state outside the hard state box has no feasible trajectory."""
+    import warnings
+    cfg = point_mass(); cfg["xmax"] = np.array([3.0, 100.0])
+    K = MPC(**dict(cfg, x0=np.array([3.5, 0.0]))); K.SOFT_ON = False
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        K.setup(); u, info = K.output(return_status=True)
+    assert info["status"] == "primal infeasible"                   # OSQP's certificate (the OSQP restatement finds it too)
+    assert np.all(u == K.u_failure)
+    assert K.stats()["admm_iters"] < 4000                          # certified, not run into max_iter
+    K.close()
