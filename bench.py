@@ -95,7 +95,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
-def cpu_arm(steps, warmup, sample_b, workload, threads=None):
+def cpu_arm(steps, warmup, sample_b, workload, threads=None, **settings):
     """Closed-loop steps of the oracle's C restatement of OSQP (one solver object per instance, OpenMP over
     instances, reference default eps=1e-3 like MPCController passes, mpc.py:266)."""
     from oracle.qp_assembly import QPData
@@ -103,7 +103,7 @@ def cpu_arm(steps, warmup, sample_b, workload, threads=None):
     osqp_port.build()
     cfg, X0, Xref = pendulum_batch(sample_b, workload)
     Q = QPData(**cfg)
-    bc = osqp_port.BatchCPU(Q, sample_b)                     # OSQP defaults: eps 1e-3, adaptive rho, warm start
+    bc = osqp_port.BatchCPU(Q, sample_b, **settings)         # OSQP defaults: eps 1e-3, adaptive rho, warm start
     X = X0.copy(); U = np.zeros((sample_b, 1))
     Ad, Bd = cfg["Ad"], cfg["Bd"]
     if threads is None:
@@ -133,7 +133,7 @@ def cpu_arm(steps, warmup, sample_b, workload, threads=None):
     bc.close()
     tot = float(np.sum(times))
     return {"value": sample_b * steps / tot, "unit": UNIT, "cores": int(threads), "kind": "port",
-            "sample": f"{sample_b} pendulum instances x {steps} closed-loop steps ({workload}), OSQP-port eps=1e-3, "
+            "sample": f"{sample_b} pendulum instances x {steps} closed-loop steps ({workload}), OSQP-port eps={settings.get('eps_abs', 1e-3):g}, "
                       f"mean {np.mean(iters):.0f} ADMM its/solve, solver-only (no Python per-instance overhead)",
             "ms_per_step": 1e3 * tot / steps}
 
@@ -150,7 +150,8 @@ def gpu_arm(args, rank, world, local_rank):
         dist.barrier()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    B = B_PER_GPU
+    # weak scaling (the contract's default): 65 536 instances per GPU; --scaling strong: BASELINE configs[4]'s 524 288 in total
+    B = B_PER_GPU if args.scaling == "weak" else (8 * B_PER_GPU) // world
     Btot = B * world
     s, e = shard_range(Btot, rank, world)
     cfgp, X0all, Xrefall = pendulum_batch(Btot, args.workload)
@@ -283,7 +284,7 @@ def gpu_arm(args, rank, world, local_rank):
     value = Btot * args.steps / (tot_ms_max * 1e-3)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": tot_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": tot_ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"inverted_pendulum nx=4 nu=1 Np=20, batch={B} per GPU ({args.workload} instances), "
                                "closed loop with the linear plant, warm start (BASELINE configs[1])",
@@ -317,6 +318,7 @@ def main():
     ap.add_argument("--workload", default="identical", choices=["identical", "random"])
     ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: 524 288 instances in total (configs[4])")
     ap.add_argument("--nccl-gather", action="store_true", help="use the NCCL all-gather instead of fused peer stores")
     args = ap.parse_args()
     if args.warmup < 3:
