@@ -46,6 +46,7 @@ struct WarpTeam {
     __device__ __forceinline__ int nwarps() const { return 1; }
     __device__ __forceinline__ int lane() const { return tid; }
     __device__ __forceinline__ int lanes() const { return 32; }
+    __device__ __forceinline__ void wsync() { __syncwarp(); }
     __device__ __forceinline__ double wsum(double v) { return sum(v); }
 };
 
@@ -90,6 +91,7 @@ struct BlockTeam {
     __device__ __forceinline__ int nwarps() const { return n >> 5; }
     __device__ __forceinline__ int lane() const { return tid & 31; }
     __device__ __forceinline__ int lanes() const { return 32; }
+    __device__ __forceinline__ void wsync() { __syncwarp(); }
     __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);

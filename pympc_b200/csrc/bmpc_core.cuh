@@ -96,6 +96,7 @@ struct SeqTeam {
     BMPC_HD int lane() const { return 0; }
     BMPC_HD int lanes() const { return 1; }
     BMPC_HD double wsum(double v) { return v; }
+    BMPC_HD void wsync() {}
 };
 
 // y_r = sum_{c in [c0(r), c1(r))} M[r*ld + c] x[c]; rows striped over the team's warps, columns over the lanes of a
@@ -668,37 +669,36 @@ BMPC_HD int bmpc_polish(Team& t, const BmpcDims& d, const BmpcSysOff& o, const d
                 S[e] = val;
             }
             t.sync();
-            // Cholesky S = L L' (lower, in place)
+            // S = L D L' (unit lower L).  The pivot column is left untouched and its scale 1/d_j kept aside (dv), so a column
+            // costs ONE barrier and one reciprocal (no square root, no scaling pass); rows go to warps, columns to lanes.
+            double* dv = zz;                                   // zz is free until the candidate rows are formed
             for (int j = 0; j < r; j++) {
                 double djj = S[BMPC_TRI(j, j)];
                 if (!(djj > 1e-300)) djj = 1e-300;           // dependent working rows: candidate will fail verification
-                double dj = sqrt(djj), dinv = 1.0 / dj;
-                t.sync();
-                for (int i = j + 1 + t.tid; i < r; i += t.n) S[BMPC_TRI(i, j)] *= dinv;
-                if (t.tid == 0) S[BMPC_TRI(j, j)] = dj;
-                t.sync();
-                for (int i = j + 1 + t.tid; i < r; i += t.n) {
-                    double lij = S[BMPC_TRI(i, j)];
-                    for (int k = j + 1; k <= i; k++) S[BMPC_TRI(i, k)] -= lij * S[BMPC_TRI(k, j)];
+                const double dinv = 1.0 / djj;
+                if (t.tid == 0) dv[j] = dinv;
+                for (int i = j + 1 + t.warp(); i < r; i += t.nwarps()) {
+                    const double lij = S[BMPC_TRI(i, j)] * dinv;
+                    for (int k = j + 1 + t.lane(); k <= i; k += t.lanes()) S[BMPC_TRI(i, k)] -= lij * S[BMPC_TRI(k, j)];
                 }
                 t.sync();
             }
-            // forward  L y = t
-            for (int j = 0; j < r; j++) {
-                double yj = tt[j] / S[BMPC_TRI(j, j)];
-                t.sync();
-                for (int i = j + 1 + t.tid; i < r; i += t.n) tt[i] -= S[BMPC_TRI(i, j)] * yj;
-                if (t.tid == 0) tt[j] = yj;
-                t.sync();
+            // triangular solves by one warp (warp-level barriers only): L y = t, z = D^-1 y, L' mu = z
+            if (t.warp() == 0) {
+                for (int j = 0; j < r; j++) {
+                    const double sj = dv[j] * tt[j];
+                    for (int i = j + 1 + t.lane(); i < r; i += t.lanes()) tt[i] -= S[BMPC_TRI(i, j)] * sj;
+                    t.wsync();
+                }
+                for (int j = t.lane(); j < r; j += t.lanes()) tt[j] *= dv[j];
+                t.wsync();
+                for (int j = r - 1; j > 0; j--) {
+                    const double mj = tt[j];
+                    for (int i = t.lane(); i < j; i += t.lanes()) tt[i] -= S[BMPC_TRI(j, i)] * dv[i] * mj;
+                    t.wsync();
+                }
             }
-            // backward L' mu = y
-            for (int j = r - 1; j >= 0; j--) {
-                double mj = tt[j] / S[BMPC_TRI(j, j)];
-                t.sync();
-                for (int i = t.tid; i < j; i += t.n) tt[i] -= S[BMPC_TRI(j, i)] * mj;
-                if (t.tid == 0) tt[j] = mj;
-                t.sync();
-            }
+            t.sync();
         }
         for (int i = t.tid; i < mc; i += t.n) murow[i] = 0.0;
         t.sync();
