@@ -197,7 +197,7 @@ __global__ void k_admm(BmpcDims d, BmpcSysOff o, const double* __restrict__ sys,
 
 
 // K3+K4 for large shapes: one CTA per TILE of T instances (bmpc_tile.cuh).  Same contract as k_admm.
-template <int T, int NS>
+template <int T, int NS, int NXC, int NUC>
 __global__ void __launch_bounds__(NS >= 4 ? 768 : 512) k_admm_tile(BmpcDims d, BmpcSysOff o, const double* __restrict__ sys, BmpcInst I, const int32_t* __restrict__ list,
                             int count, int niter, int do_prep, int cold, int xref_mode, int adapt) {
     extern __shared__ double smem[];
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(NS >= 4 ? 768 : 512) k_admm_tile(BmpcDims d, B
         for (int idx = t.tid; idx < d.mc * T; idx += t.n) { const int e = idx / d.mc, i = idx % d.mc; S.v[(size_t)i * T + e] = I.vw[(size_t)S.inst[e] * d.mc + i]; }
     }
     t.sync();
-    bmpc_admm_tile<T, NS>(t, d, o, sys, S, niter);
+    bmpc_admm_tile<T, NS, NXC, NUC>(t, d, o, sys, S, niter);
     if (adapt) {
         bmpc_tile_adapt(t, d, o, sys, S);
         if (t.tid < nact && S.nlvl[t.tid] != S.lvl[t.tid]) I.lvl[S.inst[t.tid]] = S.nlvl[t.tid];
@@ -642,6 +642,7 @@ struct bmpc_handle {
     int rmax_small = 0; size_t smem_polish_small = 0; int32_t* ovf = nullptr;   // small-capacity polish tier (CTA teams) + its overflow list
     int sm_count = 148;
     double* vprev = nullptr; int32_t* lprev = nullptr;   // snapshot of (v, level) for the infeasibility check of straggler rounds
+    void (*tile_fn[3])(BmpcDims, BmpcSysOff, const double*, BmpcInst, const int32_t*, int, int, int, int, int, int) = {nullptr, nullptr, nullptr};
     int tile_T = 0, tile_threads = 0;                  // > 0: the ADMM of this shape runs on tiles of T instances per CTA
     struct { const int32_t* list; int count; int32_t *cur, *nxt; int total, chunk, round; bool need_prep; } st = {};
     bool pending = false;              // a round is in flight and has not been retired by the host yet
@@ -767,14 +768,17 @@ static int configure_launch(bmpc_handle* h) {
         h->tile_T = 0;
         if (h->cfg.team_threads == 0 && h->cfg.n_sys <= 1) {
             for (int T : {8, 4, 2}) if (!h->tile_T && bmpc_tile_smem_doubles(d, T) * 8 <= budget) h->tile_T = T;
-            if (h->tile_T >= 8) BMPC_CUDA(cudaFuncSetAttribute(k_admm_tile<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bmpc_tile_smem_doubles(d, 8) * 8)));
-            if (h->tile_T >= 8) BMPC_CUDA(cudaFuncSetAttribute(k_admm_tile<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bmpc_tile_smem_doubles(d, 8) * 8)));
-            if (h->tile_T >= 4) BMPC_CUDA(cudaFuncSetAttribute(k_admm_tile<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bmpc_tile_smem_doubles(d, 4) * 8)));
-            if (h->tile_T >= 2) BMPC_CUDA(cudaFuncSetAttribute(k_admm_tile<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bmpc_tile_smem_doubles(d, 2) * 8)));
+            // kernels per tile size {8, 4, 2}; shapes with a compiled (nx, nu) get the unrolled instantiation
+            if (d.nx == 8 && d.nu == 4) { h->tile_fn[0] = k_admm_tile<8, 2, 8, 4>; h->tile_fn[1] = k_admm_tile<4, 2, 8, 4>; h->tile_fn[2] = k_admm_tile<2, 1, 8, 4>; }
+            else { h->tile_fn[0] = k_admm_tile<8, 2, 0, 0>; h->tile_fn[1] = k_admm_tile<4, 2, 0, 0>; h->tile_fn[2] = k_admm_tile<2, 1, 0, 0>; }
+            for (int k = 0; k < 3; k++) {
+                const int T = 8 >> k;
+                if (h->tile_T >= T) BMPC_CUDA(cudaFuncSetAttribute((const void*)h->tile_fn[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bmpc_tile_smem_doubles(d, T) * 8)));
+            }
             int th = d.NX > 2 * d.NU ? d.NX : 2 * d.NU;
             th = ((th + 31) / 32) * 32; if (th < 128) th = 128; if (th > 512) th = 512;
             if (h->cfg.warps_per_block > 0) th = h->cfg.warps_per_block * 32;      // tuning override
-            if (th > 768) th = 768;
+            if (th > 512) th = 512;
             h->tile_threads = th;
         }
         if (h->cfg.rmax == 0 && rmax > 96) { h->rmax_small = 80; h->smem_polish_small = polish_smem_doubles(d, 80) * 8; }
@@ -990,17 +994,13 @@ static void launch_admm(bmpc_handle* h, const int32_t* list, int count, int nite
     } else if (h->team == 32) {
         int grid = (count + h->wpb - 1) / h->wpb;
         k_admm<true><<<grid, h->wpb * 32, h->smem_admm, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
-    } else if (h->tile_T == 8 && count > 2 * h->sm_count * 8) {
-        // throughput tiles: 8 instances share every K^-1 entry
-        if (h->tile_threads >= 4 * h->d.NU)
-            k_admm_tile<8, 4><<<(count + 7) / 8, h->tile_threads, bmpc_tile_smem_doubles(h->d, 8) * 8, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
-        else
-        k_admm_tile<8, 2><<<(count + 7) / 8, h->tile_threads, bmpc_tile_smem_doubles(h->d, 8) * 8, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
-    } else if (h->tile_T >= 4 && count > 2 * h->sm_count * 2) {
-        k_admm_tile<4, 2><<<(count + 3) / 4, h->tile_threads, bmpc_tile_smem_doubles(h->d, 4) * 8, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
     } else if (h->tile_T > 0) {
-        // few instances left (straggler rounds): small tiles, more CTAs, a shorter dependent chain per iteration
-        k_admm_tile<2, 1><<<(count + 1) / 2, h->tile_threads, bmpc_tile_smem_doubles(h->d, 2) * 8, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
+        // throughput tiles (8 instances share every K^-1 entry) while the batch fills the GPU twice over; straggler rounds
+        // with few instances left use small tiles: more CTAs, a shorter dependent chain per iteration
+        int k = (h->tile_T == 8 && count > 2 * h->sm_count * 8) ? 0 : ((h->tile_T >= 4 && count > 2 * h->sm_count * 2) ? 1 : 2);
+        while ((8 >> k) > h->tile_T) k++;
+        const int T = 8 >> k;
+        h->tile_fn[k]<<<(count + T - 1) / T, h->tile_threads, bmpc_tile_smem_doubles(h->d, T) * 8, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
     } else {
         k_admm<false><<<count, h->team, h->smem_admm, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
     }

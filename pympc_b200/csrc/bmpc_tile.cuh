@@ -109,13 +109,15 @@ struct BmpcTile {
 //   C   xt = Kinv[level] r
 //   D   zt = A xt + cc row by row, in registers; v += alpha (zt - prox(v)); then straight away the next iteration's
 //       w = rho (2 prox(v) - v - cc) for the same element (no separate pass, no extra barrier)
-template <int T, int NS, class Team>
+// NXC, NUC: compile-time copies of d.nx, d.nu (0 = use the run-time values): the nx / nu inner loops unroll, so their
+// shared-memory loads issue back to back instead of one load -> FMA round trip per step.
+template <int T, int NS, int NXC, int NUC, class Team>
 BMPC_HD void bmpc_admm_tile(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, BmpcTile<T>& S, int niter) {
     constexpr int TG = T / NS;
     const double *H = sys + o.H, *lo0 = S.lo, *hi0 = S.hi, *rhov = S.rho, *scal = sys + o.scal;
     const double sigma = scal[BMPC_S_SIGMA], alpha = scal[BMPC_S_ALPHA], rho_e = scal[BMPC_S_RHOE];
     const bool soft_on = rho_e > 0.0;
-    const int nx = d.nx, nu = d.nu, Np = d.Np, Nc = d.Nc, NX = d.NX, NU = d.NU, mc = d.mc;
+    const int nx = NXC ? NXC : d.nx, nu = NUC ? NUC : d.nu, Np = d.Np, Nc = d.Nc, NX = d.NX, NU = d.NU, mc = d.mc;
     const int s1 = bmpc_tile_stride1(d), s2 = bmpc_tile_stride2(d);
     double *g = S.g, *cc = S.cc, *x = S.x, *v = S.v, *w = S.w, *xt = S.xt, *r = S.r;
 
@@ -126,6 +128,7 @@ BMPC_HD void bmpc_admm_tile(Team& t, const BmpcDims& d, const BmpcSysOff& o, con
         for (int k = Np; k > j; k--) {                     // descending: every lane of a warp reads the same w rows (broadcast)
             const double* blk = S.phi2 + bmpc_tile_block(d, k, j) * s2 + q;
             const double* wk = ww + (k * nx) * T + sg * TG;
+#pragma unroll
             for (int c = 0; c < nx; c++) {
                 const double m = blk[c * nu]; double wv[TG];
                 bmpc_ldv<TG>(wk + c * T, wv);
@@ -143,16 +146,24 @@ BMPC_HD void bmpc_admm_tile(Team& t, const BmpcDims& d, const BmpcSysOff& o, con
             acc[e] += sm;
         }
     };
-    // out_a = sum_b Msym[b*NU + a] in[b]   (symmetric matrix streamed from global memory, coalesced over a)
+    // out_a = sum_b Msym[b*NU + a] in[b]   (symmetric matrix streamed from global memory, coalesced over a; the next 8
+    // entries are requested before the current 8 are consumed, so the L2 latency overlaps the FMAs)
     auto symv = [&](const double* Msym, const double* in, int a, int sg, double* acc) {
         for (int e = 0; e < TG; e++) acc[e] = 0.0;
         const double* pm = Msym + a;
         const double* iv = in + sg * TG;
-        int b = 0;
-        for (; b + 8 <= NU; b += 8, pm += 8 * NU, iv += 8 * T) {    // 8 matrix loads in flight per thread
-            double m[8];
+        const int ngrp = NU / 8;
+        double m[8], mn[8];
+        if (ngrp > 0) {
 #pragma unroll
             for (int u = 0; u < 8; u++) m[u] = pm[u * NU];
+        }
+        for (int gi = 0; gi < ngrp; gi++) {
+            pm += 8 * NU;
+            if (gi + 1 < ngrp) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) mn[u] = pm[u * NU];
+            }
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 double rv[TG];
@@ -160,8 +171,11 @@ BMPC_HD void bmpc_admm_tile(Team& t, const BmpcDims& d, const BmpcSysOff& o, con
 #pragma unroll
                 for (int e = 0; e < TG; e++) acc[e] = fma(m[u], rv[e], acc[e]);
             }
+            iv += 8 * T;
+#pragma unroll
+            for (int u = 0; u < 8; u++) m[u] = mn[u];
         }
-        for (; b < NU; b++, pm += NU, iv += T) {
+        for (int b = ngrp * 8; b < NU; b++, pm += NU, iv += T) {
             const double m0 = pm[0]; double rv[TG];
             bmpc_ldv<TG>(iv, rv);
 #pragma unroll
@@ -243,6 +257,7 @@ BMPC_HD void bmpc_admm_tile(Team& t, const BmpcDims& d, const BmpcSysOff& o, con
             for (int j = 0; j < jend; j++) {
                 const double* blk = S.phi1 + bmpc_tile_block(d, k, j) * s1 + c;
                 const double* xj = xt + (j * nu) * T + sg * TG;
+#pragma unroll
                 for (int q = 0; q < nu; q++) {
                     const double m = blk[q * nx]; double xv[TG];
                     bmpc_ldv<TG>(xj + q * T, xv);

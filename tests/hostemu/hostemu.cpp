@@ -146,7 +146,8 @@ extern "C" void emu_tile_compare(int nx, int nu, int Np, int Nc, const double* s
         for (int a = 0; a < d.NU; a++) S.x[a * T + e] = cold ? 0.0 : x_in[e * d.NU + a];
         for (int i = 0; i < d.mc; i++) S.v[i * T + e] = cold ? (i < d.NX ? S.cc[i * T + e] : 0.0) : v_in[e * d.mc + i];
     }
-    bmpc_admm_tile<T, 2>(t, d, o, sys, S, niter);
+    if (nx == 8 && nu == 4) bmpc_admm_tile<T, 2, 8, 4>(t, d, o, sys, S, niter);      // the unrolled instantiation the device uses for this shape
+    else bmpc_admm_tile<T, 2, 0, 0>(t, d, o, sys, S, niter);
     bmpc_tile_adapt(t, d, o, sys, S);
     for (int e = 0; e < T; e++) {
         for (int a = 0; a < d.NU; a++) { tile_x[e * d.NU + a] = S.x[a * T + e]; tile_xt[e * d.NU + a] = S.xt[a * T + e]; }
