@@ -153,28 +153,31 @@ BMPC_HD void bmpc_admm_tile(Team& t, const BmpcDims& d, const BmpcSysOff& o, con
         const double* pm = Msym + a;
         const double* iv = in + sg * TG;
         const int ngrp = NU / 8;
-        double m[8], mn[8];
-        if (ngrp > 0) {
+        double m0[8], m1[8];
+        auto fetch = [&](double* mm) {
 #pragma unroll
-            for (int u = 0; u < 8; u++) m[u] = pm[u * NU];
-        }
-        for (int gi = 0; gi < ngrp; gi++) {
+            for (int u = 0; u < 8; u++) mm[u] = pm[u * NU];
             pm += 8 * NU;
-            if (gi + 1 < ngrp) {
-#pragma unroll
-                for (int u = 0; u < 8; u++) mn[u] = pm[u * NU];
-            }
+        };
+        auto use = [&](const double* mm) {
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 double rv[TG];
                 bmpc_ldv<TG>(iv + u * T, rv);
 #pragma unroll
-                for (int e = 0; e < TG; e++) acc[e] = fma(m[u], rv[e], acc[e]);
+                for (int e = 0; e < TG; e++) acc[e] = fma(mm[u], rv[e], acc[e]);
             }
             iv += 8 * T;
-#pragma unroll
-            for (int u = 0; u < 8; u++) m[u] = mn[u];
+        };
+        // ping-pong between two register sets: the next group is in flight while the current one is consumed
+        if (ngrp > 0) fetch(m0);
+        int gi = 0;
+        for (; gi + 2 <= ngrp; gi += 2) {
+            fetch(m1); use(m0);
+            if (gi + 2 < ngrp) fetch(m0);
+            use(m1);
         }
+        if (gi < ngrp) use(m0);
         for (int b = ngrp * 8; b < NU; b++, pm += NU, iv += T) {
             const double m0 = pm[0]; double rv[TG];
             bmpc_ldv<TG>(iv, rv);
