@@ -292,7 +292,7 @@ __global__ void k_polish(BmpcDims d, BmpcSysOff o, const double* __restrict__ sy
             if (t.tid == 0) { int pos = atomicAdd(next_count + 2, 1); ovf_list[pos] = inst; }
         } else {
             if (t.tid == 0) {
-                int used = ps == -1 ? 1 : (ps == 0 ? max_steps : -ps - 1);
+                int used = (ps < 0 ? 1 : max_steps);
                 I.psteps[inst] += used; atomicAdd(next_count + 1, used);
                 if (I.status[inst] != BMPC_PRIMAL_INFEASIBLE) { int pos = atomicAdd(next_count, 1); next_list[pos] = inst; }   // a certified instance is finished
             }
@@ -990,11 +990,10 @@ static bool use_fallback_team(const bmpc_handle* h, const int32_t* list, int cou
 
 static void launch_admm(bmpc_handle* h, const int32_t* list, int count, int niter, int do_prep) {
     const int cold = h->cold ? 1 : 0;
-    static const int straggler_mode = getenv("BMPC_STRAGGLER_ADMM") ? atoi(getenv("BMPC_STRAGGLER_ADMM")) : 0;   // experiment: 1 = one warp per CTA, 2 = packed warps
-    if (use_fallback_team(h, list, count) && straggler_mode == 1) {
+    if (use_fallback_team(h, list, count)) {
+        // stragglers of a warp-team / fast-path handle: one warp per CTA (the lanes-own-rows ADMM has the shortest
+        // dependent chain per iteration for these small shapes: measured 5 % on the random-instance bench vs a 128-thread CTA)
         k_admm<true><<<count, 32, admm_smem_doubles(h->d) * 8, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
-    } else if (use_fallback_team(h, list, count) && straggler_mode == 0) {
-        k_admm<false><<<count, h->fb_team, h->fb_smem_admm, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
     } else if (h->team == 32) {
         int grid = (count + h->wpb - 1) / h->wpb;
         k_admm<true><<<grid, h->wpb * 32, h->smem_admm, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);

@@ -610,8 +610,7 @@ BMPC_HD int bmpc_adapt_level(Team& t, const BmpcDims& d, const BmpcSysOff& o, co
 // conditions of the condensed QP (primal feasibility of hard rows, multiplier signs, soft rows on the
 // side their set says) — then it is THE minimiser.  Otherwise the sets are updated from the candidate
 // (primal-dual active-set step) and the solve repeated, up to max_steps times.
-// Returns the number of steps used (>0) on success, 0 if not verified after max_steps, -1 if the working set outgrew
-// rmax, -(steps used)-1 (<= -2) if the iteration was cut short because it revisited a working set.
+// Returns the number of steps used (>0) on success, 0 if not verified, -1 if the working set outgrew rmax.
 template <class Team>
 BMPC_HD int bmpc_polish(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, const double* um1,
                         const double* g, const double* cc, const double* v, double* W0, double* zz, double* murow,
@@ -642,7 +641,6 @@ BMPC_HD int bmpc_polish(Team& t, const BmpcDims& d, const BmpcSysOff& o, const d
     }
     t.sync();
 
-    double h0 = -1.0, h1 = -1.0, h2 = -1.0, h3 = -1.0;    // signatures of the last working sets (cycle detection)
     for (int step = 0; step < max_steps; step++) {
         // working set R (ordered compaction)
         int cnt = 0;
@@ -720,7 +718,6 @@ BMPC_HD int bmpc_polish(Team& t, const BmpcDims& d, const BmpcSysOff& o, const d
         for (int i = t.tid; i < mc; i += t.n) zz[i] = bmpc_Arow_dot(d, BcalT, U, i) + (i < NX ? cc[i] : 0.0);
         // verification + next sets
         bool ok = true;
-        double sig = 0.0;
         const double mutol = 1e-9 * (1.0 + mumax);
         for (int i = t.tid; i < mc; i += t.n) {
             double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
@@ -744,16 +741,10 @@ BMPC_HD int bmpc_polish(Team& t, const BmpcDims& d, const BmpcSysOff& o, const d
                 ns = vu ? 1 : (vd ? 2 : ((s == 1 && mu > 0.0) ? 1 : ((s == 2 && mu < 0.0) ? 2 : 0)));
             }
             st[i] = ns;
-            if (ns) sig += (double)((((unsigned)(i + 1) * 2654435761u) >> 8) + 1u) * (double)ns;   // signature of the next working set: pseudo-random 24-bit weights, summed exactly in fp64
         }
         ok = t.all(ok);
         t.sync();
         if (ok) return step + 1;
-        // the active-set iteration has no memory: a working set seen before means it cycles (or stalls) and further
-        // refinements are wasted -- hand the instance back to ADMM now.  -(steps used) - 1 tells the caller what it cost.
-        sig = t.sum(sig);
-        if (sig == h0 || sig == h1 || sig == h2 || sig == h3) return -(step + 1) - 1;
-        h3 = h2; h2 = h1; h1 = h0; h0 = sig;
     }
     return 0;
 }
