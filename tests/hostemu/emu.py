@@ -83,9 +83,8 @@ class EmuSystem:
         return U, ps
 
 
-    def tile_compare(self, X0, Um1, Xref, niter, lvl=None, x_in=None, v_in=None):
-        """Run the tile ADMM and the per-instance team ADMM on the same 4 instances; returns (ref, tile) dicts."""
-        T = 4
+    def tile_compare(self, X0, Um1, Xref, niter, lvl=None, x_in=None, v_in=None, T=4):
+        """Run the tile ADMM and the per-instance team ADMM on the same T (2, 4 or 8) instances; returns (ref, tile) dicts."""
         X0 = np.ascontiguousarray(X0, float); Um1 = np.ascontiguousarray(Um1, float); Xref = np.ascontiguousarray(Xref, float)
         mode = 0 if Xref.ndim == 2 else 1
         Xref = Xref.reshape(T, -1)
@@ -99,7 +98,7 @@ class EmuSystem:
                         "res": np.zeros((T, 4)), "lvl": np.zeros(T, np.int32)}
         f = self.L.emu_tile_compare
         f.restype = None
-        f.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 4 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 13
-        f(self.nx, self.nu, self.Np, self.Nc, _p(self.sys), _p(X0), _p(Um1), _p(Xref), mode, cold, niter, _p(lvl), _p(xin), _p(vin),
+        f.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p] * 4 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 13
+        f(T, self.nx, self.nu, self.Np, self.Nc, _p(self.sys), _p(X0), _p(Um1), _p(Xref), mode, cold, niter, _p(lvl), _p(xin), _p(vin),
           *[_p(out[tag][k]) for tag in ("ref", "tile") for k in ("x", "v", "xt", "res", "lvl")])
         return out["ref"], out["tile"]

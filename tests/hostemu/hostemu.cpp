@@ -111,14 +111,14 @@ extern "C" int emu_tpi_step(int nx, int nu, int Np, int Nc, const double* sys, c
 }
 
 
-// Tile ADMM (bmpc_tile.cuh) against the per-instance team ADMM on the same T = 4 instances: prep + niter iterations +
+// Tile ADMM (bmpc_tile.cuh) against the per-instance team ADMM on the same T instances (T, NS = the device's three tile variants): prep + niter iterations +
 // adaptive-rho move.  x, v: [T][NU], [T][mc] warm start in (ignored when cold), results out (ref_* per-instance code,
 // tile_* tile code); res [T][4]; lvl [T] in/out.
-extern "C" void emu_tile_compare(int nx, int nu, int Np, int Nc, const double* sys, const double* x0, const double* um1, const double* xref,
+template <int T, int NS>
+static void emu_tile_compare_t(int nx, int nu, int Np, int Nc, const double* sys, const double* x0, const double* um1, const double* xref,
                                  int xref_mode, int cold, int niter, const int* lvl_in, const double* x_in, const double* v_in,
                                  double* ref_x, double* ref_v, double* ref_xt, double* ref_res, int* ref_lvl,
                                  double* tile_x, double* tile_v, double* tile_xt, double* tile_res, int* tile_lvl) {
-    constexpr int T = 4;
     BmpcDims d = bmpc_make_dims(nx, nu, Np, Nc); BmpcSysOff o = bmpc_make_off(d);
     SeqTeam t;
     const int xl = xref_mode ? d.NX : d.nx;
@@ -146,8 +146,8 @@ extern "C" void emu_tile_compare(int nx, int nu, int Np, int Nc, const double* s
         for (int a = 0; a < d.NU; a++) S.x[a * T + e] = cold ? 0.0 : x_in[e * d.NU + a];
         for (int i = 0; i < d.mc; i++) S.v[i * T + e] = cold ? (i < d.NX ? S.cc[i * T + e] : 0.0) : v_in[e * d.mc + i];
     }
-    if (nx == 8 && nu == 4) bmpc_admm_tile<T, 2, 8, 4>(t, d, o, sys, S, niter);      // the unrolled instantiation the device uses for this shape
-    else bmpc_admm_tile<T, 2, 0, 0>(t, d, o, sys, S, niter);
+    if (nx == 8 && nu == 4) bmpc_admm_tile<T, NS, 8, 4>(t, d, o, sys, S, niter);      // the unrolled instantiation the device uses for this shape
+    else bmpc_admm_tile<T, NS, 0, 0>(t, d, o, sys, S, niter);
     bmpc_tile_adapt(t, d, o, sys, S);
     for (int e = 0; e < T; e++) {
         for (int a = 0; a < d.NU; a++) { tile_x[e * d.NU + a] = S.x[a * T + e]; tile_xt[e * d.NU + a] = S.xt[a * T + e]; }
@@ -156,4 +156,15 @@ extern "C" void emu_tile_compare(int nx, int nu, int Np, int Nc, const double* s
         tile_lvl[e] = S.nlvl[e];
     }
     free(sm);
+}
+
+extern "C" void emu_tile_compare(int T, int nx, int nu, int Np, int Nc, const double* sys, const double* x0, const double* um1, const double* xref,
+                                 int xref_mode, int cold, int niter, const int* lvl_in, const double* x_in, const double* v_in,
+                                 double* ref_x, double* ref_v, double* ref_xt, double* ref_res, int* ref_lvl,
+                                 double* tile_x, double* tile_v, double* tile_xt, double* tile_res, int* tile_lvl) {
+#define EMU_TILE_ARGS nx, nu, Np, Nc, sys, x0, um1, xref, xref_mode, cold, niter, lvl_in, x_in, v_in, ref_x, ref_v, ref_xt, ref_res, ref_lvl, tile_x, tile_v, tile_xt, tile_res, tile_lvl
+    if (T == 8) emu_tile_compare_t<8, 2>(EMU_TILE_ARGS);
+    else if (T == 4) emu_tile_compare_t<4, 2>(EMU_TILE_ARGS);
+    else emu_tile_compare_t<2, 1>(EMU_TILE_ARGS);
+#undef EMU_TILE_ARGS
 }

@@ -113,8 +113,8 @@ def test_tpi_fast_path_random_batch():
             x = cfg["Ad"] @ x + cfg["Bd"] @ U[:1]; um1 = U[:1]
 
 
-@pytest.mark.parametrize("name,Nc", [("mimo", None), ("pend", None), ("pend", 7), ("mimo", 12)])
-def test_tile_admm_equals_team_admm(name, Nc):
+@pytest.mark.parametrize("name,Nc,T", [("mimo", None, 4), ("pend", None, 4), ("pend", 7, 2), ("mimo", 12, 8), ("mimo", None, 2), ("pend", None, 8)])
+def test_tile_admm_equals_team_admm(name, Nc, T):
     """The tile ADMM (T instances per CTA, Toeplitz prediction blocks) is the same iteration as the per-instance team
     ADMM: identical iterates (to rounding: the sums run in a different order), residuals and adaptive-rho moves."""
     cfg = CASES[name]()
@@ -122,20 +122,20 @@ def test_tile_admm_equals_team_admm(name, Nc):
         cfg = dict(cfg, Nc=Nc)
     E = EmuSystem(cfg); nx, nu = E.nx, E.nu
     rng = np.random.default_rng(5)
-    X0 = np.asarray(cfg["x0"], float) + 0.3 * rng.standard_normal((4, nx))
-    Um1 = 0.1 * rng.standard_normal((4, nu)); Xref = np.tile(np.asarray(cfg["xref"], float), (4, 1))
-    ref, til = E.tile_compare(X0, Um1, Xref, niter=10)
+    X0 = np.asarray(cfg["x0"], float) + 0.3 * rng.standard_normal((T, nx))
+    Um1 = 0.1 * rng.standard_normal((T, nu)); Xref = np.tile(np.asarray(cfg["xref"], float), (T, 1))
+    ref, til = E.tile_compare(X0, Um1, Xref, niter=10, T=T)
     for k in ("x", "v", "xt"):
         assert np.abs(ref[k] - til[k]).max() <= 1e-9 * (1 + np.abs(ref[k]).max()), k
     assert np.allclose(ref["res"], til["res"], rtol=1e-7, atol=1e-12)
     assert (ref["lvl"] == til["lvl"]).all()
     # warm continuation on mixed ladder levels (instances of one tile may sit on different rho levels)
-    lv = np.array([1, 2, 3, 2], np.int32)
-    ref2, til2 = E.tile_compare(X0, Um1, Xref, niter=7, lvl=lv, x_in=ref["x"], v_in=ref["v"])
+    lv = np.array([1, 2, 3, 2, 2, 4, 1, 2][:T], np.int32)
+    ref2, til2 = E.tile_compare(X0, Um1, Xref, niter=7, lvl=lv, x_in=ref["x"], v_in=ref["v"], T=T)
     for k in ("x", "v", "xt"):
         assert np.abs(ref2[k] - til2[k]).max() <= 1e-9 * (1 + np.abs(ref2[k]).max()), k
     assert np.allclose(ref2["res"], til2["res"], rtol=1e-7, atol=1e-12)
     # time-varying reference (xref_mode 1)
     Xtv = np.tile(Xref[:, None, :], (1, E.Np + 1, 1)) * np.linspace(0.5, 1.0, E.Np + 1)[None, :, None]
-    ref3, til3 = E.tile_compare(X0, Um1, Xtv, niter=5)
+    ref3, til3 = E.tile_compare(X0, Um1, Xtv, niter=5, T=T)
     assert np.abs(ref3["v"] - til3["v"]).max() <= 1e-9 * (1 + np.abs(ref3["v"]).max())
