@@ -1122,6 +1122,9 @@ int bmpc_solve(bmpc_handle* h) {
     // first round: 3 iterations on the fast path (measured: as good as 10 for the warm active-set guess), 10 on the team kernels
     const bool fast = h->tpi_kind && h->xref_mode == 0;
     st.chunk = h->cfg.polish ? (h->cfg.first_iters > 0 ? h->cfg.first_iters : (fast ? 3 : 10)) : 25;
+    // a cold start has no active-set guess to refresh: 25 iterations at once on the fast path, so that the first polish
+    // usually verifies and the whole batch does not take the straggler route
+    if (h->cfg.polish && h->cfg.first_iters <= 0 && fast && h->cold) st.chunk = 25;
     if (st.chunk > h->cfg.max_iter) st.chunk = h->cfg.max_iter;
     int rc = enqueue_round(h);
     if (rc) return rc;
