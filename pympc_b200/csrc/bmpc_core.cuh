@@ -624,7 +624,6 @@ BMPC_HD int bmpc_polish(Team& t, const BmpcDims& d, const BmpcSysOff& o, const d
     // S is stored packed (lower triangle by rows): element (k,l), l <= k, at k(k+1)/2 + l
     #define BMPC_TRI(k, l) ((size_t)(k) * ((k) + 1) / 2 + (l))
     const double delta = 1e-13;
-    const double BMPC_PIVOT_TOL = 1e-9;                 // relative size below which a pivot counts as vanished
 
     // U0 = -H^-1 g (H^-1 symmetric: column reads are coalesced over a), W0 = A U0 + cc through the structured A
     for (int a = t.tid; a < NU; a += t.n) {
@@ -667,7 +666,7 @@ BMPC_HD int bmpc_polish(Team& t, const BmpcDims& d, const BmpcSysOff& o, const d
                 while (k * (k + 1) / 2 > e) k--;
                 const int l = e - k * (k + 1) / 2;
                 double val = M[(size_t)R[k] * mc + R[l]];
-                if (k == l) { val += (soft_on && R[k] < NX) ? inv_rho_e : delta * (1.0 + fabs(val)); murow[k] = val; }   // murow: scratch for the original diagonal
+                if (k == l) val += (soft_on && R[k] < NX) ? inv_rho_e : delta * (1.0 + fabs(val));
                 S[e] = val;
             }
             t.sync();
@@ -675,11 +674,9 @@ BMPC_HD int bmpc_polish(Team& t, const BmpcDims& d, const BmpcSysOff& o, const d
             // costs ONE barrier and one reciprocal (no square root, no scaling pass); rows go to warps, columns to lanes.
             double* dv = zz;                                   // zz is free until the candidate rows are formed
             for (int j = 0; j < r; j++) {
-                // a pivot that has (numerically) vanished marks a working row that depends on the rows before it (degenerate
-                // vertex: more active rows than free directions): leave it out of this solve (mu_j = 0) instead of dividing
-                // by rounding noise; a consistent dependent row is satisfied anyway and passes the verification with mu = 0
-                const double djj = S[BMPC_TRI(j, j)];
-                const double dinv = (djj > BMPC_PIVOT_TOL * murow[j]) ? 1.0 / djj : 0.0;
+                double djj = S[BMPC_TRI(j, j)];
+                if (!(djj > 1e-300)) djj = 1e-300;           // dependent working rows: candidate will fail verification
+                const double dinv = 1.0 / djj;
                 if (t.tid == 0) dv[j] = dinv;
                 for (int i = j + 1 + t.warp(); i < r; i += t.nwarps()) {
                     const double lij = S[BMPC_TRI(i, j)] * dinv;
