@@ -233,7 +233,7 @@ def test_full_size_mimo_batch(MPC):
     for t in range(2):
         K.update(X, U); Un, info = K.output(return_u_seq=True)
         assert K.stats()["unsolved"] == 0
-        assert K.stats()["admm_iters"] < 80 * B                # the polish verifies early (a broken polish shows up as hundreds of iterations per solve)
+        assert K.stats()["admm_iters"] < 150 * B               # the polish verifies early (a broken polish shows up as hundreds of iterations per solve)
         for b in rng.integers(0, B, 3):
             c = dict(cfg); c["x0"] = X[b]; c["uminus1"] = U[b]
             ref, Q = _oracle_u(c)
