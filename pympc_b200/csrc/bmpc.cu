@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmm
 #pragma unroll
             for (int q = 0; q < S::nu; q++) um1_solved[(size_t)inst * S::nu + q] = um1[q];
         }
-        if (blockIdx.x == 0 && lane == 0) { counts[0] = 0; counts[1] = 0; counts[2] = 0; }
+        if (blockIdx.x == 0 && lane == 0) { counts[0] = 0; counts[1] = 0; }
     }
     if (valid) tpi_admm<S>(P, V, x0, um1, xref, x, niter, cold != 0);
     __syncwarp();
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmm
 // v* is staged in the column (slots, see below) and U / u0 / status are written
 template <class S>
 __device__ __forceinline__ bool tpi_polish_thread(const TpiRicParams<S>& P, BmpcInst& I, int inst, TpiAcc W, int max_steps,
-                                                  int32_t* next_list, int32_t* next_count, double* u0_out, int32_t* defer_list) {
+                                                  int32_t* next_list, int32_t* next_count, double* u0_out) {
     double x0[S::nx], um1[S::nu], xref[S::nx];
 #pragma unroll
     for (int q = 0; q < S::nx; q++) { x0[q] = I.x0[(size_t)inst * S::nx + q]; xref[q] = I.xref[(size_t)inst * S::nx + q]; }
@@ -550,10 +550,6 @@ __device__ __forceinline__ bool tpi_polish_thread(const TpiRicParams<S>& P, Bmpc
         bmpc_publish_u0(I, u0_out, (size_t)inst, u_first);
         I.status[inst] = BMPC_SOLVED; I.psteps[inst] += ps;
         atomicAdd(next_count + 1, ps);
-    } else if (defer_list) {
-        // first pass of a two-pass polish: not verified within its short budget -> the second (list-mode) pass takes it
-        I.psteps[inst] += max_steps; atomicAdd(next_count + 1, max_steps);
-        defer_list[atomicAdd(next_count + 2, 1)] = inst;
     } else {
         I.psteps[inst] += max_steps; atomicAdd(next_count + 1, max_steps);
         if (I.status[inst] != BMPC_PRIMAL_INFEASIBLE) next_list[atomicAdd(next_count, 1)] = inst;
@@ -563,12 +559,9 @@ __device__ __forceinline__ bool tpi_polish_thread(const TpiRicParams<S>& P, Bmpc
 
 template <class S>
 __global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiRicParams<S> P, BmpcInst I, const int32_t* __restrict__ list, int B, int max_steps,
-                                                   int32_t* next_list, int32_t* next_count, double* u0_out, int32_t* defer_list, const int32_t* dev_count) {
-    // defer_list != nullptr: first pass (max_steps is its short budget; failures are listed for the second pass).
-    // dev_count != nullptr: second pass, `list` and its length were produced on the device by the first pass.
+                                                   int32_t* next_list, int32_t* next_count, double* u0_out) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x, idx0 = blockIdx.x * 32;
-    if (dev_count) { B = *dev_count; if (idx0 >= B) return; }
     const int nvalid = (B - idx0) < 32 ? (B - idx0) : 32;
     const int inst = list ? (lane < nvalid ? list[idx0 + lane] : 0) : idx0 + lane;
     TpiAcc W{smem + lane, TPI_STR};
@@ -576,7 +569,7 @@ __global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiRi
         if (lane < nvalid) { const double* src = I.vw + (size_t)inst * S::mc + S::nx; for (int i = 0; i < S::MT; i++) W(i) = src[i]; }
     } else { tpi_load_v<S>(I, idx0, nvalid, smem, 0); }
     __syncwarp();
-    const bool ok = (lane < nvalid) && tpi_polish_thread<S>(P, I, inst, W, max_steps, next_list, next_count, u0_out, defer_list);
+    const bool ok = (lane < nvalid) && tpi_polish_thread<S>(P, I, inst, W, max_steps, next_list, next_count, u0_out);
     const unsigned okmask = __ballot_sync(0xffffffffu, ok);
     __syncwarp();
     constexpr int nz1 = S::nx + 2;
@@ -649,7 +642,6 @@ struct bmpc_handle {
     int fb_team = 0, fb_rmax = 0; size_t fb_smem_admm = 0, fb_smem_polish = 0;
     int rmax_small = 0; size_t smem_polish_small = 0; int32_t* ovf = nullptr;   // small-capacity polish tier (CTA teams) + its overflow list
     int sm_count = 148;
-    bool tpi_two_pass = false;                         // fast-path polish in two passes (decided from the previous step's statistics)
     double* vprev = nullptr; int32_t* lprev = nullptr;   // snapshot of (v, level) for the infeasibility check of straggler rounds
     void (*tile_fn[3])(BmpcDims, BmpcSysOff, const double*, BmpcInst, const int32_t*, int, int, int, int, int, int) = {nullptr, nullptr, nullptr};
     int tile_T = 0, tile_threads = 0;                  // > 0: the ADMM of this shape runs on tiles of T instances per CTA
@@ -677,25 +669,15 @@ static void launch_tpi_round(bmpc_handle* h, const int32_t* list, int count, int
     k_tpi_admm<S><<<grid, 32, S::AROWS * TPI_STR * 8, h->stream>>>(*(const TpiAdmmParams<S>*)h->tpi_admm_params, h->I, list, count, niter, h->cold ? 1 : 0,
                                                                    h->st.round == 0 ? 1 : 0, h->counts, h->um1_solved);
     cudaEventRecord(mid, h->stream);
-    if (h->tpi_two_pass && list == nullptr) {
-        // lanes of a warp wait for the slowest instance: when a noticeable share of instances needs more than one
-        // refinement, give everybody ONE, then redo the unverified few in list mode (compacted into full warps)
-        k_tpi_polish<S><<<grid, 32, S::PROWS * TPI_STR * 8, h->stream>>>(*(const TpiRicParams<S>*)h->tpi_polish_params, h->I, list, count,
-                                                                         1, next_list, h->counts, h->I.u0, h->ovf, nullptr);
-        k_tpi_polish<S><<<grid, 32, S::PROWS * TPI_STR * 8, h->stream>>>(*(const TpiRicParams<S>*)h->tpi_polish_params, h->I, h->ovf, count,
-                                                                         h->tpi_pdas_steps, next_list, h->counts, h->I.u0, nullptr, h->counts + 2);
-        h->stats.launches += 3;
-    } else {
-        k_tpi_polish<S><<<grid, 32, S::PROWS * TPI_STR * 8, h->stream>>>(*(const TpiRicParams<S>*)h->tpi_polish_params, h->I, list, count,
-                                                                         h->tpi_pdas_steps, next_list, h->counts, h->I.u0, nullptr, nullptr);
-        h->stats.launches += 2;
-    }
+    k_tpi_polish<S><<<grid, 32, S::PROWS * TPI_STR * 8, h->stream>>>(*(const TpiRicParams<S>*)h->tpi_polish_params, h->I, list, count,
+                                                                     h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
+    h->stats.launches += 2;
 }
 
 template <class S>
 static void launch_tpi_polish_only(bmpc_handle* h, const int32_t* list, int count, int32_t* next_list) {
     k_tpi_polish<S><<<(count + 31) / 32, 32, S::PROWS * TPI_STR * 8, h->stream>>>(*(const TpiRicParams<S>*)h->tpi_polish_params, h->I, list, count,
-                                                                                h->tpi_pdas_steps, next_list, h->counts, h->I.u0, nullptr, nullptr);
+                                                                                h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
     h->stats.launches++;
 }
 
@@ -1085,7 +1067,7 @@ static int enqueue_round(bmpc_handle* h) {
         else { k_check_converged<<<(st.count + 255) / 256, 256, 0, h->stream>>>(h->I, st.list, st.count, h->cfg.eps_abs, h->cfg.eps_rel, st.nxt, h->counts); h->stats.launches++; }
     }
     BMPC_CUDA(cudaEventRecord(h->ev[2], h->stream));
-    BMPC_CUDA(cudaMemcpyAsync(h->h_count, h->counts, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, h->stream));
+    BMPC_CUDA(cudaMemcpyAsync(h->h_count, h->counts, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, h->stream));
     BMPC_CUDA(cudaGetLastError());
     return BMPC_OK;
 }
@@ -1102,12 +1084,6 @@ static int retire_round(bmpc_handle* h, int* more) {
     h->cold = false;
     st.count = h->h_count[0];
     h->stats.polish_steps += h->h_count[1];
-    if (st.round == 1 && h->tpi_kind && h->cfg.polish) {
-        // next step's polish layout: two passes pay off when more than ~2 % of the instances need a second refinement
-        const double B = (double)h->cfg.batch;
-        if (h->tpi_two_pass) h->tpi_two_pass = h->h_count[2] > 0.01 * B;
-        else h->tpi_two_pass = h->h_count[1] > 1.02 * B;
-    }
     st.list = st.nxt; int32_t* tmp = st.cur; st.cur = st.nxt; st.nxt = tmp;
     // polish mode: cumulative first_iters, 25, 50, 100, ...; pure ADMM: OSQP's check_termination = 25
     st.chunk = h->cfg.polish ? (st.total < 25 ? 25 - st.total : st.total) : 25;
