@@ -639,7 +639,7 @@ struct bmpc_handle {
     std::string err;
     size_t smem_admm = 0, smem_polish = 0;
     // low-latency CTA-per-instance variant for the few stragglers of a warp-team / TPI handle
-    int fb_team = 0, fb_rmax = 0; size_t fb_smem_admm = 0, fb_smem_polish = 0;
+    int fb_team = 0, fb_rmax = 0; size_t fb_smem_polish = 0;
     int rmax_small = 0; size_t smem_polish_small = 0; int32_t* ovf = nullptr;   // small-capacity polish tier (CTA teams) + its overflow list
     int sm_count = 148;
     double* vprev = nullptr; int32_t* lprev = nullptr;   // snapshot of (v, level) for the infeasibility check of straggler rounds
@@ -760,8 +760,7 @@ static int configure_launch(bmpc_handle* h) {
         while (frmax > 8 && polish_smem_doubles(d, frmax) * 8 > budget) frmax -= 8;
         if (polish_smem_doubles(d, frmax) * 8 <= budget) {
             h->fb_team = 128; h->fb_rmax = frmax;
-            h->fb_smem_admm = admm_smem_doubles(d) * 8; h->fb_smem_polish = polish_smem_doubles(d, frmax) * 8;
-            BMPC_CUDA(cudaFuncSetAttribute(k_admm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fb_smem_admm));
+            h->fb_smem_polish = polish_smem_doubles(d, frmax) * 8;
             BMPC_CUDA(cudaFuncSetAttribute(k_polish<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fb_smem_polish));
         }
     } else {
