@@ -342,34 +342,10 @@ __global__ void k_infeas(BmpcDims d, BmpcSysOff o, const double* __restrict__ sy
     sys += (size_t)inst * I.sys_stride;
     BlockTeam t(sd, si);
     double* dy = smem; double* um1 = dy + d.mc;
-    const double *lo0 = sys + o.lo0, *hi0 = sys + o.hi0, *rhov = sys + o.rho, *Bcal = sys + o.Bcal;
-    const double rho_e = sys[o.scal + BMPC_S_RHOE];
-    const bool soft_on = rho_e > 0.0;
     for (int q = t.tid; q < d.nu; q += t.n) um1[q] = I.um1[(size_t)inst * d.nu + q];
     t.sync();
-    const double f0 = bmpc_level_factor(lprev[inst]), f1 = bmpc_level_factor(I.lvl[inst]);
-    double ln = 0.0, ls = 0.0;
-    for (int i = t.tid; i < d.mc; i += t.n) {
-        double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
-        const bool soft = soft_on && i < d.NX;
-        const double v0 = vprev[(size_t)inst * d.mc + i], v1 = I.vw[(size_t)inst * d.mc + i];
-        const double r0 = f0 * rhov[i], r1 = f1 * rhov[i];
-        double dyi = soft ? 0.0 : r1 * (v1 - bmpc_prox(v1, lo, hi, false, r1, rho_e)) - r0 * (v0 - bmpc_prox(v0, lo, hi, false, r0, rho_e));
-        if (hi > 1e29 && dyi > 0.0) dyi = 0.0;           // projection on the polar of the recession cone of [lo, hi]
-        if (lo < -1e29 && dyi < 0.0) dyi = 0.0;
-        dy[i] = dyi;
-        ln = fmax(ln, fabs(dyi));
-        // rows are z = A U + cc: the box of A U alone is [lo - cc, hi - cc]
-        const double ci = i < d.NX ? I.cc[(size_t)inst * d.NX + i] : 0.0;
-        ls += dyi > 0.0 ? (hi - ci) * dyi : (dyi < 0.0 ? (lo - ci) * dyi : 0.0);
-    }
-    const double ndy = t.max(ln);
-    const double supp = t.sum(ls);
-    if (!(ndy > 1e-30) || !(supp < -eps_pinf * ndy)) return;
-    double la = 0.0;
-    for (int a = t.tid; a < d.NU; a += t.n) la = fmax(la, fabs(bmpc_ATcol_dot(d, Bcal, dy, a)));
-    const double nat = t.max(la);
-    if (nat < eps_pinf * ndy) {
+    if (bmpc_primal_infeasible(t, d, o, sys, um1, I.cc + (size_t)inst * d.NX, vprev + (size_t)inst * d.mc, lprev[inst],
+                               I.vw + (size_t)inst * d.mc, I.lvl[inst], dy, eps_pinf)) {
         if (t.tid == 0) I.status[inst] = BMPC_PRIMAL_INFEASIBLE;
         for (int q = t.tid; q < d.nu; q += t.n) bmpc_publish_u0(I, u0_out, (size_t)inst * d.nu + q, sys[o.uref + q]);
     }

@@ -602,6 +602,40 @@ BMPC_HD int bmpc_adapt_level(Team& t, const BmpcDims& d, const BmpcSysOff& o, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Primal infeasibility (OSQP paper 3.4) from two ADMM states (v0 on ladder level lvl0, v1 on lvl1) of the same problem:
+// dy = y1 - y0 on the hard rows (soft rows are penalties, not constraints), projected on the polar of the recession cone
+// of the row box like OSQP does; a certificate needs  ||A' dy|| < eps ||dy||  and a negative support function
+// sum_i (hi_i - cc_i) dy_i^+ + (lo_i - cc_i) dy_i^-  < -eps ||dy||   (rows are z = A U + cc).  dy: mc doubles of scratch.
+template <class Team>
+BMPC_HD bool bmpc_primal_infeasible(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, const double* um1,
+                                    const double* cc, const double* v0, int lvl0, const double* v1, int lvl1, double* dy, double eps) {
+    const double *lo0 = sys + o.lo0, *hi0 = sys + o.hi0, *rhov = sys + o.rho, *Bcal = sys + o.Bcal;
+    const double rho_e = sys[o.scal + BMPC_S_RHOE];
+    const bool soft_on = rho_e > 0.0;
+    const double f0 = bmpc_level_factor(lvl0), f1 = bmpc_level_factor(lvl1);
+    double ln = 0.0, ls = 0.0;
+    for (int i = t.tid; i < d.mc; i += t.n) {
+        double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
+        const bool soft = soft_on && i < d.NX;
+        const double a0 = v0[i], a1 = v1[i], r0 = f0 * rhov[i], r1 = f1 * rhov[i];
+        double dyi = soft ? 0.0 : r1 * (a1 - bmpc_prox(a1, lo, hi, false, r1, rho_e)) - r0 * (a0 - bmpc_prox(a0, lo, hi, false, r0, rho_e));
+        if (hi > 1e29 && dyi > 0.0) dyi = 0.0;
+        if (lo < -1e29 && dyi < 0.0) dyi = 0.0;
+        dy[i] = dyi;
+        ln = fmax(ln, fabs(dyi));
+        const double ci = i < d.NX ? cc[i] : 0.0;
+        ls += dyi > 0.0 ? (hi - ci) * dyi : (dyi < 0.0 ? (lo - ci) * dyi : 0.0);
+    }
+    const double ndy = t.max(ln);
+    const double supp = t.sum(ls);
+    if (!(ndy > 1e-30) || !(supp < -eps * ndy)) return false;      // uniform across the team
+    t.sync();
+    double la = 0.0;
+    for (int a = t.tid; a < d.NU; a += t.n) la = fmax(la, fabs(bmpc_ATcol_dot(d, Bcal, dy, a)));
+    return t.max(la) < eps * ndy;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K5: polish.  Primal-dual active-set refinement on the condensed QP, in dual (Schur) form:
 // with R the current set of "working" rows (violated soft rows + active hard rows, bound b_R),
 //     S mu = A_R U0 + cc_R - b_R,   S = (A H^-1 A')[R,R] + diag(1/rho_e on soft rows, delta on hard rows)

@@ -28,7 +28,7 @@ def _p(a):
 
 
 class EmuSystem:
-    def __init__(self, cfg, rho=0.0, sigma=1e-6, alpha=1.6):
+    def __init__(self, cfg, rho=0.0, sigma=1e-6, alpha=1.6, soft_on=1):
         self.L = build()
         Ad = np.asarray(cfg["Ad"], float); Bd = np.asarray(cfg["Bd"], float)
         self.nx, self.nu = Bd.shape
@@ -51,7 +51,7 @@ class EmuSystem:
         put("Dumin", cfg.get("Dumin", -inf * np.ones(nu))); put("Dumax", cfg.get("Dumax", inf * np.ones(nu)))
         put("uref", cfg.get("uref", np.zeros(nu)))
         self.L.emu_condense.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] + [ctypes.c_double] * 4 + [ctypes.c_int]
-        self.L.emu_condense(nx, nu, Np, Nc, _p(self.sys), rho, sigma, alpha, float(cfg.get("eps_feas", 1e6)), 1)
+        self.L.emu_condense(nx, nu, Np, Nc, _p(self.sys), rho, sigma, alpha, float(cfg.get("eps_feas", 1e6)), int(soft_on))
         self.x = np.zeros(self.NU); self.v = np.zeros(self.mc); self.cold = 1
 
     def get(self, name, shape):
@@ -102,3 +102,10 @@ class EmuSystem:
         f(T, self.nx, self.nu, self.Np, self.Nc, _p(self.sys), _p(X0), _p(Um1), _p(Xref), mode, cold, niter, _p(lvl), _p(xin), _p(vin),
           *[_p(out[tag][k]) for tag in ("ref", "tile") for k in ("x", "v", "xt", "res", "lvl")])
         return out["ref"], out["tile"]
+
+    def infeasible(self, x0, um1, xref, it0=25, it1=25, eps=1e-4):
+        """OSQP's primal-infeasibility certificate between the ADMM states after it0 and it0+it1 iterations (cold start)."""
+        x0 = np.ascontiguousarray(x0, float); um1 = np.ascontiguousarray(um1, float); xref = np.ascontiguousarray(xref, float)
+        f = self.L.emu_infeasible
+        f.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 4 + [ctypes.c_int] * 2 + [ctypes.c_double]
+        return bool(f(self.nx, self.nu, self.Np, self.Nc, _p(self.sys), _p(x0), _p(um1), _p(xref), it0, it1, eps))

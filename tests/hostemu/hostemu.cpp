@@ -3,6 +3,9 @@
 // arithmetic and algorithm logic can be checked against numpy without a GPU.  This is NOT a CPU
 // fallback: pympc_b200 never loads this library; it lives under tests/ and is built by the tests.
 #define BMPC_HOSTEMU 1
+#include <stdlib.h>
+#include <stdio.h>
+#include <string.h>
 #include "../../pympc_b200/csrc/bmpc_core.cuh"
 #include "../../pympc_b200/csrc/bmpc_tpi.cuh"
 #include "../../pympc_b200/csrc/bmpc_tile.cuh"
@@ -167,4 +170,24 @@ extern "C" void emu_tile_compare(int T, int nx, int nu, int Np, int Nc, const do
     else if (T == 4) emu_tile_compare_t<4, 2>(EMU_TILE_ARGS);
     else emu_tile_compare_t<2, 1>(EMU_TILE_ARGS);
 #undef EMU_TILE_ARGS
+}
+
+
+// OSQP's primal-infeasibility certificate as the straggler rounds evaluate it: ADMM state after it0 iterations vs after
+// it0 + it1 iterations (cold start, base rho level).  Returns 1 when certified.
+extern "C" int emu_infeasible(int nx, int nu, int Np, int Nc, const double* sys, const double* x0, const double* um1, const double* xref,
+                              int it0, int it1, double eps) {
+    BmpcDims d = bmpc_make_dims(nx, nu, Np, Nc); BmpcSysOff o = bmpc_make_off(d);
+    SeqTeam t;
+    double* buf = (double*)calloc(5 * d.NU + d.NX + 5 * d.mc + 8, sizeof(double));
+    double *g = buf, *cc = g + d.NU, *x = cc + d.NX, *v = x + d.NU, *w = v + d.mc, *xt = w + d.mc, *r = xt + d.NU, *res = r + d.NU,
+           *v0 = res + 8, *dy = v0 + d.mc;
+    bmpc_prep(t, d, o, sys, x0, um1, xref, 0, g, cc);
+    for (int i = 0; i < d.mc; i++) v[i] = i < d.NX ? cc[i] : 0.0;
+    bmpc_admm(t, d, o, sys, um1, g, cc, x, v, w, xt, r, it0, res, BMPC_LEV0);
+    memcpy(v0, v, sizeof(double) * d.mc);
+    bmpc_admm(t, d, o, sys, um1, g, cc, x, v, w, xt, r, it1, res, BMPC_LEV0);
+    int flag = bmpc_primal_infeasible(t, d, o, sys, um1, cc, v0, BMPC_LEV0, v, BMPC_LEV0, dy, eps) ? 1 : 0;
+    free(buf);
+    return flag;
 }

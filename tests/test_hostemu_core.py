@@ -139,3 +139,17 @@ def test_tile_admm_equals_team_admm(name, Nc, T):
     Xtv = np.tile(Xref[:, None, :], (1, E.Np + 1, 1)) * np.linspace(0.5, 1.0, E.Np + 1)[None, :, None]
     ref3, til3 = E.tile_compare(X0, Um1, Xtv, niter=5, T=T)
     assert np.abs(ref3["v"] - til3["v"]).max() <= 1e-9 * (1 + np.abs(ref3["v"]).max())
+
+
+def test_primal_infeasibility_certificate():
+    """OSQP's certificate as the straggler rounds evaluate it (bmpc_primal_infeasible): found for an initial state outside
+    HARD state bounds (no feasible trajectory), not found for the same problem with a feasible start or with soft bounds."""
+    cfg = point_mass(); cfg["xmax"] = np.array([3.0, 100.0])
+    hard = EmuSystem(cfg, soft_on=0); soft = EmuSystem(cfg, soft_on=1)
+    um1 = np.zeros(1)
+    # the transient parts of y have to die out before the difference is a clean certificate (fixed rho here; the device
+    # rounds also move rho, which speeds this up)
+    assert hard.infeasible(np.array([3.5, 0.0]), um1, cfg["xref"], it0=400, it1=400)
+    for it in (25, 400):
+        assert not hard.infeasible(np.array([0.1, 0.2]), um1, cfg["xref"], it0=it, it1=it)
+        assert not soft.infeasible(np.array([3.5, 0.0]), um1, cfg["xref"], it0=it, it1=it)
