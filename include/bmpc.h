@@ -68,7 +68,7 @@ typedef struct {
     float ms_admm;              /* device time of the ADMM kernels in the last solve (CUDA events) */
     float ms_polish;            /* device time of the polish kernels */
     int32_t launches;           /* kernels launched by the last solve */
-    int32_t reserved;
+    int32_t infeasible;         /* instances certified primal infeasible (status -3) in the last solve */
 } bmpc_stats;
 
 void bmpc_default_config(bmpc_config* cfg);

@@ -23,7 +23,7 @@ class BmpcConfig(ctypes.Structure):
 class BmpcStats(ctypes.Structure):
     _fields_ = [("admm_iters", ctypes.c_int64), ("rounds", ctypes.c_int32), ("unsolved", ctypes.c_int32),
                 ("polish_steps", ctypes.c_int64), ("ms_admm", ctypes.c_float), ("ms_polish", ctypes.c_float),
-                ("launches", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("launches", ctypes.c_int32), ("infeasible", ctypes.c_int32)]
 
 
 EXPORTS = ["bmpc_default_config", "bmpc_create", "bmpc_destroy", "bmpc_last_error", "bmpc_setup", "bmpc_update",

@@ -332,7 +332,7 @@ __global__ void k_snapshot(BmpcDims d, BmpcInst I, const int32_t* __restrict__ l
 }
 
 __global__ void k_infeas(BmpcDims d, BmpcSysOff o, const double* __restrict__ sys, BmpcInst I, const int32_t* __restrict__ list, int count,
-                         const double* __restrict__ vprev, const int32_t* __restrict__ lprev, double eps_pinf, double* u0_out) {
+                         const double* __restrict__ vprev, const int32_t* __restrict__ lprev, double eps_pinf, double* u0_out, int32_t* counts) {
     extern __shared__ double smem[];
     __shared__ double sd[32];
     __shared__ int si[32];
@@ -346,7 +346,7 @@ __global__ void k_infeas(BmpcDims d, BmpcSysOff o, const double* __restrict__ sy
     t.sync();
     if (bmpc_primal_infeasible(t, d, o, sys, um1, I.cc + (size_t)inst * d.NX, vprev + (size_t)inst * d.mc, lprev[inst],
                                I.vw + (size_t)inst * d.mc, I.lvl[inst], dy, eps_pinf)) {
-        if (t.tid == 0) I.status[inst] = BMPC_PRIMAL_INFEASIBLE;
+        if (t.tid == 0) { I.status[inst] = BMPC_PRIMAL_INFEASIBLE; atomicAdd(counts + 3, 1); }
         for (int q = t.tid; q < d.nu; q += t.n) bmpc_publish_u0(I, u0_out, (size_t)inst * d.nu + q, sys[o.uref + q]);
     }
 }
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmm
 #pragma unroll
             for (int q = 0; q < S::nu; q++) um1_solved[(size_t)inst * S::nu + q] = um1[q];
         }
-        if (blockIdx.x == 0 && lane == 0) { counts[0] = 0; counts[1] = 0; }
+        if (blockIdx.x == 0 && lane == 0) { counts[0] = 0; counts[1] = 0; counts[2] = 0; counts[3] = 0; }
     }
     if (valid) tpi_admm<S>(P, V, x0, um1, xref, x, niter, cold != 0);
     __syncwarp();
@@ -1031,7 +1031,7 @@ static int enqueue_round(bmpc_handle* h) {
         launch_admm(h, st.list, st.count, st.chunk, st.need_prep ? 1 : 0);
         st.need_prep = false;
         if (chk) {
-            k_infeas<<<st.count, 128, sizeof(double) * (h->d.mc + h->d.nu + 2), h->stream>>>(h->d, h->o, h->sys, h->I, st.list, st.count, h->vprev, h->lprev, 1e-4, h->I.u0);
+            k_infeas<<<st.count, 128, sizeof(double) * (h->d.mc + h->d.nu + 2), h->stream>>>(h->d, h->o, h->sys, h->I, st.list, st.count, h->vprev, h->lprev, 1e-4, h->I.u0, h->counts);
             h->stats.launches++;
         }
         BMPC_CUDA(cudaEventRecord(h->ev[1], h->stream));
@@ -1042,7 +1042,7 @@ static int enqueue_round(bmpc_handle* h) {
         else { k_check_converged<<<(st.count + 255) / 256, 256, 0, h->stream>>>(h->I, st.list, st.count, h->cfg.eps_abs, h->cfg.eps_rel, st.nxt, h->counts); h->stats.launches++; }
     }
     BMPC_CUDA(cudaEventRecord(h->ev[2], h->stream));
-    BMPC_CUDA(cudaMemcpyAsync(h->h_count, h->counts, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, h->stream));
+    BMPC_CUDA(cudaMemcpyAsync(h->h_count, h->counts, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, h->stream));
     BMPC_CUDA(cudaGetLastError());
     return BMPC_OK;
 }
@@ -1059,6 +1059,7 @@ static int retire_round(bmpc_handle* h, int* more) {
     h->cold = false;
     st.count = h->h_count[0];
     h->stats.polish_steps += h->h_count[1];
+    h->stats.infeasible += h->h_count[3];
     st.list = st.nxt; int32_t* tmp = st.cur; st.cur = st.nxt; st.nxt = tmp;
     // polish mode: cumulative first_iters, 25, 50, 100, ...; pure ADMM: OSQP's check_termination = 25
     st.chunk = h->cfg.polish ? (st.total < 25 ? 25 - st.total : st.total) : 25;

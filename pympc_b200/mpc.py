@@ -29,6 +29,28 @@ from ._lib import BmpcConfig, BmpcError, BmpcStats, PinnedArray, ptr
 _STATUS_STR = {1: "solved", 2: "solved", -2: "maximum iterations reached", -3: "primal infeasible", -10: "unsolved"}
 
 
+class _ResInfo:
+    """`res.info` of the last solve: status_val (int or int32 array), status (OSQP's strings), polished."""
+    __slots__ = ("_st", "_scalar", "_B")
+
+    def __init__(self, st, scalar, B):
+        self._st, self._scalar, self._B = st, scalar, B
+
+    @property
+    def status_val(self):
+        return int(self._st[0]) if self._scalar else self._st
+
+    @property
+    def status(self):
+        if self._scalar:
+            return _STATUS_STR.get(int(self._st[0]), "unsolved")
+        return np.array([_STATUS_STR.get(int(s), "unsolved") for s in self._st]) if self._B <= 4096 else None
+
+    @property
+    def polished(self):
+        return bool(self._st[0] == 1) if self._scalar else self._st == 1
+
+
 def __is_vector__(vec):
     # same acceptance rule as the reference helper (mpc.py:8-17)
     if vec.ndim == 1:
@@ -345,21 +367,18 @@ class MPCController:
         self._check(self._L.bmpc_output(self._h, ptr(u.array), ptr(st.array), 0, 0))
         self._u0, self._status = u.array, st.array
         self._make_res()
-        if np.any(self._status < 0):
+        # only instances that were never KKT-verified or were certified infeasible can carry a negative status: skip the
+        # scan of the status array when the solve reports none of either
+        s = BmpcStats(); self._check(self._L.bmpc_get_stats(self._h, ctypes.byref(s)))
+        if (s.unsolved != 0 or s.infeasible != 0) and np.any(self._status < 0):
             warnings.warn('OSQP did not solve the problem!')
             if self.raise_error:
                 raise ValueError('OSQP did not solve the problem!')
 
     def _make_res(self):
-        info = types.SimpleNamespace()
-        if self.batch is None:
-            info.status_val = int(self._status[0]); info.status = _STATUS_STR.get(info.status_val, "unsolved")
-            info.polished = info.status_val == 1
-        else:
-            info.status_val = self._status
-            info.status = np.array([_STATUS_STR.get(int(s), "unsolved") for s in self._status]) if self._B <= 4096 else None
-            info.polished = self._status == 1
-        self.res = types.SimpleNamespace(info=info)
+        # the reference reads res.info.status / res.info.obj_val (mpc.py:301-327,372); built lazily: nothing is derived from
+        # the status array until somebody looks
+        self.res = types.SimpleNamespace(info=_ResInfo(self._status, self.batch is None, self._B))
 
     def output(self, return_x_seq=False, return_u_seq=False, return_eps_seq=False, return_status=False, return_obj_val=False):
         """First optimal input (and optional info); commits it as the next u_{-1}.  mpc.py:271-336."""
@@ -467,7 +486,7 @@ class MPCController:
         """Counters of the last solve (ADMM iterations, rounds, device time of the kernels)."""
         s = BmpcStats()
         self._check(self._L.bmpc_get_stats(self._h, ctypes.byref(s)))
-        return {f: getattr(s, f) for f, _ in BmpcStats._fields_ if f != "reserved"}
+        return {f: getattr(s, f) for f, _ in BmpcStats._fields_}
 
     def iterations(self):
         it = np.empty(self._B, np.int32)
