@@ -1114,25 +1114,30 @@ int bmpc_output(bmpc_handle* h, double* u0, int32_t* status, int commit_uminus1,
     BMPC_CUDA(cudaSetDevice(h->cfg.device));
     const BmpcDims& d = h->d; size_t B = h->cfg.batch;
     cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-    auto copies = [&]() -> int {
-        if (u0 && u0 != h->I.u0) BMPC_CUDA(cudaMemcpyAsync(u0, h->I.u0, sizeof(double) * B * d.nu, kind, h->stream));
-        if (status) BMPC_CUDA(cudaMemcpyAsync(status, h->I.status, sizeof(int32_t) * B, kind, h->stream));
+    const bool want_u = u0 && u0 != h->I.u0;
+    auto copy_u = [&]() -> int {
+        if (want_u) BMPC_CUDA(cudaMemcpyAsync(u0, h->I.u0, sizeof(double) * B * d.nu, kind, h->stream));
         return BMPC_OK;
     };
-    bool copied = false;
+    bool u_copied = false;
     if (h->pending) {
-        // speculate that the round in flight finishes everything (the common case): queue the result copies behind it
-        // so that a single wait covers the solve and the read-back; redo them if stragglers needed more rounds
-        if (!on_device && !commit_uminus1) { int rc = copies(); if (rc) return rc; copied = true; }
+        // speculate that the round in flight finishes everything (the common case): queue the result copy behind it so
+        // that a single wait covers the solve and the read-back; redo it if stragglers needed more rounds
+        if (!on_device && !commit_uminus1) { int rc = copy_u(); if (rc) return rc; u_copied = true; }
         int more = 0; int rc = retire_round(h, &more); if (rc) return rc;
-        if (more) { copied = false; rc = finish_solve(h); if (rc) return rc; }
-        else if (h->stats.launches && (h->st.count > 0 || !h->cfg.polish)) copied = false;   // k_finalize rewrote u0/status
+        if (more) { u_copied = false; rc = finish_solve(h); if (rc) return rc; }
+        else if (h->stats.launches && (h->st.count > 0 || !h->cfg.polish)) u_copied = false;   // k_finalize rewrote u0/status
     }
     if (commit_uminus1) BMPC_CUDA(cudaMemcpyAsync(h->um1, h->I.u0, sizeof(double) * B * d.nu, cudaMemcpyDeviceToDevice, h->stream));
-    if (!copied && (u0 || status)) {
-        int rc = copies(); if (rc) return rc;
-        if (!on_device) BMPC_CUDA(cudaStreamSynchronize(h->stream));
+    // every instance KKT-verified and none certified infeasible: the status array is all BMPC_SOLVED, no need to fetch it
+    const bool all_solved = h->cfg.polish && h->stats.unsolved == 0 && h->stats.infeasible == 0;
+    bool need_sync = false;
+    if (!u_copied && want_u) { int rc = copy_u(); if (rc) return rc; need_sync = !on_device; }
+    if (status) {
+        if (all_solved && !on_device) { for (size_t i = 0; i < B; i++) status[i] = BMPC_SOLVED; }
+        else { BMPC_CUDA(cudaMemcpyAsync(status, h->I.status, sizeof(int32_t) * B, kind, h->stream)); need_sync = !on_device; }
     }
+    if (need_sync) BMPC_CUDA(cudaStreamSynchronize(h->stream));
     return BMPC_OK;
 }
 
