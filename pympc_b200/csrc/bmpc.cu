@@ -723,7 +723,27 @@ static int configure_launch(bmpc_handle* h) {
         h->err = "problem too large for the shared-memory resident kernels"; return BMPC_ERR_ARG;
     }
     h->rmax = rmax;
+    auto setup_tiles = [&]() -> int {
+        h->tile_T = 0;
+        if (h->cfg.team_threads == 0 && h->cfg.n_sys <= 1) {
+            for (int T : {8, 4, 2}) if (!h->tile_T && bmpc_tile_smem_doubles(d, T) * 8 <= budget) h->tile_T = T;
+            // kernels per tile size {8, 4, 2}; shapes with a compiled (nx, nu) get the unrolled instantiation
+            if (d.nx == 8 && d.nu == 4) { h->tile_fn[0] = k_admm_tile<8, 2, 8, 4>; h->tile_fn[1] = k_admm_tile<4, 2, 8, 4>; h->tile_fn[2] = k_admm_tile<2, 1, 8, 4>; }
+            else { h->tile_fn[0] = k_admm_tile<8, 2, 0, 0>; h->tile_fn[1] = k_admm_tile<4, 2, 0, 0>; h->tile_fn[2] = k_admm_tile<2, 1, 0, 0>; }
+            for (int k = 0; k < 3; k++) {
+                const int T = 8 >> k;
+                if (h->tile_T >= T) BMPC_CUDA(cudaFuncSetAttribute((const void*)h->tile_fn[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bmpc_tile_smem_doubles(d, T) * 8)));
+            }
+            int th = d.NX > 2 * d.NU ? d.NX : 2 * d.NU;
+            th = ((th + 31) / 32) * 32; if (th < 128) th = 128; if (th > 512) th = 512;
+            if (h->cfg.warps_per_block > 0 && h->team != 32) th = h->cfg.warps_per_block * 32;      // tuning override
+            if (th > 512) th = 512;
+            h->tile_threads = th;
+        }
+        return BMPC_OK;
+    };
     if (team == 32) {
+
         int wpb = h->cfg.warps_per_block > 0 ? h->cfg.warps_per_block : 8;
         while (wpb > 1 && (size_t)wpb * polish_smem_doubles(d, rmax) * 8 > budget) wpb--;
         h->wpb = wpb;
@@ -741,22 +761,7 @@ static int configure_launch(bmpc_handle* h) {
         }
     } else {
         // large shapes with one shared system: the ADMM runs on tiles of T instances per CTA (bmpc_tile.cuh)
-        h->tile_T = 0;
-        if (h->cfg.team_threads == 0 && h->cfg.n_sys <= 1) {
-            for (int T : {8, 4, 2}) if (!h->tile_T && bmpc_tile_smem_doubles(d, T) * 8 <= budget) h->tile_T = T;
-            // kernels per tile size {8, 4, 2}; shapes with a compiled (nx, nu) get the unrolled instantiation
-            if (d.nx == 8 && d.nu == 4) { h->tile_fn[0] = k_admm_tile<8, 2, 8, 4>; h->tile_fn[1] = k_admm_tile<4, 2, 8, 4>; h->tile_fn[2] = k_admm_tile<2, 1, 8, 4>; }
-            else { h->tile_fn[0] = k_admm_tile<8, 2, 0, 0>; h->tile_fn[1] = k_admm_tile<4, 2, 0, 0>; h->tile_fn[2] = k_admm_tile<2, 1, 0, 0>; }
-            for (int k = 0; k < 3; k++) {
-                const int T = 8 >> k;
-                if (h->tile_T >= T) BMPC_CUDA(cudaFuncSetAttribute((const void*)h->tile_fn[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bmpc_tile_smem_doubles(d, T) * 8)));
-            }
-            int th = d.NX > 2 * d.NU ? d.NX : 2 * d.NU;
-            th = ((th + 31) / 32) * 32; if (th < 128) th = 128; if (th > 512) th = 512;
-            if (h->cfg.warps_per_block > 0) th = h->cfg.warps_per_block * 32;      // tuning override
-            if (th > 512) th = 512;
-            h->tile_threads = th;
-        }
+        { int rc = setup_tiles(); if (rc) return rc; }
         if (h->cfg.rmax == 0 && rmax > 96) { h->rmax_small = 80; h->smem_polish_small = polish_smem_doubles(d, 80) * 8; }
         h->wpb = team / 32;
         h->smem_admm = admm_smem_doubles(d) * 8;
@@ -969,7 +974,7 @@ static void launch_admm(bmpc_handle* h, const int32_t* list, int count, int nite
         // stragglers of a warp-team / fast-path handle: one warp per CTA (the lanes-own-rows ADMM has the shortest
         // dependent chain per iteration for these small shapes: measured 5 % on the random-instance bench vs a 128-thread CTA)
         k_admm<true><<<count, 32, admm_smem_doubles(h->d) * 8, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
-    } else if (h->team == 32) {
+    } else if (h->team == 32 && h->tile_T == 0) {
         int grid = (count + h->wpb - 1) / h->wpb;
         k_admm<true><<<grid, h->wpb * 32, h->smem_admm, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, niter, do_prep, cold, h->xref_mode, h->cfg.polish ? 1 : 0);
     } else if (h->tile_T > 0) {
