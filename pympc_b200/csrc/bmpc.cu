@@ -433,7 +433,7 @@ __device__ __forceinline__ void tpi_load_v(const BmpcInst& I, int inst0, int nva
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-template <class S>
+template <class S, bool TV>
 __global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmmParams<S> P, BmpcInst I, const int32_t* __restrict__ list, int B, int niter, int cold,
                                                  int reset, int32_t* counts, double* um1_solved) {
     // list == nullptr: instances blockIdx*32 .. +31 (coalesced transpose of the iterate through shared memory);
@@ -452,7 +452,9 @@ __global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmm
     }
     double x0[S::nx], um1[S::nu], xref[S::nx], x[S::NU];
 #pragma unroll
-    for (int q = 0; q < S::nx; q++) { x0[q] = valid ? I.x0[(size_t)inst * S::nx + q] : 0.0; xref[q] = valid ? I.xref[(size_t)inst * S::nx + q] : 0.0; }
+    for (int q = 0; q < S::nx; q++) { x0[q] = valid ? I.x0[(size_t)inst * S::nx + q] : 0.0; xref[q] = (valid && !TV) ? I.xref[(size_t)inst * S::nx + q] : 0.0; }
+    // constant reference: in registers; time-varying: this instance's (Np+1) x nx block in global memory
+    const TpiXref<S, TV> xr{TV ? I.xref + (size_t)inst * S::NX : xref};
 #pragma unroll
     for (int q = 0; q < S::nu; q++) um1[q] = valid ? I.um1[(size_t)inst * S::nu + q] : 0.0;
 #pragma unroll
@@ -466,7 +468,7 @@ __global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmm
         }
         if (blockIdx.x == 0 && lane == 0) { counts[0] = 0; counts[1] = 0; counts[2] = 0; counts[3] = 0; }
     }
-    if (valid) tpi_admm<S>(P, V, x0, um1, xref, x, niter, cold != 0);
+    if (valid) tpi_admm<S>(P, V, x0, um1, xr, x, niter, cold != 0);
     __syncwarp();
     if (list) {
         if (valid) {
@@ -492,12 +494,13 @@ __global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmm
 
 // one instance of the TPI polish (the column W holds v on entry); returns true when KKT-verified, in which case
 // v* is staged in the column (slots, see below) and U / u0 / status are written
-template <class S>
+template <class S, bool TV>
 __device__ __forceinline__ bool tpi_polish_thread(const TpiRicParams<S>& P, BmpcInst& I, int inst, TpiAcc W, int max_steps,
                                                   int32_t* next_list, int32_t* next_count, double* u0_out) {
     double x0[S::nx], um1[S::nu], xref[S::nx];
 #pragma unroll
-    for (int q = 0; q < S::nx; q++) { x0[q] = I.x0[(size_t)inst * S::nx + q]; xref[q] = I.xref[(size_t)inst * S::nx + q]; }
+    for (int q = 0; q < S::nx; q++) { x0[q] = I.x0[(size_t)inst * S::nx + q]; xref[q] = TV ? 0.0 : I.xref[(size_t)inst * S::nx + q]; }
+    const TpiXref<S, TV> xr{TV ? I.xref + (size_t)inst * S::NX : xref};
 #pragma unroll
     for (int q = 0; q < S::nu; q++) um1[q] = I.um1[(size_t)inst * S::nu + q];
     const TpiCommon<S>& c = P.c;
@@ -510,7 +513,7 @@ __device__ __forceinline__ bool tpi_polish_thread(const TpiRicParams<S>& P, Bmpc
     constexpr int nz1 = S::nx + 2;
     double* udst = I.Us + (size_t)inst * S::NU;
     double u_first = 0.0;
-    const int ps = tpi_polish_riccati<S>(P, W, x0, um1, xref, up, dn, max_steps,
+    const int ps = tpi_polish_riccati<S>(P, W, x0, um1, xr, up, dn, max_steps,
         [&](int i, double zi, double mu, double irho) {
             int slot;
             if (i < S::NS) slot = (i / S::nx) * nz1 + (i % S::nx);
@@ -533,7 +536,7 @@ __device__ __forceinline__ bool tpi_polish_thread(const TpiRicParams<S>& P, Bmpc
     return ps > 0;
 }
 
-template <class S>
+template <class S, bool TV>
 __global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiRicParams<S> P, BmpcInst I, const int32_t* __restrict__ list, int B, int max_steps,
                                                    int32_t* next_list, int32_t* next_count, double* u0_out) {
     extern __shared__ double smem[];
@@ -545,7 +548,7 @@ __global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiRi
         if (lane < nvalid) { const double* src = I.vw + (size_t)inst * S::mc + S::nx; for (int i = 0; i < S::MT; i++) W(i) = src[i]; }
     } else { tpi_load_v<S>(I, idx0, nvalid, smem, 0); }
     __syncwarp();
-    const bool ok = (lane < nvalid) && tpi_polish_thread<S>(P, I, inst, W, max_steps, next_list, next_count, u0_out);
+    const bool ok = (lane < nvalid) && tpi_polish_thread<S, TV>(P, I, inst, W, max_steps, next_list, next_count, u0_out);
     const unsigned okmask = __ballot_sync(0xffffffffu, ok);
     __syncwarp();
     constexpr int nz1 = S::nx + 2;
@@ -642,18 +645,28 @@ static std::string g_create_err;
 template <class S>
 static void launch_tpi_round(bmpc_handle* h, const int32_t* list, int count, int niter, int32_t* next_list, cudaEvent_t mid) {
     const int grid = (count + 31) / 32;
-    k_tpi_admm<S><<<grid, 32, S::AROWS * TPI_STR * 8, h->stream>>>(*(const TpiAdmmParams<S>*)h->tpi_admm_params, h->I, list, count, niter, h->cold ? 1 : 0,
-                                                                   h->st.round == 0 ? 1 : 0, h->counts, h->um1_solved);
+    const TpiAdmmParams<S>& PA = *(const TpiAdmmParams<S>*)h->tpi_admm_params;
+    const TpiRicParams<S>& PR = *(const TpiRicParams<S>*)h->tpi_polish_params;
+    const int cold = h->cold ? 1 : 0, reset = h->st.round == 0 ? 1 : 0;
+    if (h->xref_mode)   // one (Np+1) x nx reference per instance
+        k_tpi_admm<S, true><<<grid, 32, S::AROWS * TPI_STR * 8, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts, h->um1_solved);
+    else
+        k_tpi_admm<S, false><<<grid, 32, S::AROWS * TPI_STR * 8, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts, h->um1_solved);
     cudaEventRecord(mid, h->stream);
-    k_tpi_polish<S><<<grid, 32, S::PROWS * TPI_STR * 8, h->stream>>>(*(const TpiRicParams<S>*)h->tpi_polish_params, h->I, list, count,
-                                                                     h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
+    if (h->xref_mode)
+        k_tpi_polish<S, true><<<grid, 32, S::PROWS * TPI_STR * 8, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
+    else
+        k_tpi_polish<S, false><<<grid, 32, S::PROWS * TPI_STR * 8, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
     h->stats.launches += 2;
 }
 
 template <class S>
 static void launch_tpi_polish_only(bmpc_handle* h, const int32_t* list, int count, int32_t* next_list) {
-    k_tpi_polish<S><<<(count + 31) / 32, 32, S::PROWS * TPI_STR * 8, h->stream>>>(*(const TpiRicParams<S>*)h->tpi_polish_params, h->I, list, count,
-                                                                                h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
+    const TpiRicParams<S>& PR = *(const TpiRicParams<S>*)h->tpi_polish_params;
+    if (h->xref_mode)
+        k_tpi_polish<S, true><<<(count + 31) / 32, 32, S::PROWS * TPI_STR * 8, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
+    else
+        k_tpi_polish<S, false><<<(count + 31) / 32, 32, S::PROWS * TPI_STR * 8, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
     h->stats.launches++;
 }
 
@@ -663,8 +676,10 @@ static void tpi_fill_entry(const double* hs, const BmpcSysOff& o, void* pa, void
 }
 template <class S>
 static int tpi_configure_entry() {
-    if (cudaFuncSetAttribute(k_tpi_admm<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::AROWS * TPI_STR * 8)) != cudaSuccess) return 1;
-    if (cudaFuncSetAttribute(k_tpi_polish<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::PROWS * TPI_STR * 8)) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(k_tpi_admm<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::AROWS * TPI_STR * 8)) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(k_tpi_admm<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::AROWS * TPI_STR * 8)) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(k_tpi_polish<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::PROWS * TPI_STR * 8)) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(k_tpi_polish<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::PROWS * TPI_STR * 8)) != cudaSuccess) return 1;
     return 0;
 }
 #define BMPC_TPI_SHAPE(NX_, NU_, NP_, NC_)                                                                                   \
@@ -1016,7 +1031,7 @@ static int enqueue_round(bmpc_handle* h) {
     if (st.chunk > h->cfg.max_iter - st.total) st.chunk = h->cfg.max_iter - st.total;
     // fast path (thread-per-instance kernels, throughput-optimised) for the first round; the few stragglers are
     // latency-bound and go to the CTA-per-instance team kernels
-    const bool tpi = st.round == 0 && h->tpi_kind && h->cfg.polish && h->xref_mode == 0;
+    const bool tpi = st.round == 0 && h->tpi_kind && h->cfg.polish;
     if (!tpi) {
         if (st.round == 0) {
             const int B = h->cfg.batch;
@@ -1041,7 +1056,7 @@ static int enqueue_round(bmpc_handle* h) {
         }
         BMPC_CUDA(cudaEventRecord(h->ev[1], h->stream));
         // stragglers of a fast-path shape: the Riccati polish (list mode) has ~3x lower latency than the team Schur polish
-        if (h->cfg.polish && h->tpi_kind && h->xref_mode == 0 && st.total + st.chunk <= 200)
+        if (h->cfg.polish && h->tpi_kind && st.total + st.chunk <= 200)
             g_tpi_table[h->tpi_kind - 1].launch_polish(h, st.list, st.count, st.nxt);
         else if (h->cfg.polish) launch_polish(h, st.list, st.count, st.nxt, h->counts);
         else { k_check_converged<<<(st.count + 255) / 256, 256, 0, h->stream>>>(h->I, st.list, st.count, h->cfg.eps_abs, h->cfg.eps_rel, st.nxt, h->counts); h->stats.launches++; }
@@ -1101,7 +1116,7 @@ int bmpc_solve(bmpc_handle* h) {
     st.list = nullptr; st.count = B; st.cur = h->listA; st.nxt = h->listB;
     st.total = 0; st.round = 0; st.need_prep = true;
     // first round: 3 iterations on the fast path (measured: as good as 10 for the warm active-set guess), 10 on the team kernels
-    const bool fast = h->tpi_kind && h->xref_mode == 0;
+    const bool fast = h->tpi_kind != 0;
     st.chunk = h->cfg.polish ? (h->cfg.first_iters > 0 ? h->cfg.first_iters : (fast ? 3 : 10)) : 25;
     // a cold start has no active-set guess to refresh: 25 iterations at once on the fast path, so that the first polish
     // usually verifies and the whole batch does not take the straggler route

@@ -43,6 +43,7 @@ template <class S>
 struct TpiCommon {
     double Ad[S::nx * S::nx], Bd[S::nx * S::nu];
     double Gx0[S::NU * S::nx], Gref[S::NU * S::nx], g0[S::NU], QDu[S::nu * S::nu];
+    double Qx[S::nx * S::nx], QxN[S::nx * S::nx];      // stage / terminal state weights (time-varying reference only)
     double xmin[S::nx], xmax[S::nx], c1x[S::nx], c2x[S::nx], rhox[S::nx];
     double umin[S::nu], umax[S::nu], rhou[S::nu];
     double dmin[S::nu], dmax[S::nu], rhod[S::nu];
@@ -79,39 +80,86 @@ BMPC_HD void tpi_dbounds(const TpiCommon<S>& c, const double* um1, int rr, doubl
     if (rr < S::nu) { lo += um1[rr]; hi += um1[rr]; }
 }
 
-// true linear term g (NU) of the condensed QP for this instance (constant xref)
-template <class S>
-BMPC_HD void tpi_linear_term(const TpiCommon<S>& c, const double* x0, const double* um1, const double* xref, double* g) {
+// Reference accessor: xr(k, b) = component b of the reference of stage k.  TV = false: one constant reference held in the
+// caller's registers (p points at a local array, k is ignored); TV = true: this instance's (Np+1) x nx reference in global
+// memory (mpc.py:414-421).
+template <class S, bool TV_>
+struct TpiXref {
+    static constexpr bool TV = TV_;
+    const double* p;
+    BMPC_HD double operator()(int k, int b) const { return TV_ ? p[k * S::nx + b] : p[b]; }
+};
+
+// true linear term g (NU) of the condensed QP for this instance
+template <class S, class XR>
+BMPC_HD void tpi_linear_term(const TpiCommon<S>& c, const double* x0, const double* um1, XR xr, double* g) {
+    constexpr int nx = S::nx, nu = S::nu;
 #pragma unroll
     for (int a = 0; a < S::NU; a++) {
         double acc = c.g0[a];
 #pragma unroll
-        for (int q = 0; q < S::nx; q++) acc += c.Gx0[a * S::nx + q] * x0[q] + c.Gref[a * S::nx + q] * xref[q];
-        if (a < S::nu) {
+        for (int q = 0; q < nx; q++) acc += c.Gx0[a * nx + q] * x0[q];
+        if (!XR::TV) {
 #pragma unroll
-            for (int q = 0; q < S::nu; q++) acc -= c.QDu[a * S::nu + q] * um1[q];
+            for (int q = 0; q < nx; q++) acc += c.Gref[a * nx + q] * xr(0, q);
+        }
+        if (a < nu) {
+#pragma unroll
+            for (int q = 0; q < nu; q++) acc -= c.QDu[a * nu + q] * um1[q];
         }
         g[a] = acc;
     }
 }
 
+// time-varying reference: the part -Bcal' P_X xref of g, by the adjoint recursion  lam_k = -Q_k xref_k + Ad' lam_{k+1},
+// g_{k-1} += Bd' lam_k;  add(j, value) accumulates into wherever the caller keeps g (dynamic index: not a register array)
+template <class S, class XR, class ADD>
+BMPC_HD void tpi_linear_term_tv(const TpiCommon<S>& c, XR xr, ADD add) {
+    static_assert(S::Nc == S::Np, "fast path: Nc == Np");
+    constexpr int nx = S::nx, nu = S::nu;
+    double lam[nx];
+#pragma unroll
+    for (int a = 0; a < nx; a++) lam[a] = 0.0;
+#pragma unroll 1
+    for (int k = S::Np; k >= 1; k--) {
+        double ln[nx];
+#pragma unroll
+        for (int a = 0; a < nx; a++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < nx; q++) acc += c.Ad[q * nx + a] * lam[q] - (k == S::Np ? c.QxN[a * nx + q] : c.Qx[a * nx + q]) * xr(k, q);
+            ln[a] = acc;
+        }
+#pragma unroll
+        for (int a = 0; a < nx; a++) lam[a] = ln[a];
+#pragma unroll
+        for (int b = 0; b < nu; b++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < nx; q++) acc += c.Bd[q * nu + b] * lam[q];
+            add((k - 1) * nu + b, acc);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // niter ADMM iterations.  V: this thread's iterate v (MT rows).  x: NU registers (in/out).
-template <class S>
-BMPC_HD void tpi_admm(const TpiAdmmParams<S>& P, TpiAcc V, const double* x0, const double* um1, const double* xref,
+template <class S, class XR>
+BMPC_HD void tpi_admm(const TpiAdmmParams<S>& P, TpiAcc V, const double* x0, const double* um1, XR xr,
                       double* x, int niter, bool cold) {
     constexpr int nx = S::nx, nu = S::nu, Np = S::Np, Nc = S::Nc, NS = S::NS, NU = S::NU;
     const TpiCommon<S>& c = P.c;
     // g' = g + B' R_x Acal x0 is parked in rows [MT, MT+NU) of this thread's column (read once per iteration)
     {
         double gp[NU];
-        tpi_linear_term<S>(c, x0, um1, xref, gp);
+        tpi_linear_term<S>(c, x0, um1, xr, gp);
 #pragma unroll
         for (int a = 0; a < NU; a++) {
 #pragma unroll
             for (int q = 0; q < nx; q++) gp[a] += P.Gcc[a * nx + q] * x0[q];
             V(S::MT + a) = gp[a];
         }
+        if (XR::TV) tpi_linear_term_tv<S>(c, xr, [&](int j, double val) { V(S::MT + j) += val; });
     }
     if (cold) {
         // x = 0, v = A x + cc : free response on the state rows, zeros elsewhere
@@ -323,8 +371,8 @@ BMPC_HD int tpi_pin_of(const TpiCommon<S>& c, const TpiSets& up, const TpiSets& 
     val = 0.0; return TPI_FREE;
 }
 
-template <class S>
-BMPC_HD void tpi_ric_backward(const TpiRicParams<S>& P, TpiAcc W, const double* xref, const TpiSets& up, const TpiSets& dn) {
+template <class S, class XR>
+BMPC_HD void tpi_ric_backward(const TpiRicParams<S>& P, TpiAcc W, XR xr, const TpiSets& up, const TpiSets& dn) {
     static_assert(S::nu == 1 && S::Nc == S::Np, "Riccati polish is specialised to nu == 1, Nc == Np");
     constexpr int nx = S::nx, N = S::Np, nz = nx + 1;
     const TpiCommon<S>& c = P.c;
@@ -338,7 +386,7 @@ BMPC_HD void tpi_ric_backward(const TpiRicParams<S>& P, TpiAcc W, const double* 
             const bool vu = (bu >> a) & 1u, vd = (bd >> a) & 1u;
             double q = 0.0;
 #pragma unroll
-            for (int b = 0; b < nx; b++) { Pxx[a * nx + b] = P.QxN[a * nx + b]; q += P.QxN[a * nx + b] * xref[b]; }
+            for (int b = 0; b < nx; b++) { Pxx[a * nx + b] = P.QxN[a * nx + b]; q += P.QxN[a * nx + b] * xr(N, b); }
             if (vu || vd) { Pxx[a * nx + a] += P.rho_e; q += P.rho_e * (vu ? c.xmax[a] : c.xmin[a]); }
             px[a] = -q; pxw[a] = 0.0;
         }
@@ -386,7 +434,7 @@ BMPC_HD void tpi_ric_backward(const TpiRicParams<S>& P, TpiAcc W, const double* 
                 const bool vu = (bu >> a) & 1u, vd = (bd >> a) & 1u;
                 double q = 0.0;
 #pragma unroll
-                for (int b = 0; b < nx; b++) { Hxx[a * nx + b] += P.Qx[a * nx + b]; q += P.Qx[a * nx + b] * xref[b]; }
+                for (int b = 0; b < nx; b++) { Hxx[a * nx + b] += P.Qx[a * nx + b]; q += P.Qx[a * nx + b] * xr(k, b); }
                 if (vu || vd) { Hxx[a * nx + a] += P.rho_e; q += P.rho_e * (vu ? c.xmax[a] : c.xmin[a]); }
                 gx[a] -= q;
             }
@@ -520,13 +568,13 @@ BMPC_HD bool tpi_ric_forward(const TpiRicParams<S>& P, TpiAcc W, const double* x
 // returns steps used (>0) when KKT-verified, 0 otherwise.  Every forward sweep verifies AND emits through out / outu (row
 // values v* = z* + y*/rho, inputs u_j): the values of the accepted (last) sweep are the solution, earlier ones are
 // overwritten, so no separate emit pass is needed.
-template <class S, class FR, class FU>
-BMPC_HD int tpi_polish_riccati(const TpiRicParams<S>& P, TpiAcc W, const double* x0, const double* um1, const double* xref,
+template <class S, class XR, class FR, class FU>
+BMPC_HD int tpi_polish_riccati(const TpiRicParams<S>& P, TpiAcc W, const double* x0, const double* um1, XR xr,
                                TpiSets& up, TpiSets& dn, int max_steps, FR out, FU outu) {
     double mumax = 0.0;
 #pragma unroll 1
     for (int step = 0; step < max_steps; step++) {
-        tpi_ric_backward<S>(P, W, xref, up, dn);
+        tpi_ric_backward<S>(P, W, xr, up, dn);
         TpiSets nup, ndn;
         const bool ok = tpi_ric_forward<S, 2>(P, W, x0, um1, up, dn, nup, ndn, mumax, out, outu);
         if (ok) return step + 1;
@@ -545,6 +593,7 @@ inline void tpi_fill_common(const double* sys, const BmpcSysOff& o, TpiCommon<S>
     for (int i = 0; i < NU * nx; i++) { c.Gx0[i] = sys[o.Gx0 + i]; c.Gref[i] = sys[o.Gref + i]; }
     for (int i = 0; i < NU; i++) c.g0[i] = sys[o.g0 + i];
     for (int i = 0; i < nu * nu; i++) c.QDu[i] = sys[o.QDu + i];
+    for (int i = 0; i < nx * nx; i++) { c.Qx[i] = sys[o.Qx + i]; c.QxN[i] = sys[o.QxN + i]; }
     const double rho_e = sys[o.scal + BMPC_S_RHOE];
     c.inv_rho_e = rho_e > 0.0 ? 1.0 / rho_e : 0.0;
     c.sigma = sys[o.scal + BMPC_S_SIGMA]; c.alpha = sys[o.scal + BMPC_S_ALPHA];

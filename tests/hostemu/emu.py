@@ -72,16 +72,17 @@ class EmuSystem:
         return U, st, it.value, ps.value, res
 
     def tpi_step(self, x0, um1, xref, first_iters=10, pdas_steps=8):
-        """TPI fast path (ADMM + Riccati polish) on the same generic-layout state; returns (U, polish_steps)."""
+        """TPI fast path (ADMM + Riccati polish) on the same generic-layout state; xref (nx) or time-varying (Np+1, nx).
+        Returns (U, polish_steps)."""
         x0 = np.ascontiguousarray(x0, float); um1 = np.ascontiguousarray(um1, float); xref = np.ascontiguousarray(xref, float)
+        mode = 0 if xref.ndim == 1 else 1
         U = np.zeros(self.NU)
         f = self.L.emu_tpi_step
-        f.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 4 + [ctypes.c_int] + [ctypes.c_void_p] * 3 + [ctypes.c_int] * 2
-        ps = f(self.nx, self.nu, self.Np, self.Nc, _p(self.sys), _p(x0), _p(um1), _p(xref), self.cold, _p(self.x), _p(self.v), _p(U),
+        f.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 4 + [ctypes.c_int] * 2 + [ctypes.c_void_p] * 3 + [ctypes.c_int] * 2
+        ps = f(self.nx, self.nu, self.Np, self.Nc, _p(self.sys), _p(x0), _p(um1), _p(xref), mode, self.cold, _p(self.x), _p(self.v), _p(U),
                first_iters, pdas_steps)
         self.cold = 0
         return U, ps
-
 
     def tile_compare(self, X0, Um1, Xref, niter, lvl=None, x_in=None, v_in=None, T=4):
         """Run the tile ADMM and the per-instance team ADMM on the same T (2, 4 or 8) instances; returns (ref, tile) dicts."""

@@ -79,23 +79,24 @@ int emu_solve(int nx, int nu, int Np, int Nc, const double* sys, const double* x
 // TPI fast path for one instance (nu == 1, Nc == Np shapes): first_iters ADMM iterations + Riccati polish on the
 // generic-layout state (x [NU], v [mc], in/out) exactly like the device kernels.  Returns polish steps (>0 verified,
 // 0 not verified, -100 shape not compiled).
-template <class S>
+template <class S, bool TV>
 static int emu_tpi_run(const double* sys, const double* x0, const double* um1, const double* xref, int cold, double* x,
                            double* v, double* Uout, int first_iters, int pdas_steps) {
+    const TpiXref<S, TV> xr{xref};
     BmpcDims d = bmpc_make_dims(S::nx, S::nu, S::Np, S::Nc); BmpcSysOff o = bmpc_make_off(d);
     TpiAdmmParams<S>* PA = new TpiAdmmParams<S>(); TpiRicParams<S>* PR = new TpiRicParams<S>();
     tpi_fill_admm<S>(sys, o, *PA); tpi_fill_riccati<S>(sys, o, *PR);
     double* col = (double*)calloc(S::PROWS + S::AROWS + 8, sizeof(double));
     for (int i = 0; i < S::MT; i++) col[i] = v[i + S::nx];
     TpiAcc V{col, 1};
-    tpi_admm<S>(*PA, V, x0, um1, xref, x, first_iters, cold != 0);
+    tpi_admm<S>(*PA, V, x0, um1, xr, x, first_iters, cold != 0);
     for (int i = 0; i < S::MT; i++) v[i + S::nx] = col[i];
     for (int i = 0; i < S::nx; i++) v[i] = x0[i];
     TpiSets up, dn;
     tpi_sets_from_v<S>(PR->c, um1, V, up, dn);
     // the polish emits on every forward sweep; keep the values of the accepted one
     double vstar[S::MT], Ustar[S::NU];
-    int ps = tpi_polish_riccati<S>(*PR, V, x0, um1, xref, up, dn, pdas_steps,
+    int ps = tpi_polish_riccati<S>(*PR, V, x0, um1, xr, up, dn, pdas_steps,
         [&](int i, double zi, double mu, double irho) { vstar[i] = zi + mu * irho; },
         [&](int j, double u) { Ustar[j] = u; });
     if (ps > 0) {
@@ -107,9 +108,13 @@ static int emu_tpi_run(const double* sys, const double* x0, const double* um1, c
 }
 
 extern "C" int emu_tpi_step(int nx, int nu, int Np, int Nc, const double* sys, const double* x0, const double* um1, const double* xref,
-                 int cold, double* x, double* v, double* Uout, int first_iters, int pdas_steps) {
-    if (nx == 4 && nu == 1 && Np == 20 && Nc == 20) return emu_tpi_run<TpiShape<4, 1, 20, 20>>(sys, x0, um1, xref, cold, x, v, Uout, first_iters, pdas_steps);
-    if (nx == 2 && nu == 1 && Np == 20 && Nc == 20) return emu_tpi_run<TpiShape<2, 1, 20, 20>>(sys, x0, um1, xref, cold, x, v, Uout, first_iters, pdas_steps);
+                 int xref_mode, int cold, double* x, double* v, double* Uout, int first_iters, int pdas_steps) {
+#define EMU_TPI_ARGS sys, x0, um1, xref, cold, x, v, Uout, first_iters, pdas_steps
+    if (nx == 4 && nu == 1 && Np == 20 && Nc == 20)
+        return xref_mode ? emu_tpi_run<TpiShape<4, 1, 20, 20>, true>(EMU_TPI_ARGS) : emu_tpi_run<TpiShape<4, 1, 20, 20>, false>(EMU_TPI_ARGS);
+    if (nx == 2 && nu == 1 && Np == 20 && Nc == 20)
+        return xref_mode ? emu_tpi_run<TpiShape<2, 1, 20, 20>, true>(EMU_TPI_ARGS) : emu_tpi_run<TpiShape<2, 1, 20, 20>, false>(EMU_TPI_ARGS);
+#undef EMU_TPI_ARGS
     return -100;
 }
 

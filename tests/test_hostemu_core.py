@@ -153,3 +153,31 @@ def test_primal_infeasibility_certificate():
     for it in (25, 400):
         assert not hard.infeasible(np.array([0.1, 0.2]), um1, cfg["xref"], it0=it, it1=it)
         assert not soft.infeasible(np.array([3.5, 0.0]), um1, cfg["xref"], it0=it, it1=it)
+
+
+@pytest.mark.parametrize("name", ["pend", "pm"])
+def test_tpi_fast_path_time_varying_reference(name):
+    """SURVEY 8f-2 on the fast path: a (Np+1, nx) reference per instance (mpc.py:414-421) through the thread-per-instance
+    ADMM (linear term by the adjoint recursion) and the Riccati polish (stage-wise linear terms): closed loop vs the exact
+    solver on the oracle-assembled QP and vs the generic team code."""
+    from oracle.kkt import solve_exact
+    cfg = CASES[name](); Np = cfg.get("Np", 20); nx = len(cfg["x0"])
+    rng = np.random.default_rng(8)
+    E = EmuSystem(cfg); G = EmuSystem(cfg)
+    x = np.asarray(cfg["x0"], float).copy(); um1 = np.asarray(cfg["uminus1"], float).reshape(-1).copy()
+    fast = 0
+    for t in range(6):
+        # a reference that moves along the horizon (ramp + a wiggle on the first state)
+        Xtv = np.tile(np.asarray(cfg["xref"], float), (Np + 1, 1)) * np.linspace(0.4, 1.0, Np + 1)[:, None]
+        Xtv[:, 0] += 0.05 * np.sin(0.3 * (np.arange(Np + 1) + t)) + 0.02 * rng.standard_normal()
+        U, ps = E.tpi_step(x, um1, Xtv, first_iters=10)
+        fast += ps > 0
+        if ps <= 0:                                             # stragglers take the generic route, like on the device
+            U, st, *_ = E.solve(x, um1, Xtv); assert st == 1
+        Ug, st, *_ = G.solve(x, um1, Xtv); assert st == 1
+        Q = QPData(**dict(cfg, x0=x, uminus1=um1, xref=Xtv)); z, y, r = solve_exact(Q.P, Q.q, Q.A, Q.l, Q.u)
+        ref = z[Q.NX:Q.NX + Q.NU]
+        assert np.max(np.abs(Ug - ref)) < 1e-7
+        assert np.max(np.abs(U - ref)) < 1e-7, (t, ps)
+        um1 = U[:1].copy(); x = cfg["Ad"] @ x + cfg["Bd"] @ um1
+    assert fast >= 4                                            # the fast path itself verified most steps
