@@ -344,6 +344,10 @@ def main():
 
     import torch
     import torch.distributed as dist
+    # native libraries (NCCL's version banner, ...) write to file descriptor 1: park it on stderr while the run is in
+    # progress so that stdout carries exactly the one JSON line of rank 0
+    sys.stdout.flush()
+    saved_stdout = os.dup(1); os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -356,7 +360,9 @@ def main():
             out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         elif not args.no_cpu_baseline:
             out["cpu_baseline"] = None
-        print(json.dumps(out))
+    sys.stdout.flush(); os.dup2(saved_stdout, 1); os.close(saved_stdout)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
