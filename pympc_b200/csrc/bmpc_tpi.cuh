@@ -35,7 +35,6 @@ struct TpiShape {
     static constexpr int MT = NS + NU + ND;
     static constexpr int NX = (NPc + 1) * NXc;
     static constexpr int mc = NX + NU + ND;
-    static constexpr int AROWS = MT + NCc * NUc;             // ADMM column: v rows + g'
     static constexpr int PROWS = (MT > 6 * NPc ? MT : 6 * NPc) + 1;   // polish workspace rows: v (load) / Riccati gains
 };
 
@@ -144,12 +143,14 @@ BMPC_HD void tpi_linear_term_tv(const TpiCommon<S>& c, XR xr, ADD add) {
 
 // ------------------------------------------------------------------------------------------------
 // niter ADMM iterations.  V: this thread's iterate v (MT rows).  x: NU registers (in/out).
+// G: where g' (NU values, read once per iteration) is parked: rows [MT, MT+NU) of the column, or a per-instance scratch in
+// global memory (frees shared memory: one more resident warp per SM)
 template <class S, class XR>
-BMPC_HD void tpi_admm(const TpiAdmmParams<S>& P, TpiAcc V, const double* x0, const double* um1, XR xr,
+BMPC_HD void tpi_admm(const TpiAdmmParams<S>& P, TpiAcc V, TpiAcc G, const double* x0, const double* um1, XR xr,
                       double* x, int niter, bool cold) {
     constexpr int nx = S::nx, nu = S::nu, Np = S::Np, Nc = S::Nc, NS = S::NS, NU = S::NU;
     const TpiCommon<S>& c = P.c;
-    // g' = g + B' R_x Acal x0 is parked in rows [MT, MT+NU) of this thread's column (read once per iteration)
+    // g' = g + B' R_x Acal x0 is parked in G (read once per iteration)
     {
         double gp[NU];
         tpi_linear_term<S>(c, x0, um1, xr, gp);
@@ -157,9 +158,9 @@ BMPC_HD void tpi_admm(const TpiAdmmParams<S>& P, TpiAcc V, const double* x0, con
         for (int a = 0; a < NU; a++) {
 #pragma unroll
             for (int q = 0; q < nx; q++) gp[a] += P.Gcc[a * nx + q] * x0[q];
-            V(S::MT + a) = gp[a];
+            G(a) = gp[a];
         }
-        if (XR::TV) tpi_linear_term_tv<S>(c, xr, [&](int j, double val) { V(S::MT + j) += val; });
+        if (XR::TV) tpi_linear_term_tv<S>(c, xr, [&](int j, double val) { G(j) += val; });
     }
     if (cold) {
         // x = 0, v = A x + cc : free response on the state rows, zeros elsewhere
@@ -227,7 +228,7 @@ BMPC_HD void tpi_admm(const TpiAdmmParams<S>& P, TpiAcc V, const double* x0, con
 #pragma unroll
                 for (int b = nu - 1; b >= 0; b--) {
                     const int s2 = j * nu + b;
-                    double r = c.sigma * x[s2] - V(S::MT + s2) + ((j == Nc - 1) ? hold[b] : 0.0);
+                    double r = c.sigma * x[s2] - G(s2) + ((j == Nc - 1) ? hold[b] : 0.0);
 #pragma unroll
                     for (int q = 0; q < nx; q++) r += c.Bd[q * nu + b] * lam[q];
                     const double vu = V(NS + s2);

@@ -86,10 +86,11 @@ static int emu_tpi_run(const double* sys, const double* x0, const double* um1, c
     BmpcDims d = bmpc_make_dims(S::nx, S::nu, S::Np, S::Nc); BmpcSysOff o = bmpc_make_off(d);
     TpiAdmmParams<S>* PA = new TpiAdmmParams<S>(); TpiRicParams<S>* PR = new TpiRicParams<S>();
     tpi_fill_admm<S>(sys, o, *PA); tpi_fill_riccati<S>(sys, o, *PR);
-    double* col = (double*)calloc(S::PROWS + S::AROWS + 8, sizeof(double));
+    double* col = (double*)calloc(S::PROWS + S::MT + S::NU + 8, sizeof(double));
     for (int i = 0; i < S::MT; i++) col[i] = v[i + S::nx];
     TpiAcc V{col, 1};
-    tpi_admm<S>(*PA, V, x0, um1, xr, x, first_iters, cold != 0);
+    TpiAcc G{col + S::MT, 1};
+    tpi_admm<S>(*PA, V, G, x0, um1, xr, x, first_iters, cold != 0);
     for (int i = 0; i < S::MT; i++) v[i + S::nx] = col[i];
     for (int i = 0; i < S::nx; i++) v[i] = x0[i];
     TpiSets up, dn;
