@@ -27,11 +27,12 @@ def build(force=False, verbose=False):
     return LIB
 
 
-def add_shape(nx, nu, Np):
-    """Register one more compile-time fast-path shape (nu must be 1, Nc = Np) and rebuild."""
-    if nu != 1 or Np * nx > 128 or Np >= 32:
-        raise ValueError("fast-path shapes need nu == 1, Np*nx <= 128, Np < 32")
-    line = f"BMPC_TPI_SHAPE({nx}, {nu}, {Np}, {Np})"
+def add_shape(nx, nu, Np, Nc=None):
+    """Register one more compile-time fast-path shape (nu must be 1, Nc <= Np, default Nc = Np) and rebuild."""
+    Nc = Np if Nc is None else Nc
+    if nu != 1 or Np * nx > 128 or Np >= 32 or not (1 <= Nc <= Np):
+        raise ValueError("fast-path shapes need nu == 1, Np*nx <= 128, Np < 32, 1 <= Nc <= Np")
+    line = f"BMPC_TPI_SHAPE({nx}, {nu}, {Np}, {Nc})"
     txt = open(SHAPES).read()
     if line not in txt:
         open(SHAPES, "a").write(line + "\n")

@@ -513,16 +513,11 @@ __device__ __forceinline__ bool tpi_polish_thread(const TpiRicParams<S>& P, Bmpc
     // Every forward sweep of the polish both verifies and emits: stage k produces exactly nx + 2 rows of the exact ADMM
     // fixed point v* = z* + y*/rho (x_{k+1}, u_k, delta-u row k) = the nx + 2 gain slots it has just consumed, so v* is
     // staged IN PLACE and leaves through the coalesced transpose of the caller; U goes to I.Us (an output-only array).
-    constexpr int nz1 = S::nx + 2;
     double* udst = I.Us + (size_t)inst * S::NU;
     double u_first = 0.0;
     const int ps = tpi_polish_riccati<S>(P, W, x0, um1, xr, up, dn, max_steps,
         [&](int i, double zi, double mu, double irho) {
-            int slot;
-            if (i < S::NS) slot = (i / S::nx) * nz1 + (i % S::nx);
-            else if (i < S::NS + S::NU) slot = (i - S::NS) * nz1 + S::nx;
-            else { const int rr = i - S::NS - S::NU; slot = rr < S::Np ? rr * nz1 + S::nx + 1 : S::Np * nz1; }
-            W(slot) = zi + mu * irho;
+            W(tpi_vstar_slot<S>(i)) = zi + mu * irho;
         },
         [&](int j, double u) { udst[j] = u; if (j == 0) u_first = u; });
     if (ps > 0) {
@@ -554,16 +549,11 @@ __global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiRi
     const bool ok = (lane < nvalid) && tpi_polish_thread<S, TV>(P, I, inst, W, max_steps, next_list, next_count, u0_out);
     const unsigned okmask = __ballot_sync(0xffffffffu, ok);
     __syncwarp();
-    constexpr int nz1 = S::nx + 2;
     if (list) {
         if (ok) {
             double* dst = I.vw + (size_t)inst * S::mc;
             for (int i = 0; i < S::MT; i++) {
-                int slot;
-                if (i < S::NS) slot = (i / S::nx) * nz1 + (i % S::nx);
-                else if (i < S::NS + S::NU) slot = (i - S::NS) * nz1 + S::nx;
-                else { const int rr = i - S::NS - S::NU; slot = rr < S::Np ? rr * nz1 + S::nx + 1 : S::Np * nz1; }
-                dst[S::nx + i] = W(slot);
+                dst[S::nx + i] = W(tpi_vstar_slot<S>(i));
             }
             for (int q = 0; q < S::nx; q++) dst[q] = I.x0[(size_t)inst * S::nx + q];
         }
@@ -576,11 +566,7 @@ __global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiRi
             double val;
             if (g < S::nx) val = I.x0[(size_t)(idx0 + t) * S::nx + g];
             else {
-                const int i = g - S::nx; int slot;
-                if (i < S::NS) slot = (i / S::nx) * nz1 + (i % S::nx);
-                else if (i < S::NS + S::NU) slot = (i - S::NS) * nz1 + S::nx;
-                else { const int rr = i - S::NS - S::NU; slot = rr < S::Np ? rr * nz1 + S::nx + 1 : S::Np * nz1; }
-                val = smem[slot * TPI_STR + t];
+                val = smem[tpi_vstar_slot<S>(g - S::nx) * TPI_STR + t];
             }
             dst[idx] = val;
         }
@@ -645,31 +631,38 @@ static std::string g_create_err;
         }                                                                                          \
     } while (0)
 
+// the time-varying-reference instantiations exist for Nc == Np only (enqueue_round keeps other shapes off the fast path then)
 template <class S>
 static void launch_tpi_round(bmpc_handle* h, const int32_t* list, int count, int niter, int32_t* next_list, cudaEvent_t mid) {
     const int grid = (count + 31) / 32;
     const TpiAdmmParams<S>& PA = *(const TpiAdmmParams<S>*)h->tpi_admm_params;
     const TpiRicParams<S>& PR = *(const TpiRicParams<S>*)h->tpi_polish_params;
     const int cold = h->cold ? 1 : 0, reset = h->st.round == 0 ? 1 : 0;
-    if (h->xref_mode)   // one (Np+1) x nx reference per instance
-        k_tpi_admm<S, true><<<grid, 32, S::MT * TPI_STR * 8, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts, h->um1_solved);
-    else
-        k_tpi_admm<S, false><<<grid, 32, S::MT * TPI_STR * 8, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts, h->um1_solved);
+    const size_t sa = S::MT * TPI_STR * 8, sp = S::PROWS * TPI_STR * 8;
+    bool tv = false;
+    if constexpr (S::Nc == S::Np) tv = h->xref_mode != 0;       // one (Np+1) x nx reference per instance
+    if constexpr (S::Nc == S::Np) {
+        if (tv) k_tpi_admm<S, true><<<grid, 32, sa, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts, h->um1_solved);
+    }
+    if (!tv) k_tpi_admm<S, false><<<grid, 32, sa, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts, h->um1_solved);
     cudaEventRecord(mid, h->stream);
-    if (h->xref_mode)
-        k_tpi_polish<S, true><<<grid, 32, S::PROWS * TPI_STR * 8, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
-    else
-        k_tpi_polish<S, false><<<grid, 32, S::PROWS * TPI_STR * 8, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
+    if constexpr (S::Nc == S::Np) {
+        if (tv) k_tpi_polish<S, true><<<grid, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
+    }
+    if (!tv) k_tpi_polish<S, false><<<grid, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
     h->stats.launches += 2;
 }
 
 template <class S>
 static void launch_tpi_polish_only(bmpc_handle* h, const int32_t* list, int count, int32_t* next_list) {
     const TpiRicParams<S>& PR = *(const TpiRicParams<S>*)h->tpi_polish_params;
-    if (h->xref_mode)
-        k_tpi_polish<S, true><<<(count + 31) / 32, 32, S::PROWS * TPI_STR * 8, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
-    else
-        k_tpi_polish<S, false><<<(count + 31) / 32, 32, S::PROWS * TPI_STR * 8, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
+    const size_t sp = S::PROWS * TPI_STR * 8;
+    bool tv = false;
+    if constexpr (S::Nc == S::Np) {
+        tv = h->xref_mode != 0;
+        if (tv) k_tpi_polish<S, true><<<(count + 31) / 32, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
+    }
+    if (!tv) k_tpi_polish<S, false><<<(count + 31) / 32, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
     h->stats.launches++;
 }
 
@@ -680,9 +673,11 @@ static void tpi_fill_entry(const double* hs, const BmpcSysOff& o, void* pa, void
 template <class S>
 static int tpi_configure_entry() {
     if (cudaFuncSetAttribute(k_tpi_admm<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::MT * TPI_STR * 8)) != cudaSuccess) return 1;
-    if (cudaFuncSetAttribute(k_tpi_admm<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::MT * TPI_STR * 8)) != cudaSuccess) return 1;
+    if constexpr (S::Nc == S::Np) {
+        if (cudaFuncSetAttribute(k_tpi_admm<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::MT * TPI_STR * 8)) != cudaSuccess) return 1;
+        if (cudaFuncSetAttribute(k_tpi_polish<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::PROWS * TPI_STR * 8)) != cudaSuccess) return 1;
+    }
     if (cudaFuncSetAttribute(k_tpi_polish<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::PROWS * TPI_STR * 8)) != cudaSuccess) return 1;
-    if (cudaFuncSetAttribute(k_tpi_polish<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::PROWS * TPI_STR * 8)) != cudaSuccess) return 1;
     return 0;
 }
 #define BMPC_TPI_SHAPE(NX_, NU_, NP_, NC_)                                                                                   \
@@ -1034,7 +1029,8 @@ static int enqueue_round(bmpc_handle* h) {
     if (st.chunk > h->cfg.max_iter - st.total) st.chunk = h->cfg.max_iter - st.total;
     // fast path (thread-per-instance kernels, throughput-optimised) for the first round; the few stragglers are
     // latency-bound and go to the CTA-per-instance team kernels
-    const bool tpi = st.round == 0 && h->tpi_kind && h->cfg.polish;
+    const bool tpi_ok = h->tpi_kind && (h->xref_mode == 0 || h->d.Nc == h->d.Np);   // time-varying reference on the fast path: Nc == Np
+    const bool tpi = st.round == 0 && tpi_ok && h->cfg.polish;
     if (!tpi) {
         if (st.round == 0) {
             const int B = h->cfg.batch;
@@ -1059,7 +1055,7 @@ static int enqueue_round(bmpc_handle* h) {
         }
         BMPC_CUDA(cudaEventRecord(h->ev[1], h->stream));
         // stragglers of a fast-path shape: the Riccati polish (list mode) has ~3x lower latency than the team Schur polish
-        if (h->cfg.polish && h->tpi_kind && st.total + st.chunk <= 200)
+        if (h->cfg.polish && tpi_ok && st.total + st.chunk <= 200)
             g_tpi_table[h->tpi_kind - 1].launch_polish(h, st.list, st.count, st.nxt);
         else if (h->cfg.polish) launch_polish(h, st.list, st.count, st.nxt, h->counts);
         else { k_check_converged<<<(st.count + 255) / 256, 256, 0, h->stream>>>(h->I, st.list, st.count, h->cfg.eps_abs, h->cfg.eps_rel, st.nxt, h->counts); h->stats.launches++; }
@@ -1119,7 +1115,7 @@ int bmpc_solve(bmpc_handle* h) {
     st.list = nullptr; st.count = B; st.cur = h->listA; st.nxt = h->listB;
     st.total = 0; st.round = 0; st.need_prep = true;
     // first round: 3 iterations on the fast path (measured: as good as 10 for the warm active-set guess), 10 on the team kernels
-    const bool fast = h->tpi_kind != 0;
+    const bool fast = h->tpi_kind != 0 && (h->xref_mode == 0 || h->d.Nc == h->d.Np);
     st.chunk = h->cfg.polish ? (h->cfg.first_iters > 0 ? h->cfg.first_iters : (fast ? 3 : 10)) : 25;
     // a cold start has no active-set guess to refresh: 25 iterations at once on the fast path, so that the first polish
     // usually verifies and the whole batch does not take the straggler route

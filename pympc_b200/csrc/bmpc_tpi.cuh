@@ -160,7 +160,7 @@ BMPC_HD void tpi_admm(const TpiAdmmParams<S>& P, TpiAcc V, TpiAcc G, const doubl
             for (int q = 0; q < nx; q++) gp[a] += P.Gcc[a * nx + q] * x0[q];
             G(a) = gp[a];
         }
-        if (XR::TV) tpi_linear_term_tv<S>(c, xr, [&](int j, double val) { G(j) += val; });
+        if constexpr (XR::TV) tpi_linear_term_tv<S>(c, xr, [&](int j, double val) { G(j) += val; });
     }
     if (cold) {
         // x = 0, v = A x + cc : free response on the state rows, zeros elsewhere
@@ -294,7 +294,7 @@ BMPC_HD void tpi_admm(const TpiAdmmParams<S>& P, TpiAcc V, TpiAcc G, const doubl
 // Working sets of one instance, split by row class so that the horizon loops read / write a whole stage with one
 // shift (profiles/: per-row 64-bit variable shifts were 28 % of the polish instructions):
 //   x : state rows, bit (k*nx + a) <-> row of x_{k+1}[a]   (Np*nx <= 128 bits)
-//   u : input rows, bit j;   d : delta-u rows, bit rr (rr = 0..Np; rr = Np is the reference's spurious last row)
+//   u : input rows, bit j < Nc;   d : delta-u rows, bit rr (rr = 0..Nc; rr = Nc is the reference's spurious last row)
 struct TpiSets {
     unsigned long long xl, xh;
     unsigned u, d;
@@ -317,7 +317,8 @@ BMPC_HD void tpi_xput(TpiSets& s, int pos, int n, unsigned bits) {
 template <class S, class Acc>
 BMPC_HD void tpi_sets_from_v(const TpiCommon<S>& c, const double* um1, Acc V, TpiSets& up, TpiSets& dn) {
     constexpr int nx = S::nx, Np = S::Np, NS = S::NS, NU = S::NU;
-    static_assert(S::nu == 1 && S::Nc == S::Np && S::NS <= 128 && S::Np < 32, "TPI sets: nu == 1, Nc == Np, Np*nx <= 128");
+    static_assert(S::nu == 1 && S::Nc <= S::Np && S::NS <= 128 && S::Np < 32, "TPI sets: nu == 1, Nc <= Np, Np*nx <= 128");
+    constexpr int Nc = S::Nc;
     auto over = [](double v, double hi) { return v > hi + 1e-9 * (1.0 + fabs(hi)); };
     auto under = [](double v, double lo) { return v < lo - 1e-9 * (1.0 + fabs(lo)); };
 #pragma unroll 1
@@ -329,17 +330,19 @@ BMPC_HD void tpi_sets_from_v(const TpiCommon<S>& c, const double* um1, Acc V, Tp
             bu |= (over(v, c.xmax[a]) ? 1u : 0u) << a; bd |= (under(v, c.xmin[a]) ? 1u : 0u) << a;
         }
         tpi_xput(up, k * nx, nx, bu); tpi_xput(dn, k * nx, nx, bd);
+        if (k >= Nc) continue;                              // held stages (Nc < Np) have no input / delta-u rows
         const double vu = V(NS + k);
         up.u |= (over(vu, c.umax[0]) ? 1u : 0u) << k; dn.u |= (under(vu, c.umin[0]) ? 1u : 0u) << k;
         const double vd = V(NS + NU + k), sh = (k == 0) ? um1[0] : 0.0;
         up.d |= (over(vd, c.dmax[0] + sh) ? 1u : 0u) << k; dn.d |= (under(vd, c.dmin[0] + sh) ? 1u : 0u) << k;
     }
-    const double vq = V(NS + NU + Np);
-    up.d |= (over(vq, c.dmax[0]) ? 1u : 0u) << Np; dn.d |= (under(vq, c.dmin[0]) ? 1u : 0u) << Np;
+    const double vq = V(NS + NU + Nc);
+    up.d |= (over(vq, c.dmax[0]) ? 1u : 0u) << Nc; dn.d |= (under(vq, c.dmin[0]) ? 1u : 0u) << Nc;
 }
 
 // ------------------------------------------------------------------------------------------------
-// Riccati polish (nu == 1, Nc == Np): the equality-constrained QP of one active-set step is an LQ problem
+// Riccati polish (nu == 1; Nc < Np: the stages k >= Nc hold the last input, i.e. are pinned to u_k = u_{k-1} without a
+// row or a multiplier): the equality-constrained QP of one active-set step is an LQ problem
 //   min sum_k [ 1/2 x_k' Qt_k x_k - qt_k' x_k ] + sum_j [ 1/2 Qu u_j^2 - Qu uref u_j + 1/2 QDu (u_j - u_{j-1})^2 ]
 //   s.t. x_{k+1} = Ad x_k + Bd u_k,  some inputs pinned (u_j = bound, or u_j = u_{j-1} + delta)
 // where violated soft rows enter through Qt_k = Q_k + eps_feas diag(mask_k), qt_k = Q_k xref + eps_feas mask_k.*bound.
@@ -360,7 +363,8 @@ enum { TPI_FREE = 0, TPI_UPIN = 1, TPI_DPIN = 2, TPI_QPIN = 3 };
 // spurious last row  Dumin <= -u_{N-1} <= Dumax)
 template <class S>
 BMPC_HD int tpi_pin_of(const TpiCommon<S>& c, const TpiSets& up, const TpiSets& dn, int j, double& val) {
-    constexpr int N = S::Np;
+    constexpr int N = S::Nc;                                          // decision inputs; stages j >= Nc hold u_{Nc-1}
+    if (j >= N) { val = 0.0; return TPI_DPIN; }                         // held stage: u_j = u_{j-1}, no row, no multiplier
     if ((up.u >> j) & 1u) { val = c.umax[0]; return TPI_UPIN; }
     if ((dn.u >> j) & 1u) { val = c.umin[0]; return TPI_UPIN; }
     if ((up.d >> j) & 1u) { val = c.dmax[0]; return TPI_DPIN; }
@@ -374,7 +378,7 @@ BMPC_HD int tpi_pin_of(const TpiCommon<S>& c, const TpiSets& up, const TpiSets& 
 
 template <class S, class XR>
 BMPC_HD void tpi_ric_backward(const TpiRicParams<S>& P, TpiAcc W, XR xr, const TpiSets& up, const TpiSets& dn) {
-    static_assert(S::nu == 1 && S::Nc == S::Np, "Riccati polish is specialised to nu == 1, Nc == Np");
+    static_assert(S::nu == 1 && S::Nc <= S::Np, "Riccati polish is specialised to nu == 1");
     constexpr int nx = S::nx, N = S::Np, nz = nx + 1;
     const TpiCommon<S>& c = P.c;
     // cost-to-go of stage k+1:  Pxx (sym, full storage), pxw, pww, px, pw
@@ -490,7 +494,7 @@ BMPC_HD void tpi_ric_backward(const TpiRicParams<S>& P, TpiAcc W, XR xr, const T
 template <class S, int MODE, class FR, class FU>
 BMPC_HD bool tpi_ric_forward(const TpiRicParams<S>& P, TpiAcc W, const double* x0, const double* um1, const TpiSets& up,
                              const TpiSets& dn, TpiSets& nup, TpiSets& ndn, double& mumax, FR out, FU outu) {
-    constexpr int nx = S::nx, N = S::Np, nz = nx + 1, NS = S::NS, NU = S::NU;
+    constexpr int nx = S::nx, N = S::Np, Nc = S::Nc, nz = nx + 1, NS = S::NS, NU = S::NU;
     const TpiCommon<S>& c = P.c;
     constexpr bool EMIT = (MODE >= 1), VERIFY = (MODE != 1);
     const double mutol = 1e-9 * (1.0 + mumax);
@@ -522,16 +526,18 @@ BMPC_HD bool tpi_ric_forward(const TpiRicParams<S>& P, TpiAcc W, const double* x
         else if (type == TPI_UPIN) { u = pin; mu_u = -lin; }
         else if (type == TPI_DPIN) { u = w + pin; mu_d = -lin; }
         else { u = pin; mu_q = lin; }
-        mnew = fmax(mnew, fmax(fabs(mu_u), fmax(fabs(mu_d), fabs(mu_q))));
-        if (EMIT) outu(k, u);
-        unsigned hb = hard_row(NS + k, (up.u >> k) & 1u, (dn.u >> k) & 1u, u, c.umin[0], c.umax[0], mu_u, c.irhou[0]);
-        nup.u |= (hb & 1u) << k; ndn.u |= (hb >> 1) << k;
-        const double sh = (k == 0) ? w : 0.0;               // row 0: value u_0, bounds shifted by u_-1; else u_k - u_{k-1}
-        hb = hard_row(NS + NU + k, (up.d >> k) & 1u, (dn.d >> k) & 1u, (k == 0) ? u : u - w, c.dmin[0] + sh, c.dmax[0] + sh, mu_d, c.irhod[0]);
-        nup.d |= (hb & 1u) << k; ndn.d |= (hb >> 1) << k;
-        if (k == N - 1) {
-            hb = hard_row(NS + NU + N, (up.d >> N) & 1u, (dn.d >> N) & 1u, -u, c.dmin[0], c.dmax[0], mu_q, c.irhod[0]);
-            nup.d |= (hb & 1u) << N; ndn.d |= (hb >> 1) << N;
+        if (k < Nc) {                                        // held stages (k >= Nc) own no input / delta-u rows
+            mnew = fmax(mnew, fmax(fabs(mu_u), fmax(fabs(mu_d), fabs(mu_q))));
+            if (EMIT) outu(k, u);
+            unsigned hb = hard_row(NS + k, (up.u >> k) & 1u, (dn.u >> k) & 1u, u, c.umin[0], c.umax[0], mu_u, c.irhou[0]);
+            nup.u |= (hb & 1u) << k; ndn.u |= (hb >> 1) << k;
+            const double sh = (k == 0) ? w : 0.0;           // row 0: value u_0, bounds shifted by u_-1; else u_k - u_{k-1}
+            hb = hard_row(NS + NU + k, (up.d >> k) & 1u, (dn.d >> k) & 1u, (k == 0) ? u : u - w, c.dmin[0] + sh, c.dmax[0] + sh, mu_d, c.irhod[0]);
+            nup.d |= (hb & 1u) << k; ndn.d |= (hb >> 1) << k;
+            if (k == Nc - 1) {
+                hb = hard_row(NS + NU + Nc, (up.d >> Nc) & 1u, (dn.d >> Nc) & 1u, -u, c.dmin[0], c.dmax[0], mu_q, c.irhod[0]);
+                nup.d |= (hb & 1u) << Nc; ndn.d |= (hb >> 1) << Nc;
+            }
         }
         double xn[nx];
 #pragma unroll
@@ -564,6 +570,18 @@ BMPC_HD bool tpi_ric_forward(const TpiRicParams<S>& P, TpiAcc W, const double* x
     }
     mumax = mnew;
     return ok;
+}
+
+// Where the forward sweep stages row i of the exact ADMM fixed point v* inside the (already consumed) gain slots of the
+// column: stage k owns slots [k*(nx+2), (k+1)*(nx+2)) = its nx state rows, its input row, its delta-u row; the reference's
+// spurious last delta-u row goes to the spare slot behind the last stage.
+template <class S>
+BMPC_HD int tpi_vstar_slot(int i) {
+    constexpr int nz1 = S::nx + 2;
+    if (i < S::NS) return (i / S::nx) * nz1 + (i % S::nx);
+    if (i < S::NS + S::NU) return (i - S::NS) * nz1 + S::nx;
+    const int rr = i - S::NS - S::NU;
+    return rr < S::Nc ? rr * nz1 + S::nx + 1 : S::Np * nz1;
 }
 
 // returns steps used (>0) when KKT-verified, 0 otherwise.  Every forward sweep verifies AND emits through out / outu (row

@@ -181,3 +181,23 @@ def test_tpi_fast_path_time_varying_reference(name):
         assert np.max(np.abs(U - ref)) < 1e-7, (t, ps)
         um1 = U[:1].copy(); x = cfg["Ad"] @ x + cfg["Bd"] @ um1
     assert fast >= 4                                            # the fast path itself verified most steps
+
+
+def test_tpi_fast_path_control_horizon_shorter_than_prediction():
+    """Nc < Np on the fast path (mpc.py:513-517,540-543): the input is held after Nc moves.  ADMM sweeps collect the held
+    stages into the last input; the Riccati polish treats stages k >= Nc as pinned to u_k = u_{k-1} without a row.
+    Closed loop vs the exact solver on the oracle-assembled QP."""
+    from oracle.kkt import solve_exact
+    cfg = dict(pendulum(), Nc=10)
+    E = EmuSystem(cfg); rng = np.random.default_rng(2)
+    x = np.array([0.1, 0.2, 0.2, -0.1]); um1 = np.zeros(1); fast = 0
+    for t in range(12):
+        U, ps = E.tpi_step(x, um1, cfg["xref"], first_iters=10)
+        assert ps != -100, "shape not compiled in the host emulation"
+        fast += ps > 0
+        if ps <= 0:
+            U, st, *_ = E.solve(x, um1, cfg["xref"]); assert st == 1
+        Q = QPData(**dict(cfg, x0=x, uminus1=um1)); z, y, r = solve_exact(Q.P, Q.q, Q.A, Q.l, Q.u)
+        assert np.max(np.abs(U - z[Q.NX:Q.NX + Q.NU])) < 1e-7, (t, ps)
+        um1 = U[:1].copy(); x = cfg["Ad"] @ x + cfg["Bd"] @ um1 + 0.01 * rng.standard_normal(4)
+    assert fast >= 9
