@@ -41,7 +41,7 @@ def add_shape(nx, nu, Np, Nc=None):
 
 if __name__ == "__main__":
     import sys
-    if len(sys.argv) == 3 and sys.argv[1] == "--add-shape":
+    if len(sys.argv) == 3 and sys.argv[1] == "--add-shape":          # nx,nu,Np[,Nc]
         print(add_shape(*[int(v) for v in sys.argv[2].split(",")]))
     else:
         print(build(force=True, verbose=True))
