@@ -631,7 +631,6 @@ static std::string g_create_err;
         }                                                                                          \
     } while (0)
 
-// the time-varying-reference instantiations exist for Nc == Np only (enqueue_round keeps other shapes off the fast path then)
 template <class S>
 static void launch_tpi_round(bmpc_handle* h, const int32_t* list, int count, int niter, int32_t* next_list, cudaEvent_t mid) {
     const int grid = (count + 31) / 32;
@@ -639,17 +638,15 @@ static void launch_tpi_round(bmpc_handle* h, const int32_t* list, int count, int
     const TpiRicParams<S>& PR = *(const TpiRicParams<S>*)h->tpi_polish_params;
     const int cold = h->cold ? 1 : 0, reset = h->st.round == 0 ? 1 : 0;
     const size_t sa = S::MT * TPI_STR * 8, sp = S::PROWS * TPI_STR * 8;
-    bool tv = false;
-    if constexpr (S::Nc == S::Np) tv = h->xref_mode != 0;       // one (Np+1) x nx reference per instance
-    if constexpr (S::Nc == S::Np) {
-        if (tv) k_tpi_admm<S, true><<<grid, 32, sa, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts, h->um1_solved);
-    }
-    if (!tv) k_tpi_admm<S, false><<<grid, 32, sa, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts, h->um1_solved);
+    if (h->xref_mode)   // one (Np+1) x nx reference per instance
+        k_tpi_admm<S, true><<<grid, 32, sa, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts, h->um1_solved);
+    else
+        k_tpi_admm<S, false><<<grid, 32, sa, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts, h->um1_solved);
     cudaEventRecord(mid, h->stream);
-    if constexpr (S::Nc == S::Np) {
-        if (tv) k_tpi_polish<S, true><<<grid, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
-    }
-    if (!tv) k_tpi_polish<S, false><<<grid, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
+    if (h->xref_mode)
+        k_tpi_polish<S, true><<<grid, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
+    else
+        k_tpi_polish<S, false><<<grid, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
     h->stats.launches += 2;
 }
 
@@ -657,12 +654,10 @@ template <class S>
 static void launch_tpi_polish_only(bmpc_handle* h, const int32_t* list, int count, int32_t* next_list) {
     const TpiRicParams<S>& PR = *(const TpiRicParams<S>*)h->tpi_polish_params;
     const size_t sp = S::PROWS * TPI_STR * 8;
-    bool tv = false;
-    if constexpr (S::Nc == S::Np) {
-        tv = h->xref_mode != 0;
-        if (tv) k_tpi_polish<S, true><<<(count + 31) / 32, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
-    }
-    if (!tv) k_tpi_polish<S, false><<<(count + 31) / 32, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
+    if (h->xref_mode)
+        k_tpi_polish<S, true><<<(count + 31) / 32, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
+    else
+        k_tpi_polish<S, false><<<(count + 31) / 32, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
     h->stats.launches++;
 }
 
@@ -673,10 +668,8 @@ static void tpi_fill_entry(const double* hs, const BmpcSysOff& o, void* pa, void
 template <class S>
 static int tpi_configure_entry() {
     if (cudaFuncSetAttribute(k_tpi_admm<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::MT * TPI_STR * 8)) != cudaSuccess) return 1;
-    if constexpr (S::Nc == S::Np) {
-        if (cudaFuncSetAttribute(k_tpi_admm<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::MT * TPI_STR * 8)) != cudaSuccess) return 1;
-        if (cudaFuncSetAttribute(k_tpi_polish<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::PROWS * TPI_STR * 8)) != cudaSuccess) return 1;
-    }
+    if (cudaFuncSetAttribute(k_tpi_admm<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::MT * TPI_STR * 8)) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(k_tpi_polish<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::PROWS * TPI_STR * 8)) != cudaSuccess) return 1;
     if (cudaFuncSetAttribute(k_tpi_polish<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::PROWS * TPI_STR * 8)) != cudaSuccess) return 1;
     return 0;
 }
@@ -1029,7 +1022,7 @@ static int enqueue_round(bmpc_handle* h) {
     if (st.chunk > h->cfg.max_iter - st.total) st.chunk = h->cfg.max_iter - st.total;
     // fast path (thread-per-instance kernels, throughput-optimised) for the first round; the few stragglers are
     // latency-bound and go to the CTA-per-instance team kernels
-    const bool tpi_ok = h->tpi_kind && (h->xref_mode == 0 || h->d.Nc == h->d.Np);   // time-varying reference on the fast path: Nc == Np
+    const bool tpi_ok = h->tpi_kind != 0;
     const bool tpi = st.round == 0 && tpi_ok && h->cfg.polish;
     if (!tpi) {
         if (st.round == 0) {
@@ -1115,7 +1108,7 @@ int bmpc_solve(bmpc_handle* h) {
     st.list = nullptr; st.count = B; st.cur = h->listA; st.nxt = h->listB;
     st.total = 0; st.round = 0; st.need_prep = true;
     // first round: 3 iterations on the fast path (measured: as good as 10 for the warm active-set guess), 10 on the team kernels
-    const bool fast = h->tpi_kind != 0 && (h->xref_mode == 0 || h->d.Nc == h->d.Np);
+    const bool fast = h->tpi_kind != 0;
     st.chunk = h->cfg.polish ? (h->cfg.first_iters > 0 ? h->cfg.first_iters : (fast ? 3 : 10)) : 25;
     // a cold start has no active-set guess to refresh: 25 iterations at once on the fast path, so that the first polish
     // usually verifies and the whole batch does not take the straggler route

@@ -111,10 +111,9 @@ BMPC_HD void tpi_linear_term(const TpiCommon<S>& c, const double* x0, const doub
 }
 
 // time-varying reference: the part -Bcal' P_X xref of g, by the adjoint recursion  lam_k = -Q_k xref_k + Ad' lam_{k+1},
-// g_{k-1} += Bd' lam_k;  add(j, value) accumulates into wherever the caller keeps g (dynamic index: not a register array)
+// g_{min(k-1, Nc-1)} += Bd' lam_k;  add(j, value) accumulates into wherever the caller keeps g (dynamic index: not a register array)
 template <class S, class XR, class ADD>
 BMPC_HD void tpi_linear_term_tv(const TpiCommon<S>& c, XR xr, ADD add) {
-    static_assert(S::Nc == S::Np, "fast path: Nc == Np");
     constexpr int nx = S::nx, nu = S::nu;
     double lam[nx];
 #pragma unroll
@@ -136,7 +135,7 @@ BMPC_HD void tpi_linear_term_tv(const TpiCommon<S>& c, XR xr, ADD add) {
             double acc = 0.0;
 #pragma unroll
             for (int q = 0; q < nx; q++) acc += c.Bd[q * nu + b] * lam[q];
-            add((k - 1) * nu + b, acc);
+            add(((k - 1 < S::Nc - 1) ? (k - 1) : (S::Nc - 1)) * nu + b, acc);       // stages beyond Nc feed the held last input
         }
     }
 }

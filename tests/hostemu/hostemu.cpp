@@ -115,7 +115,8 @@ extern "C" int emu_tpi_step(int nx, int nu, int Np, int Nc, const double* sys, c
         return xref_mode ? emu_tpi_run<TpiShape<4, 1, 20, 20>, true>(EMU_TPI_ARGS) : emu_tpi_run<TpiShape<4, 1, 20, 20>, false>(EMU_TPI_ARGS);
     if (nx == 2 && nu == 1 && Np == 20 && Nc == 20)
         return xref_mode ? emu_tpi_run<TpiShape<2, 1, 20, 20>, true>(EMU_TPI_ARGS) : emu_tpi_run<TpiShape<2, 1, 20, 20>, false>(EMU_TPI_ARGS);
-    if (nx == 4 && nu == 1 && Np == 20 && Nc == 10 && !xref_mode) return emu_tpi_run<TpiShape<4, 1, 20, 10>, false>(EMU_TPI_ARGS);   // held input
+    if (nx == 4 && nu == 1 && Np == 20 && Nc == 10)                                                                 // held input
+        return xref_mode ? emu_tpi_run<TpiShape<4, 1, 20, 10>, true>(EMU_TPI_ARGS) : emu_tpi_run<TpiShape<4, 1, 20, 10>, false>(EMU_TPI_ARGS);
 #undef EMU_TPI_ARGS
     return -100;
 }

@@ -201,3 +201,23 @@ def test_tpi_fast_path_control_horizon_shorter_than_prediction():
         assert np.max(np.abs(U - z[Q.NX:Q.NX + Q.NU])) < 1e-7, (t, ps)
         um1 = U[:1].copy(); x = cfg["Ad"] @ x + cfg["Bd"] @ um1 + 0.01 * rng.standard_normal(4)
     assert fast >= 9
+
+
+def test_tpi_fast_path_time_varying_reference_with_held_input():
+    """Both f2 features at once on the fast path: (Np+1, nx) reference and Nc < Np (the adjoint recursion feeds the stages
+    beyond Nc into the held last input)."""
+    from oracle.kkt import solve_exact
+    cfg = dict(pendulum(), Nc=10); Np = 20
+    E = EmuSystem(cfg); x = np.array([0.1, 0.2, 0.2, -0.1]); um1 = np.zeros(1); fast = 0
+    for t in range(6):
+        Xtv = np.tile(np.asarray(cfg["xref"], float), (Np + 1, 1)) * np.linspace(0.4, 1.0, Np + 1)[:, None]
+        Xtv[:, 0] += 0.05 * np.sin(0.3 * (np.arange(Np + 1) + t))
+        U, ps = E.tpi_step(x, um1, Xtv, first_iters=10)
+        assert ps != -100
+        fast += ps > 0
+        if ps <= 0:
+            U, st, *_ = E.solve(x, um1, Xtv); assert st == 1
+        Q = QPData(**dict(cfg, x0=x, uminus1=um1, xref=Xtv)); z, y, r = solve_exact(Q.P, Q.q, Q.A, Q.l, Q.u)
+        assert np.max(np.abs(U - z[Q.NX:Q.NX + Q.NU])) < 1e-7, (t, ps)
+        um1 = U[:1].copy(); x = cfg["Ad"] @ x + cfg["Bd"] @ um1
+    assert fast >= 4
