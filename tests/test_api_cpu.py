@@ -81,3 +81,16 @@ def test_defaults_like_reference(bmpc_lib):
     assert (K.raise_error, K.JX_ON, K.JU_ON, K.JDU_ON, K.SOFT_ON, K.COMPUTE_J_CNST) == (False, True, True, True, True, False)
     Kb = MPCController(cfg["Ad"], cfg["Bd"], batch=5, x0=np.zeros((5, 4)), xref=np.ones((5, 4)))
     assert Kb.x0.shape == (5, 4) and Kb._xref_device_layout(Kb.xref)[1] == 1
+
+
+def test_fast_path_shape_table_is_well_formed():
+    """csrc/tpi_shapes.inc: every compiled fast-path shape obeys the limits the kernels static_assert (nu == 1, Nc <= Np,
+    Np*nx <= 128 bits of working set, Np < 32) and the shipped shapes of DESIGN.md are there."""
+    import os, re
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pympc_b200", "csrc", "tpi_shapes.inc")
+    shapes = [tuple(int(v) for v in m.groups()) for m in re.finditer(r"^BMPC_TPI_SHAPE\((\d+),\s*(\d+),\s*(\d+),\s*(\d+)\)", open(path).read(), re.M)]
+    assert len(shapes) == len(set(shapes)) >= 4
+    for nx, nu, Np, Nc in shapes:
+        assert nu == 1 and 1 <= Nc <= Np < 32 and Np * nx <= 128, (nx, nu, Np, Nc)
+    for s in ((4, 1, 20, 20), (2, 1, 20, 20), (4, 1, 10, 10), (4, 1, 20, 10)):
+        assert s in shapes
