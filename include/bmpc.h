@@ -46,7 +46,7 @@ typedef struct {
     int32_t device;             /* CUDA ordinal */
     int32_t soft_on;            /* SOFT_ON flag (mpc.py:237); 0 = hard state bounds */
     int32_t max_iter;           /* ADMM iteration cap per solve (OSQP default 4000) */
-    int32_t first_iters;        /* ADMM iterations before the first polish attempt (0 = auto: 3 on the fast path, 10 on the team kernels; later rounds reach 25, 50, 100, ... cumulative) */
+    int32_t first_iters;        /* ADMM iterations before the first polish attempt (0 = auto: none on a warm fast-path solve — the polish starts from the previous solution's working sets —, 25 on a cold one, 10 on the team kernels; later rounds reach 25, 50, 100, ... cumulative) */
     int32_t pdas_steps;         /* active-set refinements per polish attempt */
     int32_t rmax;               /* working-set capacity of the polish (0 = auto) */
     int32_t polish;             /* 1 = ADMM + polish (exact), 0 = pure ADMM to eps (OSQP-like) */

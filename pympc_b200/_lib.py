@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbmpc.so")
+# BMPC_LIB: load another build of the same library (kernel-variant sweeps of tools/gpu_sweep.py); default = the in-tree build
+LIB_PATH = os.environ.get("BMPC_LIB") or os.path.join(_HERE, "libbmpc.so")
 _lib = None
 
 P = ctypes.c_void_p

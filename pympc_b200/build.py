@@ -5,8 +5,10 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "bmpc.cu")
 SHAPES = os.path.join(_HERE, "csrc", "tpi_shapes.inc")
-DEPS = [SRC, os.path.join(_HERE, "csrc", "bmpc_core.cuh"), os.path.join(_HERE, "csrc", "bmpc_tpi.cuh"), SHAPES,
-        os.path.join(_HERE, "..", "include", "bmpc.h")]
+import glob
+# every header / table the translation unit includes: an edit to any of them makes the library stale
+DEPS = sorted(set([SRC, SHAPES, os.path.join(_HERE, "..", "include", "bmpc.h")] + glob.glob(os.path.join(_HERE, "csrc", "*.cuh")) +
+                  glob.glob(os.path.join(_HERE, "csrc", "*.inc"))))
 LIB = os.path.join(_HERE, "libbmpc.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -536,11 +536,17 @@ __device__ __forceinline__ bool tpi_polish_thread(const TpiRicParams<S>& P, Bmpc
 
 template <class S, bool TV>
 __global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiRicParams<S> P, BmpcInst I, const int32_t* __restrict__ list, int B, int max_steps,
-                                                   int32_t* next_list, int32_t* next_count, double* u0_out) {
+                                                   int32_t* next_list, int32_t* next_count, double* u0_out, int reset, double* um1_solved) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x, idx0 = blockIdx.x * 32;
     const int nvalid = (B - idx0) < 32 ? (B - idx0) : 32;
     const int inst = list ? (lane < nvalid ? list[idx0 + lane] : 0) : idx0 + lane;
+    if (reset && lane < nvalid) {
+        // polish-only first round (warm start, no ADMM launch before this one): the per-solve bookkeeping rides here
+        I.status[inst] = BMPC_UNSOLVED; I.iters[inst] = 0; I.psteps[inst] = 0; I.lvl[inst] = BMPC_LEV0;
+#pragma unroll
+        for (int q = 0; q < S::nu; q++) um1_solved[(size_t)inst * S::nu + q] = I.um1[(size_t)inst * S::nu + q];
+    }
     TpiAcc W{smem + lane, TPI_STR};
     if (list) {
         if (lane < nvalid) { const double* src = I.vw + (size_t)inst * S::mc + S::nx; for (int i = 0; i < S::MT; i++) W(i) = src[i]; }
@@ -638,16 +644,22 @@ static void launch_tpi_round(bmpc_handle* h, const int32_t* list, int count, int
     const TpiRicParams<S>& PR = *(const TpiRicParams<S>*)h->tpi_polish_params;
     const int cold = h->cold ? 1 : 0, reset = h->st.round == 0 ? 1 : 0;
     const size_t sa = S::MT * TPI_STR * 8, sp = S::PROWS * TPI_STR * 8;
-    if (h->xref_mode)   // one (Np+1) x nx reference per instance
-        k_tpi_admm<S, true><<<grid, 32, sa, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts, h->um1_solved);
-    else
-        k_tpi_admm<S, false><<<grid, 32, sa, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts, h->um1_solved);
+    // niter == 0: warm start straight from the previous solution's working sets (measured: in warm closed loops a few ADMM
+    // iterations do not improve the first active-set guess) -> the ADMM launch is skipped altogether
+    if (niter > 0) {
+        if (h->xref_mode)   // one (Np+1) x nx reference per instance
+            k_tpi_admm<S, true><<<grid, 32, sa, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts, h->um1_solved);
+        else
+            k_tpi_admm<S, false><<<grid, 32, sa, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts, h->um1_solved);
+        h->stats.launches++;
+    } else if (reset) cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 4, h->stream);
     cudaEventRecord(mid, h->stream);
+    const int preset = (niter > 0) ? 0 : reset;
     if (h->xref_mode)
-        k_tpi_polish<S, true><<<grid, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
+        k_tpi_polish<S, true><<<grid, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0, preset, h->um1_solved);
     else
-        k_tpi_polish<S, false><<<grid, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
-    h->stats.launches += 2;
+        k_tpi_polish<S, false><<<grid, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0, preset, h->um1_solved);
+    h->stats.launches++;
 }
 
 template <class S>
@@ -655,9 +667,9 @@ static void launch_tpi_polish_only(bmpc_handle* h, const int32_t* list, int coun
     const TpiRicParams<S>& PR = *(const TpiRicParams<S>*)h->tpi_polish_params;
     const size_t sp = S::PROWS * TPI_STR * 8;
     if (h->xref_mode)
-        k_tpi_polish<S, true><<<(count + 31) / 32, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
+        k_tpi_polish<S, true><<<(count + 31) / 32, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0, 0, h->um1_solved);
     else
-        k_tpi_polish<S, false><<<(count + 31) / 32, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0);
+        k_tpi_polish<S, false><<<(count + 31) / 32, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0, 0, h->um1_solved);
     h->stats.launches++;
 }
 
@@ -1107,9 +1119,10 @@ int bmpc_solve(bmpc_handle* h) {
     auto& st = h->st;
     st.list = nullptr; st.count = B; st.cur = h->listA; st.nxt = h->listB;
     st.total = 0; st.round = 0; st.need_prep = true;
-    // first round: 3 iterations on the fast path (measured: as good as 10 for the warm active-set guess), 10 on the team kernels
+    // first round: NO ADMM iterations on a warm fast-path solve (the previous solution's working sets are the best first guess
+    // the active-set polish can get: measured 0 vs 1..10 iterations), 10 on the team kernels; first_iters > 0 overrides
     const bool fast = h->tpi_kind != 0;
-    st.chunk = h->cfg.polish ? (h->cfg.first_iters > 0 ? h->cfg.first_iters : (fast ? 3 : 10)) : 25;
+    st.chunk = h->cfg.polish ? (h->cfg.first_iters > 0 ? h->cfg.first_iters : (fast ? 0 : 10)) : 25;
     // a cold start has no active-set guess to refresh: 25 iterations at once on the fast path, so that the first polish
     // usually verifies and the whole batch does not take the straggler route
     if (h->cfg.polish && h->cfg.first_iters <= 0 && fast && h->cold) st.chunk = 25;
