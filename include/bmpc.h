@@ -54,6 +54,7 @@ typedef struct {
     int32_t warps_per_block;    /* 0 = auto (warp team only) */
     int32_t fast_path;          /* 1 = use the thread-per-instance kernels when the shape has one (default), 0 = team kernels only */
     int32_t n_sys;              /* 1 = every instance shares (Ad,Bd,weights,bounds); batch = one system per instance */
+    int32_t shift_warm;         /* 1 (default) = a warm fast-path solve starts from the previous working sets shifted by one stage (receding horizon: update() is one sample later); 0 = unshifted */
     double eps_feas;            /* slack weight (mpc.py:226) */
     double rho;                 /* <= 0: automatic sqrt(trace H / trace A'A) */
     double sigma, alpha;        /* OSQP defaults 1e-6, 1.6 */

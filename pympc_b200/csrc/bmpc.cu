@@ -418,13 +418,13 @@ __global__ void k_sequences(BmpcDims d, BmpcSysOff o, const double* __restrict__
 constexpr int TPI_STR = 33;   // padded lane stride of the shared-memory columns
 
 template <class S>
-__device__ __forceinline__ void tpi_load_v(const BmpcInst& I, int inst0, int nvalid, double* smem, int row_off) {
+__device__ __forceinline__ void tpi_load_v(const BmpcInst& I, int inst0, int nvalid, double* smem, int row_off, int nrows = S::MT) {
     // coalesced global read -> transposed shared write, issued as asynchronous 8-byte copies (LDGSTS) so that the 125
     // copies of a lane are all in flight at once instead of one load->store round trip per element
     const double* src = I.vw + (size_t)inst0 * S::mc;
     for (int idx = threadIdx.x; idx < nvalid * S::mc; idx += 32) {
         int t = idx / S::mc, i = idx - t * S::mc;
-        if (i >= S::nx) {
+        if (i >= S::nx && i - S::nx < nrows) {
             const unsigned dst = (unsigned)__cvta_generic_to_shared(smem + (row_off + i - S::nx) * TPI_STR + t);
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + idx) : "memory");
         }
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmm
 #pragma unroll
             for (int q = 0; q < S::nu; q++) um1_solved[(size_t)inst * S::nu + q] = um1[q];
         }
-        if (blockIdx.x == 0 && lane == 0) { counts[0] = 0; counts[1] = 0; counts[2] = 0; counts[3] = 0; }
+        if (blockIdx.x == 0 && lane < 8) counts[lane] = 0;
     }
     // g' (read once per iteration) lives in the instance's global scratch row I.g, not in shared memory: the column is
     // MT rows instead of MT + NU, which lets one more warp reside per SM (measured: ADMM kernel 12 % faster)
@@ -495,87 +495,197 @@ __global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmm
     }
 }
 
-// one instance of the TPI polish (the column W holds v on entry); returns true when KKT-verified, in which case
-// v* is staged in the column (slots, see below) and U / u0 / status are written
+// ------------------------------------------------------------------------------------------------
+// K5 + K6 of the fast path: persistent, work-stealing Riccati polish (bmpc_tpi.cuh, second generation).
+// One CTA per SM, TPI_POL_WARPS warps per CTA (as many as the gain workspace lets reside), every warp on its own: it
+//   phase A  steals chunks of 32 instances off a cursor and runs capA active-set refinements on them (a warm solve: ONE, from
+//            the stored working sets shifted by one stage); lanes that verified publish u*, U, status, v*; the others store
+//            their updated working sets and enter a device-side queue;
+//   phase B  when the cursor is exhausted the warp serves the queue: whatever instances are waiting (1..32) get up to capB more
+//            refinements in-warp.  Stragglers therefore never make 31 verified lanes wait (the first-generation kernel lost
+//            2/3 of its time to that on transient steps) and a warm solve is ONE launch whatever the refinement counts are.
+// Instances still unverified after that go to next_list for the ADMM rounds of the host loop.
+struct TpiPolArgs {
+    const int32_t* list; int count;      // instances of phase A: list[0..count) or, list == nullptr, 0..count-1
+    int mode;                            // 0 stored working sets, 1 stored and shifted one stage (receding horizon), 2 from the iterate v
+    int capA, capB;                      // refinements per instance in phase A / in phase B (0: no phase B, failures go to next_list)
+    int reset;                           // first round of a solve: per-solve bookkeeping rides here
+    int32_t* next_list; int32_t* counts; // counts[0] unfinished (-> next_list), [1] refinements; counts[4..7] queue control, see below
+    int32_t* queue;                      // phase-B queue, all -1 between launches (consumers clear what they take)
+    double* u0_out; double* um1_solved;
+    unsigned char* codes; int code_stride;   // per instance: Np working-set codes + the multiplier scale (double) of the last refinement
+};
+enum { TPI_Q_CURSOR = 4, TPI_Q_TAIL = 5, TPI_Q_HEAD = 6, TPI_Q_DONE = 7 };
+constexpr int TPI_POL_WARPS = 7;
+
+template <class S>
+struct TpiPolLayout {
+    using CT = typename TpiCode<S>::type;
+    static constexpr int GROWS = S::Np * (S::nx + 2);                      // gain rows = TPI rows of v minus the spurious last one
+    static constexpr size_t gain_bytes = (size_t)GROWS * TPI_STR * 8;
+    static constexpr size_t code_bytes = (((size_t)S::Np * 32 * sizeof(CT)) + 15) & ~(size_t)15;
+    static constexpr size_t per_warp = gain_bytes + code_bytes;
+    static constexpr int code_stride = (int)(((S::Np * sizeof(CT) + 7) & ~(size_t)7) + 8);   // bytes per instance in global memory
+    static constexpr int VROWS = S::MT - 1;                                 // TPI rows of v without the spurious last row
+    static_assert(VROWS <= GROWS, "slot layout");
+};
+
+// one batch of up to 32 instances (one per lane) through up to cap refinements; returns the mask of verified lanes
 template <class S, bool TV>
-__device__ __forceinline__ bool tpi_polish_thread(const TpiRicParams<S>& P, BmpcInst& I, int inst, TpiAcc W, int max_steps,
-                                                  int32_t* next_list, int32_t* next_count, double* u0_out) {
-    double x0[S::nx], um1[S::nu], xref[S::nx];
+__device__ __forceinline__ void tpi_pol_batch(const TpiPolParams<S>& P, const BmpcInst& I, const TpiPolArgs& A, double* wsm, typename TpiCode<S>::type* csm,
+                                              int inst, bool valid, int inst0_contig, int nvalid, int mode, int cap, bool to_queue, int reset) {
+    using L = TpiPolLayout<S>; using CT = typename TpiCode<S>::type;
+    constexpr int nx = S::nx;
+    const int lane = threadIdx.x & 31;
+    TpiAcc W{wsm + lane, TPI_STR};
+    auto C = [&](int k) -> CT& { return csm[k * 32 + lane]; };
+    double x0[nx], xref[nx], um1 = 0.0, mumax = 0.0, vq = 0.0;
 #pragma unroll
-    for (int q = 0; q < S::nx; q++) { x0[q] = I.x0[(size_t)inst * S::nx + q]; xref[q] = TV ? 0.0 : I.xref[(size_t)inst * S::nx + q]; }
+    for (int q = 0; q < nx; q++) { x0[q] = valid ? I.x0[(size_t)inst * nx + q] : 0.0; xref[q] = (valid && !TV) ? I.xref[(size_t)inst * nx + q] : 0.0; }
+    if (valid) um1 = I.um1[(size_t)inst];
     const TpiXref<S, TV> xr{TV ? I.xref + (size_t)inst * S::NX : xref};
+    unsigned char* rec = A.codes + (size_t)inst * A.code_stride;
+    if (mode == 2) {
+        // working sets from the ADMM iterate: TPI rows of v into the (still unused) gain rows
+        if (inst0_contig >= 0) tpi_load_v<S>(I, inst0_contig, nvalid, wsm, 0, L::VROWS);
+        else if (valid) { const double* src = I.vw + (size_t)inst * S::mc + nx; for (int i = 0; i < L::VROWS; i++) W(i) = src[i]; }
+        __syncwarp();
+        if (valid) tpi2_codes_from_v<S>(P, um1, W, I.vw[(size_t)inst * S::mc + nx + S::MT - 1], C);
+    } else if (valid) {
+        // stored working sets (written by another SM when this batch comes from the queue: bypass L1)
+        CT st[S::Np];
+        const unsigned long long* src = (const unsigned long long*)rec;
+        constexpr int NW = (int)((S::Np * sizeof(CT) + 7) / 8);
+        unsigned long long wbuf[NW];
 #pragma unroll
-    for (int q = 0; q < S::nu; q++) um1[q] = I.um1[(size_t)inst * S::nu + q];
-    const TpiCommon<S>& c = P.c;
-    TpiSets up, dn;
-    tpi_sets_from_v<S>(c, um1, W, up, dn);
-    // from here on the column is this thread's private workspace (Riccati gains): no cross-lane traffic.
-    // Every forward sweep of the polish both verifies and emits: stage k produces exactly nx + 2 rows of the exact ADMM
-    // fixed point v* = z* + y*/rho (x_{k+1}, u_k, delta-u row k) = the nx + 2 gain slots it has just consumed, so v* is
-    // staged IN PLACE and leaves through the coalesced transpose of the caller; U goes to I.Us (an output-only array).
+        for (int i = 0; i < NW; i++) wbuf[i] = __ldcg(src + i);
+#pragma unroll
+        for (int k = 0; k < S::Np; k++) st[k] = (CT)(wbuf[(k * sizeof(CT)) / 8] >> (8 * ((k * sizeof(CT)) % 8)));
+#pragma unroll
+        for (int k = 0; k < S::Np; k++) C(k) = (CT)tpi2_shifted_code<S>(st, k, mode == 1);
+        if (!reset) mumax = __ldcg((const double*)(rec + A.code_stride - 8));
+    }
     double* udst = I.Us + (size_t)inst * S::NU;
     double u_first = 0.0;
-    const int ps = tpi_polish_riccati<S>(P, W, x0, um1, xr, up, dn, max_steps,
-        [&](int i, double zi, double mu, double irho) {
-            W(tpi_vstar_slot<S>(i)) = zi + mu * irho;
-        },
-        [&](int j, double u) { udst[j] = u; if (j == 0) u_first = u; });
-    if (ps > 0) {
-        double* xdst = I.xw + (size_t)inst * S::NU;
-#pragma unroll 4
-        for (int j = 0; j < S::NU; j++) xdst[j] = udst[j];      // warm start x = U* (xw must stay the ADMM x on failure)
-        bmpc_publish_u0(I, u0_out, (size_t)inst, u_first);
-        I.status[inst] = BMPC_SOLVED; I.psteps[inst] += ps;
-        atomicAdd(next_count + 1, ps);
-    } else {
-        I.psteps[inst] += max_steps; atomicAdd(next_count + 1, max_steps);
-        if (I.status[inst] != BMPC_PRIMAL_INFEASIBLE) next_list[atomicAdd(next_count, 1)] = inst;
+    bool done = !valid, ok = false;
+    int used = 0;
+    for (int r = 0; r < cap; r++) {
+        if (!done) {
+            tpi2_backward<S>(P, W, C, xr);
+            ok = tpi2_forward<S>(P, W, C, x0, um1, mumax, vq, [&](int j, double u) { udst[j] = u; if (j == 0) u_first = u; });
+            used++;
+            done = ok;
+        }
+        if (__all_sync(0xffffffffu, done)) break;
     }
-    return ps > 0;
-}
-
-template <class S, bool TV>
-__global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiRicParams<S> P, BmpcInst I, const int32_t* __restrict__ list, int B, int max_steps,
-                                                   int32_t* next_list, int32_t* next_count, double* u0_out, int reset, double* um1_solved) {
-    extern __shared__ double smem[];
-    const int lane = threadIdx.x, idx0 = blockIdx.x * 32;
-    const int nvalid = (B - idx0) < 32 ? (B - idx0) : 32;
-    const int inst = list ? (lane < nvalid ? list[idx0 + lane] : 0) : idx0 + lane;
-    if (reset && lane < nvalid) {
-        // polish-only first round (warm start, no ADMM launch before this one): the per-solve bookkeeping rides here
-        I.status[inst] = BMPC_UNSOLVED; I.iters[inst] = 0; I.psteps[inst] = 0; I.lvl[inst] = BMPC_LEV0;
+    ok = ok && valid;
+    if (valid) {
+        if (reset) {
+            I.iters[inst] = 0; A.um1_solved[inst] = um1;
+            if (!ok) { I.status[inst] = BMPC_UNSOLVED; I.lvl[inst] = BMPC_LEV0; }
+        }
+        if (ok) { bmpc_publish_u0(I, A.u0_out, (size_t)inst, u_first); I.status[inst] = BMPC_SOLVED; }
+        // working sets of the accepted (or last) candidate: the next solve starts from them, phase B continues from them
+        unsigned long long* dst = (unsigned long long*)rec;
+        constexpr int NW = (int)((S::Np * sizeof(CT) + 7) / 8);
+        unsigned long long wbuf[NW];
 #pragma unroll
-        for (int q = 0; q < S::nu; q++) um1_solved[(size_t)inst * S::nu + q] = I.um1[(size_t)inst * S::nu + q];
+        for (int i = 0; i < NW; i++) wbuf[i] = 0ull;
+#pragma unroll
+        for (int k = 0; k < S::Np; k++) wbuf[(k * sizeof(CT)) / 8] |= (unsigned long long)C(k) << (8 * ((k * sizeof(CT)) % 8));
+#pragma unroll
+        for (int i = 0; i < NW; i++) dst[i] = wbuf[i];
+        *(double*)(rec + A.code_stride - 8) = mumax;
     }
-    TpiAcc W{smem + lane, TPI_STR};
-    if (list) {
-        if (lane < nvalid) { const double* src = I.vw + (size_t)inst * S::mc + S::nx; for (int i = 0; i < S::MT; i++) W(i) = src[i]; }
-    } else { tpi_load_v<S>(I, idx0, nvalid, smem, 0); }
-    __syncwarp();
-    const bool ok = (lane < nvalid) && tpi_polish_thread<S, TV>(P, I, inst, W, max_steps, next_list, next_count, u0_out);
+    // refinement count: one atomic per warp
+    int tot = used;
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, sft);
+    if (lane == 0 && tot) atomicAdd(A.counts + 1, tot);
     const unsigned okmask = __ballot_sync(0xffffffffu, ok);
     __syncwarp();
-    if (list) {
-        if (ok) {
-            double* dst = I.vw + (size_t)inst * S::mc;
-            for (int i = 0; i < S::MT; i++) {
-                dst[S::nx + i] = W(tpi_vstar_slot<S>(i));
-            }
-            for (int q = 0; q < S::nx; q++) dst[q] = I.x0[(size_t)inst * S::nx + q];
-        }
-    } else {
-        double* dst = I.vw + (size_t)idx0 * S::mc;
+    // v* = exact ADMM fixed point of this problem (warm start of a later ADMM round): staged in the consumed gain slots
+    if (inst0_contig >= 0) {
+        double* dst = I.vw + (size_t)inst0_contig * S::mc;
 #pragma unroll 5
         for (int idx = lane; idx < nvalid * S::mc; idx += 32) {
             const int t = idx / S::mc, g = idx - t * S::mc;
-            if (!((okmask >> t) & 1u)) continue;
-            double val;
-            if (g < S::nx) val = I.x0[(size_t)(idx0 + t) * S::nx + g];
-            else {
-                val = smem[tpi_vstar_slot<S>(g - S::nx) * TPI_STR + t];
-            }
-            dst[idx] = val;
+            if (!((okmask >> t) & 1u) || g == S::mc - 1) continue;
+            dst[idx] = (g < nx) ? I.x0[(size_t)(inst0_contig + t) * nx + g] : wsm[tpi_vstar_slot<S>(g - nx) * TPI_STR + t];
         }
+        if (ok) I.vw[(size_t)inst * S::mc + S::mc - 1] = vq;
+    } else if (ok) {
+        double* dst = I.vw + (size_t)inst * S::mc;
+        for (int i = 0; i < L::VROWS; i++) dst[nx + i] = W(tpi_vstar_slot<S>(i));
+        dst[S::mc - 1] = vq;
+#pragma unroll
+        for (int q = 0; q < nx; q++) dst[q] = x0[q];
+    }
+    // unfinished lanes: to the queue of phase B (their working sets must be visible first) or to the host's list
+    const bool fail = valid && !ok && I.status[inst] != BMPC_PRIMAL_INFEASIBLE;
+    const unsigned fmask = __ballot_sync(0xffffffffu, fail);
+    if (fmask) {
+        const int nf = __popc(fmask), pos = __popc(fmask & ((1u << lane) - 1u));
+        int basep = 0;
+        if (to_queue) {
+            __threadfence();
+            if (lane == 0) basep = atomicAdd(A.counts + TPI_Q_TAIL, nf);
+            basep = __shfl_sync(0xffffffffu, basep, 0);
+            if (fail) ((volatile int32_t*)A.queue)[basep + pos] = inst;
+        } else {
+            if (lane == 0) basep = atomicAdd(A.counts, nf);
+            basep = __shfl_sync(0xffffffffu, basep, 0);
+            if (fail) A.next_list[basep + pos] = inst;
+        }
+    }
+    __syncwarp();
+}
+
+template <class S, bool TV>
+__global__ void __launch_bounds__(TPI_POL_WARPS * 32, 1) k_tpi_pol(const __grid_constant__ TpiPolParams<S> P, BmpcInst I, TpiPolArgs A) {
+    using L = TpiPolLayout<S>; using CT = typename TpiCode<S>::type;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* wsm = (double*)((char*)smem + (size_t)warp * L::per_warp);
+    CT* csm = (CT*)((char*)wsm + L::gain_bytes);
+    const int nchunks = (A.count + 31) / 32;
+    // ---- phase A
+    for (;;) {
+        int chunk = 0;
+        if (lane == 0) chunk = atomicAdd(A.counts + TPI_Q_CURSOR, 1);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= nchunks) break;
+        const int idx0 = chunk * 32, nvalid = (A.count - idx0) < 32 ? (A.count - idx0) : 32;
+        const bool valid = lane < nvalid;
+        const int inst = A.list ? (valid ? A.list[idx0 + lane] : 0) : idx0 + lane;
+        tpi_pol_batch<S, TV>(P, I, A, wsm, csm, inst, valid, A.list ? -1 : idx0, nvalid, A.mode, A.capA, A.capB > 0, A.reset);
+        __threadfence();
+        if (lane == 0) atomicAdd(A.counts + TPI_Q_DONE, 1);
+    }
+    if (A.capB <= 0) return;
+    // ---- phase B: serve the queue until every chunk of phase A is finished and the queue is empty
+    volatile int32_t* ctl = (volatile int32_t*)A.counts;
+    for (;;) {
+        int h = 0, n = 0;
+        if (lane == 0) {
+            const bool all_done = ctl[TPI_Q_DONE] >= nchunks;      // read BEFORE the tail: a tail read after it is final
+            __threadfence();
+            h = ctl[TPI_Q_HEAD]; const int t = ctl[TPI_Q_TAIL];
+            if (h < t) { n = (t - h) < 32 ? (t - h) : 32; if (atomicCAS(A.counts + TPI_Q_HEAD, h, h + n) != h) n = -1; }
+            else n = all_done ? 0 : -1;
+        }
+        h = __shfl_sync(0xffffffffu, h, 0); n = __shfl_sync(0xffffffffu, n, 0);
+        if (n == 0) break;
+        if (n < 0) { __nanosleep(200); continue; }
+        const bool valid = lane < n;
+        int inst = 0;
+        if (valid) {
+            volatile int32_t* q = (volatile int32_t*)A.queue + h + lane;
+            while ((inst = *q) < 0) __nanosleep(50);
+            *q = -1;                                                 // the queue is all -1 again when the launch ends
+        }
+        __threadfence();
+        tpi_pol_batch<S, TV>(P, I, A, wsm, csm, inst, valid, -1, n, 0, A.capB, false, 0);
     }
 }
 
@@ -583,7 +693,7 @@ __global__ void __launch_bounds__(32) k_tpi_polish(const __grid_constant__ TpiRi
 // (`python -m pympc_b200.build --add-shape nx,1,Np` appends one and rebuilds).
 struct TpiEntry {
     int nx, nu, Np, Nc;
-    size_t admm_bytes, ric_bytes;
+    size_t admm_bytes, ric_bytes; int code_stride;
     void (*fill)(const double* hs, const BmpcSysOff& o, void* pa, void* pp);
     int (*configure)();
     void (*launch)(struct bmpc_handle* h, const int32_t* list, int count, int niter, int32_t* next_list, cudaEvent_t mid);
@@ -604,7 +714,8 @@ struct bmpc_handle {
     BmpcInst I;
     double *x0 = nullptr, *um1 = nullptr, *um1_solved = nullptr, *xref = nullptr, *u0_own = nullptr, *u0_bound = nullptr;
     double *seq_x = nullptr, *seq_e = nullptr, *seq_obj = nullptr;
-    int32_t *listA = nullptr, *listB = nullptr, *counts = nullptr;  // counts[2]
+    int32_t *listA = nullptr, *listB = nullptr, *counts = nullptr;  // counts[8]: [0..3] round counters, [4..7] queue control of k_tpi_pol
+    int32_t* queue = nullptr; unsigned char* codes = nullptr;        // phase-B queue and stored working sets of the fast-path polish
     int32_t* h_count = nullptr;                                      // pinned
     cudaEvent_t ev[4];
     int xref_mode = 0;
@@ -638,55 +749,70 @@ static std::string g_create_err;
     } while (0)
 
 template <class S>
+static void launch_tpi_pol(bmpc_handle* h, const int32_t* list, int count, int mode, int capA, int capB, int reset, int32_t* next_list) {
+    using L = TpiPolLayout<S>;
+    const TpiPolParams<S>& PP = *(const TpiPolParams<S>*)h->tpi_polish_params;
+    TpiPolArgs A;
+    A.list = list; A.count = count; A.mode = mode; A.capA = capA; A.capB = capB; A.reset = reset;
+    A.next_list = next_list; A.counts = h->counts; A.queue = h->queue; A.u0_out = h->I.u0; A.um1_solved = h->um1_solved;
+    A.codes = h->codes; A.code_stride = L::code_stride;
+    const int nchunks = (count + 31) / 32;
+    int grid = (nchunks + TPI_POL_WARPS - 1) / TPI_POL_WARPS;
+    if (grid > h->sm_count) grid = h->sm_count;
+    if (grid < 1) grid = 1;
+    const size_t sm = L::per_warp * TPI_POL_WARPS;
+    if (h->xref_mode) k_tpi_pol<S, true><<<grid, TPI_POL_WARPS * 32, sm, h->stream>>>(PP, h->I, A);
+    else k_tpi_pol<S, false><<<grid, TPI_POL_WARPS * 32, sm, h->stream>>>(PP, h->I, A);
+    h->stats.launches++;
+}
+
+// first round of a fast-path solve.  niter == 0 (warm start): ONE launch, the polish starts from the previous solution's working
+// sets shifted by one stage (measured: a few ADMM iterations do not improve that first guess); niter > 0 (cold start,
+// or first_iters set): thread-per-instance ADMM, then the polish takes its working sets from the iterate.
+template <class S>
 static void launch_tpi_round(bmpc_handle* h, const int32_t* list, int count, int niter, int32_t* next_list, cudaEvent_t mid) {
     const int grid = (count + 31) / 32;
     const TpiAdmmParams<S>& PA = *(const TpiAdmmParams<S>*)h->tpi_admm_params;
-    const TpiRicParams<S>& PR = *(const TpiRicParams<S>*)h->tpi_polish_params;
     const int cold = h->cold ? 1 : 0, reset = h->st.round == 0 ? 1 : 0;
-    const size_t sa = S::MT * TPI_STR * 8, sp = S::PROWS * TPI_STR * 8;
-    // niter == 0: warm start straight from the previous solution's working sets (measured: in warm closed loops a few ADMM
-    // iterations do not improve the first active-set guess) -> the ADMM launch is skipped altogether
+    const size_t sa = S::MT * TPI_STR * 8;
+    const int capA = 1, capB = h->tpi_pdas_steps - 1;
     if (niter > 0) {
         if (h->xref_mode)   // one (Np+1) x nx reference per instance
             k_tpi_admm<S, true><<<grid, 32, sa, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts, h->um1_solved);
         else
             k_tpi_admm<S, false><<<grid, 32, sa, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts, h->um1_solved);
         h->stats.launches++;
-    } else if (reset) cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 4, h->stream);
-    cudaEventRecord(mid, h->stream);
-    const int preset = (niter > 0) ? 0 : reset;
-    if (h->xref_mode)
-        k_tpi_polish<S, true><<<grid, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0, preset, h->um1_solved);
-    else
-        k_tpi_polish<S, false><<<grid, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0, preset, h->um1_solved);
-    h->stats.launches++;
+        cudaEventRecord(mid, h->stream);
+        launch_tpi_pol<S>(h, list, count, 2, capA, capB, 0, next_list);
+    } else {
+        cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 8, h->stream);
+        cudaEventRecord(mid, h->stream);
+        launch_tpi_pol<S>(h, list, count, h->cfg.shift_warm ? 1 : 0, capA, capB, reset, next_list);
+    }
 }
 
+// straggler rounds: the listed instances come back from an ADMM chunk of the team kernels, working sets from their iterate
 template <class S>
 static void launch_tpi_polish_only(bmpc_handle* h, const int32_t* list, int count, int32_t* next_list) {
-    const TpiRicParams<S>& PR = *(const TpiRicParams<S>*)h->tpi_polish_params;
-    const size_t sp = S::PROWS * TPI_STR * 8;
-    if (h->xref_mode)
-        k_tpi_polish<S, true><<<(count + 31) / 32, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0, 0, h->um1_solved);
-    else
-        k_tpi_polish<S, false><<<(count + 31) / 32, 32, sp, h->stream>>>(PR, h->I, list, count, h->tpi_pdas_steps, next_list, h->counts, h->I.u0, 0, h->um1_solved);
-    h->stats.launches++;
+    launch_tpi_pol<S>(h, list, count, 2, 2, h->tpi_pdas_steps - 2, 0, next_list);
 }
 
 template <class S>
 static void tpi_fill_entry(const double* hs, const BmpcSysOff& o, void* pa, void* pp) {
-    tpi_fill_admm<S>(hs, o, *(TpiAdmmParams<S>*)pa); tpi_fill_riccati<S>(hs, o, *(TpiRicParams<S>*)pp);
+    tpi_fill_admm<S>(hs, o, *(TpiAdmmParams<S>*)pa); tpi_fill_pol<S>(hs, o, *(TpiPolParams<S>*)pp);
 }
 template <class S>
 static int tpi_configure_entry() {
     if (cudaFuncSetAttribute(k_tpi_admm<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::MT * TPI_STR * 8)) != cudaSuccess) return 1;
     if (cudaFuncSetAttribute(k_tpi_admm<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::MT * TPI_STR * 8)) != cudaSuccess) return 1;
-    if (cudaFuncSetAttribute(k_tpi_polish<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::PROWS * TPI_STR * 8)) != cudaSuccess) return 1;
-    if (cudaFuncSetAttribute(k_tpi_polish<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::PROWS * TPI_STR * 8)) != cudaSuccess) return 1;
+    const int sm = (int)(TpiPolLayout<S>::per_warp * TPI_POL_WARPS);
+    if (cudaFuncSetAttribute(k_tpi_pol<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(k_tpi_pol<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm) != cudaSuccess) return 1;
     return 0;
 }
 #define BMPC_TPI_SHAPE(NX_, NU_, NP_, NC_)                                                                                   \
-    {NX_, NU_, NP_, NC_, sizeof(TpiAdmmParams<TpiShape<NX_, NU_, NP_, NC_>>), sizeof(TpiRicParams<TpiShape<NX_, NU_, NP_, NC_>>), \
+    {NX_, NU_, NP_, NC_, sizeof(TpiAdmmParams<TpiShape<NX_, NU_, NP_, NC_>>), sizeof(TpiPolParams<TpiShape<NX_, NU_, NP_, NC_>>), \
+     TpiPolLayout<TpiShape<NX_, NU_, NP_, NC_>>::code_stride,                                                                \
      tpi_fill_entry<TpiShape<NX_, NU_, NP_, NC_>>, tpi_configure_entry<TpiShape<NX_, NU_, NP_, NC_>>,                         \
      launch_tpi_round<TpiShape<NX_, NU_, NP_, NC_>>, launch_tpi_polish_only<TpiShape<NX_, NU_, NP_, NC_>>},
 static const TpiEntry g_tpi_table[] = {
@@ -704,7 +830,7 @@ void bmpc_default_config(bmpc_config* c) {
     memset(c, 0, sizeof(*c));
     c->Np = 20; c->Nc = 0; c->batch = 1; c->device = 0; c->soft_on = 1;
     c->max_iter = 4000; c->first_iters = 0; c->pdas_steps = 10; c->rmax = 0; c->polish = 1;
-    c->team_threads = 0; c->warps_per_block = 0; c->fast_path = 1; c->n_sys = 1;
+    c->team_threads = 0; c->warps_per_block = 0; c->fast_path = 1; c->n_sys = 1; c->shift_warm = 1;
     c->eps_feas = 1e6; c->rho = 0.0; c->sigma = 1e-6; c->alpha = 1.6; c->eps_abs = 1e-3; c->eps_rel = 1e-3;
 }
 
@@ -839,7 +965,9 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     ok &= dalloc((void**)&h->I.lvl, sizeof(int32_t) * B);
     ok &= dalloc((void**)&h->listA, sizeof(int32_t) * B);
     ok &= dalloc((void**)&h->listB, sizeof(int32_t) * B);
-    ok &= dalloc((void**)&h->counts, sizeof(int32_t) * 4);
+    ok &= dalloc((void**)&h->counts, sizeof(int32_t) * 8);
+    ok &= dalloc((void**)&h->queue, sizeof(int32_t) * B);
+    ok &= dalloc((void**)&h->codes, (size_t)B * 72);       // largest record: 32 stages x 2 bytes + 8 (Np < 32 on the fast path)
     ok &= dalloc((void**)&h->ovf, sizeof(int32_t) * (size_t)B);
     ok &= dalloc((void**)&h->vprev, sizeof(double) * (size_t)B * d.mc);
     ok &= dalloc((void**)&h->lprev, sizeof(int32_t) * (size_t)B);
@@ -852,6 +980,9 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     cudaMemset(h->u0_own, 0, sizeof(double) * B * d.nu);
     cudaMemset(h->I.Us, 0, sizeof(double) * B * d.NU);
     cudaMemset(h->I.Ua, 0, sizeof(double) * B * d.NU);
+    cudaMemset(h->queue, 0xff, sizeof(int32_t) * B);
+    cudaMemset(h->codes, 0, (size_t)B * 72);
+    cudaMemset(h->counts, 0, sizeof(int32_t) * 8);
     h->I.sys_stride = h->cfg.n_sys > 1 ? (size_t)h->o.total : 0;
     h->I.x0 = h->x0; h->I.um1 = h->um1; h->I.um1_solved = h->um1_solved; h->I.xref = h->xref; h->I.u0 = h->u0_own;
     k_reset<<<(int)((B + 255) / 256), 256, 0, h->stream>>>(h->I, (int)B);
@@ -865,7 +996,7 @@ void bmpc_destroy(bmpc_handle* h) {
     cudaSetDevice(h->cfg.device);
     if (h->pending) cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->sys, h->x0, h->um1, h->um1_solved, h->xref, h->u0_own, h->I.g, h->I.cc, h->I.xw, h->I.vw, h->I.Ua, h->I.Us, h->I.res,
-                    h->I.status, h->I.iters, h->I.psteps, h->I.lvl, h->listA, h->listB, h->counts, h->ovf, h->vprev, h->lprev, h->seq_x, h->seq_e, h->seq_obj};
+                    h->I.status, h->I.iters, h->I.psteps, h->I.lvl, h->listA, h->listB, h->counts, h->queue, h->codes, h->ovf, h->vprev, h->lprev, h->seq_x, h->seq_e, h->seq_obj};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_count) cudaFreeHost(h->h_count);
     free(h->tpi_admm_params); free(h->tpi_polish_params);
@@ -1043,7 +1174,7 @@ static int enqueue_round(bmpc_handle* h) {
             h->stats.launches++;
             BMPC_CUDA(cudaMemcpyAsync(h->um1_solved, h->um1, sizeof(double) * (size_t)B * h->d.nu, cudaMemcpyDeviceToDevice, h->stream));
         }
-        BMPC_CUDA(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 4, h->stream));
+        BMPC_CUDA(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 8, h->stream));
     }
     BMPC_CUDA(cudaEventRecord(h->ev[0], h->stream));
     if (tpi) {

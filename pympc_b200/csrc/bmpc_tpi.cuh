@@ -644,3 +644,320 @@ inline void tpi_fill_riccati(const double* sys, const BmpcSysOff& o, TpiRicParam
     for (int i = 0; i < S::nx * S::nx; i++) { P.Qx[i] = sys[o.Qx + i]; P.QxN[i] = sys[o.QxN + i]; }
     P.Qu = sys[o.Qu]; P.QDu = sys[o.QDu]; P.uref = sys[o.uref]; P.rho_e = sys[o.scal + BMPC_S_RHOE];
 }
+
+// ================================================================================================
+// Second-generation Riccati polish (nu == 1): ONE active-set refinement = tpi2_backward + tpi2_forward.
+//
+// What changed against tpi_ric_backward / tpi_ric_forward above (profiles/ncu_r1_final_summary.txt: 23 % fp64 pipe, the
+// forward sweep spent 4 instructions on set bookkeeping per fp64 instruction):
+//  * the working sets live as ONE small code word per stage (state rows up / down, input row, delta-u row, the spurious last
+//    row) in shared memory next to the gains, and between solves as 2 bytes per stage in global memory: a warm solve reads
+//    40 bytes of sets instead of the 968-byte iterate v, shifted by one stage (receding horizon: the plan of step t+1 is the
+//    tail of the plan of step t);
+//  * both sweeps are branch-free: the pin type of a stage (free / input bound / delta-u bound / spurious row) only selects
+//    coefficients, so lanes with different working sets never diverge;
+//  * the cost-to-go matrix is kept symmetric (upper triangle), verification thresholds are precomputed constants, the
+//    reciprocal of huu is MUFU + two Newton steps (no slow-path branch), the constant-reference term Q xref is hoisted.
+// Row / slot conventions are those of the first generation (tpi_vstar_slot): stage k owns gain slots [k (nx+2), (k+1)(nx+2)).
+#include <stdint.h>
+#include <type_traits>
+
+template <class S>
+struct TpiCode {
+    static constexpr unsigned XUP = 0, XDN = S::nx, UUP = 2 * S::nx, UDN = UUP + 1, DUP = UUP + 2, DDN = UUP + 3, QUP = UUP + 4, QDN = UUP + 5;
+    static constexpr unsigned BITS = 2 * S::nx + 6;
+    static constexpr unsigned XMASK = (1u << (2 * S::nx)) - 1u, UDMASK = 0xFu << UUP, QMASK = 0x3u << QUP;
+    using type = typename std::conditional<(BITS <= 16), uint16_t, uint32_t>::type;
+};
+
+template <class S>
+struct TpiPolParams {
+    double Ad[S::nx * S::nx], Bd[S::nx];
+    double Qx[S::nx * S::nx], QxN[S::nx * S::nx];
+    double xlo[S::nx], xhi[S::nx];
+    double xlo_m[S::nx], xlo_p[S::nx], xhi_m[S::nx], xhi_p[S::nx];    // bound -/+ 1e-11 (1 + |bound|): soft-row labels
+    double cx[S::nx];                                                 // rho_e / rho_x: soft-row multiplier in units of v
+    double ulo, uhi, ulo_m, uhi_p, dlo, dhi, dlo_m, dhi_p;            // hard rows: bounds and bound -/+ 1e-9 (1 + |bound|)
+    double irhou, irhod, Qu, QDu, quref, rho_e;
+};
+
+#ifdef BMPC_HOSTEMU
+BMPC_HD double tpi_rcp(double h) { return 1.0 / h; }
+#else
+// 1/h for h > 0 in the normal range (a Schur complement of a positive definite Hessian): MUFU seed + two Newton steps
+__device__ __forceinline__ double tpi_rcp(double h) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(h));
+    double e = fma(-h, r, 1.0); r = fma(r, e, r);
+    e = fma(-h, r, 1.0); r = fma(r, e, r);
+    return r;
+}
+#endif
+
+// decoded pin of one stage
+struct TpiPin { bool free_, upin, dpin, qpin; double pin; };
+template <class S>
+BMPC_HD TpiPin tpi2_pin(const TpiPolParams<S>& P, unsigned code, bool held) {
+    using C = TpiCode<S>;
+    const bool uu = (code >> C::UUP) & 1u, ud = (code >> C::UDN) & 1u, du = (code >> C::DUP) & 1u, dd = (code >> C::DDN) & 1u,
+               qu = (code >> C::QUP) & 1u, qd = (code >> C::QDN) & 1u;
+    TpiPin t;
+    t.upin = (uu || ud) && !held;
+    t.dpin = held || (!t.upin && (du || dd));
+    t.qpin = !t.upin && !t.dpin && (qu || qd);
+    t.free_ = !(t.upin || t.dpin || t.qpin);
+    // priority as in tpi_pin_of: input bound, delta-u row, then the reference's spurious last row (-u within [Dumin, Dumax])
+    double p = qu ? -P.dhi : -P.dlo;
+    p = t.qpin ? p : 0.0;
+    p = t.dpin ? (du ? P.dhi : P.dlo) : p;
+    p = held ? 0.0 : p;
+    p = t.upin ? (uu ? P.uhi : P.ulo) : p;
+    t.pin = p;
+    return t;
+}
+
+// Backward sweep: fills the gain slots of W from the working-set codes C(k).
+template <class S, class XR, class CA>
+BMPC_HD void tpi2_backward(const TpiPolParams<S>& P, TpiAcc W, CA C, XR xr) {
+    static_assert(S::nu == 1 && S::Nc <= S::Np, "Riccati polish is specialised to nu == 1");
+    constexpr int nx = S::nx, N = S::Np, Nc = S::Nc, nz1 = nx + 2;
+    using CD = TpiCode<S>;
+    double Pm[nx * nx], pxw[nx], px[nx], pww = 0.0, pw = 0.0;          // Pm symmetric: both triangles hold the same values
+    double qc[nx];                                                       // Qx xref (constant reference)
+    if (!XR::TV) {
+#pragma unroll
+        for (int a = 0; a < nx; a++) {
+            double q = 0.0;
+#pragma unroll
+            for (int b = 0; b < nx; b++) q += P.Qx[a * nx + b] * xr(0, b);
+            qc[a] = q;
+        }
+    }
+    {   // terminal cost of x_N (its rows are the state bits of stage N-1)
+        const unsigned c = C(N - 1);
+#pragma unroll
+        for (int a = 0; a < nx; a++) {
+            const bool su = (c >> (CD::XUP + a)) & 1u, sd = (c >> (CD::XDN + a)) & 1u;
+            double q = 0.0;
+#pragma unroll
+            for (int b = 0; b < nx; b++) { Pm[a * nx + b] = P.QxN[a * nx + b]; q += P.QxN[a * nx + b] * xr(N, b); }
+            const double m = (su || sd) ? P.rho_e : 0.0;
+            Pm[a * nx + a] += m;
+            px[a] = -(q + m * (su ? P.xhi[a] : P.xlo[a])); pxw[a] = 0.0;
+        }
+    }
+#pragma unroll 1
+    for (int k = N - 1; k >= 0; k--) {
+        const unsigned code = C(k);
+        const unsigned cprev = C(k >= 1 ? k - 1 : 0);                   // state bits of x_k (x_0 is data: its cost is irrelevant)
+        double T[nx * nx], PB[nx];
+#pragma unroll
+        for (int a = 0; a < nx; a++) {
+#pragma unroll
+            for (int b = 0; b < nx; b++) {
+                double acc = Pm[a * nx + 0] * P.Ad[0 * nx + b];
+#pragma unroll
+                for (int q = 1; q < nx; q++) acc = fma(Pm[a * nx + q], P.Ad[q * nx + b], acc);
+                T[a * nx + b] = acc;
+            }
+            double accb = Pm[a * nx + 0] * P.Bd[0];
+#pragma unroll
+            for (int q = 1; q < nx; q++) accb = fma(Pm[a * nx + q], P.Bd[q], accb);
+            PB[a] = accb;
+        }
+        double Hxx[nx * nx], hx[nx], gx[nx];
+        double huu = pww + (P.Qu + P.QDu), gu = pw - P.quref;
+#pragma unroll
+        for (int a = 0; a < nx; a++) { huu = fma(P.Bd[a], PB[a] + 2.0 * pxw[a], huu); gu = fma(P.Bd[a], px[a], gu); }
+#pragma unroll
+        for (int a = 0; a < nx; a++) {
+#pragma unroll
+            for (int b = a; b < nx; b++) {                              // upper triangle of A' T (symmetric)
+                double acc = P.Ad[0 * nx + a] * T[0 * nx + b];
+#pragma unroll
+                for (int q = 1; q < nx; q++) acc = fma(P.Ad[q * nx + a], T[q * nx + b], acc);
+                Hxx[a * nx + b] = acc + P.Qx[a * nx + b];
+            }
+            double h = 0.0, g = 0.0;
+#pragma unroll
+            for (int q = 0; q < nx; q++) { h = fma(P.Ad[q * nx + a], PB[q] + pxw[q], h); g = fma(P.Ad[q * nx + a], px[q], g); }
+            hx[a] = h;
+            const bool su = (cprev >> (CD::XUP + a)) & 1u, sd = (cprev >> (CD::XDN + a)) & 1u;
+            const double m = (su || sd) ? P.rho_e : 0.0;
+            double q;
+            if (XR::TV) {
+                q = 0.0;
+#pragma unroll
+                for (int b = 0; b < nx; b++) q = fma(P.Qx[a * nx + b], xr(k, b), q);
+            } else q = qc[a];
+            Hxx[a * nx + a] += m;
+            gx[a] = g - fma(m, su ? P.xhi[a] : P.xlo[a], q);
+        }
+        const bool held = (Nc < N) && (k >= Nc);
+        const TpiPin t = tpi2_pin<S>(P, code, held);
+        const double hw = -P.QDu, Hww = P.QDu;
+        const double dp = t.dpin ? 1.0 : 0.0;
+        const double inv = tpi_rcp(huu);
+        const double c1 = t.free_ ? inv : 0.0, c4 = t.free_ ? inv : 1.0;
+        const double c2 = fma(-c1, gu, t.pin);                          // free: -gu / huu ; pinned: pin
+        const double c3 = fma(-c1, hw, dp);
+        const double pinned0 = fma(huu, t.pin, gu);                     // dQ/du offset of a pinned stage
+        const int base = k * nz1;
+#pragma unroll
+        for (int a = 0; a < nx; a++) W(base + a) = hx[a] * c4;
+        W(base + nx) = t.free_ ? hw * inv : fma(dp, huu, hw);
+        W(base + nx + 1) = t.free_ ? gu * inv : pinned0;
+#pragma unroll
+        for (int a = 0; a < nx; a++) {
+            const double ha = hx[a] * c1;
+#pragma unroll
+            for (int b = a; b < nx; b++) { const double v = fma(-ha, hx[b], Hxx[a * nx + b]); Pm[a * nx + b] = v; Pm[b * nx + a] = v; }
+            px[a] = fma(hx[a], c2, gx[a]);
+            pxw[a] = hx[a] * c3;
+        }
+        pww = fma(dp, fma(2.0, hw, huu), Hww) - c1 * hw * hw;
+        pw = fma(hw, c2, dp * pinned0);
+    }
+}
+
+// Forward sweep: rolls the closed loop out, verifies the KKT conditions of the working sets, writes the NEXT working sets
+// into C(k), the inputs through outu(k, u), the exact ADMM fixed point v* = z* + y*/rho into the gain slots just consumed
+// (the spurious last row into vq) and returns true when the candidate is the minimiser.  mumax: in = scale of the multiplier
+// sign tolerance (largest multiplier of the previous refinement, 0 at first), out = largest multiplier of this one.
+template <class S, class CA, class FU>
+BMPC_HD bool tpi2_forward(const TpiPolParams<S>& P, TpiAcc W, CA C, const double* x0, double um1, double& mumax, double& vq, FU outu) {
+    constexpr int nx = S::nx, N = S::Np, Nc = S::Nc, nz1 = nx + 2;
+    using CD = TpiCode<S>;
+    const double mutol = 1e-9 * (1.0 + mumax);
+    double mnew = 0.0;
+    bool bad = false;
+    double x[nx], w = um1;
+#pragma unroll
+    for (int a = 0; a < nx; a++) x[a] = x0[a];
+    // KKT check of one hard row; returns its bits of the next working set (bit 0 up, bit 1 down)
+    auto hard_row = [&](double zi, double lo_m, double hi_p, bool su, bool sd, double mu) -> unsigned {
+        const bool vu = zi > hi_p, vd = zi < lo_m;
+        bad = bad || vu || vd || (su && mu < -mutol) || (sd && mu > mutol);
+        const bool nu_ = vu || (!vd && su && mu > 0.0);
+        const bool nd_ = !nu_ && (vd || (sd && mu < 0.0));
+        return (nu_ ? 1u : 0u) | (nd_ ? 2u : 0u);
+    };
+#pragma unroll 1
+    for (int k = 0; k < N; k++) {
+        const unsigned code = C(k);
+        const int base = k * nz1;
+        double lin = W(base + nx + 1);
+#pragma unroll
+        for (int a = 0; a < nx; a++) lin = fma(W(base + a), x[a], lin);
+        lin = fma(W(base + nx), w, lin);
+        const bool held = (Nc < N) && (k >= Nc);
+        const TpiPin t = tpi2_pin<S>(P, code, held);
+        double u = t.dpin ? w + t.pin : t.pin;
+        u = t.free_ ? -lin : u;
+        unsigned ncode = 0u;
+        if (!held) {
+            const double mu_u = t.upin ? -lin : 0.0, mu_d = t.dpin ? -lin : 0.0;
+            mnew = fmax(mnew, (t.free_ ? 0.0 : fabs(lin)));
+            outu(k, u);
+            unsigned hb = hard_row(u, P.ulo_m, P.uhi_p, (code >> CD::UUP) & 1u, (code >> CD::UDN) & 1u, mu_u);
+            ncode |= hb << CD::UUP;
+            W(base + nx) = fma(mu_u, P.irhou, u);
+            const double dz = u - w;                                    // row 0: u_0 against bounds shifted by u_-1 = the same test
+            hb = hard_row(dz, P.dlo_m, P.dhi_p, (code >> CD::DUP) & 1u, (code >> CD::DDN) & 1u, mu_d);
+            ncode |= hb << CD::DUP;
+            W(base + nx + 1) = fma(mu_d, P.irhod, (k == 0) ? u : dz);
+            if (k == Nc - 1) {
+                const double mu_q = t.qpin ? lin : 0.0;
+                hb = hard_row(-u, P.dlo_m, P.dhi_p, (code >> CD::QUP) & 1u, (code >> CD::QDN) & 1u, mu_q);
+                ncode |= hb << CD::QUP;
+                vq = fma(mu_q, P.irhod, -u);
+            }
+        }
+        double xn[nx];
+#pragma unroll
+        for (int a = 0; a < nx; a++) {
+            double a0 = P.Bd[a] * u, a1 = 0.0;
+#pragma unroll
+            for (int q = 0; q < nx; q += 2) { a0 = fma(P.Ad[a * nx + q], x[q], a0); if (q + 1 < nx) a1 = fma(P.Ad[a * nx + q + 1], x[q + 1], a1); }
+            xn[a] = a0 + a1;
+        }
+        w = u;
+#pragma unroll
+        for (int a = 0; a < nx; a++) {
+            const double zi = xn[a];
+            x[a] = zi;
+            const bool su = (code >> (CD::XUP + a)) & 1u, sd = (code >> (CD::XDN + a)) & 1u;
+            const bool nu_ = zi > P.xhi_p[a], nd_ = zi < P.xlo_m[a];
+            // a label may differ from the side the candidate is on only if the row sits on that bound (to 1e-11 relative)
+            const bool oku = su ? (zi >= P.xhi_m[a]) : !nu_;
+            const bool okd = sd ? (zi <= P.xlo_p[a]) : !nd_;
+            bad = bad || !(oku && okd);
+            const double bnd = su ? P.xhi[a] : P.xlo[a];
+            const double cm = (su || sd) ? P.cx[a] : 0.0;
+            W(base + a) = fma(cm, zi - bnd, zi);
+            ncode |= (nu_ ? 1u : 0u) << (CD::XUP + a);
+            ncode |= ((nd_ && !nu_) ? 1u : 0u) << (CD::XDN + a);
+        }
+        C(k) = (typename CD::type)ncode;
+    }
+    mumax = mnew;
+    return !bad;
+}
+
+// first working sets from an ADMM iterate v (TPI rows; after a cold start or a straggler round): as tpi_sets_from_v
+template <class S, class Acc, class CA>
+BMPC_HD void tpi2_codes_from_v(const TpiPolParams<S>& P, double um1, Acc V, double vlast, CA C) {
+    constexpr int nx = S::nx, Np = S::Np, Nc = S::Nc, NS = S::NS, NU = S::NU;
+    using CD = TpiCode<S>;
+    auto over = [](double v, double hi) { return v > hi + 1e-9 * (1.0 + fabs(hi)); };
+    auto under = [](double v, double lo) { return v < lo - 1e-9 * (1.0 + fabs(lo)); };
+#pragma unroll 1
+    for (int k = 0; k < Np; k++) {
+        unsigned c = 0u;
+#pragma unroll
+        for (int a = 0; a < nx; a++) {
+            const double v = V(k * nx + a);
+            c |= (over(v, P.xhi[a]) ? 1u : 0u) << (CD::XUP + a); c |= (under(v, P.xlo[a]) ? 1u : 0u) << (CD::XDN + a);
+        }
+        if (k < Nc) {
+            const double vu = V(NS + k);
+            c |= (over(vu, P.uhi) ? 1u : 0u) << CD::UUP; c |= (under(vu, P.ulo) ? 1u : 0u) << CD::UDN;
+            const double vd = V(NS + NU + k), sh = (k == 0) ? um1 : 0.0;
+            c |= (over(vd, P.dhi + sh) ? 1u : 0u) << CD::DUP; c |= (under(vd, P.dlo + sh) ? 1u : 0u) << CD::DDN;
+            if (k == Nc - 1) { c |= (over(vlast, P.dhi) ? 1u : 0u) << CD::QUP; c |= (under(vlast, P.dlo) ? 1u : 0u) << CD::QDN; }
+        }
+        C(k) = (typename CD::type)c;
+    }
+}
+
+// receding-horizon shift of stored working sets: stage k takes the sets of stage k + 1 (the last stage keeps its own)
+template <class S>
+BMPC_HD unsigned tpi2_shifted_code(const typename TpiCode<S>::type* stored, int k, bool shift) {
+    using CD = TpiCode<S>;
+    constexpr int Np = S::Np, Nc = S::Nc;
+    if (!shift) return stored[k];
+    const int ks = (k + 1 < Np) ? k + 1 : Np - 1, ku = (k + 1 < Nc) ? k + 1 : Nc - 1;
+    unsigned c = stored[ks] & CD::XMASK;
+    if (k < Nc) c |= stored[ku] & CD::UDMASK;
+    if (k == Nc - 1) c |= stored[Nc - 1] & CD::QMASK;
+    return c;
+}
+
+template <class S>
+inline void tpi_fill_pol(const double* sys, const BmpcSysOff& o, TpiPolParams<S>& P) {
+    constexpr int nx = S::nx, NU = S::NU, NX = S::NX;
+    for (int i = 0; i < nx * nx; i++) { P.Ad[i] = sys[o.Ad + i]; P.Qx[i] = sys[o.Qx + i]; P.QxN[i] = sys[o.QxN + i]; }
+    for (int i = 0; i < nx; i++) P.Bd[i] = sys[o.Bd + i];
+    const double rho_e = sys[o.scal + BMPC_S_RHOE];
+    auto tol = [](double b, double rel, double sgn) { return (fabs(b) > 1e300) ? b : b + sgn * rel * (1.0 + fabs(b)); };
+    for (int a = 0; a < nx; a++) {
+        const double lo = sys[o.lo0 + nx + a], hi = sys[o.hi0 + nx + a];
+        P.xlo[a] = lo; P.xhi[a] = hi;
+        P.xlo_m[a] = tol(lo, 1e-11, -1.0); P.xlo_p[a] = tol(lo, 1e-11, 1.0); P.xhi_m[a] = tol(hi, 1e-11, -1.0); P.xhi_p[a] = tol(hi, 1e-11, 1.0);
+        P.cx[a] = rho_e / sys[o.rho + nx + a];
+    }
+    P.ulo = sys[o.lo0 + NX]; P.uhi = sys[o.hi0 + NX]; P.ulo_m = tol(P.ulo, 1e-9, -1.0); P.uhi_p = tol(P.uhi, 1e-9, 1.0);
+    P.dlo = sys[o.lo0 + NX + NU]; P.dhi = sys[o.hi0 + NX + NU]; P.dlo_m = tol(P.dlo, 1e-9, -1.0); P.dhi_p = tol(P.dhi, 1e-9, 1.0);
+    P.irhou = 1.0 / sys[o.rho + NX]; P.irhod = 1.0 / sys[o.rho + NX + NU];
+    P.Qu = sys[o.Qu]; P.QDu = sys[o.QDu]; P.quref = sys[o.Qu] * sys[o.uref]; P.rho_e = rho_e;
+}

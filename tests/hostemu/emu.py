@@ -84,6 +84,19 @@ class EmuSystem:
         self.cold = 0
         return U, ps
 
+    def tpi2_step(self, x0, um1, xref, mode=1, max_ref=8):
+        """second-generation Riccati polish on the stored working-set codes (mode 0 as stored, 1 shifted one stage, 2 from v);
+        returns (U, refinements used); state: self.codes, self.v, self.mumax."""
+        x0 = np.ascontiguousarray(x0, float); um1 = np.ascontiguousarray(um1, float); xref = np.ascontiguousarray(xref, float)
+        tv = 0 if xref.ndim == 1 else 1
+        if not hasattr(self, "codes"):
+            self.codes = np.zeros(self.Np, np.uint32)
+        U = np.zeros(self.NU); mm = np.zeros(1)
+        f = self.L.emu_tpi2_step
+        f.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        ps = f(self.nx, self.nu, self.Np, self.Nc, _p(self.sys), _p(x0), _p(um1), _p(xref), tv, _p(self.codes), mode, _p(self.v), _p(U), max_ref, _p(mm))
+        return U, ps
+
     def tile_compare(self, X0, Um1, Xref, niter, lvl=None, x_in=None, v_in=None, T=4):
         """Run the tile ADMM and the per-instance team ADMM on the same T (2, 4 or 8) instances; returns (ref, tile) dicts."""
         X0 = np.ascontiguousarray(X0, float); Um1 = np.ascontiguousarray(Um1, float); Xref = np.ascontiguousarray(Xref, float)

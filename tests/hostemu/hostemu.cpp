@@ -122,6 +122,60 @@ extern "C" int emu_tpi_step(int nx, int nu, int Np, int Nc, const double* sys, c
 }
 
 
+// Second-generation Riccati polish (tpi2_*): up to max_ref refinements from the working-set codes (mode 0: as stored,
+// 1: shifted by one stage, 2: derived from the TPI rows of v).  codes: Np words in/out; v [mc] in (mode 2) / out (v* when verified);
+// mumax in/out.  Returns refinements used (> 0 verified, 0 not verified, -100 shape not compiled).
+template <class S, bool TV>
+static int emu_tpi2_run(const double* sys, const double* x0, const double* um1, const double* xref, unsigned* codes, int mode,
+                        double* v, double* Uout, int max_ref, double* mumax_io) {
+    using CT = typename TpiCode<S>::type;
+    const TpiXref<S, TV> xr{xref};
+    BmpcDims d = bmpc_make_dims(S::nx, S::nu, S::Np, S::Nc); BmpcSysOff o = bmpc_make_off(d);
+    TpiPolParams<S>* P = new TpiPolParams<S>(); tpi_fill_pol<S>(sys, o, *P);
+    double* col = (double*)calloc(S::MT + 8, sizeof(double));
+    CT stored[S::Np], cur[S::Np];
+    for (int k = 0; k < S::Np; k++) stored[k] = (CT)codes[k];
+    TpiAcc W{col, 1};
+    auto C = [&](int k) -> CT& { return cur[k]; };
+    if (mode == 2) {
+        for (int i = 0; i < S::MT; i++) col[i] = v[i + S::nx];
+        tpi2_codes_from_v<S>(*P, um1[0], W, col[S::MT - 1], C);
+    } else {
+        for (int k = 0; k < S::Np; k++) cur[k] = (CT)tpi2_shifted_code<S>(stored, k, mode == 1);
+    }
+    double mumax = *mumax_io, vq = 0.0, U[S::NU];
+    int used = 0;
+    for (int r = 0; r < max_ref; r++) {
+        tpi2_backward<S>(*P, W, C, xr);
+        const bool ok = tpi2_forward<S>(*P, W, C, x0, um1[0], mumax, vq, [&](int j, double u) { U[j] = u; });
+        if (ok) { used = r + 1; break; }
+    }
+    if (used > 0) {
+        for (int i = 0; i < S::MT - 1; i++) v[i + S::nx] = col[tpi_vstar_slot<S>(i)];
+        v[S::nx + S::MT - 1] = vq;
+        for (int q = 0; q < S::nx; q++) v[q] = x0[q];
+        for (int j = 0; j < S::NU; j++) Uout[j] = U[j];
+    }
+    for (int k = 0; k < S::Np; k++) codes[k] = cur[k];
+    *mumax_io = mumax;
+    free(col); delete P;
+    return used;
+}
+
+extern "C" int emu_tpi2_step(int nx, int nu, int Np, int Nc, const double* sys, const double* x0, const double* um1, const double* xref,
+                             int xref_mode, unsigned* codes, int mode, double* v, double* Uout, int max_ref, double* mumax_io) {
+#define EMU_TPI2_ARGS sys, x0, um1, xref, codes, mode, v, Uout, max_ref, mumax_io
+    if (nx == 4 && nu == 1 && Np == 20 && Nc == 20)
+        return xref_mode ? emu_tpi2_run<TpiShape<4, 1, 20, 20>, true>(EMU_TPI2_ARGS) : emu_tpi2_run<TpiShape<4, 1, 20, 20>, false>(EMU_TPI2_ARGS);
+    if (nx == 2 && nu == 1 && Np == 20 && Nc == 20)
+        return xref_mode ? emu_tpi2_run<TpiShape<2, 1, 20, 20>, true>(EMU_TPI2_ARGS) : emu_tpi2_run<TpiShape<2, 1, 20, 20>, false>(EMU_TPI2_ARGS);
+    if (nx == 4 && nu == 1 && Np == 20 && Nc == 10)
+        return xref_mode ? emu_tpi2_run<TpiShape<4, 1, 20, 10>, true>(EMU_TPI2_ARGS) : emu_tpi2_run<TpiShape<4, 1, 20, 10>, false>(EMU_TPI2_ARGS);
+#undef EMU_TPI2_ARGS
+    return -100;
+}
+
+
 // Tile ADMM (bmpc_tile.cuh) against the per-instance team ADMM on the same T instances (T, NS = the device's three tile variants): prep + niter iterations +
 // adaptive-rho move.  x, v: [T][NU], [T][mc] warm start in (ignored when cold), results out (ref_* per-instance code,
 // tile_* tile code); res [T][4]; lvl [T] in/out.
