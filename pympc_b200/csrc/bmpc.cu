@@ -513,9 +513,10 @@ struct TpiPolArgs {
     int32_t* next_list; int32_t* counts; // counts[0] unfinished (-> next_list), [1] refinements; counts[4..7] queue control, see below
     int32_t* queue;                      // phase-B queue, all -1 between launches (consumers clear what they take)
     double* u0_out; double* um1_solved;
+    int emit_v;                          // 1: verified instances also write v* (the next solve runs ADMM iterations first)
     unsigned char* codes; int code_stride;   // per instance: Np working-set codes + the multiplier scale (double) of the last refinement
 };
-enum { TPI_Q_CURSOR = 4, TPI_Q_TAIL = 5, TPI_Q_HEAD = 6, TPI_Q_DONE = 7 };
+enum { TPI_Q_CURSOR = 4, TPI_Q_HEAD = 5, TPI_Q_TAIL = 6 };   // counts[6..7]: one 64-bit word, low = reserved queue tail, high = finished chunks
 constexpr int TPI_POL_WARPS = 7;
 
 template <class S>
@@ -602,40 +603,53 @@ __device__ __forceinline__ void tpi_pol_batch(const TpiPolParams<S>& P, const Bm
 #pragma unroll
     for (int sft = 16; sft > 0; sft >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, sft);
     if (lane == 0 && tot) atomicAdd(A.counts + 1, tot);
-    const unsigned okmask = __ballot_sync(0xffffffffu, ok);
-    __syncwarp();
-    // v* = exact ADMM fixed point of this problem (warm start of a later ADMM round): staged in the consumed gain slots
-    if (inst0_contig >= 0) {
-        double* dst = I.vw + (size_t)inst0_contig * S::mc;
-#pragma unroll 5
-        for (int idx = lane; idx < nvalid * S::mc; idx += 32) {
-            const int t = idx / S::mc, g = idx - t * S::mc;
-            if (!((okmask >> t) & 1u) || g == S::mc - 1) continue;
-            dst[idx] = (g < nx) ? I.x0[(size_t)(inst0_contig + t) * nx + g] : wsm[tpi_vstar_slot<S>(g - nx) * TPI_STR + t];
-        }
-        if (ok) I.vw[(size_t)inst * S::mc + S::mc - 1] = vq;
-    } else if (ok) {
-        double* dst = I.vw + (size_t)inst * S::mc;
-        for (int i = 0; i < L::VROWS; i++) dst[nx + i] = W(tpi_vstar_slot<S>(i));
-        dst[S::mc - 1] = vq;
-#pragma unroll
-        for (int q = 0; q < nx; q++) dst[q] = x0[q];
-    }
     // unfinished lanes: to the queue of phase B (their working sets must be visible first) or to the host's list
-    const bool fail = valid && !ok && I.status[inst] != BMPC_PRIMAL_INFEASIBLE;
+    const bool fail = valid && !ok && (reset || I.status[inst] != BMPC_PRIMAL_INFEASIBLE);
     const unsigned fmask = __ballot_sync(0xffffffffu, fail);
-    if (fmask) {
-        const int nf = __popc(fmask), pos = __popc(fmask & ((1u << lane) - 1u));
+    const int nf = __popc(fmask), pos = __popc(fmask & ((1u << lane) - 1u));
+    if (to_queue) {
+        // one 64-bit atomic publishes "nf more entries reserved" and "one more chunk of phase A finished" together, so a
+        // consumer that reads the word sees a tail that is final once the chunk count is complete
+        if (fmask) __threadfence();
+        unsigned long long old = 0ull;
+        if (lane == 0) old = atomicAdd((unsigned long long*)(A.counts + TPI_Q_TAIL), (1ull << 32) | (unsigned long long)nf);
+        const int basep = (int)(unsigned)__shfl_sync(0xffffffffu, old, 0);
+        if (fail) ((volatile int32_t*)A.queue)[basep + pos] = inst;
+    } else if (fmask) {
         int basep = 0;
-        if (to_queue) {
-            __threadfence();
-            if (lane == 0) basep = atomicAdd(A.counts + TPI_Q_TAIL, nf);
-            basep = __shfl_sync(0xffffffffu, basep, 0);
-            if (fail) ((volatile int32_t*)A.queue)[basep + pos] = inst;
-        } else {
-            if (lane == 0) basep = atomicAdd(A.counts, nf);
-            basep = __shfl_sync(0xffffffffu, basep, 0);
-            if (fail) A.next_list[basep + pos] = inst;
+        if (lane == 0) basep = atomicAdd(A.counts, nf);
+        basep = __shfl_sync(0xffffffffu, basep, 0);
+        if (fail) {
+            A.next_list[basep + pos] = inst;
+            // the last candidate as an ADMM state v = z + mu / rho (primal rows and multipliers of the polish): the straggler
+            // rounds of the host loop start their ADMM chunk from it
+            double* dst = I.vw + (size_t)inst * S::mc;
+            for (int i = 0; i < L::VROWS; i++) dst[nx + i] = W(tpi_vstar_slot<S>(i));
+            dst[S::mc - 1] = vq;
+#pragma unroll
+            for (int q = 0; q < nx; q++) dst[q] = x0[q];
+        }
+    }
+    const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+    if (A.emit_v && okmask) {
+        // v* = exact ADMM fixed point of this problem, staged in the consumed gain slots: written only when the next solve will
+        // run ADMM iterations first (first_iters > 0); a warm solve without ADMM never reads it
+        __syncwarp();
+        if (inst0_contig >= 0) {
+            double* dst = I.vw + (size_t)inst0_contig * S::mc;
+#pragma unroll 5
+            for (int idx = lane; idx < nvalid * S::mc; idx += 32) {
+                const int t = idx / S::mc, g = idx - t * S::mc;
+                if (!((okmask >> t) & 1u) || g == S::mc - 1) continue;
+                dst[idx] = (g < nx) ? I.x0[(size_t)(inst0_contig + t) * nx + g] : wsm[tpi_vstar_slot<S>(g - nx) * TPI_STR + t];
+            }
+            if (ok) I.vw[(size_t)inst * S::mc + S::mc - 1] = vq;
+        } else if (ok) {
+            double* dst = I.vw + (size_t)inst * S::mc;
+            for (int i = 0; i < L::VROWS; i++) dst[nx + i] = W(tpi_vstar_slot<S>(i));
+            dst[S::mc - 1] = vq;
+#pragma unroll
+            for (int q = 0; q < nx; q++) dst[q] = x0[q];
         }
     }
     __syncwarp();
@@ -659,24 +673,23 @@ __global__ void __launch_bounds__(TPI_POL_WARPS * 32, 1) k_tpi_pol(const __grid_
         const bool valid = lane < nvalid;
         const int inst = A.list ? (valid ? A.list[idx0 + lane] : 0) : idx0 + lane;
         tpi_pol_batch<S, TV>(P, I, A, wsm, csm, inst, valid, A.list ? -1 : idx0, nvalid, A.mode, A.capA, A.capB > 0, A.reset);
-        __threadfence();
-        if (lane == 0) atomicAdd(A.counts + TPI_Q_DONE, 1);
     }
     if (A.capB <= 0) return;
     // ---- phase B: serve the queue until every chunk of phase A is finished and the queue is empty
-    volatile int32_t* ctl = (volatile int32_t*)A.counts;
+    volatile unsigned long long* ctl = (volatile unsigned long long*)(A.counts + TPI_Q_TAIL);
+    volatile int32_t* headp = (volatile int32_t*)(A.counts + TPI_Q_HEAD);
     for (;;) {
         int h = 0, n = 0;
         if (lane == 0) {
-            const bool all_done = ctl[TPI_Q_DONE] >= nchunks;      // read BEFORE the tail: a tail read after it is final
-            __threadfence();
-            h = ctl[TPI_Q_HEAD]; const int t = ctl[TPI_Q_TAIL];
+            const unsigned long long w = *ctl;                      // tail (low word) and finished chunks (high word) in one read
+            const int t = (int)(unsigned)w; const bool all_done = (int)(w >> 32) >= nchunks;
+            h = *headp;
             if (h < t) { n = (t - h) < 32 ? (t - h) : 32; if (atomicCAS(A.counts + TPI_Q_HEAD, h, h + n) != h) n = -1; }
             else n = all_done ? 0 : -1;
         }
         h = __shfl_sync(0xffffffffu, h, 0); n = __shfl_sync(0xffffffffu, n, 0);
         if (n == 0) break;
-        if (n < 0) { __nanosleep(200); continue; }
+        if (n < 0) { __nanosleep(400); continue; }
         const bool valid = lane < n;
         int inst = 0;
         if (valid) {
@@ -755,7 +768,7 @@ static void launch_tpi_pol(bmpc_handle* h, const int32_t* list, int count, int m
     TpiPolArgs A;
     A.list = list; A.count = count; A.mode = mode; A.capA = capA; A.capB = capB; A.reset = reset;
     A.next_list = next_list; A.counts = h->counts; A.queue = h->queue; A.u0_out = h->I.u0; A.um1_solved = h->um1_solved;
-    A.codes = h->codes; A.code_stride = L::code_stride;
+    A.codes = h->codes; A.code_stride = L::code_stride; A.emit_v = h->cfg.first_iters > 0 ? 1 : 0;
     const int nchunks = (count + 31) / 32;
     int grid = (nchunks + TPI_POL_WARPS - 1) / TPI_POL_WARPS;
     if (grid > h->sm_count) grid = h->sm_count;
@@ -1167,6 +1180,9 @@ static int enqueue_round(bmpc_handle* h) {
     // latency-bound and go to the CTA-per-instance team kernels
     const bool tpi_ok = h->tpi_kind != 0;
     const bool tpi = st.round == 0 && tpi_ok && h->cfg.polish;
+    // straggler rounds read u_-1 from the snapshot the first round took: bmpc_output may already have queued the commit of
+    // this solve's u0 into um1 (speculating that the first round finishes everything)
+    h->I.um1 = st.round > 0 ? h->um1_solved : h->um1;
     if (!tpi) {
         if (st.round == 0) {
             const int B = h->cfg.batch;
@@ -1196,6 +1212,7 @@ static int enqueue_round(bmpc_handle* h) {
         else if (h->cfg.polish) launch_polish(h, st.list, st.count, st.nxt, h->counts);
         else { k_check_converged<<<(st.count + 255) / 256, 256, 0, h->stream>>>(h->I, st.list, st.count, h->cfg.eps_abs, h->cfg.eps_rel, st.nxt, h->counts); h->stats.launches++; }
     }
+    h->I.um1 = h->um1;
     BMPC_CUDA(cudaEventRecord(h->ev[2], h->stream));
     BMPC_CUDA(cudaMemcpyAsync(h->h_count, h->counts, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, h->stream));
     BMPC_CUDA(cudaGetLastError());
@@ -1275,16 +1292,22 @@ int bmpc_output(bmpc_handle* h, double* u0, int32_t* status, int commit_uminus1,
         if (want_u) BMPC_CUDA(cudaMemcpyAsync(u0, h->I.u0, sizeof(double) * B * d.nu, kind, h->stream));
         return BMPC_OK;
     };
-    bool u_copied = false;
+    bool u_copied = false, committed = false;
+    auto commit = [&]() -> int {
+        if (commit_uminus1) BMPC_CUDA(cudaMemcpyAsync(h->um1, h->I.u0, sizeof(double) * B * d.nu, cudaMemcpyDeviceToDevice, h->stream));
+        return BMPC_OK;
+    };
     if (h->pending) {
-        // speculate that the round in flight finishes everything (the common case): queue the result copy behind it so
-        // that a single wait covers the solve and the read-back; redo it if stragglers needed more rounds
-        if (!on_device && !commit_uminus1) { int rc = copy_u(); if (rc) return rc; u_copied = true; }
+        // speculate that the round in flight finishes everything (the common case): queue the result copy and the commit of
+        // u_-1 behind it so that a single wait covers the solve and the read-back and the stream never idles while the host
+        // wakes up; both are redone if stragglers needed more rounds (they rewrite u0)
+        if (!on_device) { int rc = copy_u(); if (rc) return rc; u_copied = true; }
+        { int rc = commit(); if (rc) return rc; committed = true; }
         int more = 0; int rc = retire_round(h, &more); if (rc) return rc;
-        if (more) { u_copied = false; rc = finish_solve(h); if (rc) return rc; }
-        else if (h->stats.launches && (h->st.count > 0 || !h->cfg.polish)) u_copied = false;   // k_finalize rewrote u0/status
+        if (more) { u_copied = false; committed = false; rc = finish_solve(h); if (rc) return rc; }
+        else if (h->stats.launches && (h->st.count > 0 || !h->cfg.polish)) { u_copied = false; committed = false; }   // k_finalize rewrote u0/status
     }
-    if (commit_uminus1) BMPC_CUDA(cudaMemcpyAsync(h->um1, h->I.u0, sizeof(double) * B * d.nu, cudaMemcpyDeviceToDevice, h->stream));
+    if (!committed) { int rc = commit(); if (rc) return rc; }
     // every instance KKT-verified and none certified infeasible: the status array is all BMPC_SOLVED, no need to fetch it
     const bool all_solved = h->cfg.polish && h->stats.unsolved == 0 && h->stats.infeasible == 0;
     bool need_sync = false;

@@ -35,7 +35,6 @@ struct TpiShape {
     static constexpr int MT = NS + NU + ND;
     static constexpr int NX = (NPc + 1) * NXc;
     static constexpr int mc = NX + NU + ND;
-    static constexpr int PROWS = (MT > 6 * NPc ? MT : 6 * NPc) + 1;   // polish workspace rows: v (load) / Riccati gains
 };
 
 template <class S>
@@ -289,288 +288,6 @@ BMPC_HD void tpi_admm(const TpiAdmmParams<S>& P, TpiAcc V, TpiAcc G, const doubl
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Working sets of one instance, split by row class so that the horizon loops read / write a whole stage with one
-// shift (profiles/: per-row 64-bit variable shifts were 28 % of the polish instructions):
-//   x : state rows, bit (k*nx + a) <-> row of x_{k+1}[a]   (Np*nx <= 128 bits)
-//   u : input rows, bit j < Nc;   d : delta-u rows, bit rr (rr = 0..Nc; rr = Nc is the reference's spurious last row)
-struct TpiSets {
-    unsigned long long xl, xh;
-    unsigned u, d;
-    BMPC_HD TpiSets() : xl(0ull), xh(0ull), u(0u), d(0u) {}
-};
-// n (<= 8) state-row bits starting at bit position pos
-BMPC_HD unsigned tpi_xget(const TpiSets& s, int pos, int n) {
-    unsigned long long v;
-    if (pos >= 64) v = s.xh >> (pos - 64);
-    else { v = s.xl >> pos; if (pos + n > 64) v |= s.xh << (64 - pos); }
-    return (unsigned)v & ((1u << n) - 1u);
-}
-BMPC_HD void tpi_xput(TpiSets& s, int pos, int n, unsigned bits) {
-    const unsigned long long b = bits;
-    if (pos >= 64) s.xh |= b << (pos - 64);
-    else { s.xl |= b << pos; if (pos + n > 64) s.xh |= b >> (64 - pos); }
-}
-
-// initial working sets from the ADMM iterate v (rows sitting on a bound to rounding level stay out of the first guess)
-template <class S, class Acc>
-BMPC_HD void tpi_sets_from_v(const TpiCommon<S>& c, const double* um1, Acc V, TpiSets& up, TpiSets& dn) {
-    constexpr int nx = S::nx, Np = S::Np, NS = S::NS, NU = S::NU;
-    static_assert(S::nu == 1 && S::Nc <= S::Np && S::NS <= 128 && S::Np < 32, "TPI sets: nu == 1, Nc <= Np, Np*nx <= 128");
-    constexpr int Nc = S::Nc;
-    auto over = [](double v, double hi) { return v > hi + 1e-9 * (1.0 + fabs(hi)); };
-    auto under = [](double v, double lo) { return v < lo - 1e-9 * (1.0 + fabs(lo)); };
-#pragma unroll 1
-    for (int k = 0; k < Np; k++) {
-        unsigned bu = 0u, bd = 0u;
-#pragma unroll
-        for (int a = 0; a < nx; a++) {
-            const double v = V(k * nx + a);
-            bu |= (over(v, c.xmax[a]) ? 1u : 0u) << a; bd |= (under(v, c.xmin[a]) ? 1u : 0u) << a;
-        }
-        tpi_xput(up, k * nx, nx, bu); tpi_xput(dn, k * nx, nx, bd);
-        if (k >= Nc) continue;                              // held stages (Nc < Np) have no input / delta-u rows
-        const double vu = V(NS + k);
-        up.u |= (over(vu, c.umax[0]) ? 1u : 0u) << k; dn.u |= (under(vu, c.umin[0]) ? 1u : 0u) << k;
-        const double vd = V(NS + NU + k), sh = (k == 0) ? um1[0] : 0.0;
-        up.d |= (over(vd, c.dmax[0] + sh) ? 1u : 0u) << k; dn.d |= (under(vd, c.dmin[0] + sh) ? 1u : 0u) << k;
-    }
-    const double vq = V(NS + NU + Nc);
-    up.d |= (over(vq, c.dmax[0]) ? 1u : 0u) << Nc; dn.d |= (under(vq, c.dmin[0]) ? 1u : 0u) << Nc;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Riccati polish (nu == 1; Nc < Np: the stages k >= Nc hold the last input, i.e. are pinned to u_k = u_{k-1} without a
-// row or a multiplier): the equality-constrained QP of one active-set step is an LQ problem
-//   min sum_k [ 1/2 x_k' Qt_k x_k - qt_k' x_k ] + sum_j [ 1/2 Qu u_j^2 - Qu uref u_j + 1/2 QDu (u_j - u_{j-1})^2 ]
-//   s.t. x_{k+1} = Ad x_k + Bd u_k,  some inputs pinned (u_j = bound, or u_j = u_{j-1} + delta)
-// where violated soft rows enter through Qt_k = Q_k + eps_feas diag(mask_k), qt_k = Q_k xref + eps_feas mask_k.*bound.
-// It is solved exactly by one backward sweep on the augmented state xi = [x ; u_prev] (cost-to-go 1/2 xi'P xi + p'xi)
-// and one forward sweep; multipliers of pinned inputs are -dQ/du of the stage Q-function.  Work and storage are
-// O(Np) and independent of the size of the working set (the Schur form needs an r x r factor per instance).
-// Workspace: 6 rows per stage: free stage -> feedback (k[nx+1], kappa); pinned stage -> (m[nx+1], m0) with dQ/du = m'xi + m0.
-template <class S>
-struct TpiRicParams {
-    TpiCommon<S> c;
-    double Qx[S::nx * S::nx], QxN[S::nx * S::nx];
-    double Qu, QDu, uref, rho_e;
-};
-
-enum { TPI_FREE = 0, TPI_UPIN = 1, TPI_DPIN = 2, TPI_QPIN = 3 };
-
-// pin of stage j implied by the working set (priority: input bound, then delta-u row, then the reference's
-// spurious last row  Dumin <= -u_{N-1} <= Dumax)
-template <class S>
-BMPC_HD int tpi_pin_of(const TpiCommon<S>& c, const TpiSets& up, const TpiSets& dn, int j, double& val) {
-    constexpr int N = S::Nc;                                          // decision inputs; stages j >= Nc hold u_{Nc-1}
-    if (j >= N) { val = 0.0; return TPI_DPIN; }                         // held stage: u_j = u_{j-1}, no row, no multiplier
-    if ((up.u >> j) & 1u) { val = c.umax[0]; return TPI_UPIN; }
-    if ((dn.u >> j) & 1u) { val = c.umin[0]; return TPI_UPIN; }
-    if ((up.d >> j) & 1u) { val = c.dmax[0]; return TPI_DPIN; }
-    if ((dn.d >> j) & 1u) { val = c.dmin[0]; return TPI_DPIN; }
-    if (j == N - 1) {
-        if ((up.d >> N) & 1u) { val = -c.dmax[0]; return TPI_QPIN; }     // -u = Dumax
-        if ((dn.d >> N) & 1u) { val = -c.dmin[0]; return TPI_QPIN; }
-    }
-    val = 0.0; return TPI_FREE;
-}
-
-template <class S, class XR>
-BMPC_HD void tpi_ric_backward(const TpiRicParams<S>& P, TpiAcc W, XR xr, const TpiSets& up, const TpiSets& dn) {
-    static_assert(S::nu == 1 && S::Nc <= S::Np, "Riccati polish is specialised to nu == 1");
-    constexpr int nx = S::nx, N = S::Np, nz = nx + 1;
-    const TpiCommon<S>& c = P.c;
-    // cost-to-go of stage k+1:  Pxx (sym, full storage), pxw, pww, px, pw
-    double Pxx[nx * nx], pxw[nx], px[nx], pww = 0.0, pw = 0.0;
-    // terminal: state cost of x_N
-    {
-        const unsigned bu = tpi_xget(up, (N - 1) * nx, nx), bd = tpi_xget(dn, (N - 1) * nx, nx);
-#pragma unroll
-        for (int a = 0; a < nx; a++) {
-            const bool vu = (bu >> a) & 1u, vd = (bd >> a) & 1u;
-            double q = 0.0;
-#pragma unroll
-            for (int b = 0; b < nx; b++) { Pxx[a * nx + b] = P.QxN[a * nx + b]; q += P.QxN[a * nx + b] * xr(N, b); }
-            if (vu || vd) { Pxx[a * nx + a] += P.rho_e; q += P.rho_e * (vu ? c.xmax[a] : c.xmin[a]); }
-            px[a] = -q; pxw[a] = 0.0;
-        }
-    }
-#pragma unroll 1
-    for (int k = N - 1; k >= 0; k--) {
-        // T = Pxx A ; AtPA = A' T ; PB = Pxx B
-        double T[nx * nx], PB[nx];
-#pragma unroll
-        for (int a = 0; a < nx; a++) {
-#pragma unroll
-            for (int b = 0; b < nx; b++) {
-                double acc = 0.0;
-#pragma unroll
-                for (int q = 0; q < nx; q++) acc += Pxx[a * nx + q] * c.Ad[q * nx + b];
-                T[a * nx + b] = acc;
-            }
-            double accb = 0.0;
-#pragma unroll
-            for (int q = 0; q < nx; q++) accb += Pxx[a * nx + q] * c.Bd[q];
-            PB[a] = accb;
-        }
-        double Hxx[nx * nx], hx[nx], gx[nx];       // x-part of Hxx / hxu / gx ; the w-part is (QDu, -QDu, 0)
-        double huu = pww + P.Qu + P.QDu, gu = pw - P.Qu * P.uref;
-#pragma unroll
-        for (int a = 0; a < nx; a++) { huu += c.Bd[a] * (PB[a] + 2.0 * pxw[a]); gu += c.Bd[a] * px[a]; }
-#pragma unroll
-        for (int a = 0; a < nx; a++) {
-#pragma unroll
-            for (int b = 0; b < nx; b++) {
-                double acc = 0.0;
-#pragma unroll
-                for (int q = 0; q < nx; q++) acc += c.Ad[q * nx + a] * T[q * nx + b];
-                Hxx[a * nx + b] = acc;
-            }
-            double h = 0.0, g = 0.0;
-#pragma unroll
-            for (int q = 0; q < nx; q++) { h += c.Ad[q * nx + a] * (PB[q] + pxw[q]); g += c.Ad[q * nx + a] * px[q]; }
-            hx[a] = h; gx[a] = g;
-        }
-        if (k >= 1) {                              // stage cost of x_k (x_0 is data)
-            const unsigned bu = tpi_xget(up, (k - 1) * nx, nx), bd = tpi_xget(dn, (k - 1) * nx, nx);
-#pragma unroll
-            for (int a = 0; a < nx; a++) {
-                const bool vu = (bu >> a) & 1u, vd = (bd >> a) & 1u;
-                double q = 0.0;
-#pragma unroll
-                for (int b = 0; b < nx; b++) { Hxx[a * nx + b] += P.Qx[a * nx + b]; q += P.Qx[a * nx + b] * xr(k, b); }
-                if (vu || vd) { Hxx[a * nx + a] += P.rho_e; q += P.rho_e * (vu ? c.xmax[a] : c.xmin[a]); }
-                gx[a] -= q;
-            }
-        }
-        double hw = -P.QDu, Hww = P.QDu, gw = 0.0;   // w-parts:  hxu = [hx ; hw], Hxx_full = blkdiag(Hxx, Hww), gx_full = [gx ; gw]
-        double pin; const int type = tpi_pin_of<S>(c, up, dn, k, pin);
-        const int base = k * (nz + 1);
-        if (type == TPI_FREE) {
-            const double inv = 1.0 / huu;
-#pragma unroll
-            for (int a = 0; a < nx; a++) W(base + a) = hx[a] * inv;
-            W(base + nx) = hw * inv; W(base + nz) = gu * inv;
-            // P = Hxx - hxu hxu'/huu ; p = gx - hxu gu/huu
-#pragma unroll
-            for (int a = 0; a < nx; a++) {
-#pragma unroll
-                for (int b = 0; b < nx; b++) Pxx[a * nx + b] = Hxx[a * nx + b] - hx[a] * hx[b] * inv;
-                pxw[a] = -hx[a] * hw * inv; px[a] = gx[a] - hx[a] * gu * inv;
-            }
-            pww = Hww - hw * hw * inv; pw = gw - hw * gu * inv;
-        } else if (type == TPI_DPIN) {
-            // u = w + pin :  dQ/du = hx'x + (hw + huu) w + huu pin + gu
-#pragma unroll
-            for (int a = 0; a < nx; a++) W(base + a) = hx[a];
-            W(base + nx) = hw + huu; W(base + nz) = huu * pin + gu;
-#pragma unroll
-            for (int a = 0; a < nx; a++) {
-#pragma unroll
-                for (int b = 0; b < nx; b++) Pxx[a * nx + b] = Hxx[a * nx + b];
-                pxw[a] = hx[a]; px[a] = gx[a] + hx[a] * pin;
-            }
-            pww = Hww + 2.0 * hw + huu; pw = gw + hw * pin + huu * pin + gu;
-        } else {
-            // u = pin :  dQ/du = hx'x + hw w + huu pin + gu
-#pragma unroll
-            for (int a = 0; a < nx; a++) W(base + a) = hx[a];
-            W(base + nx) = hw; W(base + nz) = huu * pin + gu;
-#pragma unroll
-            for (int a = 0; a < nx; a++) {
-#pragma unroll
-                for (int b = 0; b < nx; b++) Pxx[a * nx + b] = Hxx[a * nx + b];
-                pxw[a] = 0.0; px[a] = gx[a] + hx[a] * pin;
-            }
-            pww = Hww; pw = gw + hw * pin;
-        }
-    }
-}
-
-// Forward sweep.  MODE 0: KKT verification only: returns ok and the next working set (nup, ndn), updates mumax.
-// MODE 1: emit only: out(i, zi, mu_i, 1/rho_i) for every TPI row and outu(j, u_j) for every input.
-// MODE 2: both in one pass (the emitted values are meaningful only if the pass returns ok).
-template <class S, int MODE, class FR, class FU>
-BMPC_HD bool tpi_ric_forward(const TpiRicParams<S>& P, TpiAcc W, const double* x0, const double* um1, const TpiSets& up,
-                             const TpiSets& dn, TpiSets& nup, TpiSets& ndn, double& mumax, FR out, FU outu) {
-    constexpr int nx = S::nx, N = S::Np, Nc = S::Nc, nz = nx + 1, NS = S::NS, NU = S::NU;
-    const TpiCommon<S>& c = P.c;
-    constexpr bool EMIT = (MODE >= 1), VERIFY = (MODE != 1);
-    const double mutol = 1e-9 * (1.0 + mumax);
-    double mnew = 0.0;
-    bool ok = true;
-    double x[nx], w = um1[0];
-#pragma unroll
-    for (int a = 0; a < nx; a++) x[a] = x0[a];
-    // hard row: KKT check of one row, returns its bits of the next working set (bit0 = up, bit1 = dn)
-    auto hard_row = [&](int i, bool su, bool sd, double zi, double lo, double hi, double mu, double irho) -> unsigned {
-        if (EMIT) out(i, zi, mu, irho);
-        if (!VERIFY) return 0u;
-        const bool vu = zi > hi + 1e-9 * (1.0 + fabs(hi)), vd = zi < lo - 1e-9 * (1.0 + fabs(lo));
-        if (vu || vd || (su && mu < -mutol) || (sd && mu > mutol)) ok = false;
-        const bool nu_ = vu || (!vd && su && mu > 0.0);
-        const bool nd_ = (!nu_) && (vd || (sd && mu < 0.0));
-        return (nu_ ? 1u : 0u) | (nd_ ? 2u : 0u);
-    };
-#pragma unroll 1
-    for (int k = 0; k < N; k++) {
-        double pin; const int type = tpi_pin_of<S>(c, up, dn, k, pin);
-        const int base = k * (nz + 1);
-        double lin = W(base + nz);
-#pragma unroll
-        for (int a = 0; a < nx; a++) lin += W(base + a) * x[a];
-        lin += W(base + nx) * w;
-        double u, mu_u = 0.0, mu_d = 0.0, mu_q = 0.0;
-        if (type == TPI_FREE) u = -lin;
-        else if (type == TPI_UPIN) { u = pin; mu_u = -lin; }
-        else if (type == TPI_DPIN) { u = w + pin; mu_d = -lin; }
-        else { u = pin; mu_q = lin; }
-        if (k < Nc) {                                        // held stages (k >= Nc) own no input / delta-u rows
-            mnew = fmax(mnew, fmax(fabs(mu_u), fmax(fabs(mu_d), fabs(mu_q))));
-            if (EMIT) outu(k, u);
-            unsigned hb = hard_row(NS + k, (up.u >> k) & 1u, (dn.u >> k) & 1u, u, c.umin[0], c.umax[0], mu_u, c.irhou[0]);
-            nup.u |= (hb & 1u) << k; ndn.u |= (hb >> 1) << k;
-            const double sh = (k == 0) ? w : 0.0;           // row 0: value u_0, bounds shifted by u_-1; else u_k - u_{k-1}
-            hb = hard_row(NS + NU + k, (up.d >> k) & 1u, (dn.d >> k) & 1u, (k == 0) ? u : u - w, c.dmin[0] + sh, c.dmax[0] + sh, mu_d, c.irhod[0]);
-            nup.d |= (hb & 1u) << k; ndn.d |= (hb >> 1) << k;
-            if (k == Nc - 1) {
-                hb = hard_row(NS + NU + Nc, (up.d >> Nc) & 1u, (dn.d >> Nc) & 1u, -u, c.dmin[0], c.dmax[0], mu_q, c.irhod[0]);
-                nup.d |= (hb & 1u) << Nc; ndn.d |= (hb >> 1) << Nc;
-            }
-        }
-        double xn[nx];
-#pragma unroll
-        for (int a = 0; a < nx; a++) {
-            double a0 = c.Bd[a] * u, a1 = 0.0;
-#pragma unroll
-            for (int q = 0; q < nx; q += 2) { a0 += c.Ad[a * nx + q] * x[q]; if (q + 1 < nx) a1 += c.Ad[a * nx + q + 1] * x[q + 1]; }
-            xn[a] = a0 + a1;
-        }
-        w = u;
-        const unsigned bu = tpi_xget(up, k * nx, nx), bd = tpi_xget(dn, k * nx, nx);
-        unsigned nbu = 0u, nbd = 0u;
-#pragma unroll
-        for (int a = 0; a < nx; a++) {
-            x[a] = xn[a];
-            const double zi = xn[a], lo = c.xmin[a], hi = c.xmax[a];
-            const bool su = (bu >> a) & 1u, sd = (bd >> a) & 1u;
-            if (EMIT) out(k * nx + a, zi, su ? P.rho_e * (zi - hi) : (sd ? P.rho_e * (zi - lo) : 0.0), c.irhox[a]);
-            if (!VERIFY) continue;
-            const bool nu_ = zi > hi + 1e-11 * (1.0 + fabs(hi)), nd_ = (!nu_) && zi < lo - 1e-11 * (1.0 + fabs(lo));
-            if (nu_ != su || nd_ != sd) {
-                const bool hi_side = (su || nu_) && !(sd || nd_), lo_side = (sd || nd_) && !(su || nu_);
-                const double gap = hi_side ? fabs(zi - hi) : (lo_side ? fabs(zi - lo) : 1e300);
-                const double bnd = hi_side ? hi : lo;
-                if (!(gap <= 1e-11 * (1.0 + fabs(bnd)))) ok = false;
-            }
-            nbu |= (nu_ ? 1u : 0u) << a; nbd |= (nd_ ? 1u : 0u) << a;
-        }
-        if (VERIFY) { tpi_xput(nup, k * nx, nx, nbu); tpi_xput(ndn, k * nx, nx, nbd); }
-    }
-    mumax = mnew;
-    return ok;
-}
-
 // Where the forward sweep stages row i of the exact ADMM fixed point v* inside the (already consumed) gain slots of the
 // column: stage k owns slots [k*(nx+2), (k+1)*(nx+2)) = its nx state rows, its input row, its delta-u row; the reference's
 // spurious last delta-u row goes to the spare slot behind the last stage.
@@ -581,24 +298,6 @@ BMPC_HD int tpi_vstar_slot(int i) {
     if (i < S::NS + S::NU) return (i - S::NS) * nz1 + S::nx;
     const int rr = i - S::NS - S::NU;
     return rr < S::Nc ? rr * nz1 + S::nx + 1 : S::Np * nz1;
-}
-
-// returns steps used (>0) when KKT-verified, 0 otherwise.  Every forward sweep verifies AND emits through out / outu (row
-// values v* = z* + y*/rho, inputs u_j): the values of the accepted (last) sweep are the solution, earlier ones are
-// overwritten, so no separate emit pass is needed.
-template <class S, class XR, class FR, class FU>
-BMPC_HD int tpi_polish_riccati(const TpiRicParams<S>& P, TpiAcc W, const double* x0, const double* um1, XR xr,
-                               TpiSets& up, TpiSets& dn, int max_steps, FR out, FU outu) {
-    double mumax = 0.0;
-#pragma unroll 1
-    for (int step = 0; step < max_steps; step++) {
-        tpi_ric_backward<S>(P, W, xr, up, dn);
-        TpiSets nup, ndn;
-        const bool ok = tpi_ric_forward<S, 2>(P, W, x0, um1, up, dn, nup, ndn, mumax, out, outu);
-        if (ok) return step + 1;
-        up = nup; dn = ndn;
-    }
-    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -638,17 +337,20 @@ inline void tpi_fill_admm(const double* sys, const BmpcSysOff& o, TpiAdmmParams<
             P.Gcc[a * nx + q] = acc;
         }
 }
-template <class S>
-inline void tpi_fill_riccati(const double* sys, const BmpcSysOff& o, TpiRicParams<S>& P) {
-    tpi_fill_common<S>(sys, o, P.c);
-    for (int i = 0; i < S::nx * S::nx; i++) { P.Qx[i] = sys[o.Qx + i]; P.QxN[i] = sys[o.QxN + i]; }
-    P.Qu = sys[o.Qu]; P.QDu = sys[o.QDu]; P.uref = sys[o.uref]; P.rho_e = sys[o.scal + BMPC_S_RHOE];
-}
 
 // ================================================================================================
-// Second-generation Riccati polish (nu == 1): ONE active-set refinement = tpi2_backward + tpi2_forward.
+// Riccati polish (nu == 1; Nc < Np: the stages k >= Nc hold the last input, i.e. are pinned to u_k = u_{k-1} without a row
+// or a multiplier).  ONE active-set refinement = tpi2_backward + tpi2_forward: the equality-constrained QP of the step is the
+// LQ problem
+//   min sum_k [ 1/2 x_k' Qt_k x_k - qt_k' x_k ] + sum_j [ 1/2 Qu u_j^2 - Qu uref u_j + 1/2 QDu (u_j - u_{j-1})^2 ]
+//   s.t. x_{k+1} = Ad x_k + Bd u_k,  some inputs pinned (u_j = bound, or u_j = u_{j-1} + delta)
+// where violated soft rows enter through Qt_k = Q_k + eps_feas diag(mask_k), qt_k = Q_k xref + eps_feas mask_k.*bound.
+// It is solved exactly by one backward sweep on the augmented state xi = [x ; u_prev] (cost-to-go 1/2 xi'P xi + p'xi)
+// and one forward sweep; multipliers of pinned inputs are -dQ/du of the stage Q-function.  Work and storage are O(Np) and
+// independent of the size of the working set (the Schur form of the team kernels needs an r x r factor per instance).
+// Workspace: nx + 2 gain slots per stage: free stage -> feedback (k[nx+1], kappa); pinned -> (m[nx+1], m0), dQ/du = m'xi + m0.
 //
-// What changed against tpi_ric_backward / tpi_ric_forward above (profiles/ncu_r1_final_summary.txt: 23 % fp64 pipe, the
+// Second generation.  What changed against the round-1 sweeps (profiles/ncu_r1_final_summary.txt: 23 % fp64 pipe, the
 // forward sweep spent 4 instructions on set bookkeeping per fp64 instruction):
 //  * the working sets live as ONE small code word per stage (state rows up / down, input row, delta-u row, the spurious last
 //    row) in shared memory next to the gains, and between solves as 2 bytes per stage in global memory: a warm solve reads

@@ -84,23 +84,30 @@ static int emu_tpi_run(const double* sys, const double* x0, const double* um1, c
                            double* v, double* Uout, int first_iters, int pdas_steps) {
     const TpiXref<S, TV> xr{xref};
     BmpcDims d = bmpc_make_dims(S::nx, S::nu, S::Np, S::Nc); BmpcSysOff o = bmpc_make_off(d);
-    TpiAdmmParams<S>* PA = new TpiAdmmParams<S>(); TpiRicParams<S>* PR = new TpiRicParams<S>();
-    tpi_fill_admm<S>(sys, o, *PA); tpi_fill_riccati<S>(sys, o, *PR);
-    double* col = (double*)calloc(S::PROWS + S::MT + S::NU + 8, sizeof(double));
+    using CT = typename TpiCode<S>::type;
+    TpiAdmmParams<S>* PA = new TpiAdmmParams<S>(); TpiPolParams<S>* PR = new TpiPolParams<S>();
+    tpi_fill_admm<S>(sys, o, *PA); tpi_fill_pol<S>(sys, o, *PR);
+    double* col = (double*)calloc(S::Np * (S::nx + 2) + S::MT + S::NU + 8, sizeof(double));
     for (int i = 0; i < S::MT; i++) col[i] = v[i + S::nx];
     TpiAcc V{col, 1};
-    TpiAcc G{col + S::MT, 1};
+    TpiAcc G{col + S::Np * (S::nx + 2) + S::MT, 1};
     tpi_admm<S>(*PA, V, G, x0, um1, xr, x, first_iters, cold != 0);
     for (int i = 0; i < S::MT; i++) v[i + S::nx] = col[i];
     for (int i = 0; i < S::nx; i++) v[i] = x0[i];
-    TpiSets up, dn;
-    tpi_sets_from_v<S>(PR->c, um1, V, up, dn);
-    // the polish emits on every forward sweep; keep the values of the accepted one
-    double vstar[S::MT], Ustar[S::NU];
-    int ps = tpi_polish_riccati<S>(*PR, V, x0, um1, xr, up, dn, pdas_steps,
-        [&](int i, double zi, double mu, double irho) { vstar[i] = zi + mu * irho; },
-        [&](int j, double u) { Ustar[j] = u; });
+    CT cur[S::Np];
+    auto C = [&](int k) -> CT& { return cur[k]; };
+    tpi2_codes_from_v<S>(*PR, um1[0], V, col[S::MT - 1], C);
+    // the polish emits on every forward sweep; the values of the accepted one are the solution
+    double Ustar[S::NU], mumax = 0.0, vq = 0.0;
+    int ps = 0;
+    for (int r = 0; r < pdas_steps; r++) {
+        tpi2_backward<S>(*PR, V, C, xr);
+        if (tpi2_forward<S>(*PR, V, C, x0, um1[0], mumax, vq, [&](int j, double u) { Ustar[j] = u; })) { ps = r + 1; break; }
+    }
     if (ps > 0) {
+        double vstar[S::MT];
+        for (int i = 0; i < S::MT - 1; i++) vstar[i] = col[tpi_vstar_slot<S>(i)];
+        vstar[S::MT - 1] = vq;
         for (int i = 0; i < S::MT; i++) v[i + S::nx] = vstar[i];
         for (int j = 0; j < S::NU; j++) { Uout[j] = Ustar[j]; x[j] = Ustar[j]; }
     }
