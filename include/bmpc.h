@@ -109,6 +109,14 @@ int bmpc_bind_output(bmpc_handle* h, double* dev_u0);
  * peer's gathered [B_total, nu] buffer, e.g. torch symmetric-memory pointers): the epilogue's NVLink peer stores replace
  * the all-gather collective; the caller only needs a cross-rank barrier before reading.  n = 0 unbinds. */
 int bmpc_bind_output_peers(bmpc_handle* h, double* const* peer_u0, int n);
+/* K6 arrival: my_flags is this rank's DEVICE array of `world` int64 counters (zero-initialised), peer_flags[p] the same array
+ * of peer p as mapped into this process (symmetric memory).  bmpc_gather_arrive(epoch) launches one small kernel behind the
+ * solver kernels that stores `epoch` into slot `rank` of every peer's array and waits until every peer's slot here holds a
+ * value >= epoch: when it completes, every peer's u* of this step has landed in the buffer bound with bmpc_bind_output_peers.
+ * Epochs must increase by one per step on all ranks.  Use two gathered buffers alternately (step parity) so that the stores
+ * of step t+1 cannot overwrite data a slower peer is still reading from step t. */
+int bmpc_bind_gather_flags(bmpc_handle* h, int64_t* my_flags, int64_t* const* peer_flags, int n_peers, int rank, int world);
+int bmpc_gather_arrive(bmpc_handle* h, int64_t epoch);
 int bmpc_set_stream(bmpc_handle* h, void* cuda_stream);   /* NULL = handle-owned stream */
 int bmpc_synchronize(bmpc_handle* h);
 

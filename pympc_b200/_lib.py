@@ -28,7 +28,8 @@ class BmpcStats(ctypes.Structure):
 
 
 EXPORTS = ["bmpc_default_config", "bmpc_create", "bmpc_destroy", "bmpc_last_error", "bmpc_setup", "bmpc_update",
-           "bmpc_solve", "bmpc_output", "bmpc_get_sequences", "bmpc_bind_output", "bmpc_bind_output_peers", "bmpc_set_stream",
+           "bmpc_solve", "bmpc_output", "bmpc_get_sequences", "bmpc_bind_output", "bmpc_bind_output_peers", "bmpc_bind_gather_flags",
+           "bmpc_gather_arrive", "bmpc_set_stream",
            "bmpc_synchronize", "bmpc_get_stats", "bmpc_get_sys", "bmpc_get_dims", "bmpc_host_alloc",
            "bmpc_host_free", "bmpc_device_count", "bmpc_est_create", "bmpc_est_destroy", "bmpc_est_predict",
            "bmpc_est_update", "bmpc_est_get", "bmpc_est_state_ptr", "bmpc_est_set_stream"]
@@ -59,6 +60,8 @@ def load():
     L.bmpc_bind_output.argtypes = [P, DP]; L.bmpc_bind_output.restype = ctypes.c_int
     L.bmpc_set_stream.argtypes = [P, P]; L.bmpc_set_stream.restype = ctypes.c_int
     L.bmpc_bind_output_peers.argtypes = [P, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]; L.bmpc_bind_output_peers.restype = ctypes.c_int
+    L.bmpc_bind_gather_flags.argtypes = [P, P, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int]; L.bmpc_bind_gather_flags.restype = ctypes.c_int
+    L.bmpc_gather_arrive.argtypes = [P, ctypes.c_int64]; L.bmpc_gather_arrive.restype = ctypes.c_int
     L.bmpc_synchronize.argtypes = [P]; L.bmpc_synchronize.restype = ctypes.c_int
     L.bmpc_get_stats.argtypes = [P, ctypes.POINTER(BmpcStats)]; L.bmpc_get_stats.restype = ctypes.c_int
     L.bmpc_get_sys.argtypes = [P, ctypes.c_char_p, DP, ctypes.c_int]; L.bmpc_get_sys.restype = ctypes.c_int

@@ -131,6 +131,24 @@ __device__ __forceinline__ void bmpc_publish_u0(const BmpcInst& I, double* u0_ou
     for (int p = 0; p < I.n_peer; p++) I.u0_peer[p][idx] = val;
 }
 
+// K6, arrival: after the epilogue's peer stores, every rank raises its flag (= the step counter) in every peer's flag array
+// and waits until all peers have raised theirs here: when the kernel ends, the gathered buffer of this step is complete on
+// this rank.  One tiny launch instead of a collective; the flag stores are ordered behind the data stores of the solver
+// kernels by the stream and a system-scope fence.
+struct BmpcPeerFlags { long long* p[8]; };
+__global__ void k_gather_arrive(long long* mine, BmpcPeerFlags P, int n_peer, int rank, int world, long long epoch) {
+    const int t = threadIdx.x;
+    if (t < n_peer) { __threadfence_system(); *(volatile long long*)(P.p[t] + rank) = epoch; }
+    if (t < world && t != rank) {
+        const long long t0 = clock64();
+        while (*(volatile long long*)(mine + t) < epoch) {
+            if (clock64() - t0 > 20000000000ll) __trap();            // ~10 s: a peer died; fail loudly instead of hanging the GPU
+            __nanosleep(100);
+        }
+    }
+    __threadfence_system();
+}
+
 // smem (doubles) per instance for the two kernels — keep in sync with the carve-up below
 __host__ __device__ static inline size_t admm_smem_doubles(const BmpcDims& d) { return 4 * (size_t)d.NU + d.NX + 2 * (size_t)d.mc + d.nu + 4 + 4; }
 __host__ __device__ static inline size_t polish_smem_doubles(const BmpcDims& d, int rmax) {
@@ -513,7 +531,6 @@ struct TpiPolArgs {
     int32_t* next_list; int32_t* counts; // counts[0] unfinished (-> next_list), [1] refinements; counts[4..7] queue control, see below
     int32_t* queue;                      // phase-B queue, all -1 between launches (consumers clear what they take)
     double* u0_out; double* um1_solved;
-    int emit_v;                          // 1: verified instances also write v* (the next solve runs ADMM iterations first)
     unsigned char* codes; int code_stride;   // per instance: Np working-set codes + the multiplier scale (double) of the last refinement
 };
 enum { TPI_Q_CURSOR = 4, TPI_Q_HEAD = 5, TPI_Q_TAIL = 6 };   // counts[6..7]: one 64-bit word, low = reserved queue tail, high = finished chunks
@@ -619,37 +636,36 @@ __device__ __forceinline__ void tpi_pol_batch(const TpiPolParams<S>& P, const Bm
         int basep = 0;
         if (lane == 0) basep = atomicAdd(A.counts, nf);
         basep = __shfl_sync(0xffffffffu, basep, 0);
-        if (fail) {
-            A.next_list[basep + pos] = inst;
-            // the last candidate as an ADMM state v = z + mu / rho (primal rows and multipliers of the polish): the straggler
-            // rounds of the host loop start their ADMM chunk from it
+        if (fail) A.next_list[basep + pos] = inst;     // its ADMM rounds start from the exact fixed point v* of its last verified solve
+    }
+    // v* = z* + y*/rho, the exact ADMM fixed point of this problem, staged in the consumed gain slots by the forward sweep: the
+    // warm start of the ADMM rounds a later solve may need for this instance (measured: starting those rounds from the failed
+    // candidate instead costs 10x the rounds).  Verified lanes only.
+    const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+    if (okmask) {
+        __syncwarp();
+        if (ok) {
             double* dst = I.vw + (size_t)inst * S::mc;
-            for (int i = 0; i < L::VROWS; i++) dst[nx + i] = W(tpi_vstar_slot<S>(i));
-            dst[S::mc - 1] = vq;
 #pragma unroll
             for (int q = 0; q < nx; q++) dst[q] = x0[q];
+            dst[S::mc - 1] = vq;
         }
-    }
-    const unsigned okmask = __ballot_sync(0xffffffffu, ok);
-    if (A.emit_v && okmask) {
-        // v* = exact ADMM fixed point of this problem, staged in the consumed gain slots: written only when the next solve will
-        // run ADMM iterations first (first_iters > 0); a warm solve without ADMM never reads it
-        __syncwarp();
         if (inst0_contig >= 0) {
-            double* dst = I.vw + (size_t)inst0_contig * S::mc;
-#pragma unroll 5
-            for (int idx = lane; idx < nvalid * S::mc; idx += 32) {
-                const int t = idx / S::mc, g = idx - t * S::mc;
-                if (!((okmask >> t) & 1u) || g == S::mc - 1) continue;
-                dst[idx] = (g < nx) ? I.x0[(size_t)(inst0_contig + t) * nx + g] : wsm[tpi_vstar_slot<S>(g - nx) * TPI_STR + t];
+            // coalesced: for every verified instance t of the chunk the warp writes its rows 32 at a time (lane = row)
+            constexpr int NG = (L::VROWS + 31) / 32;
+            int soff[NG];
+#pragma unroll
+            for (int c = 0; c < NG; c++) { const int i = c * 32 + lane; soff[c] = (i < L::VROWS) ? tpi_vstar_slot<S>(i) * TPI_STR : -1; }
+            double* dst = I.vw + (size_t)inst0_contig * S::mc + nx + lane;
+#pragma unroll 4
+            for (int t = 0; t < nvalid; t++) {
+                if (!((okmask >> t) & 1u)) continue;
+#pragma unroll
+                for (int c = 0; c < NG; c++) if (soff[c] >= 0) dst[(size_t)t * S::mc + c * 32] = wsm[soff[c] + t];
             }
-            if (ok) I.vw[(size_t)inst * S::mc + S::mc - 1] = vq;
         } else if (ok) {
             double* dst = I.vw + (size_t)inst * S::mc;
             for (int i = 0; i < L::VROWS; i++) dst[nx + i] = W(tpi_vstar_slot<S>(i));
-            dst[S::mc - 1] = vq;
-#pragma unroll
-            for (int q = 0; q < nx; q++) dst[q] = x0[q];
         }
     }
     __syncwarp();
@@ -728,6 +744,7 @@ struct bmpc_handle {
     double *x0 = nullptr, *um1 = nullptr, *um1_solved = nullptr, *xref = nullptr, *u0_own = nullptr, *u0_bound = nullptr;
     double *seq_x = nullptr, *seq_e = nullptr, *seq_obj = nullptr;
     int32_t *listA = nullptr, *listB = nullptr, *counts = nullptr;  // counts[8]: [0..3] round counters, [4..7] queue control of k_tpi_pol
+    long long* gflags = nullptr; BmpcPeerFlags gpeers = {}; int g_npeer = 0, g_rank = 0, g_world = 1;   // K6 arrival flags
     int32_t* queue = nullptr; unsigned char* codes = nullptr;        // phase-B queue and stored working sets of the fast-path polish
     int32_t* h_count = nullptr;                                      // pinned
     cudaEvent_t ev[4];
@@ -768,7 +785,7 @@ static void launch_tpi_pol(bmpc_handle* h, const int32_t* list, int count, int m
     TpiPolArgs A;
     A.list = list; A.count = count; A.mode = mode; A.capA = capA; A.capB = capB; A.reset = reset;
     A.next_list = next_list; A.counts = h->counts; A.queue = h->queue; A.u0_out = h->I.u0; A.um1_solved = h->um1_solved;
-    A.codes = h->codes; A.code_stride = L::code_stride; A.emit_v = h->cfg.first_iters > 0 ? 1 : 0;
+    A.codes = h->codes; A.code_stride = L::code_stride;
     const int nchunks = (count + 31) / 32;
     int grid = (nchunks + TPI_POL_WARPS - 1) / TPI_POL_WARPS;
     if (grid > h->sm_count) grid = h->sm_count;
@@ -1035,6 +1052,8 @@ int bmpc_synchronize(bmpc_handle* h) {
 
 int bmpc_bind_output(bmpc_handle* h, double* dev_u0) {
     if (!h) return BMPC_ERR_ARG;
+    // kernels in flight captured the old pointer: retire them first (the committed u_-1 of that solve stays what it was)
+    if (h->pending) { cudaSetDevice(h->cfg.device); int rc = finish_solve(h); if (rc) return rc; }
     h->u0_bound = dev_u0;
     h->I.u0 = dev_u0 ? dev_u0 : h->u0_own;
     return BMPC_OK;
@@ -1045,6 +1064,23 @@ int bmpc_bind_output_peers(bmpc_handle* h, double* const* peer_u0, int n) {
     if (h->pending) { cudaSetDevice(h->cfg.device); int rc = finish_solve(h); if (rc) return rc; }
     h->I.n_peer = n;
     for (int p = 0; p < n; p++) h->I.u0_peer[p] = peer_u0[p];
+    return BMPC_OK;
+}
+
+int bmpc_bind_gather_flags(bmpc_handle* h, int64_t* my_flags, int64_t* const* peer_flags, int n_peers, int rank, int world) {
+    if (!h || n_peers < 0 || n_peers > 8 || world < 1 || world > 9 || rank < 0 || rank >= world || (n_peers > 0 && (!my_flags || !peer_flags))) return BMPC_ERR_ARG;
+    h->gflags = (long long*)my_flags; h->g_npeer = n_peers; h->g_rank = rank; h->g_world = world;
+    for (int p = 0; p < n_peers; p++) h->gpeers.p[p] = (long long*)peer_flags[p];
+    return BMPC_OK;
+}
+
+int bmpc_gather_arrive(bmpc_handle* h, int64_t epoch) {
+    if (!h) return BMPC_ERR_ARG;
+    if (!h->gflags) { h->err = "bmpc_gather_arrive before bmpc_bind_gather_flags"; return BMPC_ERR_STATE; }
+    BMPC_CUDA(cudaSetDevice(h->cfg.device));
+    if (h->pending) { int rc = finish_solve(h); if (rc) return rc; }
+    k_gather_arrive<<<1, 32, 0, h->stream>>>(h->gflags, h->gpeers, h->g_npeer, h->g_rank, h->g_world, (long long)epoch);
+    BMPC_CUDA(cudaGetLastError());
     return BMPC_OK;
 }
 

@@ -517,3 +517,23 @@ def test_fast_path_control_horizon_shorter_than_prediction(MPC):
     assert Ks[0].stats()["admm_iters"] < 10 * B
     for K in Ks:
         K.close()
+
+
+def test_multi_gpu_gather_is_the_allgather_of_the_ranks_outputs(MPC):
+    """K6 on hardware (needs >= 2 GPUs, skipped otherwise): two ranks, batch sharded, u* of both ranks in both gathered
+    buffers through the epilogue's peer stores + arrival flags, double-buffered by step parity; bench.py compares every
+    rank's whole gathered buffer with an NCCL all-gather of the ranks' own outputs after the device loop and after the
+    end-to-end loop and exits non-zero on a mismatch.  Then the same with the plain NCCL all-gather path."""
+    import json, os, subprocess, sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for extra in ([], ["--nccl-gather"]):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+               "--master-port", "29611", os.path.join(root, "bench.py"), "--gpus", "2", "--steps", "6", "--warmup", "3", "--workload", "random",
+               "--no-cpu-baseline"] + extra
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+        assert line["gather_verified"] is True and line["n_gpus"] == 2 and line["solver"]["unsolved"] == 0
