@@ -627,11 +627,13 @@ __device__ __forceinline__ void tpi_pol_batch(const TpiPolParams<S>& P, const Bm
     if (to_queue) {
         // one 64-bit atomic publishes "nf more entries reserved" and "one more chunk of phase A finished" together, so a
         // consumer that reads the word sees a tail that is final once the chunk count is complete
-        if (fmask) __threadfence();
-        unsigned long long old = 0ull;
-        if (lane == 0) old = atomicAdd((unsigned long long*)(A.counts + TPI_Q_TAIL), (1ull << 32) | (unsigned long long)nf);
-        const int basep = (int)(unsigned)__shfl_sync(0xffffffffu, old, 0);
-        if (fail) ((volatile int32_t*)A.queue)[basep + pos] = inst;
+        if (fmask) {
+            __threadfence();
+            unsigned long long old = 0ull;
+            if (lane == 0) old = atomicAdd((unsigned long long*)(A.counts + TPI_Q_TAIL), (1ull << 32) | (unsigned long long)nf);
+            const int basep = (int)(unsigned)__shfl_sync(0xffffffffu, old, 0);
+            if (fail) ((volatile int32_t*)A.queue)[basep + pos] = inst;
+        } else if (lane == 0) atomicAdd((unsigned long long*)(A.counts + TPI_Q_TAIL), 1ull << 32);     // no return value: fire and forget
     } else if (fmask) {
         int basep = 0;
         if (lane == 0) basep = atomicAdd(A.counts, nf);
@@ -700,8 +702,10 @@ __global__ void __launch_bounds__(TPI_POL_WARPS * 32, 1) k_tpi_pol(const __grid_
             const unsigned long long w = *ctl;                      // tail (low word) and finished chunks (high word) in one read
             const int t = (int)(unsigned)w; const bool all_done = (int)(w >> 32) >= nchunks;
             h = *headp;
-            if (h < t) { n = (t - h) < 32 ? (t - h) : 32; if (atomicCAS(A.counts + TPI_Q_HEAD, h, h + n) != h) n = -1; }
-            else n = all_done ? 0 : -1;
+            // full batches while phase A is still producing (a warp that grabbed whatever trickles in would run the sweeps
+            // for a handful of lanes: measured 20x on steps where every instance needs a second refinement); the rest at the end
+            if (t - h >= 32 || (all_done && h < t)) { n = (t - h) < 32 ? (t - h) : 32; if (atomicCAS(A.counts + TPI_Q_HEAD, h, h + n) != h) n = -1; }
+            else n = (all_done && h >= t) ? 0 : -1;
         }
         h = __shfl_sync(0xffffffffu, h, 0); n = __shfl_sync(0xffffffffu, n, 0);
         if (n == 0) break;

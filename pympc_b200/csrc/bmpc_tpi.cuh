@@ -381,6 +381,14 @@ struct TpiPolParams {
     double cx[S::nx];                                                 // rho_e / rho_x: soft-row multiplier in units of v
     double ulo, uhi, ulo_m, uhi_p, dlo, dhi, dlo_m, dhi_p;            // hard rows: bounds and bound -/+ 1e-9 (1 + |bound|)
     double irhou, irhod, Qu, QDu, quref, rho_e;
+    // table-driven decode (dynamic index into the constant bank instead of selects and predicate logic).  Soft rows by label
+    // (0 none, 1 above, 2 below): acceptance interval of a consistent candidate [xacc_lo, xacc_hi], penalty weight xm, its
+    // linear term xmb = weight * bound, multiplier coefficient xcm = rho_e / rho (in units of v) and bound xbnd
+    double xacc_lo[S::nx][4], xacc_hi[S::nx][4], xm[S::nx][4], xmb[S::nx][4], xcm[S::nx][4], xbnd[S::nx][4];
+    // pin of a stage by its 6 hard-row bits: index 0 free, 1/2 input at max/min, 3/4 delta-u at max/min, 5/6 the spurious last
+    // row at max/min, 7 held stage (Nc < Np)
+    double pintab[8], hsgn[4];                                        // pin value by index; multiplier sign by hard label
+    unsigned char pinidx[64];
 };
 
 #ifdef BMPC_HOSTEMU
@@ -396,26 +404,15 @@ __device__ __forceinline__ double tpi_rcp(double h) {
 }
 #endif
 
-// decoded pin of one stage
-struct TpiPin { bool free_, upin, dpin, qpin; double pin; };
+// pin index of one stage from its code word (held: a stage k >= Nc of a shape with Nc < Np)
 template <class S>
-BMPC_HD TpiPin tpi2_pin(const TpiPolParams<S>& P, unsigned code, bool held) {
-    using C = TpiCode<S>;
-    const bool uu = (code >> C::UUP) & 1u, ud = (code >> C::UDN) & 1u, du = (code >> C::DUP) & 1u, dd = (code >> C::DDN) & 1u,
-               qu = (code >> C::QUP) & 1u, qd = (code >> C::QDN) & 1u;
-    TpiPin t;
-    t.upin = (uu || ud) && !held;
-    t.dpin = held || (!t.upin && (du || dd));
-    t.qpin = !t.upin && !t.dpin && (qu || qd);
-    t.free_ = !(t.upin || t.dpin || t.qpin);
-    // priority as in tpi_pin_of: input bound, delta-u row, then the reference's spurious last row (-u within [Dumin, Dumax])
-    double p = qu ? -P.dhi : -P.dlo;
-    p = t.qpin ? p : 0.0;
-    p = t.dpin ? (du ? P.dhi : P.dlo) : p;
-    p = held ? 0.0 : p;
-    p = t.upin ? (uu ? P.uhi : P.ulo) : p;
-    t.pin = p;
-    return t;
+BMPC_HD int tpi2_pinidx(const TpiPolParams<S>& P, unsigned code, bool held) {
+    return held ? 7 : (int)P.pinidx[(code >> TpiCode<S>::UUP) & 63u];
+}
+// soft-row label (0 none, 1 above its bound, 2 below) of state component a
+template <class S>
+BMPC_HD int tpi2_xlabel(unsigned code, int a) {
+    return (int)((code >> (TpiCode<S>::XUP + a)) & 1u) + 2 * (int)((code >> (TpiCode<S>::XDN + a)) & 1u);
 }
 
 // Backward sweep: fills the gain slots of W from the working-set codes C(k).
@@ -423,7 +420,6 @@ template <class S, class XR, class CA>
 BMPC_HD void tpi2_backward(const TpiPolParams<S>& P, TpiAcc W, CA C, XR xr) {
     static_assert(S::nu == 1 && S::Nc <= S::Np, "Riccati polish is specialised to nu == 1");
     constexpr int nx = S::nx, N = S::Np, Nc = S::Nc, nz1 = nx + 2;
-    using CD = TpiCode<S>;
     double Pm[nx * nx], pxw[nx], px[nx], pww = 0.0, pw = 0.0;          // Pm symmetric: both triangles hold the same values
     double qc[nx];                                                       // Qx xref (constant reference)
     if (!XR::TV) {
@@ -435,23 +431,29 @@ BMPC_HD void tpi2_backward(const TpiPolParams<S>& P, TpiAcc W, CA C, XR xr) {
             qc[a] = q;
         }
     }
+    unsigned code = C(N - 1);
     {   // terminal cost of x_N (its rows are the state bits of stage N-1)
-        const unsigned c = C(N - 1);
 #pragma unroll
         for (int a = 0; a < nx; a++) {
-            const bool su = (c >> (CD::XUP + a)) & 1u, sd = (c >> (CD::XDN + a)) & 1u;
+            const int lab = tpi2_xlabel<S>(code, a);
             double q = 0.0;
 #pragma unroll
             for (int b = 0; b < nx; b++) { Pm[a * nx + b] = P.QxN[a * nx + b]; q += P.QxN[a * nx + b] * xr(N, b); }
-            const double m = (su || sd) ? P.rho_e : 0.0;
-            Pm[a * nx + a] += m;
-            px[a] = -(q + m * (su ? P.xhi[a] : P.xlo[a])); pxw[a] = 0.0;
+            Pm[a * nx + a] += P.xm[a][lab];
+            px[a] = -(q + P.xmb[a][lab]); pxw[a] = 0.0;
         }
     }
 #pragma unroll 1
     for (int k = N - 1; k >= 0; k--) {
-        const unsigned code = C(k);
         const unsigned cprev = C(k >= 1 ? k - 1 : 0);                   // state bits of x_k (x_0 is data: its cost is irrelevant)
+        const bool held = (Nc < N) && (k >= Nc);
+        const int pi = tpi2_pinidx<S>(P, code, held);
+        const double pin = P.pintab[pi];
+        const bool free_ = pi == 0;
+        const double dp = (pi == 3 || pi == 4 || pi == 7) ? 1.0 : 0.0;
+        double xmk[nx], xmbk[nx];
+#pragma unroll
+        for (int a = 0; a < nx; a++) { const int lab = tpi2_xlabel<S>(cprev, a); xmk[a] = P.xm[a][lab]; xmbk[a] = P.xmb[a][lab]; }
         double T[nx * nx], PB[nx];
 #pragma unroll
         for (int a = 0; a < nx; a++) {
@@ -484,31 +486,26 @@ BMPC_HD void tpi2_backward(const TpiPolParams<S>& P, TpiAcc W, CA C, XR xr) {
 #pragma unroll
             for (int q = 0; q < nx; q++) { h = fma(P.Ad[q * nx + a], PB[q] + pxw[q], h); g = fma(P.Ad[q * nx + a], px[q], g); }
             hx[a] = h;
-            const bool su = (cprev >> (CD::XUP + a)) & 1u, sd = (cprev >> (CD::XDN + a)) & 1u;
-            const double m = (su || sd) ? P.rho_e : 0.0;
             double q;
             if (XR::TV) {
                 q = 0.0;
 #pragma unroll
                 for (int b = 0; b < nx; b++) q = fma(P.Qx[a * nx + b], xr(k, b), q);
             } else q = qc[a];
-            Hxx[a * nx + a] += m;
-            gx[a] = g - fma(m, su ? P.xhi[a] : P.xlo[a], q);
+            Hxx[a * nx + a] += xmk[a];
+            gx[a] = g - (q + xmbk[a]);
         }
-        const bool held = (Nc < N) && (k >= Nc);
-        const TpiPin t = tpi2_pin<S>(P, code, held);
         const double hw = -P.QDu, Hww = P.QDu;
-        const double dp = t.dpin ? 1.0 : 0.0;
         const double inv = tpi_rcp(huu);
-        const double c1 = t.free_ ? inv : 0.0, c4 = t.free_ ? inv : 1.0;
-        const double c2 = fma(-c1, gu, t.pin);                          // free: -gu / huu ; pinned: pin
+        const double c1 = free_ ? inv : 0.0, c4 = free_ ? inv : 1.0;
+        const double c2 = fma(-c1, gu, pin);                            // free: -gu / huu ; pinned: pin
         const double c3 = fma(-c1, hw, dp);
-        const double pinned0 = fma(huu, t.pin, gu);                     // dQ/du offset of a pinned stage
+        const double pinned0 = fma(huu, pin, gu);                       // dQ/du offset of a pinned stage
         const int base = k * nz1;
 #pragma unroll
         for (int a = 0; a < nx; a++) W(base + a) = hx[a] * c4;
-        W(base + nx) = t.free_ ? hw * inv : fma(dp, huu, hw);
-        W(base + nx + 1) = t.free_ ? gu * inv : pinned0;
+        W(base + nx) = free_ ? hw * inv : fma(dp, huu, hw);
+        W(base + nx + 1) = free_ ? gu * inv : pinned0;
 #pragma unroll
         for (int a = 0; a < nx; a++) {
             const double ha = hx[a] * c1;
@@ -519,58 +516,75 @@ BMPC_HD void tpi2_backward(const TpiPolParams<S>& P, TpiAcc W, CA C, XR xr) {
         }
         pww = fma(dp, fma(2.0, hw, huu), Hww) - c1 * hw * hw;
         pw = fma(hw, c2, dp * pinned0);
+        code = cprev;
     }
 }
 
 // Forward sweep: rolls the closed loop out, verifies the KKT conditions of the working sets, writes the NEXT working sets
 // into C(k), the inputs through outu(k, u), the exact ADMM fixed point v* = z* + y*/rho into the gain slots just consumed
 // (the spurious last row into vq) and returns true when the candidate is the minimiser.  mumax: in = scale of the multiplier
-// sign tolerance (largest multiplier of the previous refinement, 0 at first), out = largest multiplier of this one.
+// sign tolerance (sum of the multiplier magnitudes of the previous refinement, 0 at first), out = that of this one.
 template <class S, class CA, class FU>
 BMPC_HD bool tpi2_forward(const TpiPolParams<S>& P, TpiAcc W, CA C, const double* x0, double um1, double& mumax, double& vq, FU outu) {
     constexpr int nx = S::nx, N = S::Np, Nc = S::Nc, nz1 = nx + 2;
     using CD = TpiCode<S>;
-    const double mutol = 1e-9 * (1.0 + mumax);
+    const double mutol = -1e-9 * (1.0 + mumax);
     double mnew = 0.0;
-    bool bad = false;
+    unsigned bad = 0u;
     double x[nx], w = um1;
 #pragma unroll
     for (int a = 0; a < nx; a++) x[a] = x0[a];
-    // KKT check of one hard row; returns its bits of the next working set (bit 0 up, bit 1 down)
-    auto hard_row = [&](double zi, double lo_m, double hi_p, bool su, bool sd, double mu) -> unsigned {
-        const bool vu = zi > hi_p, vd = zi < lo_m;
-        bad = bad || vu || vd || (su && mu < -mutol) || (sd && mu > mutol);
-        const bool nu_ = vu || (!vd && su && mu > 0.0);
-        const bool nd_ = !nu_ && (vd || (sd && mu < 0.0));
-        return (nu_ ? 1u : 0u) | (nd_ ? 2u : 0u);
+    // KKT check of one hard row with label lab (0 none, 1 at max, 2 at min) and multiplier mu; returns its two bits of the next
+    // working set (bit 0 up, bit 1 down).  m = sign(label) * mu must not be negative; the label survives if m > 0.
+    auto hard_row = [&](double zi, double lo_m, double hi_p, unsigned lab, double mu) -> unsigned {
+        const double m = P.hsgn[lab] * mu;
+        const unsigned vu = zi > hi_p, vd = zi < lo_m, keep = m > 0.0;
+        bad |= vu | vd | (unsigned)(m < mutol);
+        const unsigned nu_ = vu | (~vd & keep & lab & 1u);
+        const unsigned nd_ = ~nu_ & (vd | (keep & (lab >> 1))) & 1u;
+        return (nu_ & 1u) | (nd_ << 1);
     };
+    unsigned code = C(0);
+    double g[nz1];
+#pragma unroll
+    for (int a = 0; a < nz1; a++) g[a] = W(a);
 #pragma unroll 1
     for (int k = 0; k < N; k++) {
-        const unsigned code = C(k);
         const int base = k * nz1;
-        double lin = W(base + nx + 1);
-#pragma unroll
-        for (int a = 0; a < nx; a++) lin = fma(W(base + a), x[a], lin);
-        lin = fma(W(base + nx), w, lin);
         const bool held = (Nc < N) && (k >= Nc);
-        const TpiPin t = tpi2_pin<S>(P, code, held);
-        double u = t.dpin ? w + t.pin : t.pin;
-        u = t.free_ ? -lin : u;
+        const int pi = tpi2_pinidx<S>(P, code, held);
+        const double pin = P.pintab[pi];
+        // soft-row tables of x_{k+1} (independent of the state recursion: issued before it)
+        double alo[nx], ahi[nx], cm[nx], bnd[nx];
+#pragma unroll
+        for (int a = 0; a < nx; a++) { const int lab = tpi2_xlabel<S>(code, a); alo[a] = P.xacc_lo[a][lab]; ahi[a] = P.xacc_hi[a][lab]; cm[a] = P.xcm[a][lab]; bnd[a] = P.xbnd[a][lab]; }
+        double lin = g[nx + 1];
+#pragma unroll
+        for (int a = 0; a < nx; a++) lin = fma(g[a], x[a], lin);
+        lin = fma(g[nx], w, lin);
+        // next stage's code and gains: in flight while this stage computes
+        const int kn = (k + 1 < N) ? k + 1 : k;
+        const unsigned code_n = C(kn);
+#pragma unroll
+        for (int a = 0; a < nz1; a++) g[a] = W(kn * nz1 + a);
+        const bool dpin = (pi == 3 || pi == 4 || pi == 7);
+        double u = dpin ? w + pin : pin;
+        u = (pi == 0) ? -lin : u;
         unsigned ncode = 0u;
         if (!held) {
-            const double mu_u = t.upin ? -lin : 0.0, mu_d = t.dpin ? -lin : 0.0;
-            mnew = fmax(mnew, (t.free_ ? 0.0 : fabs(lin)));
+            const double mu_u = (pi == 1 || pi == 2) ? -lin : 0.0, mu_d = (pi == 3 || pi == 4) ? -lin : 0.0;
+            mnew += (pi == 0) ? 0.0 : fabs(lin);
             outu(k, u);
-            unsigned hb = hard_row(u, P.ulo_m, P.uhi_p, (code >> CD::UUP) & 1u, (code >> CD::UDN) & 1u, mu_u);
+            unsigned hb = hard_row(u, P.ulo_m, P.uhi_p, (code >> CD::UUP) & 3u, mu_u);
             ncode |= hb << CD::UUP;
             W(base + nx) = fma(mu_u, P.irhou, u);
             const double dz = u - w;                                    // row 0: u_0 against bounds shifted by u_-1 = the same test
-            hb = hard_row(dz, P.dlo_m, P.dhi_p, (code >> CD::DUP) & 1u, (code >> CD::DDN) & 1u, mu_d);
+            hb = hard_row(dz, P.dlo_m, P.dhi_p, (code >> CD::DUP) & 3u, mu_d);
             ncode |= hb << CD::DUP;
             W(base + nx + 1) = fma(mu_d, P.irhod, (k == 0) ? u : dz);
             if (k == Nc - 1) {
-                const double mu_q = t.qpin ? lin : 0.0;
-                hb = hard_row(-u, P.dlo_m, P.dhi_p, (code >> CD::QUP) & 1u, (code >> CD::QDN) & 1u, mu_q);
+                const double mu_q = (pi == 5 || pi == 6) ? lin : 0.0;
+                hb = hard_row(-u, P.dlo_m, P.dhi_p, (code >> CD::QUP) & 3u, mu_q);
                 ncode |= hb << CD::QUP;
                 vq = fma(mu_q, P.irhod, -u);
             }
@@ -588,22 +602,19 @@ BMPC_HD bool tpi2_forward(const TpiPolParams<S>& P, TpiAcc W, CA C, const double
         for (int a = 0; a < nx; a++) {
             const double zi = xn[a];
             x[a] = zi;
-            const bool su = (code >> (CD::XUP + a)) & 1u, sd = (code >> (CD::XDN + a)) & 1u;
-            const bool nu_ = zi > P.xhi_p[a], nd_ = zi < P.xlo_m[a];
-            // a label may differ from the side the candidate is on only if the row sits on that bound (to 1e-11 relative)
-            const bool oku = su ? (zi >= P.xhi_m[a]) : !nu_;
-            const bool okd = sd ? (zi <= P.xlo_p[a]) : !nd_;
-            bad = bad || !(oku && okd);
-            const double bnd = su ? P.xhi[a] : P.xlo[a];
-            const double cm = (su || sd) ? P.cx[a] : 0.0;
-            W(base + a) = fma(cm, zi - bnd, zi);
-            ncode |= (nu_ ? 1u : 0u) << (CD::XUP + a);
-            ncode |= ((nd_ && !nu_) ? 1u : 0u) << (CD::XDN + a);
+            // a label may differ from the side the candidate is on only if the row sits on that bound (to 1e-11 relative): the
+            // candidate is consistent iff zi lies in the acceptance interval of the row's label
+            bad |= (unsigned)(zi < alo[a]) | (unsigned)(zi > ahi[a]);
+            const unsigned nu_ = zi > P.xhi_p[a], nd_ = zi < P.xlo_m[a];
+            W(base + a) = fma(cm[a], zi - bnd[a], zi);
+            ncode |= nu_ << (CD::XUP + a);
+            ncode |= (nd_ & ~nu_ & 1u) << (CD::XDN + a);
         }
         C(k) = (typename CD::type)ncode;
+        code = code_n;
     }
     mumax = mnew;
-    return !bad;
+    return bad == 0u;
 }
 
 // first working sets from an ADMM iterate v (TPI rows; after a cold start or a straggler round): as tpi_sets_from_v
@@ -662,4 +673,23 @@ inline void tpi_fill_pol(const double* sys, const BmpcSysOff& o, TpiPolParams<S>
     P.dlo = sys[o.lo0 + NX + NU]; P.dhi = sys[o.hi0 + NX + NU]; P.dlo_m = tol(P.dlo, 1e-9, -1.0); P.dhi_p = tol(P.dhi, 1e-9, 1.0);
     P.irhou = 1.0 / sys[o.rho + NX]; P.irhod = 1.0 / sys[o.rho + NX + NU];
     P.Qu = sys[o.Qu]; P.QDu = sys[o.QDu]; P.quref = sys[o.Qu] * sys[o.uref]; P.rho_e = rho_e;
+    const double inf = HUGE_VAL;
+    for (int a = 0; a < nx; a++) {
+        const double lo = P.xlo[a], hi = P.xhi[a];
+        const double al[4] = {P.xlo_m[a], P.xhi_m[a], -inf, -inf}, ah[4] = {P.xhi_p[a], inf, P.xlo_p[a], inf};
+        const double m[4] = {0.0, rho_e, rho_e, 0.0}, bd[4] = {0.0, hi, lo, 0.0};
+        for (int l = 0; l < 4; l++) {
+            P.xacc_lo[a][l] = al[l]; P.xacc_hi[a][l] = ah[l]; P.xm[a][l] = m[l]; P.xbnd[a][l] = (fabs(bd[l]) > 1e300) ? 0.0 : bd[l];
+            P.xmb[a][l] = m[l] * P.xbnd[a][l]; P.xcm[a][l] = (l == 1 || l == 2) ? P.cx[a] : 0.0;
+        }
+    }
+    const double pt[8] = {0.0, P.uhi, P.ulo, P.dhi, P.dlo, -P.dhi, -P.dlo, 0.0};
+    for (int i = 0; i < 8; i++) P.pintab[i] = pt[i];
+    P.hsgn[0] = 0.0; P.hsgn[1] = 1.0; P.hsgn[2] = -1.0; P.hsgn[3] = 0.0;
+    for (int b = 0; b < 64; b++) {
+        // bits: 0 input up, 1 input down, 2 delta-u up, 3 delta-u down, 4 spurious row up, 5 spurious row down; priority as listed
+        int idx = 0;
+        if (b & 1) idx = 1; else if (b & 2) idx = 2; else if (b & 4) idx = 3; else if (b & 8) idx = 4; else if (b & 16) idx = 5; else if (b & 32) idx = 6;
+        P.pinidx[b] = (unsigned char)idx;
+    }
 }

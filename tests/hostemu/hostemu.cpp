@@ -139,7 +139,7 @@ static int emu_tpi2_run(const double* sys, const double* x0, const double* um1, 
     const TpiXref<S, TV> xr{xref};
     BmpcDims d = bmpc_make_dims(S::nx, S::nu, S::Np, S::Nc); BmpcSysOff o = bmpc_make_off(d);
     TpiPolParams<S>* P = new TpiPolParams<S>(); tpi_fill_pol<S>(sys, o, *P);
-    double* col = (double*)calloc(S::MT + 8, sizeof(double));
+    double* col = (double*)calloc(S::Np * (S::nx + 2) + S::MT + 8, sizeof(double));
     CT stored[S::Np], cur[S::Np];
     for (int k = 0; k < S::Np; k++) stored[k] = (CT)codes[k];
     TpiAcc W{col, 1};

@@ -25,15 +25,17 @@ for r in rows[2:]:
                      st={s: int(r[col[s]] or 0) for s in stall_cols}))
 tot = sum(d["n"] for d in data)
 regions = []
-for a in sys.argv[2:]:
+for a in [x for x in sys.argv[2:] if not x.startswith("--")]:
     lo, hi, name = a.split(":"); regions.append((int(lo, 16), int(hi, 16), name))
 if not regions:
     for d in data:
         m = re.search(r"BRA(?:\.\w+)* .*?(0x[0-9a-f]+)\s*;?$", d["src"])
         if m:
-            t = int(m.group(1), 16) - 0  # absolute target in kernel-relative addressing
-            if t < d["off"] and d["off"] - t > 16 * 40:
+            t = int(m.group(1), 16) - base                            # targets are absolute addresses
+            if 0 <= t < d["off"] and d["off"] - t > 16 * 40:
                 regions.append((t, d["off"], f"loop@{t:#x}"))
+    # innermost loops only (plus everything else as "other")
+    regions = [r for r in sorted(set(regions)) if not any(o != r and r[0] <= o[0] and o[1] <= r[1] for o in set(regions))]
 print(f"total samples {tot}")
 for lo, hi, name in regions:
     sel = [d for d in data if lo <= d["off"] <= hi]
