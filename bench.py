@@ -280,7 +280,7 @@ def device_loop(torch, dist, K, cfg, X0, steps, warmup, dev, world, gather, flus
         flush.zero_()                                             # L2 flush between timed iterations (outside the events)
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        L.bmpc_update(h, Xd.data_ptr(), Uprev.data_ptr(), None, 1, 1)
+        L.bmpc_update(h, Xd.data_ptr(), Uprev.data_ptr(), None, 1, 2)     # device-resident inputs, read in place (borrowed)
         rc = L.bmpc_solve(h)
         assert rc == 0, L.bmpc_last_error(h)
         L.bmpc_output(h, None, None, 1, 1)

@@ -9,7 +9,9 @@
  *
  * Conventions: plain pointers and sizes, row-major fp64, batch-major [B, ...]; every call returns 0
  * on success or a negative bmpc_error; the message is available from bmpc_last_error().  The
- * library owns all device state; callers own every buffer they pass (copied at call time).
+ * library owns all device state; callers own every buffer they pass.  HOST buffers handed to bmpc_update / bmpc_est_* are read by
+ * an asynchronous copy queued on the handle's stream: leave them untouched until the next call that waits for the device
+ * (bmpc_output to host memory, bmpc_synchronize, bmpc_get_*); pympc_b200.MPCController double-buffers its staging arrays.
  * One handle <-> one device + one stream; a handle is not thread-safe.
  */
 #ifndef BMPC_H
@@ -88,14 +90,17 @@ int bmpc_setup(bmpc_handle* h, const double* Ad, const double* Bd, const double*
 /* replaces update()/_update_QP_matrices_/OSQP.update (mpc.py:338-364, 386-454).
  * x0 [B,nx]; uminus1 [B,nu] or NULL (keep: the previously committed output, quirk Q9);
  * xref [B,nx] (xref_rows = 1) or [B,Np+1,nx] (xref_rows = Np+1) or NULL (keep).
- * on_device != 0: the pointers are device pointers on this handle's device. */
+ * on_device = 1: the pointers are device pointers on this handle's device (copied, stream-ordered);
+ * on_device = 2: device pointers that are BORROWED — the solver kernels read x0 / uminus1 in place, no copy; the caller leaves
+ * them unchanged until the next solve has been retired (bmpc_output, bmpc_synchronize); xref is always copied. */
 int bmpc_update(bmpc_handle* h, const double* x0, const double* uminus1, const double* xref, int xref_rows, int on_device);
 
 /* replaces OSQP.solve (mpc.py:366-375): K3 + K4 + K5 */
 int bmpc_solve(bmpc_handle* h);
 
 /* replaces output() (mpc.py:271-336): u0 [B,nu] (u_failure = uref where status < 0), status [B] (nullable);
- * commit_uminus1 != 0 stores u0 as the next uminus1 (mpc.py:330). */
+ * commit_uminus1 != 0 makes u0 the next uminus1 (mpc.py:330): every kernel that publishes u0 also writes a shadow copy, so the
+ * commit is a pointer swap, not a copy. */
 int bmpc_output(bmpc_handle* h, double* u0, int32_t* status, int commit_uminus1, int on_device);
 
 /* optional info of output(): u_seq [B,Nc*nu], x_seq [B,(Np+1)*nx], eps_seq [B,(Np+1)*nx], obj_val [B]
@@ -141,6 +146,10 @@ int bmpc_est_update(bmpc_estimator* e, const double* y_meas /* [batch,ny] */, in
 int bmpc_est_get(bmpc_estimator* e, double* x /* [batch,nx] or NULL */, double* y /* [batch,ny] or NULL */);
 double* bmpc_est_state_ptr(bmpc_estimator* e);           /* device pointer to x [batch,nx] */
 int bmpc_est_set_stream(bmpc_estimator* e, void* cuda_stream);
+/* on-device chain estimator <-> controller without host reads in between: the estimator runs on the controller's stream (its
+ * kernels are ordered against bmpc_update(on_device=1) reading bmpc_est_state_ptr() and against the solver writing u0), and
+ * a predict/update that takes a device pointer first retires the controller's deferred solve.  h = NULL detaches. */
+int bmpc_est_attach(bmpc_estimator* e, bmpc_handle* h);
 
 /* pinned host memory for the end-to-end path (cudaHostAlloc / cudaFreeHost) */
 void* bmpc_host_alloc(uint64_t bytes);

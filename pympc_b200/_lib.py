@@ -32,7 +32,7 @@ EXPORTS = ["bmpc_default_config", "bmpc_create", "bmpc_destroy", "bmpc_last_erro
            "bmpc_gather_arrive", "bmpc_set_stream",
            "bmpc_synchronize", "bmpc_get_stats", "bmpc_get_sys", "bmpc_get_dims", "bmpc_host_alloc",
            "bmpc_host_free", "bmpc_device_count", "bmpc_est_create", "bmpc_est_destroy", "bmpc_est_predict",
-           "bmpc_est_update", "bmpc_est_get", "bmpc_est_state_ptr", "bmpc_est_set_stream"]
+           "bmpc_est_update", "bmpc_est_get", "bmpc_est_state_ptr", "bmpc_est_set_stream", "bmpc_est_attach"]
 
 
 class BmpcError(RuntimeError):
@@ -76,6 +76,7 @@ def load():
     L.bmpc_est_get.argtypes = [P, DP, DP]; L.bmpc_est_get.restype = ctypes.c_int
     L.bmpc_est_state_ptr.argtypes = [P]; L.bmpc_est_state_ptr.restype = P
     L.bmpc_est_set_stream.argtypes = [P, P]; L.bmpc_est_set_stream.restype = ctypes.c_int
+    L.bmpc_est_attach.argtypes = [P, P]; L.bmpc_est_attach.restype = ctypes.c_int
     _lib = L
     return L
 

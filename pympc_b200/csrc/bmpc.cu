@@ -119,6 +119,7 @@ struct BmpcInst {
     int32_t* iters;       // [B]
     int32_t* psteps;      // [B]
     int32_t* lvl;         // [B] adaptive-rho ladder level (reset to the base level at every solve)
+    double* u0_shadow;    // second copy of the output = the NEXT solve's u_-1 if output() commits it (a pointer swap instead of a copy)
     double* u0_peer[8];   // extra copies of the output slice in peer GPUs' buffers (NVLink peer stores), see bmpc_bind_output_peers
     int n_peer;
     size_t sys_stride;    // 0: all instances share one system block; o.total: instance i uses block i (per-instance Ad, Bd, ...)
@@ -128,6 +129,7 @@ struct BmpcInst {
 // GPU's copy of the gathered buffer over NVLink (the all-gather is fused into the kernel: no collective launch)
 __device__ __forceinline__ void bmpc_publish_u0(const BmpcInst& I, double* u0_out, size_t idx, double val) {
     u0_out[idx] = val;
+    I.u0_shadow[idx] = val;
     for (int p = 0; p < I.n_peer; p++) I.u0_peer[p][idx] = val;
 }
 
@@ -484,7 +486,7 @@ __global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmm
 #pragma unroll
             for (int q = 0; q < S::nu; q++) um1_solved[(size_t)inst * S::nu + q] = um1[q];
         }
-        if (blockIdx.x == 0 && lane < 8) counts[lane] = 0;
+        if (blockIdx.x == 0 && lane < 8) counts[lane] = 0;        // (the polish launch behind this one zeroes the other half)
     }
     // g' (read once per iteration) lives in the instance's global scratch row I.g, not in shared memory: the column is
     // MT rows instead of MT + NU, which lets one more warp reside per SM (measured: ADMM kernel 12 % faster)
@@ -528,8 +530,9 @@ struct TpiPolArgs {
     int mode;                            // 0 stored working sets, 1 stored and shifted one stage (receding horizon), 2 from the iterate v
     int capA, capB;                      // refinements per instance in phase A / in phase B (0: no phase B, failures go to next_list)
     int reset;                           // first round of a solve: per-solve bookkeeping rides here
+    int32_t* counts_next;                // the 8 counters of the NEXT round: zeroed here (saves a memset launch per solve)
     int32_t* next_list; int32_t* counts; // counts[0] unfinished (-> next_list), [1] refinements; counts[4..7] queue control, see below
-    int32_t* queue;                      // phase-B queue, all -1 between launches (consumers clear what they take)
+    int32_t* queue; int qcap;            // phase-B queue (capacity qcap), all -1 between launches (consumers clear what they take)
     double* u0_out; double* um1_solved;
     unsigned char* codes; int code_stride;   // per instance: Np working-set codes + the multiplier scale (double) of the last refinement
 };
@@ -659,11 +662,27 @@ __device__ __forceinline__ void tpi_pol_batch(const TpiPolParams<S>& P, const Bm
 #pragma unroll
             for (int c = 0; c < NG; c++) { const int i = c * 32 + lane; soff[c] = (i < L::VROWS) ? tpi_vstar_slot<S>(i) * TPI_STR : -1; }
             double* dst = I.vw + (size_t)inst0_contig * S::mc + nx + lane;
-#pragma unroll 4
-            for (int t = 0; t < nvalid; t++) {
-                if (!((okmask >> t) & 1u)) continue;
+            if (okmask == 0xffffffffu) {
+                // every instance of the chunk verified (the steady state): 4 instances per trip, all loads ahead of the stores
+#pragma unroll 1
+                for (int t = 0; t < 32; t += 4) {
+                    double val[4][NG];
 #pragma unroll
-                for (int c = 0; c < NG; c++) if (soff[c] >= 0) dst[(size_t)t * S::mc + c * 32] = wsm[soff[c] + t];
+                    for (int j = 0; j < 4; j++)
+#pragma unroll
+                        for (int c = 0; c < NG; c++) val[j][c] = (soff[c] >= 0) ? wsm[soff[c] + t + j] : 0.0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+#pragma unroll
+                        for (int c = 0; c < NG; c++) if (soff[c] >= 0) dst[(size_t)(t + j) * S::mc + c * 32] = val[j][c];
+                }
+            } else {
+#pragma unroll 2
+                for (int t = 0; t < nvalid; t++) {
+                    if (!((okmask >> t) & 1u)) continue;
+#pragma unroll
+                    for (int c = 0; c < NG; c++) if (soff[c] >= 0) dst[(size_t)t * S::mc + c * 32] = wsm[soff[c] + t];
+                }
             }
         } else if (ok) {
             double* dst = I.vw + (size_t)inst * S::mc;
@@ -681,6 +700,7 @@ __global__ void __launch_bounds__(TPI_POL_WARPS * 32, 1) k_tpi_pol(const __grid_
     double* wsm = (double*)((char*)smem + (size_t)warp * L::per_warp);
     CT* csm = (CT*)((char*)wsm + L::gain_bytes);
     const int nchunks = (A.count + 31) / 32;
+    if (blockIdx.x == 0 && threadIdx.x < 8) A.counts_next[threadIdx.x] = 0;
     // ---- phase A
     for (;;) {
         int chunk = 0;
@@ -693,32 +713,32 @@ __global__ void __launch_bounds__(TPI_POL_WARPS * 32, 1) k_tpi_pol(const __grid_
         tpi_pol_batch<S, TV>(P, I, A, wsm, csm, inst, valid, A.list ? -1 : idx0, nvalid, A.mode, A.capA, A.capB > 0, A.reset);
     }
     if (A.capB <= 0) return;
-    // ---- phase B: serve the queue until every chunk of phase A is finished and the queue is empty
+    // ---- phase B: serve the queue until every chunk of phase A is finished and the queue is empty.  Tickets: a warp takes the
+    // next 32 queue slots with one fetch-and-add (no compare-and-swap races between a thousand warps) and waits until they are
+    // filled or phase A has ended short of them, so batches are full while phase A still produces.
     volatile unsigned long long* ctl = (volatile unsigned long long*)(A.counts + TPI_Q_TAIL);
-    volatile int32_t* headp = (volatile int32_t*)(A.counts + TPI_Q_HEAD);
     for (;;) {
-        int h = 0, n = 0;
-        if (lane == 0) {
-            const unsigned long long w = *ctl;                      // tail (low word) and finished chunks (high word) in one read
-            const int t = (int)(unsigned)w; const bool all_done = (int)(w >> 32) >= nchunks;
-            h = *headp;
-            // full batches while phase A is still producing (a warp that grabbed whatever trickles in would run the sweeps
-            // for a handful of lanes: measured 20x on steps where every instance needs a second refinement); the rest at the end
-            if (t - h >= 32 || (all_done && h < t)) { n = (t - h) < 32 ? (t - h) : 32; if (atomicCAS(A.counts + TPI_Q_HEAD, h, h + n) != h) n = -1; }
-            else n = (all_done && h >= t) ? 0 : -1;
+        int h = 0;
+        if (lane == 0) h = atomicAdd(A.counts + TPI_Q_HEAD, 32);
+        h = __shfl_sync(0xffffffffu, h, 0);
+        const int idx = h + lane;
+        int inst = -1;
+        for (;;) {
+            unsigned wlo = 0u, whi = 0u;
+            if (lane == 0) { const unsigned long long w = *ctl; wlo = (unsigned)w; whi = (unsigned)(w >> 32); }   // tail | finished chunks
+            wlo = __shfl_sync(0xffffffffu, wlo, 0); whi = __shfl_sync(0xffffffffu, whi, 0);
+            const bool all_done = (int)whi >= nchunks;
+            if (inst < 0 && idx < A.qcap && (idx < (int)wlo)) inst = ((volatile int32_t*)A.queue)[idx];
+            const bool ready = inst >= 0 || (all_done && idx >= (int)wlo);
+            if (__all_sync(0xffffffffu, ready)) break;
+            __nanosleep(200);
         }
-        h = __shfl_sync(0xffffffffu, h, 0); n = __shfl_sync(0xffffffffu, n, 0);
-        if (n == 0) break;
-        if (n < 0) { __nanosleep(400); continue; }
-        const bool valid = lane < n;
-        int inst = 0;
-        if (valid) {
-            volatile int32_t* q = (volatile int32_t*)A.queue + h + lane;
-            while ((inst = *q) < 0) __nanosleep(50);
-            *q = -1;                                                 // the queue is all -1 again when the launch ends
-        }
+        const bool valid = inst >= 0;
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        if (!vmask) break;                                            // ticket beyond the end of the queue: nothing left
+        if (valid) ((volatile int32_t*)A.queue)[idx] = -1;            // the queue is all -1 again when the launch ends
         __threadfence();
-        tpi_pol_batch<S, TV>(P, I, A, wsm, csm, inst, valid, -1, n, 0, A.capB, false, 0);
+        tpi_pol_batch<S, TV>(P, I, A, wsm, csm, valid ? inst : 0, valid, -1, __popc(vmask), 0, A.capB, false, 0);
     }
 }
 
@@ -745,7 +765,9 @@ struct bmpc_handle {
     cudaStream_t stream, own_stream;
     double* sys = nullptr;
     BmpcInst I;
-    double *x0 = nullptr, *um1 = nullptr, *um1_solved = nullptr, *xref = nullptr, *u0_own = nullptr, *u0_bound = nullptr;
+    double *x0 = nullptr, *um1 = nullptr, *um1_alt = nullptr, *um1_solved = nullptr, *xref = nullptr, *u0_own = nullptr, *u0_bound = nullptr;
+    const double *x0_cur = nullptr, *um1_cur = nullptr;    // what the next solve reads: the handle's copies or buffers borrowed from the caller (bmpc_update on_device = 2)
+    int cpar = 0;                                          // which half of counts[16] the round in flight uses (the fast-path kernel zeroes the other half for the next one)
     double *seq_x = nullptr, *seq_e = nullptr, *seq_obj = nullptr;
     int32_t *listA = nullptr, *listB = nullptr, *counts = nullptr;  // counts[8]: [0..3] round counters, [4..7] queue control of k_tpi_pol
     long long* gflags = nullptr; BmpcPeerFlags gpeers = {}; int g_npeer = 0, g_rank = 0, g_world = 1;   // K6 arrival flags
@@ -753,7 +775,7 @@ struct bmpc_handle {
     int32_t* h_count = nullptr;                                      // pinned
     cudaEvent_t ev[4];
     int xref_mode = 0;
-    bool is_setup = false, cold = true, solved = false;
+    bool is_setup = false, cold = true, solved = false, committed = true;   // committed: this solve's u0 already is the next u_-1
     bmpc_stats stats;
     std::string err;
     size_t smem_admm = 0, smem_polish = 0;
@@ -788,7 +810,7 @@ static void launch_tpi_pol(bmpc_handle* h, const int32_t* list, int count, int m
     const TpiPolParams<S>& PP = *(const TpiPolParams<S>*)h->tpi_polish_params;
     TpiPolArgs A;
     A.list = list; A.count = count; A.mode = mode; A.capA = capA; A.capB = capB; A.reset = reset;
-    A.next_list = next_list; A.counts = h->counts; A.queue = h->queue; A.u0_out = h->I.u0; A.um1_solved = h->um1_solved;
+    A.next_list = next_list; A.counts = h->counts + 8 * h->cpar; A.counts_next = h->counts + 8 * (1 - h->cpar); A.queue = h->queue; A.qcap = h->cfg.batch; A.u0_out = h->I.u0; A.um1_solved = h->um1_solved;
     A.codes = h->codes; A.code_stride = L::code_stride;
     const int nchunks = (count + 31) / 32;
     int grid = (nchunks + TPI_POL_WARPS - 1) / TPI_POL_WARPS;
@@ -812,15 +834,14 @@ static void launch_tpi_round(bmpc_handle* h, const int32_t* list, int count, int
     const int capA = 1, capB = h->tpi_pdas_steps - 1;
     if (niter > 0) {
         if (h->xref_mode)   // one (Np+1) x nx reference per instance
-            k_tpi_admm<S, true><<<grid, 32, sa, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts, h->um1_solved);
+            k_tpi_admm<S, true><<<grid, 32, sa, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts + 8 * h->cpar, h->um1_solved);
         else
-            k_tpi_admm<S, false><<<grid, 32, sa, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts, h->um1_solved);
+            k_tpi_admm<S, false><<<grid, 32, sa, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts + 8 * h->cpar, h->um1_solved);
         h->stats.launches++;
         cudaEventRecord(mid, h->stream);
         launch_tpi_pol<S>(h, list, count, 2, capA, capB, 0, next_list);
     } else {
-        cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 8, h->stream);
-        cudaEventRecord(mid, h->stream);
+        cudaEventRecord(mid, h->stream);          // this round's counters were zeroed by the previous fast-path launch (or a memset)
         launch_tpi_pol<S>(h, list, count, h->cfg.shift_warm ? 1 : 0, capA, capB, reset, next_list);
     }
 }
@@ -983,6 +1004,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     ok &= dalloc((void**)&h->sys, sizeof(double) * (size_t)h->o.total * h->cfg.n_sys);
     ok &= dalloc((void**)&h->x0, sizeof(double) * B * d.nx);
     ok &= dalloc((void**)&h->um1, sizeof(double) * B * d.nu);
+    ok &= dalloc((void**)&h->um1_alt, sizeof(double) * B * d.nu);
     ok &= dalloc((void**)&h->um1_solved, sizeof(double) * B * d.nu);
     ok &= dalloc((void**)&h->xref, sizeof(double) * B * d.NX);
     ok &= dalloc((void**)&h->u0_own, sizeof(double) * B * d.nu);
@@ -999,7 +1021,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     ok &= dalloc((void**)&h->I.lvl, sizeof(int32_t) * B);
     ok &= dalloc((void**)&h->listA, sizeof(int32_t) * B);
     ok &= dalloc((void**)&h->listB, sizeof(int32_t) * B);
-    ok &= dalloc((void**)&h->counts, sizeof(int32_t) * 8);
+    ok &= dalloc((void**)&h->counts, sizeof(int32_t) * 16);
     ok &= dalloc((void**)&h->queue, sizeof(int32_t) * B);
     ok &= dalloc((void**)&h->codes, (size_t)B * 72);       // largest record: 32 stages x 2 bytes + 8 (Np < 32 on the fast path)
     ok &= dalloc((void**)&h->ovf, sizeof(int32_t) * (size_t)B);
@@ -1016,9 +1038,11 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     cudaMemset(h->I.Ua, 0, sizeof(double) * B * d.NU);
     cudaMemset(h->queue, 0xff, sizeof(int32_t) * B);
     cudaMemset(h->codes, 0, (size_t)B * 72);
-    cudaMemset(h->counts, 0, sizeof(int32_t) * 8);
+    cudaMemset(h->counts, 0, sizeof(int32_t) * 16);
+    cudaMemset(h->um1_alt, 0, sizeof(double) * B * d.nu);
     h->I.sys_stride = h->cfg.n_sys > 1 ? (size_t)h->o.total : 0;
-    h->I.x0 = h->x0; h->I.um1 = h->um1; h->I.um1_solved = h->um1_solved; h->I.xref = h->xref; h->I.u0 = h->u0_own;
+    h->I.x0 = h->x0; h->I.um1 = h->um1; h->I.um1_solved = h->um1_solved; h->I.xref = h->xref; h->I.u0 = h->u0_own; h->I.u0_shadow = h->um1_alt;
+    h->x0_cur = h->x0; h->um1_cur = h->um1;
     k_reset<<<(int)((B + 255) / 256), 256, 0, h->stream>>>(h->I, (int)B);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "device initialisation failed"; return fail(BMPC_ERR_CUDA); }
     *out = h;
@@ -1029,7 +1053,7 @@ void bmpc_destroy(bmpc_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->pending) cudaStreamSynchronize(h->stream);
-    void* ptrs[] = {h->sys, h->x0, h->um1, h->um1_solved, h->xref, h->u0_own, h->I.g, h->I.cc, h->I.xw, h->I.vw, h->I.Ua, h->I.Us, h->I.res,
+    void* ptrs[] = {h->sys, h->x0, h->um1, h->um1_alt, h->um1_solved, h->xref, h->u0_own, h->I.g, h->I.cc, h->I.xw, h->I.vw, h->I.Ua, h->I.Us, h->I.res,
                     h->I.status, h->I.iters, h->I.psteps, h->I.lvl, h->listA, h->listB, h->counts, h->queue, h->codes, h->ovf, h->vprev, h->lprev, h->seq_x, h->seq_e, h->seq_obj};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_count) cudaFreeHost(h->h_count);
@@ -1156,8 +1180,16 @@ int bmpc_update(bmpc_handle* h, const double* x0, const double* uminus1, const d
     if (h->pending) { int rc = finish_solve(h); if (rc) return rc; }
     const BmpcDims& d = h->d; size_t B = h->cfg.batch;
     cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    if (x0) BMPC_CUDA(cudaMemcpyAsync(h->x0, x0, sizeof(double) * B * d.nx, kind, h->stream));
-    if (uminus1) BMPC_CUDA(cudaMemcpyAsync(h->um1, uminus1, sizeof(double) * B * d.nu, kind, h->stream));
+    if (on_device == 2) {
+        // borrowed device buffers: the solver kernels read them in place (no copy); the caller keeps them unchanged until the
+        // results of the next solve have been retired (bmpc_output / bmpc_synchronize)
+        if (x0) h->x0_cur = x0;
+        if (uminus1) h->um1_cur = uminus1;
+    } else {
+        if (x0) { BMPC_CUDA(cudaMemcpyAsync(h->x0, x0, sizeof(double) * B * d.nx, kind, h->stream)); h->x0_cur = h->x0; }
+        if (uminus1) { BMPC_CUDA(cudaMemcpyAsync(h->um1, uminus1, sizeof(double) * B * d.nu, kind, h->stream)); h->um1_cur = h->um1; }
+    }
+    h->I.x0 = h->x0_cur; h->I.um1 = h->um1_cur;
     if (xref) {
         if (xref_rows != 1 && xref_rows != d.Np + 1) { h->err = "xref_rows must be 1 or Np+1"; return BMPC_ERR_ARG; }
         h->xref_mode = xref_rows == 1 ? 0 : 1;
@@ -1222,15 +1254,18 @@ static int enqueue_round(bmpc_handle* h) {
     const bool tpi = st.round == 0 && tpi_ok && h->cfg.polish;
     // straggler rounds read u_-1 from the snapshot the first round took: bmpc_output may already have queued the commit of
     // this solve's u0 into um1 (speculating that the first round finishes everything)
-    h->I.um1 = st.round > 0 ? h->um1_solved : h->um1;
+    h->cpar ^= 1;                                        // counters of this round: the half the previous round left zeroed
+    int32_t* cnt = h->counts + 8 * h->cpar;
+    h->I.um1 = st.round > 0 ? h->um1_solved : h->um1_cur;
+    h->I.x0 = h->x0_cur; h->I.u0_shadow = h->um1_alt;
     if (!tpi) {
         if (st.round == 0) {
             const int B = h->cfg.batch;
             k_reset<<<(B + 255) / 256, 256, 0, h->stream>>>(h->I, B);
             h->stats.launches++;
-            BMPC_CUDA(cudaMemcpyAsync(h->um1_solved, h->um1, sizeof(double) * (size_t)B * h->d.nu, cudaMemcpyDeviceToDevice, h->stream));
+            BMPC_CUDA(cudaMemcpyAsync(h->um1_solved, h->um1_cur, sizeof(double) * (size_t)B * h->d.nu, cudaMemcpyDeviceToDevice, h->stream));
         }
-        BMPC_CUDA(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 8, h->stream));
+        BMPC_CUDA(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 16, h->stream));     // this round's half and the next one's
     }
     BMPC_CUDA(cudaEventRecord(h->ev[0], h->stream));
     if (tpi) {
@@ -1242,19 +1277,19 @@ static int enqueue_round(bmpc_handle* h) {
         launch_admm(h, st.list, st.count, st.chunk, st.need_prep ? 1 : 0);
         st.need_prep = false;
         if (chk) {
-            k_infeas<<<st.count, 128, sizeof(double) * (h->d.mc + h->d.nu + 2), h->stream>>>(h->d, h->o, h->sys, h->I, st.list, st.count, h->vprev, h->lprev, 1e-4, h->I.u0, h->counts);
+            k_infeas<<<st.count, 128, sizeof(double) * (h->d.mc + h->d.nu + 2), h->stream>>>(h->d, h->o, h->sys, h->I, st.list, st.count, h->vprev, h->lprev, 1e-4, h->I.u0, cnt);
             h->stats.launches++;
         }
         BMPC_CUDA(cudaEventRecord(h->ev[1], h->stream));
         // stragglers of a fast-path shape: the Riccati polish (list mode) has ~3x lower latency than the team Schur polish
         if (h->cfg.polish && tpi_ok && st.total + st.chunk <= 200)
             g_tpi_table[h->tpi_kind - 1].launch_polish(h, st.list, st.count, st.nxt);
-        else if (h->cfg.polish) launch_polish(h, st.list, st.count, st.nxt, h->counts);
-        else { k_check_converged<<<(st.count + 255) / 256, 256, 0, h->stream>>>(h->I, st.list, st.count, h->cfg.eps_abs, h->cfg.eps_rel, st.nxt, h->counts); h->stats.launches++; }
+        else if (h->cfg.polish) launch_polish(h, st.list, st.count, st.nxt, cnt);
+        else { k_check_converged<<<(st.count + 255) / 256, 256, 0, h->stream>>>(h->I, st.list, st.count, h->cfg.eps_abs, h->cfg.eps_rel, st.nxt, cnt); h->stats.launches++; }
     }
-    h->I.um1 = h->um1;
+    h->I.um1 = h->um1_cur;
     BMPC_CUDA(cudaEventRecord(h->ev[2], h->stream));
-    BMPC_CUDA(cudaMemcpyAsync(h->h_count, h->counts, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, h->stream));
+    BMPC_CUDA(cudaMemcpyAsync(h->h_count, cnt, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, h->stream));
     BMPC_CUDA(cudaGetLastError());
     return BMPC_OK;
 }
@@ -1317,7 +1352,7 @@ int bmpc_solve(bmpc_handle* h) {
     if (st.chunk > h->cfg.max_iter) st.chunk = h->cfg.max_iter;
     int rc = enqueue_round(h);
     if (rc) return rc;
-    h->pending = true; h->solved = true;
+    h->pending = true; h->solved = true; h->committed = false;
     return BMPC_OK;
 }
 
@@ -1332,22 +1367,22 @@ int bmpc_output(bmpc_handle* h, double* u0, int32_t* status, int commit_uminus1,
         if (want_u) BMPC_CUDA(cudaMemcpyAsync(u0, h->I.u0, sizeof(double) * B * d.nu, kind, h->stream));
         return BMPC_OK;
     };
-    bool u_copied = false, committed = false;
-    auto commit = [&]() -> int {
-        if (commit_uminus1) BMPC_CUDA(cudaMemcpyAsync(h->um1, h->I.u0, sizeof(double) * B * d.nu, cudaMemcpyDeviceToDevice, h->stream));
-        return BMPC_OK;
-    };
+    bool u_copied = false;
     if (h->pending) {
-        // speculate that the round in flight finishes everything (the common case): queue the result copy and the commit of
-        // u_-1 behind it so that a single wait covers the solve and the read-back and the stream never idles while the host
-        // wakes up; both are redone if stragglers needed more rounds (they rewrite u0)
+        // speculate that the round in flight finishes everything (the common case): queue the result copy behind it so that a
+        // single wait covers the solve and the read-back; redone if stragglers needed more rounds (they rewrite u0)
         if (!on_device) { int rc = copy_u(); if (rc) return rc; u_copied = true; }
-        { int rc = commit(); if (rc) return rc; committed = true; }
         int more = 0; int rc = retire_round(h, &more); if (rc) return rc;
-        if (more) { u_copied = false; committed = false; rc = finish_solve(h); if (rc) return rc; }
-        else if (h->stats.launches && (h->st.count > 0 || !h->cfg.polish)) { u_copied = false; committed = false; }   // k_finalize rewrote u0/status
+        if (more) { u_copied = false; rc = finish_solve(h); if (rc) return rc; }
+        else if (h->stats.launches && (h->st.count > 0 || !h->cfg.polish)) u_copied = false;   // k_finalize rewrote u0/status
     }
-    if (!committed) { int rc = commit(); if (rc) return rc; }
+    if (commit_uminus1 && !h->committed) {
+        // every kernel that publishes u0 also wrote it into the shadow buffer: committing it as the next u_-1 (mpc.py:330) is a
+        // pointer swap, no copy
+        double* t = h->um1; h->um1 = h->um1_alt; h->um1_alt = t;
+        h->um1_cur = h->um1; h->I.um1 = h->um1; h->I.u0_shadow = h->um1_alt;
+        h->committed = true;
+    }
     // every instance KKT-verified and none certified infeasible: the status array is all BMPC_SOLVED, no need to fetch it
     const bool all_solved = h->cfg.polish && h->stats.unsolved == 0 && h->stats.infeasible == 0;
     bool need_sync = false;
@@ -1454,6 +1489,7 @@ struct bmpc_estimator {
     int nx, nu, ny, B, device;
     double *mats = nullptr, *x = nullptr, *y = nullptr, *in = nullptr;
     cudaStream_t stream = nullptr, own = nullptr;
+    bmpc_handle* mpc = nullptr;        // attached controller: same stream, and its deferred solve is retired before its u0 is read
 };
 
 extern "C" {
@@ -1498,6 +1534,12 @@ void bmpc_est_destroy(bmpc_estimator* e) {
 static int est_run(bmpc_estimator* e, const double* in, int n, int on_device, int mode) {
     if (!e || !in) return BMPC_ERR_ARG;
     if (cudaSetDevice(e->device) != cudaSuccess) return BMPC_ERR_CUDA;
+    if (e->mpc) {
+        // on-device chain estimator <-> controller: one stream orders the kernels; a solve whose first round is still in flight may
+        // need straggler rounds (host driven) before its u0 is final, so it is retired here
+        if (on_device && e->mpc->pending) { int rc = finish_solve(e->mpc); if (rc) return rc; }
+        e->stream = e->mpc->stream;
+    }
     const double* src = in;
     if (!on_device) {
         if (cudaMemcpyAsync(e->in, in, (size_t)e->B * n * 8, cudaMemcpyHostToDevice, e->stream) != cudaSuccess) return BMPC_ERR_CUDA;
@@ -1518,5 +1560,12 @@ int bmpc_est_get(bmpc_estimator* e, double* x, double* y) {
 }
 double* bmpc_est_state_ptr(bmpc_estimator* e) { return e ? e->x : nullptr; }
 int bmpc_est_set_stream(bmpc_estimator* e, void* s) { if (!e) return BMPC_ERR_ARG; e->stream = s ? (cudaStream_t)s : e->own; return BMPC_OK; }
+int bmpc_est_attach(bmpc_estimator* e, bmpc_handle* h) {
+    if (!e) return BMPC_ERR_ARG;
+    if (h && h->cfg.device != e->device) return BMPC_ERR_ARG;
+    cudaSetDevice(e->device); cudaStreamSynchronize(e->stream);
+    e->mpc = h; e->stream = h ? h->stream : e->own;
+    return BMPC_OK;
+}
 
 }  // extern "C"

@@ -69,6 +69,14 @@ class LinearStateEstimator:
     def update_device(self, y_ptr):
         return self._L.bmpc_est_update(self._h, y_ptr, 1)
 
+    def attach(self, controller):
+        """Chain this estimator with an MPCController on the device (estimate -> update_from_device -> u0 -> predict_device)
+        without host reads in between: both run on the controller's stream, and the controller's deferred solve is retired before
+        its output buffer is consumed.  `None` detaches."""
+        rc = self._L.bmpc_est_attach(self._h, controller.handle if controller is not None else None)
+        if rc < 0:
+            raise BmpcError("bmpc_est_attach failed (controller on another device?)")
+
     def device_state(self):
         """Device pointer (int) of x [B, nx], usable as bmpc_update(x0=..., on_device=1)."""
         return self._L.bmpc_est_state_ptr(self._h)

@@ -18,7 +18,6 @@ verified), which is what parity at 1e-6 needs; ``eps_abs``/``e
 OSQP's meaning for instances the polish cannot verify, and in ``polish=False`` mode.
 """
 import ctypes
-import types
 import warnings
 
 import numpy as np
@@ -30,11 +29,13 @@ _STATUS_STR = {1: "solved", 2: "solved", -2: "maximum iterations reached", -3: "
 
 
 class _ResInfo:
-    """`res.info` of the last solve: status_val (int or int32 array), status (OSQP's strings), polished."""
-    __slots__ = ("_st", "_scalar", "_B")
+    """`res.info` of the last solve like OSQP's (the reference reads status / obj_val, mpc.py:301-327,372): status_val (int or
+    int32 array), status (OSQP's strings), polished, and — fetched from the device on first access — obj_val (objective of the
+    reference-form QP, without J_CNST) and iter (ADMM iterations; 0 when the polish verified the warm start directly)."""
+    __slots__ = ("_st", "_scalar", "_B", "_K", "_cache", "_id")
 
-    def __init__(self, st, scalar, B):
-        self._st, self._scalar, self._B = st, scalar, B
+    def __init__(self, st, scalar, B, K=None, solve_id=0):
+        self._st, self._scalar, self._B, self._K, self._cache, self._id = st, scalar, B, K, {}, solve_id
 
     @property
     def status_val(self):
@@ -49,6 +50,36 @@ class _ResInfo:
     @property
     def polished(self):
         return bool(self._st[0] == 1) if self._scalar else self._st == 1
+
+    def _fetch(self, what):
+        if what not in self._cache:
+            self._cache[what] = self._K._res_fetch(what, self._id)
+        v = self._cache[what]
+        return (v[0].item() if self._scalar else v)
+
+    @property
+    def obj_val(self):
+        return self._fetch("obj_val")
+
+    @property
+    def iter(self):
+        return self._fetch("iter")
+
+
+class _Res:
+    """Result object of the last solve with the attributes the reference reads from OSQP's (mpc.py:302-327): `x` — the primal
+    solution in the reference's variable order [x_0..x_Np | u_0..u_{Nc-1} | eps_0..eps_Np] (fetched from the device on first
+    access; shape (n,) unbatched, (B, n) batched) — and `info`."""
+    __slots__ = ("info", "_K", "_x", "_id")
+
+    def __init__(self, info, K, solve_id=0):
+        self.info, self._K, self._x, self._id = info, K, None, solve_id
+
+    @property
+    def x(self):
+        if self._x is None:
+            self._x = self._K._res_fetch("x", self._id)
+        return self._x[0] if self._K.batch is None else self._x
 
 
 def __is_vector__(vec):
@@ -192,6 +223,7 @@ class MPCController:
         self._J_CNST = None
         self._J_dirty = True
         self._pin = {}
+        self._pin_flip = {}
         self._status = None
         self._u0 = None
 
@@ -241,10 +273,18 @@ class MPCController:
         raise ValueError("time-varying xref needs exactly Np+1 rows")
 
     def _stage(self, name, arr, shape):
-        """copy into a pinned staging buffer (allocated once) and return it"""
-        pin = self._pin.get(name)
+        """copy into a pinned staging buffer (two per name, used alternately: the asynchronous H2D copy of the previous call may
+        still be reading the other one) and return it"""
+        flip = self._pin_flip[name] = 1 - self._pin_flip.get(name, 1)
+        key = name if flip == 0 else name + "#1"
+        arr_in = np.asarray(arr)
+        for k in (name, name + "#1"):                       # the caller's own pinned buffer (pinned_buffer()): no staging copy
+            pk = self._pin.get(k)
+            if pk is not None and arr_in.shape == pk.array.shape and arr_in.ctypes.data == pk.array.ctypes.data:
+                return pk.array
+        pin = self._pin.get(key)
         if pin is None or pin.array.shape != tuple(shape):
-            pin = PinnedArray(shape); self._pin[name] = pin
+            pin = PinnedArray(shape); self._pin[key] = pin
         arr = np.asarray(arr)
         if not (arr.shape == pin.array.shape and arr.ctypes.data == pin.array.ctypes.data):
             np.copyto(pin.array, np.broadcast_to(arr, shape))
@@ -348,12 +388,13 @@ class MPCController:
         if solve:
             self.solve()
 
-    def update_from_device(self, x_ptr, u_ptr=None, solve=True):
+    def update_from_device(self, x_ptr, u_ptr=None, solve=True, borrow=False):
         """update() with x (and optionally u_-1) already resident on this device, e.g. the state of a
-        ``pympc_b200.kalman.LinearStateEstimator`` — no host round trip between estimator and K3."""
+        ``pympc_b200.kalman.LinearStateEstimator`` — no host round trip between estimator and K3.  borrow=True: the kernels read
+        the buffers in place (no device-to-device copy); keep them unchanged until output() has returned."""
         if self._h is None:
             raise BmpcError("update_from_device() before setup()")
-        self._check(self._L.bmpc_update(self._h, x_ptr, u_ptr, None, 1, 1))
+        self._check(self._L.bmpc_update(self._h, x_ptr, u_ptr, None, 1, 2 if borrow else 1))
         self._J_dirty = True
         if solve:
             self.solve()
@@ -378,7 +419,25 @@ class MPCController:
     def _make_res(self):
         # the reference reads res.info.status / res.info.obj_val (mpc.py:301-327,372); built lazily: nothing is derived from
         # the status array until somebody looks
-        self.res = types.SimpleNamespace(info=_ResInfo(self._status, self.batch is None, self._B))
+        self._solve_id = getattr(self, "_solve_id", 0) + 1
+        self.res = _Res(_ResInfo(self._status, self.batch is None, self._B, self, self._solve_id), self, self._solve_id)
+
+    def _res_fetch(self, what, solve_id):
+        """lazy part of `res`: device -> host on first access (bmpc_get_sequences); only the latest solve is on the device"""
+        if solve_id != self._solve_id:
+            raise BmpcError("this `res` belongs to an earlier solve: its lazily fetched fields are no longer on the device")
+        B, nx, nu, Np, Nc = self._B, self.nx, self.nu, self.Np, self.Nc
+        if what == "iter":
+            it = np.empty(B, np.int32)
+            self._check(self._L.bmpc_get_sequences(self._h, None, None, None, None, ptr(it)))
+            return it
+        if what == "obj_val":
+            obj = np.empty(B)
+            self._check(self._L.bmpc_get_sequences(self._h, None, None, None, ptr(obj), None))
+            return obj
+        useq = np.empty((B, Nc * nu)); xseq = np.empty((B, (Np + 1) * nx)); eseq = np.empty((B, (Np + 1) * nx))
+        self._check(self._L.bmpc_get_sequences(self._h, ptr(useq), ptr(xseq), ptr(eseq), None, None))
+        return np.hstack([xseq, useq, eseq] if self.SOFT_ON else [xseq, useq])
 
     def output(self, return_x_seq=False, return_u_seq=False, return_eps_seq=False, return_status=False, return_obj_val=False):
         """First optimal input (and optional info); commits it as the next u_{-1}.  mpc.py:271-336."""

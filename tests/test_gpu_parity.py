@@ -56,6 +56,17 @@ def test_first_solve_vs_golden(MPC, name, fast):
     assert np.max(np.abs(info["x_seq"].ravel() - g["x_seq"])) < 1e-5
     assert np.max(np.abs(info["eps_seq"].ravel() - g["eps_seq"])) < 1e-5
     assert abs(info["obj_val"] - (float(g["obj"]) + float(g["J_CNST"]))) < 1e-6 * (1 + abs(float(g["obj"])))
+    # the OSQP result object the reference reads (mpc.py:302-327): res.x in the reference's variable order, res.info.*
+    z = np.concatenate([g["x_seq"], g["u_seq"], g["eps_seq"]])
+    assert K.res.x.shape == z.shape and np.max(np.abs(K.res.x - z)) < 1e-5
+    assert np.max(np.abs(K.res.x[g["x_seq"].size:g["x_seq"].size + g["u_seq"].size] - g["u_seq"])) < TOL
+    assert abs(K.res.info.obj_val - float(g["obj"])) < 1e-6 * (1 + abs(float(g["obj"])))
+    assert K.res.info.status == "solved" and K.res.info.status_val == 1 and isinstance(K.res.info.iter, int) and K.res.info.iter >= 0
+    # lazily fetched fields live on the device only until the next solve: an older `res` says so instead of returning new data
+    K.update(np.array(cfg["x0"], float), np.array(cfg["uminus1"], float)); old = K.res
+    K.update(np.array(cfg["x0"], float), np.array(cfg["uminus1"], float))
+    with pytest.raises(Exception, match="earlier solve"):
+        old.info.obj_val
     K.close()
 
 
@@ -291,6 +302,51 @@ def test_batched_state_estimator_vs_oracle(MPC):
     assert np.max(np.abs(u_dev - u_host)) < 1e-9
     Ka.close()
     K.close(); E.close()
+
+
+def test_estimator_controller_chain_on_device_without_host_reads(MPC):
+    """estimate -> update_from_device (deferred solve) -> u0 (device) -> predict_device -> update_device -> ... with NO host read
+    in between: LinearStateEstimator.attach() puts both on one stream and retires the controller's deferred solve before its
+    output buffer is consumed.  Compared after 6 steps with the same chain driven through host arrays."""
+    import torch
+    from pympc_b200.kalman import LinearStateEstimator
+    cfg = pendulum(); rng = np.random.default_rng(17); B = 4096
+    A, Bm = cfg["Ad"], cfg["Bd"]; C = np.array([[1.0, 0, 0, 0], [0, 0, 1.0, 0]]); D = np.zeros((2, 1))
+    Lg = 0.1 * rng.standard_normal((4, 2))
+    X0, Xref = pendulum_random(B, seed=2)
+    Ys = 0.05 * rng.standard_normal((6, B, 2))
+    kw = {k: cfg[k] for k in ("Qx", "QxN", "Qu", "QDu", "xmin", "xmax", "umin", "umax", "Dumin", "Dumax", "eps_feas")}
+    # host-driven chain
+    Eh = LinearStateEstimator(X0, A, Bm, C, D, Lg, batch=B)
+    Kh = MPC(cfg["Ad"], cfg["Bd"], Np=20, x0=X0, xref=Xref, uminus1=np.zeros(1), batch=B, **kw); Kh.setup(); U = Kh.output()
+    for t in range(6):
+        Eh.predict(U); x = Eh.update(Ys[t] + Eh.y)
+        Kh.update(x); U = Kh.output()
+    # device chain
+    Ed = LinearStateEstimator(X0, A, Bm, C, D, Lg, batch=B)
+    Kd = MPC(cfg["Ad"], cfg["Bd"], Np=20, x0=X0, xref=Xref, uminus1=np.zeros(1), batch=B, **kw); Kd.setup(); Kd.output()
+    Ed.attach(Kd)
+    Ud = torch.zeros(B, 1, dtype=torch.float64, device="cuda")
+    Yd = torch.zeros(B, 2, dtype=torch.float64, device="cuda")
+    Ud.copy_(torch.from_numpy(Kd._u0.copy()))
+    torch.cuda.synchronize()
+    Lb, h = Kd._L, Kd.handle
+    assert Lb.bmpc_bind_output(h, Ud.data_ptr()) == 0
+    Yhost = np.empty((B, 2))
+    for t in range(6):
+        assert Ed.predict_device(Ud.data_ptr()) == 0
+        # measurement = predicted output + noise: needs y on the host only to BUILD the synthetic measurement (test harness)
+        Lb.bmpc_est_get(Ed._h, None, Yhost.ctypes.data_as(__import__("ctypes").c_void_p))
+        Yd.copy_(torch.from_numpy(Ys[t] + Yhost)); torch.cuda.synchronize()
+        assert Ed.update_device(Yd.data_ptr()) == 0
+        assert Lb.bmpc_update(h, Ed.device_state(), None, None, 1, 1) == 0       # x from the estimator, u_-1 = committed output
+        assert Lb.bmpc_solve(h) == 0                                              # deferred: returns with the round in flight
+        assert Lb.bmpc_output(h, None, None, 1, 1) == 0
+    torch.cuda.synchronize()
+    assert np.max(np.abs(Ud.cpu().numpy() - U)) < 1e-9
+    assert np.max(np.abs(Ed.x - Eh.x)) < 1e-10
+    for o in (Eh, Ed, Kh, Kd):
+        o.close()
 
 
 def test_per_instance_systems_vs_oracle(MPC):

@@ -129,3 +129,19 @@ def test_batch_cpu_driver_matches_single(osqp_port_lib):
     U, st, it = bc.step(X0, Um1, Xref, nthreads=2)
     assert np.all(st == 1) and np.max(np.abs(U - g["u"][0])) < 1e-6
     bc.close()
+
+
+@pytest.mark.parametrize("name", ["pm", "pend", "mimo"])
+def test_goldens_vs_independent_ldp_solver(name):
+    """the goldens (oracle/kkt.py: ADMM -> active set on the reference-form QP) against an algorithmically independent exact
+    solver: condensed QP with explicit slack as a least-distance problem solved by ONE Lawson-Hanson NNLS (oracle/ldp.py)"""
+    from oracle.ldp import solve_mpc
+    cfg = {"pm": point_mass, "pend": pendulum, "mimo": mimo}[name](); g = golden(f"{name}_first.npz")
+    assert np.max(np.abs(solve_mpc(QPData(**cfg)) - g["u_seq"])) < 1e-9
+    if name == "mimo":
+        return
+    gl = golden(f"{name}_loop.npz"); x = np.array(cfg["x0"], float); u = np.array(cfg["uminus1"], float)
+    for t in range(10):
+        c = dict(cfg); c["x0"] = x; c["uminus1"] = u
+        assert abs(solve_mpc(QPData(**c))[0] - gl["u"][t][0]) < 1e-9, t
+        u = gl["u"][t]; x = cfg["Ad"] @ x + cfg["Bd"] @ u

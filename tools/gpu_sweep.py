@@ -46,7 +46,7 @@ def run_one(spec, steps, warmup, B):
         flush.zero_()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        L.bmpc_update(h, Xd.data_ptr(), Uloc.data_ptr(), None, 1, 1)
+        L.bmpc_update(h, Xd.data_ptr(), Uloc.data_ptr(), None, 1, int(os.environ.get('SWEEP_ONDEV', '1')))
         assert L.bmpc_solve(h) == 0
         L.bmpc_output(h, None, None, 1, 1)
         e1.record(stream)
