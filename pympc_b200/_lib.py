@@ -17,7 +17,7 @@ DP = ctypes.c_void_p
 class BmpcConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
                 ("nx", "nu", "Np", "Nc", "batch", "device", "soft_on", "max_iter", "first_iters", "pdas_steps",
-                 "rmax", "polish", "team_threads", "warps_per_block", "fast_path", "n_sys", "shift_warm")] + \
+                 "rmax", "polish", "team_threads", "warps_per_block", "fast_path", "n_sys", "shift_warm", "candidate_warm")] + \
                [(n, ctypes.c_double) for n in ("eps_feas", "rho", "sigma", "alpha", "eps_abs", "eps_rel")]
 
 

@@ -20,6 +20,12 @@
 #include "bmpc_tpi.cuh"
 #include "bmpc_tile.cuh"
 
+// One block of round counters = BMPC_CNT ints (the handle keeps two, used alternately): [0] instances still unfinished (-> next list),
+// [1] active-set refinements, [2] overflow of the small polish tier, [3] certified infeasible, [4..7] queue control of k_tpi_pol
+// (cursor, head, and one 64-bit word: low = reserved queue tail, high = finished chunks), [8] instances that left as "solved,
+// unpolished" on tight ADMM residuals.
+enum { TPI_Q_CURSOR = 4, TPI_Q_HEAD = 5, TPI_Q_TAIL = 6, BMPC_CNT_TIGHT = 8, BMPC_CNT = 16 };
+
 // ------------------------------------------------------------------------------------------------
 // teams
 struct WarpTeam {
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(NS >= 4 ? 768 : 512) k_admm_tile(BmpcDims d, B
 template <bool WARP>
 __global__ void k_polish(BmpcDims d, BmpcSysOff o, const double* __restrict__ sys, BmpcInst I, const int32_t* __restrict__ list,
                          int count, int rmax, int max_steps, int32_t* next_list, int32_t* next_count, double* u0_out,
-                         const int32_t* dev_count, int32_t* ovf_list) {
+                         const int32_t* dev_count, int32_t* ovf_list, int cand_warm) {
     extern __shared__ double smem[];
     __shared__ double sd[32];
     __shared__ int si[32];
@@ -311,10 +317,27 @@ __global__ void k_polish(BmpcDims d, BmpcSysOff o, const double* __restrict__ sy
             // working set larger than this tier's capacity: hand the instance to the large-capacity launch that follows
             if (t.tid == 0) { int pos = atomicAdd(next_count + 2, 1); ovf_list[pos] = inst; }
         } else {
+            // not verified.  (a) ADMM residuals far below any tolerance: the iterate is the answer to ~1e-8 although the active-set
+            // iteration cannot certify it (degenerate vertex): "solved" like OSQP would say, no more rounds.  (b) otherwise, if the
+            // last candidate is sane (hard rows feasible to 1e-2), its rows and multipliers become the ADMM state of the next
+            // round: a strongly violated soft row carries the multiplier eps_feas * d, which ADMM alone builds in eps_feas d / rho steps
+            const double* resg = I.res + (size_t)inst * 4;
+            const bool tight = bmpc_residuals_tight(resg) && I.iters[inst] >= 25;
+            if (tight) {
+                for (int a = t.tid; a < d.NU; a += t.n) {
+                    const double ua = I.Ua[(size_t)inst * d.NU + a];
+                    I.Us[(size_t)inst * d.NU + a] = ua;
+                    if (a < d.nu) bmpc_publish_u0(I, u0_out, (size_t)inst * d.nu + a, ua);
+                }
+            } else if (ps == 0 && cand_warm && bmpc_candidate_usable(t, d, o, sys, um1, zz, murow)) {
+                const int lvl = I.lvl[inst];
+                bmpc_warm_from_candidate(t, d, o, sys, zz, murow, U, I.xw + (size_t)inst * d.NU, I.vw + (size_t)inst * d.mc, lvl);
+            }
             if (t.tid == 0) {
                 int used = (ps < 0 ? 1 : max_steps);
                 I.psteps[inst] += used; atomicAdd(next_count + 1, used);
-                if (I.status[inst] != BMPC_PRIMAL_INFEASIBLE) { int pos = atomicAdd(next_count, 1); next_list[pos] = inst; }   // a certified instance is finished
+                if (tight) { I.status[inst] = BMPC_SOLVED_UNPOLISHED; atomicAdd(next_count + BMPC_CNT_TIGHT, 1); }
+                else if (I.status[inst] != BMPC_PRIMAL_INFEASIBLE) { int pos = atomicAdd(next_count, 1); next_list[pos] = inst; }   // a certified instance is finished
             }
         }
     };
@@ -486,7 +509,7 @@ __global__ void __launch_bounds__(32) k_tpi_admm(const __grid_constant__ TpiAdmm
 #pragma unroll
             for (int q = 0; q < S::nu; q++) um1_solved[(size_t)inst * S::nu + q] = um1[q];
         }
-        if (blockIdx.x == 0 && lane < 8) counts[lane] = 0;        // (the polish launch behind this one zeroes the other half)
+        if (blockIdx.x == 0 && lane < BMPC_CNT) counts[lane] = 0;        // (the polish launch behind this one zeroes the other half)
     }
     // g' (read once per iteration) lives in the instance's global scratch row I.g, not in shared memory: the column is
     // MT rows instead of MT + NU, which lets one more warp reside per SM (measured: ADMM kernel 12 % faster)
@@ -534,9 +557,9 @@ struct TpiPolArgs {
     int32_t* next_list; int32_t* counts; // counts[0] unfinished (-> next_list), [1] refinements; counts[4..7] queue control, see below
     int32_t* queue; int qcap;            // phase-B queue (capacity qcap), all -1 between launches (consumers clear what they take)
     double* u0_out; double* um1_solved;
+    int cand_warm;                       // 1: an unverified instance hands its last candidate to the ADMM rounds when that candidate is sane
     unsigned char* codes; int code_stride;   // per instance: Np working-set codes + the multiplier scale (double) of the last refinement
 };
-enum { TPI_Q_CURSOR = 4, TPI_Q_HEAD = 5, TPI_Q_TAIL = 6 };   // counts[6..7]: one 64-bit word, low = reserved queue tail, high = finished chunks
 constexpr int TPI_POL_WARPS = 7;
 
 template <class S>
@@ -554,7 +577,8 @@ struct TpiPolLayout {
 // one batch of up to 32 instances (one per lane) through up to cap refinements; returns the mask of verified lanes
 template <class S, bool TV>
 __device__ __forceinline__ void tpi_pol_batch(const TpiPolParams<S>& P, const BmpcInst& I, const TpiPolArgs& A, double* wsm, typename TpiCode<S>::type* csm,
-                                              int inst, bool valid, int inst0_contig, int nvalid, int mode, int cap, bool to_queue, int reset) {
+                                              int inst, bool valid_in, int inst0_contig, int nvalid, int mode, int cap, bool to_queue, int reset) {
+    bool valid = valid_in;
     using L = TpiPolLayout<S>; using CT = typename TpiCode<S>::type;
     constexpr int nx = S::nx;
     const int lane = threadIdx.x & 31;
@@ -589,6 +613,17 @@ __device__ __forceinline__ void tpi_pol_batch(const TpiPolParams<S>& P, const Bm
     double* udst = I.Us + (size_t)inst * S::NU;
     double u_first = 0.0;
     bool done = !valid, ok = false;
+    if (mode == 2 && A.list != nullptr && !reset && valid) {
+        // straggler round (an ADMM chunk of the team kernels ran just before): residuals far below any tolerance end the instance
+        // as "solved, unpolished" — its iterate is the answer although the active-set iteration cannot certify it (bmpc_residuals_tight)
+        if (bmpc_residuals_tight(I.res + (size_t)inst * 4) && I.iters[inst] >= 25) {
+            const double* ua = I.Ua + (size_t)inst * S::NU;
+            for (int j = 0; j < S::NU; j++) udst[j] = ua[j];
+            bmpc_publish_u0(I, A.u0_out, (size_t)inst, ua[0]);
+            I.status[inst] = BMPC_SOLVED_UNPOLISHED; atomicAdd(A.counts + BMPC_CNT_TIGHT, 1);
+            done = true; valid = false;
+        }
+    }
     int used = 0;
     for (int r = 0; r < cap; r++) {
         if (!done) {
@@ -641,7 +676,26 @@ __device__ __forceinline__ void tpi_pol_batch(const TpiPolParams<S>& P, const Bm
         int basep = 0;
         if (lane == 0) basep = atomicAdd(A.counts, nf);
         basep = __shfl_sync(0xffffffffu, basep, 0);
-        if (fail) A.next_list[basep + pos] = inst;     // its ADMM rounds start from the exact fixed point v* of its last verified solve
+        if (fail) {
+            A.next_list[basep + pos] = inst;
+            // its ADMM rounds start from the exact fixed point v* of its last verified solve, unless the last candidate is sane (hard
+            // rows feasible to 1e-2): then from the candidate's rows and multipliers v = z + mu / rho (bmpc_candidate_usable's policy)
+            bool usable = A.cand_warm != 0;
+            double up = um1;
+            for (int j = 0; j < S::NU && usable; j++) {
+                const double u = udst[j], dz = u - up;
+                usable = u <= P.uhi + 1e-2 * (1.0 + fabs(P.uhi)) && u >= P.ulo - 1e-2 * (1.0 + fabs(P.ulo)) &&
+                         dz <= P.dhi + 1e-2 * (1.0 + fabs(P.dhi)) && dz >= P.dlo - 1e-2 * (1.0 + fabs(P.dlo));
+                up = u;
+            }
+            if (usable) {
+                double* dst = I.vw + (size_t)inst * S::mc;
+                for (int i = 0; i < L::VROWS; i++) dst[nx + i] = W(tpi_vstar_slot<S>(i));
+                dst[S::mc - 1] = vq;
+#pragma unroll
+                for (int q = 0; q < nx; q++) dst[q] = x0[q];
+            }
+        }
     }
     // v* = z* + y*/rho, the exact ADMM fixed point of this problem, staged in the consumed gain slots by the forward sweep: the
     // warm start of the ADMM rounds a later solve may need for this instance (measured: starting those rounds from the failed
@@ -700,7 +754,7 @@ __global__ void __launch_bounds__(TPI_POL_WARPS * 32, 1) k_tpi_pol(const __grid_
     double* wsm = (double*)((char*)smem + (size_t)warp * L::per_warp);
     CT* csm = (CT*)((char*)wsm + L::gain_bytes);
     const int nchunks = (A.count + 31) / 32;
-    if (blockIdx.x == 0 && threadIdx.x < 8) A.counts_next[threadIdx.x] = 0;
+    if (blockIdx.x == 0 && threadIdx.x < BMPC_CNT) A.counts_next[threadIdx.x] = 0;
     // ---- phase A
     for (;;) {
         int chunk = 0;
@@ -786,7 +840,7 @@ struct bmpc_handle {
     double* vprev = nullptr; int32_t* lprev = nullptr;   // snapshot of (v, level) for the infeasibility check of straggler rounds
     void (*tile_fn[3])(BmpcDims, BmpcSysOff, const double*, BmpcInst, const int32_t*, int, int, int, int, int, int) = {nullptr, nullptr, nullptr};
     int tile_T = 0, tile_threads = 0;                  // > 0: the ADMM of this shape runs on tiles of T instances per CTA
-    struct { const int32_t* list; int count; int32_t *cur, *nxt; int total, chunk, round; bool need_prep; } st = {};
+    struct { const int32_t* list; int count; int32_t *cur, *nxt; int total, chunk, round; bool need_prep; int tight; } st = {};
     bool pending = false;              // a round is in flight and has not been retired by the host yet
     int tpi_kind = 0;                  // 0 none, else 1 + index into g_tpi_table (compiled fast-path shapes)
     void *tpi_admm_params = nullptr, *tpi_polish_params = nullptr;   // host copies of the parameter blocks
@@ -810,8 +864,8 @@ static void launch_tpi_pol(bmpc_handle* h, const int32_t* list, int count, int m
     const TpiPolParams<S>& PP = *(const TpiPolParams<S>*)h->tpi_polish_params;
     TpiPolArgs A;
     A.list = list; A.count = count; A.mode = mode; A.capA = capA; A.capB = capB; A.reset = reset;
-    A.next_list = next_list; A.counts = h->counts + 8 * h->cpar; A.counts_next = h->counts + 8 * (1 - h->cpar); A.queue = h->queue; A.qcap = h->cfg.batch; A.u0_out = h->I.u0; A.um1_solved = h->um1_solved;
-    A.codes = h->codes; A.code_stride = L::code_stride;
+    A.next_list = next_list; A.counts = h->counts + BMPC_CNT * h->cpar; A.counts_next = h->counts + BMPC_CNT * (1 - h->cpar); A.queue = h->queue; A.qcap = h->cfg.batch; A.u0_out = h->I.u0; A.um1_solved = h->um1_solved;
+    A.codes = h->codes; A.code_stride = L::code_stride; A.cand_warm = h->cfg.candidate_warm;
     const int nchunks = (count + 31) / 32;
     int grid = (nchunks + TPI_POL_WARPS - 1) / TPI_POL_WARPS;
     if (grid > h->sm_count) grid = h->sm_count;
@@ -834,9 +888,9 @@ static void launch_tpi_round(bmpc_handle* h, const int32_t* list, int count, int
     const int capA = 1, capB = h->tpi_pdas_steps - 1;
     if (niter > 0) {
         if (h->xref_mode)   // one (Np+1) x nx reference per instance
-            k_tpi_admm<S, true><<<grid, 32, sa, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts + 8 * h->cpar, h->um1_solved);
+            k_tpi_admm<S, true><<<grid, 32, sa, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts + BMPC_CNT * h->cpar, h->um1_solved);
         else
-            k_tpi_admm<S, false><<<grid, 32, sa, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts + 8 * h->cpar, h->um1_solved);
+            k_tpi_admm<S, false><<<grid, 32, sa, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts + BMPC_CNT * h->cpar, h->um1_solved);
         h->stats.launches++;
         cudaEventRecord(mid, h->stream);
         launch_tpi_pol<S>(h, list, count, 2, capA, capB, 0, next_list);
@@ -885,7 +939,7 @@ void bmpc_default_config(bmpc_config* c) {
     memset(c, 0, sizeof(*c));
     c->Np = 20; c->Nc = 0; c->batch = 1; c->device = 0; c->soft_on = 1;
     c->max_iter = 4000; c->first_iters = 0; c->pdas_steps = 10; c->rmax = 0; c->polish = 1;
-    c->team_threads = 0; c->warps_per_block = 0; c->fast_path = 1; c->n_sys = 1; c->shift_warm = 1;
+    c->team_threads = 0; c->warps_per_block = 0; c->fast_path = 1; c->n_sys = 1; c->shift_warm = 1; c->candidate_warm = 1;
     c->eps_feas = 1e6; c->rho = 0.0; c->sigma = 1e-6; c->alpha = 1.6; c->eps_abs = 1e-3; c->eps_rel = 1e-3;
 }
 
@@ -1021,14 +1075,14 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     ok &= dalloc((void**)&h->I.lvl, sizeof(int32_t) * B);
     ok &= dalloc((void**)&h->listA, sizeof(int32_t) * B);
     ok &= dalloc((void**)&h->listB, sizeof(int32_t) * B);
-    ok &= dalloc((void**)&h->counts, sizeof(int32_t) * 16);
+    ok &= dalloc((void**)&h->counts, sizeof(int32_t) * 2 * BMPC_CNT);
     ok &= dalloc((void**)&h->queue, sizeof(int32_t) * B);
     ok &= dalloc((void**)&h->codes, (size_t)B * 72);       // largest record: 32 stages x 2 bytes + 8 (Np < 32 on the fast path)
     ok &= dalloc((void**)&h->ovf, sizeof(int32_t) * (size_t)B);
     ok &= dalloc((void**)&h->vprev, sizeof(double) * (size_t)B * d.mc);
     ok &= dalloc((void**)&h->lprev, sizeof(int32_t) * (size_t)B);
     if (!ok) { h->err = "cudaMalloc failed"; cudaGetLastError(); return fail(BMPC_ERR_CUDA); }
-    if (cudaHostAlloc((void**)&h->h_count, sizeof(int32_t) * 4, cudaHostAllocDefault) != cudaSuccess) { h->err = "cudaHostAlloc failed"; return fail(BMPC_ERR_CUDA); }
+    if (cudaHostAlloc((void**)&h->h_count, sizeof(int32_t) * BMPC_CNT, cudaHostAllocDefault) != cudaSuccess) { h->err = "cudaHostAlloc failed"; return fail(BMPC_ERR_CUDA); }
     cudaMemset(h->sys, 0, sizeof(double) * (size_t)h->o.total * h->cfg.n_sys);
     cudaMemset(h->x0, 0, sizeof(double) * B * d.nx);
     cudaMemset(h->um1, 0, sizeof(double) * B * d.nu);
@@ -1038,7 +1092,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     cudaMemset(h->I.Ua, 0, sizeof(double) * B * d.NU);
     cudaMemset(h->queue, 0xff, sizeof(int32_t) * B);
     cudaMemset(h->codes, 0, (size_t)B * 72);
-    cudaMemset(h->counts, 0, sizeof(int32_t) * 16);
+    cudaMemset(h->counts, 0, sizeof(int32_t) * 2 * BMPC_CNT);
     cudaMemset(h->um1_alt, 0, sizeof(double) * B * d.nu);
     h->I.sys_stride = h->cfg.n_sys > 1 ? (size_t)h->o.total : 0;
     h->I.x0 = h->x0; h->I.um1 = h->um1; h->I.um1_solved = h->um1_solved; h->I.xref = h->xref; h->I.u0 = h->u0_own; h->I.u0_shadow = h->um1_alt;
@@ -1226,18 +1280,18 @@ static void launch_admm(bmpc_handle* h, const int32_t* list, int count, int nite
 
 static void launch_polish(bmpc_handle* h, const int32_t* list, int count, int32_t* next_list, int32_t* next_count) {
     if (use_fallback_team(h, list, count)) {
-        k_polish<false><<<count, h->fb_team, h->fb_smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->fb_rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0, nullptr, nullptr);
+        k_polish<false><<<count, h->fb_team, h->fb_smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->fb_rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0, nullptr, nullptr, h->cfg.candidate_warm);
     } else if (h->team == 32) {
         int grid = (count + h->wpb - 1) / h->wpb;
-        k_polish<true><<<grid, h->wpb * 32, h->smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0, nullptr, nullptr);
+        k_polish<true><<<grid, h->wpb * 32, h->smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0, nullptr, nullptr, h->cfg.candidate_warm);
     } else if (h->rmax_small > 0) {
         // two capacity tiers: the small one keeps several CTAs resident per SM (the polish is latency-bound); working
         // sets that outgrow it are listed and redone by the full-capacity launch right after (count read on the device)
-        k_polish<false><<<count, h->team, h->smem_polish_small, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->rmax_small, h->cfg.pdas_steps, next_list, next_count, h->I.u0, nullptr, h->ovf);
-        k_polish<false><<<count, h->team, h->smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, h->ovf, count, h->rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0, next_count + 2, nullptr);
+        k_polish<false><<<count, h->team, h->smem_polish_small, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->rmax_small, h->cfg.pdas_steps, next_list, next_count, h->I.u0, nullptr, h->ovf, h->cfg.candidate_warm);
+        k_polish<false><<<count, h->team, h->smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, h->ovf, count, h->rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0, next_count + 2, nullptr, h->cfg.candidate_warm);
         h->stats.launches++;
     } else {
-        k_polish<false><<<count, h->team, h->smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0, nullptr, nullptr);
+        k_polish<false><<<count, h->team, h->smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0, nullptr, nullptr, h->cfg.candidate_warm);
     }
     h->stats.launches++;
 }
@@ -1255,7 +1309,7 @@ static int enqueue_round(bmpc_handle* h) {
     // straggler rounds read u_-1 from the snapshot the first round took: bmpc_output may already have queued the commit of
     // this solve's u0 into um1 (speculating that the first round finishes everything)
     h->cpar ^= 1;                                        // counters of this round: the half the previous round left zeroed
-    int32_t* cnt = h->counts + 8 * h->cpar;
+    int32_t* cnt = h->counts + BMPC_CNT * h->cpar;
     h->I.um1 = st.round > 0 ? h->um1_solved : h->um1_cur;
     h->I.x0 = h->x0_cur; h->I.u0_shadow = h->um1_alt;
     if (!tpi) {
@@ -1265,7 +1319,7 @@ static int enqueue_round(bmpc_handle* h) {
             h->stats.launches++;
             BMPC_CUDA(cudaMemcpyAsync(h->um1_solved, h->um1_cur, sizeof(double) * (size_t)B * h->d.nu, cudaMemcpyDeviceToDevice, h->stream));
         }
-        BMPC_CUDA(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 16, h->stream));     // this round's half and the next one's
+        BMPC_CUDA(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 2 * BMPC_CNT, h->stream));     // this round's half and the next one's
     }
     BMPC_CUDA(cudaEventRecord(h->ev[0], h->stream));
     if (tpi) {
@@ -1289,7 +1343,7 @@ static int enqueue_round(bmpc_handle* h) {
     }
     h->I.um1 = h->um1_cur;
     BMPC_CUDA(cudaEventRecord(h->ev[2], h->stream));
-    BMPC_CUDA(cudaMemcpyAsync(h->h_count, cnt, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, h->stream));
+    BMPC_CUDA(cudaMemcpyAsync(h->h_count, cnt, sizeof(int32_t) * BMPC_CNT, cudaMemcpyDeviceToHost, h->stream));
     BMPC_CUDA(cudaGetLastError());
     return BMPC_OK;
 }
@@ -1307,6 +1361,7 @@ static int retire_round(bmpc_handle* h, int* more) {
     st.count = h->h_count[0];
     h->stats.polish_steps += h->h_count[1];
     h->stats.infeasible += h->h_count[3];
+    st.tight += h->h_count[BMPC_CNT_TIGHT];
     st.list = st.nxt; int32_t* tmp = st.cur; st.cur = st.nxt; st.nxt = tmp;
     // polish mode: cumulative first_iters, 25, 50, 100, ...; pure ADMM: OSQP's check_termination = 25
     st.chunk = h->cfg.polish ? (st.total < 25 ? 25 - st.total : st.total) : 25;
@@ -1322,7 +1377,7 @@ static int retire_round(bmpc_handle* h, int* more) {
         h->stats.launches++;
     }
     BMPC_CUDA(cudaGetLastError());
-    h->stats.rounds = st.round; h->stats.unsolved = h->cfg.polish ? st.count : -1;
+    h->stats.rounds = st.round; h->stats.unsolved = h->cfg.polish ? st.count + st.tight : -1;   // not KKT-verified: status 2 or -2
     h->pending = false;
     return BMPC_OK;
 }
@@ -1341,7 +1396,7 @@ int bmpc_solve(bmpc_handle* h) {
     memset(&h->stats, 0, sizeof(h->stats));
     auto& st = h->st;
     st.list = nullptr; st.count = B; st.cur = h->listA; st.nxt = h->listB;
-    st.total = 0; st.round = 0; st.need_prep = true;
+    st.total = 0; st.round = 0; st.need_prep = true; st.tight = 0;
     // first round: NO ADMM iterations on a warm fast-path solve (the previous solution's working sets are the best first guess
     // the active-set polish can get: measured 0 vs 1..10 iterations), 10 on the team kernels; first_iters > 0 overrides
     const bool fast = h->tpi_kind != 0;

@@ -602,6 +602,41 @@ BMPC_HD int bmpc_adapt_level(Team& t, const BmpcDims& d, const BmpcSysOff& o, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// What to do with a polish candidate that did not verify (the active-set iteration cycles on degenerate vertices).
+// Its multipliers are still worth a lot to ADMM when a soft row is strongly violated: the row's multiplier eps_feas * d
+// would otherwise be built in steps of rho * residual (eps_feas * d / rho iterations; the reference's OSQP path, with
+// explicit slack and equilibration, needs ~700).  Policy (DESIGN.md section 7, round-1 host study): take the candidate as
+// the new ADMM state v = zz + mu / rho only if its hard rows are feasible to 1e-2 (relative) — a wild candidate is
+// worse than the iterate it would replace.
+template <class Team>
+BMPC_HD bool bmpc_candidate_usable(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, const double* um1,
+                                   const double* zz, const double* murow) {
+    const double *lo0 = sys + o.lo0, *hi0 = sys + o.hi0;
+    const bool soft_on = sys[o.scal + BMPC_S_RHOE] > 0.0;
+    bool ok = true;
+    for (int i = t.tid; i < d.mc; i += t.n) {
+        if (soft_on && i < d.NX) continue;
+        double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
+        const double zi = zz[i];
+        if (zi > hi + 1e-2 * (1.0 + fabs(hi)) || zi < lo - 1e-2 * (1.0 + fabs(lo)) || !(fabs(murow[i]) < 1e300)) ok = false;
+    }
+    return t.all(ok);
+}
+template <class Team>
+BMPC_HD void bmpc_warm_from_candidate(Team& t, const BmpcDims& d, const BmpcSysOff& o, const double* sys, const double* zz,
+                                      const double* murow, const double* U, double* x, double* v, int lvl) {
+    const double* rhov = sys + o.rho; const double fac = bmpc_level_factor(lvl);
+    for (int i = t.tid; i < d.mc; i += t.n) v[i] = zz[i] + murow[i] / (fac * rhov[i]);
+    for (int a = t.tid; a < d.NU; a += t.n) x[a] = U[a];
+    t.sync();
+}
+// ADMM residuals far below any tolerance a caller can ask for: the iterate IS the solution to ~1e-8 even if the polish cannot
+// certify it (degenerate vertex): stop iterating, status "solved" (unpolished).  res as written by bmpc_admm.
+BMPC_HD bool bmpc_residuals_tight(const double* res) {
+    return res[0] <= 1e-9 * (1.0 + res[2]) && res[1] <= 1e-9 * (1.0 + res[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Primal infeasibility (OSQP paper 3.4) from two ADMM states (v0 on ladder level lvl0, v1 on lvl1) of the same problem:
 // dy = y1 - y0 on the hard rows (soft rows are penalties, not constraints), projected on the polar of the recession cone
 // of the row box like OSQP does; a certificate needs  ||A' dy|| < eps ||dy||  and a negative support function

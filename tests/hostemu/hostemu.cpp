@@ -60,10 +60,13 @@ int emu_solve(int nx, int nu, int Np, int Nc, const double* sys, const double* x
             for (int i = 0; i < d.mc; i++) v[i] = zz[i] + murow[i] / rhov[i];
             break;
         }
+        // the device policy for unverified candidates (bmpc_warm_from_candidate / early exit), mirrored here
+        if (!getenv("EMU_NOWARM") && ps == 0 && (getenv("EMU_ALWAYS") || bmpc_candidate_usable(t, d, o, sys, um1, zz, murow))) bmpc_warm_from_candidate(t, d, o, sys, zz, murow, U, x, v, lvl);
+        if (!getenv("EMU_NOTIGHT") && bmpc_residuals_tight(res)) { status = 2; for (int a = 0; a < d.NU; a++) Uout[a] = xt[a]; break; }
         psteps += pdas_steps;
         chunk = total < 25 ? 25 - total : total;   // 10, 15, 25, 50, 100, ...
     }
-    if (status != 1) {
+    if (status != 1 && status != 2) {
         bool conv = res[0] <= eps_abs + eps_rel * res[2] && res[1] <= eps_abs + eps_rel * res[3];
         status = conv ? 2 : -2;
         for (int a = 0; a < d.NU; a++) Uout[a] = xt[a];
