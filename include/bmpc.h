@@ -155,6 +155,8 @@ int bmpc_est_attach(bmpc_estimator* e, bmpc_handle* h);
 /* pinned host memory for the end-to-end path (cudaHostAlloc / cudaFreeHost) */
 void* bmpc_host_alloc(uint64_t bytes);
 void bmpc_host_free(void* p);
+/* 1 if this build of the library holds the thread-per-instance fast path for the shape (nu == 1; Nc <= 0 means Nc = Np) */
+int bmpc_has_fast_path(int nx, int nu, int Np, int Nc);
 /* number of visible CUDA devices (0 if none / driver missing) */
 int bmpc_device_count(void);
 

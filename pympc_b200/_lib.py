@@ -31,7 +31,7 @@ EXPORTS = ["bmpc_default_config", "bmpc_create", "bmpc_destroy", "bmpc_last_erro
            "bmpc_solve", "bmpc_output", "bmpc_get_sequences", "bmpc_bind_output", "bmpc_bind_output_peers", "bmpc_bind_gather_flags",
            "bmpc_gather_arrive", "bmpc_set_stream",
            "bmpc_synchronize", "bmpc_get_stats", "bmpc_get_sys", "bmpc_get_dims", "bmpc_host_alloc",
-           "bmpc_host_free", "bmpc_device_count", "bmpc_est_create", "bmpc_est_destroy", "bmpc_est_predict",
+           "bmpc_host_free", "bmpc_device_count", "bmpc_has_fast_path", "bmpc_est_create", "bmpc_est_destroy", "bmpc_est_predict",
            "bmpc_est_update", "bmpc_est_get", "bmpc_est_state_ptr", "bmpc_est_set_stream", "bmpc_est_attach"]
 
 
@@ -39,15 +39,20 @@ class BmpcError(RuntimeError):
     pass
 
 
-def load():
-    """Load libbmpc.so; raises BmpcError if it has not been built (run ``python -m pympc_b200.build``)."""
+_libs = {}
+
+
+def load(path=None):
+    """Load libbmpc.so (or, with `path`, a per-shape build of it made by pympc_b200.build.jit_shape); raises BmpcError if it has
+    not been built (run ``python -m pympc_b200.build``)."""
     global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise BmpcError(f"{LIB_PATH} not found: build the CUDA extension first (python -m pympc_b200.build). "
+    path = os.path.abspath(path or LIB_PATH)
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise BmpcError(f"{path} not found: build the CUDA extension first (python -m pympc_b200.build). "
                         "pympc_b200 has no CPU fallback.")
-    L = ctypes.CDLL(LIB_PATH)
+    L = ctypes.CDLL(path)
     L.bmpc_default_config.argtypes = [ctypes.POINTER(BmpcConfig)]; L.bmpc_default_config.restype = None
     L.bmpc_create.argtypes = [ctypes.POINTER(BmpcConfig), ctypes.POINTER(P)]; L.bmpc_create.restype = ctypes.c_int
     L.bmpc_destroy.argtypes = [P]; L.bmpc_destroy.restype = None
@@ -77,7 +82,10 @@ def load():
     L.bmpc_est_state_ptr.argtypes = [P]; L.bmpc_est_state_ptr.restype = P
     L.bmpc_est_set_stream.argtypes = [P, P]; L.bmpc_est_set_stream.restype = ctypes.c_int
     L.bmpc_est_attach.argtypes = [P, P]; L.bmpc_est_attach.restype = ctypes.c_int
-    _lib = L
+    L.bmpc_has_fast_path.argtypes = [ctypes.c_int] * 4; L.bmpc_has_fast_path.restype = ctypes.c_int
+    _libs[path] = L
+    if path == os.path.abspath(LIB_PATH):
+        _lib = L
     return L
 
 

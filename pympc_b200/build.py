@@ -41,6 +41,26 @@ def add_shape(nx, nu, Np, Nc=None):
     return build(force=True)
 
 
+def jit_shape(nx, nu, Np, Nc=None, verbose=False):
+    """Build (once; cached under pympc_b200/_jit/) a copy of the library whose fast-path table holds exactly the shape
+    (nx, 1, Np, Nc) and return its path: lets a controller of ANY single-input shape run on the thread-per-instance kernels
+    without editing csrc/tpi_shapes.inc.  Raises on shapes the fast path cannot hold or when nvcc is not available."""
+    Nc = Np if Nc is None else Nc
+    if nu != 1 or Np * nx > 128 or Np >= 32 or not (1 <= Nc <= Np):
+        raise ValueError("fast-path shapes need nu == 1, Np*nx <= 128, Np < 32, 1 <= Nc <= Np")
+    jdir = os.path.join(_HERE, "_jit"); os.makedirs(jdir, exist_ok=True)
+    tag = f"{nx}_{nu}_{Np}_{Nc}"
+    inc = os.path.join(jdir, f"shape_{tag}.inc"); lib = os.path.join(jdir, f"libbmpc_{tag}.so")
+    if not os.path.exists(inc):
+        open(inc, "w").write(f"BMPC_TPI_SHAPE({nx}, {nu}, {Np}, {Nc})\n")
+    deps = [p for p in DEPS if p != SHAPES]
+    if not os.path.exists(lib) or any(os.path.getmtime(lib) < os.path.getmtime(p) for p in deps):
+        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [f'-DBMPC_TPI_SHAPES_FILE="{inc}"', SRC, "-o", lib + ".tmp"]
+        subprocess.check_call(cmd)
+        os.replace(lib + ".tmp", lib)
+    return lib
+
+
 if __name__ == "__main__":
     import sys
     if len(sys.argv) == 3 and sys.argv[1] == "--add-shape":          # nx,nu,Np[,Nc]

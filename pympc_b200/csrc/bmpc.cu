@@ -322,14 +322,15 @@ __global__ void k_polish(BmpcDims d, BmpcSysOff o, const double* __restrict__ sy
             // last candidate is sane (hard rows feasible to 1e-2), its rows and multipliers become the ADMM state of the next
             // round: a strongly violated soft row carries the multiplier eps_feas * d, which ADMM alone builds in eps_feas d / rho steps
             const double* resg = I.res + (size_t)inst * 4;
-            const bool tight = bmpc_residuals_tight(resg) && I.iters[inst] >= 25;
+            const int itsg = I.iters[inst];
+            const bool tight = bmpc_residuals_tight(resg, itsg);
             if (tight) {
                 for (int a = t.tid; a < d.NU; a += t.n) {
                     const double ua = I.Ua[(size_t)inst * d.NU + a];
                     I.Us[(size_t)inst * d.NU + a] = ua;
                     if (a < d.nu) bmpc_publish_u0(I, u0_out, (size_t)inst * d.nu + a, ua);
                 }
-            } else if (ps == 0 && cand_warm && bmpc_candidate_usable(t, d, o, sys, um1, zz, murow)) {
+            } else if (ps == 0 && cand_warm && bmpc_admm_stalled(resg, itsg) && bmpc_candidate_usable(t, d, o, sys, um1, zz, murow)) {
                 const int lvl = I.lvl[inst];
                 bmpc_warm_from_candidate(t, d, o, sys, zz, murow, U, I.xw + (size_t)inst * d.NU, I.vw + (size_t)inst * d.mc, lvl);
             }
@@ -616,7 +617,7 @@ __device__ __forceinline__ void tpi_pol_batch(const TpiPolParams<S>& P, const Bm
     if (mode == 2 && A.list != nullptr && !reset && valid) {
         // straggler round (an ADMM chunk of the team kernels ran just before): residuals far below any tolerance end the instance
         // as "solved, unpolished" — its iterate is the answer although the active-set iteration cannot certify it (bmpc_residuals_tight)
-        if (bmpc_residuals_tight(I.res + (size_t)inst * 4) && I.iters[inst] >= 25) {
+        if (bmpc_residuals_tight(I.res + (size_t)inst * 4, I.iters[inst])) {
             const double* ua = I.Ua + (size_t)inst * S::NU;
             for (int j = 0; j < S::NU; j++) udst[j] = ua[j];
             bmpc_publish_u0(I, A.u0_out, (size_t)inst, ua[0]);
@@ -680,7 +681,7 @@ __device__ __forceinline__ void tpi_pol_batch(const TpiPolParams<S>& P, const Bm
             A.next_list[basep + pos] = inst;
             // its ADMM rounds start from the exact fixed point v* of its last verified solve, unless the last candidate is sane (hard
             // rows feasible to 1e-2): then from the candidate's rows and multipliers v = z + mu / rho (bmpc_candidate_usable's policy)
-            bool usable = A.cand_warm != 0;
+            bool usable = A.cand_warm != 0 && mode == 2 && A.list != nullptr && bmpc_admm_stalled(I.res + (size_t)inst * 4, I.iters[inst]);   // straggler rounds only
             double up = um1;
             for (int j = 0; j < S::NU && usable; j++) {
                 const double u = udst[j], dz = u - up;
@@ -924,8 +925,13 @@ static int tpi_configure_entry() {
      TpiPolLayout<TpiShape<NX_, NU_, NP_, NC_>>::code_stride,                                                                \
      tpi_fill_entry<TpiShape<NX_, NU_, NP_, NC_>>, tpi_configure_entry<TpiShape<NX_, NU_, NP_, NC_>>,                         \
      launch_tpi_round<TpiShape<NX_, NU_, NP_, NC_>>, launch_tpi_polish_only<TpiShape<NX_, NU_, NP_, NC_>>},
+// BMPC_TPI_SHAPES_FILE: pympc_b200.build.jit_shape() compiles a copy of the library whose table holds the one shape a controller
+// asked for (any nx, Np with nu == 1) when the in-tree table does not have it
+#ifndef BMPC_TPI_SHAPES_FILE
+#define BMPC_TPI_SHAPES_FILE "tpi_shapes.inc"
+#endif
 static const TpiEntry g_tpi_table[] = {
-#include "tpi_shapes.inc"
+#include BMPC_TPI_SHAPES_FILE
 };
 #undef BMPC_TPI_SHAPE
 static const int g_tpi_count = (int)(sizeof(g_tpi_table) / sizeof(g_tpi_table[0]));
@@ -941,6 +947,13 @@ void bmpc_default_config(bmpc_config* c) {
     c->max_iter = 4000; c->first_iters = 0; c->pdas_steps = 10; c->rmax = 0; c->polish = 1;
     c->team_threads = 0; c->warps_per_block = 0; c->fast_path = 1; c->n_sys = 1; c->shift_warm = 1; c->candidate_warm = 1;
     c->eps_feas = 1e6; c->rho = 0.0; c->sigma = 1e-6; c->alpha = 1.6; c->eps_abs = 1e-3; c->eps_rel = 1e-3;
+}
+
+int bmpc_has_fast_path(int nx, int nu, int Np, int Nc) {
+    if (Nc <= 0) Nc = Np;
+    for (int k = 0; k < g_tpi_count; k++)
+        if (g_tpi_table[k].nx == nx && g_tpi_table[k].nu == nu && g_tpi_table[k].Np == Np && g_tpi_table[k].Nc == Nc) return 1;
+    return 0;
 }
 
 int bmpc_device_count(void) {

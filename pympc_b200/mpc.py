@@ -18,6 +18,7 @@ verified), which is what parity at 1e-6 needs; ``eps_abs``/``e
 OSQP's meaning for instances the polish cannot verify, and in ``polish=False`` mode.
 """
 import ctypes
+import os
 import warnings
 
 import numpy as np
@@ -307,6 +308,7 @@ class MPCController:
     # ------------------------------------------------------------------ reference API
     def setup(self, solve=True):
         """Set up the QP (condense + factor on the GPU).  mpc.py:254-269."""
+        self._L = self._pick_library()
         L = self._L
         B, nx, nu = self._B, self.nx, self.nu
         self.x0_rh = np.copy(self.x0)
@@ -359,6 +361,32 @@ class MPCController:
         self._J_dirty = True
         if solve:
             self.solve()
+
+    def _pick_library(self):
+        """The in-tree build, or — for a single-input shape its fast-path table does not hold — a per-shape build made on the spot
+        (pympc_b200.build.jit_shape, cached): every (nx, 1, Np, Nc) runs on the thread-per-instance kernels, like the reference
+        handles every shape uniformly (mpc.py:456-615).  Falls back to the generic team kernels with a warning if that build is
+        not possible (no nvcc on this machine)."""
+        L = _lib.load()
+        opts = self.solver_options
+        wants_fast = opts.get("fast_path", 1) and not opts.get("team_threads", 0) and opts.get("polish", 1) and self.SOFT_ON and not self._per_instance
+        NX, NU = (self.Np + 1) * self.nx, self.Nc * self.nu
+        small = (NX + NU + (self.Nc + 1) * self.nu) <= 192 and NU <= 64          # the library's own rule for the warp-team family
+        if not (wants_fast and self.nu == 1 and small) or L.bmpc_has_fast_path(self.nx, self.nu, self.Np, self.Nc):
+            return L
+        if self.Np * self.nx > 128 or self.Np >= 32:
+            return L
+        if os.environ.get("BMPC_NO_JIT"):
+            warnings.warn(f"no compiled fast path for shape (nx={self.nx}, nu=1, Np={self.Np}, Nc={self.Nc}): running on the generic team "
+                          f"kernels (about 15x slower); add it with  python -m pympc_b200.build --add-shape {self.nx},1,{self.Np},{self.Nc}")
+            return L
+        try:
+            from . import build
+            return _lib.load(build.jit_shape(self.nx, 1, self.Np, self.Nc))
+        except Exception as exc:
+            warnings.warn(f"no compiled fast path for shape (nx={self.nx}, nu=1, Np={self.Np}, Nc={self.Nc}) and building one failed ({exc}): "
+                          "running on the generic team kernels (about 15x slower)")
+            return L
 
     def _push(self, x0, um1, xref):
         B, nx, nu = self._B, self.nx, self.nu

@@ -84,6 +84,16 @@ class EmuSystem:
         self.cold = 0
         return U, ps
 
+    def polish_only(self, x0, um1, xref, pdas_steps=10, rmax=None):
+        """team (Schur) polish alone from self.v; returns (U, refinements) and replaces self.v by v* when verified"""
+        x0 = np.ascontiguousarray(x0, float); um1 = np.ascontiguousarray(um1, float); xref = np.ascontiguousarray(xref, float)
+        mode = 0 if xref.ndim == 1 else 1
+        U = np.zeros(self.NU)
+        f = self.L.emu_polish_only
+        f.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        ps = f(self.nx, self.nu, self.Np, self.Nc, _p(self.sys), _p(x0), _p(um1), _p(xref), mode, _p(self.v), _p(U), pdas_steps, rmax or self.mc)
+        return U, ps
+
     def tpi2_step(self, x0, um1, xref, mode=1, max_ref=8):
         """second-generation Riccati polish on the stored working-set codes (mode 0 as stored, 1 shifted one stage, 2 from v);
         returns (U, refinements used); state: self.codes, self.v, self.mumax."""

@@ -61,8 +61,8 @@ int emu_solve(int nx, int nu, int Np, int Nc, const double* sys, const double* x
             break;
         }
         // the device policy for unverified candidates (bmpc_warm_from_candidate / early exit), mirrored here
-        if (!getenv("EMU_NOWARM") && ps == 0 && (getenv("EMU_ALWAYS") || bmpc_candidate_usable(t, d, o, sys, um1, zz, murow))) bmpc_warm_from_candidate(t, d, o, sys, zz, murow, U, x, v, lvl);
-        if (!getenv("EMU_NOTIGHT") && bmpc_residuals_tight(res)) { status = 2; for (int a = 0; a < d.NU; a++) Uout[a] = xt[a]; break; }
+        if (!getenv("EMU_NOWARM") && ps == 0 && bmpc_admm_stalled(res, total) && (getenv("EMU_ALWAYS") || bmpc_candidate_usable(t, d, o, sys, um1, zz, murow))) bmpc_warm_from_candidate(t, d, o, sys, zz, murow, U, x, v, lvl);
+        if (!getenv("EMU_NOTIGHT") && bmpc_residuals_tight(res, total)) { status = 2; for (int a = 0; a < d.NU; a++) Uout[a] = xt[a]; break; }
         psteps += pdas_steps;
         chunk = total < 25 ? 25 - total : total;   // 10, 15, 25, 50, 100, ...
     }
@@ -131,6 +131,27 @@ extern "C" int emu_tpi_step(int nx, int nu, int Np, int Nc, const double* sys, c
     return -100;
 }
 
+
+// Team (Schur-form) polish alone from a given ADMM state v (e.g. the previous solve's v*): returns refinements used (> 0 verified,
+// 0 not verified, -1 working set beyond rmax); on success U and v (= v*) are written.
+extern "C" int emu_polish_only(int nx, int nu, int Np, int Nc, const double* sys, const double* x0, const double* um1, const double* xref,
+                               int xref_mode, double* v, double* Uout, int pdas_steps, int rmax) {
+    BmpcDims d = bmpc_make_dims(nx, nu, Np, Nc); BmpcSysOff o = bmpc_make_off(d);
+    SeqTeam t;
+    double* buf = (double*)calloc(8 * d.mc + 8 * d.NU + d.NX + rmax * (rmax + 1) / 2 + rmax + 16, sizeof(double));
+    double *g = buf, *cc = g + d.NU, *W0 = cc + d.NX, *zz = W0 + d.mc, *murow = zz + d.mc, *S = murow + d.mc,
+           *tt = S + rmax * (rmax + 1) / 2, *U0 = tt + rmax, *U = U0 + d.NU;
+    int* st = (int*)calloc(d.mc + rmax, sizeof(int)); int* R = st + d.mc;
+    bmpc_prep(t, d, o, sys, x0, um1, xref, xref_mode, g, cc);
+    int ps = bmpc_polish(t, d, o, sys, um1, g, cc, v, W0, zz, murow, st, S, tt, R, U0, U, rmax, pdas_steps);
+    if (ps > 0) {
+        const double* rhov = sys + o.rho;
+        for (int a = 0; a < d.NU; a++) Uout[a] = U[a];
+        for (int i = 0; i < d.mc; i++) v[i] = zz[i] + murow[i] / rhov[i];
+    }
+    free(buf); free(st);
+    return ps;
+}
 
 // Second-generation Riccati polish (tpi2_*): up to max_ref refinements from the working-set codes (mode 0: as stored,
 // 1: shifted by one stage, 2: derived from the TPI rows of v).  codes: Np words in/out; v [mc] in (mode 2) / out (v* when verified);

@@ -94,3 +94,14 @@ def test_fast_path_shape_table_is_well_formed():
         assert nu == 1 and 1 <= Nc <= Np < 32 and Np * nx <= 128, (nx, nu, Np, Nc)
     for s in ((4, 1, 20, 20), (2, 1, 20, 20), (4, 1, 10, 10), (4, 1, 20, 10)):
         assert s in shapes
+
+
+def test_fast_path_table_query_and_on_demand_shape_build(bmpc_lib):
+    """bmpc_has_fast_path reports the compiled table; build.jit_shape validates the shape limits of the thread-per-instance kernels
+    (nu == 1, Np * nx <= 128, Np < 32, Nc <= Np) before invoking nvcc"""
+    from pympc_b200 import build
+    assert bmpc_lib.bmpc_has_fast_path(4, 1, 20, 20) == 1 and bmpc_lib.bmpc_has_fast_path(4, 1, 20, 0) == 1
+    assert bmpc_lib.bmpc_has_fast_path(4, 1, 20, 10) == 1 and bmpc_lib.bmpc_has_fast_path(5, 1, 17, 17) == 0
+    for bad in ((4, 2, 20, None), (8, 1, 20, None), (2, 1, 40, None), (3, 1, 10, 11)):
+        with pytest.raises(ValueError):
+            build.jit_shape(*bad)

@@ -663,3 +663,33 @@ def test_random_systems_vs_oracle(MPC, eps_feas):
     print("random systems tally", eps_feas, tally)
     assert tally["fail"] <= 0.03 * total, tally          # the remaining failures are what 4000 un-equilibrated ADMM iterations leave
     assert tally[1] >= 0.6 * total, tally
+
+
+def test_any_single_input_shape_gets_the_fast_path(MPC):
+    """a shape that is NOT in csrc/tpi_shapes.inc (nx=3, nu=1, Np=12, Nc=9): setup() builds the one instantiation on demand
+    (pympc_b200.build.jit_shape, cached) and the controller runs on the thread-per-instance kernels — same answers as the oracle and
+    as the generic team kernels, and warm steps without ADMM iterations prove the fast path carried them."""
+    rng = np.random.default_rng(5); B = 300
+    c = _random_system(rng, 3, 1, 12, 9, 1e4)
+    X0 = rng.uniform(0.8 * c["xmin"], 0.8 * c["xmax"], (B, 3)); Xref = 0.3 * rng.standard_normal((B, 3))
+    Ks = [MPC(**dict(c, x0=X0, xref=Xref, uminus1=np.zeros(1)), batch=B, fast_path=f) for f in (1, 0)]
+    for K in Ks:
+        K.setup()
+    assert Ks[0]._L.bmpc_has_fast_path(3, 1, 12, 9) == 1 and Ks[1]._L.bmpc_has_fast_path(3, 1, 12, 9) == 0
+    X = X0.copy(); U = np.zeros((B, 1))
+    for t in range(4):
+        outs = []
+        for K in Ks:
+            if t > 0:
+                K.update(X, U)
+            Un, info = K.output(return_u_seq=True); outs.append(info["u_seq"].reshape(B, -1))
+            assert (K.res.info.status_val > 0).all()
+        both = (Ks[0].res.info.status_val == 1) & (Ks[1].res.info.status_val == 1)
+        assert both.mean() > 0.95 and np.max(np.abs(outs[0][both] - outs[1][both])) < TOL
+        for b in np.flatnonzero(both)[:3]:
+            ref, Q = _oracle_u(dict(c, x0=X[b], xref=Xref[b], uminus1=U[b]))
+            assert np.max(np.abs(outs[0][b] - ref)) < TOL
+        U = Un; X = X @ c["Ad"].T + U @ c["Bd"].T
+    assert Ks[0].stats()["admm_iters"] < 2 * B
+    for K in Ks:
+        K.close()
