@@ -24,7 +24,10 @@
 // [1] active-set refinements, [2] overflow of the small polish tier, [3] certified infeasible, [4..7] queue control of k_tpi_pol
 // (cursor, head, and one 64-bit word: low = reserved queue tail, high = finished chunks), [8] instances that left as "solved,
 // unpolished" on tight ADMM residuals.
-enum { TPI_Q_CURSOR = 4, TPI_Q_HEAD = 5, TPI_Q_TAIL = 6, BMPC_CNT_TIGHT = 8, BMPC_CNT = 16 };
+// [10..11] / [12..13]: ~(earliest start) and latest end of k_tpi_pol in ns of the GPU's global timer (64-bit each): the kernel's
+// own duration, for the roofline of bench.py (CUDA events around a launch also count launch gaps).
+enum { TPI_Q_CURSOR = 4, TPI_Q_HEAD = 5, TPI_Q_TAIL = 6, BMPC_CNT_TIGHT = 8, BMPC_CNT_T0 = 10, BMPC_CNT_T1 = 12, BMPC_CNT = 16 };
+__device__ __forceinline__ unsigned long long bmpc_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 // ------------------------------------------------------------------------------------------------
 // teams
@@ -756,6 +759,7 @@ __global__ void __launch_bounds__(TPI_POL_WARPS * 32, 1) k_tpi_pol(const __grid_
     CT* csm = (CT*)((char*)wsm + L::gain_bytes);
     const int nchunks = (A.count + 31) / 32;
     if (blockIdx.x == 0 && threadIdx.x < BMPC_CNT) A.counts_next[threadIdx.x] = 0;
+    if (threadIdx.x == 0) atomicMax((unsigned long long*)(A.counts + BMPC_CNT_T0), ~bmpc_globaltimer());
     // ---- phase A
     for (;;) {
         int chunk = 0;
@@ -767,7 +771,7 @@ __global__ void __launch_bounds__(TPI_POL_WARPS * 32, 1) k_tpi_pol(const __grid_
         const int inst = A.list ? (valid ? A.list[idx0 + lane] : 0) : idx0 + lane;
         tpi_pol_batch<S, TV>(P, I, A, wsm, csm, inst, valid, A.list ? -1 : idx0, nvalid, A.mode, A.capA, A.capB > 0, A.reset);
     }
-    if (A.capB <= 0) return;
+    if (A.capB <= 0) { if (lane == 0) atomicMax((unsigned long long*)(A.counts + BMPC_CNT_T1), bmpc_globaltimer()); return; }
     // ---- phase B: serve the queue until every chunk of phase A is finished and the queue is empty.  Tickets: a warp takes the
     // next 32 queue slots with one fetch-and-add (no compare-and-swap races between a thousand warps) and waits until they are
     // filled or phase A has ended short of them, so batches are full while phase A still produces.
@@ -795,6 +799,7 @@ __global__ void __launch_bounds__(TPI_POL_WARPS * 32, 1) k_tpi_pol(const __grid_
         __threadfence();
         tpi_pol_batch<S, TV>(P, I, A, wsm, csm, valid ? inst : 0, valid, -1, __popc(vmask), 0, A.capB, false, 0);
     }
+    if (lane == 0) atomicMax((unsigned long long*)(A.counts + BMPC_CNT_T1), bmpc_globaltimer());
 }
 
 // Compiled fast-path shapes (nx, nu, Np, Nc) with nu == 1 and Nc == Np: one line per shape in csrc/tpi_shapes.inc
@@ -945,7 +950,7 @@ void bmpc_default_config(bmpc_config* c) {
     memset(c, 0, sizeof(*c));
     c->Np = 20; c->Nc = 0; c->batch = 1; c->device = 0; c->soft_on = 1;
     c->max_iter = 4000; c->first_iters = 0; c->pdas_steps = 10; c->rmax = 0; c->polish = 1;
-    c->team_threads = 0; c->warps_per_block = 0; c->fast_path = 1; c->n_sys = 1; c->shift_warm = 1; c->candidate_warm = 1;
+    c->team_threads = 0; c->warps_per_block = 0; c->fast_path = 1; c->n_sys = 1; c->shift_warm = 1; c->candidate_warm = 0;
     c->eps_feas = 1e6; c->rho = 0.0; c->sigma = 1e-6; c->alpha = 1.6; c->eps_abs = 1e-3; c->eps_rel = 1e-3;
 }
 
@@ -1367,6 +1372,10 @@ static int retire_round(bmpc_handle* h, int* more) {
     BMPC_CUDA(cudaStreamSynchronize(h->stream));
     float a = 0.f, p = 0.f;
     cudaEventElapsedTime(&a, h->ev[0], h->ev[1]); cudaEventElapsedTime(&p, h->ev[1], h->ev[2]);
+    {   // a fast-path polish launch timed itself (global timer): more faithful than events, which also see launch gaps
+        unsigned long long t0n, t1; memcpy(&t0n, h->h_count + BMPC_CNT_T0, 8); memcpy(&t1, h->h_count + BMPC_CNT_T1, 8);
+        if (t1 != 0ull && t0n != 0ull && t1 > ~t0n) p = (float)((double)(t1 - ~t0n) * 1e-6);
+    }
     h->stats.ms_admm += a; h->stats.ms_polish += p;
     h->stats.admm_iters += (int64_t)st.count * st.chunk;
     st.total += st.chunk; st.round++;

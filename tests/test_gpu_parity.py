@@ -207,8 +207,16 @@ def _oracle_u(cfg, **qp_kw):
     from oracle.qp_assembly import QPData
     from oracle.kkt import solve_exact
     Q = QPData(**cfg, **qp_kw)
-    z, y, r = solve_exact(Q.P, Q.q, Q.A, Q.l, Q.u)
-    return z[Q.NX:Q.NX + Q.NU], Q
+    try:
+        z, y, r = solve_exact(Q.P, Q.q, Q.A, Q.l, Q.u)
+        return z[Q.NX:Q.NX + Q.NU], Q
+    except RuntimeError:
+        # the ADMM -> active-set oracle cannot certify some very ill-conditioned QPs (eps_feas = 1e5, state far outside its
+        # box): the independent exact solver (least-distance problem through NNLS) takes over
+        from oracle.ldp import solve_mpc
+        if qp_kw:
+            raise
+        return solve_mpc(Q), Q
 
 
 def test_hidden_flags_like_reference(MPC):
@@ -636,7 +644,7 @@ def test_random_systems_vs_oracle(MPC, eps_feas):
             X0 = np.stack([rng.uniform(1.5 * c["xmin"], 1.5 * c["xmax"]) for c in cfgs]); Xref = 0.5 * rng.standard_normal((B, nx))
             K = MPC(stack("Ad"), stack("Bd"), Np=Np, Nc=Nc, x0=X0, xref=Xref, uminus1=np.zeros(nu), batch=B, Qx=stack("Qx"), QxN=stack("QxN"),
                     Qu=stack("Qu"), QDu=stack("QDu"), xmin=stack("xmin"), xmax=stack("xmax"), umin=stack("umin"), umax=stack("umax"),
-                    Dumin=stack("Dumin"), Dumax=stack("Dumax"), eps_feas=eps_feas, team_threads=team)
+                    Dumin=stack("Dumin"), Dumax=stack("Dumax"), eps_feas=eps_feas, team_threads=team, candidate_warm=1)
             K.setup(); U = K.output()
             cl = [dict(c, Np=Np, Nc=Nc or Np) for c in cfgs]
             check(K, cl, X0, Xref, np.zeros((B, nu)), U, nu)
@@ -648,7 +656,7 @@ def test_random_systems_vs_oracle(MPC, eps_feas):
         for (nx, nu, Np, B) in ((6, 3, 24, 200), (4, 1, 20, 512)):
             c = _random_system(rng, nx, nu, Np, None, eps_feas)
             X0 = rng.uniform(1.5 * c["xmin"], 1.5 * c["xmax"], (B, nx)); Xref = 0.5 * rng.standard_normal((B, nx))
-            K = MPC(**dict(c, x0=X0, xref=Xref, uminus1=np.zeros(nu)), batch=B)
+            K = MPC(**dict(c, x0=X0, xref=Xref, uminus1=np.zeros(nu)), batch=B, candidate_warm=1)
             K.setup(); U = K.output()
             idx = rng.choice(B, 40, replace=False)
             sub = lambda A: A[idx]
