@@ -561,6 +561,7 @@ struct TpiPolArgs {
     int32_t* next_list; int32_t* counts; // counts[0] unfinished (-> next_list), [1] refinements; counts[4..7] queue control, see below
     int32_t* queue; int qcap;            // phase-B queue (capacity qcap), all -1 between launches (consumers clear what they take)
     double* u0_out; double* um1_solved;
+    const double* pview; int pstride;    // per-instance parameter blocks (PERINST instantiation): base and field stride (= batch)
     int cand_warm;                       // 1: an unverified instance hands its last candidate to the ADMM rounds when that candidate is sane
     unsigned char* codes; int code_stride;   // per instance: Np working-set codes + the multiplier scale (double) of the last refinement
 };
@@ -579,8 +580,8 @@ struct TpiPolLayout {
 };
 
 // one batch of up to 32 instances (one per lane) through up to cap refinements; returns the mask of verified lanes
-template <class S, bool TV>
-__device__ __forceinline__ void tpi_pol_batch(const TpiPolParams<S>& P, const BmpcInst& I, const TpiPolArgs& A, double* wsm, typename TpiCode<S>::type* csm,
+template <class S, bool TV, class PP>
+__device__ __forceinline__ void tpi_pol_batch(const PP& P, const BmpcInst& I, const TpiPolArgs& A, double* wsm, typename TpiCode<S>::type* csm,
                                               int inst, bool valid_in, int inst0_contig, int nvalid, int mode, int cap, bool to_queue, int reset) {
     bool valid = valid_in;
     using L = TpiPolLayout<S>; using CT = typename TpiCode<S>::type;
@@ -688,8 +689,9 @@ __device__ __forceinline__ void tpi_pol_batch(const TpiPolParams<S>& P, const Bm
             double up = um1;
             for (int j = 0; j < S::NU && usable; j++) {
                 const double u = udst[j], dz = u - up;
-                usable = u <= P.uhi + 1e-2 * (1.0 + fabs(P.uhi)) && u >= P.ulo - 1e-2 * (1.0 + fabs(P.ulo)) &&
-                         dz <= P.dhi + 1e-2 * (1.0 + fabs(P.dhi)) && dz >= P.dlo - 1e-2 * (1.0 + fabs(P.dlo));
+                const double uh = P.uhi, ul = P.ulo, dh = P.dhi, dl = P.dlo;
+                usable = u <= uh + 1e-2 * (1.0 + fabs(uh)) && u >= ul - 1e-2 * (1.0 + fabs(ul)) &&
+                         dz <= dh + 1e-2 * (1.0 + fabs(dh)) && dz >= dl - 1e-2 * (1.0 + fabs(dl));
                 up = u;
             }
             if (usable) {
@@ -750,7 +752,18 @@ __device__ __forceinline__ void tpi_pol_batch(const TpiPolParams<S>& P, const Bm
     __syncwarp();
 }
 
-template <class S, bool TV>
+// per-instance parameter blocks (n_sys = batch): field-major in global memory, see TpiPolView
+template <class S>
+__global__ void k_tpi_fill_view(BmpcSysOff o, const double* __restrict__ sys, size_t sys_stride, int B, double* __restrict__ pg) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= B) return;
+    TpiPolParams<S> P;
+    tpi_fill_pol<S>(sys + (size_t)inst * sys_stride, o, P);
+    const double* src = (const double*)&P;
+    for (int f = 0; f < TpiPolView<S>::NF; f++) pg[(size_t)f * B + inst] = src[f];
+}
+
+template <class S, bool TV, bool PERINST>
 __global__ void __launch_bounds__(TPI_POL_WARPS * 32, 1) k_tpi_pol(const __grid_constant__ TpiPolParams<S> P, BmpcInst I, TpiPolArgs A) {
     using L = TpiPolLayout<S>; using CT = typename TpiCode<S>::type;
     extern __shared__ double smem[];
@@ -769,7 +782,8 @@ __global__ void __launch_bounds__(TPI_POL_WARPS * 32, 1) k_tpi_pol(const __grid_
         const int idx0 = chunk * 32, nvalid = (A.count - idx0) < 32 ? (A.count - idx0) : 32;
         const bool valid = lane < nvalid;
         const int inst = A.list ? (valid ? A.list[idx0 + lane] : 0) : idx0 + lane;
-        tpi_pol_batch<S, TV>(P, I, A, wsm, csm, inst, valid, A.list ? -1 : idx0, nvalid, A.mode, A.capA, A.capB > 0, A.reset);
+        if constexpr (PERINST) { const TpiPolView<S> Pv(A.pview + inst, (size_t)A.pstride); tpi_pol_batch<S, TV>(Pv, I, A, wsm, csm, inst, valid, A.list ? -1 : idx0, nvalid, A.mode, A.capA, A.capB > 0, A.reset); }
+        else tpi_pol_batch<S, TV>(P, I, A, wsm, csm, inst, valid, A.list ? -1 : idx0, nvalid, A.mode, A.capA, A.capB > 0, A.reset);
     }
     if (A.capB <= 0) { if (lane == 0) atomicMax((unsigned long long*)(A.counts + BMPC_CNT_T1), bmpc_globaltimer()); return; }
     // ---- phase B: serve the queue until every chunk of phase A is finished and the queue is empty.  Tickets: a warp takes the
@@ -797,7 +811,8 @@ __global__ void __launch_bounds__(TPI_POL_WARPS * 32, 1) k_tpi_pol(const __grid_
         if (!vmask) break;                                            // ticket beyond the end of the queue: nothing left
         if (valid) ((volatile int32_t*)A.queue)[idx] = -1;            // the queue is all -1 again when the launch ends
         __threadfence();
-        tpi_pol_batch<S, TV>(P, I, A, wsm, csm, valid ? inst : 0, valid, -1, __popc(vmask), 0, A.capB, false, 0);
+        if constexpr (PERINST) { const TpiPolView<S> Pv(A.pview + (valid ? inst : 0), (size_t)A.pstride); tpi_pol_batch<S, TV>(Pv, I, A, wsm, csm, valid ? inst : 0, valid, -1, __popc(vmask), 0, A.capB, false, 0); }
+        else tpi_pol_batch<S, TV>(P, I, A, wsm, csm, valid ? inst : 0, valid, -1, __popc(vmask), 0, A.capB, false, 0);
     }
     if (lane == 0) atomicMax((unsigned long long*)(A.counts + BMPC_CNT_T1), bmpc_globaltimer());
 }
@@ -808,6 +823,7 @@ struct TpiEntry {
     int nx, nu, Np, Nc;
     size_t admm_bytes, ric_bytes; int code_stride;
     void (*fill)(const double* hs, const BmpcSysOff& o, void* pa, void* pp);
+    int view_fields; void (*fill_view)(struct bmpc_handle* h);
     int (*configure)();
     void (*launch)(struct bmpc_handle* h, const int32_t* list, int count, int niter, int32_t* next_list, cudaEvent_t mid);
     void (*launch_polish)(struct bmpc_handle* h, const int32_t* list, int count, int32_t* next_list);
@@ -851,6 +867,8 @@ struct bmpc_handle {
     int tpi_kind = 0;                  // 0 none, else 1 + index into g_tpi_table (compiled fast-path shapes)
     void *tpi_admm_params = nullptr, *tpi_polish_params = nullptr;   // host copies of the parameter blocks
     int tpi_pdas_steps = 8;
+    double* tpi_view = nullptr;       // per-instance parameter blocks of the fast path (n_sys = batch), field-major
+    bool codes_valid = false;         // the stored working sets come from a fast-path polish of the whole batch
 };
 
 static std::string g_create_err;
@@ -877,8 +895,14 @@ static void launch_tpi_pol(bmpc_handle* h, const int32_t* list, int count, int m
     if (grid > h->sm_count) grid = h->sm_count;
     if (grid < 1) grid = 1;
     const size_t sm = L::per_warp * TPI_POL_WARPS;
-    if (h->xref_mode) k_tpi_pol<S, true><<<grid, TPI_POL_WARPS * 32, sm, h->stream>>>(PP, h->I, A);
-    else k_tpi_pol<S, false><<<grid, TPI_POL_WARPS * 32, sm, h->stream>>>(PP, h->I, A);
+    A.pview = h->tpi_view; A.pstride = h->cfg.batch;
+    if (h->tpi_view) {
+        if (h->xref_mode) k_tpi_pol<S, true, true><<<grid, TPI_POL_WARPS * 32, sm, h->stream>>>(PP, h->I, A);
+        else k_tpi_pol<S, false, true><<<grid, TPI_POL_WARPS * 32, sm, h->stream>>>(PP, h->I, A);
+    } else {
+        if (h->xref_mode) k_tpi_pol<S, true, false><<<grid, TPI_POL_WARPS * 32, sm, h->stream>>>(PP, h->I, A);
+        else k_tpi_pol<S, false, false><<<grid, TPI_POL_WARPS * 32, sm, h->stream>>>(PP, h->I, A);
+    }
     h->stats.launches++;
 }
 
@@ -902,8 +926,11 @@ static void launch_tpi_round(bmpc_handle* h, const int32_t* list, int count, int
         launch_tpi_pol<S>(h, list, count, 2, capA, capB, 0, next_list);
     } else {
         cudaEventRecord(mid, h->stream);          // this round's counters were zeroed by the previous fast-path launch (or a memset)
-        launch_tpi_pol<S>(h, list, count, h->cfg.shift_warm ? 1 : 0, capA, capB, reset, next_list);
+        // working sets: stored ones (shifted one stage), or — when the last solve of the batch did not go through this kernel (cold
+        // start on the team kernels) — from the iterate v
+        launch_tpi_pol<S>(h, list, count, h->codes_valid ? (h->cfg.shift_warm ? 1 : 0) : 2, capA, capB, reset, next_list);
     }
+    if (list == nullptr) h->codes_valid = true;
 }
 
 // straggler rounds: the listed instances come back from an ADMM chunk of the team kernels, working sets from their iterate
@@ -917,18 +944,26 @@ static void tpi_fill_entry(const double* hs, const BmpcSysOff& o, void* pa, void
     tpi_fill_admm<S>(hs, o, *(TpiAdmmParams<S>*)pa); tpi_fill_pol<S>(hs, o, *(TpiPolParams<S>*)pp);
 }
 template <class S>
+static void tpi_fill_view_entry(bmpc_handle* h) {
+    const int B = h->cfg.batch;
+    k_tpi_fill_view<S><<<(B + 63) / 64, 64, 0, h->stream>>>(h->o, h->sys, (size_t)h->o.total, B, h->tpi_view);
+}
+template <class S>
 static int tpi_configure_entry() {
     if (cudaFuncSetAttribute(k_tpi_admm<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::MT * TPI_STR * 8)) != cudaSuccess) return 1;
     if (cudaFuncSetAttribute(k_tpi_admm<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S::MT * TPI_STR * 8)) != cudaSuccess) return 1;
     const int sm = (int)(TpiPolLayout<S>::per_warp * TPI_POL_WARPS);
-    if (cudaFuncSetAttribute(k_tpi_pol<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm) != cudaSuccess) return 1;
-    if (cudaFuncSetAttribute(k_tpi_pol<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(k_tpi_pol<S, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(k_tpi_pol<S, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(k_tpi_pol<S, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(k_tpi_pol<S, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm) != cudaSuccess) return 1;
     return 0;
 }
 #define BMPC_TPI_SHAPE(NX_, NU_, NP_, NC_)                                                                                   \
     {NX_, NU_, NP_, NC_, sizeof(TpiAdmmParams<TpiShape<NX_, NU_, NP_, NC_>>), sizeof(TpiPolParams<TpiShape<NX_, NU_, NP_, NC_>>), \
      TpiPolLayout<TpiShape<NX_, NU_, NP_, NC_>>::code_stride,                                                                \
-     tpi_fill_entry<TpiShape<NX_, NU_, NP_, NC_>>, tpi_configure_entry<TpiShape<NX_, NU_, NP_, NC_>>,                         \
+     tpi_fill_entry<TpiShape<NX_, NU_, NP_, NC_>>, TpiPolView<TpiShape<NX_, NU_, NP_, NC_>>::NF, tpi_fill_view_entry<TpiShape<NX_, NU_, NP_, NC_>>, \
+     tpi_configure_entry<TpiShape<NX_, NU_, NP_, NC_>>,                                                                        \
      launch_tpi_round<TpiShape<NX_, NU_, NP_, NC_>>, launch_tpi_polish_only<TpiShape<NX_, NU_, NP_, NC_>>},
 // BMPC_TPI_SHAPES_FILE: pympc_b200.build.jit_shape() compiles a copy of the library whose table holds the one shape a controller
 // asked for (any nx, Np with nu == 1) when the in-tree table does not have it
@@ -1130,6 +1165,7 @@ void bmpc_destroy(bmpc_handle* h) {
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_count) cudaFreeHost(h->h_count);
     free(h->tpi_admm_params); free(h->tpi_polish_params);
+    if (h->tpi_view) cudaFree(h->tpi_view);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -1224,7 +1260,7 @@ int bmpc_setup(bmpc_handle* h, const double* Ad, const double* Bd, const double*
     // thread-per-instance fast path for the compiled small shapes (pendulum, point mass)
     h->tpi_kind = 0;
     // (the Riccati polish treats state rows as the soft penalty they are by default; hard state rows -> team kernels)
-    if (h->cfg.fast_path && h->team == 32 && h->cfg.soft_on && ns == 1) {
+    if (h->cfg.fast_path && h->team == 32 && h->cfg.soft_on) {
         for (int k = 0; k < g_tpi_count; k++)
             if (g_tpi_table[k].nx == d.nx && g_tpi_table[k].nu == d.nu && g_tpi_table[k].Np == d.Np && g_tpi_table[k].Nc == d.Nc) { h->tpi_kind = k + 1; break; }
     }
@@ -1235,11 +1271,18 @@ int bmpc_setup(bmpc_handle* h, const double* Ad, const double* Bd, const double*
         BMPC_CUDA(cudaStreamSynchronize(h->stream));
         free(h->tpi_admm_params); free(h->tpi_polish_params);
         h->tpi_admm_params = malloc(te.admm_bytes); h->tpi_polish_params = malloc(te.ric_bytes);
-        te.fill(hs.data(), o, h->tpi_admm_params, h->tpi_polish_params);
+        te.fill(hs.data(), o, h->tpi_admm_params, h->tpi_polish_params);          // system 0 (the only one when the system is shared)
         if (te.configure()) { h->err = "fast path: shared-memory configuration failed"; return BMPC_ERR_CUDA; }
+        if (h->tpi_view) { cudaFree(h->tpi_view); h->tpi_view = nullptr; }
+        if (ns > 1) {
+            // one parameter block per instance, built on the device from each instance's condensed system block
+            BMPC_CUDA(cudaMalloc((void**)&h->tpi_view, sizeof(double) * (size_t)te.view_fields * h->cfg.batch));
+            te.fill_view(h);
+            BMPC_CUDA(cudaGetLastError());
+        }
     }
     // uminus1 default = uref for every instance (mpc.py:141); caller overrides through bmpc_update
-    h->is_setup = true; h->cold = true; h->solved = false; h->pending = false;
+    h->is_setup = true; h->cold = true; h->solved = false; h->pending = false; h->codes_valid = false;
     return BMPC_OK;
 }
 
@@ -1323,7 +1366,9 @@ static int enqueue_round(bmpc_handle* h) {
     // fast path (thread-per-instance kernels, throughput-optimised) for the first round; the few stragglers are
     // latency-bound and go to the CTA-per-instance team kernels
     const bool tpi_ok = h->tpi_kind != 0;
-    const bool tpi = st.round == 0 && tpi_ok && h->cfg.polish;
+    // (per-instance systems have no thread-per-instance ADMM — its matrices live in the constant bank —: their cold start and any
+    // first_iters > 0 go through the team kernels, the warm polish-only round through k_tpi_pol with per-instance parameter blocks)
+    const bool tpi = st.round == 0 && tpi_ok && h->cfg.polish && (h->tpi_view == nullptr || st.chunk == 0);
     // straggler rounds read u_-1 from the snapshot the first round took: bmpc_output may already have queued the commit of
     // this solve's u0 into um1 (speculating that the first round finishes everything)
     h->cpar ^= 1;                                        // counters of this round: the half the previous round left zeroed
@@ -1426,6 +1471,7 @@ int bmpc_solve(bmpc_handle* h) {
     // a cold start has no active-set guess to refresh: 25 iterations at once on the fast path, so that the first polish
     // usually verifies and the whole batch does not take the straggler route
     if (h->cfg.polish && h->cfg.first_iters <= 0 && fast && h->cold) st.chunk = 25;
+    if (h->cfg.polish && fast && h->tpi_view && !h->cold && h->cfg.first_iters > 0) st.chunk = h->cfg.first_iters;
     if (st.chunk > h->cfg.max_iter) st.chunk = h->cfg.max_iter;
     int rc = enqueue_round(h);
     if (rc) return rc;

@@ -362,6 +362,7 @@ inline void tpi_fill_admm(const double* sys, const BmpcSysOff& o, TpiAdmmParams<
 //    reciprocal of huu is MUFU + two Newton steps (no slow-path branch), the constant-reference term Q xref is hoisted.
 // Row / slot conventions are those of the first generation (tpi_vstar_slot): stage k owns gain slots [k (nx+2), (k+1)(nx+2)).
 #include <stdint.h>
+#include <stddef.h>
 #include <type_traits>
 
 template <class S>
@@ -385,10 +386,9 @@ struct TpiPolParams {
     // (0 none, 1 above, 2 below): acceptance interval of a consistent candidate [xacc_lo, xacc_hi], penalty weight xm, its
     // linear term xmb = weight * bound, multiplier coefficient xcm = rho_e / rho (in units of v) and bound xbnd
     double xacc_lo[S::nx][4], xacc_hi[S::nx][4], xm[S::nx][4], xmb[S::nx][4], xcm[S::nx][4], xbnd[S::nx][4];
-    // pin of a stage by its 6 hard-row bits: index 0 free, 1/2 input at max/min, 3/4 delta-u at max/min, 5/6 the spurious last
-    // row at max/min, 7 held stage (Nc < Np)
-    double pintab[8], hsgn[4];                                        // pin value by index; multiplier sign by hard label
-    unsigned char pinidx[64];
+    // pin value of a stage by its pin index (first set bit of the 6 hard-row bits): 0 free, 1/2 input at max/min, 3/4 delta-u at
+    // max/min, 5/6 the spurious last row at max/min, 7 held stage (Nc < Np)
+    double pintab[8];                                                 // pin value by index
 };
 
 #ifdef BMPC_HOSTEMU
@@ -405,9 +405,15 @@ __device__ __forceinline__ double tpi_rcp(double h) {
 #endif
 
 // pin index of one stage from its code word (held: a stage k >= Nc of a shape with Nc < Np)
+#ifdef BMPC_HOSTEMU
+BMPC_HD int tpi_ffs(unsigned b) { return __builtin_ffs((int)b); }
+#else
+__device__ __forceinline__ int tpi_ffs(unsigned b) { return __ffs((int)b); }
+#endif
+// first set bit of the 6 hard-row bits = the priority order input bound, delta-u row, spurious row (0: free stage)
 template <class S>
-BMPC_HD int tpi2_pinidx(const TpiPolParams<S>& P, unsigned code, bool held) {
-    return held ? 7 : (int)P.pinidx[(code >> TpiCode<S>::UUP) & 63u];
+BMPC_HD int tpi2_pinidx(unsigned code, bool held) {
+    return held ? 7 : tpi_ffs((code >> TpiCode<S>::UUP) & 63u);
 }
 // soft-row label (0 none, 1 above its bound, 2 below) of state component a
 template <class S>
@@ -416,12 +422,13 @@ BMPC_HD int tpi2_xlabel(unsigned code, int a) {
 }
 
 // Backward sweep: fills the gain slots of W from the working-set codes C(k).
-template <class S, class XR, class CA>
-BMPC_HD void tpi2_backward(const TpiPolParams<S>& P, TpiAcc W, CA C, XR xr) {
+template <class S, class PP, class XR, class CA>
+BMPC_HD void tpi2_backward(const PP& P, TpiAcc W, CA C, XR xr) {
     static_assert(S::nu == 1 && S::Nc <= S::Np, "Riccati polish is specialised to nu == 1");
     constexpr int nx = S::nx, N = S::Np, Nc = S::Nc, nz1 = nx + 2;
     double Pm[nx * nx], pxw[nx], px[nx], pww = 0.0, pw = 0.0;          // Pm symmetric: both triangles hold the same values
     double qc[nx];                                                       // Qx xref (constant reference)
+    const double P_QDu = P.QDu, P_QuQDu = (double)P.Qu + P_QDu, P_quref = P.quref;   // scalars once (PP may be a view in global memory)
     if (!XR::TV) {
 #pragma unroll
         for (int a = 0; a < nx; a++) {
@@ -447,7 +454,7 @@ BMPC_HD void tpi2_backward(const TpiPolParams<S>& P, TpiAcc W, CA C, XR xr) {
     for (int k = N - 1; k >= 0; k--) {
         const unsigned cprev = C(k >= 1 ? k - 1 : 0);                   // state bits of x_k (x_0 is data: its cost is irrelevant)
         const bool held = (Nc < N) && (k >= Nc);
-        const int pi = tpi2_pinidx<S>(P, code, held);
+        const int pi = tpi2_pinidx<S>(code, held);
         const double pin = P.pintab[pi];
         const bool free_ = pi == 0;
         const double dp = (pi == 3 || pi == 4 || pi == 7) ? 1.0 : 0.0;
@@ -470,7 +477,7 @@ BMPC_HD void tpi2_backward(const TpiPolParams<S>& P, TpiAcc W, CA C, XR xr) {
             PB[a] = accb;
         }
         double Hxx[nx * nx], hx[nx], gx[nx];
-        double huu = pww + (P.Qu + P.QDu), gu = pw - P.quref;
+        double huu = pww + P_QuQDu, gu = pw - P_quref;
 #pragma unroll
         for (int a = 0; a < nx; a++) { huu = fma(P.Bd[a], PB[a] + 2.0 * pxw[a], huu); gu = fma(P.Bd[a], px[a], gu); }
 #pragma unroll
@@ -495,7 +502,7 @@ BMPC_HD void tpi2_backward(const TpiPolParams<S>& P, TpiAcc W, CA C, XR xr) {
             Hxx[a * nx + a] += xmk[a];
             gx[a] = g - (q + xmbk[a]);
         }
-        const double hw = -P.QDu, Hww = P.QDu;
+        const double hw = -P_QDu, Hww = P_QDu;
         const double inv = tpi_rcp(huu);
         const double c1 = free_ ? inv : 0.0, c4 = free_ ? inv : 1.0;
         const double c2 = fma(-c1, gu, pin);                            // free: -gu / huu ; pinned: pin
@@ -524,11 +531,12 @@ BMPC_HD void tpi2_backward(const TpiPolParams<S>& P, TpiAcc W, CA C, XR xr) {
 // into C(k), the inputs through outu(k, u), the exact ADMM fixed point v* = z* + y*/rho into the gain slots just consumed
 // (the spurious last row into vq) and returns true when the candidate is the minimiser.  mumax: in = scale of the multiplier
 // sign tolerance (sum of the multiplier magnitudes of the previous refinement, 0 at first), out = that of this one.
-template <class S, class CA, class FU>
-BMPC_HD bool tpi2_forward(const TpiPolParams<S>& P, TpiAcc W, CA C, const double* x0, double um1, double& mumax, double& vq, FU outu) {
+template <class S, class PP, class CA, class FU>
+BMPC_HD bool tpi2_forward(const PP& P, TpiAcc W, CA C, const double* x0, double um1, double& mumax, double& vq, FU outu) {
     constexpr int nx = S::nx, N = S::Np, Nc = S::Nc, nz1 = nx + 2;
     using CD = TpiCode<S>;
     const double mutol = -1e-9 * (1.0 + mumax);
+    const double ulo_m = P.ulo_m, uhi_p = P.uhi_p, dlo_m = P.dlo_m, dhi_p = P.dhi_p, irhou = P.irhou, irhod = P.irhod;
     double mnew = 0.0;
     unsigned bad = 0u;
     double x[nx], w = um1;
@@ -537,7 +545,7 @@ BMPC_HD bool tpi2_forward(const TpiPolParams<S>& P, TpiAcc W, CA C, const double
     // KKT check of one hard row with label lab (0 none, 1 at max, 2 at min) and multiplier mu; returns its two bits of the next
     // working set (bit 0 up, bit 1 down).  m = sign(label) * mu must not be negative; the label survives if m > 0.
     auto hard_row = [&](double zi, double lo_m, double hi_p, unsigned lab, double mu) -> unsigned {
-        const double m = P.hsgn[lab] * mu;
+        const double m = (double)((int)(lab & 1u) - (int)(lab >> 1)) * mu;
         const unsigned vu = zi > hi_p, vd = zi < lo_m, keep = m > 0.0;
         bad |= vu | vd | (unsigned)(m < mutol);
         const unsigned nu_ = vu | (~vd & keep & lab & 1u);
@@ -552,7 +560,7 @@ BMPC_HD bool tpi2_forward(const TpiPolParams<S>& P, TpiAcc W, CA C, const double
     for (int k = 0; k < N; k++) {
         const int base = k * nz1;
         const bool held = (Nc < N) && (k >= Nc);
-        const int pi = tpi2_pinidx<S>(P, code, held);
+        const int pi = tpi2_pinidx<S>(code, held);
         const double pin = P.pintab[pi];
         // soft-row tables of x_{k+1} (independent of the state recursion: issued before it)
         double alo[nx], ahi[nx], cm[nx], bnd[nx];
@@ -575,18 +583,18 @@ BMPC_HD bool tpi2_forward(const TpiPolParams<S>& P, TpiAcc W, CA C, const double
             const double mu_u = (pi == 1 || pi == 2) ? -lin : 0.0, mu_d = (pi == 3 || pi == 4) ? -lin : 0.0;
             mnew += (pi == 0) ? 0.0 : fabs(lin);
             outu(k, u);
-            unsigned hb = hard_row(u, P.ulo_m, P.uhi_p, (code >> CD::UUP) & 3u, mu_u);
+            unsigned hb = hard_row(u, ulo_m, uhi_p, (code >> CD::UUP) & 3u, mu_u);
             ncode |= hb << CD::UUP;
-            W(base + nx) = fma(mu_u, P.irhou, u);
+            W(base + nx) = fma(mu_u, irhou, u);
             const double dz = u - w;                                    // row 0: u_0 against bounds shifted by u_-1 = the same test
-            hb = hard_row(dz, P.dlo_m, P.dhi_p, (code >> CD::DUP) & 3u, mu_d);
+            hb = hard_row(dz, dlo_m, dhi_p, (code >> CD::DUP) & 3u, mu_d);
             ncode |= hb << CD::DUP;
-            W(base + nx + 1) = fma(mu_d, P.irhod, (k == 0) ? u : dz);
+            W(base + nx + 1) = fma(mu_d, irhod, (k == 0) ? u : dz);
             if (k == Nc - 1) {
                 const double mu_q = (pi == 5 || pi == 6) ? lin : 0.0;
-                hb = hard_row(-u, P.dlo_m, P.dhi_p, (code >> CD::QUP) & 3u, mu_q);
+                hb = hard_row(-u, dlo_m, dhi_p, (code >> CD::QUP) & 3u, mu_q);
                 ncode |= hb << CD::QUP;
-                vq = fma(mu_q, P.irhod, -u);
+                vq = fma(mu_q, irhod, -u);
             }
         }
         double xn[nx];
@@ -618,26 +626,27 @@ BMPC_HD bool tpi2_forward(const TpiPolParams<S>& P, TpiAcc W, CA C, const double
 }
 
 // first working sets from an ADMM iterate v (TPI rows; after a cold start or a straggler round): as tpi_sets_from_v
-template <class S, class Acc, class CA>
-BMPC_HD void tpi2_codes_from_v(const TpiPolParams<S>& P, double um1, Acc V, double vlast, CA C) {
+template <class S, class PP, class Acc, class CA>
+BMPC_HD void tpi2_codes_from_v(const PP& P, double um1, Acc V, double vlast, CA C) {
     constexpr int nx = S::nx, Np = S::Np, Nc = S::Nc, NS = S::NS, NU = S::NU;
     using CD = TpiCode<S>;
     auto over = [](double v, double hi) { return v > hi + 1e-9 * (1.0 + fabs(hi)); };
     auto under = [](double v, double lo) { return v < lo - 1e-9 * (1.0 + fabs(lo)); };
+    const double uhi = P.uhi, ulo = P.ulo, dhi = P.dhi, dlo = P.dlo;
 #pragma unroll 1
     for (int k = 0; k < Np; k++) {
         unsigned c = 0u;
 #pragma unroll
         for (int a = 0; a < nx; a++) {
-            const double v = V(k * nx + a);
-            c |= (over(v, P.xhi[a]) ? 1u : 0u) << (CD::XUP + a); c |= (under(v, P.xlo[a]) ? 1u : 0u) << (CD::XDN + a);
+            const double v = V(k * nx + a), xh = P.xhi[a], xl = P.xlo[a];
+            c |= (over(v, xh) ? 1u : 0u) << (CD::XUP + a); c |= (under(v, xl) ? 1u : 0u) << (CD::XDN + a);
         }
         if (k < Nc) {
             const double vu = V(NS + k);
-            c |= (over(vu, P.uhi) ? 1u : 0u) << CD::UUP; c |= (under(vu, P.ulo) ? 1u : 0u) << CD::UDN;
+            c |= (over(vu, uhi) ? 1u : 0u) << CD::UUP; c |= (under(vu, ulo) ? 1u : 0u) << CD::UDN;
             const double vd = V(NS + NU + k), sh = (k == 0) ? um1 : 0.0;
-            c |= (over(vd, P.dhi + sh) ? 1u : 0u) << CD::DUP; c |= (under(vd, P.dlo + sh) ? 1u : 0u) << CD::DDN;
-            if (k == Nc - 1) { c |= (over(vlast, P.dhi) ? 1u : 0u) << CD::QUP; c |= (under(vlast, P.dlo) ? 1u : 0u) << CD::QDN; }
+            c |= (over(vd, dhi + sh) ? 1u : 0u) << CD::DUP; c |= (under(vd, dlo + sh) ? 1u : 0u) << CD::DDN;
+            if (k == Nc - 1) { c |= (over(vlast, dhi) ? 1u : 0u) << CD::QUP; c |= (under(vlast, dlo) ? 1u : 0u) << CD::QDN; }
         }
         C(k) = (typename CD::type)c;
     }
@@ -657,7 +666,7 @@ BMPC_HD unsigned tpi2_shifted_code(const typename TpiCode<S>::type* stored, int 
 }
 
 template <class S>
-inline void tpi_fill_pol(const double* sys, const BmpcSysOff& o, TpiPolParams<S>& P) {
+BMPC_HOSTDEV void tpi_fill_pol(const double* sys, const BmpcSysOff& o, TpiPolParams<S>& P) {
     constexpr int nx = S::nx, NU = S::NU, NX = S::NX;
     for (int i = 0; i < nx * nx; i++) { P.Ad[i] = sys[o.Ad + i]; P.Qx[i] = sys[o.Qx + i]; P.QxN[i] = sys[o.QxN + i]; }
     for (int i = 0; i < nx; i++) P.Bd[i] = sys[o.Bd + i];
@@ -673,7 +682,7 @@ inline void tpi_fill_pol(const double* sys, const BmpcSysOff& o, TpiPolParams<S>
     P.dlo = sys[o.lo0 + NX + NU]; P.dhi = sys[o.hi0 + NX + NU]; P.dlo_m = tol(P.dlo, 1e-9, -1.0); P.dhi_p = tol(P.dhi, 1e-9, 1.0);
     P.irhou = 1.0 / sys[o.rho + NX]; P.irhod = 1.0 / sys[o.rho + NX + NU];
     P.Qu = sys[o.Qu]; P.QDu = sys[o.QDu]; P.quref = sys[o.Qu] * sys[o.uref]; P.rho_e = rho_e;
-    const double inf = HUGE_VAL;
+    const double inf = 1.0 / 0.0;
     for (int a = 0; a < nx; a++) {
         const double lo = P.xlo[a], hi = P.xhi[a];
         const double al[4] = {P.xlo_m[a], P.xhi_m[a], -inf, -inf}, ah[4] = {P.xhi_p[a], inf, P.xlo_p[a], inf};
@@ -685,11 +694,30 @@ inline void tpi_fill_pol(const double* sys, const BmpcSysOff& o, TpiPolParams<S>
     }
     const double pt[8] = {0.0, P.uhi, P.ulo, P.dhi, P.dlo, -P.dhi, -P.dlo, 0.0};
     for (int i = 0; i < 8; i++) P.pintab[i] = pt[i];
-    P.hsgn[0] = 0.0; P.hsgn[1] = 1.0; P.hsgn[2] = -1.0; P.hsgn[3] = 0.0;
-    for (int b = 0; b < 64; b++) {
-        // bits: 0 input up, 1 input down, 2 delta-u up, 3 delta-u down, 4 spurious row up, 5 spurious row down; priority as listed
-        int idx = 0;
-        if (b & 1) idx = 1; else if (b & 2) idx = 2; else if (b & 4) idx = 3; else if (b & 8) idx = 4; else if (b & 16) idx = 5; else if (b & 32) idx = 6;
-        P.pinidx[b] = (unsigned char)idx;
-    }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Per-instance systems on the fast path: the same parameter block, one per instance, in GLOBAL memory stored
+// field-major — double number f of instance i at pg[f * B + i] — so that the 32 lanes of a warp (32 consecutive instances)
+// read every field with one coalesced access.  TpiPolView offers the member names of TpiPolParams (P.Ad[i], P.xm[a][lab],
+// P.uhi_p, ...), so the sweeps above compile unchanged against either.
+struct TpiGScalar { const double* p; BMPC_HD operator double() const { return *p; } };
+struct TpiGArr { const double* p; size_t B; BMPC_HD double operator[](int i) const { return p[(size_t)i * B]; } };
+struct TpiGArr2 { const double* p; size_t B; BMPC_HD TpiGArr operator[](int a) const { return TpiGArr{p + (size_t)a * 4 * B, B}; } };
+template <class S>
+struct TpiPolView {
+    using PS = TpiPolParams<S>;
+    TpiGArr Ad, Bd, Qx, QxN, xlo, xhi, xlo_m, xlo_p, xhi_m, xhi_p, cx, pintab;
+    TpiGArr2 xacc_lo, xacc_hi, xm, xmb, xcm, xbnd;
+    TpiGScalar ulo, uhi, ulo_m, uhi_p, dlo, dhi, dlo_m, dhi_p, irhou, irhod, Qu, QDu, quref, rho_e;
+    static constexpr int NF = (int)(sizeof(PS) / sizeof(double));
+#define BMPC_VF(m) (p + (offsetof(PS, m) / sizeof(double)) * B)
+    BMPC_HD TpiPolView(const double* p, size_t B)
+        : Ad{BMPC_VF(Ad), B}, Bd{BMPC_VF(Bd), B}, Qx{BMPC_VF(Qx), B}, QxN{BMPC_VF(QxN), B}, xlo{BMPC_VF(xlo), B}, xhi{BMPC_VF(xhi), B},
+          xlo_m{BMPC_VF(xlo_m), B}, xlo_p{BMPC_VF(xlo_p), B}, xhi_m{BMPC_VF(xhi_m), B}, xhi_p{BMPC_VF(xhi_p), B}, cx{BMPC_VF(cx), B},
+          pintab{BMPC_VF(pintab), B}, xacc_lo{BMPC_VF(xacc_lo), B}, xacc_hi{BMPC_VF(xacc_hi), B}, xm{BMPC_VF(xm), B}, xmb{BMPC_VF(xmb), B},
+          xcm{BMPC_VF(xcm), B}, xbnd{BMPC_VF(xbnd), B}, ulo{BMPC_VF(ulo)}, uhi{BMPC_VF(uhi)}, ulo_m{BMPC_VF(ulo_m)}, uhi_p{BMPC_VF(uhi_p)},
+          dlo{BMPC_VF(dlo)}, dhi{BMPC_VF(dhi)}, dlo_m{BMPC_VF(dlo_m)}, dhi_p{BMPC_VF(dhi_p)}, irhou{BMPC_VF(irhou)}, irhod{BMPC_VF(irhod)},
+          Qu{BMPC_VF(Qu)}, QDu{BMPC_VF(QDu)}, quref{BMPC_VF(quref)}, rho_e{BMPC_VF(rho_e)} {}
+#undef BMPC_VF
+};
