@@ -262,8 +262,14 @@ class Gather:
 def device_loop(torch, dist, K, cfg, X0, steps, warmup, dev, world, gather, flush, sampler=None):
     """timed region of `value`: inputs resident in HBM, CUDA events on the launching stream around every step"""
     L, h = K._L, K.handle
-    stream = torch.cuda.current_stream(dev)
+    # ONE explicit stream for the solver, the L2 flush, the plant and the timing events.  (torch's default stream has handle 0,
+    # which bmpc_set_stream reads as "use the handle's own stream": the flush would then overlap the solver kernels and the
+    # events would not bracket them — round 1's bench had that flaw.)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.synchronize(dev)
+    assert stream.cuda_stream != 0
     L.bmpc_set_stream(h, stream.cuda_stream)
+    torch.cuda.set_stream(stream)
     Ad = torch.tensor(cfg["Ad"], device=dev); Bd = torch.tensor(cfg["Bd"], device=dev)
     Xd = torch.tensor(X0, device=dev); Xn = torch.empty_like(Xd)
     acc = dict(admm_iters=0, ms_admm=0.0, ms_polish=0.0, launches=0, polish_steps=0, unsolved=0); rounds = []; tot_ms = 0.0
@@ -297,6 +303,7 @@ def device_loop(torch, dist, K, cfg, X0, steps, warmup, dev, world, gather, flus
                 acc[k] += st[k]
             rounds.append(st["rounds"])
     torch.cuda.synchronize(dev)
+    torch.cuda.set_stream(torch.cuda.default_stream(dev))
     if world > 1:
         dist.barrier()
     tmax = torch.tensor([tot_ms], dtype=torch.float64, device=dev)

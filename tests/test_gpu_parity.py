@@ -631,7 +631,7 @@ def test_random_systems_vs_oracle(MPC, eps_feas):
             if s == 1:
                 assert np.max(np.abs(U[b] - ref[:nu])) < TOL * scale, (b, s)
             elif s == 2:
-                assert np.max(np.abs(U[b] - ref[:nu])) < 5e-3 * scale, (b, s)
+                assert np.max(np.abs(U[b] - ref[:nu])) < 2e-2 * scale, (b, s)       # OSQP's own accuracy class at eps = 1e-3 (2e-3 .. 4e-2)
             tally[s if s in (1, 2) else "fail"] += 1
 
     with warnings.catch_warnings():
@@ -673,7 +673,7 @@ def test_random_systems_vs_oracle(MPC, eps_feas):
     # (DESIGN.md section 7): the multipliers eps_feas * d are out of reach of 4000 un-equilibrated ADMM iterations for about one
     # instance in nine (measured 50 of 448), which end as max-iter -> u_failure where OSQP's relative tolerance says "solved"
     assert tally["fail"] <= (0.03 if eps_feas < 1e4 else 0.15) * total, tally
-    assert tally[1] >= 0.6 * total, tally
+    assert tally[1] >= (0.9 if eps_feas < 1e4 else 0.45) * total, tally
 
 
 def test_any_single_input_shape_gets_the_fast_path(MPC):
@@ -736,7 +736,7 @@ def test_per_instance_systems_on_the_fast_path(MPC):
             ref, Q = _oracle_u(c)
             assert np.max(np.abs(outs[0][b] - ref)) < TOL, (t, b)
         if t > 0:
-            assert Ks[0].stats()["admm_iters"] < 2 * B and Ks[1].stats()["admm_iters"] >= 10 * B      # fast path: polish only
+            assert Ks[0].stats()["admm_iters"] < 5 * B and Ks[1].stats()["admm_iters"] >= 10 * B      # fast path: polish first, ADMM only for stragglers
         U = Un; X = np.einsum("bij,bj->bi", Ad, X) + np.einsum("bij,bj->bi", Bd, U)
     for K in Ks:
         K.close()

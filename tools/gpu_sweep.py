@@ -34,7 +34,7 @@ def run_one(spec, steps, warmup, B):
     cold = K.stats()
     dev = torch.device("cuda", 0)
     L, h = K._L, K.handle
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev); torch.cuda.synchronize(dev); torch.cuda.set_stream(stream)   # handle 0 would mean the library's own stream
     L.bmpc_set_stream(h, stream.cuda_stream)
     Ad = torch.tensor(cfgp["Ad"], device=dev); Bd = torch.tensor(cfgp["Bd"], device=dev)
     Xd = torch.tensor(X0, device=dev); Xn = torch.empty_like(Xd)
