@@ -26,7 +26,9 @@
 // unpolished" on tight ADMM residuals.
 // [10..11] / [12..13]: ~(earliest start) and latest end of k_tpi_pol in ns of the GPU's global timer (64-bit each): the kernel's
 // own duration, for the roofline of bench.py (CUDA events around a launch also count launch gaps).
-enum { TPI_Q_CURSOR = 4, TPI_Q_HEAD = 5, TPI_Q_TAIL = 6, BMPC_CNT_TIGHT = 8, BMPC_CNT_T0 = 10, BMPC_CNT_T1 = 12, BMPC_CNT = 16 };
+// [14]: warps of k_tpi_pol that have left; the last one copies the block into the handle's MAPPED pinned host buffer and raises
+// [15] = launch epoch there: the host spins on that word instead of paying a D2H copy + stream synchronisation per solve.
+enum { TPI_Q_CURSOR = 4, TPI_Q_HEAD = 5, TPI_Q_TAIL = 6, BMPC_CNT_TIGHT = 8, BMPC_CNT_T0 = 10, BMPC_CNT_T1 = 12, BMPC_CNT_EXIT = 14, BMPC_CNT_EPOCH = 15, BMPC_CNT = 16 };
 __device__ __forceinline__ unsigned long long bmpc_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 // ------------------------------------------------------------------------------------------------
@@ -558,6 +560,7 @@ struct TpiPolArgs {
     int capA, capB;                      // refinements per instance in phase A / in phase B (0: no phase B, failures go to next_list)
     int reset;                           // first round of a solve: per-solve bookkeeping rides here
     int32_t* counts_next;                // the 8 counters of the NEXT round: zeroed here (saves a memset launch per solve)
+    int32_t* host_counts; int epoch;     // mapped pinned copy of the counters + the value the last warp stores into its epoch slot (0: off)
     int32_t* next_list; int32_t* counts; // counts[0] unfinished (-> next_list), [1] refinements; counts[4..7] queue control, see below
     int32_t* queue; int qcap;            // phase-B queue (capacity qcap), all -1 between launches (consumers clear what they take)
     double* u0_out; double* um1_solved;
@@ -785,7 +788,21 @@ __global__ void __launch_bounds__(TPI_POL_WARPS * 32, 1) k_tpi_pol(const __grid_
         if constexpr (PERINST) { const TpiPolView<S> Pv(A.pview + inst, (size_t)A.pstride); tpi_pol_batch<S, TV>(Pv, I, A, wsm, csm, inst, valid, A.list ? -1 : idx0, nvalid, A.mode, A.capA, A.capB > 0, A.reset); }
         else tpi_pol_batch<S, TV>(P, I, A, wsm, csm, inst, valid, A.list ? -1 : idx0, nvalid, A.mode, A.capA, A.capB > 0, A.reset);
     }
-    if (A.capB <= 0) { if (lane == 0) atomicMax((unsigned long long*)(A.counts + BMPC_CNT_T1), bmpc_globaltimer()); return; }
+    auto leave = [&]() {
+        if (lane != 0) return;
+        atomicMax((unsigned long long*)(A.counts + BMPC_CNT_T1), bmpc_globaltimer());
+        if (A.epoch == 0) return;
+        __threadfence();
+        if (atomicAdd(A.counts + BMPC_CNT_EXIT, 1) == (int)(gridDim.x * TPI_POL_WARPS) - 1) {
+            // last warp out: every counter of the launch is final.  Hand them to the host through mapped memory.
+            __threadfence();
+            volatile int32_t* src = (volatile int32_t*)A.counts; volatile int32_t* dst = (volatile int32_t*)A.host_counts;
+            for (int i = 0; i < BMPC_CNT_EXIT; i++) dst[i] = src[i];
+            __threadfence_system();
+            dst[BMPC_CNT_EPOCH] = A.epoch;
+        }
+    };
+    if (A.capB <= 0) { leave(); return; }
     // ---- phase B: serve the queue until every chunk of phase A is finished and the queue is empty.  Tickets: a warp takes the
     // next 32 queue slots with one fetch-and-add (no compare-and-swap races between a thousand warps) and waits until they are
     // filled or phase A has ended short of them, so batches are full while phase A still produces.
@@ -814,7 +831,7 @@ __global__ void __launch_bounds__(TPI_POL_WARPS * 32, 1) k_tpi_pol(const __grid_
         if constexpr (PERINST) { const TpiPolView<S> Pv(A.pview + (valid ? inst : 0), (size_t)A.pstride); tpi_pol_batch<S, TV>(Pv, I, A, wsm, csm, valid ? inst : 0, valid, -1, __popc(vmask), 0, A.capB, false, 0); }
         else tpi_pol_batch<S, TV>(P, I, A, wsm, csm, valid ? inst : 0, valid, -1, __popc(vmask), 0, A.capB, false, 0);
     }
-    if (lane == 0) atomicMax((unsigned long long*)(A.counts + BMPC_CNT_T1), bmpc_globaltimer());
+    leave();
 }
 
 // Compiled fast-path shapes (nx, nu, Np, Nc) with nu == 1 and Nc == Np: one line per shape in csrc/tpi_shapes.inc
@@ -848,9 +865,11 @@ struct bmpc_handle {
     int32_t *listA = nullptr, *listB = nullptr, *counts = nullptr;  // counts[8]: [0..3] round counters, [4..7] queue control of k_tpi_pol
     long long* gflags = nullptr; BmpcPeerFlags gpeers = {}; int g_npeer = 0, g_rank = 0, g_world = 1;   // K6 arrival flags
     int32_t* queue = nullptr; unsigned char* codes = nullptr;        // phase-B queue and stored working sets of the fast-path polish
-    int32_t* h_count = nullptr;                                      // pinned
+    int32_t* h_count = nullptr;                                      // pinned, mapped
+    int epoch = 0, spin_epoch = 0;                                   // launch epochs of the fast-path kernel's host notification
     cudaEvent_t ev[4];
     int xref_mode = 0;
+    bool sync_after_round = false;     // bmpc_output queued a result copy behind the round: wait for the stream, not only for the kernel
     bool is_setup = false, cold = true, solved = false, committed = true;   // committed: this solve's u0 already is the next u_-1
     bmpc_stats stats;
     std::string err;
@@ -896,6 +915,7 @@ static void launch_tpi_pol(bmpc_handle* h, const int32_t* list, int count, int m
     if (grid < 1) grid = 1;
     const size_t sm = L::per_warp * TPI_POL_WARPS;
     A.pview = h->tpi_view; A.pstride = h->cfg.batch;
+    A.host_counts = h->h_count; A.epoch = h->spin_epoch;
     if (h->tpi_view) {
         if (h->xref_mode) k_tpi_pol<S, true, true><<<grid, TPI_POL_WARPS * 32, sm, h->stream>>>(PP, h->I, A);
         else k_tpi_pol<S, false, true><<<grid, TPI_POL_WARPS * 32, sm, h->stream>>>(PP, h->I, A);
@@ -936,6 +956,7 @@ static void launch_tpi_round(bmpc_handle* h, const int32_t* list, int count, int
 // straggler rounds: the listed instances come back from an ADMM chunk of the team kernels, working sets from their iterate
 template <class S>
 static void launch_tpi_polish_only(bmpc_handle* h, const int32_t* list, int count, int32_t* next_list) {
+    h->spin_epoch = 0;
     launch_tpi_pol<S>(h, list, count, 2, 2, h->tpi_pdas_steps - 2, 0, next_list);
 }
 
@@ -1135,7 +1156,7 @@ int bmpc_create(const bmpc_config* cfg, bmpc_handle** out) {
     ok &= dalloc((void**)&h->vprev, sizeof(double) * (size_t)B * d.mc);
     ok &= dalloc((void**)&h->lprev, sizeof(int32_t) * (size_t)B);
     if (!ok) { h->err = "cudaMalloc failed"; cudaGetLastError(); return fail(BMPC_ERR_CUDA); }
-    if (cudaHostAlloc((void**)&h->h_count, sizeof(int32_t) * BMPC_CNT, cudaHostAllocDefault) != cudaSuccess) { h->err = "cudaHostAlloc failed"; return fail(BMPC_ERR_CUDA); }
+    if (cudaHostAlloc((void**)&h->h_count, sizeof(int32_t) * BMPC_CNT, cudaHostAllocMapped) != cudaSuccess) { h->err = "cudaHostAlloc failed"; return fail(BMPC_ERR_CUDA); }
     cudaMemset(h->sys, 0, sizeof(double) * (size_t)h->o.total * h->cfg.n_sys);
     cudaMemset(h->x0, 0, sizeof(double) * B * d.nx);
     cudaMemset(h->um1, 0, sizeof(double) * B * d.nu);
@@ -1385,7 +1406,9 @@ static int enqueue_round(bmpc_handle* h) {
         BMPC_CUDA(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 2 * BMPC_CNT, h->stream));     // this round's half and the next one's
     }
     BMPC_CUDA(cudaEventRecord(h->ev[0], h->stream));
+    h->spin_epoch = 0;
     if (tpi) {
+        if (st.chunk == 0) { h->epoch = (h->epoch % 1000000000) + 1; h->spin_epoch = h->epoch; ((volatile int32_t*)h->h_count)[BMPC_CNT_EPOCH] = 0; }
         g_tpi_table[h->tpi_kind - 1].launch(h, st.list, st.count, st.chunk, st.nxt, h->ev[1]);
     } else {
         // infeasible instances never pass the polish: from the third round on, look for OSQP's certificate
@@ -1406,7 +1429,7 @@ static int enqueue_round(bmpc_handle* h) {
     }
     h->I.um1 = h->um1_cur;
     BMPC_CUDA(cudaEventRecord(h->ev[2], h->stream));
-    BMPC_CUDA(cudaMemcpyAsync(h->h_count, cnt, sizeof(int32_t) * BMPC_CNT, cudaMemcpyDeviceToHost, h->stream));
+    if (!h->spin_epoch) BMPC_CUDA(cudaMemcpyAsync(h->h_count, cnt, sizeof(int32_t) * BMPC_CNT, cudaMemcpyDeviceToHost, h->stream));
     BMPC_CUDA(cudaGetLastError());
     return BMPC_OK;
 }
@@ -1414,9 +1437,21 @@ static int enqueue_round(bmpc_handle* h) {
 // waits for the round in flight; returns 1 in *more if another round was enqueued (stragglers), 0 if the solve is complete
 static int retire_round(bmpc_handle* h, int* more) {
     auto& st = h->st;
-    BMPC_CUDA(cudaStreamSynchronize(h->stream));
     float a = 0.f, p = 0.f;
-    cudaEventElapsedTime(&a, h->ev[0], h->ev[1]); cudaEventElapsedTime(&p, h->ev[1], h->ev[2]);
+    bool spun = false;
+    if (h->spin_epoch && !h->sync_after_round) {
+        // the kernel's last warp raises the epoch word in mapped host memory when every counter is final: a few microseconds
+        // after the kernel ends, instead of a D2H copy + cudaStreamSynchronize (the round trip sits in every step of a control loop)
+        volatile int32_t* flag = (volatile int32_t*)h->h_count + BMPC_CNT_EPOCH;
+        for (long spins = 0; *flag != h->spin_epoch; spins++)
+            if (spins > 200000000L) break;                              // ~ seconds: fall back to the stream
+        spun = *flag == h->spin_epoch;
+    }
+    if (!spun) {
+        BMPC_CUDA(cudaStreamSynchronize(h->stream));
+        if (h->spin_epoch && ((volatile int32_t*)h->h_count)[BMPC_CNT_EPOCH] != h->spin_epoch) { h->err = "fast-path kernel did not report"; return BMPC_ERR_CUDA; }
+        cudaEventElapsedTime(&a, h->ev[0], h->ev[1]); cudaEventElapsedTime(&p, h->ev[1], h->ev[2]);
+    }
     {   // a fast-path polish launch timed itself (global timer): more faithful than events, which also see launch gaps
         unsigned long long t0n, t1; memcpy(&t0n, h->h_count + BMPC_CNT_T0, 8); memcpy(&t1, h->h_count + BMPC_CNT_T1, 8);
         if (t1 != 0ull && t0n != 0ull && t1 > ~t0n) p = (float)((double)(t1 - ~t0n) * 1e-6);
@@ -1495,7 +1530,8 @@ int bmpc_output(bmpc_handle* h, double* u0, int32_t* status, int commit_uminus1,
         // speculate that the round in flight finishes everything (the common case): queue the result copy behind it so that a
         // single wait covers the solve and the read-back; redone if stragglers needed more rounds (they rewrite u0)
         if (!on_device) { int rc = copy_u(); if (rc) return rc; u_copied = true; }
-        int more = 0; int rc = retire_round(h, &more); if (rc) return rc;
+        h->sync_after_round = !on_device && want_u;
+        int more = 0; int rc = retire_round(h, &more); h->sync_after_round = false; if (rc) return rc;
         if (more) { u_copied = false; rc = finish_solve(h); if (rc) return rc; }
         else if (h->stats.launches && (h->st.count > 0 || !h->cfg.polish)) u_copied = false;   // k_finalize rewrote u0/status
     }

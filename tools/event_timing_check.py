@@ -5,7 +5,8 @@ B = 65536
 cfg, X0, Xref = pendulum_batch(B, "identical")
 K = make_controller(cfg, X0, Xref, B, 0); K.solve(); K.output()
 dev = torch.device("cuda", 0); L, h = K._L, K.handle
-stream = torch.cuda.Stream(dev); torch.cuda.synchronize(dev); torch.cuda.set_stream(stream)   # handle 0 would mean the library's own stream; L.bmpc_set_stream(h, stream.cuda_stream)
+stream = torch.cuda.Stream(dev); torch.cuda.synchronize(dev); torch.cuda.set_stream(stream)   # handle 0 would mean the library's own stream
+L.bmpc_set_stream(h, stream.cuda_stream)
 Ad = torch.tensor(cfg["Ad"], device=dev); Bd = torch.tensor(cfg["Bd"], device=dev)
 Xd = torch.tensor(X0, device=dev); Xn = torch.empty_like(Xd)
 U = [torch.zeros(B, 1, dtype=torch.float64, device=dev) for _ in range(2)]
