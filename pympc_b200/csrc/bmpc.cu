@@ -869,6 +869,7 @@ struct bmpc_handle {
     int epoch = 0, spin_epoch = 0;                                   // launch epochs of the fast-path kernel's host notification
     cudaEvent_t ev[4];
     int xref_mode = 0;
+    const int32_t* status_filled = nullptr;   // host status array last filled with BMPC_SOLVED everywhere (skip refilling it)
     bool sync_after_round = false;     // bmpc_output queued a result copy behind the round: wait for the stream, not only for the kernel
     bool is_setup = false, cold = true, solved = false, committed = true;   // committed: this solve's u0 already is the next u_-1
     bmpc_stats stats;
@@ -945,7 +946,7 @@ static void launch_tpi_round(bmpc_handle* h, const int32_t* list, int count, int
         cudaEventRecord(mid, h->stream);
         launch_tpi_pol<S>(h, list, count, 2, capA, capB, 0, next_list);
     } else {
-        cudaEventRecord(mid, h->stream);          // this round's counters were zeroed by the previous fast-path launch (or a memset)
+        // (this round's counters were zeroed by the previous fast-path launch, or by a memset)
         // working sets: stored ones (shifted one stage), or — when the last solve of the batch did not go through this kernel (cold
         // start on the team kernels) — from the iterate v
         launch_tpi_pol<S>(h, list, count, h->codes_valid ? (h->cfg.shift_warm ? 1 : 0) : 2, capA, capB, reset, next_list);
@@ -1405,10 +1406,11 @@ static int enqueue_round(bmpc_handle* h) {
         }
         BMPC_CUDA(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 2 * BMPC_CNT, h->stream));     // this round's half and the next one's
     }
-    BMPC_CUDA(cudaEventRecord(h->ev[0], h->stream));
     h->spin_epoch = 0;
+    if (tpi && st.chunk == 0) { h->epoch = (h->epoch % 1000000000) + 1; h->spin_epoch = h->epoch; ((volatile int32_t*)h->h_count)[BMPC_CNT_EPOCH] = 0; }
+    // (a warm fast-path round times itself with the global timer and reports through mapped memory: no event records in the stream)
+    if (!h->spin_epoch) BMPC_CUDA(cudaEventRecord(h->ev[0], h->stream));
     if (tpi) {
-        if (st.chunk == 0) { h->epoch = (h->epoch % 1000000000) + 1; h->spin_epoch = h->epoch; ((volatile int32_t*)h->h_count)[BMPC_CNT_EPOCH] = 0; }
         g_tpi_table[h->tpi_kind - 1].launch(h, st.list, st.count, st.chunk, st.nxt, h->ev[1]);
     } else {
         // infeasible instances never pass the polish: from the third round on, look for OSQP's certificate
@@ -1428,7 +1430,7 @@ static int enqueue_round(bmpc_handle* h) {
         else { k_check_converged<<<(st.count + 255) / 256, 256, 0, h->stream>>>(h->I, st.list, st.count, h->cfg.eps_abs, h->cfg.eps_rel, st.nxt, cnt); h->stats.launches++; }
     }
     h->I.um1 = h->um1_cur;
-    BMPC_CUDA(cudaEventRecord(h->ev[2], h->stream));
+    if (!h->spin_epoch) BMPC_CUDA(cudaEventRecord(h->ev[2], h->stream));
     if (!h->spin_epoch) BMPC_CUDA(cudaMemcpyAsync(h->h_count, cnt, sizeof(int32_t) * BMPC_CNT, cudaMemcpyDeviceToHost, h->stream));
     BMPC_CUDA(cudaGetLastError());
     return BMPC_OK;
@@ -1450,7 +1452,7 @@ static int retire_round(bmpc_handle* h, int* more) {
     if (!spun) {
         BMPC_CUDA(cudaStreamSynchronize(h->stream));
         if (h->spin_epoch && ((volatile int32_t*)h->h_count)[BMPC_CNT_EPOCH] != h->spin_epoch) { h->err = "fast-path kernel did not report"; return BMPC_ERR_CUDA; }
-        cudaEventElapsedTime(&a, h->ev[0], h->ev[1]); cudaEventElapsedTime(&p, h->ev[1], h->ev[2]);
+        if (!h->spin_epoch) { cudaEventElapsedTime(&a, h->ev[0], h->ev[1]); cudaEventElapsedTime(&p, h->ev[1], h->ev[2]); }
     }
     {   // a fast-path polish launch timed itself (global timer): more faithful than events, which also see launch gaps
         unsigned long long t0n, t1; memcpy(&t0n, h->h_count + BMPC_CNT_T0, 8); memcpy(&t1, h->h_count + BMPC_CNT_T1, 8);
@@ -1547,8 +1549,11 @@ int bmpc_output(bmpc_handle* h, double* u0, int32_t* status, int commit_uminus1,
     bool need_sync = false;
     if (!u_copied && want_u) { int rc = copy_u(); if (rc) return rc; need_sync = !on_device; }
     if (status) {
-        if (all_solved && !on_device) { for (size_t i = 0; i < B; i++) status[i] = BMPC_SOLVED; }
-        else { BMPC_CUDA(cudaMemcpyAsync(status, h->I.status, sizeof(int32_t) * B, kind, h->stream)); need_sync = !on_device; }
+        if (all_solved && !on_device) {
+            // (a closed loop asks with the same array every step: filled once while it stays all-solved)
+            if (h->status_filled != status) { for (size_t i = 0; i < B; i++) status[i] = BMPC_SOLVED; h->status_filled = status; }
+        }
+        else { BMPC_CUDA(cudaMemcpyAsync(status, h->I.status, sizeof(int32_t) * B, kind, h->stream)); need_sync = !on_device; h->status_filled = nullptr; }
     }
     if (need_sync) BMPC_CUDA(cudaStreamSynchronize(h->stream));
     return BMPC_OK;
