@@ -208,17 +208,24 @@ class Gather:
                 self.flags = symm_mem.empty((world,), dtype=torch.int64, device=dev); self.flags.zero_()
                 self.hf = symm_mem.rendezvous(self.flags, dist.group.WORLD)
                 self.peer_bufs = [int(p) for p in self.hs.buffer_ptrs]
-                peer_flags = [int(p) for r, p in enumerate(self.hf.buffer_ptrs) if r != rank]
-                arr = (ct.c_void_p * len(peer_flags))(*peer_flags)
-                assert L.bmpc_bind_gather_flags(h, self.flags.data_ptr(), arr, len(peer_flags), rank, world) == 0
-                dist.barrier(); torch.cuda.synchronize(dev)
+                self.peer_flags = [int(p) for r, p in enumerate(self.hf.buffer_ptrs) if r != rank]
                 self.fused = True
+                self.attach()
+                dist.barrier(); torch.cuda.synchronize(dev)
             except Exception as exc:                               # pragma: no cover
+                self.fused = False
                 if rank == 0:
                     print("symmetric memory unavailable, using the NCCL all-gather:", exc, file=sys.stderr)
         if not self.fused:
             self.buf = torch.zeros(2, self.Btot, nu, dtype=torch.float64, device=dev)
         self.bind(0)
+
+    def attach(self):
+        """(re)bind the arrival flags to the controller's current handle (setup() creates a new one)"""
+        if self.fused:
+            import ctypes as ct
+            arr = (ct.c_void_p * len(self.peer_flags))(*self.peer_flags)
+            assert self.K._L.bmpc_bind_gather_flags(self.K.handle, self.flags.data_ptr(), arr, len(self.peer_flags), self.rank, self.world) == 0
 
     def bind(self, parity):
         """point the solver epilogue at this step's half of the gathered buffer (own slice + the same slice of every peer)"""
@@ -320,6 +327,8 @@ def e2e_loop(torch, dist, K, cfg, X0, steps, warmup, dev, world, gather, flush):
     Xh = K.pinned_buffer("x0"); Uh = K.pinned_buffer("uminus1")
     Xh[...] = X0; Uh[...] = 0.0
     K.setup(solve=True); K.output()
+    L, h = K._L, K.handle
+    gather.attach()
     Adn, Bdn = cfg["Ad"], cfg["Bd"]
     e2e_t = 0.0
     for t in range(warmup + steps):
