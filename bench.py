@@ -225,7 +225,7 @@ class Gather:
         if self.fused:
             import ctypes as ct
             arr = (ct.c_void_p * len(self.peer_flags))(*self.peer_flags)
-            assert self.K._L.bmpc_bind_gather_flags(self.K.handle, self.flags.data_ptr(), arr, len(self.peer_flags), self.rank, self.world) == 0
+            assert self.K._L.bmpc_bind_gather_flags(self.K.handle, self.flags.data_ptr(), arr, len(self.peer_flags), self.rank, self.world, self.epoch) == 0
 
     def bind(self, parity):
         """point the solver epilogue at this step's half of the gathered buffer (own slice + the same slice of every peer)"""
@@ -450,7 +450,7 @@ def gpu_arm(args, rank, world, local_rank):
     value = Btot * args.steps / (tot_ms_max * 1e-3)
     par = f"batch-shard x{world}"
     if world > 1:
-        par += (", u* gathered by peer stores fused into the solver epilogue (NVLink symmetric memory, double-buffered) + 1 arrival-flag kernel/step"
+        par += (", u* gathered by peer stores fused into the solver epilogue (NVLink symmetric memory, double-buffered), arrival flags raised and awaited by the solver kernel's last warp (no collective, no extra launch)"
                 if G.fused else ", 1 NCCL all-gather of u*/step")
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -58,6 +58,7 @@ typedef struct {
     int32_t n_sys;              /* 1 = every instance shares (Ad,Bd,weights,bounds); batch = one system per instance */
     int32_t shift_warm;         /* 1 (default) = a warm fast-path solve starts from the previous working sets shifted by one stage (receding horizon: update() is one sample later); 0 = unshifted */
     int32_t candidate_warm;     /* 1 = an instance the polish could not verify AND whose ADMM is stalled (relative primal residual > 1e-2 after >= 25 iterations) continues its ADMM rounds from the last candidate (rows and multipliers) when that candidate's hard rows are feasible to 1e-2: the remedy for strongly violated soft rows with a large eps_feas; 0 (default) = from its own ADMM state: on regular transients replacing the iterate costs a few instances their verification */
+    int32_t cold_iters;         /* ADMM iterations before the first polish attempt of a COLD solve on the team / tile kernels (0 = auto: 50) */
     double eps_feas;            /* slack weight (mpc.py:226) */
     double rho;                 /* <= 0: automatic sqrt(trace H / trace A'A) */
     double sigma, alpha;        /* OSQP defaults 1e-6, 1.6 */
@@ -116,12 +117,16 @@ int bmpc_bind_output(bmpc_handle* h, double* dev_u0);
  * the all-gather collective; the caller only needs a cross-rank barrier before reading.  n = 0 unbinds. */
 int bmpc_bind_output_peers(bmpc_handle* h, double* const* peer_u0, int n);
 /* K6 arrival: my_flags is this rank's DEVICE array of `world` int64 counters (zero-initialised), peer_flags[p] the same array
- * of peer p as mapped into this process (symmetric memory).  bmpc_gather_arrive(epoch) launches one small kernel behind the
- * solver kernels that stores `epoch` into slot `rank` of every peer's array and waits until every peer's slot here holds a
- * value >= epoch: when it completes, every peer's u* of this step has landed in the buffer bound with bmpc_bind_output_peers.
- * Epochs must increase by one per step on all ranks.  Use two gathered buffers alternately (step parity) so that the stores
- * of step t+1 cannot overwrite data a slower peer is still reading from step t. */
-int bmpc_bind_gather_flags(bmpc_handle* h, int64_t* my_flags, int64_t* const* peer_flags, int n_peers, int rank, int world);
+ * of peer p as mapped into this process (symmetric memory).  From then on every bmpc_solve is one arrival epoch (base_epoch + 1,
+ * + 2, ...; all ranks solve in lockstep).  Arrival = store the epoch into slot `rank` of every peer's array and wait until every
+ * peer's slot here holds a value >= epoch: then every peer's u* of this step has landed in the buffer bound with
+ * bmpc_bind_output_peers.  A warm fast-path solve that finishes every instance does this in the last warp of the solver kernel
+ * itself (no launch); otherwise bmpc_gather_arrive launches one small kernel behind the straggler rounds.  Call
+ * bmpc_gather_arrive after bmpc_output in every step (it is a no-op when the kernel already arrived); its epoch argument is
+ * ignored.  Rebinding (a new handle) continues at base_epoch = the number of solves the ranks have gathered so far.  Use two
+ * gathered buffers alternately (step parity) so that the stores of step t+1 cannot overwrite data a slower peer is still
+ * reading from step t. */
+int bmpc_bind_gather_flags(bmpc_handle* h, int64_t* my_flags, int64_t* const* peer_flags, int n_peers, int rank, int world, int64_t base_epoch);
 int bmpc_gather_arrive(bmpc_handle* h, int64_t epoch);
 int bmpc_set_stream(bmpc_handle* h, void* cuda_stream);   /* NULL = handle-owned stream */
 int bmpc_synchronize(bmpc_handle* h);

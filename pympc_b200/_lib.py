@@ -17,7 +17,7 @@ DP = ctypes.c_void_p
 class BmpcConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
                 ("nx", "nu", "Np", "Nc", "batch", "device", "soft_on", "max_iter", "first_iters", "pdas_steps",
-                 "rmax", "polish", "team_threads", "warps_per_block", "fast_path", "n_sys", "shift_warm", "candidate_warm")] + \
+                 "rmax", "polish", "team_threads", "warps_per_block", "fast_path", "n_sys", "shift_warm", "candidate_warm", "cold_iters")] + \
                [(n, ctypes.c_double) for n in ("eps_feas", "rho", "sigma", "alpha", "eps_abs", "eps_rel")]
 
 
@@ -65,7 +65,7 @@ def load(path=None):
     L.bmpc_bind_output.argtypes = [P, DP]; L.bmpc_bind_output.restype = ctypes.c_int
     L.bmpc_set_stream.argtypes = [P, P]; L.bmpc_set_stream.restype = ctypes.c_int
     L.bmpc_bind_output_peers.argtypes = [P, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]; L.bmpc_bind_output_peers.restype = ctypes.c_int
-    L.bmpc_bind_gather_flags.argtypes = [P, P, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int]; L.bmpc_bind_gather_flags.restype = ctypes.c_int
+    L.bmpc_bind_gather_flags.argtypes = [P, P, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64]; L.bmpc_bind_gather_flags.restype = ctypes.c_int
     L.bmpc_gather_arrive.argtypes = [P, ctypes.c_int64]; L.bmpc_gather_arrive.restype = ctypes.c_int
     L.bmpc_synchronize.argtypes = [P]; L.bmpc_synchronize.restype = ctypes.c_int
     L.bmpc_get_stats.argtypes = [P, ctypes.POINTER(BmpcStats)]; L.bmpc_get_stats.restype = ctypes.c_int

@@ -561,6 +561,7 @@ struct TpiPolArgs {
     int reset;                           // first round of a solve: per-solve bookkeeping rides here
     int32_t* counts_next;                // the 8 counters of the NEXT round: zeroed here (saves a memset launch per solve)
     int32_t* host_counts; int epoch;     // mapped pinned copy of the counters + the value the last warp stores into its epoch slot (0: off)
+    long long* gflags; BmpcPeerFlags gpeers; int g_npeer, g_rank, g_world; long long g_epoch;   // K6 arrival folded into this launch (g_epoch 0: off)
     int32_t* next_list; int32_t* counts; // counts[0] unfinished (-> next_list), [1] refinements; counts[4..7] queue control, see below
     int32_t* queue; int qcap;            // phase-B queue (capacity qcap), all -1 between launches (consumers clear what they take)
     double* u0_out; double* um1_solved;
@@ -792,12 +793,32 @@ __global__ void __launch_bounds__(TPI_POL_WARPS * 32, 1) k_tpi_pol(const __grid_
         if (lane != 0) return;
         atomicMax((unsigned long long*)(A.counts + BMPC_CNT_T1), bmpc_globaltimer());
         if (A.epoch == 0) return;
-        __threadfence();
+        if (A.g_epoch > 0) __threadfence_system(); else __threadfence();     // this warp's u* stores (peers included) before its exit count
         if (atomicAdd(A.counts + BMPC_CNT_EXIT, 1) == (int)(gridDim.x * TPI_POL_WARPS) - 1) {
-            // last warp out: every counter of the launch is final.  Hand them to the host through mapped memory.
+            // last warp out: every counter of the launch is final.
             __threadfence();
             volatile int32_t* src = (volatile int32_t*)A.counts; volatile int32_t* dst = (volatile int32_t*)A.host_counts;
+            int gathered = 0;
+            if (A.g_epoch > 0 && src[0] == 0) {
+                // K6 arrival without a launch of its own: every instance of this rank is final and stored in every peer's gathered
+                // buffer -> raise this rank's flag at the peers, then wait for theirs: when this kernel ends the gathered buffer of
+                // the step is complete here.  (Instances left for straggler rounds: the host calls bmpc_gather_arrive afterwards.)
+                __threadfence_system();
+                for (int pr = 0; pr < A.g_npeer; pr++) *(volatile long long*)(A.gpeers.p[pr] + A.g_rank) = A.g_epoch;
+                const long long t0 = clock64();
+                for (int r = 0; r < A.g_world; r++) {
+                    if (r == A.g_rank) continue;
+                    while (*(volatile long long*)(A.gflags + r) < A.g_epoch) {
+                        if (clock64() - t0 > 20000000000ll) __trap();        // ~10 s: a peer died; fail loudly instead of hanging the GPU
+                        __nanosleep(100);
+                    }
+                }
+                __threadfence_system();
+                gathered = 1;
+            }
+            // ... and hand the counters to the host through mapped memory
             for (int i = 0; i < BMPC_CNT_EXIT; i++) dst[i] = src[i];
+            dst[BMPC_CNT_TIGHT + 1] = gathered;
             __threadfence_system();
             dst[BMPC_CNT_EPOCH] = A.epoch;
         }
@@ -864,6 +885,7 @@ struct bmpc_handle {
     double *seq_x = nullptr, *seq_e = nullptr, *seq_obj = nullptr;
     int32_t *listA = nullptr, *listB = nullptr, *counts = nullptr;  // counts[8]: [0..3] round counters, [4..7] queue control of k_tpi_pol
     long long* gflags = nullptr; BmpcPeerFlags gpeers = {}; int g_npeer = 0, g_rank = 0, g_world = 1;   // K6 arrival flags
+    long long g_epoch = 0, g_done_epoch = 0;       // one epoch per solve while flags are bound; the last epoch whose arrival is complete
     int32_t* queue = nullptr; unsigned char* codes = nullptr;        // phase-B queue and stored working sets of the fast-path polish
     int32_t* h_count = nullptr;                                      // pinned, mapped
     int epoch = 0, spin_epoch = 0;                                   // launch epochs of the fast-path kernel's host notification
@@ -917,6 +939,8 @@ static void launch_tpi_pol(bmpc_handle* h, const int32_t* list, int count, int m
     const size_t sm = L::per_warp * TPI_POL_WARPS;
     A.pview = h->tpi_view; A.pstride = h->cfg.batch;
     A.host_counts = h->h_count; A.epoch = h->spin_epoch;
+    A.gflags = h->gflags; A.gpeers = h->gpeers; A.g_npeer = h->g_npeer; A.g_rank = h->g_rank; A.g_world = h->g_world;
+    A.g_epoch = (h->gflags && h->spin_epoch && h->g_world > 1) ? h->g_epoch : 0;
     if (h->tpi_view) {
         if (h->xref_mode) k_tpi_pol<S, true, true><<<grid, TPI_POL_WARPS * 32, sm, h->stream>>>(PP, h->I, A);
         else k_tpi_pol<S, false, true><<<grid, TPI_POL_WARPS * 32, sm, h->stream>>>(PP, h->I, A);
@@ -1007,7 +1031,7 @@ void bmpc_default_config(bmpc_config* c) {
     memset(c, 0, sizeof(*c));
     c->Np = 20; c->Nc = 0; c->batch = 1; c->device = 0; c->soft_on = 1;
     c->max_iter = 4000; c->first_iters = 0; c->pdas_steps = 10; c->rmax = 0; c->polish = 1;
-    c->team_threads = 0; c->warps_per_block = 0; c->fast_path = 1; c->n_sys = 1; c->shift_warm = 1; c->candidate_warm = 0;
+    c->team_threads = 0; c->warps_per_block = 0; c->fast_path = 1; c->n_sys = 1; c->shift_warm = 1; c->candidate_warm = 0; c->cold_iters = 0;
     c->eps_feas = 1e6; c->rho = 0.0; c->sigma = 1e-6; c->alpha = 1.6; c->eps_abs = 1e-3; c->eps_rel = 1e-3;
 }
 
@@ -1225,9 +1249,10 @@ int bmpc_bind_output_peers(bmpc_handle* h, double* const* peer_u0, int n) {
     return BMPC_OK;
 }
 
-int bmpc_bind_gather_flags(bmpc_handle* h, int64_t* my_flags, int64_t* const* peer_flags, int n_peers, int rank, int world) {
+int bmpc_bind_gather_flags(bmpc_handle* h, int64_t* my_flags, int64_t* const* peer_flags, int n_peers, int rank, int world, int64_t base_epoch) {
     if (!h || n_peers < 0 || n_peers > 8 || world < 1 || world > 9 || rank < 0 || rank >= world || (n_peers > 0 && (!my_flags || !peer_flags))) return BMPC_ERR_ARG;
     h->gflags = (long long*)my_flags; h->g_npeer = n_peers; h->g_rank = rank; h->g_world = world;
+    h->g_epoch = h->g_done_epoch = base_epoch;
     for (int p = 0; p < n_peers; p++) h->gpeers.p[p] = (long long*)peer_flags[p];
     return BMPC_OK;
 }
@@ -1237,7 +1262,10 @@ int bmpc_gather_arrive(bmpc_handle* h, int64_t epoch) {
     if (!h->gflags) { h->err = "bmpc_gather_arrive before bmpc_bind_gather_flags"; return BMPC_ERR_STATE; }
     BMPC_CUDA(cudaSetDevice(h->cfg.device));
     if (h->pending) { int rc = finish_solve(h); if (rc) return rc; }
-    k_gather_arrive<<<1, 32, 0, h->stream>>>(h->gflags, h->gpeers, h->g_npeer, h->g_rank, h->g_world, (long long)epoch);
+    (void)epoch;                                       // the library counts the epochs itself (one per solve on every rank)
+    if (h->g_done_epoch == h->g_epoch) return BMPC_OK;  // the solver kernel's last warp already signalled and waited
+    k_gather_arrive<<<1, 32, 0, h->stream>>>(h->gflags, h->gpeers, h->g_npeer, h->g_rank, h->g_world, h->g_epoch);
+    h->g_done_epoch = h->g_epoch;
     BMPC_CUDA(cudaGetLastError());
     return BMPC_OK;
 }
@@ -1466,6 +1494,7 @@ static int retire_round(bmpc_handle* h, int* more) {
     h->stats.polish_steps += h->h_count[1];
     h->stats.infeasible += h->h_count[3];
     st.tight += h->h_count[BMPC_CNT_TIGHT];
+    if (spun && h->h_count[BMPC_CNT_TIGHT + 1] == 1) h->g_done_epoch = h->g_epoch;
     st.list = st.nxt; int32_t* tmp = st.cur; st.cur = st.nxt; st.nxt = tmp;
     // polish mode: cumulative first_iters, 25, 50, 100, ...; pure ADMM: OSQP's check_termination = 25
     st.chunk = h->cfg.polish ? (st.total < 25 ? 25 - st.total : st.total) : 25;
@@ -1501,6 +1530,7 @@ int bmpc_solve(bmpc_handle* h) {
     auto& st = h->st;
     st.list = nullptr; st.count = B; st.cur = h->listA; st.nxt = h->listB;
     st.total = 0; st.round = 0; st.need_prep = true; st.tight = 0;
+    if (h->gflags) h->g_epoch++;                     // every rank solves in lockstep: the arrival epoch of this step
     // first round: NO ADMM iterations on a warm fast-path solve (the previous solution's working sets are the best first guess
     // the active-set polish can get: measured 0 vs 1..10 iterations), 10 on the team kernels; first_iters > 0 overrides
     const bool fast = h->tpi_kind != 0;
@@ -1508,6 +1538,9 @@ int bmpc_solve(bmpc_handle* h) {
     // a cold start has no active-set guess to refresh: 25 iterations at once on the fast path, so that the first polish
     // usually verifies and the whole batch does not take the straggler route
     if (h->cfg.polish && h->cfg.first_iters <= 0 && fast && h->cold) st.chunk = 25;
+    // team / tile kernels, cold: 10 iterations from the free response leave working sets of hundreds of rows for the Schur polish
+    // (round 1 measured 180 ms launches on the MIMO shape): iterate longer before the first attempt
+    if (h->cfg.polish && h->cfg.first_iters <= 0 && !fast && h->cold) st.chunk = h->cfg.cold_iters > 0 ? h->cfg.cold_iters : 50;
     if (h->cfg.polish && fast && h->tpi_view && !h->cold && h->cfg.first_iters > 0) st.chunk = h->cfg.first_iters;
     if (st.chunk > h->cfg.max_iter) st.chunk = h->cfg.max_iter;
     int rc = enqueue_round(h);
