@@ -157,7 +157,9 @@ int bmpc_est_set_stream(bmpc_estimator* e, void* cuda_stream);
  * a predict/update that takes a device pointer first retires the controller's deferred solve.  h = NULL detaches. */
 int bmpc_est_attach(bmpc_estimator* e, bmpc_handle* h);
 
-/* pinned host memory for the end-to-end path (cudaHostAlloc / cudaFreeHost) */
+/* pinned host memory for the end-to-end path (cudaHostAlloc mapped + portable / cudaFreeHost): the GPU can read and write it in place,
+ * so such a buffer may be passed to bmpc_update(..., on_device = 2) and to bmpc_bind_output — the solver kernels then fetch x0 / u_-1
+ * over PCIe while they compute and store u* straight into host memory: no H2D / D2H copy phases around the solve */
 void* bmpc_host_alloc(uint64_t bytes);
 void bmpc_host_free(void* p);
 /* 1 if this build of the library holds the thread-per-instance fast path for the shape (nu == 1; Nc <= 0 means Nc = Np) */

@@ -793,7 +793,7 @@ __global__ void __launch_bounds__(TPI_POL_WARPS * 32, 1) k_tpi_pol(const __grid_
         if (lane != 0) return;
         atomicMax((unsigned long long*)(A.counts + BMPC_CNT_T1), bmpc_globaltimer());
         if (A.epoch == 0) return;
-        if (A.g_epoch > 0) __threadfence_system(); else __threadfence();     // this warp's u* stores (peers included) before its exit count
+        __threadfence_system();                 // this warp's u* stores (to peers / to mapped host memory too) before its exit count
         if (atomicAdd(A.counts + BMPC_CNT_EXIT, 1) == (int)(gridDim.x * TPI_POL_WARPS) - 1) {
             // last warp out: every counter of the launch is final.
             __threadfence();
@@ -1052,7 +1052,9 @@ const char* bmpc_last_error(const bmpc_handle* h) { return h ? h->err.c_str() : 
 
 void* bmpc_host_alloc(uint64_t bytes) {
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    // mapped + portable: the device can read / write the buffer in place (bmpc_update on_device = 2, bmpc_bind_output): with unified
+    // addressing the host pointer is the device pointer
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return p;
 }
 void bmpc_host_free(void* p) { if (p) cudaFreeHost(p); }
@@ -1430,7 +1432,7 @@ static int enqueue_round(bmpc_handle* h) {
             const int B = h->cfg.batch;
             k_reset<<<(B + 255) / 256, 256, 0, h->stream>>>(h->I, B);
             h->stats.launches++;
-            BMPC_CUDA(cudaMemcpyAsync(h->um1_solved, h->um1_cur, sizeof(double) * (size_t)B * h->d.nu, cudaMemcpyDeviceToDevice, h->stream));
+            BMPC_CUDA(cudaMemcpyAsync(h->um1_solved, h->um1_cur, sizeof(double) * (size_t)B * h->d.nu, cudaMemcpyDefault, h->stream));   // (um1_cur may be mapped host memory)
         }
         BMPC_CUDA(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * 2 * BMPC_CNT, h->stream));     // this round's half and the next one's
     }

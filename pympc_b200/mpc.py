@@ -216,6 +216,9 @@ class MPCController:
 
         self.device = int(device)
         self.solver_options = dict(solver_options)
+        # zero_copy (default on): the kernels read x0 / u_-1 from, and write u* to, pinned host memory in place (see _push / solve)
+        self._zero_copy = bool(self.solver_options.pop("zero_copy", True))
+        self._bound_u = None
         self._L = _lib.load()                      # raises if the CUDA extension is missing
         self._h = None
         self.res = None
@@ -315,6 +318,7 @@ class MPCController:
         self.uminus1_rh = np.copy(self.uminus1)
         if self._h is not None:
             L.bmpc_destroy(self._h); self._h = None
+        self._bound_u = None
         cfg = BmpcConfig(); L.bmpc_default_config(cfg)
         cfg.nx, cfg.nu, cfg.Np, cfg.Nc, cfg.batch, cfg.device = nx, nu, self.Np, self.Nc, B, self.device
         cfg.soft_on = 1 if self.SOFT_ON else 0
@@ -388,7 +392,10 @@ class MPCController:
                           "running on the generic team kernels (about 15x slower)")
             return L
 
-    def _push(self, x0, um1, xref):
+    def _push(self, x0, um1, xref, borrow=False):
+        """hand (x0, u_-1, xref) to the device.  borrow=True: x0 / u_-1 sit in pinned, device-mapped staging buffers that the
+        solver kernels read IN PLACE over PCIe while they compute (no H2D copy phase) — only valid when the solve is issued and
+        retired before the buffers can change, i.e. from update(..., solve=True)"""
         B, nx, nu = self._B, self.nx, self.nu
         px = pu = pr = None; rows = 1
         if x0 is not None:
@@ -398,7 +405,9 @@ class MPCController:
         if xref is not None:
             arr, rows = self._xref_device_layout(xref)
             pr = ptr(self._stage("xref" if rows == 1 else "xref_tv", arr, arr.shape))
-        self._check(self._L.bmpc_update(self._h, px, pu, pr, rows, 0))
+        if borrow and pr is not None:
+            self._check(self._L.bmpc_update(self._h, None, None, pr, rows, 0)); pr = None      # xref is always copied
+        self._check(self._L.bmpc_update(self._h, px, pu, pr, rows, 2 if borrow else 0))
 
     def update(self, x, u=None, xref=None, solve=True):
         """New measurement (and optionally u_{-1}, xref); re-solve warm-started.  mpc.py:338-364."""
@@ -411,7 +420,7 @@ class MPCController:
             self.xref = xref
         # u=None: the device already holds the previously output control as uminus1 (committed by output(), Q9)
         self._um1_for_J = self.uminus1_rh
-        self._push(x, u, xref)
+        self._push(x, u, xref, borrow=bool(solve) and self._zero_copy)
         self._J_dirty = True           # J_CNST is recomputed lazily (it is O(B) host work and rarely read)
         if solve:
             self.solve()
@@ -429,10 +438,13 @@ class MPCController:
 
     def solve(self):
         """Solve the QP batch.  mpc.py:366-375."""
-        self._check(self._L.bmpc_solve(self._h))
         B, nu = self._B, self.nu
         u = self._pin.get("u") or self._pin.setdefault("u", PinnedArray((B, nu)))
         st = self._pin.get("status") or self._pin.setdefault("status", PinnedArray((B,), np.int32))
+        if self._zero_copy and self._bound_u != u.array.ctypes.data:
+            # the solver epilogue stores u* straight into the pinned (device-mapped) result array: no D2H copy after the solve
+            self._check(self._L.bmpc_bind_output(self._h, ptr(u.array))); self._bound_u = u.array.ctypes.data
+        self._check(self._L.bmpc_solve(self._h))
         self._check(self._L.bmpc_output(self._h, ptr(u.array), ptr(st.array), 0, 0))
         self._u0, self._status = u.array, st.array
         self._make_res()
