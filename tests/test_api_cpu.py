@@ -105,3 +105,26 @@ def test_fast_path_table_query_and_on_demand_shape_build(bmpc_lib):
     for bad in ((4, 2, 20, None), (8, 1, 20, None), (2, 1, 40, None), (3, 1, 10, 11)):
         with pytest.raises(ValueError):
             build.jit_shape(*bad)
+
+
+def test_output_arrays_are_reused_only_when_the_caller_dropped_them():
+    """output() returns an array the caller owns (like the reference's fresh array per call); arrays handed out earlier are
+    recycled only once nobody references them — never while the caller (or uminus1_rh) still holds them"""
+    from pympc_b200.mpc import MPCController
+    class Fake:
+        pass
+    f = Fake(); f._out_pool = []; f.uminus1_rh = None; f._u0 = np.arange(16384.0).reshape(-1, 1)
+    fresh = MPCController._fresh_output
+    a = fresh(f); f.uminus1_rh = a
+    b = fresh(f); f.uminus1_rh = b
+    assert a is not b and np.array_equal(a, f._u0)
+    ida = id(a); del a
+    c = fresh(f); f.uminus1_rh = c
+    assert id(c) == ida                                   # the dropped one came back
+    keep = [c]
+    d = fresh(f); f.uminus1_rh = d
+    e = fresh(f); f.uminus1_rh = e
+    assert d is not c and e is not c and e is not d
+    for t in range(10):                                   # a plain closed loop cycles through two arrays
+        U = fresh(f); f.uminus1_rh = U
+    assert len(f._out_pool) <= 5

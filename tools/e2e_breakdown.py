@@ -15,19 +15,9 @@ L, h = K._L, K.handle
 from pympc_b200._lib import ptr
 acc = np.zeros(6); n = 0
 for t in range(60):
-    t0 = time.perf_counter(); K.update(Xh, Uh, solve=False); t1 = time.perf_counter(); K.solve(); t2 = time.perf_counter(); U = K.output(); t3 = time.perf_counter()
+    t0 = time.perf_counter(); K.update(Xh, Uh); t1 = time.perf_counter(); t2 = t1; U = K.output(); t3 = time.perf_counter()
     Uh[...] = U; Xh[...] = Xh @ cfg["Ad"].T + U @ cfg["Bd"].T
     if t >= 10:
         acc[:3] += (t1 - t0, t2 - t1, t3 - t2); n += 1
-print("python API  : update %.1f us  solve %.1f us  output %.1f us  total %.1f us" % (*(1e6 * acc[:3] / n), 1e6 * acc[:3].sum() / n))
-# raw C ABI with the same buffers
-u = K._pin["u"].array; st = K._pin["status"].array
-acc = np.zeros(4); n = 0
-for t in range(60):
-    t0 = time.perf_counter(); L.bmpc_update(h, ptr(Xh), ptr(Uh), None, 1, 0); t1 = time.perf_counter(); L.bmpc_solve(h); t2 = time.perf_counter()
-    L.bmpc_output(h, ptr(u), ptr(st), 1, 0); t3 = time.perf_counter()
-    Uh[...] = u; Xh[...] = Xh @ cfg["Ad"].T + u @ cfg["Bd"].T
-    if t >= 10:
-        acc[:3] += (t1 - t0, t2 - t1, t3 - t2); n += 1
-print("raw C calls : update %.1f us  solve %.1f us  output %.1f us  total %.1f us" % (*(1e6 * acc[:3] / n), 1e6 * acc[:3].sum() / n))
+print("python API  : update+solve %.1f us  (-) %.1f us  output %.1f us  total %.1f us" % (*(1e6 * acc[:3] / n), 1e6 * acc[:3].sum() / n))
 K.close()
