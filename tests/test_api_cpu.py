@@ -127,4 +127,4 @@ def test_output_arrays_are_reused_only_when_the_caller_dropped_them():
     assert d is not c and e is not c and e is not d
     for t in range(10):                                   # a plain closed loop cycles through two arrays
         U = fresh(f); f.uminus1_rh = U
-    assert len(f._out_pool) <= 5
+    assert len(f._out_pool) <= 7                          # b, c, d, e are still held by this test; the loop itself needs two
