@@ -19,6 +19,7 @@
 #include "bmpc_core.cuh"
 #include "bmpc_tpi.cuh"
 #include "bmpc_tile.cuh"
+#include "bmpc_tpm.cuh"
 
 // One block of round counters = BMPC_CNT ints (the handle keeps two, used alternately): [0] instances still unfinished (-> next list),
 // [1] active-set refinements, [2] overflow of the small polish tier, [3] certified infeasible, [4..7] queue control of k_tpi_pol
@@ -586,7 +587,8 @@ struct TpiPolLayout {
 // one batch of up to 32 instances (one per lane) through up to cap refinements; returns the mask of verified lanes
 template <class S, bool TV, class PP>
 __device__ __forceinline__ void tpi_pol_batch(const PP& P, const BmpcInst& I, const TpiPolArgs& A, double* wsm, typename TpiCode<S>::type* csm,
-                                              int inst, bool valid_in, int inst0_contig, int nvalid, int mode, int cap, bool to_queue, int reset) {
+                                              int inst, bool valid_in, int inst0_contig, int nvalid, int mode, int cap, bool to_queue, int reset,
+                                              const double* x0_pre = nullptr, double um1_pre = 0.0) {
     bool valid = valid_in;
     using L = TpiPolLayout<S>; using CT = typename TpiCode<S>::type;
     constexpr int nx = S::nx;
@@ -595,8 +597,11 @@ __device__ __forceinline__ void tpi_pol_batch(const PP& P, const BmpcInst& I, co
     auto C = [&](int k) -> CT& { return csm[k * 32 + lane]; };
     double x0[nx], xref[nx], um1 = 0.0, mumax = 0.0, vq = 0.0;
 #pragma unroll
-    for (int q = 0; q < nx; q++) { x0[q] = valid ? I.x0[(size_t)inst * nx + q] : 0.0; xref[q] = (valid && !TV) ? I.xref[(size_t)inst * nx + q] : 0.0; }
-    if (valid) um1 = I.um1[(size_t)inst];
+    for (int q = 0; q < nx; q++) {
+        x0[q] = x0_pre ? x0_pre[q] : (valid ? I.x0[(size_t)inst * nx + q] : 0.0);       // phase A: fetched while the previous chunk was computing
+        xref[q] = (valid && !TV) ? I.xref[(size_t)inst * nx + q] : 0.0;
+    }
+    um1 = x0_pre ? um1_pre : (valid ? I.um1[(size_t)inst] : 0.0);
     const TpiXref<S, TV> xr{TV ? I.xref + (size_t)inst * S::NX : xref};
     unsigned char* rec = A.codes + (size_t)inst * A.code_stride;
     if (mode == 2) {
@@ -777,17 +782,35 @@ __global__ void __launch_bounds__(TPI_POL_WARPS * 32, 1) k_tpi_pol(const __grid_
     const int nchunks = (A.count + 31) / 32;
     if (blockIdx.x == 0 && threadIdx.x < BMPC_CNT) A.counts_next[threadIdx.x] = 0;
     if (threadIdx.x == 0) atomicMax((unsigned long long*)(A.counts + BMPC_CNT_T0), ~bmpc_globaltimer());
-    // ---- phase A
-    for (;;) {
-        int chunk = 0;
-        if (lane == 0) chunk = atomicAdd(A.counts + TPI_Q_CURSOR, 1);
-        chunk = __shfl_sync(0xffffffffu, chunk, 0);
-        if (chunk >= nchunks) break;
-        const int idx0 = chunk * 32, nvalid = (A.count - idx0) < 32 ? (A.count - idx0) : 32;
-        const bool valid = lane < nvalid;
-        const int inst = A.list ? (valid ? A.list[idx0 + lane] : 0) : idx0 + lane;
-        if constexpr (PERINST) { const TpiPolView<S> Pv(A.pview + inst, (size_t)A.pstride); tpi_pol_batch<S, TV>(Pv, I, A, wsm, csm, inst, valid, A.list ? -1 : idx0, nvalid, A.mode, A.capA, A.capB > 0, A.reset); }
-        else tpi_pol_batch<S, TV>(P, I, A, wsm, csm, inst, valid, A.list ? -1 : idx0, nvalid, A.mode, A.capA, A.capB > 0, A.reset);
+    // ---- phase A.  x0 and u_-1 of the NEXT chunk are requested before the current chunk is processed: they may live in mapped host
+    // memory (the end-to-end path reads them over PCIe in place), and a refinement is long enough to hide that latency completely
+    auto grab = [&]() { int c = 0; if (lane == 0) c = atomicAdd(A.counts + TPI_Q_CURSOR, 1); return __shfl_sync(0xffffffffu, c, 0); };
+    auto locate = [&](int chunk, int& idx0, int& nvalid, bool& valid, int& inst) {
+        idx0 = chunk * 32; nvalid = (A.count - idx0) < 32 ? (A.count - idx0) : 32;
+        valid = lane < nvalid; inst = A.list ? (valid ? A.list[idx0 + lane] : 0) : idx0 + lane;
+    };
+    double x0n[S::nx], um1n = 0.0;
+    int chunk = grab();
+    if (chunk < nchunks) {
+        int idx0, nvalid, inst; bool valid; locate(chunk, idx0, nvalid, valid, inst);
+#pragma unroll
+        for (int q = 0; q < S::nx; q++) x0n[q] = valid ? I.x0[(size_t)inst * S::nx + q] : 0.0;
+        um1n = valid ? I.um1[(size_t)inst] : 0.0;
+    }
+    while (chunk < nchunks) {
+        int idx0, nvalid, inst; bool valid; locate(chunk, idx0, nvalid, valid, inst);
+        double x0c[S::nx]; const double um1c = um1n;
+#pragma unroll
+        for (int q = 0; q < S::nx; q++) x0c[q] = x0n[q];
+        chunk = grab();
+        if (chunk < nchunks) {
+            int idx0b, nvalidb, instb; bool validb; locate(chunk, idx0b, nvalidb, validb, instb);
+#pragma unroll
+            for (int q = 0; q < S::nx; q++) x0n[q] = validb ? I.x0[(size_t)instb * S::nx + q] : 0.0;
+            um1n = validb ? I.um1[(size_t)instb] : 0.0;
+        }
+        if constexpr (PERINST) { const TpiPolView<S> Pv(A.pview + inst, (size_t)A.pstride); tpi_pol_batch<S, TV>(Pv, I, A, wsm, csm, inst, valid, A.list ? -1 : idx0, nvalid, A.mode, A.capA, A.capB > 0, A.reset, x0c, um1c); }
+        else tpi_pol_batch<S, TV>(P, I, A, wsm, csm, inst, valid, A.list ? -1 : idx0, nvalid, A.mode, A.capA, A.capB > 0, A.reset, x0c, um1c);
     }
     auto leave = [&]() {
         if (lane != 0) return;
@@ -855,6 +878,133 @@ __global__ void __launch_bounds__(TPI_POL_WARPS * 32, 1) k_tpi_pol(const __grid_
     leave();
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Multi-input fast path (bmpc_tpm.cuh): K5 of shapes with nu > 1 and one shared system — the constrained Riccati polish with one
+// THREAD per instance and one warp (32 instances) per CTA.  Gain rows in global memory (per resident warp: slots x 32 lanes,
+// lane-interleaved), working sets in local memory, the system in the constant bank (kernel parameter).
+//  mode -1: warm first round of a solve: per instance, the stored working sets shifted one stage (record flag set: its last
+//           solve was verified here) or, failing that, the working sets read off its ADMM fixed point v* of the previous
+//           problem (left by whichever kernel finished it), shifted;
+//  mode  2: straggler rounds: an ADMM chunk of the team / tile kernels ran just before; working sets from the iterate v.
+// Verified: plan, u0 (published like every epilogue: output slice, shadow, peers), status, v* (standard row order: the warm
+// start of any later ADMM round), x (ADMM warm start), working-set record.  Not verified: listed for the next round.
+struct TpmArgs {
+    const int32_t* list; int count, mode, cap, reset;
+    int32_t* counts; int32_t* next_list; double* u0_out; double* um1_solved;
+    double* W; unsigned long long* rec; int rec_stride;               // record of instance i: Np code words, mumax, flag (rec_stride 64-bit words)
+};
+struct TpmDiscard { unsigned long long sink; };
+
+template <class S, bool TV>
+__global__ void __launch_bounds__(32) k_tpm_pol(const __grid_constant__ TpmParams<S> P, BmpcInst I, TpmArgs A) {
+    using L = TpmLayout<S>; using CD = TpmCode<S>;
+    constexpr int nx = S::nx, nu = S::nu, Np = S::Np, NU = S::NU, mc = S::mc, NX = S::NX;
+    const int lane = threadIdx.x, idx = blockIdx.x * 32 + lane;
+    const bool valid = idx < A.count;
+    const int inst = valid ? (A.list ? A.list[idx] : idx) : 0;
+    TpiAcc W{A.W + (size_t)blockIdx.x * L::slots * 32 + lane, 32};
+    uint64_t cur[Np], atb[Np];
+    uint64_t dump = 0ull; uint64_t* const dp = &dump;
+    auto C = [&](int k) -> uint64_t& { return cur[k]; };
+    auto CB = [&](int k) -> uint64_t& { return atb[k]; };
+    auto CK = [dp](int) -> uint64_t& { return *dp; };
+    double x0[nx], um1[nu], xref[nx];
+#pragma unroll
+    for (int q = 0; q < nx; q++) { x0[q] = valid ? I.x0[(size_t)inst * nx + q] : 0.0; xref[q] = (valid && !TV) ? I.xref[(size_t)inst * nx + q] : 0.0; }
+#pragma unroll
+    for (int j = 0; j < nu; j++) um1[j] = valid ? I.um1[(size_t)inst * nu + j] : 0.0;
+    const TpiXref<S, TV> xr{TV ? I.xref + (size_t)inst * NX : xref};
+    unsigned long long* rec = A.rec + (size_t)inst * A.rec_stride;
+    double mumax = 0.0;
+    bool done = !valid, ok = false;
+    if (valid) {
+        const bool stored = A.mode < 0 && rec[Np + 1] == 1ull;
+        if (stored) {
+            uint64_t st[Np];
+            for (int k = 0; k < Np; k++) st[k] = rec[k];
+            unsigned first[nu];
+#pragma unroll
+            for (int j = 0; j < nu; j++) first[j] = (S::Nc > 1) ? tpm_first_label<S>(P, j, I.Us[(size_t)inst * NU + j], I.Us[(size_t)inst * NU + nu + j]) : 0u;
+            const int tail = tpm_tail_start<S>(st);
+            for (int k = 0; k < Np; k++) cur[k] = tpm_shifted_code<S>(st, k, true, first, tail);
+            mumax = __longlong_as_double((long long)rec[Np]);
+        } else {
+            const double* v = I.vw + (size_t)inst * mc;
+            tpm_codes_from_v<S>(P, um1, [&](int i) { return v[i]; }, C, A.mode < 0 ? 1 : 0);
+        }
+        if (A.mode == 2 && !A.reset && bmpc_residuals_tight(I.res + (size_t)inst * 4, I.iters[inst])) {
+            // residuals far below any tolerance: the iterate is the answer although the active-set iteration cannot certify it
+            const double* ua = I.Ua + (size_t)inst * NU;
+            for (int a = 0; a < NU; a++) { I.Us[(size_t)inst * NU + a] = ua[a]; if (a < nu) bmpc_publish_u0(I, A.u0_out, (size_t)inst * nu + a, ua[a]); }
+            I.status[inst] = BMPC_SOLVED_UNPOLISHED; atomicAdd(A.counts + BMPC_CNT_TIGHT, 1);
+            done = true;
+        }
+    }
+    const bool live = valid && !done;
+    double vfirst[nu], vq = 0.0;
+    double* udst = I.Us + (size_t)inst * NU;
+    int used = 0;
+    for (int r = 0; r < A.cap; r++) {
+        if (!done) {
+            tpm_backward<S>(P, W, C, xr, um1);
+            const int fl = tpm_forward<S>(P, W, C, CB, CK, x0, um1, mumax, vfirst, vq, [&](int k, int j, double u) { udst[k * nu + j] = u; });
+            used++;
+            ok = fl == 0; done = ok;
+        }
+        if (__all_sync(0xffffffffu, done)) break;
+    }
+    ok = ok && live;
+    if (valid && A.reset) {
+        I.iters[inst] = 0; I.psteps[inst] = 0; I.lvl[inst] = BMPC_LEV0;
+#pragma unroll
+        for (int j = 0; j < nu; j++) A.um1_solved[(size_t)inst * nu + j] = um1[j];
+        if (!ok) I.status[inst] = BMPC_UNSOLVED;
+    }
+    if (live) {
+        I.psteps[inst] += used;
+        if (ok) {
+#pragma unroll
+            for (int j = 0; j < nu; j++) bmpc_publish_u0(I, A.u0_out, (size_t)inst * nu + j, udst[j]);
+            I.status[inst] = BMPC_SOLVED;
+            double* xw = I.xw + (size_t)inst * NU;
+            for (int a = 0; a < NU; a++) xw[a] = udst[a];
+            // v* in the standard row order
+            double* v = I.vw + (size_t)inst * mc;
+#pragma unroll
+            for (int q = 0; q < nx; q++) v[q] = x0[q];
+            for (int k = 0; k < Np; k++)
+                for (int p = 0; p < 2 * nu + nx; p++) { const int row = tpm_vstar_row<S>(k, p); if (row >= 0) v[row] = W(k * L::per_stage + p); }
+#pragma unroll
+            for (int j = 0; j < nu; j++) v[NX + NU + j] = vfirst[j];
+            v[mc - 1] = vq;
+            for (int k = 0; k < Np; k++) rec[k] = atb[k];
+            rec[Np] = (unsigned long long)__double_as_longlong(mumax); rec[Np + 1] = 1ull;
+        } else {
+            rec[Np + 1] = 0ull;                                         // whoever finishes this instance leaves v*: the next solve starts from that
+        }
+    }
+    int tot = live ? used : 0;
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, sft);
+    if (lane == 0 && tot) atomicAdd(A.counts + 1, tot);
+    const bool fail = live && !ok && (A.reset || I.status[inst] != BMPC_PRIMAL_INFEASIBLE);
+    const unsigned fmask = __ballot_sync(0xffffffffu, fail);
+    if (fmask) {
+        int basep = 0;
+        if (lane == 0) basep = atomicAdd(A.counts, __popc(fmask));
+        basep = __shfl_sync(0xffffffffu, basep, 0);
+        if (fail) A.next_list[basep + __popc(fmask & ((1u << lane) - 1u))] = inst;
+    }
+}
+
+// Compiled multi-input fast-path shapes: one line per shape in csrc/tpm_shapes.inc
+struct TpmEntry {
+    int nx, nu, Np, Nc; size_t par_bytes; int slots;
+    bool (*fill)(const double* hs, const BmpcSysOff& o, void* pp);
+    void (*launch)(struct bmpc_handle* h, const int32_t* list, int count, int mode, int cap, int reset, int32_t* next_list);
+};
+
 // Compiled fast-path shapes (nx, nu, Np, Nc) with nu == 1 and Nc == Np: one line per shape in csrc/tpi_shapes.inc
 // (`python -m pympc_b200.build --add-shape nx,1,Np` appends one and rebuilds).
 struct TpiEntry {
@@ -911,6 +1061,10 @@ struct bmpc_handle {
     int tpi_pdas_steps = 8;
     double* tpi_view = nullptr;       // per-instance parameter blocks of the fast path (n_sys = batch), field-major
     bool codes_valid = false;         // the stored working sets come from a fast-path polish of the whole batch
+    int tpm_kind = 0;                  // 0 none, else 1 + index into g_tpm_table (compiled multi-input fast-path shapes)
+    void* tpm_params = nullptr;        // host copy of the parameter block
+    double* tpm_W = nullptr; unsigned long long* tpm_rec = nullptr;   // gain rows of the resident warps, working-set records
+    int tpm_first_cap = 8, tpm_round_cap = 6;
 };
 
 static std::string g_create_err;
@@ -1021,6 +1175,29 @@ static const TpiEntry g_tpi_table[] = {
 };
 #undef BMPC_TPI_SHAPE
 static const int g_tpi_count = (int)(sizeof(g_tpi_table) / sizeof(g_tpi_table[0]));
+
+template <class S>
+static void launch_tpm(bmpc_handle* h, const int32_t* list, int count, int mode, int cap, int reset, int32_t* next_list) {
+    TpmArgs A;
+    A.list = list; A.count = count; A.mode = mode; A.cap = cap; A.reset = reset;
+    A.counts = h->counts + BMPC_CNT * h->cpar; A.next_list = next_list; A.u0_out = h->I.u0; A.um1_solved = h->um1_solved;
+    A.W = h->tpm_W; A.rec = h->tpm_rec; A.rec_stride = S::Np + 2;
+    const TpmParams<S>& P = *(const TpmParams<S>*)h->tpm_params;
+    const int grid = (count + 31) / 32;
+    if (h->xref_mode) k_tpm_pol<S, true><<<grid, 32, 0, h->stream>>>(P, h->I, A);
+    else k_tpm_pol<S, false><<<grid, 32, 0, h->stream>>>(P, h->I, A);
+    h->stats.launches++;
+}
+template <class S>
+static bool tpm_fill_entry(const double* hs, const BmpcSysOff& o, void* pp) { return tpm_fill<S>(hs, o, *(TpmParams<S>*)pp); }
+#define BMPC_TPM_SHAPE(NX_, NU_, NP_, NC_)                                                                                   \
+    {NX_, NU_, NP_, NC_, sizeof(TpmParams<TpiShape<NX_, NU_, NP_, NC_>>), TpmLayout<TpiShape<NX_, NU_, NP_, NC_>>::slots,     \
+     tpm_fill_entry<TpiShape<NX_, NU_, NP_, NC_>>, launch_tpm<TpiShape<NX_, NU_, NP_, NC_>>},
+static const TpmEntry g_tpm_table[] = {
+#include "tpm_shapes.inc"
+};
+#undef BMPC_TPM_SHAPE
+static const int g_tpm_count = (int)(sizeof(g_tpm_table) / sizeof(g_tpm_table[0]));
 
 
 extern "C" {
@@ -1212,8 +1389,10 @@ void bmpc_destroy(bmpc_handle* h) {
                     h->I.status, h->I.iters, h->I.psteps, h->I.lvl, h->listA, h->listB, h->counts, h->queue, h->codes, h->ovf, h->vprev, h->lprev, h->seq_x, h->seq_e, h->seq_obj};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_count) cudaFreeHost(h->h_count);
-    free(h->tpi_admm_params); free(h->tpi_polish_params);
+    free(h->tpi_admm_params); free(h->tpi_polish_params); free(h->tpm_params);
     if (h->tpi_view) cudaFree(h->tpi_view);
+    if (h->tpm_W) cudaFree(h->tpm_W);
+    if (h->tpm_rec) cudaFree(h->tpm_rec);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -1333,6 +1512,27 @@ int bmpc_setup(bmpc_handle* h, const double* Ad, const double* Bd, const double*
             BMPC_CUDA(cudaGetLastError());
         }
     }
+    // multi-input fast path: compiled shape, one shared system, soft state rows, diagonal QDu
+    h->tpm_kind = 0;
+    if (h->cfg.fast_path && !h->tpi_kind && h->cfg.soft_on && ns == 1 && h->cfg.polish) {
+        for (int k = 0; k < g_tpm_count; k++)
+            if (g_tpm_table[k].nx == d.nx && g_tpm_table[k].nu == d.nu && g_tpm_table[k].Np == d.Np && g_tpm_table[k].Nc == d.Nc) { h->tpm_kind = k + 1; break; }
+    }
+    if (h->tpm_kind) {
+        const TpmEntry& te = g_tpm_table[h->tpm_kind - 1];
+        std::vector<double> hs(o.total);
+        BMPC_CUDA(cudaMemcpyAsync(hs.data(), h->sys, sizeof(double) * o.total, cudaMemcpyDeviceToHost, h->stream));
+        BMPC_CUDA(cudaStreamSynchronize(h->stream));
+        free(h->tpm_params); h->tpm_params = malloc(te.par_bytes);
+        if (!te.fill(hs.data(), o, h->tpm_params)) h->tpm_kind = 0;      // QDu not diagonal: team kernels
+    }
+    if (h->tpm_kind) {
+        const TpmEntry& te = g_tpm_table[h->tpm_kind - 1];
+        const size_t B = h->cfg.batch, nwarp = (B + 31) / 32;
+        if (!h->tpm_W) BMPC_CUDA(cudaMalloc((void**)&h->tpm_W, sizeof(double) * nwarp * 32 * (size_t)te.slots));
+        if (!h->tpm_rec) BMPC_CUDA(cudaMalloc((void**)&h->tpm_rec, sizeof(unsigned long long) * B * (size_t)(d.Np + 2)));
+        BMPC_CUDA(cudaMemsetAsync(h->tpm_rec, 0, sizeof(unsigned long long) * B * (size_t)(d.Np + 2), h->stream));
+    }
     // uminus1 default = uref for every instance (mpc.py:141); caller overrides through bmpc_update
     h->is_setup = true; h->cold = true; h->solved = false; h->pending = false; h->codes_valid = false;
     return BMPC_OK;
@@ -1421,6 +1621,8 @@ static int enqueue_round(bmpc_handle* h) {
     // (per-instance systems have no thread-per-instance ADMM — its matrices live in the constant bank —: their cold start and any
     // first_iters > 0 go through the team kernels, the warm polish-only round through k_tpi_pol with per-instance parameter blocks)
     const bool tpi = st.round == 0 && tpi_ok && h->cfg.polish && (h->tpi_view == nullptr || st.chunk == 0);
+    // multi-input fast path: a warm solve starts with the Riccati polish alone (no ADMM, no prep)
+    const bool tpm0 = st.round == 0 && h->tpm_kind != 0 && st.chunk == 0 && !h->cold;
     // straggler rounds read u_-1 from the snapshot the first round took: bmpc_output may already have queued the commit of
     // this solve's u0 into um1 (speculating that the first round finishes everything)
     h->cpar ^= 1;                                        // counters of this round: the half the previous round left zeroed
@@ -1428,7 +1630,7 @@ static int enqueue_round(bmpc_handle* h) {
     h->I.um1 = st.round > 0 ? h->um1_solved : h->um1_cur;
     h->I.x0 = h->x0_cur; h->I.u0_shadow = h->um1_alt;
     if (!tpi) {
-        if (st.round == 0) {
+        if (st.round == 0 && !tpm0) {
             const int B = h->cfg.batch;
             k_reset<<<(B + 255) / 256, 256, 0, h->stream>>>(h->I, B);
             h->stats.launches++;
@@ -1442,6 +1644,9 @@ static int enqueue_round(bmpc_handle* h) {
     if (!h->spin_epoch) BMPC_CUDA(cudaEventRecord(h->ev[0], h->stream));
     if (tpi) {
         g_tpi_table[h->tpi_kind - 1].launch(h, st.list, st.count, st.chunk, st.nxt, h->ev[1]);
+    } else if (tpm0) {
+        BMPC_CUDA(cudaEventRecord(h->ev[1], h->stream));
+        g_tpm_table[h->tpm_kind - 1].launch(h, nullptr, st.count, -1, h->tpm_first_cap, 1, st.nxt);
     } else {
         // infeasible instances never pass the polish: from the third round on, look for OSQP's certificate
         const bool chk = st.total >= 25 && st.list != nullptr;
@@ -1456,6 +1661,10 @@ static int enqueue_round(bmpc_handle* h) {
         // stragglers of a fast-path shape: the Riccati polish (list mode) has ~3x lower latency than the team Schur polish
         if (h->cfg.polish && tpi_ok && st.total + st.chunk <= 200)
             g_tpi_table[h->tpi_kind - 1].launch_polish(h, st.list, st.count, st.nxt);
+        // multi-input fast-path shapes: the Riccati polish (a refinement costs about one ADMM iteration of this shape) instead of
+        // the Schur-form one, which takes over for the instances that are still open after 200 iterations (any working set)
+        else if (h->cfg.polish && h->tpm_kind && st.list != nullptr && st.total + st.chunk <= 200)
+            g_tpm_table[h->tpm_kind - 1].launch(h, st.list, st.count, 2, h->tpm_round_cap, 0, st.nxt);
         else if (h->cfg.polish) launch_polish(h, st.list, st.count, st.nxt, cnt);
         else { k_check_converged<<<(st.count + 255) / 256, 256, 0, h->stream>>>(h->I, st.list, st.count, h->cfg.eps_abs, h->cfg.eps_rel, st.nxt, cnt); h->stats.launches++; }
     }
@@ -1535,7 +1744,7 @@ int bmpc_solve(bmpc_handle* h) {
     if (h->gflags) h->g_epoch++;                     // every rank solves in lockstep: the arrival epoch of this step
     // first round: NO ADMM iterations on a warm fast-path solve (the previous solution's working sets are the best first guess
     // the active-set polish can get: measured 0 vs 1..10 iterations), 10 on the team kernels; first_iters > 0 overrides
-    const bool fast = h->tpi_kind != 0;
+    const bool fast = h->tpi_kind != 0 || (h->tpm_kind != 0 && !h->cold);
     st.chunk = h->cfg.polish ? (h->cfg.first_iters > 0 ? h->cfg.first_iters : (fast ? 0 : 10)) : 25;
     // a cold start has no active-set guess to refresh: 25 iterations at once on the fast path, so that the first polish
     // usually verifies and the whole batch does not take the straggler route

@@ -17,8 +17,9 @@ def build():
     core = os.path.join(_HERE, "..", "..", "pympc_b200", "csrc", "bmpc_core.cuh")
     tpi = os.path.join(_HERE, "..", "..", "pympc_b200", "csrc", "bmpc_tpi.cuh")
     tile = os.path.join(_HERE, "..", "..", "pympc_b200", "csrc", "bmpc_tile.cuh")
+    tpm = os.path.join(_HERE, "..", "..", "pympc_b200", "csrc", "bmpc_tpm.cuh")
     os.makedirs(os.path.dirname(_SO), exist_ok=True)
-    if (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(core), os.path.getmtime(tpi), os.path.getmtime(tile)):
+    if (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(core), os.path.getmtime(tpi), os.path.getmtime(tile), os.path.getmtime(tpm)):
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-x", "c++", src, "-o", _SO])
     return ctypes.CDLL(_SO)
 
@@ -106,6 +107,33 @@ class EmuSystem:
         f.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         ps = f(self.nx, self.nu, self.Np, self.Nc, _p(self.sys), _p(x0), _p(um1), _p(xref), tv, _p(self.codes), mode, _p(self.v), _p(U), max_ref, _p(mm))
         return U, ps
+
+    def tpm_step(self, x0, um1, xref, mode=1, max_ref=8):
+        """multi-input Riccati polish (bmpc_tpm.cuh) on the stored working-set codes (mode 0 as stored, 1 shifted one stage, 2 from
+        self.v); returns (U, refinements used); state: self.mcodes, self.v, self.mumax."""
+        x0 = np.ascontiguousarray(x0, float); um1 = np.ascontiguousarray(um1, float); xref = np.ascontiguousarray(xref, float)
+        tv = 0 if xref.ndim == 1 else 1
+        if not hasattr(self, "mcodes"):
+            self.mcodes = np.zeros(self.Np, np.uint64)
+        U = np.ascontiguousarray(getattr(self, "Uplan", np.zeros(self.NU)), float).copy(); mm = np.zeros(1)
+        f = self.L.emu_tpm_step
+        f.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        ps = f(self.nx, self.nu, self.Np, self.Nc, _p(self.sys), _p(x0), _p(um1), _p(xref), tv, _p(self.mcodes), mode, _p(self.v), _p(U), max_ref, _p(mm))
+        if ps > 0:
+            self.Uplan = U.copy()
+        return U, ps
+
+    def admm_only(self, x0, um1, xref, niter):
+        """niter team-core ADMM iterations on (self.x, self.v) with the adaptive-rho move; returns the residual quadruple"""
+        x0 = np.ascontiguousarray(x0, float); um1 = np.ascontiguousarray(um1, float); xref = np.ascontiguousarray(xref, float)
+        tv = 0 if xref.ndim == 1 else 1
+        lvl = ctypes.c_int(getattr(self, "lvl", 2)); res = np.zeros(4)
+        f = self.L.emu_admm_only
+        f.restype = None
+        f.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 4 + [ctypes.c_int] * 2 + [ctypes.c_void_p] * 2 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        f(self.nx, self.nu, self.Np, self.Nc, _p(self.sys), _p(x0), _p(um1), _p(xref), tv, self.cold, _p(self.x), _p(self.v), niter, ctypes.byref(lvl), _p(res))
+        self.cold = 0; self.lvl = lvl.value
+        return res
 
     def tile_compare(self, X0, Um1, Xref, niter, lvl=None, x_in=None, v_in=None, T=4):
         """Run the tile ADMM and the per-instance team ADMM on the same T (2, 4 or 8) instances; returns (ref, tile) dicts."""

@@ -284,3 +284,86 @@ extern "C" int emu_infeasible(int nx, int nu, int Np, int Nc, const double* sys,
     free(buf);
     return flag;
 }
+
+
+// Multi-input Riccati polish (bmpc_tpm.cuh): up to max_ref refinements from the working-set codes (mode 0: as stored, 1: shifted
+// by one stage — Uout then holds the previous plan on entry —, 2: derived from v in the standard row order, 3: from v of the
+// previous problem, shifted).  codes: Np 64-bit words in/out; v [mc] in (modes 2, 3) / out (v* when verified); mumax in/out.
+// Returns refinements used (> 0 verified, 0 not verified, -100 shape not compiled, -101 QDu not diagonal).
+#include "../../pympc_b200/csrc/bmpc_tpm.cuh"
+template <class S, bool TV>
+static int emu_tpm_run(const double* sys, const double* x0, const double* um1, const double* xref, uint64_t* codes, int mode,
+                       double* v, double* Uout, int max_ref, double* mumax_io) {
+    using L = TpmLayout<S>;
+    const TpiXref<S, TV> xr{xref};
+    BmpcDims d = bmpc_make_dims(S::nx, S::nu, S::Np, S::Nc); BmpcSysOff o = bmpc_make_off(d);
+    TpmParams<S>* P = new TpmParams<S>();
+    if (!tpm_fill<S>(sys, o, *P)) { delete P; return -101; }
+    double* col = (double*)calloc(L::slots + 8, sizeof(double));
+    uint64_t cur[S::Np], atb[S::Np], keep[S::Np];
+    TpiAcc W{col, 1};
+    auto C = [&](int k) -> uint64_t& { return cur[k]; };
+    auto CB = [&](int k) -> uint64_t& { return atb[k]; };
+    auto CK = [&](int k) -> uint64_t& { return keep[k]; };
+    if (mode >= 2) { TpiAcc V{v, 1}; tpm_codes_from_v<S>(*P, um1, V, C, mode == 3); }
+    else {
+        unsigned first[S::nu];
+        for (int j = 0; j < S::nu; j++) first[j] = (mode == 1 && S::Nc > 1) ? tpm_first_label<S>(*P, j, Uout[j], Uout[S::nu + j]) : 0u;
+        const int tail = tpm_tail_start<S>(codes);
+        for (int k = 0; k < S::Np; k++) cur[k] = tpm_shifted_code<S>(codes, k, mode == 1, first, tail);
+    }
+    double mumax = *mumax_io, vfirst[S::nu], vq = 0.0, U[S::NU];
+    int used = 0;
+    for (int r = 0; r < max_ref; r++) {
+        tpm_backward<S>(*P, W, C, xr, um1);
+        const int fl = tpm_forward<S>(*P, W, C, CB, CK, x0, um1, mumax, vfirst, vq, [&](int k, int j, double u) { U[k * S::nu + j] = u; });
+        if (fl == 0) { used = r + 1; break; }
+    }
+    if (used > 0) {
+        for (int k = 0; k < S::Np; k++)
+            for (int p = 0; p < 2 * S::nu + S::nx; p++) { const int row = tpm_vstar_row<S>(k, p); if (row >= 0) v[row] = col[k * L::per_stage + p]; }
+        for (int j = 0; j < S::nu; j++) v[S::NX + S::NU + j] = vfirst[j];
+        v[S::mc - 1] = vq;
+        for (int q = 0; q < S::nx; q++) v[q] = x0[q];
+        for (int j = 0; j < S::NU; j++) Uout[j] = U[j];
+    }
+    for (int k = 0; k < S::Np; k++) codes[k] = (used > 0) ? atb[k] : cur[k];       // a verified vertex is described by the rows at their bounds
+    *mumax_io = mumax;
+    free(col); delete P;
+    return used;
+}
+
+extern "C" int emu_tpm_step(int nx, int nu, int Np, int Nc, const double* sys, const double* x0, const double* um1, const double* xref,
+                            int xref_mode, uint64_t* codes, int mode, double* v, double* Uout, int max_ref, double* mumax_io) {
+#define EMU_TPM_ARGS sys, x0, um1, xref, codes, mode, v, Uout, max_ref, mumax_io
+#define EMU_TPM_SHAPE(a, b, c, e) \
+    if (nx == a && nu == b && Np == c && Nc == e) \
+        return xref_mode ? emu_tpm_run<TpiShape<a, b, c, e>, true>(EMU_TPM_ARGS) : emu_tpm_run<TpiShape<a, b, c, e>, false>(EMU_TPM_ARGS);
+    EMU_TPM_SHAPE(8, 4, 40, 40)
+    EMU_TPM_SHAPE(8, 4, 12, 5)
+    EMU_TPM_SHAPE(8, 4, 12, 12)
+    EMU_TPM_SHAPE(4, 1, 20, 20)
+    EMU_TPM_SHAPE(2, 1, 20, 20)
+    EMU_TPM_SHAPE(4, 1, 20, 10)
+    EMU_TPM_SHAPE(3, 2, 10, 10)
+    EMU_TPM_SHAPE(3, 2, 10, 6)
+#undef EMU_TPM_SHAPE
+#undef EMU_TPM_ARGS
+    return -100;
+}
+
+// niter ADMM iterations of the team core on the generic-layout state (x [NU], v [mc], in/out; cold != 0 -> initialise), with the
+// adaptive-rho move afterwards (lvl in/out); res_out [4].  Used by the policy studies of the polish kernels.
+extern "C" void emu_admm_only(int nx, int nu, int Np, int Nc, const double* sys, const double* x0, const double* um1, const double* xref,
+                              int xref_mode, int cold, double* x, double* v, int niter, int* lvl_io, double* res_out) {
+    BmpcDims d = bmpc_make_dims(nx, nu, Np, Nc); BmpcSysOff o = bmpc_make_off(d);
+    SeqTeam t;
+    double* buf = (double*)calloc(4 * d.NU + d.NX + 2 * d.mc + 16, sizeof(double));
+    double *g = buf, *cc = g + d.NU, *w = cc + d.NX, *xt = w + d.mc, *r = xt + d.NU, *res = r + d.NU;
+    bmpc_prep(t, d, o, sys, x0, um1, xref, xref_mode, g, cc);
+    if (cold) { for (int a = 0; a < d.NU; a++) x[a] = 0.0; for (int i = 0; i < d.mc; i++) v[i] = i < d.NX ? cc[i] : 0.0; }
+    bmpc_admm(t, d, o, sys, um1, g, cc, x, v, w, xt, r, niter, res, *lvl_io);
+    *lvl_io = bmpc_adapt_level(t, d, o, sys, um1, v, res, *lvl_io);
+    for (int k = 0; k < 4; k++) res_out[k] = res[k];
+    free(buf);
+}

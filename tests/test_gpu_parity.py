@@ -75,8 +75,6 @@ def test_first_solve_vs_golden(MPC, name, fast):
 def test_closed_loop_vs_golden(MPC, name, steps, fast):
     """update(x, u) -> output() loop of the reference examples (examples/example_inverted_pendulum.py:65-88),
     linear plant, warm start; includes the analytic point-mass ramp 0.2, 0.4, ..., 1.2."""
-    if name == "mimo" and fast == 0:
-        pytest.skip("mimo has no fast path: covered by fast=1")
     cfg = CASES[name](); g = golden(f"{name}_loop.npz")
     K = MPC(**cfg, fast_path=fast); K.setup()
     x = np.array(cfg["x0"], float); u = np.array(cfg["uminus1"], float)
@@ -738,5 +736,38 @@ def test_per_instance_systems_on_the_fast_path(MPC):
         if t > 0:
             assert Ks[0].stats()["admm_iters"] < 5 * B and Ks[1].stats()["admm_iters"] >= 10 * B      # fast path: polish first, ADMM only for stragglers
         U = Un; X = np.einsum("bij,bj->bi", Ad, X) + np.einsum("bij,bj->bi", Bd, U)
+    for K in Ks:
+        K.close()
+
+
+
+def test_multi_input_fast_path_agrees_with_team_path(MPC):
+    """MIMO shape (nx=8, nu=4, Np=40) on the thread-per-instance Riccati polish (bmpc_tpm.cuh: scalar sub-steps along the
+    reference's scalar-shift delta-u chain, anchored runs, interval test of degenerate vertices) vs the team / tile kernels on the
+    same 512 random transients, and vs the oracle on a sample.  The fast path must carry most warm solves without ADMM."""
+    cfg = mimo(); B = 512
+    rng = np.random.default_rng(4)
+    X0 = 0.3 * rng.standard_normal((B, 8))
+    kw = {k: cfg[k] for k in ("Qx", "QxN", "Qu", "QDu", "xmin", "xmax", "umin", "umax", "Dumin", "Dumax")}
+    Ks = [MPC(cfg["Ad"], cfg["Bd"], Np=40, x0=X0, xref=cfg["xref"], uminus1=np.zeros(4), batch=B, fast_path=f, **kw) for f in (1, 0)]
+    for K in Ks:
+        K.setup()
+    X = X0.copy(); U = np.zeros((B, 4)); iters = [0, 0]
+    for t in range(10):
+        outs = []; sts = []
+        for i, K in enumerate(Ks):
+            K.update(X, U); Un, info = K.output(return_u_seq=True)
+            outs.append(info["u_seq"].reshape(B, -1)); sts.append(np.array(K.res.info.status_val).copy())
+            iters[i] += K.stats()["admm_iters"]
+            assert np.isin(sts[-1], (1, 2)).all(), (t, i)
+        both = (sts[0] == 1) & (sts[1] == 1)
+        assert both.mean() > 0.98, (t, both.mean())
+        assert np.max(np.abs(outs[0][both] - outs[1][both])) < TOL, t
+        for b in (1, B // 3, B - 5):
+            if sts[0][b] == 1:
+                ref, Q = _oracle_u(dict(cfg, x0=X[b], uminus1=U[b]))
+                assert np.max(np.abs(outs[0][b] - ref)) < TOL, (t, b)
+        U = outs[1][:, :4].copy(); X = X @ cfg["Ad"].T + U @ cfg["Bd"].T
+    assert iters[0] < 0.8 * iters[1], iters                        # warm solves mostly verify from the shifted working sets
     for K in Ks:
         K.close()
