@@ -1000,7 +1000,7 @@ __global__ void __launch_bounds__(32) k_tpm_pol(const __grid_constant__ TpmParam
 
 // Compiled multi-input fast-path shapes: one line per shape in csrc/tpm_shapes.inc
 struct TpmEntry {
-    int nx, nu, Np, Nc; size_t par_bytes; int slots;
+    int nx, nu, Np, Nc; unsigned long long amask; unsigned bmask; size_t par_bytes; int slots;
     bool (*fill)(const double* hs, const BmpcSysOff& o, void* pp);
     void (*launch)(struct bmpc_handle* h, const int32_t* list, int count, int mode, int cap, int reset, int32_t* next_list);
 };
@@ -1064,7 +1064,7 @@ struct bmpc_handle {
     int tpm_kind = 0;                  // 0 none, else 1 + index into g_tpm_table (compiled multi-input fast-path shapes)
     void* tpm_params = nullptr;        // host copy of the parameter block
     double* tpm_W = nullptr; unsigned long long* tpm_rec = nullptr;   // gain rows of the resident warps, working-set records
-    int tpm_first_cap = 8, tpm_round_cap = 6;
+    int tpm_first_cap = 12, tpm_round_cap = 4, tpm_chunk = 100;   // (measured on the MIMO side bench, tools/sweep_tpm_caps.sh: 13.3 ms/step at 8,6,25 -> 11.4 ms)      // refinements of the first launch / of a straggler round, ADMM iterations of the first straggler round
 };
 
 static std::string g_create_err;
@@ -1190,13 +1190,17 @@ static void launch_tpm(bmpc_handle* h, const int32_t* list, int count, int mode,
 }
 template <class S>
 static bool tpm_fill_entry(const double* hs, const BmpcSysOff& o, void* pp) { return tpm_fill<S>(hs, o, *(TpmParams<S>*)pp); }
-#define BMPC_TPM_SHAPE(NX_, NU_, NP_, NC_)                                                                                   \
-    {NX_, NU_, NP_, NC_, sizeof(TpmParams<TpiShape<NX_, NU_, NP_, NC_>>), TpmLayout<TpiShape<NX_, NU_, NP_, NC_>>::slots,     \
-     tpm_fill_entry<TpiShape<NX_, NU_, NP_, NC_>>, launch_tpm<TpiShape<NX_, NU_, NP_, NC_>>},
+#define BMPC_TPM_ENTRY(S_) {S_::nx, S_::nu, S_::Np, S_::Nc, S_::amask, S_::bmask, sizeof(TpmParams<S_>), TpmLayout<S_>::slots, tpm_fill_entry<S_>, launch_tpm<S_>},
+#define BMPC_TPM_SHAPE(NX_, NU_, NP_, NC_) BMPC_TPM_ENTRY(BMPC_TPM_T4(TpiShape, NX_, NU_, NP_, NC_))
+#define BMPC_TPM_SPARSE_SHAPE(NX_, NU_, NP_, NC_, AM_, BM_) BMPC_TPM_ENTRY(BMPC_TPM_T6(TpmSparseShape, NX_, NU_, NP_, NC_, AM_, BM_))
+#define BMPC_TPM_T4(T_, a, b, c, d) T_<a, b, c, d>
+#define BMPC_TPM_T6(T_, a, b, c, d, e, f) T_<a, b, c, d, e, f>
+// (entries are tried in order: sparse patterns first, the dense instantiation of a shape last)
 static const TpmEntry g_tpm_table[] = {
 #include "tpm_shapes.inc"
 };
 #undef BMPC_TPM_SHAPE
+#undef BMPC_TPM_SPARSE_SHAPE
 static const int g_tpm_count = (int)(sizeof(g_tpm_table) / sizeof(g_tpm_table[0]));
 
 
@@ -1515,8 +1519,15 @@ int bmpc_setup(bmpc_handle* h, const double* Ad, const double* Bd, const double*
     // multi-input fast path: compiled shape, one shared system, soft state rows, diagonal QDu
     h->tpm_kind = 0;
     if (h->cfg.fast_path && !h->tpi_kind && h->cfg.soft_on && ns == 1 && h->cfg.polish) {
+        // sparsity pattern of (Ad, Bd): an entry fits when its compile-time masks contain it
+        unsigned long long am = 0ull; unsigned bm = 0u;
+        if (d.nx * d.nx <= 64 && d.nx * d.nu <= 32) {
+            for (int i = 0; i < d.nx * d.nx; i++) if (in[o.Ad + i] != 0.0) am |= 1ull << i;
+            for (int i = 0; i < d.nx * d.nu; i++) if (in[o.Bd + i] != 0.0) bm |= 1u << i;
+        } else { am = ~0ull; bm = ~0u; }
         for (int k = 0; k < g_tpm_count; k++)
-            if (g_tpm_table[k].nx == d.nx && g_tpm_table[k].nu == d.nu && g_tpm_table[k].Np == d.Np && g_tpm_table[k].Nc == d.Nc) { h->tpm_kind = k + 1; break; }
+            if (g_tpm_table[k].nx == d.nx && g_tpm_table[k].nu == d.nu && g_tpm_table[k].Np == d.Np && g_tpm_table[k].Nc == d.Nc &&
+                (am & ~g_tpm_table[k].amask) == 0ull && (bm & ~g_tpm_table[k].bmask) == 0u) { h->tpm_kind = k + 1; break; }
     }
     if (h->tpm_kind) {
         const TpmEntry& te = g_tpm_table[h->tpm_kind - 1];
@@ -1527,6 +1538,7 @@ int bmpc_setup(bmpc_handle* h, const double* Ad, const double* Bd, const double*
         if (!te.fill(hs.data(), o, h->tpm_params)) h->tpm_kind = 0;      // QDu not diagonal: team kernels
     }
     if (h->tpm_kind) {
+        if (const char* e = getenv("BMPC_TPM_CAPS")) sscanf(e, "%d,%d,%d", &h->tpm_first_cap, &h->tpm_round_cap, &h->tpm_chunk);   // tuning knob (tools/gpu_sweep.py)
         const TpmEntry& te = g_tpm_table[h->tpm_kind - 1];
         const size_t B = h->cfg.batch, nwarp = (B + 31) / 32;
         if (!h->tpm_W) BMPC_CUDA(cudaMalloc((void**)&h->tpm_W, sizeof(double) * nwarp * 32 * (size_t)te.slots));
@@ -1709,6 +1721,7 @@ static int retire_round(bmpc_handle* h, int* more) {
     st.list = st.nxt; int32_t* tmp = st.cur; st.cur = st.nxt; st.nxt = tmp;
     // polish mode: cumulative first_iters, 25, 50, 100, ...; pure ADMM: OSQP's check_termination = 25
     st.chunk = h->cfg.polish ? (st.total < 25 ? 25 - st.total : st.total) : 25;
+    if (h->tpm_kind && st.total == 0 && h->cfg.polish) st.chunk = h->tpm_chunk;        // first straggler round of a multi-input fast-path solve
     if (st.count > 0 && st.total < h->cfg.max_iter) { *more = 1; return enqueue_round(h); }
     *more = 0;
     const int B = h->cfg.batch;

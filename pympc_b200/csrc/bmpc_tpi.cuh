@@ -35,6 +35,10 @@ struct TpiShape {
     static constexpr int MT = NS + NU + ND;
     static constexpr int NX = (NPc + 1) * NXc;
     static constexpr int mc = NX + NU + ND;
+    // dense (Ad, Bd): see TpmSparseShape in bmpc_tpm.cuh for shapes with a compile-time sparsity pattern
+    static constexpr unsigned long long amask = ~0ull; static constexpr unsigned bmask = ~0u;
+    BMPC_HD static constexpr bool a_nz(int, int) { return true; }
+    BMPC_HD static constexpr bool b_nz(int, int) { return true; }
 };
 
 template <class S>

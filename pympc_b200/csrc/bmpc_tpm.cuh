@@ -29,6 +29,18 @@
 #pragma once
 #include "bmpc_tpi.cuh"
 
+// A shape with the sparsity pattern of (Ad, Bd) fixed at compile time (bit q nx + b of AM: Ad[q][b] may be non-zero, bit a nu + j of
+// BM: Bd[a][j]): the sweeps skip the structural zeros — the MIMO reference governor's Ad is block diagonal (12 of 64 entries), its
+// Bd has one entry per channel.  A system whose pattern is contained in the masks runs on this instantiation; the plain TpiShape
+// is dense.  (nx nx <= 64, nx nu <= 32.)
+template <int NXc, int NUc, int NPc, int NCc, unsigned long long AM, unsigned BM>
+struct TpmSparseShape : TpiShape<NXc, NUc, NPc, NCc> {
+    static_assert(NXc * NXc <= 64 && NXc * NUc <= 32, "pattern masks hold nx nx <= 64 and nx nu <= 32 bits");
+    static constexpr unsigned long long amask = AM; static constexpr unsigned bmask = BM;
+    BMPC_HD static constexpr bool a_nz(int q, int b) { return (AM >> (q * NXc + b)) & 1ull; }
+    BMPC_HD static constexpr bool b_nz(int a, int j) { return (BM >> (a * NUc + j)) & 1u; }
+};
+
 template <class S>
 struct TpmCode {
     // channel j: bits CH0 + 8 j + {0 u max, 1 u min, 2 first max, 3 first min, 4 chain max, 5 chain min, 6 last max, 7 last min}
@@ -134,12 +146,12 @@ BMPC_HD void tpm_backward(const PP& P, WA W, CA C, XR xr, const double* um1) {
             for (int t = 0; t < n; t++) {
                 double acc = PM(t, io);
 #pragma unroll
-                for (int a = 0; a < nx; a++) acc = fma(PM(t, a), P.Bd[a * nu + j], acc);
+                for (int a = 0; a < nx; a++) if (S::b_nz(a, j)) acc = fma(PM(t, a), P.Bd[a * nu + j], acc);
                 Pb[t] = acc;
             }
             double huu = Pb[io] + P.Qu[j * nu + j] + P.QDu[j], gu = p[io] - P.quref[j];
 #pragma unroll
-            for (int a = 0; a < nx; a++) { huu = fma(P.Bd[a * nu + j], Pb[a], huu); gu = fma(P.Bd[a * nu + j], p[a], gu); }
+            for (int a = 0; a < nx; a++) if (S::b_nz(a, j)) { huu = fma(P.Bd[a * nu + j], Pb[a], huu); gu = fma(P.Bd[a * nu + j], p[a], gu); }
             double hus[n];
 #pragma unroll
             for (int t = 0; t < n; t++) hus[t] = Pb[t];
@@ -191,9 +203,9 @@ BMPC_HD void tpm_backward(const PP& P, WA W, CA C, XR xr, const double* um1) {
             for (int a = 0; a < nx; a++)
 #pragma unroll
                 for (int b = 0; b < nx; b++) {
-                    double acc = PM(a, 0) * P.Ad[0 * nx + b];
+                    double acc = 0.0;
 #pragma unroll
-                    for (int q = 1; q < nx; q++) acc = fma(PM(a, q), P.Ad[q * nx + b], acc);
+                    for (int q = 0; q < nx; q++) if (S::a_nz(q, b)) acc = fma(PM(a, q), P.Ad[q * nx + b], acc);
                     T[a * nx + b] = acc;
                 }
             double pyn[nx], Pyr[nx * nu];
@@ -201,13 +213,13 @@ BMPC_HD void tpm_backward(const PP& P, WA W, CA C, XR xr, const double* um1) {
             for (int a = 0; a < nx; a++) {
                 double g = 0.0;
 #pragma unroll
-                for (int q = 0; q < nx; q++) g = fma(P.Ad[q * nx + a], p[q], g);
+                for (int q = 0; q < nx; q++) if (S::a_nz(q, a)) g = fma(P.Ad[q * nx + a], p[q], g);
                 pyn[a] = g;
 #pragma unroll
                 for (int j = 0; j < nu; j++) {
                     double acc = 0.0;
 #pragma unroll
-                    for (int q = 0; q < nx; q++) acc = fma(P.Ad[q * nx + a], PM(q, nx + j), acc);
+                    for (int q = 0; q < nx; q++) if (S::a_nz(q, a)) acc = fma(P.Ad[q * nx + a], PM(q, nx + j), acc);
                     Pyr[a * nu + j] = acc;
                 }
             }
@@ -216,9 +228,9 @@ BMPC_HD void tpm_backward(const PP& P, WA W, CA C, XR xr, const double* um1) {
                 const int lab = tpm_xlabel<S>(cprev, a);
 #pragma unroll
                 for (int b = a; b < nx; b++) {
-                    double acc = P.Ad[0 * nx + a] * T[0 * nx + b];
+                    double acc = 0.0;
 #pragma unroll
-                    for (int q = 1; q < nx; q++) acc = fma(P.Ad[q * nx + a], T[q * nx + b], acc);
+                    for (int q = 0; q < nx; q++) if (S::a_nz(q, a)) acc = fma(P.Ad[q * nx + a], T[q * nx + b], acc);
                     acc += P.Qx[a * nx + b];
                     PM(a, b) = acc;
                 }
@@ -321,7 +333,7 @@ BMPC_HD int tpm_forward(const PP& P, WA W, CA C, CB_ CB, CK_ CK, const double* x
             for (int a = 0; a < nx; a++) {
                 double acc = 0.0;
 #pragma unroll
-                for (int q = 0; q < nx; q++) acc = fma(P.Ad[a * nx + q], s[q], acc);
+                for (int q = 0; q < nx; q++) if (S::a_nz(a, q)) acc = fma(P.Ad[a * nx + q], s[q], acc);
                 y[a] = acc;
             }
 #pragma unroll
@@ -394,7 +406,7 @@ BMPC_HD int tpm_forward(const PP& P, WA W, CA C, CB_ CB, CK_ CK, const double* x
                 prev_tau = tau; prev_mag = fabs(tot);
             }
 #pragma unroll
-            for (int a = 0; a < nx; a++) s[a] = fma(P.Bd[a * nu + j], u, s[a]);
+            for (int a = 0; a < nx; a++) if (S::b_nz(a, j)) s[a] = fma(P.Bd[a * nu + j], u, s[a]);
             s[io] = u;
         }
 #pragma unroll

@@ -339,6 +339,10 @@ extern "C" int emu_tpm_step(int nx, int nu, int Np, int Nc, const double* sys, c
 #define EMU_TPM_SHAPE(a, b, c, e) \
     if (nx == a && nu == b && Np == c && Nc == e) \
         return xref_mode ? emu_tpm_run<TpiShape<a, b, c, e>, true>(EMU_TPM_ARGS) : emu_tpm_run<TpiShape<a, b, c, e>, false>(EMU_TPM_ARGS);
+    if (nx == 8 && nu == 4 && Np == 40 && Nc == 40 && getenv("EMU_TPM_SPARSE")) {      // the device's pattern-specialised instantiation (MIMO reference governor)
+        using SP = TpmSparseShape<8, 4, 40, 40, 0x40c01030040c0103ull, 0x8040201u>;
+        return xref_mode ? emu_tpm_run<SP, true>(EMU_TPM_ARGS) : emu_tpm_run<SP, false>(EMU_TPM_ARGS);
+    }
     EMU_TPM_SHAPE(8, 4, 40, 40)
     EMU_TPM_SHAPE(8, 4, 12, 5)
     EMU_TPM_SHAPE(8, 4, 12, 12)

@@ -352,3 +352,29 @@ def test_tpm_polish_variants_vs_oracle():
             assert np.max(np.abs(U - z[Q.NX:Q.NX + Q.NU])) < (1e-7 if st == 1 else 1e-3), (Nc, t, ps)
             x = c["Ad"] @ x + c["Bd"] @ U[:2]; um1 = U[:2].copy()
         assert fast >= 5, (Nc, fast)
+
+
+def test_tpm_pattern_specialised_shape_equals_dense(monkeypatch):
+    """the instantiation with the MIMO reference governor's (Ad, Bd) sparsity pattern fixed at compile time (what the device runs
+    for that system) follows the dense instantiation refinement by refinement"""
+    cfg = mimo(); x0 = 0.3 * np.random.default_rng(3).standard_normal(8)
+    runs = []
+    for sparse in (False, True):
+        if sparse:
+            monkeypatch.setenv("EMU_TPM_SPARSE", "1")
+        E = EmuSystem(cfg); x = x0.copy(); um1 = np.zeros(4); out = []
+        for t in range(8):
+            if t == 0:
+                Ut, st, *_ = E.solve(x, um1, cfg["xref"]); assert st == 1
+                U, ps = E.tpm_step(x, um1, cfg["xref"], mode=2, max_ref=2); assert ps > 0
+            else:
+                U, ps = E.tpm_step(x, um1, cfg["xref"], mode=1, max_ref=16)
+                if ps <= 0:
+                    U, st, *_ = E.solve(x, um1, cfg["xref"]); assert st == 1
+                    E.tpm_step(x, um1, cfg["xref"], mode=2, max_ref=2); E.Uplan = U.copy()
+            out.append((ps, U.copy()))
+            x = cfg["Ad"] @ x + cfg["Bd"] @ U[:4]; um1 = U[:4].copy()
+        runs.append(out)
+    assert sum(ps > 0 for ps, _ in runs[0]) >= 6
+    for (pa, Ua), (pb, Ub) in zip(*runs):
+        assert pa == pb and np.max(np.abs(Ua - Ub)) < 1e-10

@@ -50,6 +50,21 @@ out = {"pendulum_4_1_20_20": {
     "fp64_per_admm_iteration": admm,
     "how": "tools/count_fp64_ops.py: DFMA+DADD+DMUL+DSETP in the stage loops of the compiled SASS x Np stages",
 }}
+# multi-input fast path (MIMO reference-governor shape, pattern-specialised instantiation): the backward and the forward stage loops
+# of k_tpm_pol are its two loops with the most fp64 instructions (sub-steps are unrolled inside them)
+try:
+    mn, mins, mloops, minner = loops_of("k_tpm_polI14TpmSparseShapeILi8ELi4ELi40ELi40E")
+    mc = sorted((sc.region_cost(mins, lo, hi)["fp64"] for lo, hi in mloops), reverse=True)
+    # (the refinement loop encloses both sweeps: its count is their sum, skip it)
+    sweeps = [c for c in mc if c < mc[0]][:2] if len(mc) > 2 and mc[0] >= mc[1] + mc[2] - 8 else mc[:2]
+    out["mimo_8_4_40_40"] = {
+        "polish_kernel": "k_tpm_pol<TpmSparseShape<8,4,40,40,...>>", "admm_kernel": "k_admm_tile<8,2,8,4>",
+        "fp64_backward_per_stage": sweeps[0], "fp64_forward_per_stage": sweeps[1], "fp64_per_refinement": 40 * (sweeps[0] + sweeps[1]),
+        "how": "tools/count_fp64_ops.py: DFMA+DADD+DMUL+DSETP in the two stage loops of the compiled SASS x Np stages (the straggler rounds' Schur-form "
+               "refinements and the tile ADMM are not counted: their entries carry time shares only)",
+    }
+except Exception as exc:                                    # shape not in the table of this build
+    print("mimo shape:", exc)
 path = os.path.join(ROOT, "profiles", "fp64_ops.json")
 old = {}
 try:
