@@ -587,8 +587,7 @@ struct TpiPolLayout {
 // one batch of up to 32 instances (one per lane) through up to cap refinements; returns the mask of verified lanes
 template <class S, bool TV, class PP>
 __device__ __forceinline__ void tpi_pol_batch(const PP& P, const BmpcInst& I, const TpiPolArgs& A, double* wsm, typename TpiCode<S>::type* csm,
-                                              int inst, bool valid_in, int inst0_contig, int nvalid, int mode, int cap, bool to_queue, int reset,
-                                              const double* x0_pre = nullptr, double um1_pre = 0.0) {
+                                              int inst, bool valid_in, int inst0_contig, int nvalid, int mode, int cap, bool to_queue, int reset) {
     bool valid = valid_in;
     using L = TpiPolLayout<S>; using CT = typename TpiCode<S>::type;
     constexpr int nx = S::nx;
@@ -597,11 +596,8 @@ __device__ __forceinline__ void tpi_pol_batch(const PP& P, const BmpcInst& I, co
     auto C = [&](int k) -> CT& { return csm[k * 32 + lane]; };
     double x0[nx], xref[nx], um1 = 0.0, mumax = 0.0, vq = 0.0;
 #pragma unroll
-    for (int q = 0; q < nx; q++) {
-        x0[q] = x0_pre ? x0_pre[q] : (valid ? I.x0[(size_t)inst * nx + q] : 0.0);       // phase A: fetched while the previous chunk was computing
-        xref[q] = (valid && !TV) ? I.xref[(size_t)inst * nx + q] : 0.0;
-    }
-    um1 = x0_pre ? um1_pre : (valid ? I.um1[(size_t)inst] : 0.0);
+    for (int q = 0; q < nx; q++) { x0[q] = valid ? I.x0[(size_t)inst * nx + q] : 0.0; xref[q] = (valid && !TV) ? I.xref[(size_t)inst * nx + q] : 0.0; }
+    if (valid) um1 = I.um1[(size_t)inst];
     const TpiXref<S, TV> xr{TV ? I.xref + (size_t)inst * S::NX : xref};
     unsigned char* rec = A.codes + (size_t)inst * A.code_stride;
     if (mode == 2) {
@@ -782,35 +778,17 @@ __global__ void __launch_bounds__(TPI_POL_WARPS * 32, 1) k_tpi_pol(const __grid_
     const int nchunks = (A.count + 31) / 32;
     if (blockIdx.x == 0 && threadIdx.x < BMPC_CNT) A.counts_next[threadIdx.x] = 0;
     if (threadIdx.x == 0) atomicMax((unsigned long long*)(A.counts + BMPC_CNT_T0), ~bmpc_globaltimer());
-    // ---- phase A.  x0 and u_-1 of the NEXT chunk are requested before the current chunk is processed: they may live in mapped host
-    // memory (the end-to-end path reads them over PCIe in place), and a refinement is long enough to hide that latency completely
-    auto grab = [&]() { int c = 0; if (lane == 0) c = atomicAdd(A.counts + TPI_Q_CURSOR, 1); return __shfl_sync(0xffffffffu, c, 0); };
-    auto locate = [&](int chunk, int& idx0, int& nvalid, bool& valid, int& inst) {
-        idx0 = chunk * 32; nvalid = (A.count - idx0) < 32 ? (A.count - idx0) : 32;
-        valid = lane < nvalid; inst = A.list ? (valid ? A.list[idx0 + lane] : 0) : idx0 + lane;
-    };
-    double x0n[S::nx], um1n = 0.0;
-    int chunk = grab();
-    if (chunk < nchunks) {
-        int idx0, nvalid, inst; bool valid; locate(chunk, idx0, nvalid, valid, inst);
-#pragma unroll
-        for (int q = 0; q < S::nx; q++) x0n[q] = valid ? I.x0[(size_t)inst * S::nx + q] : 0.0;
-        um1n = valid ? I.um1[(size_t)inst] : 0.0;
-    }
-    while (chunk < nchunks) {
-        int idx0, nvalid, inst; bool valid; locate(chunk, idx0, nvalid, valid, inst);
-        double x0c[S::nx]; const double um1c = um1n;
-#pragma unroll
-        for (int q = 0; q < S::nx; q++) x0c[q] = x0n[q];
-        chunk = grab();
-        if (chunk < nchunks) {
-            int idx0b, nvalidb, instb; bool validb; locate(chunk, idx0b, nvalidb, validb, instb);
-#pragma unroll
-            for (int q = 0; q < S::nx; q++) x0n[q] = validb ? I.x0[(size_t)instb * S::nx + q] : 0.0;
-            um1n = validb ? I.um1[(size_t)instb] : 0.0;
-        }
-        if constexpr (PERINST) { const TpiPolView<S> Pv(A.pview + inst, (size_t)A.pstride); tpi_pol_batch<S, TV>(Pv, I, A, wsm, csm, inst, valid, A.list ? -1 : idx0, nvalid, A.mode, A.capA, A.capB > 0, A.reset, x0c, um1c); }
-        else tpi_pol_batch<S, TV>(P, I, A, wsm, csm, inst, valid, A.list ? -1 : idx0, nvalid, A.mode, A.capA, A.capB > 0, A.reset, x0c, um1c);
+    // ---- phase A
+    for (;;) {
+        int chunk = 0;
+        if (lane == 0) chunk = atomicAdd(A.counts + TPI_Q_CURSOR, 1);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= nchunks) break;
+        const int idx0 = chunk * 32, nvalid = (A.count - idx0) < 32 ? (A.count - idx0) : 32;
+        const bool valid = lane < nvalid;
+        const int inst = A.list ? (valid ? A.list[idx0 + lane] : 0) : idx0 + lane;
+        if constexpr (PERINST) { const TpiPolView<S> Pv(A.pview + inst, (size_t)A.pstride); tpi_pol_batch<S, TV>(Pv, I, A, wsm, csm, inst, valid, A.list ? -1 : idx0, nvalid, A.mode, A.capA, A.capB > 0, A.reset); }
+        else tpi_pol_batch<S, TV>(P, I, A, wsm, csm, inst, valid, A.list ? -1 : idx0, nvalid, A.mode, A.capA, A.capB > 0, A.reset);
     }
     auto leave = [&]() {
         if (lane != 0) return;
