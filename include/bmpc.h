@@ -164,6 +164,11 @@ void* bmpc_host_alloc(uint64_t bytes);
 void bmpc_host_free(void* p);
 /* 1 if this build of the library holds the thread-per-instance fast path for the shape (nu == 1; Nc <= 0 means Nc = Np) */
 int bmpc_has_fast_path(int nx, int nu, int Np, int Nc);
+
+/* 1 when this build holds a thread-per-instance instantiation of the multi-input Riccati polish (csrc/bmpc_tpm.cuh) for the shape
+ * (any sparsity pattern; bmpc_setup picks the entry whose compile-time (Ad, Bd) pattern contains the system's, or none).  Such a
+ * controller starts every warm solve with that polish alone — no ADMM — and falls back to the ADMM rounds per instance. */
+int bmpc_has_multi_input_fast_path(int nx, int nu, int Np, int Nc);
 /* number of visible CUDA devices (0 if none / driver missing) */
 int bmpc_device_count(void);
 

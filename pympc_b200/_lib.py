@@ -31,7 +31,7 @@ EXPORTS = ["bmpc_default_config", "bmpc_create", "bmpc_destroy", "bmpc_last_erro
            "bmpc_solve", "bmpc_output", "bmpc_get_sequences", "bmpc_bind_output", "bmpc_bind_output_peers", "bmpc_bind_gather_flags",
            "bmpc_gather_arrive", "bmpc_set_stream",
            "bmpc_synchronize", "bmpc_get_stats", "bmpc_get_sys", "bmpc_get_dims", "bmpc_host_alloc",
-           "bmpc_host_free", "bmpc_device_count", "bmpc_has_fast_path", "bmpc_est_create", "bmpc_est_destroy", "bmpc_est_predict",
+           "bmpc_host_free", "bmpc_device_count", "bmpc_has_fast_path", "bmpc_has_multi_input_fast_path", "bmpc_est_create", "bmpc_est_destroy", "bmpc_est_predict",
            "bmpc_est_update", "bmpc_est_get", "bmpc_est_state_ptr", "bmpc_est_set_stream", "bmpc_est_attach"]
 
 
@@ -83,6 +83,7 @@ def load(path=None):
     L.bmpc_est_set_stream.argtypes = [P, P]; L.bmpc_est_set_stream.restype = ctypes.c_int
     L.bmpc_est_attach.argtypes = [P, P]; L.bmpc_est_attach.restype = ctypes.c_int
     L.bmpc_has_fast_path.argtypes = [ctypes.c_int] * 4; L.bmpc_has_fast_path.restype = ctypes.c_int
+    L.bmpc_has_multi_input_fast_path.argtypes = [ctypes.c_int] * 4; L.bmpc_has_multi_input_fast_path.restype = ctypes.c_int
     _libs[path] = L
     if path == os.path.abspath(LIB_PATH):
         _lib = L

@@ -61,6 +61,33 @@ def jit_shape(nx, nu, Np, Nc=None, verbose=False):
     return lib
 
 
+def jit_multi_input_shape(nx, nu, Np, Nc=None, Ad=None, Bd=None, verbose=False):
+    """Build (once; cached under pympc_b200/_jit/) a copy of the library whose multi-input fast-path table holds the shape
+    (nx, nu, Np, Nc) — with the sparsity pattern of (Ad, Bd) fixed at compile time when they are given and small enough for the
+    pattern masks (the sweeps then skip the structural zeros) — and return its path."""
+    import numpy as np
+    Nc = Np if Nc is None else Nc
+    if nu < 1 or 2 * nx + 10 * nu > 64 or not (1 <= Nc <= Np):
+        raise ValueError("multi-input fast-path shapes need 2 nx + 10 nu <= 64 and 1 <= Nc <= Np")
+    line = f"BMPC_TPM_SHAPE({nx}, {nu}, {Np}, {Nc})"; tag = f"m{nx}_{nu}_{Np}_{Nc}"
+    if Ad is not None and Bd is not None and nx * nx <= 64 and nx * nu <= 32:
+        A = np.asarray(Ad, float).reshape(nx, nx); Bm = np.asarray(Bd, float).reshape(nx, nu)
+        am = sum(1 << i for i, v in enumerate(A.ravel()) if v != 0.0); bm = sum(1 << i for i, v in enumerate(Bm.ravel()) if v != 0.0)
+        if am != (1 << (nx * nx)) - 1 or bm != (1 << (nx * nu)) - 1:
+            line = f"BMPC_TPM_SPARSE_SHAPE({nx}, {nu}, {Np}, {Nc}, 0x{am:x}ull, 0x{bm:x}u)\n" + line      # the dense entry stays behind it
+            tag += f"_{am:x}_{bm:x}"
+    jdir = os.path.join(_HERE, "_jit"); os.makedirs(jdir, exist_ok=True)
+    inc = os.path.join(jdir, f"shape_{tag}.inc"); lib = os.path.join(jdir, f"libbmpc_{tag}.so")
+    if not os.path.exists(inc):
+        open(inc, "w").write(line + "\n")
+    deps = [p for p in DEPS if not p.endswith("tpm_shapes.inc")]
+    if not os.path.exists(lib) or any(os.path.getmtime(lib) < os.path.getmtime(p) for p in deps):
+        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [f'-DBMPC_TPM_SHAPES_FILE="{inc}"', SRC, "-o", lib + ".tmp"]
+        subprocess.check_call(cmd)
+        os.replace(lib + ".tmp", lib)
+    return lib
+
+
 if __name__ == "__main__":
     import sys
     if len(sys.argv) == 3 and sys.argv[1] == "--add-shape":          # nx,nu,Np[,Nc]

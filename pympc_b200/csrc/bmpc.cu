@@ -1174,8 +1174,11 @@ static bool tpm_fill_entry(const double* hs, const BmpcSysOff& o, void* pp) { re
 #define BMPC_TPM_T4(T_, a, b, c, d) T_<a, b, c, d>
 #define BMPC_TPM_T6(T_, a, b, c, d, e, f) T_<a, b, c, d, e, f>
 // (entries are tried in order: sparse patterns first, the dense instantiation of a shape last)
+#ifndef BMPC_TPM_SHAPES_FILE
+#define BMPC_TPM_SHAPES_FILE "tpm_shapes.inc"
+#endif
 static const TpmEntry g_tpm_table[] = {
-#include "tpm_shapes.inc"
+#include BMPC_TPM_SHAPES_FILE
 };
 #undef BMPC_TPM_SHAPE
 #undef BMPC_TPM_SPARSE_SHAPE
@@ -1198,6 +1201,13 @@ int bmpc_has_fast_path(int nx, int nu, int Np, int Nc) {
     if (Nc <= 0) Nc = Np;
     for (int k = 0; k < g_tpi_count; k++)
         if (g_tpi_table[k].nx == nx && g_tpi_table[k].nu == nu && g_tpi_table[k].Np == Np && g_tpi_table[k].Nc == Nc) return 1;
+    return 0;
+}
+
+int bmpc_has_multi_input_fast_path(int nx, int nu, int Np, int Nc) {
+    if (Nc <= 0) Nc = Np;
+    for (int k = 0; k < g_tpm_count; k++)
+        if (g_tpm_table[k].nx == nx && g_tpm_table[k].nu == nu && g_tpm_table[k].Np == Np && g_tpm_table[k].Nc == Nc) return 1;
     return 0;
 }
 
@@ -1653,7 +1663,7 @@ static int enqueue_round(bmpc_handle* h) {
             g_tpi_table[h->tpi_kind - 1].launch_polish(h, st.list, st.count, st.nxt);
         // multi-input fast-path shapes: the Riccati polish (a refinement costs about one ADMM iteration of this shape) instead of
         // the Schur-form one, which takes over for the instances that are still open after 200 iterations (any working set)
-        else if (h->cfg.polish && h->tpm_kind && st.list != nullptr && st.total + st.chunk <= 200)
+        else if (h->cfg.polish && h->tpm_kind && st.total + st.chunk <= 200)           // (also the first attempt of a cold start: working sets from the iterate)
             g_tpm_table[h->tpm_kind - 1].launch(h, st.list, st.count, 2, h->tpm_round_cap, 0, st.nxt);
         else if (h->cfg.polish) launch_polish(h, st.list, st.count, st.nxt, cnt);
         else { k_check_converged<<<(st.count + 255) / 256, 256, 0, h->stream>>>(h->I, st.list, st.count, h->cfg.eps_abs, h->cfg.eps_rel, st.nxt, cnt); h->stats.launches++; }

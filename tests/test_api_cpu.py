@@ -105,6 +105,12 @@ def test_fast_path_table_query_and_on_demand_shape_build(bmpc_lib):
     for bad in ((4, 2, 20, None), (8, 1, 20, None), (2, 1, 40, None), (3, 1, 10, 11)):
         with pytest.raises(ValueError):
             build.jit_shape(*bad)
+    # multi-input table (thread-per-instance Riccati polish over the scalar delta-u chain): MIMO reference-governor shape compiled in
+    assert bmpc_lib.bmpc_has_multi_input_fast_path(8, 4, 40, 40) == 1 and bmpc_lib.bmpc_has_multi_input_fast_path(8, 4, 40, 0) == 1
+    assert bmpc_lib.bmpc_has_multi_input_fast_path(8, 4, 12, 5) == 1 and bmpc_lib.bmpc_has_multi_input_fast_path(3, 2, 10, 10) == 0
+    for bad in ((12, 5, 10, None), (3, 2, 10, 11), (30, 1, 10, None)):      # working-set word: 2 nx + 10 nu <= 64 bits
+        with pytest.raises(ValueError):
+            build.jit_multi_input_shape(*bad)
 
 
 def test_output_arrays_are_reused_only_when_the_caller_dropped_them():

@@ -771,3 +771,42 @@ def test_multi_input_fast_path_agrees_with_team_path(MPC):
     assert iters[0] < 0.8 * iters[1], iters                        # warm solves mostly verify from the shifted working sets
     for K in Ks:
         K.close()
+
+
+def test_multi_input_fast_path_built_on_demand_for_a_dense_system(MPC):
+    """fast_path=2: a shape the in-tree table does not hold (3 states, 2 inputs, Np = 10, Nc = 6; dense Ad, Bd with one structural
+    zero) gets its multi-input Riccati polish built on the spot with the system's sparsity pattern; input boxes, delta-u chain,
+    soft state rows, held input, full Qu, uref, time-varying reference — against the team kernels on every instance and the
+    oracle on a sample."""
+    rng = np.random.default_rng(5); B = 256
+    A = rng.standard_normal((3, 3)); A *= 0.95 / max(abs(np.linalg.eigvals(A))); A[2, 0] = 0.0
+    c = dict(Ad=A, Bd=rng.standard_normal((3, 2)), Np=10, Nc=6, Qx=np.diag([1.0, 0.5, 0.2]), QxN=np.diag([2.0, 0.5, 0.2]),
+             Qu=np.array([[0.1, 0.02], [0.02, 0.3]]), QDu=np.diag([0.5, 0.2]), xmin=-1.5 * np.ones(3), xmax=1.5 * np.ones(3),
+             umin=-np.array([0.8, 0.5]), umax=np.array([0.6, 0.9]), Dumin=-np.array([0.3, 0.4]), Dumax=np.array([0.4, 0.3]),
+             eps_feas=1e3, uref=np.array([0.05, -0.05]))
+    X0 = rng.uniform(-1.2, 1.2, (B, 3)); Xr = 0.3 * rng.standard_normal((B, 3))
+    Ks = [MPC(**dict(c, x0=X0, xref=Xr, uminus1=np.zeros(2)), batch=B, fast_path=f) for f in (2, 0)]
+    for K in Ks:
+        K.setup()
+    assert Ks[0]._L.bmpc_has_multi_input_fast_path(3, 2, 10, 6) == 1 and Ks[1]._L.bmpc_has_multi_input_fast_path(3, 2, 10, 6) == 0
+    X = X0.copy(); U = np.zeros((B, 2)); its = [0, 0]
+    for t in range(8):
+        Xtv = None
+        if t >= 5:                                                  # time-varying reference on top (mpc.py:414-421)
+            Xtv = Xr[:, None, :] * np.linspace(0.5, 1.0, 11)[None, :, None]
+        outs = []; sts = []
+        for i, K in enumerate(Ks):
+            K.update(X, U, xref=Xtv) if Xtv is not None else K.update(X, U)
+            Un, info = K.output(return_u_seq=True)
+            outs.append(info["u_seq"].reshape(B, -1)); sts.append(np.array(K.res.info.status_val).copy()); its[i] += K.stats()["admm_iters"]
+            assert np.isin(sts[-1], (1, 2)).all(), (t, i)
+        both = (sts[0] == 1) & (sts[1] == 1)
+        assert both.mean() > 0.95 and np.max(np.abs(outs[0][both] - outs[1][both])) < TOL, (t, both.mean())
+        for b in (0, B // 2, B - 1):
+            if sts[0][b] == 1:
+                ref, Q = _oracle_u(dict(c, x0=X[b], xref=(Xtv[b] if Xtv is not None else Xr[b]), uminus1=U[b]))
+                assert np.max(np.abs(outs[0][b] - ref)) < TOL, (t, b)
+        U = outs[1][:, :2].copy(); X = X @ c["Ad"].T + U @ c["Bd"].T + 0.02 * rng.standard_normal((B, 3))
+    assert its[0] < 0.7 * its[1], its
+    for K in Ks:
+        K.close()
