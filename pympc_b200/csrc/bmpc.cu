@@ -881,7 +881,7 @@ __global__ void __launch_bounds__(32) k_tpm_pol(const __grid_constant__ TpmParam
     const int lane = threadIdx.x, idx = blockIdx.x * 32 + lane;
     const bool valid = idx < A.count;
     const int inst = valid ? (A.list ? A.list[idx] : idx) : 0;
-    TpiAcc W{A.W + (size_t)blockIdx.x * L::slots * 32 + lane, 32};
+    TpiStreamAcc W{A.W + (size_t)blockIdx.x * L::slots * 32 + lane, 32};
     uint64_t cur[Np], atb[Np];
     uint64_t dump = 0ull; uint64_t* const dp = &dump;
     auto C = [&](int k) -> uint64_t& { return cur[k]; };
@@ -952,7 +952,7 @@ __global__ void __launch_bounds__(32) k_tpm_pol(const __grid_constant__ TpmParam
 #pragma unroll
             for (int q = 0; q < nx; q++) v[q] = x0[q];
             for (int k = 0; k < Np; k++)
-                for (int p = 0; p < 2 * nu + nx; p++) { const int row = tpm_vstar_row<S>(k, p); if (row >= 0) v[row] = W(k * L::per_stage + p); }
+                for (int p = 0; p < 2 * nu + nx; p++) { const int row = tpm_vstar_row<S>(k, p); if (row >= 0) v[row] = W.ld(k * L::per_stage + p); }
 #pragma unroll
             for (int j = 0; j < nu; j++) v[NX + NU + j] = vfirst[j];
             v[mc - 1] = vq;

@@ -64,7 +64,18 @@ struct TpiAdmmParams {
 struct TpiAcc {
     double* p; int stride;
     BMPC_HD double& operator()(int i) const { return p[i * stride]; }
+    BMPC_HD double ld(int i) const { return p[i * stride]; }
+    BMPC_HD void st(int i, double v) const { p[i * stride] = v; }
 };
+#ifndef BMPC_HOSTEMU
+// the same column in GLOBAL memory, streamed: loads and stores marked evict-first so that the gain rows (written once, read once
+// per refinement) do not push the kernel's local memory out of L1 / L2
+struct TpiStreamAcc {
+    double* p; int stride;
+    __device__ __forceinline__ double ld(int i) const { return __ldcs(p + (size_t)i * stride); }
+    __device__ __forceinline__ void st(int i, double v) const { __stcs(p + (size_t)i * stride, v); }
+};
+#endif
 
 // plain selects (no IEEE fmin/fmax NaN handling: ~3 instructions instead of ~10 in fp64)
 BMPC_HD double tpi_clamp(double v, double lo, double hi) { double t = v; t = (v > hi) ? hi : t; t = (v < lo) ? lo : t; return t; }

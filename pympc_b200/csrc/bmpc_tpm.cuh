@@ -173,9 +173,9 @@ BMPC_HD void tpm_backward(const PP& P, WA W, CA C, XR xr, const double* um1) {
             for (int t = 0; t < n; t++) yrow[t] = hus[t];
             yrow[io] = fma(huu, so, yrow[io]); yrow[in_] = fma(huu, sn, yrow[in_]);
 #pragma unroll
-            for (int t = 0; t < n; t++) W(base + j * nz + t) = free_ ? hus[t] * inv : yrow[t];
-            W(base + j * nz + n) = free_ ? gu * inv : y0;
-            W(base + j * nz + n + 1) = pin; W(base + j * nz + n + 2) = (double)tau;
+            for (int t = 0; t < n; t++) W.st(base + j * nz + t, free_ ? hus[t] * inv : yrow[t]);
+            W.st(base + j * nz + n, free_ ? gu * inv : y0);
+            W.st(base + j * nz + n + 1, pin); W.st(base + j * nz + n + 2, (double)tau);
             // P' = Hss - kap hus hus' + (so e_io + sn e_in) y~' + hus (so e_io + sn e_in)'   with y~ = y of the pinned policy
             // p' = gs + hus k0 + k (gu + huu k0)
 #pragma unroll
@@ -340,14 +340,18 @@ BMPC_HD int tpm_forward(const PP& P, WA W, CA C, CB_ CB, CK_ CK, const double* x
             for (int a = 0; a < nx; a++) s[a] = y[a];
         }
         uint64_t ncode = 0ull, acode = 0ull, kcode = 0ull;
+        // the stage's rows, all requested before the first use (the staging stores below alias them: the compiler would not hoist)
+        double g[nu * nz];
+#pragma unroll
+        for (int i = 0; i < nu * nz; i++) g[i] = W.ld(base + i);
 #pragma unroll
         for (int j = 0; j < nu; j++) {
             const int io = nx + j, in_ = nx + (j > 0 ? j - 1 : nu - 1);
-            double lin = W(base + j * nz + n);
+            double lin = g[j * nz + n];
 #pragma unroll
-            for (int t = 0; t < n; t++) lin = fma(W(base + j * nz + t), s[t], lin);
-            const double pin = W(base + j * nz + n + 1);
-            const int tau = (int)W(base + j * nz + n + 2);
+            for (int t = 0; t < n; t++) lin = fma(g[j * nz + t], s[t], lin);
+            const double pin = g[j * nz + n + 1];
+            const int tau = (int)g[j * nz + n + 2];
             const double rold = s[io], prev = s[in_];
             double u = pin;                                             // absolute pins
             u = (tau == TPM_HELD) ? rold : u;
@@ -366,7 +370,7 @@ BMPC_HD int tpm_forward(const PP& P, WA W, CA C, CB_ CB, CK_ CK, const double* x
                 r = hard_row(u, P.ulo_m[j], P.uhi_p[j], P.ulo[j], P.uhi[j], cb & 3u, mu_u);
                 nb |= r & 3u; ab |= (r >> 2) & 3u; kb |= (r >> 4) & 3u;
                 TpmInterval M = TpmInterval::row((r >> 2) & 1u, (r >> 3) & 1u);
-                W(base + 2 * j) = stage_v(u, mu_u, P.irhou[j], cb & 3u, r, P.ulo[j], P.uhi[j]);
+                W.st(base + 2 * j, stage_v(u, mu_u, P.irhou[j], cb & 3u, r, P.ulo[j], P.uhi[j]));
                 if (k == 0) {
                     r = hard_row(u - rold, P.flo_m[j], P.fhi_p[j], P.flo[j], P.fhi[j], (cb >> 2) & 3u, mu_f);
                     nb |= (r & 3u) << 2; ab |= ((r >> 2) & 3u) << 2; kb |= ((r >> 4) & 3u) << 2;
@@ -377,7 +381,7 @@ BMPC_HD int tpm_forward(const PP& P, WA W, CA C, CB_ CB, CK_ CK, const double* x
                 if (k > 0 || j > 0) {
                     r = hard_row(u - prev, P.clo_m[j], P.chi_p[j], P.clo[j], P.chi[j], (cb >> 4) & 3u, mu_c);
                     nb |= (r & 3u) << 4; ab |= ((r >> 2) & 3u) << 4; kb |= ((r >> 4) & 3u) << 4;
-                    W(base + 2 * j + 1) = stage_v(u - prev, mu_c, P.irhoc[j], (cb >> 4) & 3u, r, P.clo[j], P.chi[j]);
+                    W.st(base + 2 * j + 1, stage_v(u - prev, mu_c, P.irhoc[j], (cb >> 4) & 3u, r, P.clo[j], P.chi[j]));
                     // violated although both of its scalars are held by other rows: two anchors in one run.  Next resolution lets this row
                     // pin the scalar whose anchor carries the smaller multiplier (hint bits 8 / 9 of the channel field)
                     if (((r >> 6) & 1u) && !carry_on && tau != TPM_CHAIN && tau != TPM_FREE && prev_tau != TPM_FREE && prev_tau != TPM_HELD) {
@@ -415,7 +419,7 @@ BMPC_HD int tpm_forward(const PP& P, WA W, CA C, CB_ CB, CK_ CK, const double* x
             const double zi = s[a];
             pbad |= (unsigned)(zi < P.xacc_lo[a][lab]) | (unsigned)(zi > P.xacc_hi[a][lab]);
             const uint64_t nu_ = zi > P.xhi_p[a], nd_ = zi < P.xlo_m[a];
-            W(base + 2 * nu + a) = fma(P.xcm[a][lab], zi - P.xbnd[a][lab], zi);
+            W.st(base + 2 * nu + a, fma(P.xcm[a][lab], zi - P.xbnd[a][lab], zi));
             ncode |= nu_ << (CD::XUP + a);
             ncode |= (nd_ & ~nu_ & 1ull) << (CD::XDN + a);
         }
