@@ -249,8 +249,8 @@ class MPCController:
             return np.zeros(nx)
         xref = np.asarray(xref, dtype=float)
         if self.batch is not None:
-            if xref.ndim == 3 and xref.shape[0] == B and xref.shape[2] == nx and xref.shape[1] >= Np:
-                return xref
+            if xref.ndim == 3 and xref.shape[0] == B and xref.shape[2] == nx and (xref.shape[1] >= Np or xref.shape[1] == 1):
+                return xref                                     # (B, Np+1, nx) per-instance trajectories, (B, 1, nx) per-instance constants
             if xref.ndim == 2 and xref.shape == (B, nx) and not (B >= Np and B == Np + 1):
                 return xref
         if __is_vector__(xref) and xref.size == nx:
@@ -265,6 +265,8 @@ class MPCController:
         xref = np.asarray(xref, dtype=float)
         if xref.ndim == 1:
             return np.broadcast_to(xref, (B, nx)), 1
+        if xref.ndim == 3 and xref.shape[1] == 1:
+            return xref.reshape(B, nx), 1                       # explicit per-instance constant references (unambiguous for any batch size)
         if xref.ndim == 3:
             if xref.shape[1] != Np + 1:
                 raise ValueError("time-varying xref needs exactly Np+1 rows")   # the reference crashes here too (Q6)
@@ -274,6 +276,9 @@ class MPCController:
         if xref.shape[0] >= Np + 1:
             if xref.shape[0] != Np + 1:
                 raise ValueError("time-varying xref needs exactly Np+1 rows")
+            if self.batch is not None and B == Np + 1:
+                warnings.warn("xref of shape (Np+1, nx) with batch == Np+1 is read as ONE time-varying reference shared by all instances "
+                              "(the reference's meaning of a 2-D xref); pass shape (batch, 1, nx) for per-instance constant references")
             return np.broadcast_to(xref.reshape(1, -1), (B, (Np + 1) * nx)), Np + 1
         raise ValueError("time-varying xref needs exactly Np+1 rows")
 

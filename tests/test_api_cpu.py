@@ -134,3 +134,23 @@ def test_output_arrays_are_reused_only_when_the_caller_dropped_them():
     for t in range(10):                                   # a plain closed loop cycles through two arrays
         U = fresh(f); f.uminus1_rh = U
     assert len(f._out_pool) <= 7                          # b, c, d, e are still held by this test; the loop itself needs two
+
+
+def test_batched_xref_shapes_are_unambiguous():
+    """a 2-D xref keeps the reference's meaning (one (Np+1, nx) trajectory, mpc.py:120,414-421) even when batch == Np+1 — with a
+    warning —; per-instance constant references have the explicit form (batch, 1, nx)"""
+    import warnings
+    from pympc_b200.mpc import MPCController
+    Ad = np.array([[1.0, 0.2], [0.0, 1.0]]); Bd = np.array([[0.0], [0.2]])
+    K = MPCController(Ad, Bd, Np=3, batch=4, x0=np.zeros((4, 2)), Qx=np.eye(2), QDu=np.eye(1))
+    R = np.arange(8.0).reshape(4, 2)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        arr, rows = K._xref_device_layout(R)
+    assert rows == 4 and arr.shape == (4, 8) and (arr == R.ravel()).all() and any("batch, 1, nx" in str(m.message) for m in w)
+    arr, rows = K._xref_device_layout(R[:, None, :])
+    assert rows == 1 and arr.shape == (4, 2) and (arr == R).all()
+    assert K._xref_arg(R[:, None, :]).shape == (4, 1, 2)
+    K5 = MPCController(Ad, Bd, Np=3, batch=5, x0=np.zeros((5, 2)), Qx=np.eye(2), QDu=np.eye(1))
+    arr, rows = K5._xref_device_layout(np.ones((5, 2)))          # batch != Np+1: (B, nx) is per-instance, as before
+    assert rows == 1 and arr.shape == (5, 2)

@@ -810,3 +810,36 @@ def test_multi_input_fast_path_built_on_demand_for_a_dense_system(MPC):
     assert its[0] < 0.7 * its[1], its
     for K in Ks:
         K.close()
+
+
+def test_straggler_rounds_after_the_speculative_result_copy(MPC):
+    """output() queues the device-to-host copy of u0 behind the first round, speculating that it finishes every instance
+    (bmpc_output).  Here it does not: after three warm steps the state of 64 instances jumps, their shifted working sets fail
+    and they take straggler rounds that rewrite u0 — the array output() returns must hold the FINAL values (checked against the
+    team kernels on all instances and the oracle on the jumped ones)."""
+    cfg = pendulum(); B = 4096
+    X0, Xref = pendulum_random(B, seed=21)
+    kw = {k: cfg[k] for k in ("Qx", "QxN", "Qu", "QDu", "xmin", "xmax", "umin", "umax", "Dumin", "Dumax", "eps_feas")}
+    Ks = [MPC(cfg["Ad"], cfg["Bd"], Np=20, x0=X0, xref=Xref, uminus1=np.zeros(1), batch=B, fast_path=f, **kw) for f in (1, 0)]
+    for K in Ks:
+        K.setup()
+    rng = np.random.default_rng(2)
+    X = X0.copy(); U = np.zeros((B, 1)); saw_rounds = 0
+    for t in range(6):
+        if t == 3:
+            jump = rng.choice(B, 64, replace=False)
+            X[jump] = pendulum_random(64, seed=77)[0]                  # fresh random states: far from where the plans expected them
+        outs = []
+        for K in Ks:
+            K.update(X, U); outs.append(K.output().copy())
+            assert (np.array(K.res.info.status_val) == 1).all(), (t, np.unique(np.array(K.res.info.status_val), return_counts=True))
+        if t == 3:
+            saw_rounds = Ks[0].stats()["rounds"]
+            for b in jump[:4]:
+                ref, Q = _oracle_u(dict(cfg, x0=X[b], xref=Xref[b], uminus1=U[b]))
+                assert abs(outs[0][b, 0] - ref[0]) < TOL, b
+        assert np.max(np.abs(outs[0] - outs[1])) < TOL, t
+        U = outs[0]; X = X @ cfg["Ad"].T + U @ cfg["Bd"].T
+    assert saw_rounds > 1, "the jump was meant to force straggler rounds"
+    for K in Ks:
+        K.close()
