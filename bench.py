@@ -233,6 +233,7 @@ class Gather:
         L, h = self.K._L, self.K.handle
         self.parity = parity
         self.Uloc = self.buf[parity, self.s:self.e]
+        self.K._external_output = True                             # the controller must not rebind its own pinned result arrays
         L.bmpc_bind_output(h, self.Uloc.data_ptr())
         if self.fused:
             off = (parity * self.Btot + self.s) * self.nu * 8

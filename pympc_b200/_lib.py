@@ -107,6 +107,7 @@ class PinnedArray:
         if not self._p:
             raise BmpcError("cudaHostAlloc failed")
         buf = (ctypes.c_char * max(self.nbytes, 8)).from_address(self._p)
+        buf._owner = self                     # views handed out (numpy -> memoryview -> buf) keep the allocation alive
         self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
         self.array[...] = 0
 

@@ -218,8 +218,10 @@ class MPCController:
         self.solver_options = dict(solver_options)
         # zero_copy (default on): the kernels read x0 / u_-1 from, and write u* to, pinned host memory in place (see _push / solve)
         self._zero_copy = bool(self.solver_options.pop("zero_copy", True))
+        self._external_output = False        # set by whoever binds the solver's output buffer himself (bmpc_bind_output: bench.py's gather)
         self._bound_u = None
         self._out_pool = []
+        self._out_pins = []; self._u0_pooled = False
         self._L = _lib.load()                      # raises if the CUDA extension is missing
         self._h = None
         self.res = None
@@ -456,10 +458,14 @@ class MPCController:
     def solve(self):
         """Solve the QP batch.  mpc.py:366-375."""
         B, nu = self._B, self.nu
-        u = self._pin.get("u") or self._pin.setdefault("u", PinnedArray((B, nu)))
+        u = self._next_result_array() if (self._zero_copy and not self._external_output) else None
+        self._u0_pooled = u is not None
+        if u is None:
+            u = self._pin.get("u") or self._pin.setdefault("u", PinnedArray((B, nu)))
         st = self._pin.get("status") or self._pin.setdefault("status", PinnedArray((B,), np.int32))
-        if self._zero_copy and self._bound_u != u.array.ctypes.data:
-            # the solver epilogue stores u* straight into the pinned (device-mapped) result array: no D2H copy after the solve
+        if self._zero_copy and not self._external_output and self._bound_u != u.array.ctypes.data:
+            # the solver epilogue stores u* straight into a pinned (device-mapped) result array: no D2H copy after the solve — and, with a
+            # small pool of such arrays, none on the host either: output() hands the array itself to the caller
             self._check(self._L.bmpc_bind_output(self._h, ptr(u.array))); self._bound_u = u.array.ctypes.data
         self._check(self._L.bmpc_solve(self._h))
         self._check(self._L.bmpc_output(self._h, ptr(u.array), ptr(st.array), 0, 0))
@@ -502,7 +508,7 @@ class MPCController:
             raise BmpcError("output() before a solve")
         B, nx, nu, Np, Nc = self._B, self.nx, self.nu, self.Np, self.Nc
         # failed instances already carry u_failure = uref (written by the device epilogue, mpc.py:303-304)
-        uMPC = self._fresh_output()
+        uMPC = self._u0 if self._u0_pooled else self._fresh_output()
         info = {}
         if return_x_seq or return_u_seq or return_eps_seq or return_obj_val:
             useq = np.empty((B, Nc * nu)) if return_u_seq else None
@@ -532,6 +538,18 @@ class MPCController:
         if len(info) == 0:
             return uMPC
         return uMPC, info
+
+    def _next_result_array(self):
+        """a pinned result array nobody outside holds any more (the caller dropped what output() gave it two steps ago; the current
+        result and uminus1_rh are references too), or a new one while the pool is small; None: fall back to one array + a copy"""
+        import sys
+        for pin in self._out_pins:
+            if sys.getrefcount(pin.array) <= 2:                  # pin.array + getrefcount's argument
+                return pin
+        if len(self._out_pins) < 6:
+            pin = PinnedArray((self._B, self.nu)); self._out_pins.append(pin)
+            return pin
+        return None
 
     def _fresh_output(self):
         """a copy of the result the caller owns, like the reference returns a new array every call — but without paying an

@@ -154,3 +154,34 @@ def test_batched_xref_shapes_are_unambiguous():
     K5 = MPCController(Ad, Bd, Np=3, batch=5, x0=np.zeros((5, 2)), Qx=np.eye(2), QDu=np.eye(1))
     arr, rows = K5._xref_device_layout(np.ones((5, 2)))          # batch != Np+1: (B, nx) is per-instance, as before
     assert rows == 1 and arr.shape == (5, 2)
+
+
+def test_result_arrays_handed_out_without_a_copy_are_not_overwritten_while_held(monkeypatch):
+    """zero-copy results: the solver writes u* into one of a few pinned arrays and output() returns that array itself; an array is
+    bound again only when nobody outside holds it (the caller, uminus1_rh and the current result are references)"""
+    import pympc_b200.mpc as M
+
+    class FakePin:
+        def __init__(self, shape, dtype=np.float64):
+            self.array = np.zeros(shape, dtype)
+    monkeypatch.setattr(M, "PinnedArray", FakePin)
+
+    class Fake:
+        pass
+    f = Fake(); f._out_pins = []; f._B = 8; f.nu = 1
+    nxt = M.MPCController._next_result_array
+    held = []
+    p0 = nxt(f); held.append(p0.array)                        # the caller keeps the first result
+    p1 = nxt(f); assert p1 is not p0
+    a1 = p1.array; del p1
+    p2 = nxt(f); assert p2.array is not a1 and p2.array is not held[0]      # a1 still referenced here
+    del a1, p2
+    p3 = nxt(f); assert p3.array is not held[0]               # one of the dropped ones comes back, never the held one
+    assert len(f._out_pins) <= 3
+    del p3
+    for _ in range(10):                                       # a caller that keeps everything: the pool stops growing, then no array is offered
+        p = nxt(f)
+        if p is None:
+            break
+        held.append(p.array); del p
+    assert len(f._out_pins) == 6 and nxt(f) is None
