@@ -267,7 +267,7 @@ class Gather:
         return bool(ok.item() == 1.0)
 
 
-def device_loop(torch, dist, K, cfg, X0, steps, warmup, dev, world, gather, flush, sampler=None):
+def device_loop(torch, dist, K, cfg, X0, steps, warmup, dev, world, gather, flush, sampler=None, t_off=0):
     """timed region of `value`: inputs resident in HBM, CUDA events on the launching stream around every step"""
     L, h = K._L, K.handle
     # ONE explicit stream for the solver, the L2 flush, the plant and the timing events.  (torch's default stream has handle 0,
@@ -289,8 +289,8 @@ def device_loop(torch, dist, K, cfg, X0, steps, warmup, dev, world, gather, flus
             torch.cuda.synchronize(dev)
             if sampler is not None:
                 sampler.start()
-        gather.bind(t & 1)
-        Uprev = gather.buf[(t & 1) ^ 1, gather.s:gather.e]        # u* of the previous step = this step's u_-1
+        gather.bind((t + t_off) & 1)
+        Uprev = gather.buf[((t + t_off) & 1) ^ 1, gather.s:gather.e]    # u* of the previous step = this step's u_-1
         flush.zero_()                                             # L2 flush between timed iterations (outside the events)
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -379,7 +379,7 @@ def make_controller(cfg, X0, Xref, B, device, **opts):
     return K
 
 
-def side_config(torch, dist, dev, name, cfg, X0, Xref, steps, warmup, shape_key, peaks, flush):
+def side_config(torch, dist, dev, name, cfg, X0, Xref, steps, warmup, shape_key, peaks, flush, settle_steps=0):
     """one extra BASELINE config on rank 0 of a single-GPU run: device + e2e throughput, solver statistics, oracle spot check"""
     B = X0.shape[0]; nu = cfg["Bd"].shape[1]
     K = make_controller(cfg, X0, Xref, B, dev.index)
@@ -387,6 +387,13 @@ def side_config(torch, dist, dev, name, cfg, X0, Xref, steps, warmup, shape_key,
     cold_ms = 1e3 * (time.perf_counter() - t0); cold = K.stats()
     G = Gather(K, torch, dist, dev, B, nu, 0, 1, True)
     tot_ms, acc, rounds, Xd = device_loop(torch, dist, K, cfg, X0, steps, warmup, dev, 1, G, flush)
+    settled = None
+    if settle_steps > 0:
+        # the same closed loop continued until the transient is over: the regime a controller spends its life in
+        s_ms, s_acc, s_rounds, Xd = device_loop(torch, dist, K, cfg, Xd.cpu().numpy(), steps, settle_steps, dev, 1, G, flush, t_off=steps + warmup)
+        settled = {"after_steps": steps + warmup + settle_steps, "steps": steps, "value": B * steps / (s_ms * 1e-3), "unit": UNIT, "ms_per_step": s_ms / steps,
+                   "solver": {"mean_rounds": float(np.mean(s_rounds)), "unsolved": int(s_acc["unsolved"]), "admm_iters_per_solve": s_acc["admm_iters"] / (B * steps),
+                              "refinements_per_solve": s_acc["polish_steps"] / (B * steps)}}
     e2e_steps = min(steps, 200)
     K._L.bmpc_bind_output(K.handle, None)
     e2e_t, Xh, Uh = e2e_loop(torch, dist, K, cfg, X0, e2e_steps, warmup, dev, 1, G, flush)
@@ -399,7 +406,7 @@ def side_config(torch, dist, dev, name, cfg, X0, Xref, steps, warmup, shape_key,
                        "refinements_per_solve": acc["polish_steps"] / (B * steps), "launches_per_step": acc["launches"] / steps},
             "cold_first_solve": {"ms": cold_ms, "rounds": cold["rounds"], "unsolved": cold["unsolved"]},
             "oracle_spot_check": {"instances": 8, "max_abs_err_u": err, "tol": 1e-6, "ok": bool(err < 1e-6)},
-            "roofline": kern}
+            "roofline": kern, **({"settled": settled} if settled else {})}
 
 
 def gpu_arm(args, rank, world, local_rank):
@@ -497,8 +504,8 @@ def gpu_arm(args, rank, world, local_rank):
             cfgs["random_1000"] = {"error": repr(exc)}
         try:
             c4, X4, R4 = mimo_batch(16384)
-            cfgs["mimo_16384"] = side_config(torch, dist, dev, "configs[3]: MIMO reference-governor shape nx=8 nu=4 Np=40, B=16384, random x0",
-                                             c4, X4, R4, 10, 3, "mimo_8_4_40_40", peaks, flush)
+            cfgs["mimo_16384"] = side_config(torch, dist, dev, "configs[3]: MIMO reference-governor shape nx=8 nu=4 Np=40, B=16384, random x0; value = steps 4-13 of the transient from a cold start, settled = the same loop 60 steps later",
+                                             c4, X4, R4, 10, 3, "mimo_8_4_40_40", peaks, flush, settle_steps=60)
         except Exception as exc:                                   # pragma: no cover
             cfgs["mimo_16384"] = {"error": repr(exc)}
         out["configs"] = cfgs
