@@ -385,7 +385,8 @@ class MPCController:
         wants_fast = opts.get("fast_path", 1) and not opts.get("team_threads", 0) and opts.get("polish", 1) and self.SOFT_ON and not self._per_instance
         NX, NU = (self.Np + 1) * self.nx, self.Nc * self.nu
         small = (NX + NU + (self.Nc + 1) * self.nu) <= 192 and NU <= 64          # the library's own rule for the warp-team family
-        if wants_fast and int(opts.get("fast_path", 1)) >= 2 and self.nu >= 1 and not (self.nu == 1 and small) and 2 * self.nx + 10 * self.nu <= 64 \
+        tpi_fits = self.nu == 1 and small and self.Np * self.nx <= 128 and self.Np < 32        # the single-input kernels hold this shape
+        if wants_fast and int(opts.get("fast_path", 1)) >= 2 and not tpi_fits and 2 * self.nx + 10 * self.nu <= 64 \
                 and not L.bmpc_has_multi_input_fast_path(self.nx, self.nu, self.Np, self.Nc) and not os.environ.get("BMPC_NO_JIT"):
             # fast_path=2: also build the multi-input Riccati polish for this shape (and this system's sparsity pattern) on the spot
             try:
