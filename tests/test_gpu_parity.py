@@ -843,3 +843,35 @@ def test_straggler_rounds_after_the_speculative_result_copy(MPC):
     assert saw_rounds > 1, "the jump was meant to force straggler rounds"
     for K in Ks:
         K.close()
+
+
+def test_multi_input_fast_path_dense_instantiation(MPC):
+    """an 8-state 4-input system WITHOUT the reference governor's sparsity pattern (dense random Ad, Bd; input boxes; soft state rows)
+    at the compiled horizons takes the dense instantiation of k_tpm_pol (bmpc_setup picks the first table entry whose pattern
+    masks contain the system's): same plans as the team kernels, oracle on a sample"""
+    rng = np.random.default_rng(8); B = 96
+    A = rng.standard_normal((8, 8)); A *= 0.9 / max(abs(np.linalg.eigvals(A)))
+    c = dict(Ad=A, Bd=0.5 * rng.standard_normal((8, 4)), Np=40, Qx=np.diag(rng.uniform(0.2, 2.0, 8)), QxN=np.diag(rng.uniform(0.2, 2.0, 8)),
+             Qu=0.05 * np.eye(4), QDu=np.diag([0.5, 0.3, 0.4, 0.6]), xmin=-2.0 * np.ones(8), xmax=2.0 * np.ones(8), umin=-1.0 * np.ones(4),
+             umax=1.0 * np.ones(4), Dumin=-0.3 * np.ones(4), Dumax=0.3 * np.ones(4), eps_feas=1e3)
+    X0 = rng.uniform(-1.5, 1.5, (B, 8)); Xr = 0.2 * rng.standard_normal((B, 8))
+    Ks = [MPC(**dict(c, x0=X0, xref=Xr, uminus1=np.zeros(4)), batch=B, fast_path=f) for f in (1, 0)]
+    for K in Ks:
+        K.setup()
+    assert Ks[0]._L.bmpc_has_multi_input_fast_path(8, 4, 40, 40) == 1
+    X = X0.copy(); U = np.zeros((B, 4)); its = [0, 0]
+    for t in range(5):
+        outs = []; sts = []
+        for i, K in enumerate(Ks):
+            K.update(X, U); Un, info = K.output(return_u_seq=True)
+            outs.append(info["u_seq"].reshape(B, -1)); sts.append(np.array(K.res.info.status_val).copy()); its[i] += K.stats()["admm_iters"]
+            assert np.isin(sts[-1], (1, 2)).all(), (t, i)
+        both = (sts[0] == 1) & (sts[1] == 1)
+        assert both.mean() > 0.9 and np.max(np.abs(outs[0][both] - outs[1][both])) < TOL, (t, both.mean())
+        b = int(np.flatnonzero(both)[0])
+        ref, Q = _oracle_u(dict(c, x0=X[b], xref=Xr[b], uminus1=U[b]))
+        assert np.max(np.abs(outs[0][b] - ref)) < TOL, (t, b)
+        U = outs[1][:, :4].copy(); X = X @ c["Ad"].T + U @ c["Bd"].T + 0.01 * rng.standard_normal((B, 8))
+    assert its[0] < its[1], its                                  # the warm solves did start with the polish alone
+    for K in Ks:
+        K.close()
