@@ -110,6 +110,7 @@ class PinnedArray:
         buf._owner = self                     # views handed out (numpy -> memoryview -> buf) keep the allocation alive
         self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
         self.array[...] = 0
+        self.ptr = ctypes.c_void_p(self._p)   # (a.ctypes.data_as costs ~2.5 us per call: cached for the per-step calls)
 
     def __del__(self):
         try:

@@ -218,10 +218,12 @@ class MPCController:
         self.solver_options = dict(solver_options)
         # zero_copy (default on): the kernels read x0 / u_-1 from, and write u* to, pinned host memory in place (see _push / solve)
         self._zero_copy = bool(self.solver_options.pop("zero_copy", True))
+        self._stats_buf = BmpcStats(); self._stats_ref = ctypes.byref(self._stats_buf)
         self._external_output = False        # set by whoever binds the solver's output buffer himself (bmpc_bind_output: bench.py's gather)
         self._bound_u = None
         self._out_pool = []
         self._out_pins = []; self._u0_pooled = False
+        self._pin_ptr = getattr(self, "_pin_ptr", {})
         self._L = _lib.load()                      # raises if the CUDA extension is missing
         self._h = None
         self.res = None
@@ -308,7 +310,9 @@ class MPCController:
         shapes = {"x0": (self._B, self.nx), "uminus1": (self._B, self.nu), "xref": (self._B, self.nx), "u": (self._B, self.nu)}
         if name not in self._pin:
             self._pin[name] = PinnedArray(shapes[name])
-        return self._pin[name].array
+        pin = self._pin[name]
+        self._pin_ptr[id(pin.array)] = pin                   # update() recognises the caller's pinned buffers by identity (no per-call ctypes work)
+        return pin.array
 
     def _check(self, rc):
         if rc < 0:
@@ -418,6 +422,12 @@ class MPCController:
         retired before the buffers can change, i.e. from update(..., solve=True)"""
         B, nx, nu = self._B, self.nx, self.nu
         px = pu = pr = None; rows = 1
+        if borrow and xref is None and x0 is not None:
+            # the per-step call of a closed loop with the caller's own pinned buffers: two dictionary look-ups, one C call
+            ex = self._pin_ptr.get(id(x0)); eu = self._pin_ptr.get(id(um1)) if um1 is not None else None
+            if ex is not None and ex.array is x0 and (um1 is None or (eu is not None and eu.array is um1)):
+                self._check(self._L.bmpc_update(self._h, ex.ptr, eu.ptr if eu is not None else None, None, 1, 2))
+                return
         if x0 is not None:
             px = ptr(self._stage("x0", np.asarray(x0, dtype=float).reshape(-1, nx) if np.ndim(x0) > 1 else np.asarray(x0, dtype=float), (B, nx)))
         if um1 is not None:
@@ -464,17 +474,18 @@ class MPCController:
         if u is None:
             u = self._pin.get("u") or self._pin.setdefault("u", PinnedArray((B, nu)))
         st = self._pin.get("status") or self._pin.setdefault("status", PinnedArray((B,), np.int32))
-        if self._zero_copy and not self._external_output and self._bound_u != u.array.ctypes.data:
+        if self._zero_copy and not self._external_output and self._bound_u != u.ptr.value:
             # the solver epilogue stores u* straight into a pinned (device-mapped) result array: no D2H copy after the solve — and, with a
             # small pool of such arrays, none on the host either: output() hands the array itself to the caller
-            self._check(self._L.bmpc_bind_output(self._h, ptr(u.array))); self._bound_u = u.array.ctypes.data
+            self._check(self._L.bmpc_bind_output(self._h, u.ptr)); self._bound_u = u.ptr.value
         self._check(self._L.bmpc_solve(self._h))
-        self._check(self._L.bmpc_output(self._h, ptr(u.array), ptr(st.array), 0, 0))
+        self._check(self._L.bmpc_output(self._h, u.ptr, st.ptr, 0, 0))
         self._u0, self._status = u.array, st.array
         self._make_res()
         # only instances that were never KKT-verified or were certified infeasible can carry a negative status: skip the
         # scan of the status array when the solve reports none of either
-        s = BmpcStats(); self._check(self._L.bmpc_get_stats(self._h, ctypes.byref(s)))
+        s = self._stats_buf
+        self._check(self._L.bmpc_get_stats(self._h, self._stats_ref))
         if (s.unsolved != 0 or s.infeasible != 0) and np.any(self._status < 0):
             warnings.warn('OSQP did not solve the problem!')
             if self.raise_error:
