@@ -185,3 +185,32 @@ def test_result_arrays_handed_out_without_a_copy_are_not_overwritten_while_held(
             break
         held.append(p.array); del p
     assert len(f._out_pins) == 6 and nxt(f) is None
+
+
+def test_multi_input_shape_table_is_well_formed():
+    """csrc/tpm_shapes.inc: every entry fits the 64-bit working-set word (2 nx + 10 nu), pattern entries come before the dense entry of
+    their shape (bmpc_setup takes the first entry whose masks contain the system's pattern) and the masks of the MIMO reference
+    governor's entry are exactly the non-zeros of that system (pympc_b200.workloads.mimo)"""
+    import os, re
+    from pympc_b200.workloads import mimo
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pympc_b200", "csrc", "tpm_shapes.inc")
+    entries = []
+    for line in open(path):
+        m = re.match(r"^BMPC_TPM_SPARSE_SHAPE\((\d+),\s*(\d+),\s*(\d+),\s*(\d+),\s*(0x[0-9a-fA-F]+)ull,\s*(0x[0-9a-fA-F]+)u\)", line)
+        if m:
+            entries.append(tuple(int(v) for v in m.groups()[:4]) + (int(m.group(5), 16), int(m.group(6), 16)))
+            continue
+        m = re.match(r"^BMPC_TPM_SHAPE\((\d+),\s*(\d+),\s*(\d+),\s*(\d+)\)", line)
+        if m:
+            entries.append(tuple(int(v) for v in m.groups()) + (None, None))
+    assert len(entries) >= 3
+    for nx, nu, Np, Nc, am, bm in entries:
+        assert 2 * nx + 10 * nu <= 64 and 1 <= Nc <= Np, (nx, nu, Np, Nc)
+        if am is not None:
+            assert nx * nx <= 64 and nx * nu <= 32 and am < (1 << (nx * nx)) and bm < (1 << (nx * nu))
+            later_dense = [e for e in entries[entries.index((nx, nu, Np, Nc, am, bm)) + 1:] if e[:4] == (nx, nu, Np, Nc) and e[4] is None]
+            assert later_dense, "a pattern entry needs the dense entry of its shape behind it"
+    c = mimo()
+    am = sum(1 << i for i, v in enumerate(np.asarray(c["Ad"]).ravel()) if v != 0.0)
+    bm = sum(1 << i for i, v in enumerate(np.asarray(c["Bd"]).ravel()) if v != 0.0)
+    assert (8, 4, 40, 40, am, bm) in entries
