@@ -47,9 +47,10 @@ struct BmpcSysOff {
 // scal[] slots
 // adaptive-rho table: level l uses rho * 10^((l - BMPC_LEV0)/2) and its own K^-1 (OSQP refactors on a rho change; with shared
 // matrices the factors for a fixed ladder are precomputed once instead)
-enum { BMPC_NLEV = 7, BMPC_LEV0 = 2 };
+enum { BMPC_NLEV = 11, BMPC_LEV0 = 2 };
 BMPC_HOSTDEV double bmpc_level_factor(int l) {
-    const double f[BMPC_NLEV] = {0.1, 0.31622776601683794, 1.0, 3.1622776601683795, 10.0, 31.622776601683793, 100.0};
+    const double f[BMPC_NLEV] = {0.1, 0.31622776601683794, 1.0, 3.1622776601683795, 10.0, 31.622776601683793, 100.0,
+                                 316.22776601683796, 1000.0, 3162.2776601683795, 10000.0};
     return f[l];
 }
 
@@ -678,6 +679,26 @@ BMPC_HD bool bmpc_primal_infeasible(Team& t, const BmpcDims& d, const BmpcSysOff
     return t.max(la) < eps * ndy;
 }
 
+// triangular solves with the packed unit-lower factor of S = L D L' (dv = 1/d_j), in place, by ONE warp (warp-level barriers
+// only): L y = t, z = D^-1 y, L' mu = z
+template <class Team>
+BMPC_HD void bmpc_ldl_solve(Team& t, const double* S, const double* dv, double* tt, int r) {
+    #define BMPC_TRI_(k, l) ((size_t)(k) * ((k) + 1) / 2 + (l))
+    for (int j = 0; j < r; j++) {
+        const double sj = dv[j] * tt[j];
+        for (int i = j + 1 + t.lane(); i < r; i += t.lanes()) tt[i] -= S[BMPC_TRI_(i, j)] * sj;
+        t.wsync();
+    }
+    for (int j = t.lane(); j < r; j += t.lanes()) tt[j] *= dv[j];
+    t.wsync();
+    for (int j = r - 1; j > 0; j--) {
+        const double mj = tt[j];
+        for (int i = t.lane(); i < j; i += t.lanes()) tt[i] -= S[BMPC_TRI_(j, i)] * dv[i] * mj;
+        t.wsync();
+    }
+    #undef BMPC_TRI_
+}
+
 // ------------------------------------------------------------------------------------------------
 // K5: polish.  Primal-dual active-set refinement on the condensed QP, in dual (Schur) form:
 // with R the current set of "working" rows (violated soft rows + active hard rows, bound b_R),
@@ -762,21 +783,30 @@ BMPC_HD int bmpc_polish(Team& t, const BmpcDims& d, const BmpcSysOff& o, const d
                 t.sync();
             }
             // triangular solves by one warp (warp-level barriers only): L y = t, z = D^-1 y, L' mu = z
-            if (t.warp() == 0) {
-                for (int j = 0; j < r; j++) {
-                    const double sj = dv[j] * tt[j];
-                    for (int i = j + 1 + t.lane(); i < r; i += t.lanes()) tt[i] -= S[BMPC_TRI(i, j)] * sj;
-                    t.wsync();
-                }
-                for (int j = t.lane(); j < r; j += t.lanes()) tt[j] *= dv[j];
-                t.wsync();
-                for (int j = r - 1; j > 0; j--) {
-                    const double mj = tt[j];
-                    for (int i = t.lane(); i < j; i += t.lanes()) tt[i] -= S[BMPC_TRI(j, i)] * dv[i] * mj;
-                    t.wsync();
-                }
-            }
+            if (t.warp() == 0) bmpc_ldl_solve(t, S, dv, tt, r);
             t.sync();
+            // Large multipliers (a state far outside its soft box with a big eps_feas: mu ~ eps_feas * distance, balanced by the
+            // active hard rows) make the hard-row regularisation visible: the candidate's active hard rows miss their bounds by
+            // delta (1 + M_kk) mu_k (4e-8 at mu = 3e5) and fail the 1e-9 feasibility test although the working set is the right
+            // one — 70 % of such instances then never verify.  One step of iterative refinement against the unregularised system
+            // removes it: S e = Delta mu, mu += e.  Only when that miss comes near the tolerance: with ordinary multipliers the
+            // correction is below rounding, and on dependent working rows (degenerate vertices) it would amplify the null-space
+            // component the regularisation keeps small.
+            double* mu0 = murow;                               // free until the multipliers are scattered below
+            double lm0 = 0.0;
+            for (int k = t.tid; k < r; k += t.n) {
+                const int i = R[k]; const double m = tt[k];
+                const double miss = (soft_on && i < NX) ? 0.0 : delta * (1.0 + fabs(M[(size_t)i * mc + i])) * m;
+                mu0[k] = miss; lm0 = fmax(lm0, fabs(miss));
+            }
+            if (t.max(lm0) > 2e-10) {
+                for (int k = t.tid; k < r; k += t.n) { const double m = tt[k]; tt[k] = mu0[k]; mu0[k] = m; }
+                t.sync();
+                if (t.warp() == 0) bmpc_ldl_solve(t, S, dv, tt, r);
+                t.sync();
+                for (int k = t.tid; k < r; k += t.n) tt[k] += mu0[k];
+                t.sync();
+            }
         }
         for (int i = t.tid; i < mc; i += t.n) murow[i] = 0.0;
         t.sync();
