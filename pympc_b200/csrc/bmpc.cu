@@ -1592,19 +1592,20 @@ static void launch_admm(bmpc_handle* h, const int32_t* list, int count, int nite
 }
 
 static void launch_polish(bmpc_handle* h, const int32_t* list, int count, int32_t* next_list, int32_t* next_count) {
+    const int steps = bmpc_polish_steps(h->cfg.pdas_steps, h->st.round);
     if (use_fallback_team(h, list, count)) {
-        k_polish<false><<<count, h->fb_team, h->fb_smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->fb_rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0, nullptr, nullptr, h->cfg.candidate_warm);
+        k_polish<false><<<count, h->fb_team, h->fb_smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->fb_rmax, steps, next_list, next_count, h->I.u0, nullptr, nullptr, h->cfg.candidate_warm);
     } else if (h->team == 32) {
         int grid = (count + h->wpb - 1) / h->wpb;
-        k_polish<true><<<grid, h->wpb * 32, h->smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0, nullptr, nullptr, h->cfg.candidate_warm);
+        k_polish<true><<<grid, h->wpb * 32, h->smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->rmax, steps, next_list, next_count, h->I.u0, nullptr, nullptr, h->cfg.candidate_warm);
     } else if (h->rmax_small > 0) {
         // two capacity tiers: the small one keeps several CTAs resident per SM (the polish is latency-bound); working
         // sets that outgrow it are listed and redone by the full-capacity launch right after (count read on the device)
-        k_polish<false><<<count, h->team, h->smem_polish_small, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->rmax_small, h->cfg.pdas_steps, next_list, next_count, h->I.u0, nullptr, h->ovf, h->cfg.candidate_warm);
-        k_polish<false><<<count, h->team, h->smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, h->ovf, count, h->rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0, next_count + 2, nullptr, h->cfg.candidate_warm);
+        k_polish<false><<<count, h->team, h->smem_polish_small, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->rmax_small, steps, next_list, next_count, h->I.u0, nullptr, h->ovf, h->cfg.candidate_warm);
+        k_polish<false><<<count, h->team, h->smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, h->ovf, count, h->rmax, steps, next_list, next_count, h->I.u0, next_count + 2, nullptr, h->cfg.candidate_warm);
         h->stats.launches++;
     } else {
-        k_polish<false><<<count, h->team, h->smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->rmax, h->cfg.pdas_steps, next_list, next_count, h->I.u0, nullptr, nullptr, h->cfg.candidate_warm);
+        k_polish<false><<<count, h->team, h->smem_polish, h->stream>>>(h->d, h->o, h->sys, h->I, list, count, h->rmax, steps, next_list, next_count, h->I.u0, nullptr, nullptr, h->cfg.candidate_warm);
     }
     h->stats.launches++;
 }

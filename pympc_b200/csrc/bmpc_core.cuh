@@ -48,6 +48,11 @@ struct BmpcSysOff {
 // adaptive-rho table: level l uses rho * 10^((l - BMPC_LEV0)/2) and its own K^-1 (OSQP refactors on a rho change; with shared
 // matrices the factors for a fixed ladder are precomputed once instead)
 enum { BMPC_NLEV = 11, BMPC_LEV0 = 2 };
+// polish: active-set steps that update all rows at once before the hard rows switch to single exchanges
+enum { BMPC_PDAS_FULL = 3 };
+// refinements allowed per polish attempt: the configured count in the first two rounds of a solve (every instance passes there),
+// three times as many for the instances that come back from further ADMM rounds (few, and single exchanges need the room)
+BMPC_HOSTDEV int bmpc_polish_steps(int pdas_steps, int round) { return round >= 2 ? 3 * pdas_steps : pdas_steps; }
 BMPC_HOSTDEV double bmpc_level_factor(int l) {
     const double f[BMPC_NLEV] = {0.1, 0.31622776601683794, 1.0, 3.1622776601683795, 10.0, 31.622776601683793, 100.0,
                                  316.22776601683796, 1000.0, 3162.2776601683795, 10000.0};
@@ -823,9 +828,15 @@ BMPC_HD int bmpc_polish(Team& t, const BmpcDims& d, const BmpcSysOff& o, const d
         }
         t.sync();
         for (int i = t.tid; i < mc; i += t.n) zz[i] = bmpc_Arow_dot(d, BcalT, U, i) + (i < NX ? cc[i] : 0.0);
-        // verification + next sets
+        // verification + next sets.  The first BMPC_PDAS_FULL steps update every row at once (primal-dual active-set step: two or
+        // three of them settle an ordinary solve).  That update can cycle when many hard rows are active at once; from then on the
+        // soft-row labels still follow the candidate, but the hard rows change by single exchanges — per step the most violated
+        // row enters and the row with the largest wrong-signed multiplier leaves — which does not cycle in practice (host study,
+        // tools/soft_row_study.py: instances ending as max-iter 5 % -> 0.5 %, ADMM iterations per solve 553 -> 63).
         bool ok = true;
         const double mutol = 1e-9 * (1.0 + mumax);
+        const bool exchange = step >= BMPC_PDAS_FULL;
+        double best_add = -1.0, best_drop = -1.0; int i_add = -1, i_drop = -1, s_add = 0;
         for (int i = t.tid; i < mc; i += t.n) {
             double lo, hi; bmpc_row_bounds(d, lo0, hi0, um1, i, lo, hi);
             int s = st[i], ns; double zi = zz[i];
@@ -846,8 +857,21 @@ BMPC_HD int bmpc_polish(Team& t, const BmpcDims& d, const BmpcSysOff& o, const d
                 bool bad = vu || vd || (s == 1 && mu < -mutol) || (s == 2 && mu > mutol);
                 if (bad) ok = false;
                 ns = vu ? 1 : (vd ? 2 : ((s == 1 && mu > 0.0) ? 1 : ((s == 2 && mu < 0.0) ? 2 : 0)));
+                if (exchange && ns != s) {
+                    if (ns == 0) { const double sc = fabs(mu); if (sc > best_drop) { best_drop = sc; i_drop = i; } }
+                    else {
+                        const double sc = fmax(zi - hi, lo - zi) / (1.0 + fmin(fabs(hi), fabs(lo)));
+                        if (sc > best_add) { best_add = sc; i_add = i; s_add = ns; }
+                    }
+                    ns = s;
+                }
             }
             st[i] = ns;
+        }
+        if (exchange) {
+            const double g_add = t.max(best_add), g_drop = t.max(best_drop);
+            if (i_add >= 0 && best_add == g_add) st[i_add] = s_add;
+            if (i_drop >= 0 && best_drop == g_drop) st[i_drop] = 0;
         }
         ok = t.all(ok);
         t.sync();
