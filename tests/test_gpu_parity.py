@@ -667,9 +667,10 @@ def test_random_systems_vs_oracle(MPC, eps_feas):
             K.close()
     total = sum(tally.values())
     print("random systems tally", eps_feas, tally)
-    # eps_feas = 1e3: practically everything is solved.  eps_feas = 1e5 with states 1.5x outside the box is the documented gap
-    # (DESIGN.md section 7): the multipliers eps_feas * d are out of reach of 4000 un-equilibrated ADMM iterations for about one
-    # instance in nine (measured 50 of 448), which end as max-iter -> u_failure where OSQP's relative tolerance says "solved"
+    # eps_feas = 1e3: practically everything is solved.  eps_feas = 1e5 with states 1.5x outside the box was round 1's documented gap
+    # (DESIGN.md section 7): before the polish learned iterative refinement and single exchanges one instance in nine (50 of 448)
+    # ended as max-iter -> u_failure where OSQP's relative tolerance says "solved".  The bounds below are the ones that run passed
+    # with; the host-emulation twin of this test (test_states_far_outside_the_soft_box_still_verify) holds the tight ones
     assert tally["fail"] <= (0.03 if eps_feas < 1e4 else 0.15) * total, tally
     assert tally[1] >= (0.9 if eps_feas < 1e4 else 0.45) * total, tally
 
