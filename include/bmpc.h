@@ -58,7 +58,7 @@ typedef struct {
     int32_t n_sys;              /* 1 = every instance shares (Ad,Bd,weights,bounds); batch = one system per instance */
     int32_t shift_warm;         /* 1 (default) = a warm fast-path solve starts from the previous working sets shifted by one stage (receding horizon: update() is one sample later); 0 = unshifted */
     int32_t candidate_warm;     /* 1 = an instance the polish could not verify AND whose ADMM is stalled (relative primal residual > 1e-2 after >= 25 iterations) continues its ADMM rounds from the last candidate (rows and multipliers) when that candidate's hard rows are feasible to 1e-2: the remedy for strongly violated soft rows with a large eps_feas; 0 (default) = from its own ADMM state: on regular transients replacing the iterate costs a few instances their verification */
-    int32_t cold_iters;         /* ADMM iterations before the first polish attempt of a COLD solve on the team / tile kernels (0 = auto: 50) */
+    int32_t cold_iters;         /* ADMM iterations before the first polish attempt of a COLD solve on the team / tile kernels (0 = auto: 50; 25 on multi-input fast-path shapes) */
     double eps_feas;            /* slack weight (mpc.py:226) */
     double rho;                 /* <= 0: automatic sqrt(trace H / trace A'A) */
     double sigma, alpha;        /* OSQP defaults 1e-6, 1.6 */

@@ -1032,7 +1032,7 @@ struct bmpc_handle {
     double* vprev = nullptr; int32_t* lprev = nullptr;   // snapshot of (v, level) for the infeasibility check of straggler rounds
     void (*tile_fn[3])(BmpcDims, BmpcSysOff, const double*, BmpcInst, const int32_t*, int, int, int, int, int, int) = {nullptr, nullptr, nullptr};
     int tile_T = 0, tile_threads = 0;                  // > 0: the ADMM of this shape runs on tiles of T instances per CTA
-    struct { const int32_t* list; int count; int32_t *cur, *nxt; int total, chunk, round; bool need_prep; int tight; } st = {};
+    struct { const int32_t* list; int count; int32_t *cur, *nxt; int total, chunk, round; bool need_prep; int tight; bool cold; } st = {};
     bool pending = false;              // a round is in flight and has not been retired by the host yet
     int tpi_kind = 0;                  // 0 none, else 1 + index into g_tpi_table (compiled fast-path shapes)
     void *tpi_admm_params = nullptr, *tpi_polish_params = nullptr;   // host copies of the parameter blocks
@@ -1043,6 +1043,10 @@ struct bmpc_handle {
     void* tpm_params = nullptr;        // host copy of the parameter block
     double* tpm_W = nullptr; unsigned long long* tpm_rec = nullptr;   // gain rows of the resident warps, working-set records
     int tpm_first_cap = 12, tpm_round_cap = 4, tpm_chunk = 100;   // (measured on the MIMO side bench, tools/sweep_tpm_caps.sh: 13.3 ms/step at 8,6,25 -> 11.4 ms)      // refinements of the first launch / of a straggler round, ADMM iterations of the first straggler round
+    // cold solves: working sets read off a rough ADMM iterate need 8 - 14 refinements, not 4 (host study on 48 random MIMO starts,
+    // first polish after 25 iterations: cap 4 verifies none and the solve takes 333 iterations in 4.5 rounds, cap 12 79 %, cap 16 92 %,
+    // cap 24 all of them in the first round; after 50 iterations the same picture): every polish attempt of a cold solve gets this cap
+    int tpm_cold_cap = 24;
 };
 
 static std::string g_create_err;
@@ -1092,7 +1096,9 @@ static void launch_tpi_round(bmpc_handle* h, const int32_t* list, int count, int
     const TpiAdmmParams<S>& PA = *(const TpiAdmmParams<S>*)h->tpi_admm_params;
     const int cold = h->cold ? 1 : 0, reset = h->st.round == 0 ? 1 : 0;
     const size_t sa = S::MT * TPI_STR * 8;
-    const int capA = 1, capB = h->tpi_pdas_steps - 1;
+    // (a cold solve reads its working sets off a rough ADMM iterate: twice the refinements — host study on 300 random pendulum starts,
+    // first polish after 25 iterations: 88 % verify within 8 refinements, 99 % within 16, at most 3 rounds instead of 5)
+    const int capA = 1, capB = (h->st.cold ? 2 * h->tpi_pdas_steps : h->tpi_pdas_steps) - 1;
     if (niter > 0) {
         if (h->xref_mode)   // one (Np+1) x nx reference per instance
             k_tpi_admm<S, true><<<grid, 32, sa, h->stream>>>(PA, h->I, list, count, niter, cold, reset, h->counts + BMPC_CNT * h->cpar, h->um1_solved);
@@ -1114,7 +1120,7 @@ static void launch_tpi_round(bmpc_handle* h, const int32_t* list, int count, int
 template <class S>
 static void launch_tpi_polish_only(bmpc_handle* h, const int32_t* list, int count, int32_t* next_list) {
     h->spin_epoch = 0;
-    launch_tpi_pol<S>(h, list, count, 2, 2, h->tpi_pdas_steps - 2, 0, next_list);
+    launch_tpi_pol<S>(h, list, count, 2, 2, (h->st.cold ? 2 * h->tpi_pdas_steps : h->tpi_pdas_steps) - 2, 0, next_list);
 }
 
 template <class S>
@@ -1526,7 +1532,7 @@ int bmpc_setup(bmpc_handle* h, const double* Ad, const double* Bd, const double*
         if (!te.fill(hs.data(), o, h->tpm_params)) h->tpm_kind = 0;      // QDu not diagonal: team kernels
     }
     if (h->tpm_kind) {
-        if (const char* e = getenv("BMPC_TPM_CAPS")) sscanf(e, "%d,%d,%d", &h->tpm_first_cap, &h->tpm_round_cap, &h->tpm_chunk);   // tuning knob (tools/gpu_sweep.py)
+        if (const char* e = getenv("BMPC_TPM_CAPS")) sscanf(e, "%d,%d,%d,%d", &h->tpm_first_cap, &h->tpm_round_cap, &h->tpm_chunk, &h->tpm_cold_cap);   // tuning knob (tools/gpu_sweep.py)
         const TpmEntry& te = g_tpm_table[h->tpm_kind - 1];
         const size_t B = h->cfg.batch, nwarp = (B + 31) / 32;
         if (!h->tpm_W) BMPC_CUDA(cudaMalloc((void**)&h->tpm_W, sizeof(double) * nwarp * 32 * (size_t)te.slots));
@@ -1665,7 +1671,7 @@ static int enqueue_round(bmpc_handle* h) {
         // multi-input fast-path shapes: the Riccati polish (a refinement costs about one ADMM iteration of this shape) instead of
         // the Schur-form one, which takes over for the instances that are still open after 200 iterations (any working set)
         else if (h->cfg.polish && h->tpm_kind && st.total + st.chunk <= 200)           // (also the first attempt of a cold start: working sets from the iterate)
-            g_tpm_table[h->tpm_kind - 1].launch(h, st.list, st.count, 2, h->tpm_round_cap, 0, st.nxt);
+            g_tpm_table[h->tpm_kind - 1].launch(h, st.list, st.count, 2, st.cold ? h->tpm_cold_cap : h->tpm_round_cap, 0, st.nxt);
         else if (h->cfg.polish) launch_polish(h, st.list, st.count, st.nxt, cnt);
         else { k_check_converged<<<(st.count + 255) / 256, 256, 0, h->stream>>>(h->I, st.list, st.count, h->cfg.eps_abs, h->cfg.eps_rel, st.nxt, cnt); h->stats.launches++; }
     }
@@ -1742,7 +1748,7 @@ int bmpc_solve(bmpc_handle* h) {
     memset(&h->stats, 0, sizeof(h->stats));
     auto& st = h->st;
     st.list = nullptr; st.count = B; st.cur = h->listA; st.nxt = h->listB;
-    st.total = 0; st.round = 0; st.need_prep = true; st.tight = 0;
+    st.total = 0; st.round = 0; st.need_prep = true; st.tight = 0; st.cold = h->cold;
     if (h->gflags) h->g_epoch++;                     // every rank solves in lockstep: the arrival epoch of this step
     // first round: NO ADMM iterations on a warm fast-path solve (the previous solution's working sets are the best first guess
     // the active-set polish can get: measured 0 vs 1..10 iterations), 10 on the team kernels; first_iters > 0 overrides
@@ -1753,7 +1759,8 @@ int bmpc_solve(bmpc_handle* h) {
     if (h->cfg.polish && h->cfg.first_iters <= 0 && fast && h->cold) st.chunk = 25;
     // team / tile kernels, cold: 10 iterations from the free response leave working sets of hundreds of rows for the Schur polish
     // (round 1 measured 180 ms launches on the MIMO shape): iterate longer before the first attempt
-    if (h->cfg.polish && h->cfg.first_iters <= 0 && !fast && h->cold) st.chunk = h->cfg.cold_iters > 0 ? h->cfg.cold_iters : 50;
+    // (multi-input fast-path shapes: the Riccati polish takes the first attempt there and copes with the iterate after 25)
+    if (h->cfg.polish && h->cfg.first_iters <= 0 && !fast && h->cold) st.chunk = h->cfg.cold_iters > 0 ? h->cfg.cold_iters : (h->tpm_kind ? 25 : 50);
     if (h->cfg.polish && fast && h->tpi_view && !h->cold && h->cfg.first_iters > 0) st.chunk = h->cfg.first_iters;
     if (st.chunk > h->cfg.max_iter) st.chunk = h->cfg.max_iter;
     int rc = enqueue_round(h);
