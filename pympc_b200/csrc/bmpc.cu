@@ -874,7 +874,7 @@ struct TpmArgs {
 };
 struct TpmDiscard { unsigned long long sink; };
 
-template <class S, bool TV>
+template <class S, bool TV, bool EX>
 __global__ void __launch_bounds__(32) k_tpm_pol(const __grid_constant__ TpmParams<S> P, BmpcInst I, TpmArgs A) {
     using L = TpmLayout<S>; using CD = TpmCode<S>;
     constexpr int nx = S::nx, nu = S::nu, Np = S::Np, NU = S::NU, mc = S::mc, NX = S::NX;
@@ -926,7 +926,7 @@ __global__ void __launch_bounds__(32) k_tpm_pol(const __grid_constant__ TpmParam
     for (int r = 0; r < A.cap; r++) {
         if (!done) {
             tpm_backward<S>(P, W, C, xr, um1);
-            const int fl = tpm_forward<S>(P, W, C, CB, CK, x0, um1, mumax, vfirst, vq, [&](int k, int j, double u) { udst[k * nu + j] = u; });
+            const int fl = tpm_forward<S, EX>(P, W, C, CB, CK, x0, um1, mumax, vfirst, vq, [&](int k, int j, double u) { udst[k * nu + j] = u; });
             used++;
             ok = fl == 0; done = ok;
         }
@@ -980,7 +980,7 @@ __global__ void __launch_bounds__(32) k_tpm_pol(const __grid_constant__ TpmParam
 struct TpmEntry {
     int nx, nu, Np, Nc; unsigned long long amask; unsigned bmask; size_t par_bytes; int slots;
     bool (*fill)(const double* hs, const BmpcSysOff& o, void* pp);
-    void (*launch)(struct bmpc_handle* h, const int32_t* list, int count, int mode, int cap, int reset, int32_t* next_list);
+    void (*launch)(struct bmpc_handle* h, const int32_t* list, int count, int mode, int cap, int reset, int32_t* next_list, int exchange);
 };
 
 // Compiled fast-path shapes (nx, nu, Np, Nc) with nu == 1 and Nc == Np: one line per shape in csrc/tpi_shapes.inc
@@ -1042,7 +1042,11 @@ struct bmpc_handle {
     int tpm_kind = 0;                  // 0 none, else 1 + index into g_tpm_table (compiled multi-input fast-path shapes)
     void* tpm_params = nullptr;        // host copy of the parameter block
     double* tpm_W = nullptr; unsigned long long* tpm_rec = nullptr;   // gain rows of the resident warps, working-set records
-    int tpm_first_cap = 12, tpm_round_cap = 4, tpm_chunk = 100;   // (measured on the MIMO side bench, tools/sweep_tpm_caps.sh: 13.3 ms/step at 8,6,25 -> 11.4 ms)      // refinements of the first launch / of a straggler round, ADMM iterations of the first straggler round
+    // refinements of the first launch / of a straggler round, ADMM iterations of the first straggler round.  (12, 4, 100) was measured on
+    // the MIMO side bench with the all-at-once update in the straggler rounds too (tools/sweep_tpm_caps.sh: 13.3 ms/step at 8,6,25 ->
+    // 11.4 ms); the straggler rounds now run in exchange mode, where 12 refinements finish every straggler of the host study in the
+    // first round (all-at-once, cap 4: 54 %, three rounds for the rest) — chosen in host emulation, not yet swept on the GPU
+    int tpm_first_cap = 12, tpm_round_cap = 12, tpm_chunk = 100;
     // cold solves: working sets read off a rough ADMM iterate need 8 - 14 refinements, not 4 (host study on 48 random MIMO starts,
     // first polish after 25 iterations: cap 4 verifies none and the solve takes 333 iterations in 4.5 rounds, cap 12 79 %, cap 16 92 %,
     // cap 24 all of them in the first round; after 50 iterations the same picture): every polish attempt of a cold solve gets this cap
@@ -1161,15 +1165,21 @@ static const TpiEntry g_tpi_table[] = {
 static const int g_tpi_count = (int)(sizeof(g_tpi_table) / sizeof(g_tpi_table[0]));
 
 template <class S>
-static void launch_tpm(bmpc_handle* h, const int32_t* list, int count, int mode, int cap, int reset, int32_t* next_list) {
+static void launch_tpm(bmpc_handle* h, const int32_t* list, int count, int mode, int cap, int reset, int32_t* next_list, int exchange) {
     TpmArgs A;
     A.list = list; A.count = count; A.mode = mode; A.cap = cap; A.reset = reset;
     A.counts = h->counts + BMPC_CNT * h->cpar; A.next_list = next_list; A.u0_out = h->I.u0; A.um1_solved = h->um1_solved;
     A.W = h->tpm_W; A.rec = h->tpm_rec; A.rec_stride = S::Np + 2;
     const TpmParams<S>& P = *(const TpmParams<S>*)h->tpm_params;
     const int grid = (count + 31) / 32;
-    if (h->xref_mode) k_tpm_pol<S, true><<<grid, 32, 0, h->stream>>>(P, h->I, A);
-    else k_tpm_pol<S, false><<<grid, 32, 0, h->stream>>>(P, h->I, A);
+    // exchange: the straggler rounds' instantiation (hard rows change by single exchanges, tpm_forward<S, true>)
+    if (exchange) {
+        if (h->xref_mode) k_tpm_pol<S, true, true><<<grid, 32, 0, h->stream>>>(P, h->I, A);
+        else k_tpm_pol<S, false, true><<<grid, 32, 0, h->stream>>>(P, h->I, A);
+    } else {
+        if (h->xref_mode) k_tpm_pol<S, true, false><<<grid, 32, 0, h->stream>>>(P, h->I, A);
+        else k_tpm_pol<S, false, false><<<grid, 32, 0, h->stream>>>(P, h->I, A);
+    }
     h->stats.launches++;
 }
 template <class S>
@@ -1653,7 +1663,7 @@ static int enqueue_round(bmpc_handle* h) {
         g_tpi_table[h->tpi_kind - 1].launch(h, st.list, st.count, st.chunk, st.nxt, h->ev[1]);
     } else if (tpm0) {
         BMPC_CUDA(cudaEventRecord(h->ev[1], h->stream));
-        g_tpm_table[h->tpm_kind - 1].launch(h, nullptr, st.count, -1, h->tpm_first_cap, 1, st.nxt);
+        g_tpm_table[h->tpm_kind - 1].launch(h, nullptr, st.count, -1, h->tpm_first_cap, 1, st.nxt, 0);
     } else {
         // infeasible instances never pass the polish: from the third round on, look for OSQP's certificate
         const bool chk = st.total >= 25 && st.list != nullptr;
@@ -1671,7 +1681,8 @@ static int enqueue_round(bmpc_handle* h) {
         // multi-input fast-path shapes: the Riccati polish (a refinement costs about one ADMM iteration of this shape) instead of
         // the Schur-form one, which takes over for the instances that are still open after 200 iterations (any working set)
         else if (h->cfg.polish && h->tpm_kind && st.total + st.chunk <= 200)           // (also the first attempt of a cold start: working sets from the iterate)
-            g_tpm_table[h->tpm_kind - 1].launch(h, st.list, st.count, 2, st.cold ? h->tpm_cold_cap : h->tpm_round_cap, 0, st.nxt);
+            // (first attempt of a cold solve: all-at-once updates, tpm_cold_cap; every straggler round: single exchanges)
+            g_tpm_table[h->tpm_kind - 1].launch(h, st.list, st.count, 2, (st.cold && st.round == 0) ? h->tpm_cold_cap : h->tpm_round_cap, 0, st.nxt, (st.cold && st.round == 0) ? 0 : 1);
         else if (h->cfg.polish) launch_polish(h, st.list, st.count, st.nxt, cnt);
         else { k_check_converged<<<(st.count + 255) / 256, 256, 0, h->stream>>>(h->I, st.list, st.count, h->cfg.eps_abs, h->cfg.eps_rel, st.nxt, cnt); h->stats.launches++; }
     }

@@ -272,7 +272,13 @@ struct TpmInterval {
 // C(k): in = the working sets, out = the primal-dual active-set update; CB(k): out = the rows AT a bound at this candidate
 // (the description of a verified, possibly degenerate, vertex: what the next solve should start from); CK(k): out = the update without dual
 // drops (violated rows join, labelled rows stay while they sit at their bound).
-template <class S, class PP, class WA, class CA, class CB_, class CK_, class FU>
+// EX (exchange mode, the straggler rounds): the soft-row labels follow the candidate as always, but the hard-row labels change by
+// single exchanges — per refinement the most violated row enters and the PINNING row with the largest wrong-signed multiplier
+// leaves; labels of rows that pin nothing (no multiplier) still go.  The all-rows-at-once update of the default mode settles an
+// ordinary solve in 3 - 4 refinements but cycles on ~6 % of the MIMO transient's warm solves; single exchanges do not (host study
+// tools/tpm_search_study.py: every one of those stragglers verifies within 12 refinements after their ADMM chunk; 54 % with the
+// default update capped at 4).  A separate instantiation: the code of the default mode is unchanged.
+template <class S, bool EX, class PP, class WA, class CA, class CB_, class CK_, class FU>
 BMPC_HD int tpm_forward(const PP& P, WA W, CA C, CB_ CB, CK_ CK, const double* x0, const double* um1, double& mumax, double* vfirst, double& vq, FU outu) {
     constexpr int nx = S::nx, nu = S::nu, N = S::Np, Nc = S::Nc, n = TpmLayout<S>::n, nz = TpmLayout<S>::nz, PS = TpmLayout<S>::per_stage;
     using CD = TpmCode<S>;
@@ -288,10 +294,28 @@ BMPC_HD int tpm_forward(const PP& P, WA W, CA C, CB_ CB, CK_ CK, const double* x
 #pragma unroll
     for (int j = 0; j < nu; j++) s[nx + j] = um1[j];
     // one hard row: primal check, next label by the primal-dual rule (bits 0-1), at-bound label (bits 2-3), label without dual drops (bits 4-5), violated (bit 6)
-    auto hard_row = [&](double zi, double lo_m, double hi_p, double lo, double hi, unsigned lab, double mu) -> unsigned {
+    double x_add = -1.0, x_drop = 0.0; int xk_add = -1, xk_drop = -1; unsigned xp_add = 0u, xp_drop = 0u, xl_add = 0u;     // (EX only)
+    auto hard_row = [&](double zi, double lo_m, double hi_p, double lo, double hi, unsigned lab, double mu, unsigned pos) -> unsigned {
         const double m = (double)((int)(lab & 1u) - (int)(lab >> 1)) * mu;
         const unsigned vu = zi > hi_p, vd = zi < lo_m, keep = m > 0.0;
         pbad |= vu | vd;
+        if (EX) {
+            // pos: bit position of the row's label in the code word of stage tr_k
+            const unsigned au = zi >= hi - (hi_p - hi), ad = (zi <= lo + (lo - lo_m)) & ~au & 1u;
+            const unsigned ku = vu | (lab & au & 1u), kd = ~ku & (vd | ((lab >> 1) & ad)) & 1u;
+            unsigned nl = lab;
+            if (vu | vd) {
+                const unsigned want = vu ? 1u : 2u;
+                if (want != lab) {
+                    const double sc = (vu ? zi - hi : lo - zi) / (1.0 + fabs(vu ? hi : lo));
+                    if (sc > x_add) { x_add = sc; xk_add = tr_k; xp_add = pos; xl_add = want; }
+                }
+            } else if (lab != 0u && !keep) {
+                if (m < 0.0) { if (-m > x_drop) { x_drop = -m; xk_drop = tr_k; xp_drop = pos; } }
+                else nl = 0u;
+            }
+            return (nl & 3u) | (au << 2) | (ad << 3) | (ku << 4) | (kd << 5) | ((vu | vd) << 6);
+        }
 #ifdef TPM_TRACE
         if (vu | vd) printf("  hard row violated (k %d): z %.6g [%.6g, %.6g] lab %u mu %.6g\n", tr_k, zi, lo_m, hi_p, lab, mu);
 #endif
@@ -367,19 +391,19 @@ BMPC_HD int tpm_forward(const PP& P, WA W, CA C, CB_ CB, CK_ CK, const double* x
                 mnew += (tau == TPM_FREE) ? 0.0 : fabs(lin);
                 outu(k, j, u);
                 unsigned nb = 0u, ab = 0u, kb = 0u, r;                 // (nb: 10 bits: labels + hints)
-                r = hard_row(u, P.ulo_m[j], P.uhi_p[j], P.ulo[j], P.uhi[j], cb & 3u, mu_u);
+                r = hard_row(u, P.ulo_m[j], P.uhi_p[j], P.ulo[j], P.uhi[j], cb & 3u, mu_u, CD::CH0 + CD::CHS * j);
                 nb |= r & 3u; ab |= (r >> 2) & 3u; kb |= (r >> 4) & 3u;
                 TpmInterval M = TpmInterval::row((r >> 2) & 1u, (r >> 3) & 1u);
                 W.st(base + 2 * j, stage_v(u, mu_u, P.irhou[j], cb & 3u, r, P.ulo[j], P.uhi[j]));
                 if (k == 0) {
-                    r = hard_row(u - rold, P.flo_m[j], P.fhi_p[j], P.flo[j], P.fhi[j], (cb >> 2) & 3u, mu_f);
+                    r = hard_row(u - rold, P.flo_m[j], P.fhi_p[j], P.flo[j], P.fhi[j], (cb >> 2) & 3u, mu_f, CD::CH0 + CD::CHS * j + 2);
                     nb |= (r & 3u) << 2; ab |= ((r >> 2) & 3u) << 2; kb |= ((r >> 4) & 3u) << 2;
                     const TpmInterval Mf = TpmInterval::row((r >> 2) & 1u, (r >> 3) & 1u);
                     M.lo += Mf.lo; M.hi += Mf.hi;
                     vfirst[j] = stage_v(u - rold, mu_f, P.irhof[j], (cb >> 2) & 3u, r, P.flo[j], P.fhi[j]) + rold;   // the row is u_0[j] itself against bounds shifted by u_-1[j]
                 }
                 if (k > 0 || j > 0) {
-                    r = hard_row(u - prev, P.clo_m[j], P.chi_p[j], P.clo[j], P.chi[j], (cb >> 4) & 3u, mu_c);
+                    r = hard_row(u - prev, P.clo_m[j], P.chi_p[j], P.clo[j], P.chi[j], (cb >> 4) & 3u, mu_c, CD::CH0 + CD::CHS * j + 4);
                     nb |= (r & 3u) << 4; ab |= ((r >> 2) & 3u) << 4; kb |= ((r >> 4) & 3u) << 4;
                     W.st(base + 2 * j + 1, stage_v(u - prev, mu_c, P.irhoc[j], (cb >> 4) & 3u, r, P.clo[j], P.chi[j]));
                     // violated although both of its scalars are held by other rows: two anchors in one run.  Next resolution lets this row
@@ -398,7 +422,7 @@ BMPC_HD int tpm_forward(const PP& P, WA W, CA C, CB_ CB, CK_ CK, const double* x
                 pend.lo = Y.lo + M.lo + G; pend.hi = Y.hi + M.hi + G;
                 if (k == Nc - 1 && j == nu - 1) {
                     const double mu_q = (tau == TPM_LAST) ? tot : 0.0;
-                    r = hard_row(-u, P.clo_m[0], P.chi_p[0], P.clo[0], P.chi[0], (cb >> 6) & 3u, mu_q);     // bounds of channel nu-1 = those of the chain row ending at channel 0
+                    r = hard_row(-u, P.clo_m[0], P.chi_p[0], P.clo[0], P.chi[0], (cb >> 6) & 3u, mu_q, CD::CH0 + CD::CHS * j + 6);     // bounds of channel nu-1 = those of the chain row ending at channel 0
                     nb |= (r & 3u) << 6; ab |= ((r >> 2) & 3u) << 6; kb |= ((r >> 4) & 3u) << 6;
                     vq = stage_v(-u, mu_q, P.irhoc[0], (cb >> 6) & 3u, r, P.clo[0], P.chi[0]);
                     (void)meet(pend, TpmInterval::row((r >> 2) & 1u, (r >> 3) & 1u));    // 0 = gamma + mu + y - mu_q
@@ -427,6 +451,10 @@ BMPC_HD int tpm_forward(const PP& P, WA W, CA C, CB_ CB, CK_ CK, const double* x
         C(k) = ncode; CB(k) = acode; CK(k) = kcode;
     }
     mumax = mnew;
+    if (EX && (pbad | ibad)) {
+        if (xk_add >= 0) C(xk_add) = (C(xk_add) & ~(3ull << xp_add)) | ((uint64_t)xl_add << xp_add);
+        if (xk_drop >= 0) C(xk_drop) &= ~(3ull << xp_drop);
+    }
     return (int)(pbad != 0u) | ((int)(ibad != 0u) << 1);                // 0: verified
 }
 

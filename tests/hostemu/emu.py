@@ -108,17 +108,18 @@ class EmuSystem:
         ps = f(self.nx, self.nu, self.Np, self.Nc, _p(self.sys), _p(x0), _p(um1), _p(xref), tv, _p(self.codes), mode, _p(self.v), _p(U), max_ref, _p(mm))
         return U, ps
 
-    def tpm_step(self, x0, um1, xref, mode=1, max_ref=8):
+    def tpm_step(self, x0, um1, xref, mode=1, max_ref=8, exchange_from=-1):
         """multi-input Riccati polish (bmpc_tpm.cuh) on the stored working-set codes (mode 0 as stored, 1 shifted one stage, 2 from
-        self.v); returns (U, refinements used); state: self.mcodes, self.v, self.mumax."""
+        self.v); exchange_from >= 0: refinements from that index on update the hard rows by single exchanges (the device's straggler
+        rounds: 0); returns (U, refinements used); state: self.mcodes, self.v, self.mumax."""
         x0 = np.ascontiguousarray(x0, float); um1 = np.ascontiguousarray(um1, float); xref = np.ascontiguousarray(xref, float)
         tv = 0 if xref.ndim == 1 else 1
         if not hasattr(self, "mcodes"):
             self.mcodes = np.zeros(self.Np, np.uint64)
         U = np.ascontiguousarray(getattr(self, "Uplan", np.zeros(self.NU)), float).copy(); mm = np.zeros(1)
         f = self.L.emu_tpm_step
-        f.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
-        ps = f(self.nx, self.nu, self.Np, self.Nc, _p(self.sys), _p(x0), _p(um1), _p(xref), tv, _p(self.mcodes), mode, _p(self.v), _p(U), max_ref, _p(mm))
+        f.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        ps = f(self.nx, self.nu, self.Np, self.Nc, _p(self.sys), _p(x0), _p(um1), _p(xref), tv, _p(self.mcodes), mode, _p(self.v), _p(U), max_ref, _p(mm), exchange_from)
         if ps > 0:
             self.Uplan = U.copy()
         return U, ps

@@ -293,7 +293,7 @@ extern "C" int emu_infeasible(int nx, int nu, int Np, int Nc, const double* sys,
 #include "../../pympc_b200/csrc/bmpc_tpm.cuh"
 template <class S, bool TV>
 static int emu_tpm_run(const double* sys, const double* x0, const double* um1, const double* xref, uint64_t* codes, int mode,
-                       double* v, double* Uout, int max_ref, double* mumax_io) {
+                       double* v, double* Uout, int max_ref, double* mumax_io, int exchange_from) {
     using L = TpmLayout<S>;
     const TpiXref<S, TV> xr{xref};
     BmpcDims d = bmpc_make_dims(S::nx, S::nu, S::Np, S::Nc); BmpcSysOff o = bmpc_make_off(d);
@@ -316,7 +316,10 @@ static int emu_tpm_run(const double* sys, const double* x0, const double* um1, c
     int used = 0;
     for (int r = 0; r < max_ref; r++) {
         tpm_backward<S>(*P, W, C, xr, um1);
-        const int fl = tpm_forward<S>(*P, W, C, CB, CK, x0, um1, mumax, vfirst, vq, [&](int k, int j, double u) { U[k * S::nu + j] = u; });
+        auto outu = [&](int k, int j, double u) { U[k * S::nu + j] = u; };
+        const bool ex = exchange_from >= 0 && r >= exchange_from;
+        const int fl = ex ? tpm_forward<S, true>(*P, W, C, CB, CK, x0, um1, mumax, vfirst, vq, outu)
+                          : tpm_forward<S, false>(*P, W, C, CB, CK, x0, um1, mumax, vfirst, vq, outu);
         if (fl == 0) { used = r + 1; break; }
     }
     if (used > 0) {
@@ -334,8 +337,8 @@ static int emu_tpm_run(const double* sys, const double* x0, const double* um1, c
 }
 
 extern "C" int emu_tpm_step(int nx, int nu, int Np, int Nc, const double* sys, const double* x0, const double* um1, const double* xref,
-                            int xref_mode, uint64_t* codes, int mode, double* v, double* Uout, int max_ref, double* mumax_io) {
-#define EMU_TPM_ARGS sys, x0, um1, xref, codes, mode, v, Uout, max_ref, mumax_io
+                            int xref_mode, uint64_t* codes, int mode, double* v, double* Uout, int max_ref, double* mumax_io, int exchange_from) {
+#define EMU_TPM_ARGS sys, x0, um1, xref, codes, mode, v, Uout, max_ref, mumax_io, exchange_from
 #define EMU_TPM_SHAPE(a, b, c, e) \
     if (nx == a && nu == b && Np == c && Nc == e) \
         return xref_mode ? emu_tpm_run<TpiShape<a, b, c, e>, true>(EMU_TPM_ARGS) : emu_tpm_run<TpiShape<a, b, c, e>, false>(EMU_TPM_ARGS);

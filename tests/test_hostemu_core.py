@@ -334,6 +334,42 @@ def test_tpm_polish_random_mimo_transients_vs_team_path():
     assert ok >= 0.7 * tot, (ok, tot)
 
 
+def test_tpm_exchange_mode_finishes_the_stragglers():
+    """the straggler rounds of the multi-input fast path (bmpc.cu::enqueue_round: ADMM chunk from the previous v*, then the polish from
+    the iterate) in exchange mode (tpm_forward<S, true>: hard rows change by single exchanges): the warm MIMO solves whose first
+    attempt (all-at-once updates from the shifted sets, 12 refinements) cycled all verify within 12 refinements of the first
+    straggler round (all-at-once capped at 4, round 2's policy: about half), and a verified plan is the team path's exact answer"""
+    cfg = mimo(); rng = np.random.default_rng(4)
+    done = {"x": 0, "a": 0}; n = 0
+    for b in range(16):
+        E = EmuSystem(cfg); x = 0.3 * rng.standard_normal(8); um1 = np.zeros(4)
+        for t in range(9):
+            if t == 0:
+                Ut, st, *_ = E.solve(x, um1, cfg["xref"]); assert st == 1
+                U, ps = E.tpm_step(x, um1, cfg["xref"], mode=2, max_ref=2); assert ps > 0
+            else:
+                E.mcodes, E.Uplan = codes.copy(), plan.copy(); vprev = E.v.copy()
+                U, ps = E.tpm_step(x, um1, cfg["xref"], mode=1, max_ref=12)
+                if ps <= 0:
+                    n += 1
+                    E.v = vprev.copy(); E.x = plan.copy(); E.cold = 0
+                    Ut, st, *_ = E.solve(x, um1, cfg["xref"]); assert st == 1
+                    for key, cap, xf in (("a", 4, -1), ("x", 12, 0)):
+                        E.v = vprev.copy(); E.x = plan.copy(); E.cold = 0; E.lvl = 2
+                        E.admm_only(x, um1, cfg["xref"], 100)
+                        U2, ps2 = E.tpm_step(x, um1, cfg["xref"], mode=2, max_ref=cap, exchange_from=xf)
+                        if ps2 > 0:
+                            done[key] += 1
+                            assert np.max(np.abs(U2 - Ut)) < 1e-7, (b, t, key)
+                    E.v = vprev.copy(); E.x = plan.copy(); E.cold = 0
+                    Ut, st, *_ = E.solve(x, um1, cfg["xref"]); assert st == 1
+                    U, ps = E.tpm_step(x, um1, cfg["xref"], mode=2, max_ref=4); assert ps > 0
+            codes, plan = E.mcodes.copy(), U.copy()
+            x = cfg["Ad"] @ x + cfg["Bd"] @ U[:4]; um1 = U[:4].copy()
+    assert n >= 5, n                                    # the workload does produce stragglers
+    assert done["x"] >= 0.95 * n and done["x"] > done["a"], (done, n)
+
+
 def test_tpm_polish_variants_vs_oracle():
     """input bounds, Nc < Np (held stages), soft state rows and a full Qu on a MIMO shape; time-varying reference on a small
     two-input system: verified answers equal the exact solver's on the oracle-assembled QP"""
