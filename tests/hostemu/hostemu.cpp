@@ -60,8 +60,9 @@ int emu_solve(int nx, int nu, int Np, int Nc, const double* sys, const double* x
             for (int i = 0; i < d.mc; i++) v[i] = zz[i] + murow[i] / rhov[i];
             break;
         }
-        // the device policy for unverified candidates (bmpc_warm_from_candidate / early exit), mirrored here
-        if (!getenv("EMU_NOWARM") && ps == 0 && bmpc_admm_stalled(res, total) && (getenv("EMU_ALWAYS") || bmpc_candidate_usable(t, d, o, sys, um1, zz, murow))) bmpc_warm_from_candidate(t, d, o, sys, zz, murow, U, x, v, lvl);
+        // the device policy for unverified candidates (early exit; bmpc_warm_from_candidate only with EMU_WARM = the solver option
+        // candidate_warm, off by default on the device too), mirrored here
+        if (getenv("EMU_WARM") && ps == 0 && bmpc_admm_stalled(res, total) && (getenv("EMU_ALWAYS") || bmpc_candidate_usable(t, d, o, sys, um1, zz, murow))) bmpc_warm_from_candidate(t, d, o, sys, zz, murow, U, x, v, lvl);
         if (!getenv("EMU_NOTIGHT") && bmpc_residuals_tight(res, total)) { status = 2; for (int a = 0; a < d.NU; a++) Uout[a] = xt[a]; break; }
         psteps += bmpc_polish_steps(pdas_steps, round - 1);
         chunk = total < 25 ? 25 - total : total;   // 10, 15, 25, 50, 100, ...
