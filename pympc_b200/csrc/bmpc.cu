@@ -1681,8 +1681,10 @@ static int enqueue_round(bmpc_handle* h) {
         // multi-input fast-path shapes: the Riccati polish (a refinement costs about one ADMM iteration of this shape) instead of
         // the Schur-form one, which takes over for the instances that are still open after 200 iterations (any working set)
         else if (h->cfg.polish && h->tpm_kind && st.total + st.chunk <= 200)           // (also the first attempt of a cold start: working sets from the iterate)
-            // (first attempt of a cold solve: all-at-once updates, tpm_cold_cap; every straggler round: single exchanges)
-            g_tpm_table[h->tpm_kind - 1].launch(h, st.list, st.count, 2, (st.cold && st.round == 0) ? h->tpm_cold_cap : h->tpm_round_cap, 0, st.nxt, (st.cold && st.round == 0) ? 0 : 1);
+            // (first attempt of a cold solve: all-at-once updates; every straggler round: single exchanges — with the cold cap in a
+            // cold solve, whose iterate is still rough: host study on 45 cold stragglers: cap 24 finishes all of them in their first
+            // straggler round, cap 12 needs two or three)
+            g_tpm_table[h->tpm_kind - 1].launch(h, st.list, st.count, 2, st.cold ? h->tpm_cold_cap : h->tpm_round_cap, 0, st.nxt, (st.cold && st.round == 0) ? 0 : 1);
         else if (h->cfg.polish) launch_polish(h, st.list, st.count, st.nxt, cnt);
         else { k_check_converged<<<(st.count + 255) / 256, 256, 0, h->stream>>>(h->I, st.list, st.count, h->cfg.eps_abs, h->cfg.eps_rel, st.nxt, cnt); h->stats.launches++; }
     }
