@@ -370,6 +370,19 @@ def test_tpm_exchange_mode_finishes_the_stragglers():
     assert done["x"] >= 0.95 * n and done["x"] > done["a"], (done, n)
 
 
+def test_multi_input_round_loop_policy_in_emulation():
+    """the multi-input fast path's round loop as bmpc.cu::enqueue_round runs it (tools/mimo_flow_study.py mirrors chunks, caps and
+    modes): cold solves finish within two rounds, warm transient solves within the first launch plus ONE straggler round, nothing
+    falls through to the Schur-form polish (round 2's measured policy: five rounds for a cold solve, up to three straggler rounds)"""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    from mimo_flow_study import run
+    r = run(40, 3)
+    assert r["fallthrough"] == 0
+    assert len(r["cold_rounds"]) <= 3 and r["cold_rounds"][1] >= 36, r           # [_, in one round, in two]
+    assert len(r["warm_rounds"]) <= 3 and r["warm_rounds"][1] >= 0.8 * r["warm_rounds"].sum(), r
+
+
 def test_tpm_polish_variants_vs_oracle():
     """input bounds, Nc < Np (held stages), soft state rows and a full Qu on a MIMO shape; time-varying reference on a small
     two-input system: verified answers equal the exact solver's on the oracle-assembled QP"""
