@@ -279,6 +279,10 @@ def test_states_far_outside_the_soft_box_still_verify(eps_feas, scale, max_fail)
         if st == 1:
             Q = QPData(**c); z, y, r = solve_exact(Q.P, Q.q, Q.A, Q.l, Q.u); ref = z[Q.NX:Q.NX + Q.NU]
             assert np.max(np.abs(U - ref)) < 1e-6 * (1 + np.max(np.abs(ref))), (i, st)
+            if i % 4 == 0:                              # ... and the algorithmically independent exact solver (least-distance form, NNLS)
+                from oracle.ldp import solve_mpc
+                ref2 = solve_mpc(Q)
+                assert np.max(np.abs(U - ref2)) < 1e-6 * (1 + np.max(np.abs(ref2))), (i, "ldp")
     assert tally[-2] <= max_fail * n and tally[1] >= 0.9 * n, tally
 
 
