@@ -1,7 +1,8 @@
 """Host-emulation study of the slow soft-row regime: random small systems, x0 up to `scale` x OUTSIDE the
 soft state box, large eps_feas.  Runs the generic (team) core of the device code compiled for the host (tests/hostemu) and
 tallies verified (1) / solved-unpolished (2) / max-iter (-2) plus the distance of every answer from the oracle's exact
-minimiser.  Usage: python tools/soft_row_study.py [n_systems] [eps_feas] [scale]"""
+minimiser.  Usage: python tools/soft_row_study.py [n_systems] [eps_feas] [scale] [nx,nu,Np]
+(shape: random small shapes by default; "4,1,20" = pendulum-size problems, polish capacity as on the device)"""
 import os
 import sys
 import time
@@ -28,16 +29,23 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 150
     eps_feas = float(sys.argv[2]) if len(sys.argv) > 2 else 1e5
     scale = float(sys.argv[3]) if len(sys.argv) > 3 else 2.5
+    shape = tuple(int(v) for v in sys.argv[4].split(",")) if len(sys.argv) > 4 else None
     rng = np.random.default_rng(2024)
     tally = {1: 0, 2: 0, -2: 0}; err2 = []; errf = []; its = []
     t0 = time.time()
     for i in range(n):
-        nx, nu, Np = int(rng.integers(2, 5)), int(rng.integers(1, 3)), int(rng.integers(4, 10))
+        nx, nu, Np = shape if shape else (int(rng.integers(2, 5)), int(rng.integers(1, 3)), int(rng.integers(4, 10)))
         c = random_system(rng, nx, nu, Np, None, eps_feas)
         c["x0"] = rng.uniform(scale * c["xmin"], scale * c["xmax"]); c["xref"] = 0.5 * rng.standard_normal(nx); c["uminus1"] = np.zeros(nu)
         E = EmuSystem(c)
-        U, st, it, ps, res = E.solve(c["x0"], c["uminus1"], c["xref"], rmax=E.mc, pdas_steps=int(os.environ.get("PDAS", 10)))
-        Q = QPData(**c); z, y, r = solve_exact(Q.P, Q.q, Q.A, Q.l, Q.u); ref = z[Q.NX:Q.NX + Q.NU]
+        U, st, it, ps, res = E.solve(c["x0"], c["uminus1"], c["xref"], rmax=min(E.mc, 128), pdas_steps=int(os.environ.get("PDAS", 10)),
+                                      first_iters=50 if shape else 10)
+        Q = QPData(**c)
+        try:
+            z, y, r = solve_exact(Q.P, Q.q, Q.A, Q.l, Q.u); ref = z[Q.NX:Q.NX + Q.NU]
+        except RuntimeError:                    # the ADMM -> active-set oracle cannot certify some of the stiffest QPs: the independent exact solver takes over
+            from oracle.ldp import solve_mpc
+            ref = solve_mpc(Q)
         e = np.max(np.abs(U - ref)) / (1 + np.max(np.abs(ref)))
         tally[st if st in tally else -2] += 1; its.append(it)
         if st == 1:
