@@ -2,7 +2,8 @@
 soft state box, large eps_feas.  Runs the generic (team) core of the device code compiled for the host (tests/hostemu) and
 tallies verified (1) / solved-unpolished (2) / max-iter (-2) plus the distance of every answer from the oracle's exact
 minimiser.  Usage: python tools/soft_row_study.py [n_systems] [eps_feas] [scale] [nx,nu,Np]
-(shape: random small shapes by default; "4,1,20" = pendulum-size problems, polish capacity as on the device)"""
+(shape: random small shapes by default; "4,1,20" = pendulum-size problems, polish capacity as on the device).  With OSQP=1 in the
+environment the oracle's OSQP restatement (the reference's own solver path, eps 1e-3, max_iter 4000) runs on the same QPs."""
 import os
 import sys
 import time
@@ -31,7 +32,7 @@ def main():
     scale = float(sys.argv[3]) if len(sys.argv) > 3 else 2.5
     shape = tuple(int(v) for v in sys.argv[4].split(",")) if len(sys.argv) > 4 else None
     rng = np.random.default_rng(2024)
-    tally = {1: 0, 2: 0, -2: 0}; err2 = []; errf = []; its = []
+    tally = {1: 0, 2: 0, -2: 0}; err2 = []; errf = []; its = []; osqp_rows = []
     t0 = time.time()
     for i in range(n):
         nx, nu, Np = shape if shape else (int(rng.integers(2, 5)), int(rng.integers(1, 3)), int(rng.integers(4, 10)))
@@ -47,6 +48,12 @@ def main():
             from oracle.ldp import solve_mpc
             ref = solve_mpc(Q)
         e = np.max(np.abs(U - ref)) / (1 + np.max(np.abs(ref)))
+        if os.environ.get("OSQP"):
+            import scipy.sparse as sp
+            from oracle import osqp_port
+            S = osqp_port.OSQP(); S.setup(sp.csc_matrix(Q.P), Q.q, sp.csc_matrix(Q.A), Q.l, Q.u, warm_start=True, verbose=False, eps_abs=1e-3, eps_rel=1e-3)
+            ro = S.solve()
+            osqp_rows.append((ro.info.status_val, ro.info.iter, np.max(np.abs(ro.x[Q.NX:Q.NX + Q.NU] - ref)) / (1 + np.max(np.abs(ref)))))
         tally[st if st in tally else -2] += 1; its.append(it)
         if st == 1:
             assert e < 1e-6, (i, e)
@@ -54,6 +61,10 @@ def main():
             err2.append(e)
         else:
             errf.append(e)
+    if osqp_rows:
+        st = [r[0] for r in osqp_rows]; ok = [r for r in osqp_rows if r[0] == 1]
+        print(f"OSQP restatement on the same QPs: solved {len(ok)}, max-iter {sum(1 for v in st if v == -2)}, other {sum(1 for v in st if v not in (1, -2))};"
+              f" mean iters {np.mean([r[1] for r in osqp_rows]):.0f}; relative error of its 'solved' answers median {np.median([r[2] for r in ok]):.1e} max {max(r[2] for r in ok):.1e}")
     print(f"n={n} eps_feas={eps_feas:g} scale={scale}: verified {tally[1]}, solved-unpolished {tally[2]}, max-iter {tally[-2]};"
           f" mean iters {np.mean(its):.0f}; status-2 err max {max(err2, default=0):.2e} median {np.median(err2) if err2 else 0:.2e};"
           f" failed err max {max(errf, default=0):.2e}  [{time.time() - t0:.0f} s]")
