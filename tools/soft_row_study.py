@@ -41,12 +41,12 @@ def main():
         E = EmuSystem(c)
         U, st, it, ps, res = E.solve(c["x0"], c["uminus1"], c["xref"], rmax=min(E.mc, 128), pdas_steps=int(os.environ.get("PDAS", 10)),
                                       first_iters=50 if shape else 10)
-        Q = QPData(**c)
+        Q = QPData(**c); tol = 1e-6
         try:
             z, y, r = solve_exact(Q.P, Q.q, Q.A, Q.l, Q.u); ref = z[Q.NX:Q.NX + Q.NU]
         except RuntimeError:                    # the ADMM -> active-set oracle cannot certify some of the stiffest QPs: the independent exact solver takes over
             from oracle.ldp import solve_mpc
-            ref = solve_mpc(Q)
+            ref = solve_mpc(Q); tol = 1e-4      # (to NNLS accuracy)
         e = np.max(np.abs(U - ref)) / (1 + np.max(np.abs(ref)))
         if os.environ.get("OSQP"):
             import scipy.sparse as sp
@@ -56,7 +56,7 @@ def main():
             osqp_rows.append((ro.info.status_val, ro.info.iter, np.max(np.abs(ro.x[Q.NX:Q.NX + Q.NU] - ref)) / (1 + np.max(np.abs(ref)))))
         tally[st if st in tally else -2] += 1; its.append(it)
         if st == 1:
-            assert e < 1e-6, (i, e)
+            assert e < tol, (i, e)
         elif st == 2:
             err2.append(e)
         else:
